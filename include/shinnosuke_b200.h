@@ -1,0 +1,195 @@
+/*
+ * shinnosuke_b200 — C ABI of the B200-native training hot path.
+ *
+ * The reference (E1eveNn/shinnosuke) is pure Python + NumPy and has no FFI; the
+ * "interface each entry point replaces" is therefore the NumPy code of the
+ * reference method cited next to it (paths relative to the reference tree).
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a non-zero code otherwise; the
+ *     message is available from sn_last_error() (thread local).  Nothing throws
+ *     or aborts.
+ *   - all work is asynchronous on the caller supplied stream (a cudaStream_t
+ *     passed as void*; NULL = the legacy default stream).  No hidden host sync.
+ *   - device tensors are plain pointers to float (fp32) unless stated.
+ *   - activation maps are NHWC on the device ("pixel rows x channel columns"):
+ *     x[n][h][w][c].  Convolution filters are [F][kh][kw][C] ("KRSC"), so the
+ *     contraction index is ordered (u, v, c).  Dense layers are the H=W=kh=kw=1
+ *     case: X[batch][n_in], W[n_out][n_in].  sn_nchw_to_nhwc / sn_nhwc_to_nchw
+ *     convert at the API boundary, where the reference's NCHW order is visible.
+ *   - "accumulate" arguments: 0 = overwrite the destination, 1 = add into it
+ *     (the reference's  `grads += ...`).
+ */
+#ifndef SHINNOSUKE_B200_H
+#define SHINNOSUKE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SN_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SN_API __attribute__((visibility("default")))
+#else
+#define SN_API
+#endif
+
+/* error codes (CUDA runtime errors are returned as their positive cudaError_t) */
+#define SN_OK                 0
+#define SN_ERR_INVALID_ARG   -1
+#define SN_ERR_UNSUPPORTED   -2
+#define SN_ERR_NO_DEVICE     -3
+
+/* activation fused into a forward epilogue (utils/Activator.py) */
+#define SN_ACT_LINEAR 0
+#define SN_ACT_RELU   1
+
+/* arithmetic tier of the contraction kernels */
+#define SN_PREC_FP32 0   /* CUDA-core FFMA, fp32 operands and accumulators (1e-5 tier)      */
+#define SN_PREC_TF32 1   /* tcgen05.mma kind::tf32, fp32 storage, fp32 TMEM accumulators    */
+#define SN_PREC_BF16 2   /* tcgen05.mma kind::f16 on bf16 copies of the operands            */
+
+/* max-pool backward semantics (layers/Convolution.py:266-269) */
+#define SN_POOL_TIE_SPLIT    0   /* 'reshape' mode: ties share the gradient equally         */
+#define SN_POOL_FIRST_ARGMAX 1   /* 'im2col'  mode: first maximum in (u,v) order wins       */
+
+/* ---------------------------------------------------------------- runtime */
+SN_API int         sn_abi_version(void);
+SN_API const char *sn_last_error(void);
+SN_API int sn_device_count(int *count);
+SN_API int sn_set_device(int device);
+SN_API int sn_device_props(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *global_mem);
+SN_API int sn_malloc(void **ptr, size_t bytes);
+SN_API int sn_free(void *ptr);
+SN_API int sn_malloc_host(void **ptr, size_t bytes);          /* pinned */
+SN_API int sn_free_host(void *ptr);
+SN_API int sn_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+SN_API int sn_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+SN_API int sn_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+SN_API int sn_memset(void *dst, int byte, size_t bytes, void *stream);
+SN_API int sn_stream_create(void **stream);
+SN_API int sn_stream_destroy(void *stream);
+SN_API int sn_stream_sync(void *stream);
+/* CUDA-event timing on the launching stream (bench.py's per-kernel clock) */
+SN_API int sn_event_create(void **event);
+SN_API int sn_event_destroy(void *event);
+SN_API int sn_event_record(void *event, void *stream);
+SN_API int sn_event_elapsed_ms(void *start, void *stop, float *ms);   /* synchronises on `stop` */
+/* number of kernels this library launched since the last reset (bench "gpu_launches") */
+SN_API long long sn_launch_count(void);
+SN_API void      sn_launch_count_reset(void);
+
+/* ----------------------------------------------------------------- layout */
+/* API-boundary transposes between the reference's NCHW and the device's NHWC. */
+SN_API int sn_nchw_to_nhwc(const float *src, float *dst, int N, int C, int H, int W, void *stream);
+SN_API int sn_nhwc_to_nchw(const float *src, float *dst, int N, int C, int H, int W, int accumulate, void *stream);
+SN_API int sn_cast_f64_to_f32(const double *src, float *dst, long long n, void *stream);
+SN_API int sn_cast_f32_to_f64(const float *src, double *dst, long long n, void *stream);
+SN_API int sn_axpy(float alpha, const float *x, float *y, long long n, void *stream);     /* y += alpha*x */
+
+/* ---------------------------------------------------------------- Conv2D */
+/* Conv2D.forward, layers/Convolution.py:131-161 (true zero padding):
+ *   y[n,i,j,f] = act(b[f] + sum_{u,v,c} w[f,u,v,c] * x[n, i*s+u-ph, j*s+v-pw, c])
+ * With act == SN_ACT_RELU negative pre-activations are stored as -0.0f so the
+ * backward mask "pre-activation < 0" (utils/Activator.py:25) survives in y. */
+SN_API int sn_conv2d_fprop(const float *x, const float *w, const float *bias, float *y,
+                    int N, int C, int H, int W, int F, int kh, int kw,
+                    int stride, int pad_h, int pad_w, int act, int precision, void *stream);
+/* Conv2D.backward dX, layers/Convolution.py:199-202 + utils/ConvCol.py:24-42 (col2im-free) */
+SN_API int sn_conv2d_dgrad(const float *dy, const float *w, float *dx,
+                    int N, int C, int H, int W, int F, int kh, int kw,
+                    int stride, int pad_h, int pad_w, int accumulate, int precision, void *stream);
+/* Conv2D.backward dW (+= dYr . cols^T, :197) and db (+= sum dY, :192); db may be NULL */
+SN_API int sn_conv2d_wgrad(const float *x, const float *dy, float *dw, float *db,
+                    int N, int C, int H, int W, int F, int kh, int kw,
+                    int stride, int pad_h, int pad_w, int accumulate, int precision, void *stream);
+/* Relu._backward, utils/Activator.py:24-28: dy[i] = 0 where the pre-activation was < 0
+ * (sign bit of y, see sn_conv2d_fprop); in place. */
+SN_API int sn_relu_bwd(float *dy, const float *y, long long n, void *stream);
+/* stand-alone Relu forward with the -0.0f convention (Activation layer, layers/Activation.py) */
+SN_API int sn_relu_fwd(const float *x, float *y, long long n, void *stream);
+
+/* ZeroPadding2D.forward / backward, layers/Convolution.py:232-251: y (N,H+2ph,W+2pw,C) is x
+ * surrounded by zeros; backward crops dy to dx (N,H,W,C). */
+SN_API int sn_pad2d_fwd(const float *x, float *y, int N, int H, int W, int C, int pad_h, int pad_w, void *stream);
+SN_API int sn_pad2d_bwd(const float *dy, float *dx, int N, int H, int W, int C, int pad_h, int pad_w,
+                 int accumulate, void *stream);
+
+/* ----------------------------------------------------------------- Dense */
+/* Dense.forward, layers/FC.py:124-134: y = act(x . W + b), x[M][K], w[Nout][K] */
+SN_API int sn_dense_fprop(const float *x, const float *w, const float *bias, float *y,
+                   int M, int K, int Nout, int act, int precision, void *stream);
+/* Dense.backward dX = dZ . W^T, layers/FC.py:147 */
+SN_API int sn_dense_dgrad(const float *dy, const float *w, float *dx,
+                   int M, int K, int Nout, int accumulate, int precision, void *stream);
+/* Dense.backward dW += X^T . dZ (:144), db += sum_rows dZ (:146) */
+SN_API int sn_dense_wgrad(const float *x, const float *dy, float *dw, float *db,
+                   int M, int K, int Nout, int accumulate, int precision, void *stream);
+
+/* ---------------------------------------------------------- MaxPooling2D */
+/* MaxPooling2D.forward, layers/Convolution.py:287-324.  x NHWC (N,H,W,C) -> y (N,oh,ow,C),
+ * oh = (H-pool)/stride+1 (floor).  `code` (one byte per output element, order (n,i,j,c)) is
+ *   SN_POOL_TIE_SPLIT   : bit (u*pool+v) set where x == max   (pool*pool <= 8; for 9..16 window
+ *                         elements the code is TWO bytes per output element, little endian)
+ *   SN_POOL_FIRST_ARGMAX: u*pool+v of the first maximum               (== the reference's
+ *                         int64 argmax_index, same order, one byte each)
+ * code may be NULL when not training. */
+SN_API int sn_maxpool2d_fwd(const float *x, float *y, uint8_t *code,
+                     int N, int H, int W, int C, int pool, int stride, int mode, void *stream);
+/* MaxPooling2D.backward, layers/Convolution.py:326-362 */
+SN_API int sn_maxpool2d_bwd(const float *dy, const uint8_t *code, float *dx,
+                     int N, int H, int W, int C, int pool, int stride, int mode,
+                     int accumulate, void *stream);
+
+/* --------------------------------------------------------------- Flatten */
+/* Flatten.forward/backward, layers/FC.py:39-58: the reference flattens NCHW in (c,i,j)
+ * order; on the device that is the NHWC -> NCHW transpose (and back). */
+/* (sn_nhwc_to_nchw / sn_nchw_to_nhwc above) */
+
+/* ---------------------------------------------------- BatchNormalization */
+/* BatchNormalization.forward (training), layers/Normalization.py:116-128, channel = last
+ * (fastest) index of x[rows][C].  Writes y, save_mean[C], save_invstd[C] and updates the moving
+ * statistics in place.  scratch: >= 2*C doubles, zeroed by the call. */
+SN_API int sn_batchnorm_fwd_train(const float *x, const float *gamma, const float *beta, float *y,
+                           float *save_mean, float *save_invstd, float *moving_mean, float *moving_var,
+                           double *scratch, long long rows, int C, float eps, float momentum, void *stream);
+/* inference branch, :130-132 */
+SN_API int sn_batchnorm_fwd_infer(const float *x, const float *gamma, const float *beta, float *y,
+                           const float *moving_mean, const float *moving_var,
+                           long long rows, int C, float eps, void *stream);
+/* BatchNormalization.backward, :186-230. dgamma/dbeta accumulate (+=).  If relu_y != NULL the
+ * ReLU mask of the producing layer (sign bit of relu_y == x) is applied to dx on the way out. */
+SN_API int sn_batchnorm_bwd(const float *dy, const float *x, const float *gamma,
+                     const float *save_mean, const float *save_invstd,
+                     float *dx, float *dgamma, float *dbeta, double *scratch,
+                     long long rows, int C, int accumulate_dx, int mask_relu, void *stream);
+
+/* ------------------------------------------------------------------ loss */
+/* Softmax._forward, utils/Activator.py:108-110 (row-wise; the reference's global shift cancels) */
+SN_API int sn_softmax_fwd(const float *logits, float *probs, int rows, int classes, void *stream);
+/* SparseCategoricalCrossEntropy.backward / calc_loss / calc_acc, utils/Objectives.py:72-91
+ * (one-hot labels).  dlogits = (probs - onehot)/denom_rows, where denom_rows is the reference's
+ * N = prod(shape[:-1]) — the GLOBAL minibatch rows when `rows` is one data-parallel shard of it
+ * (pass 0 for denom_rows == rows);  metrics[0] += sum(-y log p), metrics[1] += #(argmax p ==
+ * argmax y).  metrics must be zeroed by the caller; may be NULL. */
+SN_API int sn_scce_bwd(const float *probs, const float *onehot, float *dlogits, float *metrics,
+                int rows, int classes, int denom_rows, void *stream);
+
+/* ------------------------------------------------------------- optimizer */
+/* StochasticGradientDescent.update, utils/Optimizers.py:29-32 over a flat arena:
+ *   w -= lr * grad_scale * g ;  g = 0 */
+SN_API int sn_sgd_update(float *w, float *g, long long n, float lr, float grad_scale, void *stream);
+/* Momentum.update, utils/Optimizers.py:46-55:  v = rho*v + (1-rho)*g ; w -= lr*v ; g kept.
+ * If gstep != NULL (data-parallel): g += grad_scale*gstep ; gstep = 0 first. */
+SN_API int sn_momentum_update(float *w, float *g, float *v, float *gstep, long long n,
+                       float lr, float rho, float grad_scale, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHINNOSUKE_B200_H */

@@ -1,0 +1,87 @@
+"""ctypes binding of libshinnosuke_b200.so (the C ABI declared in include/shinnosuke_b200.h).
+
+There is no CPU fallback: if the library cannot be loaded every compute entry point raises."""
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'shinnosuke_b200.h')
+LIB_PATH = os.path.join(_HERE, 'lib', 'libshinnosuke_b200.so')
+
+_CTYPES = {
+    'int': ctypes.c_int, 'long long': ctypes.c_longlong, 'float': ctypes.c_float,
+    'size_t': ctypes.c_size_t, 'void': None,
+}
+
+
+def parse_header(path=HEADER):
+    """Returns {name: (restype, [argtypes])} for every SN_API prototype in the header."""
+    text = open(path).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r'SN_API\s+([\w\s\*]+?)\s*\b(sn_\w+)\s*\(([^)]*)\)\s*;', text):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        if '*' in ret:
+            restype = ctypes.c_char_p if 'char' in ret else ctypes.c_void_p
+        else:
+            restype = _CTYPES[ret]
+        argtypes = []
+        if args and args != 'void':
+            for a in args.split(','):
+                a = a.strip()
+                if '*' in a:
+                    argtypes.append(ctypes.c_void_p)
+                else:
+                    base = re.sub(r'\b(const|unsigned)\b', '', a).strip()
+                    base = ' '.join(base.split()[:-1])      # drop the parameter name
+                    argtypes.append(_CTYPES[base])
+        protos[name] = (restype, argtypes)
+    return protos
+
+
+class ShinnosukeLibError(RuntimeError):
+    pass
+
+
+class _Lib(object):
+    def __init__(self):
+        self._dll = None
+        self._err = None
+
+    def load(self):
+        if self._dll is not None:
+            return self._dll
+        if not os.path.exists(LIB_PATH):
+            raise ShinnosukeLibError(
+                'shinnosuke_b200: CUDA library %s is missing; build it with '
+                '`python -c "import __graft_entry__ as g; g.build()"` (there is no CPU fallback)' % LIB_PATH)
+        dll = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in parse_header().items():
+            fn = getattr(dll, name)          # AttributeError if the .so is stale
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if dll.sn_abi_version() != 1:
+            raise ShinnosukeLibError('libshinnosuke_b200.so ABI version mismatch')
+        self._dll = dll
+        return dll
+
+    def __getattr__(self, name):
+        dll = self.load()
+        fn = getattr(dll, name)
+        if fn.restype is ctypes.c_int and name not in ('sn_abi_version',):
+            def checked(*args, _fn=fn, _name=name):
+                rc = _fn(*args)
+                if rc != 0:
+                    raise ShinnosukeLibError('%s failed (%d): %s' % (_name, rc, dll.sn_last_error().decode()))
+            setattr(self, name, checked)
+            return checked
+        setattr(self, name, fn)
+        return fn
+
+
+lib = _Lib()
+
+ACT = {'linear': 0, 'relu': 1}
+PRECISION = {'fp32': 0, 'tf32': 1, 'bf16': 2}
+POOL_MODE = {'reshape': 0, 'im2col': 1}

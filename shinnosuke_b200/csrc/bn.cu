@@ -1,0 +1,226 @@
+// BatchNormalization over x[rows][C] with the channel as the fastest index
+// (layers/Normalization.py:93-230).  HBM-bound: one reduction pass + one elementwise pass per
+// direction; per-channel sums are accumulated in float64 (B200 has full-rate-enough FP64 for a
+// memory-bound reduction) so the 1e-5 tier holds even when |mean| >> std.
+#include "common.cuh"
+using namespace sn;
+
+// blockDim = (32, 8): threadIdx.x walks 4 channels each (float4), threadIdx.y walks rows.
+// grid = (ceil(C/128), row_chunks).  Accumulates sum a and sum b per channel into scratch
+// (doubles): STATS: a = x, b = x*x.   BWD: a = dy, b = dy * xhat.
+template <bool BWD>
+__global__ void bn_reduce_kernel(const float *__restrict__ x, const float *__restrict__ dy,
+                                 const float *__restrict__ mean, const float *__restrict__ invstd,
+                                 double *__restrict__ scratch, long long rows, int C) {
+    const int c0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+    if (c0 < C) {
+        float mu[4] = {0, 0, 0, 0}, is[4] = {1, 1, 1, 1};
+        if (BWD) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (c0 + k < C) { mu[k] = mean[c0 + k]; is[k] = invstd[c0 + k]; }
+        }
+        const bool vec = (C % 4 == 0);
+        for (long long r = blockIdx.y * (long long)blockDim.y + threadIdx.y; r < rows; r += (long long)gridDim.y * blockDim.y) {
+            float xv[4], gv[4];
+            if (vec) {
+                float4 t = ldg4(x + r * C + c0);
+                xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+                if (BWD) { float4 g = ldg4(dy + r * C + c0); gv[0] = g.x; gv[1] = g.y; gv[2] = g.z; gv[3] = g.w; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    xv[k] = (c0 + k < C) ? x[r * C + c0 + k] : 0.f;
+                    if (BWD) gv[k] = (c0 + k < C) ? dy[r * C + c0 + k] : 0.f;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (BWD) { a[k] += (double)gv[k]; b[k] += (double)gv[k] * (double)((xv[k] - mu[k]) * is[k]); }
+                else     { a[k] += (double)xv[k]; b[k] += (double)xv[k] * (double)xv[k]; }
+            }
+        }
+    }
+    __shared__ double sa[8][32][4], sb[8][32][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sa[threadIdx.y][threadIdx.x][k] = a[k]; sb[threadIdx.y][threadIdx.x][k] = b[k]; }
+    __syncthreads();
+    if (threadIdx.y == 0 && c0 < C) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (c0 + k >= C) break;
+            double ta = 0, tb = 0;
+            for (int yy = 0; yy < 8; ++yy) { ta += sa[yy][threadIdx.x][k]; tb += sb[yy][threadIdx.x][k]; }
+            atomicAdd(scratch + c0 + k, ta);
+            atomicAdd(scratch + C + c0 + k, tb);
+        }
+    }
+}
+
+// y = gamma*(x-mean)*invstd + beta; block 0 also publishes mean / invstd / moving statistics.
+__global__ void bn_apply_train_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
+                                      const float *__restrict__ beta, float *__restrict__ y,
+                                      float *__restrict__ save_mean, float *__restrict__ save_invstd,
+                                      float *__restrict__ moving_mean, float *__restrict__ moving_var,
+                                      const double *__restrict__ scratch, long long rows, int C, float eps, float momentum) {
+    extern __shared__ float sm[];            // scale[C], shift[C]
+    float *scale = sm, *shift = sm + C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double m = scratch[c] / (double)rows;
+        double var = scratch[C + c] / (double)rows - m * m;
+        if (var < 0) var = 0;
+        double is = 1.0 / sqrt(var + (double)eps);
+        float g = gamma[c];
+        scale[c] = (float)(g * is);
+        shift[c] = (float)(beta[c] - g * is * m);
+        if (blockIdx.x == 0) {
+            save_mean[c] = (float)m;
+            save_invstd[c] = (float)is;
+            moving_mean[c] = momentum * moving_mean[c] + (1.f - momentum) * (float)m;
+            moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * (float)var;
+        }
+    }
+    __syncthreads();
+    const long long total = rows * C;
+    if (C % 4 == 0) {
+        const int C4 = C >> 2;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (total >> 2); i += (long long)gridDim.x * blockDim.x) {
+            int c = (int)(i % C4) * 4;
+            float4 v = ldg4(x + 4 * i);
+            v.x = v.x * scale[c] + shift[c]; v.y = v.y * scale[c + 1] + shift[c + 1];
+            v.z = v.z * scale[c + 2] + shift[c + 2]; v.w = v.w * scale[c + 3] + shift[c + 3];
+            reinterpret_cast<float4 *>(y)[i] = v;
+        }
+    } else {
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            int c = (int)(i % C);
+            y[i] = x[i] * scale[c] + shift[c];
+        }
+    }
+}
+
+__global__ void bn_apply_infer_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
+                                      const float *__restrict__ beta, float *__restrict__ y,
+                                      const float *__restrict__ moving_mean, const float *__restrict__ moving_var,
+                                      long long rows, int C, float eps) {
+    extern __shared__ float sm[];
+    float *scale = sm, *shift = sm + C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = gamma[c] / sqrtf(moving_var[c] + eps);
+        scale[c] = s;
+        shift[c] = beta[c] - moving_mean[c] * s;
+    }
+    __syncthreads();
+    const long long total = rows * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        y[i] = x[i] * scale[c] + shift[c];
+    }
+}
+
+// dx = gamma*invstd*(dy - mean(dy) - xhat*mean(dy*xhat)); block 0 adds dgamma / dbeta.
+template <bool ACC, bool MASK>
+__global__ void bn_bwd_apply_kernel(const float *__restrict__ dy, const float *__restrict__ x,
+                                    const float *__restrict__ gamma, const float *__restrict__ mean,
+                                    const float *__restrict__ invstd, float *__restrict__ dx,
+                                    float *__restrict__ dgamma, float *__restrict__ dbeta,
+                                    const double *__restrict__ scratch, long long rows, int C) {
+    extern __shared__ float sm[];            // k1[C] = gamma*invstd, k2[C] = mean(dy), k3[C] = mean(dy*xhat), mu[C], is[C]
+    float *k1 = sm, *k2 = sm + C, *k3 = sm + 2 * C, *mu = sm + 3 * C, *is = sm + 4 * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double sdy = scratch[c], sdyx = scratch[C + c];
+        k1[c] = gamma[c] * invstd[c];
+        k2[c] = (float)(sdy / (double)rows);
+        k3[c] = (float)(sdyx / (double)rows);
+        mu[c] = mean[c];
+        is[c] = invstd[c];
+        if (blockIdx.x == 0) {
+            if (dbeta) dbeta[c] += (float)sdy;
+            if (dgamma) dgamma[c] += (float)sdyx;
+        }
+    }
+    __syncthreads();
+    const long long total = rows * C;
+    if (C % 4 == 0) {
+        const int C4 = C >> 2;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (total >> 2); i += (long long)gridDim.x * blockDim.x) {
+            int c = (int)(i % C4) * 4;
+            float4 g = ldg4(dy + 4 * i), xv = ldg4(x + 4 * i), o;
+            float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {g.x, g.y, g.z, g.w}, r[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float xh = (xs[k] - mu[c + k]) * is[c + k];
+                r[k] = k1[c + k] * (gs[k] - k2[c + k] - xh * k3[c + k]);
+                if (MASK && relu_blocked(xs[k])) r[k] = 0.f;
+            }
+            if (ACC) { float4 p = reinterpret_cast<float4 *>(dx)[i]; r[0] += p.x; r[1] += p.y; r[2] += p.z; r[3] += p.w; }
+            o.x = r[0]; o.y = r[1]; o.z = r[2]; o.w = r[3];
+            reinterpret_cast<float4 *>(dx)[i] = o;
+        }
+    } else {
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            int c = (int)(i % C);
+            float xh = (x[i] - mu[c]) * is[c];
+            float r = k1[c] * (dy[i] - k2[c] - xh * k3[c]);
+            if (MASK && relu_blocked(x[i])) r = 0.f;
+            dx[i] = ACC ? dx[i] + r : r;
+        }
+    }
+}
+
+static dim3 reduce_grid(long long rows, int C) {
+    int gx = (C + 127) / 128;
+    long long chunks = (rows + 7) / 8;
+    long long want = (long long)num_sms() * 8 / gx;       // ~8 CTAs per SM in total
+    if (want < 1) want = 1;
+    int gy = (int)(chunks < want ? chunks : want);
+    if (gy < 1) gy = 1;
+    return dim3(gx, gy);
+}
+
+extern "C" {
+
+int sn_batchnorm_fwd_train(const float *x, const float *gamma, const float *beta, float *y, float *save_mean,
+                           float *save_invstd, float *moving_mean, float *moving_var, double *scratch,
+                           long long rows, int C, float eps, float momentum, void *stream) {
+    SN_REQUIRE(x && gamma && beta && y && save_mean && save_invstd && moving_mean && moving_var && scratch, "null tensor");
+    SN_REQUIRE(rows > 0 && C > 0 && C <= 4096, "bad shape (C must be <= 4096)");
+    cudaStream_t st = as_stream(stream);
+    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
+    bn_reduce_kernel<false><<<reduce_grid(rows, C), dim3(32, 8), 0, st>>>(x, nullptr, nullptr, nullptr, scratch, rows, C);
+    int e = after_launch("bn_reduce_kernel");
+    if (e) return e;
+    bn_apply_train_kernel<<<grid_for((rows * C + 3) / 4, 256), 256, 2 * C * sizeof(float), st>>>(
+        x, gamma, beta, y, save_mean, save_invstd, moving_mean, moving_var, scratch, rows, C, eps, momentum);
+    return after_launch("bn_apply_train_kernel");
+}
+
+int sn_batchnorm_fwd_infer(const float *x, const float *gamma, const float *beta, float *y, const float *moving_mean,
+                           const float *moving_var, long long rows, int C, float eps, void *stream) {
+    SN_REQUIRE(x && gamma && beta && y && moving_mean && moving_var, "null tensor");
+    SN_REQUIRE(rows > 0 && C > 0 && C <= 4096, "bad shape (C must be <= 4096)");
+    bn_apply_infer_kernel<<<grid_for(rows * C, 256), 256, 2 * C * sizeof(float), as_stream(stream)>>>(
+        x, gamma, beta, y, moving_mean, moving_var, rows, C, eps);
+    return after_launch("bn_apply_infer_kernel");
+}
+
+int sn_batchnorm_bwd(const float *dy, const float *x, const float *gamma, const float *save_mean,
+                     const float *save_invstd, float *dx, float *dgamma, float *dbeta, double *scratch,
+                     long long rows, int C, int accumulate_dx, int mask_relu, void *stream) {
+    SN_REQUIRE(dy && x && gamma && save_mean && save_invstd && dx && scratch, "null tensor");
+    SN_REQUIRE(rows > 0 && C > 0 && C <= 2048, "bad shape (C must be <= 2048)");
+    cudaStream_t st = as_stream(stream);
+    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
+    bn_reduce_kernel<true><<<reduce_grid(rows, C), dim3(32, 8), 0, st>>>(x, dy, save_mean, save_invstd, scratch, rows, C);
+    int e = after_launch("bn_reduce_kernel");
+    if (e) return e;
+    int grid = grid_for((rows * C + 3) / 4, 256);
+    size_t smem = 5 * C * sizeof(float);
+#define SN_LAUNCH(A, M) bn_bwd_apply_kernel<A, M><<<grid, 256, smem, st>>>(dy, x, gamma, save_mean, save_invstd, dx, dgamma, dbeta, scratch, rows, C)
+    if (accumulate_dx) { if (mask_relu) SN_LAUNCH(true, true); else SN_LAUNCH(true, false); }
+    else { if (mask_relu) SN_LAUNCH(false, true); else SN_LAUNCH(false, false); }
+#undef SN_LAUNCH
+    return after_launch("bn_bwd_apply_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// Shared helpers for the shinnosuke_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/shinnosuke_b200.h"
+
+namespace sn {
+
+void set_error(const char *fmt, ...);
+extern long long g_launch_count;
+
+inline int check_cuda(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return SN_OK;
+}
+
+// Called after every kernel launch: counts it and surfaces launch-configuration errors.
+inline int after_launch(const char *name) {
+    ++g_launch_count;
+    return check_cuda(cudaPeekAtLastError(), name);
+}
+
+#define SN_REQUIRE(cond, msg)                                   \
+    do {                                                        \
+        if (!(cond)) {                                          \
+            sn::set_error("%s: %s", __func__, msg);             \
+            return SN_ERR_INVALID_ARG;                          \
+        }                                                       \
+    } while (0)
+
+#define SN_CUDA(call)                                           \
+    do {                                                        \
+        int _e = sn::check_cuda((call), #call);                 \
+        if (_e) return _e;                                      \
+    } while (0)
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline int num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+    }
+    return sms;
+}
+
+// grid for a grid-stride elementwise kernel: enough CTAs for `work` items, capped at a
+// multiple of the SM count (148 on B200) so the last wave is full.
+inline int grid_for(long long work, int block, int ctas_per_sm = 8) {
+    long long need = (work + block - 1) / block;
+    long long cap = (long long)num_sms() * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+__device__ __forceinline__ float relu_keep_sign(float z) {
+    // max(0, z) with the sign of a negative pre-activation kept as -0.0f: numerically
+    // zero for every consumer, but "pre-activation < 0" stays recoverable for backward.
+    return z > 0.f ? z : (z < 0.f ? -0.f : 0.f);
+}
+__device__ __forceinline__ bool relu_blocked(float y) { return __float_as_uint(y) == 0x80000000u; }
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+}  // namespace sn

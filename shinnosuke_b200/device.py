@@ -1,0 +1,192 @@
+"""Device buffers for the CUDA path.
+
+PyTorch is used here only as plumbing: its caching allocator owns the HBM, its current stream
+is the stream every C-ABI call is issued on, and ``torch.distributed`` carries the gradient
+all-reduce.  All arithmetic is done by libshinnosuke_b200.so.
+
+A :class:`DeviceTensor` is an fp32 buffer plus the *logical* shape the reference would see and a
+layout tag saying how that logical tensor is stored:
+
+    'flat'    : stored exactly as the logical C-order array
+    'nhwc'    : logical (N, C, H, W)         stored as [N][H][W][C]
+    'krsc'    : logical (F, C, kh, kw)       stored as [F][kh][kw][C]
+    'dense_w' : logical (n_in, n_out)        stored as [n_out][n_in]
+"""
+import ctypes
+
+import numpy as np
+
+from ._lib import lib, ShinnosukeLibError
+
+_torch = None
+
+
+def torch():
+    global _torch
+    if _torch is None:
+        import torch as _t
+        _torch = _t
+    return _torch
+
+
+def require_cuda():
+    t = torch()
+    if not t.cuda.is_available():
+        raise ShinnosukeLibError('shinnosuke_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    lib.load()
+    return t
+
+
+def current_stream():
+    """cudaStream_t of torch's current stream as an int (what the C ABI takes as void*)."""
+    return torch().cuda.current_stream().cuda_stream
+
+
+def empty(n, dtype=None):
+    t = require_cuda()
+    return t.empty(int(n), dtype=dtype or t.float32, device='cuda')
+
+
+def zeros(n, dtype=None):
+    buf = empty(n, dtype)
+    lib.sn_memset(buf.data_ptr(), 0, buf.numel() * buf.element_size(), current_stream())
+    return buf
+
+
+def _to_storage(arr, layout):
+    """logical float64/float32 ndarray -> C-contiguous float32 ndarray in storage order."""
+    a = np.asarray(arr)
+    if layout == 'nhwc':
+        a = a.transpose(0, 2, 3, 1)
+    elif layout == 'krsc':
+        a = a.transpose(0, 2, 3, 1)
+    elif layout == 'dense_w':
+        a = a.T
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _from_storage(a, shape, layout):
+    if layout == 'nhwc':
+        n, c, h, w = shape
+        a = a.reshape(n, h, w, c).transpose(0, 3, 1, 2)
+    elif layout == 'krsc':
+        f, c, kh, kw = shape
+        a = a.reshape(f, kh, kw, c).transpose(0, 3, 1, 2)
+    elif layout == 'dense_w':
+        n_in, n_out = shape
+        a = a.reshape(n_out, n_in).T
+    else:
+        a = a.reshape(shape)
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def layout_for(shape, kind=None):
+    if kind is not None:
+        return kind
+    return 'nhwc' if len(shape) == 4 else 'flat'
+
+
+class DeviceTensor(object):
+    __slots__ = ('buf', 'shape', 'layout', 'ptr')
+
+    def __init__(self, buf, shape, layout='flat'):
+        self.buf = buf
+        self.shape = tuple(int(s) for s in shape)
+        self.layout = layout
+        self.ptr = buf.data_ptr()
+        assert buf.numel() == int(np.prod(self.shape)), (buf.numel(), self.shape)
+
+    # ---- construction -------------------------------------------------
+    @classmethod
+    def empty(cls, shape, layout=None):
+        shape = tuple(int(s) for s in shape)
+        return cls(empty(int(np.prod(shape))), shape, layout_for(shape, layout))
+
+    @classmethod
+    def zeros(cls, shape, layout=None):
+        shape = tuple(int(s) for s in shape)
+        return cls(zeros(int(np.prod(shape))), shape, layout_for(shape, layout))
+
+    @classmethod
+    def from_numpy(cls, arr, layout=None):
+        arr = np.asarray(arr)
+        layout = layout_for(arr.shape, layout)
+        out = cls.empty(arr.shape, layout)
+        out.set(arr)
+        return out
+
+    def set(self, arr):
+        """Upload a logical-layout host array (any float dtype) into this buffer."""
+        arr = np.asarray(arr)
+        assert tuple(arr.shape) == self.shape, (arr.shape, self.shape)
+        host = _to_storage(arr, self.layout)
+        lib.sn_memcpy_h2d(self.ptr, host.ctypes.data, host.nbytes, current_stream())
+        lib.sn_stream_sync(current_stream())        # `host` is pageable and about to be freed
+
+    # ---- host views ----------------------------------------------------
+    def numpy(self):
+        """float64 array in the reference's layout (synchronises)."""
+        host = np.empty(self.buf.numel(), dtype=np.float32)
+        lib.sn_memcpy_d2h(host.ctypes.data, self.ptr, host.nbytes, current_stream())
+        lib.sn_stream_sync(current_stream())
+        return _from_storage(host, self.shape, self.layout)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+    @property
+    def size(self):
+        return self.buf.numel()
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    def view(self, shape, layout='flat'):
+        return DeviceTensor(self.buf, shape, layout)
+
+    def zero_(self):
+        lib.sn_memset(self.ptr, 0, self.buf.numel() * 4, current_stream())
+        return self
+
+    def copy_from(self, other):
+        assert other.buf.numel() == self.buf.numel()
+        lib.sn_memcpy_d2d(self.ptr, other.ptr, self.buf.numel() * 4, current_stream())
+        return self
+
+    def add_(self, other, alpha=1.0):
+        lib.sn_axpy(float(alpha), other.ptr, self.ptr, self.buf.numel(), current_stream())
+        return self
+
+    def __repr__(self):
+        return 'DeviceTensor(shape=%s, layout=%s)' % (self.shape, self.layout)
+
+
+def as_device(x, layout=None):
+    """Accepts a DeviceTensor or anything array-like in the reference's layout."""
+    if isinstance(x, DeviceTensor):
+        return x
+    return DeviceTensor.from_numpy(np.asarray(x), layout)
+
+
+class Arena(object):
+    """One flat fp32 allocation holding every trainable parameter (and a twin for the
+    gradients), so the optimizer is ONE kernel and the data-parallel all-reduce ONE call."""
+    ALIGN = 32          # floats (128 bytes): TMA global addresses want >= 16-byte alignment
+
+    def __init__(self, sizes, extra=0):
+        offs, total = [], 0
+        for s in sizes:
+            offs.append(total)
+            total += (int(s) + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.offsets, self.param_floats = offs, total
+        self.total = total + extra
+        self.w = zeros(self.total)
+        self.g = zeros(self.total)
+        self.v = None       # momentum velocity, allocated on demand
+        self.gstep = None   # data-parallel Momentum: per-step gradients
+
+    def slice(self, which, i, size):
+        buf = getattr(self, which)
+        return buf[self.offsets[i]:self.offsets[i] + int(size)]

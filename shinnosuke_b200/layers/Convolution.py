@@ -1,0 +1,233 @@
+"""Conv2D / ZeroPadding2D / MaxPooling2D on the device.
+
+Operator interface of the reference's layers/Convolution.py (Conv2D :8-205, ZeroPadding2D
+:209-251, MaxPooling2D :254-362); the arithmetic is done by the sm_100a kernels behind
+sn_conv2d_* / sn_maxpool2d_* (include/shinnosuke_b200.h).  Maps are NHWC on the device and the
+filters [F][kh][kw][C]; np.asarray() of any tensor gives the reference's NCHW view.
+"""
+import numpy as np
+
+from .Base import Layer, Variable
+from ..device import DeviceTensor, current_stream
+from .._lib import lib, ACT, PRECISION, POOL_MODE
+from ..utils.Initializers import get_initializer
+from ..utils.Activator import get_activator
+
+
+class Conv2D(Layer):
+    def __init__(self, filter_nums, filter_size, input_shape=None, stride=1, padding='VALID', activation='linear',
+                 initializer='Normal'):
+        self.filter_nums = filter_nums
+        self.filter_size = filter_size
+        self.stride = stride
+        self.padding = padding
+        self.activator = get_activator(activation)
+        self.initializer = get_initializer(initializer)
+        super(Conv2D, self).__init__(input_shape=input_shape)
+
+    # shape inference + parameter creation: layers/Convolution.py:20-57 / :59-90
+    def _infer(self, input_shape):
+        assert len(input_shape) == 4
+        batch_nums, n_C_prev, n_H_prev, n_W_prev = input_shape
+        filter_h, filter_w = self.filter_size
+        assert isinstance(self.padding, str)
+        self.padding = self.padding.upper()
+        s = self.stride
+        if self.padding == 'SAME':
+            pad_h = (s * (n_H_prev - 1) - n_H_prev + filter_h) // 2
+            pad_w = (s * (n_W_prev - 1) - n_W_prev + filter_w) // 2
+            n_H, n_W = n_H_prev, n_W_prev
+            true_h = (n_H_prev + 2 * pad_h - filter_h) // s + 1
+            true_w = (n_W_prev + 2 * pad_w - filter_w) // s + 1
+            if (true_h, true_w) != (n_H, n_W):
+                # the reference declares oh = H for SAME but its pad formula only delivers it for
+                # odd filters at stride 1; anything else has no well-defined result there either
+                raise ValueError('padding=SAME needs an odd filter and stride 1 (got %r, stride %d)'
+                                 % (self.filter_size, s))
+            self.pad_size = (pad_h, pad_w)
+        elif self.padding == 'VALID':
+            n_H = (n_H_prev - filter_h) // s + 1
+            n_W = (n_W_prev - filter_w) // s + 1
+            self.pad_size = (0, 0)
+        else:
+            raise TypeError('Unknown padding type!plz inputs SAME or VALID')
+        self.output_shape = (batch_nums, self.filter_nums, n_H, n_W)
+        # RNG order of the reference: initializer(W.shape) then randn(1, F) (:52-53)
+        W = Variable(self.initializer((self.filter_nums, n_C_prev, filter_h, filter_w)), name='conv_w', layout='krsc')
+        b = Variable(np.random.randn(1, self.filter_nums), name='conv_b', layout='flat')
+        self.variables.append(W)
+        self.variables.append(b)
+
+    def connect(self, prev_layer):
+        if prev_layer is None:
+            assert self.input_shape is not None
+            input_shape = self.input_shape
+        else:
+            input_shape = prev_layer.output_shape
+            Layer.connect(self, prev_layer)
+        self._infer(input_shape)
+
+    def __call__(self, prev_layer):
+        super(Conv2D, self).__call__(prev_layer)
+        self._infer(self.input_shape)
+        return self
+
+    def _act_code(self):
+        name = self.activator.__class__.__name__.lower()
+        if name not in ACT:
+            raise NotImplementedError('Conv2D on the device fuses linear/relu epilogues only (got %s)' % name)
+        return ACT[name]
+
+    def forward(self, is_training=True):
+        """layers/Convolution.py:131-161 with true zero padding (SAME policy)."""
+        W, b = self._param_ptrs()
+        x = self.input_tensor
+        N, C, H, Wd = x.shape
+        self.input_shape = x.shape
+        F = self.filter_nums
+        kh, kw = self.filter_size
+        oh, ow = self.output_shape[2:]
+        y = self._buf('out', (N, F, oh, ow), 'nhwc')
+        lib.sn_conv2d_fprop(x.ptr, W.output_tensor.ptr, b.output_tensor.ptr, y.ptr, N, C, H, Wd, F, kh, kw,
+                            self.stride, self.pad_size[0], self.pad_size[1], self._act_code(),
+                            PRECISION[self.precision], current_stream())
+        self.output_tensor = y
+        super(Conv2D, self).forward(is_training)
+
+    def backward(self):
+        """layers/Convolution.py:182-205."""
+        W, b = self.variables
+        x, y, g = self.input_tensor, self.output_tensor, self.grads
+        N, C, H, Wd = x.shape
+        F = self.filter_nums
+        kh, kw = self.filter_size
+        st = current_stream()
+        prec = PRECISION[self.precision]
+        if self._act_code() == ACT['relu'] and not self._grads_premasked:
+            lib.sn_relu_bwd(g.ptr, y.ptr, g.size, st)
+        geom = (N, C, H, Wd, F, kh, kw, self.stride, self.pad_size[0], self.pad_size[1])
+        if W.require_grads or b.require_grads:
+            lib.sn_conv2d_wgrad(x.ptr, g.ptr, W.grads.ptr, b.grads.ptr if b.require_grads else None,
+                                *geom, 1, prec, st)
+        for layer in self.inbounds:
+            self._push_grad(layer, lambda dst, acc: lib.sn_conv2d_dgrad(
+                g.ptr, W.output_tensor.ptr, dst.ptr, *geom, acc, prec, st))
+
+
+class ZeroPadding2D(Layer):
+    """layers/Convolution.py:209-251.  The reference needs this layer to get a correct SAME
+    convolution.  Deviation: the reference marks it require_grads=False,
+    which makes a Conv2D behind it hand over its raw output gradient (:204) so that the crop in
+    :248 only type-checks when nothing upstream needs a gradient; here the layer carries the
+    true dX through (crop of the padded gradient)."""
+
+    def __init__(self, pad_size):
+        assert len(pad_size) == 2
+        self.pad_h, self.pad_w = pad_size
+        super(ZeroPadding2D, self).__init__()
+
+    def connect(self, prev_layer):
+        (batch_nums, C, H, W) = prev_layer.output_shape
+        self.output_shape = (batch_nums, C, H + 2 * self.pad_h, W + 2 * self.pad_w)
+        Layer.connect(self, prev_layer)
+
+    def __call__(self, prev_layer):
+        super(ZeroPadding2D, self).__call__(prev_layer)
+        (batch_nums, C, H, W) = self.input_shape
+        self.output_shape = (batch_nums, C, H + 2 * self.pad_h, W + 2 * self.pad_w)
+        return self
+
+    def forward(self, is_training=True):
+        x = self.input_tensor
+        N, C, H, W = x.shape
+        y = self._buf('out', (N, C, H + 2 * self.pad_h, W + 2 * self.pad_w), 'nhwc')
+        lib.sn_pad2d_fwd(x.ptr, y.ptr, N, H, W, C, self.pad_h, self.pad_w, current_stream())
+        self.output_tensor = y
+        super(ZeroPadding2D, self).forward(is_training)
+
+    def backward(self):
+        if not self._grads_written:
+            return
+        g = self.grads
+        N, C, Hp, Wp = g.shape
+        st = current_stream()
+        for layer in self.inbounds:
+            self._push_grad(layer, lambda dst, acc: lib.sn_pad2d_bwd(
+                g.ptr, dst.ptr, N, Hp - 2 * self.pad_h, Wp - 2 * self.pad_w, C, self.pad_h, self.pad_w, acc, st))
+
+
+class MaxPooling2D(Layer):
+    def __init__(self, pool_size, stride=None):
+        assert len(pool_size) == 2
+        assert pool_size[0] == pool_size[1]
+        self.pool_size = pool_size
+        self.stride = pool_size[0] if stride is None else stride
+        super(MaxPooling2D, self).__init__()
+
+    def _infer(self, input_shape):
+        batch_nums, n_C, n_H_prev, n_W_prev = input_shape
+        pool_h, pool_w = self.pool_size
+        assert pool_w == pool_h
+        # layers/Convolution.py:266-269
+        self.mode = 'reshape' if pool_h == pool_w == self.stride else 'im2col'
+        n_H, n_W = (n_H_prev - pool_h) // self.stride + 1, (n_W_prev - pool_w) // self.stride + 1
+        self.output_shape = (batch_nums, n_C, n_H, n_W)
+
+    def connect(self, prev_layer):
+        self._infer(prev_layer.output_shape)
+        Layer.connect(self, prev_layer)
+
+    def __call__(self, prev_layer):
+        super(MaxPooling2D, self).__call__(prev_layer)
+        self._infer(self.input_shape)
+        return self
+
+    def forward(self, is_training=True):
+        """layers/Convolution.py:287-324.  'reshape' mode keeps a tie bit-mask, 'im2col' mode the
+        first-argmax index; both are one byte per output element in (n,i,j,c) order.  On maps
+        whose side is not a multiple of the pool the reference's 'reshape' mode raises; here it
+        floors like the layer's own declared output_shape."""
+        x = self.input_tensor
+        N, C, H, W = x.shape
+        self.input_shape = x.shape
+        p, s = self.pool_size[0], self.stride
+        oh, ow = (H - p) // s + 1, (W - p) // s + 1
+        y = self._buf('out', (N, C, oh, ow), 'nhwc')
+        code = None
+        if is_training:
+            wide = 2 if (self.mode == 'reshape' and p * p > 8) else 1
+            key = ('code', N * C * oh * ow * wide)
+            code = self._bufs.get(key)
+            if code is None:
+                from ..device import empty, torch
+                code = empty(key[1], torch().uint8)
+                self._bufs[key] = code
+        lib.sn_maxpool2d_fwd(x.ptr, y.ptr, code.data_ptr() if code is not None else None, N, H, W, C, p, s,
+                             POOL_MODE[self.mode], current_stream())
+        self._code, self._code_mode = code, self.mode
+        self.output_tensor = y
+        super(MaxPooling2D, self).forward(is_training)
+
+    @property
+    def argmax_index(self):
+        """The reference's int64 argmax vector (layers/Convolution.py:303,309), order (n,i,j,c)."""
+        if self._code_mode != 'im2col':
+            raise AttributeError('argmax_index exists in im2col mode only')
+        from ..device import torch
+        torch().cuda.current_stream().synchronize()
+        return self._code.cpu().numpy().astype(np.int64)
+
+    def backward(self):
+        """layers/Convolution.py:326-362."""
+        g = self.grads
+        N, C, H, W = self.input_shape
+        p, s = self.pool_size[0], self.stride
+        st = current_stream()
+        for layer in self.inbounds:
+            self._push_grad(layer, lambda dst, acc: lib.sn_maxpool2d_bwd(
+                g.ptr, self._code.data_ptr(), dst.ptr, N, H, W, C, p, s, POOL_MODE[self._code_mode], acc, st))
+
+    def __getstate__(self):
+        d = Layer.__getstate__(self)
+        d.pop('_code', None)
+        return d

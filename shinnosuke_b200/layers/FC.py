@@ -1,0 +1,149 @@
+"""Flatten / Dense on the device (reference: layers/FC.py, Flatten :10-58, Dense :64-153)."""
+import numpy as np
+
+from .Base import Layer, Variable
+from ..device import current_stream
+from .._lib import lib, ACT, PRECISION
+from ..utils.Initializers import get_initializer
+from ..utils.Activator import get_activator
+from ..utils.Regularizers import get_regularizer
+
+
+class Flatten(Layer):
+    def __init__(self, out_dim=2):
+        if out_dim < 1:
+            raise ValueError('out_dim must be > 0')
+        if out_dim != 2:
+            raise NotImplementedError('the device path flattens to (N, features) only (out_dim=2)')
+        self.out_dim = out_dim
+        super(Flatten, self).__init__()
+
+    def _infer(self, input_shape):
+        flatten_shape = np.prod(np.array(input_shape[self.out_dim - 1:])).tolist()
+        self.output_shape = tuple(input_shape[:self.out_dim - 1]) + (flatten_shape,)
+
+    def connect(self, prev_layer):
+        assert len(prev_layer.output_shape) >= 3
+        self._infer(prev_layer.output_shape)
+        Layer.connect(self, prev_layer)
+
+    def __call__(self, layers):
+        super(Flatten, self).__call__(layers)
+        self._infer(self.input_shape)
+        return self
+
+    def forward(self, is_training=True):
+        """layers/FC.py:39-48.  The reference flattens NCHW in (c,i,j) order, which fixes the row
+        order of the next Dense's weights; the device map is NHWC, so this is a real transpose."""
+        x = self.input_tensor
+        self.input_shape = x.shape
+        if x.ndim == 4:
+            N, C, H, W = x.shape
+            y = self._buf('out', (N, C * H * W), 'flat')
+            lib.sn_nhwc_to_nchw(x.ptr, y.ptr, N, C, H, W, 0, current_stream())
+        else:
+            y = x.view((x.shape[0], int(np.prod(x.shape[1:]))))
+        self.output_tensor = y
+        super(Flatten, self).forward(is_training)
+
+    def backward(self):
+        """layers/FC.py:53-58."""
+        g = self.grads
+        st = current_stream()
+        for layer in self.inbounds:
+            if len(self.input_shape) == 4:
+                N, C, H, W = self.input_shape
+
+                def writer(dst, acc):
+                    if acc:
+                        tmp = self._buf('bwd_tmp', self.input_shape, 'nhwc')
+                        lib.sn_nchw_to_nhwc(g.ptr, tmp.ptr, N, C, H, W, st)
+                        dst.add_(tmp)
+                    else:
+                        lib.sn_nchw_to_nhwc(g.ptr, dst.ptr, N, C, H, W, st)
+            else:
+                def writer(dst, acc):
+                    dst.add_(g) if acc else dst.copy_from(g)
+            self._push_grad(layer, writer)
+
+
+class Dense(Layer):
+    def __init__(self, n_out, n_in=None, initializer='Normal', activation='linear', kernel_regularizer=None, **kwargs):
+        self.n_out = n_out
+        self.n_in = n_in
+        self.initializer = get_initializer(initializer)
+        self.activator = get_activator(activation)
+        self.kernel_regularizer = get_regularizer(kernel_regularizer)   # stored, never applied (as in the reference)
+        super(Dense, self).__init__(**kwargs)
+
+    def connect(self, prev_layer):
+        if prev_layer is None:
+            if self.n_in is None and self.input_shape is None:
+                raise ValueError('must specify n_in or input_shape')
+            elif self.input_shape is None:
+                self.input_shape = (None, self.n_in)
+        else:
+            self.input_shape = prev_layer.output_shape
+        self._initial_params()
+        Layer.connect(self, prev_layer)
+        self.output_shape = self.compute_output_shape()
+
+    def __call__(self, prev_layer):
+        super(Dense, self).__call__(prev_layer)
+        self._initial_params()
+        self.output_shape = self.compute_output_shape()
+        return self
+
+    def _initial_params(self):
+        """layers/FC.py:105-113: W (n_in, n_out) from the initializer, b zeros (1, n_out).  On the
+        device W is stored [n_out][n_in] so Dense is the 1x1 case of the convolution kernels."""
+        n_in = self.input_shape[-1]
+        W = Variable(self.initializer((n_in, self.n_out)), name='dense_w', layout='dense_w')
+        b = Variable(np.zeros((1, self.n_out)), name='dense_b', layout='flat')
+        self.variables.append(W)
+        self.variables.append(b)
+
+    def compute_output_shape(self):
+        return tuple(self.input_shape[:-1]) + (self.n_out,)
+
+    def _act_name(self):
+        name = self.activator.__class__.__name__.lower()
+        if name not in ('linear', 'relu', 'softmax'):
+            raise NotImplementedError('Dense on the device supports linear/relu/softmax (got %s)' % name)
+        return name
+
+    def forward(self, is_training=True):
+        """layers/FC.py:124-134."""
+        W, b = self._param_ptrs()
+        x = self.input_tensor
+        if x.ndim != 2:
+            raise NotImplementedError('Dense on the device takes (N, features) inputs')
+        M, K = x.shape
+        act = self._act_name()
+        st = current_stream()
+        z = self._buf('out', (M, self.n_out), 'flat')
+        lib.sn_dense_fprop(x.ptr, W.output_tensor.ptr, b.output_tensor.ptr, z.ptr, M, K, self.n_out,
+                           ACT['relu'] if act == 'relu' else ACT['linear'], PRECISION[self.precision], st)
+        if act == 'softmax':
+            p = self._buf('probs', (M, self.n_out), 'flat')
+            lib.sn_softmax_fwd(z.ptr, p.ptr, M, self.n_out, st)
+            self.output_tensor = p
+        else:
+            self.output_tensor = z
+        super(Dense, self).forward(is_training)
+
+    def backward(self):
+        """layers/FC.py:140-153 (Softmax backward is the identity, utils/Activator.py:121-124)."""
+        W, b = self.variables
+        x, g = self.input_tensor, self.grads
+        M, K = x.shape
+        st = current_stream()
+        prec = PRECISION[self.precision]
+        if self._act_name() == 'relu' and not self._grads_premasked:
+            lib.sn_relu_bwd(g.ptr, self.output_tensor.ptr, g.size, st)
+        if W.require_grads or b.require_grads:
+            lib.sn_dense_wgrad(x.ptr, g.ptr, W.grads.ptr, b.grads.ptr if b.require_grads else None,
+                               M, K, self.n_out, 1, prec, st)
+        for layer in self.inbounds:
+            self._push_grad(layer, lambda dst, acc: lib.sn_dense_dgrad(
+                g.ptr, W.output_tensor.ptr, dst.ptr, M, K, self.n_out, acc, prec, st))

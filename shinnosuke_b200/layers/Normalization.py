@@ -1,0 +1,110 @@
+"""BatchNormalization on the device (reference: layers/Normalization.py:8-230)."""
+import numpy as np
+
+from .Base import Layer, Variable
+from ..device import DeviceTensor, current_stream, zeros, torch
+from .._lib import lib
+from ..utils.Initializers import get_initializer
+
+
+class BatchNormalization(Layer):
+    def __init__(self, epsilon=1e-6, momentum=0.99, axis=1, gamma_initializer='ones', beta_initializer='zeros',
+                 moving_mean_initializer='zeros', moving_variance_initializer='ones'):
+        self.epsilon = epsilon
+        self.axis = axis
+        self.momentum = momentum
+        self.gamma_initializer = get_initializer(gamma_initializer)
+        self.beta_initializer = get_initializer(beta_initializer)
+        self.moving_mean_initializer = get_initializer(moving_mean_initializer)
+        self.moving_variance_initializer = get_initializer(moving_variance_initializer)
+        super(BatchNormalization, self).__init__()
+
+    def _infer(self, shape):
+        assert len(shape) >= 2
+        if len(shape) not in (2, 4) or self.axis not in (1, -1 if len(shape) == 2 else 1):
+            raise NotImplementedError('device BatchNormalization normalises axis 1 of (N,C,H,W) or (N,M) inputs')
+        n_in = shape[1]
+        self.variables.append(Variable(self.gamma_initializer(n_in), name='bn_gamma'))
+        self.variables.append(Variable(self.beta_initializer(n_in), name='bn_beta'))
+        self._mm_host = np.asarray(self.moving_mean_initializer(n_in), dtype=np.float64)
+        self._mv_host = np.asarray(self.moving_variance_initializer(n_in), dtype=np.float64)
+        self._stats = None
+        self.output_shape = shape
+
+    def connect(self, prev_layer):
+        self._infer(prev_layer.output_shape)
+        Layer.connect(self, prev_layer)
+
+    def __call__(self, prev_layer):
+        super(BatchNormalization, self).__call__(prev_layer)
+        self._infer(self.input_shape)
+        return self
+
+    def _device_stats(self, C):
+        if self._stats is None:
+            self._stats = dict(mm=DeviceTensor.from_numpy(self._mm_host), mv=DeviceTensor.from_numpy(self._mv_host),
+                               mean=DeviceTensor.empty((C,)), invstd=DeviceTensor.empty((C,)),
+                               scratch=zeros(2 * C, torch().float64))
+        return self._stats
+
+    @property
+    def moving_mean(self):
+        return self._stats['mm'].numpy() if self._stats is not None else self._mm_host
+
+    @property
+    def moving_variance(self):
+        return self._stats['mv'].numpy() if self._stats is not None else self._mv_host
+
+    def forward(self, is_training=True):
+        """layers/Normalization.py:93-156 (biased variance, eps inside the sqrt)."""
+        gamma, beta = self._param_ptrs()
+        x = self.input_tensor
+        self.input_shape = x.shape
+        C = x.shape[1]
+        rows = x.size // C
+        s = self._device_stats(C)
+        y = self._buf('out', x.shape, x.layout)
+        st = current_stream()
+        if is_training:
+            lib.sn_batchnorm_fwd_train(x.ptr, gamma.output_tensor.ptr, beta.output_tensor.ptr, y.ptr, s['mean'].ptr,
+                                       s['invstd'].ptr, s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows, C,
+                                       float(self.epsilon), float(self.momentum), st)
+        else:
+            lib.sn_batchnorm_fwd_infer(x.ptr, gamma.output_tensor.ptr, beta.output_tensor.ptr, y.ptr, s['mm'].ptr,
+                                       s['mv'].ptr, rows, C, float(self.epsilon), st)
+        self.output_tensor = y
+        super(BatchNormalization, self).forward(is_training)
+
+    def backward(self):
+        """layers/Normalization.py:186-230.  If the single producer is a ReLU-fused layer whose
+        only consumer is this BN, its mask `pre-activation < 0` (utils/Activator.py:25) is applied
+        while dX is written, saving that layer one read-modify-write pass over its gradient."""
+        gamma, beta = self.variables
+        x, g = self.input_tensor, self.grads
+        C = x.shape[1]
+        rows = x.size // C
+        s = self._stats
+        st = current_stream()
+        for layer in self.inbounds:
+            fuse = bool(layer.require_grads and getattr(layer, '_fused_relu', lambda: False)()
+                        and len(layer.outbound_layers) == 1 and not layer._grads_written)
+
+            def writer(dst, acc, fuse=fuse):
+                lib.sn_batchnorm_bwd(g.ptr, x.ptr, gamma.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr, dst.ptr,
+                                     gamma.grads.ptr if gamma.require_grads else None,
+                                     beta.grads.ptr if beta.require_grads else None,
+                                     s['scratch'].data_ptr(), rows, C, acc, 1 if fuse else 0, st)
+            if layer.require_grads:
+                self._push_grad(layer, writer)
+                layer._grads_premasked = fuse
+            else:
+                # parameter gradients are still needed when nothing upstream wants dX
+                tmp = self._buf('dx_unused', x.shape, x.layout)
+                writer(tmp, 0, False)
+
+    def __getstate__(self):
+        if self._stats is not None:
+            self._mm_host, self._mv_host = self._stats['mm'].numpy(), self._stats['mv'].numpy()
+        d = Layer.__getstate__(self)
+        d['_stats'] = None
+        return d

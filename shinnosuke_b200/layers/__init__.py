@@ -1,0 +1,8 @@
+from .Base import *          # noqa: F401,F403
+from .Base import Layer, Variable, Input
+from .Activation import Activation
+from .FC import Flatten, Dense
+from .Convolution import Conv2D, ZeroPadding2D, MaxPooling2D
+from .Normalization import BatchNormalization
+
+name = 'shinnosuke-b200-layers'

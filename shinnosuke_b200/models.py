@@ -1,0 +1,421 @@
+"""Sequential / Model training drivers on the device.
+
+API of the reference's models.py (Sequential :12-266, Model :272-588): compile / fit / predict /
+evaluate / calc_gradients / save / load, `train_loss` / `train_acc` histories.  What changes:
+
+  * compile() takes `precision=` ('fp32' CUDA-core tier, 'tf32' / 'bf16' tensor-core tiers);
+  * the first fit/predict places every trainable Variable in ONE flat fp32 parameter arena with
+    a twin gradient arena, so the optimizer is one fused kernel and — under
+    ``torch.distributed`` (one process per GPU) — the gradient exchange is one NCCL all-reduce;
+  * fit() shards each minibatch across the ranks (contiguous rows); the loss
+    gradient is divided by the GLOBAL row count so the summed shard gradients are exactly the
+    reference's full-batch gradients;
+  * the whole step (forward sweep, loss, backward sweep, all-reduce, update) is captured once
+    per batch shape in a CUDA graph and replayed; the inputs are copied host->device from pinned
+    memory every step and the (loss, acc) pair is copied back every step without blocking.
+"""
+import os
+import pickle
+import time
+
+import numpy as np
+
+from .device import Arena, DeviceTensor, as_device, current_stream, require_cuda, torch, zeros
+from ._lib import lib, PRECISION
+from .layers.Base import Layer, Variable, Input
+from .utils.MiniBatch import batch_permutation, batch_slices
+from .utils.Objectives import get_objective
+from .utils.Optimizers import get_optimizer, Momentum
+
+
+class VariableList(list):
+    """`trainable_variables` with a handle on the arena that backs them."""
+    arena = None
+
+
+def _dist():
+    t = torch()
+    if t.distributed.is_available() and t.distributed.is_initialized():
+        return t.distributed
+    return None
+
+
+class _Trainer(object):
+    """Everything Sequential and Model share once the layer order is known."""
+
+    process_bar_nums = 30
+    process_bar_trained = '='
+    process_bar_untrain = '*'
+
+    def _init_histories(self):
+        self.train_loss = []
+        self.train_acc = []
+        self.valid_loss = []
+        self.valid_acc = []
+        self.precision = 'fp32'
+        self.use_cuda_graph = True
+        self._arena = None
+        self._graphs = {}
+        self._warm = set()
+        self._metrics_out = None
+
+    # ---- to be provided by the subclass ---------------------------------
+    def _forward_order(self):
+        raise NotImplementedError
+
+    def _backward_order(self):
+        raise NotImplementedError
+
+    def _input_layer(self):
+        raise NotImplementedError
+
+    def _output_layer(self):
+        raise NotImplementedError
+
+    # ---- compile ---------------------------------------------------------
+    def _finish_compile(self, optimizer, loss, precision):
+        if precision not in PRECISION:
+            raise ValueError('precision must be one of %s' % sorted(PRECISION))
+        self.precision = precision
+        for layer in self._forward_order():
+            layer.precision = precision
+        self.loss = get_objective(loss)
+        self.optimizer = get_optimizer(optimizer)
+
+    def _materialize(self):
+        """Place all trainable variables in the arena (once)."""
+        if self._arena is not None:
+            return
+        require_cuda()
+        tv = [v for v in self.trainable_variables if isinstance(v, Variable)]
+        arena = Arena([v.size for v in tv], extra=Arena.ALIGN)
+        for i, v in enumerate(tv):
+            v.bind(arena.slice('w', i, v.size), arena.slice('g', i, v.size))
+        self._arena = arena
+        vl = VariableList(tv)
+        vl.arena = arena
+        self.trainable_variables = vl
+        self._metrics_out = zeros(2)
+        dist = _dist()
+        if dist is not None and dist.get_world_size() > 1:
+            # replicas must start from identical weights: rank 0's initial values win
+            dist.broadcast(arena.w, src=0)
+            if isinstance(self.optimizer, Momentum):
+                arena.gstep = zeros(arena.total)
+        lib.sn_stream_sync(current_stream())
+
+    # ---- forward / backward sweeps (models.py:124-129, 82-83, 445-449) -----
+    def _forward_device(self, x_dev, is_training):
+        self._input_layer().input_tensor = x_dev
+        for layer in self._forward_order():
+            layer.forward(is_training=is_training)
+        return self._output_layer().output_tensor
+
+    def predict(self, X, is_training=True):
+        self._materialize()
+        return self._forward_device(self._to_device_input(X), is_training)
+
+    def _to_device_input(self, X):
+        if isinstance(X, DeviceTensor):
+            return X
+        return as_device(np.asarray(X))
+
+    def calc_gradients(self, y_hat, y_true, denom_rows=0, metrics_ptr=None):
+        out = self._output_layer()
+        out._seed_grads(self.loss.backward(y_hat, as_device(y_true), metrics_ptr, denom_rows))
+        for layer in self._backward_order():
+            layer.backward()
+
+    # ---- one training step on device-resident shards ---------------------
+    def _grad_arena_for_step(self):
+        a = self._arena
+        return a.gstep if a.gstep is not None else a.g
+
+    def _step_body(self, x_dev, y_dev, global_rows):
+        """forward, loss, backward, gradient all-reduce, update.  No host sync inside: this is
+        what gets captured in the CUDA graph."""
+        a = self._arena
+        st = current_stream()
+        dist = _dist()
+        world = dist.get_world_size() if dist is not None else 1
+        garena = self._grad_arena_for_step()
+        metrics = garena[a.param_floats:a.param_floats + 2]
+        if a.gstep is not None:
+            # data-parallel Momentum: layers accumulate this step's gradients into gstep
+            for i, v in enumerate(self.trainable_variables):
+                v._grads = DeviceTensor(a.slice('gstep', i, v.size), v.output_shape, v.layout or 'flat')
+        y_hat = self._forward_device(x_dev, True)
+        self.calc_gradients(y_hat, y_dev, denom_rows=global_rows, metrics_ptr=metrics.data_ptr())
+        if world > 1:
+            dist.all_reduce(garena)                         # NCCL sum over NVLink; metrics ride along
+        lib.sn_memcpy_d2d(self._metrics_out.data_ptr(), metrics.data_ptr(), 8, st)
+        self.optimizer.grad_scale = 1.0                     # shards already divide by the global rows
+        self.optimizer.update(self.trainable_variables)
+        # the optimizer touches arena.g[:param_floats] only; clear the metric tail for the next step
+        lib.sn_memset(metrics.data_ptr(), 0, 8, st)
+
+    def _run_step(self, x_dev, y_dev, global_rows):
+        if not self.use_cuda_graph:
+            self._step_body(x_dev, y_dev, global_rows)
+            return
+        key = (x_dev.ptr, y_dev.ptr, x_dev.shape, global_rows)
+        graph = self._graphs.get(key)
+        if graph is None:
+            if key not in self._warm:
+                # first step of this shape runs eagerly: allocates every layer buffer and loads
+                # every kernel, so that nothing but launches happens during capture
+                self._warm.add(key)
+                self._step_body(x_dev, y_dev, global_rows)
+                return
+            t = torch()
+            graph = t.cuda.CUDAGraph()
+            with t.cuda.graph(graph):
+                self._step_body(x_dev, y_dev, global_rows)
+            self._graphs[key] = graph
+        graph.replay()
+
+    # ---- fit (models.py:47-119 / :370-431) --------------------------------
+    def fit(self, X, Y, batch_size=64, epochs=20, shuffle=True, validation_data=None, validation_ratio=0.1,
+            draw_acc_loss=False, draw_save_path=None, verbose=1):
+        if draw_acc_loss:
+            raise NotImplementedError('live matplotlib plotting is out of scope of the device path')
+        t = require_cuda()
+        self._materialize()
+        X = np.asarray(X)
+        Y = np.asarray(Y)
+        if validation_data is None:
+            if 0. < validation_ratio < 1.:
+                split = int(X.shape[0] * validation_ratio)
+                valid_X, valid_Y = X[-split:], Y[-split:]
+                train_X, train_Y = X[:-split], Y[:-split]
+                validation_data = (valid_X, valid_Y)
+            else:
+                train_X, train_Y = X, Y
+        else:
+            valid_X, valid_Y = validation_data
+            train_X, train_Y = X, Y
+
+        dist = _dist()
+        world = dist.get_world_size() if dist is not None else 1
+        rank = dist.get_rank() if dist is not None else 0
+        m = train_X.shape[0]
+        X32 = np.ascontiguousarray(train_X, dtype=np.float32)
+        Y32 = np.ascontiguousarray(train_Y, dtype=np.float32)
+        # float32 pinned staging of the (shuffled) epoch, like get_batches' shuffled copies
+        pin_x = t.empty(train_X.shape, dtype=t.float32).pin_memory()
+        pin_y = t.empty(train_Y.shape, dtype=t.float32).pin_memory()
+        np_px, np_py = pin_x.numpy(), pin_y.numpy()
+        slices = batch_slices(m, batch_size)
+        pin_metrics = t.zeros((len(slices), 2), dtype=t.float32).pin_memory()
+        inp = self._input_layer()
+        st = current_stream()
+        is4d = train_X.ndim == 4 and train_X.shape[1] > 1 and train_X.shape[2] * train_X.shape[3] > 1
+
+        for epoch in range(epochs):
+            perm = batch_permutation(m, epoch, shuffle)
+            if perm is None:
+                np_px[...] = X32
+                np_py[...] = Y32
+            else:
+                np.take(X32, perm, axis=0, out=np_px)
+                np.take(Y32, perm, axis=0, out=np_py)
+            if verbose:
+                print('\033[0;31m Epoch[%d/%d]' % (epoch + 1, epochs))
+            start_time = time.time()
+            rows_done = []
+            for bi, (a, b) in enumerate(slices):
+                rows = b - a
+                # this rank's contiguous shard of the minibatch
+                lo = a + (rows * rank) // world
+                hi = a + (rows * (rank + 1)) // world
+                n_loc = hi - lo
+                shape_x = (n_loc,) + train_X.shape[1:]
+                xs = inp._buf('fit_x', shape_x, 'nhwc' if train_X.ndim == 4 else 'flat')
+                ys = inp._buf('fit_y', (n_loc,) + train_Y.shape[1:], 'flat')
+                if is4d:
+                    stage = inp._buf('fit_x_nchw', shape_x, 'flat')
+                    lib.sn_memcpy_h2d(stage.ptr, pin_x[lo:hi].data_ptr(), n_loc * int(np.prod(train_X.shape[1:])) * 4, st)
+                    lib.sn_nchw_to_nhwc(stage.ptr, xs.ptr, n_loc, shape_x[1], shape_x[2], shape_x[3], st)
+                else:
+                    lib.sn_memcpy_h2d(xs.ptr, pin_x[lo:hi].data_ptr(), n_loc * int(np.prod(train_X.shape[1:])) * 4, st)
+                lib.sn_memcpy_h2d(ys.ptr, pin_y[lo:hi].data_ptr(), n_loc * int(np.prod(train_Y.shape[1:])) * 4, st)
+                self._run_step(xs, ys, rows)
+                lib.sn_memcpy_d2h(pin_metrics[bi].data_ptr(), self._metrics_out.data_ptr(), 8, st)
+                rows_done.append(rows)
+                if validation_data is not None:
+                    valid_acc, valid_loss = self.evaluate(valid_X, valid_Y, batch_size=batch_size)
+                    self.valid_loss.append(valid_loss)
+                    self.valid_acc.append(valid_acc)
+            lib.sn_stream_sync(st)
+            gap = time.time() - start_time
+            mets = pin_metrics.numpy()
+            for bi, rows in enumerate(rows_done):
+                self.train_loss.append(float(mets[bi, 0]) / rows)
+                self.train_acc.append(float(mets[bi, 1]) / rows)
+            if verbose:
+                bar = self.process_bar_trained * (self.process_bar_nums - 1) + '>'
+                msg = '\r{:d}/{:d} [{}] -{:.0f}s -{:.0f}ms/batch -batch_loss: {:.4f} -batch_acc: {:.4f} '.format(
+                    m, m, bar, gap, gap * 1000 / max(1, len(slices)), self.train_loss[-1], self.train_acc[-1])
+                if validation_data is not None:
+                    msg += '-val_loss: {:.4f} -val_acc: {:.4f}'.format(self.valid_loss[-1], self.valid_acc[-1])
+                print(msg)
+
+    # ---- evaluate (models.py:144-171) -------------------------------------
+    def evaluate(self, X, Y, batch_size=None):
+        self._materialize()
+        X, Y = np.asarray(X), np.asarray(Y)
+        if batch_size is not None:
+            assert type(batch_size) is int
+            acc_list, loss_list = [], []
+            for a, b in batch_slices(X.shape[0], batch_size):
+                y_hat = self.predict(X[a:b], is_training=False)
+                loss, acc = self.loss.calc_loss_acc(y_hat, Y[a:b])
+                acc_list.append(acc)
+                loss_list.append(loss)
+            # un-weighted mean of the chunk means, like the reference (:161-162)
+            return sum(acc_list) / len(acc_list), sum(loss_list) / len(loss_list)
+        y_hat = self.predict(X, is_training=False)
+        loss, acc = self.loss.calc_loss_acc(y_hat, Y)
+        return acc, loss
+
+    # ---- save / load (models.py:208-220, 530-543) -------------------------
+    def _sync_to_host(self):
+        for v in self.trainable_variables:
+            if isinstance(v, Variable):
+                v.to_host()
+
+    def _drop_device_state(self):
+        self._arena = None
+        self._graphs = {}
+        self._warm = set()
+        self._metrics_out = None
+        for layer in self._forward_order():
+            layer._bufs = {}
+            for v in layer.variables:
+                if isinstance(v, Variable):
+                    v._dev = None
+                    v._grads = None
+
+
+class Sequential(_Trainer):
+    def __init__(self, layers=None):
+        self.layers = [] if layers is None else layers
+        self._init_histories()
+
+    def add(self, layer):
+        self.layers.append(layer)
+
+    def compile(self, optimizer, loss, precision='fp32'):
+        """models.py:30-43: connect the layers in order (shape inference + host-side parameter
+        creation, same RNG consumption as the reference), collect the trainable variables."""
+        assert self.layers
+        trainable_variables = []
+        next_layer = None
+        for layer in self.layers:
+            layer.connect(next_layer)
+            next_layer = layer
+            for var in layer.variables:
+                if var.require_grads:
+                    trainable_variables.append(var)
+        self.trainable_variables = trainable_variables
+        self._finish_compile(optimizer, loss, precision)
+
+    def _forward_order(self):
+        return self.layers
+
+    def _backward_order(self):
+        return list(reversed(self.layers))
+
+    def _input_layer(self):
+        return self.layers[0]
+
+    def _output_layer(self):
+        return self.layers[-1]
+
+    def pop(self, index=-1):
+        layer = self.layers.pop(index)
+        print('success delete %s layer' % (layer.__class__.__name__))
+
+    def save(self, save_path):
+        self._sync_to_host()
+        with open(save_path + '.pkl', 'wb') as f:
+            pickle.dump([self.layers, self.optimizer, self.loss], f)
+
+    def load(self, model_path):
+        with open(model_path + '.pkl', 'rb') as f:
+            layers, optimizer, loss = pickle.load(f)
+        self.layers, self.optimizer, self.loss = layers, optimizer, loss
+        self.trainable_variables = [v for l in layers for v in l.variables if v.require_grads]
+        self._drop_device_state()
+        if layers:
+            self.precision = layers[0].precision
+
+
+class Model(_Trainer):
+    def __init__(self, inputs=None, outputs=None):
+        self.inputs = inputs
+        self.outputs = outputs
+        self._init_histories()
+
+    @staticmethod
+    def _kahn(start, edges_out, edges_in):
+        """Kahn's algorithm from `start` following `edges_out` (models.py:287-356)."""
+        seen, order, indeg = {}, [], {}
+        queue = [start]
+        while queue:
+            n = queue.pop(0)
+            if id(n) in seen:
+                continue
+            seen[id(n)] = n
+            for m in edges_out(n):
+                queue.append(m)
+        for n in seen.values():
+            indeg[id(n)] = sum(1 for p in edges_in(n) if id(p) in seen)
+        ready = [n for n in seen.values() if indeg[id(n)] == 0]
+        while ready:
+            n = ready.pop(0)
+            order.append(n)
+            for m in edges_out(n):
+                indeg[id(m)] -= 1
+                if indeg[id(m)] == 0:
+                    ready.append(m)
+        return order
+
+    def compile(self, optimizer, loss, precision='fp32'):
+        assert self.inputs is not None and self.outputs is not None
+        self.forward_graph = self._kahn(self.inputs, lambda n: n.outbound_layers, lambda n: n.inbounds)
+        self.backward_graph = self._kahn(self.outputs, lambda n: n.inbounds, lambda n: n.outbound_layers)
+        tv = []
+        for layer in self.forward_graph:
+            for var in layer.variables:
+                # only real Variables: the reference also registers the Layer operands of Add
+                # here (models.py:304-307), which then breaks its optimizer
+                if isinstance(var, Variable) and var.require_grads and var not in tv:
+                    tv.append(var)
+        self.trainable_variables = tv
+        self._finish_compile(optimizer, loss, precision)
+
+    def _forward_order(self):
+        return self.forward_graph
+
+    def _backward_order(self):
+        return self.backward_graph
+
+    def _input_layer(self):
+        return self.inputs
+
+    def _output_layer(self):
+        return self.outputs
+
+    def save(self, save_path):
+        self._sync_to_host()
+        with open(save_path + '.pkl', 'wb') as f:
+            pickle.dump([self.forward_graph, self.backward_graph, self.optimizer, self.loss], f)
+
+    def load(self, model_path):
+        with open(model_path + '.pkl', 'rb') as f:
+            fg, bg, optimizer, loss = pickle.load(f)
+        self.forward_graph, self.backward_graph, self.optimizer, self.loss = fg, bg, optimizer, loss
+        self.inputs, self.outputs = fg[0], bg[0]
+        self.trainable_variables = [v for l in fg for v in l.variables if isinstance(v, Variable) and v.require_grads]
+        self._drop_device_state()

@@ -1,0 +1,136 @@
+"""CPU: host-side logic of the reference-facing API (shape inference, parameter creation order,
+graph ordering, batching) checked against the golden fixtures.  No GPU work."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+import shinnosuke_b200 as sb
+from shinnosuke_b200 import (Sequential, Model, Input, Dense, Conv2D, MaxPooling2D, Flatten, BatchNormalization,
+                             ZeroPadding2D, Activation)
+from shinnosuke_b200.utils.MiniBatch import get_batches, batch_slices
+from shinnosuke_b200.utils.Preprocess import to_categorical
+from shinnosuke_b200.utils import Initializers as I
+from oracle import shinnosuke_oracle as O
+
+
+def test_initial_weights_match_reference_stream():
+    """np.random.seed(0) + compile must reproduce the reference's initial weights (KAT A values)."""
+    np.random.seed(0)
+    x = Input((None, 3, 8, 8))
+    c = Conv2D(4, (3, 3), padding='SAME', activation='relu', initializer='normal')(x)
+    W, b = c.variables
+    assert np.allclose(W.output_tensor[0, 0, 0, :], [0.176405234597, 0.040015720837, 0.097873798411], atol=1e-12)
+    assert np.allclose(b.output_tensor[0, :2], [1.92294202648, 1.480514791434], atol=1e-11)
+    assert c.output_shape == (None, 4, 8, 8) and c.pad_size == (1, 1)
+
+
+def test_sequential_compile_shapes_cfg3():
+    np.random.seed(0)
+    m = Sequential()
+    m.add(Conv2D(64, (3, 3), input_shape=(None, 3, 32, 32), padding='SAME', activation='relu'))
+    m.add(BatchNormalization()); m.add(MaxPooling2D((2, 2)))
+    for f in (128, 256, 256):
+        m.add(Conv2D(f, (3, 3), padding='SAME', activation='relu')); m.add(BatchNormalization()); m.add(MaxPooling2D((2, 2)))
+    m.add(Flatten()); m.add(Dense(10, activation='softmax'))
+    m.compile(optimizer='sgd', loss='sparse_categorical_crossentropy', precision='tf32')
+    assert m.layers[-1].output_shape == (None, 10)
+    assert m.layers[-2].output_shape == (None, 1024)
+    assert sum(v.size for v in m.trainable_variables) == 972554          # SURVEY.md / BASELINE.md
+    assert all(l.precision == 'tf32' for l in m.layers)
+    # same RNG consumption as the oracle's builder (which is pinned to the reference)
+    np.random.seed(0)
+    spec, ishape = O.spec_cfg3()
+    net = O.OracleNet(spec, ishape)
+    ours = [np.asarray(v.output_tensor) for v in m.trainable_variables]
+    assert len(ours) == len(net.params)
+    for a, b in zip(ours, net.params):
+        assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_functional_graph_order_cfg1():
+    np.random.seed(0)
+    X_in = Input(shape=(None, 1, 28, 28))
+    h = Conv2D(8, (2, 2), padding='VALID', initializer='normal', activation='relu')(X_in)
+    h = MaxPooling2D((2, 2))(h)
+    h = Flatten()(h)
+    y = Dense(10, initializer='normal', activation='softmax')(h)
+    model = Model(inputs=X_in, outputs=y)
+    model.compile(optimizer='sgd', loss='sparse_categorical_crossentropy')
+    assert [l.__class__.__name__ for l in model.forward_graph] == ['Input', 'Conv2D', 'MaxPooling2D', 'Flatten', 'Dense']
+    assert [l.__class__.__name__ for l in model.backward_graph] == ['Dense', 'Flatten', 'MaxPooling2D', 'Conv2D', 'Input']
+    assert sum(v.size for v in model.trainable_variables) == 13570
+    assert model.forward_graph[2].output_shape == (None, 8, 13, 13) and model.forward_graph[2].mode == 'reshape'
+    g = load_golden('traj_cfg1')     # not the initial weights, but shapes must agree
+    assert model.forward_graph[1].variables[0].output_shape == g['convW'].shape
+
+
+def test_mlp_param_count_matches_readme():
+    m = Sequential([Dense(500, activation='relu', n_in=784), Dense(10, activation='softmax')])
+    m.compile('sgd', 'sparse_categorical_crossentropy')
+    assert sum(v.size for v in m.trainable_variables) == 397510            # README.md:81
+
+
+def test_pool_mode_selection_and_floor():
+    inp = Input((None, 8, 27, 27))
+    p = MaxPooling2D((2, 2))(inp)
+    assert p.mode == 'reshape' and p.output_shape == (None, 8, 13, 13)
+    p2 = MaxPooling2D((3, 3), stride=2)(inp)
+    assert p2.mode == 'im2col' and p2.output_shape == (None, 8, 13, 13)
+
+
+def test_error_behaviour_mirrors_reference():
+    with pytest.raises(TypeError):
+        Conv2D(4, (3, 3), padding='full')(Input((None, 1, 8, 8)))
+    with pytest.raises(ValueError):
+        Sequential([Dense(3)]).compile('sgd', 'sparse_categorical_crossentropy')
+    with pytest.raises(ValueError):
+        sb.get_optimizer(3.5)
+    with pytest.raises(ValueError):
+        Flatten(out_dim=0)
+    with pytest.raises(AssertionError):
+        MaxPooling2D((2, 3))
+
+
+def test_get_batches_matches_reference():
+    g = load_golden('get_batches')
+    X = np.arange(46, dtype=np.float64).reshape(23, 2)
+    Y = np.arange(23, dtype=np.float64).reshape(23, 1)
+    for epoch in (0, 1):
+        mb = get_batches(X, Y, 5, epoch, True)
+        assert len(mb) == int(g['e%d_n' % epoch])
+        assert np.array_equal(np.concatenate([b[1] for b in mb]), g['e%d_y' % epoch])
+    assert batch_slices(23, 5) == [(0, 5), (5, 10), (10, 15), (15, 20), (20, 23)]
+    assert batch_slices(0, 5) == []
+
+
+def test_to_categorical():
+    assert np.array_equal(to_categorical(np.array([0, 2, 1])), np.eye(3)[[0, 2, 1]])
+    assert np.array_equal(to_categorical(np.array([[1], [0]])), np.eye(2)[[1, 0]])
+    with pytest.raises(ValueError):
+        to_categorical(np.zeros((2, 2, 2), dtype=int))
+
+
+def test_initializers_consume_rng_like_reference():
+    np.random.seed(3)
+    a = I.get_initializer('glorot_uniform')((4, 6))
+    np.random.seed(3)
+    s = np.sqrt(6. / 10)
+    assert np.array_equal(a, np.random.uniform(-s, s, size=(4, 6)))
+    np.random.seed(4)
+    b = I.get_initializer('he_normal')((8, 3, 3, 3))
+    np.random.seed(4)
+    assert np.array_equal(b, np.random.normal(0.0, np.sqrt(2. / 27), size=(8, 3, 3, 3)))
+    assert I.get_initializer('orthogonal')((6, 4)).shape == (6, 4)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the compute path must fail loudly, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    m = Sequential([Dense(4, activation='softmax', n_in=3)])
+    m.compile('sgd', 'sparse_categorical_crossentropy')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m.fit(np.zeros((2, 3)), np.eye(4)[:2], batch_size=2, epochs=1, validation_ratio=0.)
+    with pytest.raises(RuntimeError):
+        m.predict(np.zeros((2, 3)))
