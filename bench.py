@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Headline benchmark: training samples/s of the data-parallel hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm
+
+Workload (BASELINE.json configs[2]): VGG-style CNN on synthetic CIFAR-shaped 3x32x32 data,
+4x[Conv2D 3x3 SAME + ReLU -> BatchNormalization -> MaxPooling 2x2] with 64-128-256-256 filters,
+Flatten, Dense(10, softmax), SGD; batch 512 per GPU (weak scaling: global batch 512*N).
+A "step" = forward sweep, softmax cross-entropy, backward sweep, gradient all-reduce (N>1),
+fused SGD update over the flat parameter arena.
+
+JSON line (rank 0): see the bench contract in DESIGN.md.  `value` is measured with the step's
+inputs already resident in HBM (CUDA-graph replays); `e2e` goes through Sequential.fit() with
+HOST buffers — every step copies its inputs host->device from pinned memory and copies the
+(loss, acc) pair back.  `roofline` is the dominant kernel timed with CUDA events on its own
+stream during an instrumented pass of the same steps; `cpu_baseline` is the CPU oracle (a NumPy
+port of the reference's algorithm, pinned to the reference) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    'cfg3': dict(name='VGG-style CNN 3x32x32: 4x[Conv2D(64-128-256-256,3x3,SAME,relu)+BatchNorm+MaxPool2x2]+Dense10, SGD',
+                 shape=(3, 32, 32), per_gpu_batch=512, flops_per_sample=290.3e6),
+    'cfg1': dict(name='README CNN 1x28x28: Conv2D(8,2x2,VALID,relu)+MaxPool2x2+Flatten+Dense10, SGD',
+                 shape=(1, 28, 28), per_gpu_batch=256, flops_per_sample=0.174e6),
+    'cfg2': dict(name='MLP 784-500-10, SGD', shape=(784,), per_gpu_batch=128, flops_per_sample=1.60e6),
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return dict(hbm=p['hbm_gbs'], bf16=p['bf16_tflops'], bf16_sustained=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                    source='measured')
+    except Exception:
+        return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source='fallback')
+
+
+def synth(cfg, n, seed=1234):
+    r = np.random.default_rng(seed)
+    shape = CONFIGS[cfg]['shape']
+    if cfg == 'cfg3':
+        X = r.standard_normal((n,) + shape, dtype=np.float32)
+    else:
+        X = r.random((n,) + shape, dtype=np.float32)
+    labels = r.integers(0, 10, n)
+    labels[:10] = np.arange(10)
+    Y = np.eye(10, dtype=np.float32)[labels]
+    return X, Y
+
+
+def build_model(cfg, precision):
+    from shinnosuke_b200 import Sequential, Conv2D, BatchNormalization, MaxPooling2D, Flatten, Dense
+    np.random.seed(0)
+    m = Sequential()
+    if cfg == 'cfg3':
+        first = True
+        for f in (64, 128, 256, 256):
+            kw = dict(input_shape=(None, 3, 32, 32)) if first else {}
+            first = False
+            m.add(Conv2D(f, (3, 3), padding='SAME', activation='relu', initializer='normal', **kw))
+            m.add(BatchNormalization())
+            m.add(MaxPooling2D((2, 2)))
+        m.add(Flatten())
+        m.add(Dense(10, activation='softmax'))
+    elif cfg == 'cfg1':
+        m.add(Conv2D(8, (2, 2), input_shape=(None, 1, 28, 28), padding='VALID', activation='relu', initializer='normal'))
+        m.add(MaxPooling2D((2, 2)))
+        m.add(Flatten())
+        m.add(Dense(10, activation='softmax', initializer='normal'))
+    else:
+        m.add(Dense(500, activation='relu', n_in=784))
+        m.add(Dense(10, activation='softmax'))
+    m.compile(optimizer='sgd', loss='sparse_categorical_crossentropy', precision=precision)
+    return m
+
+
+def oracle_spec(cfg):
+    from oracle import shinnosuke_oracle as O
+    return {'cfg1': O.spec_cfg1, 'cfg2': O.spec_cfg2, 'cfg3': O.spec_cfg3}[cfg]()
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(',')]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), c[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------- roofline table
+def kernel_work(name, a, precision):
+    """Algorithmic work of one launch from its integer arguments (SURVEY.md 8(d) formulas).
+    Returns (kind, amount): kind 'flops' or 'bytes'."""
+    if name in ('sn_conv2d_fprop', 'sn_conv2d_dgrad', 'sn_conv2d_wgrad'):
+        N, C, H, W, F, kh, kw, stride, ph, pw = a[:10]
+        oh = (H + 2 * ph - kh) // stride + 1
+        ow = (W + 2 * pw - kw) // stride + 1
+        return 'flops', 2.0 * N * F * oh * ow * C * kh * kw
+    if name in ('sn_dense_fprop', 'sn_dense_dgrad', 'sn_dense_wgrad'):
+        M, K, Nout = a[:3]
+        return 'flops', 2.0 * M * K * Nout
+    if name in ('sn_maxpool2d_fwd', 'sn_maxpool2d_bwd'):
+        N, H, W, C, pool, stride = a[:6]
+        oh, ow = (H - pool) // stride + 1, (W - pool) // stride + 1
+        return 'bytes', 4.0 * N * C * (H * W + oh * ow) + N * C * oh * ow
+    if name == 'sn_batchnorm_fwd_train':
+        rows, C = a[0], a[1]
+        return 'bytes', 4.0 * rows * C * 3          # read x (stats), read x + write y (apply)
+    if name == 'sn_batchnorm_bwd':
+        rows, C = a[0], a[1]
+        return 'bytes', 4.0 * rows * C * 5          # read dy,x (reduce), read dy,x + write dx (apply)
+    if name == 'sn_sgd_update':
+        return 'bytes', 16.0 * a[0]
+    if name == 'sn_momentum_update':
+        return 'bytes', 20.0 * a[0]
+    if name in ('sn_relu_bwd',):
+        return 'bytes', 12.0 * a[0]
+    if name in ('sn_nchw_to_nhwc', 'sn_nhwc_to_nchw'):
+        return 'bytes', 8.0 * a[0] * a[1] * a[2] * a[3]
+    return 'bytes', 0.0
+
+
+def roofline_from_profile(summary, precision, pk):
+    """Pick the kernel class with the largest share of the step and report it against its roof."""
+    rows = []
+    total = 0.0
+    for (name, a), ms_list in summary.items():
+        ms = float(np.mean(ms_list))
+        kind, amount = kernel_work(name, a, precision)
+        rows.append(dict(name=name, args=list(a), ms=ms, launches=len(ms_list), kind=kind, work=amount))
+        total += float(np.sum(ms_list))
+    rows.sort(key=lambda r: -r['ms'] * r['launches'])
+    for r in rows:
+        r['share'] = r['ms'] * r['launches'] / total if total else 0.0
+    top = rows[0]
+    if top['kind'] == 'flops':
+        tensor_peak = {'fp32': None, 'tf32': pk['bf16'] / 2, 'bf16': pk['bf16']}[precision]
+        achieved = top['work'] / (top['ms'] * 1e-3) / 1e12
+        if tensor_peak is None:
+            # CUDA-core tier: there is no tensor-pipe roof; report against the TF32 tensor roof it competes with
+            tensor_peak = pk['bf16'] / 2
+        roof = dict(bound='tensor', achieved=achieved, peak=tensor_peak, unit='TFLOP/s', frac=achieved / tensor_peak)
+    else:
+        achieved = top['work'] / (top['ms'] * 1e-3) / 1e9
+        roof = dict(bound='hbm', achieved=achieved, peak=pk['hbm'], unit='GB/s', frac=achieved / pk['hbm'])
+    roof.update(kernel=top['name'], kernel_args=top['args'], kernel_ms=top['ms'], share_of_step=top['share'],
+                traffic=None, peak_source=pk['source'])
+    return roof, rows
+
+
+# --------------------------------------------------------------- CPU legs
+def cpu_oracle_throughput(cfg, batch, steps, warmup=1):
+    """The reference's algorithm (NumPy float64, all host cores through OpenBLAS) on `steps`
+    minibatches of `batch` samples of the workload."""
+    from oracle import shinnosuke_oracle as O
+    spec, ishape = oracle_spec(cfg)
+    np.random.seed(0)
+    net = O.OracleNet(spec, ishape)
+    X, Y = synth(cfg, batch * (steps + warmup))
+    X = X.astype(np.float64)
+    Y = Y.astype(np.float64)
+    for i in range(warmup):
+        net.step(X[i * batch:(i + 1) * batch], Y[i * batch:(i + 1) * batch])
+    t0 = time.perf_counter()
+    for i in range(warmup, warmup + steps):
+        net.step(X[i * batch:(i + 1) * batch], Y[i * batch:(i + 1) * batch])
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is a
+    pure-Python package that cannot travel to the GPU box, so this times oracle/ (its NumPy
+    restatement, pinned to the live reference by tests/golden)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cfg = args.config
+    sample_batch = {'cfg3': 64, 'cfg1': 256, 'cfg2': 128}[cfg]
+    steps = max(1, args.steps)
+    value, s_per_step = cpu_oracle_throughput(cfg, sample_batch, steps, max(1, min(args.warmup, 2)))
+    cores = os.cpu_count()
+    sample = '%d steps of batch %d (float64 NumPy, OpenBLAS threads = all %d cores)' % (steps, sample_batch, cores)
+    line = dict(impl='reference', metric='train_samples_per_sec', value=value, unit='samples/s', n_gpus=args.gpus,
+                steps=steps, warmup=args.warmup, ms_per_step=s_per_step * 1e3, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f64', data='synthetic',
+                config=dict(workload=CONFIGS[cfg]['name'], per_gpu_batch=args.per_gpu_batch or CONFIGS[cfg]['per_gpu_batch'],
+                            sample_batch=sample_batch),
+                cpu_baseline=dict(value=value, unit='samples/s', cores=cores, kind='port', sample=sample),
+                e2e=dict(value=value, unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from shinnosuke_b200._lib import lib
+    from shinnosuke_b200.device import current_stream
+
+    cfg = args.config
+    B = args.per_gpu_batch or CONFIGS[cfg]['per_gpu_batch']
+    G = B * world                                   # global minibatch (weak scaling)
+    K, Wm = args.steps, max(3, args.warmup)
+    precision = args.precision
+    pk = peaks()
+    m = build_model(cfg, precision)
+
+    # every rank holds the whole synthetic set, like every rank running the same script would
+    X, Y = synth(cfg, G * max(K, Wm, 4))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- leg 1: through the public API with HOST buffers (e2e) ----------------
+    Xt, Yt = X[:G * K], Y[:G * K]
+    # warm-up: same call, same arrays (captures the step graphs, page-locks the staging ring)
+    m.fit(Xt[:G * max(Wm, 4)], Yt[:G * max(Wm, 4)], batch_size=G, epochs=1, shuffle=False, validation_ratio=0., verbose=0)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    m.fit(Xt, Yt, batch_size=G, epochs=1, shuffle=False, validation_ratio=0., verbose=0)
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    losses_e2e = list(m.train_loss[-K:])
+
+    # ---- leg 2: inputs resident in HBM, graph replays (value) -------------------
+    inp = m.layers[0]
+    n_loc = B
+    xs = inp._buf('fit_x0', (n_loc,) + X.shape[1:], 'nhwc' if X.ndim == 4 else 'flat')
+    ys = inp._buf('fit_y0', (n_loc, Y.shape[1]), 'flat')
+    for _ in range(Wm):
+        m._run_step(xs, ys, G)
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        m._run_step(xs, ys, G)
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+
+    # ---- instrumented pass: per-kernel CUDA-event durations (eager, same buffers) ---
+    m.use_cuda_graph = False
+    lib.sn_launch_count_reset()
+    m._run_step(xs, ys, G)
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.sn_launch_count())
+    lib.start_profiling()
+    for _ in range(min(K, 10)):
+        m._run_step(xs, ys, G)
+    summary = lib.stop_profiling()
+    m.use_cuda_graph = True
+    roof, rows = roofline_from_profile(summary, precision, pk)
+
+    t = torch.tensor([dev_ms, e2e_ms], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        if args.kernel_table:
+            os.makedirs(os.path.dirname(os.path.abspath(args.kernel_table)), exist_ok=True)
+            with open(args.kernel_table, 'w') as f:
+                json.dump(dict(config=cfg, per_gpu_batch=B, precision=precision, step_ms_graph=dev_ms / K, kernels=rows), f, indent=1)
+        cpu_batch = {'cfg3': 64, 'cfg1': 256, 'cfg2': 128}[cfg]
+        cpu_steps = {'cfg3': 6, 'cfg1': 30, 'cfg2': 200}[cfg]
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_val, _ = cpu_oracle_throughput(cfg, cpu_batch, cpu_steps)
+            cpu = dict(value=cpu_val, unit='samples/s', cores=os.cpu_count(), kind='port',
+                       sample='%d steps of batch %d of the same workload, float64 NumPy oracle' % (cpu_steps, cpu_batch))
+        else:
+            cpu = None
+        h2d = int(n_loc * (np.prod(X.shape[1:]) + Y.shape[1]) * 4)
+        line = dict(metric='train_samples_per_sec', value=G * K / (dev_ms * 1e-3), unit='samples/s', n_gpus=world, steps=K,
+                    warmup=Wm, ms_per_step=dev_ms / K, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype=precision, data='synthetic',
+                    config=dict(workload=CONFIGS[cfg]['name'], per_gpu_batch=B, global_batch=G, parallelism='dp%d' % world,
+                                precision=precision, l2='working set per step exceeds the 126 MB L2 (no flush)' if cfg == 'cfg3' and B >= 256
+                                else 'small working set, no flush: the step is launch-latency bound',
+                                step_tflops=CONFIGS[cfg]['flops_per_sample'] * G / world / (dev_ms / K * 1e-3) / 1e12),
+                    clocks=clocks,
+                    e2e=dict(value=G * K / (e2e_ms * 1e-3), unit='samples/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,
+                             ms_per_step=e2e_ms / K, final_loss=losses_e2e[-1] if losses_e2e else None),
+                    gpu_launches=launches_per_step * K, roofline=roof, cpu_baseline=cpu)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='cfg3', choices=sorted(CONFIGS))
+    ap.add_argument('--per-gpu-batch', type=int, default=0)
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'tf32', 'bf16'])
+    ap.add_argument('--kernel-table', default='', help='write the per-kernel CUDA-event table (JSON) here')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

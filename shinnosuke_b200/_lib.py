@@ -44,10 +44,59 @@ class ShinnosukeLibError(RuntimeError):
     pass
 
 
+class KernelProfiler(object):
+    """Brackets every compute entry point with CUDA events on the launching stream (the last
+    argument of every such call).  bench.py uses it for the per-kernel roofline; off by default."""
+    SKIP = ('sn_event_', 'sn_stream_', 'sn_malloc', 'sn_free', 'sn_set_device', 'sn_device_', 'sn_memcpy_h2d',
+            'sn_memcpy_d2h')
+
+    def __init__(self, dll):
+        self.dll = dll
+        self.records = []          # (name, args, start_event, stop_event)
+        self._pool = []
+
+    def _event(self):
+        if self._pool:
+            return self._pool.pop()
+        ev = ctypes.c_void_p()
+        self.dll.sn_event_create(ctypes.byref(ev))
+        return ev
+
+    def call(self, name, fn, args):
+        stream = args[-1]
+        a, b = self._event(), self._event()
+        self.dll.sn_event_record(a, stream)
+        rc = fn(*args)
+        self.dll.sn_event_record(b, stream)
+        self.records.append((name, args, a, b))
+        return rc
+
+    def summary(self):
+        """{(name, int-args): [ms, ...]}; synchronises.  Pointer arguments are dropped from the key."""
+        out = {}
+        ms = ctypes.c_float()
+        for name, args, a, b in self.records:
+            self.dll.sn_event_elapsed_ms(a, b, ctypes.byref(ms))
+            key = (name, tuple(x for x in args[:-1] if isinstance(x, (int, float)) and not isinstance(x, bool) and abs(x) < (1 << 40)))
+            out.setdefault(key, []).append(ms.value)
+            self._pool += [a, b]
+        self.records = []
+        return out
+
+
 class _Lib(object):
     def __init__(self):
         self._dll = None
         self._err = None
+        self.profiler = None
+
+    def start_profiling(self):
+        self.profiler = KernelProfiler(self.load())
+        return self.profiler
+
+    def stop_profiling(self):
+        prof, self.profiler = self.profiler, None
+        return prof.summary() if prof is not None else {}
 
     def load(self):
         if self._dll is not None:
@@ -70,8 +119,11 @@ class _Lib(object):
         dll = self.load()
         fn = getattr(dll, name)
         if fn.restype is ctypes.c_int and name not in ('sn_abi_version',):
-            def checked(*args, _fn=fn, _name=name):
-                rc = _fn(*args)
+            timed = not name.startswith(KernelProfiler.SKIP)
+
+            def checked(*args, _fn=fn, _name=name, _timed=timed):
+                prof = self.profiler
+                rc = prof.call(_name, _fn, args) if (prof is not None and _timed) else _fn(*args)
                 if rc != 0:
                     raise ShinnosukeLibError('%s failed (%d): %s' % (_name, rc, dll.sn_last_error().decode()))
             setattr(self, name, checked)

@@ -58,6 +58,7 @@ class _Trainer(object):
         self._graphs = {}
         self._warm = set()
         self._metrics_out = None
+        self._fit_res = None
 
     # ---- to be provided by the subclass ---------------------------------
     def _forward_order(self):
@@ -175,10 +176,36 @@ class _Trainer(object):
         graph.replay()
 
     # ---- fit (models.py:47-119 / :370-431) --------------------------------
+    def _fit_resources(self, n_loc_max, x_row, y_row, n_batches):
+        """Pinned staging ring, copy stream and metric buffers; cached on the model because
+        page-locking host memory is far slower than a training step."""
+        t = torch()
+        key = (x_row, y_row)
+        res = self._fit_res
+        if res is None or res['key'] != key or res['cap'] < n_loc_max:
+            depth = 4
+            res = dict(key=key, cap=n_loc_max, depth=depth,
+                       x=[t.empty((n_loc_max, x_row), dtype=t.float32).pin_memory() for _ in range(depth)],
+                       y=[t.empty((n_loc_max, y_row), dtype=t.float32).pin_memory() for _ in range(depth)],
+                       copy_stream=t.cuda.Stream(), metrics=None,
+                       h2d_done=[t.cuda.Event() for _ in range(2)], compute_done=[t.cuda.Event() for _ in range(2)],
+                       slot_copied=[t.cuda.Event() for _ in range(depth)])
+            self._fit_res = res
+        if res['metrics'] is None or res['metrics'].shape[0] < n_batches:
+            res['metrics'] = t.zeros((n_batches, 2), dtype=t.float32).pin_memory()
+        return res
+
     def fit(self, X, Y, batch_size=64, epochs=20, shuffle=True, validation_data=None, validation_ratio=0.1,
             draw_acc_loss=False, draw_save_path=None, verbose=1):
+        """The reference's minibatch loop (models.py:62-118) as a three-stage pipeline:
+        a host thread gathers minibatch i+1.. (get_batches' permutation order) into pinned
+        staging; a copy stream moves it host->device and transposes NCHW->NHWC into one of two
+        device input buffers; the compute stream replays the captured step graph and copies the
+        (loss, acc) pair back.  Nothing in the loop blocks on the device except ring reuse."""
         if draw_acc_loss:
             raise NotImplementedError('live matplotlib plotting is out of scope of the device path')
+        import queue
+        import threading
         t = require_cuda()
         self._materialize()
         X = np.asarray(X)
@@ -199,66 +226,119 @@ class _Trainer(object):
         world = dist.get_world_size() if dist is not None else 1
         rank = dist.get_rank() if dist is not None else 0
         m = train_X.shape[0]
-        X32 = np.ascontiguousarray(train_X, dtype=np.float32)
-        Y32 = np.ascontiguousarray(train_Y, dtype=np.float32)
-        # float32 pinned staging of the (shuffled) epoch, like get_batches' shuffled copies
-        pin_x = t.empty(train_X.shape, dtype=t.float32).pin_memory()
-        pin_y = t.empty(train_Y.shape, dtype=t.float32).pin_memory()
-        np_px, np_py = pin_x.numpy(), pin_y.numpy()
+        x_row = int(np.prod(train_X.shape[1:]))
+        y_row = int(np.prod(train_Y.shape[1:]))
+        X2 = np.ascontiguousarray(train_X, dtype=np.float32).reshape(m, x_row)     # no copy if already float32
+        Y2 = np.ascontiguousarray(train_Y, dtype=np.float32).reshape(m, y_row)
         slices = batch_slices(m, batch_size)
-        pin_metrics = t.zeros((len(slices), 2), dtype=t.float32).pin_memory()
+        if not slices:
+            return
+        shards = []
+        for a, b in slices:                         # this rank's contiguous rows of each minibatch
+            rows = b - a
+            shards.append((a + (rows * rank) // world, a + (rows * (rank + 1)) // world, rows))
+        n_loc_max = max(hi - lo for lo, hi, _ in shards)
+        res = self._fit_resources(n_loc_max, x_row, y_row, len(slices))
+        depth, copy_stream = res['depth'], res['copy_stream']
         inp = self._input_layer()
-        st = current_stream()
         is4d = train_X.ndim == 4 and train_X.shape[1] > 1 and train_X.shape[2] * train_X.shape[3] > 1
+        x_layout = 'nhwc' if train_X.ndim == 4 else 'flat'
 
-        for epoch in range(epochs):
-            perm = batch_permutation(m, epoch, shuffle)
-            if perm is None:
-                np_px[...] = X32
-                np_py[...] = Y32
-            else:
-                np.take(X32, perm, axis=0, out=np_px)
-                np.take(Y32, perm, axis=0, out=np_py)
-            if verbose:
-                print('\033[0;31m Epoch[%d/%d]' % (epoch + 1, epochs))
-            start_time = time.time()
-            rows_done = []
-            for bi, (a, b) in enumerate(slices):
-                rows = b - a
-                # this rank's contiguous shard of the minibatch
-                lo = a + (rows * rank) // world
-                hi = a + (rows * (rank + 1)) // world
-                n_loc = hi - lo
-                shape_x = (n_loc,) + train_X.shape[1:]
-                xs = inp._buf('fit_x', shape_x, 'nhwc' if train_X.ndim == 4 else 'flat')
-                ys = inp._buf('fit_y', (n_loc,) + train_Y.shape[1:], 'flat')
-                if is4d:
-                    stage = inp._buf('fit_x_nchw', shape_x, 'flat')
-                    lib.sn_memcpy_h2d(stage.ptr, pin_x[lo:hi].data_ptr(), n_loc * int(np.prod(train_X.shape[1:])) * 4, st)
-                    lib.sn_nchw_to_nhwc(stage.ptr, xs.ptr, n_loc, shape_x[1], shape_x[2], shape_x[3], st)
-                else:
-                    lib.sn_memcpy_h2d(xs.ptr, pin_x[lo:hi].data_ptr(), n_loc * int(np.prod(train_X.shape[1:])) * 4, st)
-                lib.sn_memcpy_h2d(ys.ptr, pin_y[lo:hi].data_ptr(), n_loc * int(np.prod(train_Y.shape[1:])) * 4, st)
-                self._run_step(xs, ys, rows)
-                lib.sn_memcpy_d2h(pin_metrics[bi].data_ptr(), self._metrics_out.data_ptr(), 8, st)
-                rows_done.append(rows)
-                if validation_data is not None:
-                    valid_acc, valid_loss = self.evaluate(valid_X, valid_Y, batch_size=batch_size)
-                    self.valid_loss.append(valid_loss)
-                    self.valid_acc.append(valid_acc)
-            lib.sn_stream_sync(st)
-            gap = time.time() - start_time
-            mets = pin_metrics.numpy()
-            for bi, rows in enumerate(rows_done):
-                self.train_loss.append(float(mets[bi, 0]) / rows)
-                self.train_acc.append(float(mets[bi, 1]) / rows)
-            if verbose:
-                bar = self.process_bar_trained * (self.process_bar_nums - 1) + '>'
-                msg = '\r{:d}/{:d} [{}] -{:.0f}s -{:.0f}ms/batch -batch_loss: {:.4f} -batch_acc: {:.4f} '.format(
-                    m, m, bar, gap, gap * 1000 / max(1, len(slices)), self.train_loss[-1], self.train_acc[-1])
-                if validation_data is not None:
-                    msg += '-val_loss: {:.4f} -val_acc: {:.4f}'.format(self.valid_loss[-1], self.valid_acc[-1])
-                print(msg)
+        # ---- stage 1: host gather thread --------------------------------------
+        free_slots = threading.Semaphore(depth)
+        ready = queue.Queue()
+        perms = queue.Queue()
+        stop = threading.Event()
+
+        def gather():
+            seq = 0
+            while True:
+                perm = perms.get()
+                if perm is False:
+                    return
+                for lo, hi, _ in shards:
+                    free_slots.acquire()
+                    if stop.is_set():
+                        return
+                    slot = seq % depth
+                    n = hi - lo
+                    px, py = res['x'][slot].numpy(), res['y'][slot].numpy()
+                    if perm is None:
+                        px[:n] = X2[lo:hi]
+                        py[:n] = Y2[lo:hi]
+                    else:
+                        np.take(X2, perm[lo:hi], axis=0, out=px[:n])
+                        np.take(Y2, perm[lo:hi], axis=0, out=py[:n])
+                    ready.put(slot)
+                    seq += 1
+
+        worker = threading.Thread(target=gather, daemon=True)
+        worker.start()
+        compute_stream = t.cuda.current_stream()
+        st = compute_stream.cuda_stream
+        cs = copy_stream.cuda_stream
+        pending_slots = []          # (slot) whose H2D has been issued but not yet confirmed done
+        step_no = 0
+        try:
+            for epoch in range(epochs):
+                perms.put(batch_permutation(m, epoch, shuffle))
+                if verbose:
+                    print('\033[0;31m Epoch[%d/%d]' % (epoch + 1, epochs))
+                start_time = time.time()
+                pin_metrics = res['metrics']
+                for bi, (lo, hi, rows) in enumerate(shards):
+                    n_loc = hi - lo
+                    slot = ready.get()
+                    j = step_no & 1
+                    shape_x = (n_loc,) + train_X.shape[1:]
+                    xs = inp._buf('fit_x%d' % j, shape_x, x_layout)
+                    ys = inp._buf('fit_y%d' % j, (n_loc,) + train_Y.shape[1:], 'flat')
+                    # ---- stage 2: copy stream ------------------------------------
+                    copy_stream.wait_event(res['compute_done'][j])      # device buffer j is free again
+                    if is4d:
+                        stage = inp._buf('fit_x_nchw%d' % j, shape_x, 'flat')
+                        lib.sn_memcpy_h2d(stage.ptr, res['x'][slot].data_ptr(), n_loc * x_row * 4, cs)
+                        lib.sn_nchw_to_nhwc(stage.ptr, xs.ptr, n_loc, shape_x[1], shape_x[2], shape_x[3], cs)
+                    else:
+                        lib.sn_memcpy_h2d(xs.ptr, res['x'][slot].data_ptr(), n_loc * x_row * 4, cs)
+                    lib.sn_memcpy_h2d(ys.ptr, res['y'][slot].data_ptr(), n_loc * y_row * 4, cs)
+                    res['slot_copied'][slot].record(copy_stream)
+                    res['h2d_done'][j].record(copy_stream)
+                    pending_slots.append(slot)
+                    # ---- stage 3: compute stream ---------------------------------
+                    compute_stream.wait_event(res['h2d_done'][j])
+                    self._run_step(xs, ys, rows)
+                    res['compute_done'][j].record(compute_stream)
+                    lib.sn_memcpy_d2h(pin_metrics[bi].data_ptr(), self._metrics_out.data_ptr(), 8, st)
+                    step_no += 1
+                    # hand staging slots whose copy has certainly finished back to the gather thread
+                    while len(pending_slots) > 2:
+                        res['slot_copied'][pending_slots.pop(0)].synchronize()
+                        free_slots.release()
+                    if validation_data is not None:
+                        valid_acc, valid_loss = self.evaluate(valid_X, valid_Y, batch_size=batch_size)
+                        self.valid_loss.append(valid_loss)
+                        self.valid_acc.append(valid_acc)
+                lib.sn_stream_sync(st)
+                gap = time.time() - start_time
+                mets = pin_metrics.numpy()
+                for bi, (_, _, rows) in enumerate(shards):
+                    self.train_loss.append(float(mets[bi, 0]) / rows)
+                    self.train_acc.append(float(mets[bi, 1]) / rows)
+                if verbose:
+                    bar = self.process_bar_trained * (self.process_bar_nums - 1) + '>'
+                    msg = '\r{:d}/{:d} [{}] -{:.0f}s -{:.0f}ms/batch -batch_loss: {:.4f} -batch_acc: {:.4f} '.format(
+                        m, m, bar, gap, gap * 1000 / max(1, len(slices)), self.train_loss[-1], self.train_acc[-1])
+                    if validation_data is not None:
+                        msg += '-val_loss: {:.4f} -val_acc: {:.4f}'.format(self.valid_loss[-1], self.valid_acc[-1])
+                    print(msg)
+        finally:
+            stop.set()
+            perms.put(False)
+            for _ in range(depth + 1):
+                free_slots.release()
+            copy_stream.synchronize()
+            worker.join(timeout=10)
 
     # ---- evaluate (models.py:144-171) -------------------------------------
     def evaluate(self, X, Y, batch_size=None):
@@ -289,6 +369,7 @@ class _Trainer(object):
         self._graphs = {}
         self._warm = set()
         self._metrics_out = None
+        self._fit_res = None
         for layer in self._forward_order():
             layer._bufs = {}
             for v in layer.variables:
