@@ -52,7 +52,7 @@ extern "C" {
 /* arithmetic tier of the contraction kernels */
 #define SN_PREC_FP32 0   /* CUDA-core FFMA, fp32 operands and accumulators (1e-5 tier)      */
 #define SN_PREC_TF32 1   /* tcgen05.mma kind::tf32, fp32 storage, fp32 TMEM accumulators    */
-#define SN_PREC_BF16 2   /* tcgen05.mma kind::f16 on bf16 copies of the operands            */
+#define SN_PREC_BF16 2   /* tcgen05.mma kind::f16 on bf16 copies of the operands (reserved)  */
 
 /* max-pool backward semantics (layers/Convolution.py:266-269) */
 #define SN_POOL_TIE_SPLIT    0   /* 'reshape' mode: ties share the gradient equally         */
@@ -100,10 +100,15 @@ SN_API int sn_axpy(float alpha, const float *x, float *y, long long n, void *str
 SN_API int sn_conv2d_fprop(const float *x, const float *w, const float *bias, float *y,
                     int N, int C, int H, int W, int F, int kh, int kw,
                     int stride, int pad_h, int pad_w, int act, int precision, void *stream);
-/* Conv2D.backward dX, layers/Convolution.py:199-202 + utils/ConvCol.py:24-42 (col2im-free) */
+/* Conv2D.backward dX, layers/Convolution.py:199-202 + utils/ConvCol.py:24-42 (col2im-free).
+ * The tensor-core tiers run dgrad as a forward convolution of dY with the filters flipped and
+ * transposed; `workspace` holds that copy (sn_conv2d_dgrad_workspace() bytes, device memory,
+ * rewritten by every call).  workspace == NULL selects the CUDA-core kernel. */
+SN_API size_t sn_conv2d_dgrad_workspace(int C, int F, int kh, int kw, int precision);
 SN_API int sn_conv2d_dgrad(const float *dy, const float *w, float *dx,
                     int N, int C, int H, int W, int F, int kh, int kw,
-                    int stride, int pad_h, int pad_w, int accumulate, int precision, void *stream);
+                    int stride, int pad_h, int pad_w, int accumulate, int precision,
+                    void *workspace, void *stream);
 /* Conv2D.backward dW (+= dYr . cols^T, :197) and db (+= sum dY, :192); db may be NULL */
 SN_API int sn_conv2d_wgrad(const float *x, const float *dy, float *dw, float *db,
                     int N, int C, int H, int W, int F, int kh, int kw,
@@ -126,7 +131,8 @@ SN_API int sn_dense_fprop(const float *x, const float *w, const float *bias, flo
                    int M, int K, int Nout, int act, int precision, void *stream);
 /* Dense.backward dX = dZ . W^T, layers/FC.py:147 */
 SN_API int sn_dense_dgrad(const float *dy, const float *w, float *dx,
-                   int M, int K, int Nout, int accumulate, int precision, void *stream);
+                   int M, int K, int Nout, int accumulate, int precision,
+                   void *workspace /* sn_conv2d_dgrad_workspace(K, Nout, 1, 1, precision) */, void *stream);
 /* Dense.backward dW += X^T . dZ (:144), db += sum_rows dZ (:146) */
 SN_API int sn_dense_wgrad(const float *x, const float *dy, float *dw, float *db,
                    int M, int K, int Nout, int accumulate, int precision, void *stream);

@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed building libshinnosuke_b200.so')
-    link = [NVCC, '-shared', '-o', LIB] + objs + ['-lcuda']
+    link = [NVCC, '-shared', '-o', LIB] + objs
     subprocess.check_call(link)
     return LIB
 

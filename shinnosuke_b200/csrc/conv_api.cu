@@ -6,10 +6,22 @@ namespace sn {
 int conv_fprop_simt(const float *, const float *, const float *, float *, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv_dgrad_simt(const float *, const float *, float *, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv_wgrad_simt(const float *, const float *, float *, float *, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+bool conv_tc_eligible(int N, int C, int OH, int OW, int F, int stride);
+bool wgrad_tc_eligible(int N, int C, int OH, int OW, int F, int stride);
+int conv_igemm_tc(const float *x, const float *w, const float *bias, float *out, int N, int C, int IH, int IW, int F, int kh,
+                  int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, cudaStream_t st);
+int conv_wgrad_tc(const float *x, const float *dy, float *dw, int N, int C, int IH, int IW, int F, int kh, int kw, int OH,
+                  int OW, int pad_h, int pad_w, cudaStream_t st);
+int flip_transpose_filters(const float *w, float *wt, int F, int C, int kh, int kw, cudaStream_t st);
+int colsum_accumulate(const float *dy, float *db, long long rows, int F, cudaStream_t st);
 }
 
 static int check_prec(int precision) {
-    if (precision != SN_PREC_FP32 && precision != SN_PREC_TF32 && precision != SN_PREC_BF16) {
+    if (precision == SN_PREC_BF16) {
+        set_error("the bf16 tier is not built yet; use SN_PREC_TF32 (tensor cores) or SN_PREC_FP32");
+        return SN_ERR_UNSUPPORTED;
+    }
+    if (precision != SN_PREC_FP32 && precision != SN_PREC_TF32) {
         set_error("unknown precision tier %d", precision);
         return SN_ERR_INVALID_ARG;
     }
@@ -24,14 +36,35 @@ int sn_conv2d_fprop(const float *x, const float *w, const float *bias, float *y,
     SN_REQUIRE(act == SN_ACT_LINEAR || act == SN_ACT_RELU, "unknown activation");
     int e = check_prec(precision);
     if (e) return e;
+    if (N > 0 && precision == SN_PREC_TF32 && H + 2 * pad_h >= kh && W + 2 * pad_w >= kw) {
+        const int oh = (H + 2 * pad_h - kh) / stride + 1, ow = (W + 2 * pad_w - kw) / stride + 1;
+        if (conv_tc_eligible(N, C, oh, ow, F, stride))
+            return conv_igemm_tc(x, w, bias, y, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, act, 0, as_stream(stream));
+    }
     return conv_fprop_simt(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, as_stream(stream));
 }
 
+size_t sn_conv2d_dgrad_workspace(int C, int F, int kh, int kw, int precision) {
+    if (precision == SN_PREC_FP32 || C <= 0 || F <= 0 || kh <= 0 || kw <= 0) return 0;
+    return sizeof(float) * (size_t)C * F * kh * kw;
+}
+
 int sn_conv2d_dgrad(const float *dy, const float *w, float *dx, int N, int C, int H, int W, int F, int kh, int kw,
-                    int stride, int pad_h, int pad_w, int accumulate, int precision, void *stream) {
+                    int stride, int pad_h, int pad_w, int accumulate, int precision, void *workspace, void *stream) {
     SN_REQUIRE(dy && w && dx, "null tensor");
     int e = check_prec(precision);
     if (e) return e;
+    if (N > 0 && precision == SN_PREC_TF32 && workspace && stride == 1 && H + 2 * pad_h >= kh && W + 2 * pad_w >= kw &&
+        kh - 1 - pad_h >= 0 && kw - 1 - pad_w >= 0) {
+        // dX = forward convolution of dY (N, oh, ow, F) with Wt[c][kh-1-u][kw-1-v][f], padding k-1-p, output (H, W)
+        const int oh = H + 2 * pad_h - kh + 1, ow = W + 2 * pad_w - kw + 1;
+        if (conv_tc_eligible(N, F, H, W, C, 1)) {
+            e = flip_transpose_filters(w, (float *)workspace, F, C, kh, kw, as_stream(stream));
+            if (e) return e;
+            return conv_igemm_tc(dy, (const float *)workspace, nullptr, dx, N, F, oh, ow, C, kh, kw, H, W, kh - 1 - pad_h,
+                                 kw - 1 - pad_w, SN_ACT_LINEAR, accumulate, as_stream(stream));
+        }
+    }
     return conv_dgrad_simt(dy, w, dx, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, accumulate, as_stream(stream));
 }
 
@@ -40,6 +73,19 @@ int sn_conv2d_wgrad(const float *x, const float *dy, float *dw, float *db, int N
     SN_REQUIRE(x && dy && dw, "null tensor");
     int e = check_prec(precision);
     if (e) return e;
+    if (N > 0 && precision == SN_PREC_TF32 && H + 2 * pad_h >= kh && W + 2 * pad_w >= kw) {
+        const int oh = (H + 2 * pad_h - kh) / stride + 1, ow = (W + 2 * pad_w - kw) / stride + 1;
+        if (wgrad_tc_eligible(N, C, oh, ow, F, stride)) {
+            cudaStream_t st = as_stream(stream);
+            if (!accumulate) {
+                SN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)F * kh * kw * C, st));
+                if (db) SN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * F, st));
+            }
+            e = conv_wgrad_tc(x, dy, dw, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, st);
+            if (e || !db) return e;
+            return colsum_accumulate(dy, db, (long long)N * oh * ow, F, st);
+        }
+    }
     return conv_wgrad_simt(x, dy, dw, db, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, accumulate, as_stream(stream));
 }
 
@@ -49,8 +95,8 @@ int sn_dense_fprop(const float *x, const float *w, const float *bias, float *y, 
     return sn_conv2d_fprop(x, w, bias, y, M, K, 1, 1, Nout, 1, 1, 1, 0, 0, act, precision, stream);
 }
 int sn_dense_dgrad(const float *dy, const float *w, float *dx, int M, int K, int Nout, int accumulate, int precision,
-                   void *stream) {
-    return sn_conv2d_dgrad(dy, w, dx, M, K, 1, 1, Nout, 1, 1, 1, 0, 0, accumulate, precision, stream);
+                   void *workspace, void *stream) {
+    return sn_conv2d_dgrad(dy, w, dx, M, K, 1, 1, Nout, 1, 1, 1, 0, 0, accumulate, precision, workspace, stream);
 }
 int sn_dense_wgrad(const float *x, const float *dy, float *dw, float *db, int M, int K, int Nout, int accumulate,
                    int precision, void *stream) {

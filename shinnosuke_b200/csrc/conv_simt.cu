@@ -180,6 +180,8 @@ int conv_geom(ConvP &p, int N, int C, int H, int W, int F, int kh, int kw, int s
 
 namespace sn {
 
+int colsum_accumulate(const float *dy, float *db, long long rows, int F, cudaStream_t st);
+
 int conv_fprop_simt(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F,
                     int kh, int kw, int stride, int ph, int pw, int act, cudaStream_t st) {
     ConvP p{};
@@ -230,16 +232,17 @@ int conv_wgrad_simt(const float *x, const float *dy, float *dw, float *db, int N
     igemm_simt_kernel<WGRAD, false, false><<<grid, 256, 0, st>>>(p);
     e = after_launch("igemm_simt_kernel<WGRAD>");
     if (e) return e;
-    if (db) {
-        long long rows = p.K;
-        int gx = (F + 31) / 32;
-        long long chunks = (rows + 7) / 8, cap = (long long)num_sms() * 4 / gx;
-        if (cap < 1) cap = 1;
-        dim3 g2(gx, (unsigned)(chunks < cap ? chunks : cap));
-        colsum_kernel<<<g2, dim3(32, 8), 0, st>>>(dy, db, rows, F);
-        e = after_launch("colsum_kernel");
-    }
+    if (db) e = colsum_accumulate(dy, db, p.K, F, st);
     return e;
+}
+
+int colsum_accumulate(const float *dy, float *db, long long rows, int F, cudaStream_t st) {
+    int gx = (F + 31) / 32;
+    long long chunks = (rows + 7) / 8, cap = (long long)num_sms() * 4 / gx;
+    if (cap < 1) cap = 1;
+    dim3 g2(gx, (unsigned)(chunks < cap ? chunks : cap));
+    colsum_kernel<<<g2, dim3(32, 8), 0, st>>>(dy, db, rows, F);
+    return after_launch("colsum_kernel");
 }
 
 }  // namespace sn

@@ -1,0 +1,547 @@
+// Tensor-core implicit-GEMM convolution for sm_100a: tcgen05.mma (kind::tf32, fp32 operands read
+// as TF32, fp32 accumulators in TMEM) fed by TMA, no column matrix.
+//
+// fprop / dgrad / Dense forward+dX  ("K-major" kernel, conv_igemm_kernel):
+//     D[p][f] = sum_{tap=(u,v)} sum_{c} X[n, h+u-ph, w+v-pw, c] * Wt[f][tap][c]
+//   * A tile  = 128 output pixels x 32 channels of ONE tap: a 4-D TMA box (32c, tw, th, tn) of the
+//     NHWC map whose start coordinate is shifted by the tap; the halo is TMA's out-of-bounds
+//     zero fill.  Rows land 128 B apart with the 128-byte swizzle = UMMA's K-major layout.
+//   * B tile  = BN filters x 32 contraction elements of the [F][kh*kw*C] filter matrix (2-D box).
+//   * one CTA per SM, persistent over output tiles; warp 0 = TMA producer, warp 1 = MMA issuer,
+//     warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU -> global).  smem ring of STAGES
+//     k-blocks (full/empty mbarriers), two TMEM accumulator buffers so the epilogue of tile i
+//     overlaps the MMAs of tile i+1.
+//   dgrad (stride 1) is the same kernel on dY with the filters flipped and transposed
+//   (flip_transpose_filters_kernel), padding k-1-p.
+//
+// wgrad ("MN-major" kernel, conv_wgrad_kernel):
+//     dW[f][tap][c] += sum_{p} dY[p][f] * X[p shifted by tap][c]
+//   the contraction runs over pixels, the slow index of both operands, so both are MN-major
+//   UMMA operands: A = 4 TMA boxes (32 f x 32 px) of dY, B = C/32 boxes (32 c, tw, th, tn) of X.
+//   Split over pixel ranges across CTAs (the output is tiny), fp32 red.global.add epilogue.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <mutex>
+
+using namespace sn;
+using namespace sn::tc;
+
+namespace sn {
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+int make_tmap_f32(CUtensorMap *out, const void *base, int rank, const long long *dims, const long long *strides_elems,
+                  const int *box) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return SN_ERR_UNSUPPORTED; }
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = (cuuint64_t)dims[i]; bdim[i] = (cuuint32_t)box[i]; estr[i] = 1; }
+    for (int i = 1; i < rank; ++i) gstr[i - 1] = (cuuint64_t)strides_elems[i] * 4;
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bdim, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %lld %lld %lld %lld box %d %d %d %d", (int)r, rank, dims[0],
+                  rank > 1 ? dims[1] : 0, rank > 2 ? dims[2] : 0, rank > 3 ? dims[3] : 0, box[0], rank > 1 ? box[1] : 0,
+                  rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+        return SN_ERR_UNSUPPORTED;
+    }
+    return SN_OK;
+}
+
+}  // namespace sn
+
+namespace {
+
+constexpr int BM = 128;          // output pixels per tile (UMMA M)
+constexpr int BK = 32;           // fp32 contraction elements per k-block = one 128-byte swizzle row
+constexpr int UK = 8;            // UMMA K for kind::tf32
+constexpr int A_BYTES = BM * BK * 4;
+constexpr int NUM_THREADS = 192;
+
+struct IgemmParams {
+    float *out;
+    const float *bias;
+    int rows;              // total output pixels (N * OH * OW)
+    int F;                 // output channels (GEMM N)
+    int taps_w;            // kw
+    int ntaps;             // kh * kw
+    int C;                 // channels per tap (GEMM K per tap)
+    int cblocks;           // ceil(C / 32)
+    int tiles_m, tiles_n;
+    int th, tn;            // box: th rows of tn images (tw = OW always)
+    int bands_per_image;   // OH / th when an image is split into row bands, else 0
+    int pad_h, pad_w;
+    int act, accumulate;
+};
+
+template <int BN> struct IgemmCfg {
+    static constexpr int B_BYTES = BN * BK * 4;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
+    static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;      // power of two >= 32
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
+    using Cfg = IgemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + Cfg::STAGES;
+    uint64_t *tmem_full = empty_bar + Cfg::STAGES;
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int kblocks = p.ntaps * p.cblocks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int tm = tile / p.tiles_n, tn_idx = tile % p.tiles_n;
+                int n0, h0;
+                if (p.bands_per_image) { n0 = tm / p.bands_per_image; h0 = (tm % p.bands_per_image) * p.th; }
+                else { n0 = tm * p.tn; h0 = 0; }
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    const int tap = kb / p.cblocks, cb = kb % p.cblocks;
+                    const int u = tap / p.taps_w, v = tap % p.taps_w;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    uint8_t *sa = smem + stage * Cfg::STAGE_BYTES;
+                    tma_load_4d(sa, &tmA, &full_bar[stage], cb * BK, v - p.pad_w, h0 + u - p.pad_h, n0);
+                    tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], tap * p.C + cb * BK, tn_idx * BN);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(2, BM, BN, 0, 0);
+            int stage = 0; uint32_t phase = 0;
+            int iter = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+                const int acc = iter & 1;
+                mbar_wait(&tmem_empty[acc], ((iter >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t adesc = make_smem_desc(sa, 0, 1024);
+                    const uint64_t bdesc = make_smem_desc(sa + A_BYTES, 0, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k) {
+                        // advancing K inside the 128-byte swizzle row: +32 bytes = +2 descriptor units
+                        mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    mma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                mma_commit(&tmem_full[acc]);                       // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                  // TMEM lane quarter this warp may read
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+            const int tm = tile / p.tiles_n, tn_idx = tile % p.tiles_n;
+            const int acc = iter & 1;
+            mbar_wait(&tmem_full[acc], (iter >> 1) & 1);
+            tc_fence_after();
+            const int row = tm * BM + q * 32 + lane;
+            const bool row_ok = row < p.rows;
+            float *orow = p.out + (long long)row * p.F;
+            constexpr int CHUNK = (BN >= 32) ? 32 : 16;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += CHUNK) {
+                uint32_t r[CHUNK];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
+                if constexpr (CHUNK == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+                tmem_ld_wait();
+                const int f0 = tn_idx * BN + c0;
+                if (row_ok) {
+                    if (f0 + CHUNK <= p.F && (p.F & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < CHUNK; j += 4) {
+                            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                                   __uint_as_float(r[j + 3]));
+                            if (p.bias) {
+                                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + f0 + j));
+                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                            }
+                            if (p.act == SN_ACT_RELU) {
+                                v.x = relu_keep_sign(v.x); v.y = relu_keep_sign(v.y); v.z = relu_keep_sign(v.z); v.w = relu_keep_sign(v.w);
+                            }
+                            float4 *dst = reinterpret_cast<float4 *>(orow + f0 + j);
+                            if (p.accumulate) { float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                            *dst = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CHUNK; ++j) {
+                            const int f = f0 + j;
+                            if (f < p.F) {
+                                float v = __uint_as_float(r[j]);
+                                if (p.bias) v += __ldg(p.bias + f);
+                                if (p.act == SN_ACT_RELU) v = relu_keep_sign(v);
+                                if (p.accumulate) v += orow[f];
+                                orow[f] = v;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// Wt[c][kh-1-u][kw-1-v][f] = W[f][u][v][c]  (dgrad as a forward convolution of dY)
+__global__ void flip_transpose_filters_kernel(const float *__restrict__ w, float *__restrict__ wt, int F, int C, int kh, int kw) {
+    const long long total = (long long)F * kh * kw * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        // i indexes Wt: ((c * kh + u2) * kw + v2) * F + f
+        int f = (int)(i % F);
+        long long t = i / F;
+        int v2 = (int)(t % kw); t /= kw;
+        int u2 = (int)(t % kh);
+        int c = (int)(t / kh);
+        wt[i] = w[(((long long)f * kh + (kh - 1 - u2)) * kw + (kw - 1 - v2)) * C + c];
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// wgrad: dW[f][tap][c] += sum over a pixel range of dY[p][f] * X[p + tap][c]; both operands MN-major.
+constexpr int PB = 32;                   // pixels per k-block (4 UMMA K-steps of 8)
+constexpr int ATOM_BYTES = PB * 128;     // one MN-atom column: 32 pixel rows x 128 B
+constexpr int WG_A_BYTES = 4 * ATOM_BYTES;   // 128 filters
+
+struct WgradParams {
+    float *dw;
+    int F, C, ntaps, taps_w;
+    int c_tiles, f_tiles;      // work items = f_tiles * c_tiles * ntaps
+    int splits, pblocks_per_split, pblocks;
+    int th, tn, S;             // pixel-block box: th rows of tn images; S = OH*OW
+    int OW;
+    int pad_h, pad_w;
+};
+
+template <int CN> struct WgradCfg {
+    static constexpr int B_BYTES = (CN / 32) * ATOM_BYTES;
+    static constexpr int STAGE_BYTES = WG_A_BYTES + B_BYTES;
+    static constexpr int STAGES = (CN <= 64) ? 8 : (CN <= 128 ? 6 : 4);
+    static constexpr int TMEM_COLS = CN < 32 ? 32 : CN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int CN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+    using Cfg = WgradCfg<CN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + Cfg::STAGES;
+    uint64_t *acc_full = empty_bar + Cfg::STAGES;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // work item of this CTA
+    const int split = blockIdx.x % p.splits;
+    int item = blockIdx.x / p.splits;
+    const int tap = item % p.ntaps; item /= p.ntaps;
+    const int ct = item % p.c_tiles;
+    const int ft = item / p.c_tiles;
+    const int pb0 = split * p.pblocks_per_split;
+    const int pb1 = min(p.pblocks, pb0 + p.pblocks_per_split);
+    const int nkb = pb1 - pb0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmDY);
+        tma_prefetch_desc(&tmX);
+        for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (nkb > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                const int u = tap / p.taps_w, v = tap % p.taps_w;
+                int stage = 0; uint32_t phase = 0;
+                for (int pb = pb0; pb < pb1; ++pb) {
+                    const int pix = pb * PB;
+                    int n0, i0;
+                    if (p.S >= PB) { n0 = pix / p.S; i0 = (pix % p.S) / p.OW; }
+                    else { n0 = pix / p.S; i0 = 0; }
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    uint8_t *sa = smem + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+                        tma_load_2d(sa + a * ATOM_BYTES, &tmDY, &full_bar[stage], ft * 128 + a * 32, pix);
+#pragma unroll
+                    for (int b = 0; b < CN / 32; ++b)
+                        tma_load_4d(sa + WG_A_BYTES + b * ATOM_BYTES, &tmX, &full_bar[stage], ct * CN + b * 32, v - p.pad_w,
+                                    i0 + u - p.pad_h, n0);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                constexpr uint32_t idesc = make_idesc(2, 128, CN, 1, 1);      // both operands MN-major
+                int stage = 0; uint32_t phase = 0;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < PB / UK; ++k) {
+                        // K-group k = pixel rows 8k..8k+7 of every atom: +1024 B
+                        const uint64_t adesc = make_smem_desc(sa + k * 1024, ATOM_BYTES, 1024);
+                        const uint64_t bdesc = make_smem_desc(sa + WG_A_BYTES + k * 1024, ATOM_BYTES, 1024);
+                        mma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    mma_commit(&empty_bar[stage]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                mma_commit(acc_full);
+            }
+        } else {
+            const int q = warp & 3;
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+            const int f = ft * 128 + q * 32 + lane;
+            float *row = p.dw + ((long long)f * p.ntaps + tap) * p.C + ct * CN;
+            constexpr int CHUNK = (CN >= 32) ? 32 : 16;
+#pragma unroll 1
+            for (int c0 = 0; c0 < CN; c0 += CHUNK) {
+                uint32_t r[CHUNK];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                if constexpr (CHUNK == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+                tmem_ld_wait();
+                if (f < p.F) {
+#pragma unroll
+                    for (int j = 0; j < CHUNK; ++j)
+                        if (ct * CN + c0 + j < p.C) atomicAdd(row + c0 + j, __uint_as_float(r[j]));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+template <int CN>
+int launch_wgrad(const CUtensorMap &tmDY, const CUtensorMap &tmX, const WgradParams &p, cudaStream_t st) {
+    using Cfg = WgradCfg<CN>;
+    static bool configured = false;
+    if (!configured) {
+        SN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    int grid = p.f_tiles * p.c_tiles * p.ntaps * p.splits;
+    conv_wgrad_kernel<CN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tmDY, tmX, p);
+    return after_launch("conv_wgrad_kernel");
+}
+
+// --------------------------------------------------------------------------------------------
+// Geometry of the 128-pixel tile: full-width boxes (tw = OW), th rows, tn images.
+struct TileGeom { int th, tn, bands_per_image; };
+
+bool tile_geometry(int N, int OH, int OW, TileGeom &g) {
+    if (OW <= 0 || OW > BM || (BM % OW) != 0) return false;
+    const int S = OH * OW;
+    if (S >= BM) {
+        g.th = BM / OW;
+        if (OH % g.th) return false;
+        g.tn = 1;
+        g.bands_per_image = OH / g.th;
+    } else {
+        if (BM % S) return false;
+        g.th = OH;
+        g.tn = BM / S;
+        g.bands_per_image = 0;
+        if (g.tn > 256) return false;
+    }
+    return g.th <= 256;
+}
+
+template <int BN>
+int launch_igemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const IgemmParams &p, cudaStream_t st) {
+    using Cfg = IgemmCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        SN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    int tiles = p.tiles_m * p.tiles_n;
+    int grid = tiles < num_sms() ? tiles : num_sms();
+    conv_igemm_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+    return after_launch("conv_igemm_kernel");
+}
+
+}  // namespace
+
+namespace sn {
+
+// Can the tensor-core path take this forward-style convolution (stride 1)?
+bool conv_tc_eligible(int N, int C, int OH, int OW, int F, int stride) {
+    TileGeom g;
+    if (stride != 1 || (C & 3) || C < 8) return false;
+    if (!tile_geometry(N, OH, OW, g)) return false;
+    long long flops = 2ll * N * OH * OW * F * C;
+    return flops >= (1ll << 22);            // tiny problems stay on the CUDA-core kernel (launch-latency bound anyway)
+}
+
+// x: NHWC (N, IH, IW, C); w: [F][kh*kw][C]; out: (N*OH*OW, F).
+int conv_igemm_tc(const float *x, const float *w, const float *bias, float *out, int N, int C, int IH, int IW, int F, int kh,
+                  int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, cudaStream_t st) {
+    TileGeom g;
+    if (!tile_geometry(N, OH, OW, g)) { set_error("conv_igemm_tc: unsupported output geometry %dx%d", OH, OW); return SN_ERR_UNSUPPORTED; }
+    if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)out) & 15) { set_error("conv_igemm_tc: tensors must be 16-byte aligned"); return SN_ERR_INVALID_ARG; }
+    const int BN = F > 128 ? 256 : (F > 64 ? 128 : (F > 32 ? 64 : (F > 16 ? 32 : 16)));
+    CUtensorMap tmA, tmB;
+    long long adims[4] = {C, IW, IH, N};
+    long long astr[4] = {1, C, (long long)IW * C, (long long)IH * IW * C};
+    int abox[4] = {BK, OW, g.th, g.tn};
+    int e = make_tmap_f32(&tmA, x, 4, adims, astr, abox);
+    if (e) return e;
+    long long ktot = (long long)kh * kw * C;
+    long long bdims[2] = {ktot, F};
+    long long bstr[2] = {1, ktot};
+    int bbox[2] = {BK, BN > 256 ? 256 : BN};
+    e = make_tmap_f32(&tmB, w, 2, bdims, bstr, bbox);
+    if (e) return e;
+    IgemmParams p{};
+    p.out = out; p.bias = bias; p.rows = N * OH * OW; p.F = F; p.taps_w = kw; p.ntaps = kh * kw; p.C = C;
+    p.cblocks = (C + BK - 1) / BK;
+    p.tiles_m = (p.rows + BM - 1) / BM; p.tiles_n = (F + BN - 1) / BN;
+    p.th = g.th; p.tn = g.tn; p.bands_per_image = g.bands_per_image;
+    p.pad_h = pad_h; p.pad_w = pad_w; p.act = act; p.accumulate = accumulate;
+    switch (BN) {
+        case 16: return launch_igemm<16>(tmA, tmB, p, st);
+        case 32: return launch_igemm<32>(tmA, tmB, p, st);
+        case 64: return launch_igemm<64>(tmA, tmB, p, st);
+        case 128: return launch_igemm<128>(tmA, tmB, p, st);
+        default: return launch_igemm<256>(tmA, tmB, p, st);
+    }
+}
+
+bool wgrad_tc_eligible(int N, int C, int OH, int OW, int F, int stride) {
+    if (stride != 1 || (C & 31) || (F & 3)) return false;
+    if (OW <= 0 || OW > PB || (PB % OW)) return false;
+    const int S = OH * OW;
+    if (S >= PB ? (S % PB) != 0 : (PB % S) != 0) return false;
+    long long flops = 2ll * N * OH * OW * F * C;
+    return flops >= (1ll << 24);
+}
+
+// x: NHWC (N, IH, IW, C); dy: (N*OH*OW, F); dw: [F][kh*kw][C], accumulated into (+=).
+int conv_wgrad_tc(const float *x, const float *dy, float *dw, int N, int C, int IH, int IW, int F, int kh, int kw, int OH,
+                  int OW, int pad_h, int pad_w, cudaStream_t st) {
+    if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) { set_error("conv_wgrad_tc: tensors must be 16-byte aligned"); return SN_ERR_INVALID_ARG; }
+    const int S = OH * OW;
+    const long long P = (long long)N * S;
+    const int CN = (C % 256 == 0) ? 256 : ((C % 128 == 0) ? 128 : ((C % 64 == 0) ? 64 : 32));
+    WgradParams p{};
+    p.dw = dw; p.F = F; p.C = C; p.ntaps = kh * kw; p.taps_w = kw;
+    p.c_tiles = C / CN; p.f_tiles = (F + 127) / 128;
+    p.pblocks = (int)((P + PB - 1) / PB);
+    int items = p.f_tiles * p.c_tiles * p.ntaps;
+    int splits = num_sms() / items;
+    if (splits < 1) splits = 1;
+    if (splits > p.pblocks) splits = p.pblocks;
+    p.pblocks_per_split = (p.pblocks + splits - 1) / splits;
+    p.splits = (p.pblocks + p.pblocks_per_split - 1) / p.pblocks_per_split;
+    p.S = S; p.OW = OW;
+    if (S >= PB) { p.th = PB / OW; p.tn = 1; } else { p.th = OH; p.tn = PB / S; }
+    p.pad_h = pad_h; p.pad_w = pad_w;
+    CUtensorMap tmDY, tmX;
+    long long ddims[2] = {F, P};
+    long long dstr[2] = {1, F};
+    int dbox[2] = {32, PB};
+    int e = make_tmap_f32(&tmDY, dy, 2, ddims, dstr, dbox);
+    if (e) return e;
+    long long xdims[4] = {C, IW, IH, N};
+    long long xstr[4] = {1, C, (long long)IW * C, (long long)IH * IW * C};
+    int xbox[4] = {32, OW, p.th, p.tn};
+    e = make_tmap_f32(&tmX, x, 4, xdims, xstr, xbox);
+    if (e) return e;
+    switch (CN) {
+        case 32: return launch_wgrad<32>(tmDY, tmX, p, st);
+        case 64: return launch_wgrad<64>(tmDY, tmX, p, st);
+        case 128: return launch_wgrad<128>(tmDY, tmX, p, st);
+        default: return launch_wgrad<256>(tmDY, tmX, p, st);
+    }
+}
+
+int flip_transpose_filters(const float *w, float *wt, int F, int C, int kh, int kw, cudaStream_t st) {
+    long long total = (long long)F * kh * kw * C;
+    flip_transpose_filters_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, wt, F, C, kh, kw);
+    return after_launch("flip_transpose_filters_kernel");
+}
+
+}  // namespace sn

@@ -109,9 +109,11 @@ class Conv2D(Layer):
         if W.require_grads or b.require_grads:
             lib.sn_conv2d_wgrad(x.ptr, g.ptr, W.grads.ptr, b.grads.ptr if b.require_grads else None,
                                 *geom, 1, prec, st)
+        ws_bytes = lib.sn_conv2d_dgrad_workspace(C, F, kh, kw, prec)
+        ws = self._buf('dgrad_ws', (ws_bytes // 4,), 'flat').ptr if ws_bytes else None
         for layer in self.inbounds:
             self._push_grad(layer, lambda dst, acc: lib.sn_conv2d_dgrad(
-                g.ptr, W.output_tensor.ptr, dst.ptr, *geom, acc, prec, st))
+                g.ptr, W.output_tensor.ptr, dst.ptr, *geom, acc, prec, ws, st))
 
 
 class ZeroPadding2D(Layer):

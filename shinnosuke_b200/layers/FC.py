@@ -144,6 +144,8 @@ class Dense(Layer):
         if W.require_grads or b.require_grads:
             lib.sn_dense_wgrad(x.ptr, g.ptr, W.grads.ptr, b.grads.ptr if b.require_grads else None,
                                M, K, self.n_out, 1, prec, st)
+        ws_bytes = lib.sn_conv2d_dgrad_workspace(K, self.n_out, 1, 1, prec)
+        ws = self._buf('dgrad_ws', (ws_bytes // 4,), 'flat').ptr if ws_bytes else None
         for layer in self.inbounds:
             self._push_grad(layer, lambda dst, acc: lib.sn_dense_dgrad(
-                g.ptr, W.output_tensor.ptr, dst.ptr, M, K, self.n_out, acc, prec, st))
+                g.ptr, W.output_tensor.ptr, dst.ptr, M, K, self.n_out, acc, prec, ws, st))

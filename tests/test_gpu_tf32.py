@@ -1,0 +1,140 @@
+"""-m gpu: the tensor-core tier (precision='tf32': tcgen05.mma kind::tf32, fp32 storage, fp32 TMEM
+accumulators) against the float64 oracle.
+
+Tolerance: single-pass TF32 keeps 10 explicit mantissa bits of each operand (the tensor core reads
+the fp32 word and drops the low 13 bits), i.e. ~1e-3 relative per product, ~3e-4 after
+accumulation over K = 27..2304 (measured by emulation).  The stated bound
+for this tier is TOL_TF32 = 2e-3 (max|a-r| / max|r| per tensor); the 1e-5 tier is precision='fp32'.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_err
+from gpu_helpers import set_params
+from oracle import shinnosuke_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL_TF32 = 2e-3
+
+
+def _run_conv(shape, precision='tf32'):
+    from shinnosuke_b200 import Conv2D, Input, Activation
+    from shinnosuke_b200.device import as_device
+    N, C, H, W, F, k, stride, padding, act = shape
+    r = np.random.default_rng(abs(hash(shape)) % 2**32)
+    x = r.standard_normal((N, C, H, W)).astype(np.float32).astype(np.float64)
+    w = (0.1 * r.standard_normal((F, C, k, k))).astype(np.float32).astype(np.float64)
+    b = r.standard_normal((1, F)).astype(np.float32).astype(np.float64)
+    (_, _, oh, ow), pad = O.conv_output_shape((N, C, H, W), F, (k, k), stride, padding)
+    gup = r.standard_normal((N, F, oh, ow)).astype(np.float32).astype(np.float64)
+    y_ref, cache = O.conv2d_forward(x, w, b, stride, pad, act)
+    dx_ref, dw_ref, db_ref = O.conv2d_backward(gup, cache)
+    layer = Conv2D(F, (k, k), stride=stride, padding=padding, activation=act)
+    inp = Input((None, C, H, W)); src = Activation('linear')(inp); layer(src)
+    layer.precision = precision
+    set_params(layer, w, b)
+    inp.input_tensor = x
+    for l in (inp, src, layer):
+        l.forward(True)
+    y = np.asarray(layer.output_tensor)
+    layer._seed_grads(as_device(gup)); layer.backward()
+    return dict(y=(y, y_ref), dw=(np.asarray(layer.variables[0].grads), dw_ref),
+                db=(np.asarray(layer.variables[1].grads).reshape(-1), db_ref), dx=(np.asarray(src.grads), dx_ref))
+
+
+@pytest.mark.parametrize('shape', [
+    (4, 64, 16, 16, 128, 3, 1, 'SAME', 'relu'),      # cfg3 conv2: image split into row bands (tw=16, th=8)
+    (6, 128, 8, 8, 256, 3, 1, 'SAME', 'relu'),       # cfg3 conv3: 2 images per tile, 2 filter tiles... N not a multiple of tn
+    (24, 256, 4, 4, 256, 3, 1, 'SAME', 'linear'),    # cfg3 conv4: 8 images per tile
+    (2, 64, 32, 32, 64, 3, 1, 'SAME', 'relu'),       # cfg4 res64 (tw=32, th=4)
+    (3, 32, 16, 16, 48, 3, 1, 'SAME', 'linear'),     # F not a power of two (masked filter tile), ragged pixel tiles
+    (2, 48, 8, 8, 64, 1, 1, 'VALID', 'relu'),        # 1x1, C not a multiple of 32 (zero-filled k-block tail)
+    (5, 64, 8, 8, 96, 5, 1, 'SAME', 'linear'),       # 5x5 taps
+    (2, 64, 18, 18, 64, 3, 1, 'VALID', 'relu'),      # VALID 18->16 (power-of-two output, non-power-of-two input)
+])
+def test_conv2d_tf32_vs_oracle(shape):
+    out = _run_conv(shape)
+    for name, (got, ref) in out.items():
+        assert rel_err(got, ref) < TOL_TF32, name
+    # the same layer on the fp32 tier must still meet 1e-5 (dispatch sanity)
+    out32 = _run_conv(shape, 'fp32')
+    for name, (got, ref) in out32.items():
+        assert rel_err(got, ref) < 1e-5, name
+
+
+def test_tf32_path_is_really_taken_and_exact_on_tf32_representable_data():
+    """Inputs with <= 10 mantissa bits make single-pass TF32 products exact, so the tensor-core
+    result must match the oracle to fp32 accumulation accuracy — a much sharper check of the
+    TMA halo / descriptor / tile indexing than the 2e-3 bound."""
+    from shinnosuke_b200 import Conv2D, Input, Activation
+    from shinnosuke_b200.device import as_device
+    from shinnosuke_b200._lib import lib
+    r = np.random.default_rng(7)
+    N, C, H, W, F = 4, 64, 16, 16, 128
+    x = r.integers(-8, 9, (N, C, H, W)).astype(np.float64) / 8.0
+    w = r.integers(-8, 9, (F, C, 3, 3)).astype(np.float64) / 16.0
+    b = r.integers(-4, 5, (1, F)).astype(np.float64)
+    gup = r.integers(-8, 9, (N, F, H, W)).astype(np.float64) / 4.0
+    y_ref, cache = O.conv2d_forward(x, w, b, 1, (1, 1), 'relu')
+    dx_ref, dw_ref, db_ref = O.conv2d_backward(gup, cache)
+    layer = Conv2D(F, (3, 3), padding='SAME', activation='relu')
+    inp = Input((None, C, H, W)); src = Activation('linear')(inp); layer(src)
+    layer.precision = 'tf32'
+    set_params(layer, w, b)
+    inp.input_tensor = x
+    for l in (inp, src, layer):
+        l.forward(True)
+    assert rel_err(np.asarray(layer.output_tensor), y_ref) < 1e-6
+    layer._seed_grads(as_device(gup)); layer.backward()
+    assert rel_err(np.asarray(layer.variables[0].grads), dw_ref) < 1e-6
+    assert rel_err(np.asarray(src.grads), dx_ref) < 1e-6
+    assert rel_err(np.asarray(layer.variables[1].grads).reshape(-1), db_ref) < 1e-6
+
+
+@pytest.mark.parametrize('mkn', [(512, 1024, 10), (128, 784, 500), (256, 512, 256), (130, 72, 66)])
+def test_dense_tf32_vs_oracle(mkn):
+    from shinnosuke_b200 import Dense, Input, Activation
+    from shinnosuke_b200.device import as_device
+    M, K, Nout = mkn
+    r = np.random.default_rng(M + K)
+    x = r.standard_normal((M, K)).astype(np.float32).astype(np.float64)
+    w = (0.1 * r.standard_normal((K, Nout))).astype(np.float32).astype(np.float64)
+    b = r.standard_normal((1, Nout)).astype(np.float32).astype(np.float64)
+    gup = r.standard_normal((M, Nout)).astype(np.float32).astype(np.float64)
+    y_ref, cache = O.dense_forward(x, w, b, 'relu')
+    dx_ref, dw_ref, db_ref = O.dense_backward(gup, cache)
+    layer = Dense(Nout, activation='relu')
+    inp = Input((None, K)); src = Activation('linear')(inp); layer(src)
+    layer.precision = 'tf32'
+    set_params(layer, w, b)
+    inp.input_tensor = x
+    for l in (inp, src, layer):
+        l.forward(True)
+    assert rel_err(np.asarray(layer.output_tensor), y_ref) < TOL_TF32
+    layer._seed_grads(as_device(gup)); layer.backward()
+    assert rel_err(np.asarray(layer.variables[0].grads), dw_ref) < TOL_TF32
+    assert rel_err(np.asarray(layer.variables[1].grads), db_ref) < TOL_TF32
+    assert rel_err(np.asarray(src.grads), dx_ref) < TOL_TF32
+
+
+def test_trajectory_cfg3_tf32():
+    """Config 3, full widths, batch 16, 2 steps on the tensor-core tier vs the float64 oracle."""
+    from test_gpu_train import _vgg, _data
+    r, X = _data((32, 3, 32, 32), kind='normal')
+    Y = O.to_categorical(np.concatenate([np.arange(10), r.integers(0, 10, 22)]))
+    np.random.seed(0)
+    spec, ishape = O.spec_cfg3()
+    net = O.OracleNet(spec, ishape)
+    net.fit(X, Y, 16, 1, shuffle=False)
+    m = _vgg('tf32')
+    m.fit(X, Y, batch_size=16, epochs=1, shuffle=False, validation_ratio=0., verbose=0)
+    assert np.allclose(m.train_loss, net.train_loss, rtol=2e-2)      # loss after ~10 TF32 layers
+    convs = [l for l in m.layers if l.__class__.__name__ == 'Conv2D']
+    assert rel_err(np.asarray(convs[1].variables[0].output_tensor), net.params[4]) < TOL_TF32
+
+
+def test_bf16_tier_is_reported_as_not_built():
+    from shinnosuke_b200 import Sequential, Dense
+    m = Sequential([Dense(4, n_in=8)])
+    with pytest.raises(ValueError):
+        m.compile('sgd', 'sparse_categorical_crossentropy', precision='bf16')
