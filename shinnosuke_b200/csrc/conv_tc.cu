@@ -17,7 +17,8 @@
 // wgrad ("MN-major" kernel, conv_wgrad_kernel):
 //     dW[f][tap][c] += sum_{p} dY[p][f] * X[p shifted by tap][c]
 //   the contraction runs over pixels, the slow index of both operands, so both are MN-major
-//   UMMA operands: A = 4 TMA boxes (32 f x 32 px) of dY, B = C/32 boxes (32 c, tw, th, tn) of X.
+//   UMMA operands: A = 4 TMA boxes (32 f x 32 px) of dY, B = C/32 boxes (32 c, tw, th, tn) of X,
+//   in the 128B-swizzle-with-32B-atoms layout that fp32 MN-major operands require.
 //   Split over pixel ranges across CTAs (the output is tiny), fp32 red.global.add epilogue.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -42,7 +43,7 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 int make_tmap_f32(CUtensorMap *out, const void *base, int rank, const long long *dims, const long long *strides_elems,
-                  const int *box) {
+                  const int *box, bool atom32b) {
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return SN_ERR_UNSUPPORTED; }
     cuuint64_t gdim[5], gstr[5];
@@ -50,7 +51,8 @@ int make_tmap_f32(CUtensorMap *out, const void *base, int rank, const long long 
     for (int i = 0; i < rank; ++i) { gdim[i] = (cuuint64_t)dims[i]; bdim[i] = (cuuint32_t)box[i]; estr[i] = 1; }
     for (int i = 1; i < rank; ++i) gstr[i - 1] = (cuuint64_t)strides_elems[i] * 4;
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bdim, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %lld %lld %lld %lld box %d %d %d %d", (int)r, rank, dims[0],
@@ -354,9 +356,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < PB / UK; ++k) {
-                        // K-group k = pixel rows 8k..8k+7 of every atom: +1024 B
-                        const uint64_t adesc = make_smem_desc(sa + k * 1024, ATOM_BYTES, 1024);
-                        const uint64_t bdesc = make_smem_desc(sa + WG_A_BYTES + k * 1024, ATOM_BYTES, 1024);
+                        // UMMA K-step k = pixel rows 8k..8k+7 of every atom column (+1024 B) = two 4-row
+                        // K groups 512 B apart (SBO); atom columns of 32 f / 32 c are ATOM_BYTES apart (LBO)
+                        const uint64_t adesc = make_smem_desc(sa + k * 1024, ATOM_BYTES, 512, LAYOUT_SW128_BASE32B);
+                        const uint64_t bdesc = make_smem_desc(sa + WG_A_BYTES + k * 1024, ATOM_BYTES, 512, LAYOUT_SW128_BASE32B);
                         mma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     mma_commit(&empty_bar[stage]);
@@ -523,12 +526,12 @@ int conv_wgrad_tc(const float *x, const float *dy, float *dw, int N, int C, int 
     long long ddims[2] = {F, P};
     long long dstr[2] = {1, F};
     int dbox[2] = {32, PB};
-    int e = make_tmap_f32(&tmDY, dy, 2, ddims, dstr, dbox);
+    int e = make_tmap_f32(&tmDY, dy, 2, ddims, dstr, dbox, true);
     if (e) return e;
     long long xdims[4] = {C, IW, IH, N};
     long long xstr[4] = {1, C, (long long)IW * C, (long long)IH * IW * C};
     int xbox[4] = {32, OW, p.th, p.tn};
-    e = make_tmap_f32(&tmX, x, 4, xdims, xstr, xbox);
+    e = make_tmap_f32(&tmX, x, 4, xdims, xstr, xbox, true);
     if (e) return e;
     switch (CN) {
         case 32: return launch_wgrad<32>(tmDY, tmX, p, st);

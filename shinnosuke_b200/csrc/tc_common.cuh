@@ -127,13 +127,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   K-major  (rows of 128 B along K): SBO = stride between 8-row groups (1024 B when dense), LBO unused.
 //   MN-major (rows of 128 B along M/N, 8 K-rows per atom): LBO = stride between 128-byte-wide
 //            atoms along M/N, SBO = stride between 8-row K groups.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   fp32/tf32 MN-major operands must use the "128-byte swizzle with 32-byte atoms" (layout type 1,
+//   TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): K groups are 4 rows of 128 B, SBO = stride between them.
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = LAYOUT_SW128) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 
@@ -153,6 +157,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 EncodeTiledFn get_encode_tiled();
 // fp32 tensor, rank <= 4, dims fastest-first, strides in ELEMENTS for dims 1..rank-1, 128-byte swizzle.
 int make_tmap_f32(CUtensorMap *out, const void *base, int rank, const long long *dims, const long long *strides_elems,
-                  const int *box);
+                  const int *box, bool atom32b = false);
 
 }  // namespace sn
