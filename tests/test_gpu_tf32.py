@@ -28,7 +28,6 @@ def _run_conv(shape, precision='tf32'):
     (_, _, oh, ow), pad = O.conv_output_shape((N, C, H, W), F, (k, k), stride, padding)
     gup = r.standard_normal((N, F, oh, ow)).astype(np.float32).astype(np.float64)
     y_ref, cache = O.conv2d_forward(x, w, b, stride, pad, act)
-    dx_ref, dw_ref, db_ref = O.conv2d_backward(gup, cache)
     layer = Conv2D(F, (k, k), stride=stride, padding=padding, activation=act)
     inp = Input((None, C, H, W)); src = Activation('linear')(inp); layer(src)
     layer.precision = precision
@@ -37,6 +36,17 @@ def _run_conv(shape, precision='tf32'):
     for l in (inp, src, layer):
         l.forward(True)
     y = np.asarray(layer.output_tensor)
+    if act == 'relu':
+        # ReLU is discontinuous: a pre-activation within TF32 rounding of zero may land on the other
+        # side of the kink, which flips one mask bit and moves dW by a whole |g*x| term.  That is a
+        # property of ANY reduced-precision forward, not of the backward kernels, so the backward
+        # reference uses the mask the device forward actually produced (sign bit of y, the -0.0
+        # convention) and the number of flipped bits is bounded separately.
+        blocked = np.signbit(y)
+        flips = np.count_nonzero(blocked != (cache['z'] < 0))
+        assert flips <= 2e-3 * y.size, flips
+        cache['z'] = np.where(blocked, -1.0, 1.0)
+    dx_ref, dw_ref, db_ref = O.conv2d_backward(gup, cache)
     layer._seed_grads(as_device(gup)); layer.backward()
     return dict(y=(y, y_ref), dw=(np.asarray(layer.variables[0].grads), dw_ref),
                 db=(np.asarray(layer.variables[1].grads).reshape(-1), db_ref), dx=(np.asarray(src.grads), dx_ref))
@@ -102,7 +112,6 @@ def test_dense_tf32_vs_oracle(mkn):
     b = r.standard_normal((1, Nout)).astype(np.float32).astype(np.float64)
     gup = r.standard_normal((M, Nout)).astype(np.float32).astype(np.float64)
     y_ref, cache = O.dense_forward(x, w, b, 'relu')
-    dx_ref, dw_ref, db_ref = O.dense_backward(gup, cache)
     layer = Dense(Nout, activation='relu')
     inp = Input((None, K)); src = Activation('linear')(inp); layer(src)
     layer.precision = 'tf32'
@@ -110,7 +119,10 @@ def test_dense_tf32_vs_oracle(mkn):
     inp.input_tensor = x
     for l in (inp, src, layer):
         l.forward(True)
-    assert rel_err(np.asarray(layer.output_tensor), y_ref) < TOL_TF32
+    y = np.asarray(layer.output_tensor)
+    assert rel_err(y, y_ref) < TOL_TF32
+    cache['z'] = np.where(np.signbit(y), -1.0, 1.0)       # device mask, see _run_conv
+    dx_ref, dw_ref, db_ref = O.dense_backward(gup, cache)
     layer._seed_grads(as_device(gup)); layer.backward()
     assert rel_err(np.asarray(layer.variables[0].grads), dw_ref) < TOL_TF32
     assert rel_err(np.asarray(layer.variables[1].grads), db_ref) < TOL_TF32
