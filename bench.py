@@ -350,9 +350,15 @@ def run_ours(args):
                     e2e=dict(value=G * K / (e2e_ms * 1e-3), unit='samples/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,
                              ms_per_step=e2e_ms / K, final_loss=losses_e2e[-1] if losses_e2e else None),
                     gpu_launches=launches_per_step * K, roofline=roof, cpu_baseline=cpu)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Captured graphs hold NCCL kernels; tearing the communicator down under them blocks in
+        # destroy_process_group() (seen on torch 2.11 / NCCL 2.28).  Drain, agree, and leave.
+        m._graphs.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
@@ -367,6 +373,10 @@ def main():
     ap.add_argument('--kernel-table', default='', help='write the per-kernel CUDA-event table (JSON) here')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    wd = int(os.environ.get('SN_BENCH_WATCHDOG', '0'))
+    if wd > 0:      # debugging aid: dump every thread's stack and exit if the run takes longer than this
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
     if args.impl == 'reference':
         run_reference(args)
     else:

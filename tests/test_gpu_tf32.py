@@ -142,7 +142,11 @@ def test_trajectory_cfg3_tf32():
     m.fit(X, Y, batch_size=16, epochs=1, shuffle=False, validation_ratio=0., verbose=0)
     assert np.allclose(m.train_loss, net.train_loss, rtol=2e-2)      # loss after ~10 TF32 layers
     convs = [l for l in m.layers if l.__class__.__name__ == 'Conv2D']
-    assert rel_err(np.asarray(convs[1].variables[0].output_tensor), net.params[4]) < TOL_TF32
+    # Trajectory-level bound, NOT the op-level TOL_TF32: on a random-init net ~1e-3 of the ReLU
+    # masks sit within TF32 rounding of the kink; a weight gradient is a random-sign sum over P
+    # pixels, so flipping a fraction q of its terms moves it by ~sqrt(q) ~ 3 % (measured 2.1 %).
+    # Op-level parity with the device's own mask is asserted in test_conv2d_tf32_vs_oracle.
+    assert rel_err(np.asarray(convs[1].variables[0].output_tensor), net.params[4]) < 5e-2
 
 
 def test_bf16_tier_is_reported_as_not_built():
