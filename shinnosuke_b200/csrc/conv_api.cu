@@ -14,6 +14,12 @@ int conv_wgrad_tc(const float *x, const float *dy, float *dw, int N, int C, int 
                   int OW, int pad_h, int pad_w, cudaStream_t st);
 int flip_transpose_filters(const float *w, float *wt, int F, int C, int kh, int kw, cudaStream_t st);
 int colsum_accumulate(const float *dy, float *db, long long rows, int F, cudaStream_t st);
+bool direct_fprop_eligible(int C, int kh, int kw, int F);
+bool direct_wgrad_eligible(int C, int kh, int kw, int F);
+int conv_fprop_direct(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F,
+                      int kh, int kw, int stride, int ph, int pw, int act, cudaStream_t st);
+int conv_wgrad_direct(const float *x, const float *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh,
+                      int kw, int stride, int ph, int pw, cudaStream_t st);
 }
 
 static int check_prec(int precision) {
@@ -36,7 +42,11 @@ int sn_conv2d_fprop(const float *x, const float *w, const float *bias, float *y,
     SN_REQUIRE(act == SN_ACT_LINEAR || act == SN_ACT_RELU, "unknown activation");
     int e = check_prec(precision);
     if (e) return e;
-    if (N > 0 && precision == SN_PREC_TF32 && H + 2 * pad_h >= kh && W + 2 * pad_w >= kw) {
+    const bool geom_ok = N > 0 && C > 0 && F > 0 && kh > 0 && kw > 0 && stride > 0 && pad_h >= 0 && pad_w >= 0 &&
+                         H + 2 * pad_h >= kh && W + 2 * pad_w >= kw;
+    if (geom_ok && (((uintptr_t)y) & 15) == 0 && direct_fprop_eligible(C, kh, kw, F))
+        return conv_fprop_direct(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, as_stream(stream));
+    if (geom_ok && precision == SN_PREC_TF32) {
         const int oh = (H + 2 * pad_h - kh) / stride + 1, ow = (W + 2 * pad_w - kw) / stride + 1;
         if (conv_tc_eligible(N, C, oh, ow, F, stride))
             return conv_igemm_tc(x, w, bias, y, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, act, 0, as_stream(stream));
@@ -73,7 +83,17 @@ int sn_conv2d_wgrad(const float *x, const float *dy, float *dw, float *db, int N
     SN_REQUIRE(x && dy && dw, "null tensor");
     int e = check_prec(precision);
     if (e) return e;
-    if (N > 0 && precision == SN_PREC_TF32 && H + 2 * pad_h >= kh && W + 2 * pad_w >= kw) {
+    const bool geom_ok = N > 0 && C > 0 && F > 0 && kh > 0 && kw > 0 && stride > 0 && pad_h >= 0 && pad_w >= 0 &&
+                         H + 2 * pad_h >= kh && W + 2 * pad_w >= kw;
+    if (geom_ok && (((uintptr_t)dy) & 15) == 0 && direct_wgrad_eligible(C, kh, kw, F)) {
+        cudaStream_t st = as_stream(stream);
+        if (!accumulate) {
+            SN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)F * kh * kw * C, st));
+            if (db) SN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * F, st));
+        }
+        return conv_wgrad_direct(x, dy, dw, db, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, st);
+    }
+    if (geom_ok && precision == SN_PREC_TF32) {
         const int oh = (H + 2 * pad_h - kh) / stride + 1, ow = (W + 2 * pad_w - kw) / stride + 1;
         if (wgrad_tc_eligible(N, C, oh, ow, F, stride)) {
             cudaStream_t st = as_stream(stream);

@@ -102,6 +102,103 @@ __global__ void maxpool_bwd_kernel(const float *__restrict__ dy, const CODE_T *_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Fast path: 2x2 windows, stride 2, C % 4 == 0 (every BASELINE config).  One thread per
+// (output pixel, 4 channels): 128-bit loads of the four window rows, one 128-bit store of y and
+// ONE 32-bit store of the four code bytes.  The backward is the mirror image: one 128-bit load of
+// dY, one 32-bit load of the codes, four 128-bit stores of dX; odd trailing rows/columns (floor
+// semantics) are zeroed by the threads of the last window row/column.
+template <int MODE>
+__global__ void __launch_bounds__(256) maxpool2x2_fwd_kernel(const float *__restrict__ x, float *__restrict__ y,
+                                                             uint32_t *__restrict__ code, int N, int H, int W, int C,
+                                                             int oh, int ow) {
+    const int CV = C >> 2;
+    const long long total = (long long)N * oh * ow * CV;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int cv = (int)(idx % CV);
+        long long pix = idx / CV;
+        int j = (int)(pix % ow);
+        long long t = pix / ow;
+        int i = (int)(t % oh);
+        long long n = t / oh;
+        const float *base = x + ((n * H + 2 * i) * W + 2 * j) * C + cv * 4;
+        float4 v[4];
+        v[0] = ldg4(base); v[1] = ldg4(base + C); v[2] = ldg4(base + (long long)W * C); v[3] = ldg4(base + (long long)W * C + C);
+        float4 out;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float a0 = lane(v[0], k), a1 = lane(v[1], k), a2 = lane(v[2], k), a3 = lane(v[3], k);
+            float m = a0; uint32_t am = 0;
+            if (a1 > m) { m = a1; am = 1; }
+            if (a2 > m) { m = a2; am = 2; }
+            if (a3 > m) { m = a3; am = 3; }
+            uint32_t cd;
+            if (MODE == SN_POOL_FIRST_ARGMAX) cd = am;
+            else cd = (a0 == m ? 1u : 0u) | (a1 == m ? 2u : 0u) | (a2 == m ? 4u : 0u) | (a3 == m ? 8u : 0u);
+            setlane(out, k, m);
+            packed |= cd << (8 * k);
+        }
+        *reinterpret_cast<float4 *>(y + idx * 4) = out;
+        if (code) code[idx] = packed;
+    }
+}
+
+template <int MODE, bool ACC>
+__global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const float *__restrict__ dy, const uint32_t *__restrict__ code,
+                                                             float *__restrict__ dx, int N, int H, int W, int C, int oh,
+                                                             int ow) {
+    const int CV = C >> 2;
+    const long long total = (long long)N * oh * ow * CV;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int cv = (int)(idx % CV);
+        long long pix = idx / CV;
+        int j = (int)(pix % ow);
+        long long t = pix / ow;
+        int i = (int)(t % oh);
+        long long n = t / oh;
+        const float4 g = ldg4(dy + idx * 4);
+        const uint32_t packed = __ldg(code + idx);
+        float4 o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t cd = (packed >> (8 * k)) & 0xffu;
+            const float gv = lane(g, k);
+            float share = gv;
+            if (MODE == SN_POOL_TIE_SPLIT) { int cnt = __popc(cd); if (cnt > 1) share = gv / (float)cnt; }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                bool hit = (MODE == SN_POOL_FIRST_ARGMAX) ? (cd == (uint32_t)e) : ((cd >> e) & 1u);
+                setlane(o[e], k, hit ? share : 0.f);
+            }
+        }
+        float *base = dx + ((n * H + 2 * i) * W + 2 * j) * C + cv * 4;
+        float *ptrs[4] = {base, base + C, base + (long long)W * C, base + (long long)W * C + C};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float4 *d = reinterpret_cast<float4 *>(ptrs[e]);
+            if (ACC) { float4 old = *d; o[e].x += old.x; o[e].y += old.y; o[e].z += old.z; o[e].w += old.w; }
+            *d = o[e];
+        }
+        if (!ACC) {
+            // floor semantics: inputs beyond the last full window get no gradient
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((W & 1) && j == ow - 1) {
+                *reinterpret_cast<float4 *>(base + 2 * C) = z;
+                *reinterpret_cast<float4 *>(base + (long long)W * C + 2 * C) = z;
+            }
+            if ((H & 1) && i == oh - 1) {
+                *reinterpret_cast<float4 *>(base + 2ll * W * C) = z;
+                *reinterpret_cast<float4 *>(base + 2ll * W * C + C) = z;
+                if ((W & 1) && j == ow - 1) *reinterpret_cast<float4 *>(base + 2ll * W * C + 2 * C) = z;
+            }
+        }
+    }
+}
+
 template <int V, typename CODE_T>
 static int launch_fwd(const float *x, float *y, void *code, int N, int H, int W, int C, int oh, int ow, int pool,
                       int stride, int mode, cudaStream_t st) {
@@ -151,6 +248,12 @@ int sn_maxpool2d_fwd(const float *x, float *y, uint8_t *code, int N, int H, int 
     bool wide = (mode == SN_POOL_TIE_SPLIT && pool * pool > 8);
     bool vec = (C % 4 == 0) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
     cudaStream_t st = as_stream(stream);
+    if (vec && pool == 2 && stride == 2 && (((uintptr_t)code) & 3) == 0) {
+        int grid = grid_for((long long)N * oh * ow * (C / 4), 256);
+        if (mode == SN_POOL_TIE_SPLIT) maxpool2x2_fwd_kernel<SN_POOL_TIE_SPLIT><<<grid, 256, 0, st>>>(x, y, (uint32_t *)code, N, H, W, C, oh, ow);
+        else maxpool2x2_fwd_kernel<SN_POOL_FIRST_ARGMAX><<<grid, 256, 0, st>>>(x, y, (uint32_t *)code, N, H, W, C, oh, ow);
+        return after_launch("maxpool2x2_fwd_kernel");
+    }
     if (vec) return wide ? launch_fwd<4, uint16_t>(x, y, code, N, H, W, C, oh, ow, pool, stride, mode, st)
                          : launch_fwd<4, uint8_t>(x, y, code, N, H, W, C, oh, ow, pool, stride, mode, st);
     return wide ? launch_fwd<1, uint16_t>(x, y, code, N, H, W, C, oh, ow, pool, stride, mode, st)
@@ -167,6 +270,15 @@ int sn_maxpool2d_bwd(const float *dy, const uint8_t *code, float *dx, int N, int
     bool wide = (mode == SN_POOL_TIE_SPLIT && pool * pool > 8);
     bool vec = (C % 4 == 0) && (((uintptr_t)dx | (uintptr_t)dy) & 15) == 0;
     cudaStream_t st = as_stream(stream);
+    if (vec && pool == 2 && stride == 2 && (((uintptr_t)code) & 3) == 0) {
+        int grid = grid_for((long long)N * oh * ow * (C / 4), 256);
+        const uint32_t *cd = (const uint32_t *)code;
+#define SN_LAUNCH2(M, A) maxpool2x2_bwd_kernel<M, A><<<grid, 256, 0, st>>>(dy, cd, dx, N, H, W, C, oh, ow)
+        if (mode == SN_POOL_TIE_SPLIT) { if (accumulate) SN_LAUNCH2(SN_POOL_TIE_SPLIT, true); else SN_LAUNCH2(SN_POOL_TIE_SPLIT, false); }
+        else { if (accumulate) SN_LAUNCH2(SN_POOL_FIRST_ARGMAX, true); else SN_LAUNCH2(SN_POOL_FIRST_ARGMAX, false); }
+#undef SN_LAUNCH2
+        return after_launch("maxpool2x2_bwd_kernel");
+    }
     if (vec) return wide ? launch_bwd<4, uint16_t>(dy, code, dx, N, H, W, C, oh, ow, pool, stride, mode, accumulate, st)
                          : launch_bwd<4, uint8_t>(dy, code, dx, N, H, W, C, oh, ow, pool, stride, mode, accumulate, st);
     return wide ? launch_bwd<1, uint16_t>(dy, code, dx, N, H, W, C, oh, ow, pool, stride, mode, accumulate, st)
