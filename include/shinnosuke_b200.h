@@ -160,7 +160,7 @@ SN_API int sn_maxpool2d_bwd(const float *dy, const uint8_t *code, float *dx,
 /* ---------------------------------------------------- BatchNormalization */
 /* BatchNormalization.forward (training), layers/Normalization.py:116-128, channel = last
  * (fastest) index of x[rows][C].  Writes y, save_mean[C], save_invstd[C] and updates the moving
- * statistics in place.  scratch: >= 2*C doubles, zeroed by the call. */
+ * statistics in place.  scratch: >= 16*C doubles of device memory, zeroed by the call. */
 SN_API int sn_batchnorm_fwd_train(const float *x, const float *gamma, const float *beta, float *y,
                            float *save_mean, float *save_invstd, float *moving_mean, float *moving_var,
                            double *scratch, long long rows, int C, float eps, float momentum, void *stream);

@@ -177,6 +177,7 @@ __global__ void bn_bwd_apply_kernel(const float *__restrict__ dy, const float *_
 // bounded run (the forward shifts by a per-channel pivot x[0][c], so E[(x-k)^2] - E[x-k]^2 has no
 // cancellation); across threads and blocks they are combined in float64.
 constexpr int BN_UNROLL = 4;
+constexpr int BN_SLOTS = 8;      // copies of the per-channel sums: keeps same-address atomic chains short
 
 template <bool BWD>
 __global__ void __launch_bounds__(256) bn_reduce_pow2_kernel(const float *__restrict__ x, const float *__restrict__ dy,
@@ -230,10 +231,17 @@ __global__ void __launch_bounds__(256) bn_reduce_pow2_kernel(const float *__rest
         for (int k = 0; k < 4; ++k) {
             double ta = 0, tb = 0;
             for (int t = threadIdx.x; t < 256; t += Q) { ta += sa[t][k]; tb += sb[t][k]; }
-            atomicAdd(scratch + cq * 4 + k, ta);
-            atomicAdd(scratch + C + cq * 4 + k, tb);
+            double *slot = scratch + (size_t)(blockIdx.x % BN_SLOTS) * 2 * C;
+            atomicAdd(slot + cq * 4 + k, ta);
+            atomicAdd(slot + C + cq * 4 + k, tb);
         }
     }
+}
+
+__device__ __forceinline__ void bn_slot_sums(const double *__restrict__ scratch, int C, int c, double &a, double &b) {
+    a = 0; b = 0;
+#pragma unroll
+    for (int s = 0; s < BN_SLOTS; ++s) { a += scratch[(size_t)s * 2 * C + c]; b += scratch[(size_t)s * 2 * C + C + c]; }
 }
 
 __global__ void __launch_bounds__(256) bn_apply_train_pow2_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
@@ -249,8 +257,10 @@ __global__ void __launch_bounds__(256) bn_apply_train_pow2_kernel(const float *_
     for (int k = 0; k < 4; ++k) {
         const int c = cq * 4 + k;
         const double pivot = (double)__ldg(x + c);
-        const double m1 = scratch[c] / (double)rows;                   // E[x - pivot]
-        double var = scratch[C + c] / (double)rows - m1 * m1;
+        double s1, s2;
+        bn_slot_sums(scratch, C, c, s1, s2);
+        const double m1 = s1 / (double)rows;                           // E[x - pivot]
+        double var = s2 / (double)rows - m1 * m1;
         if (var < 0) var = 0;
         const double m = pivot + m1;
         const double is = 1.0 / sqrt(var + (double)eps);
@@ -293,7 +303,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_pow2_kernel(const float *__r
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int c = cq * 4 + k;
-        const double sdy = scratch[c], sdyx = scratch[C + c];
+        double sdy, sdyx;
+        bn_slot_sums(scratch, C, c, sdy, sdyx);
         mu[k] = __ldg(mean + c);
         is[k] = __ldg(invstd + c);
         k1[k] = __ldg(gamma + c) * is[k];
@@ -359,8 +370,8 @@ int sn_batchnorm_fwd_train(const float *x, const float *gamma, const float *beta
     SN_REQUIRE(x && gamma && beta && y && save_mean && save_invstd && moving_mean && moving_var && scratch, "null tensor");
     SN_REQUIRE(rows > 0 && C > 0 && C <= 4096, "bad shape (C must be <= 4096)");
     cudaStream_t st = as_stream(stream);
-    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
     if (bn_pow2(C) && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0) {
+        SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C * BN_SLOTS, st));
         const long long total4 = rows * C / 4;
         bn_reduce_pow2_kernel<false><<<bn_grid(total4), 256, 0, st>>>(x, nullptr, nullptr, nullptr, scratch, total4, C);
         int e2 = after_launch("bn_reduce_pow2_kernel");
@@ -369,6 +380,7 @@ int sn_batchnorm_fwd_train(const float *x, const float *gamma, const float *beta
                                                                   moving_var, scratch, total4, C, rows, eps, momentum);
         return after_launch("bn_apply_train_pow2_kernel");
     }
+    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
     bn_reduce_kernel<false><<<reduce_grid(rows, C), dim3(32, 8), 0, st>>>(x, nullptr, nullptr, nullptr, scratch, rows, C);
     int e = after_launch("bn_reduce_kernel");
     if (e) return e;
@@ -392,8 +404,8 @@ int sn_batchnorm_bwd(const float *dy, const float *x, const float *gamma, const 
     SN_REQUIRE(dy && x && gamma && save_mean && save_invstd && dx && scratch, "null tensor");
     SN_REQUIRE(rows > 0 && C > 0 && C <= 2048, "bad shape (C must be <= 2048)");
     cudaStream_t st = as_stream(stream);
-    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
     if (bn_pow2(C) && ((((uintptr_t)x) | ((uintptr_t)dy) | ((uintptr_t)dx)) & 15) == 0) {
+        SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C * BN_SLOTS, st));
         const long long total4 = rows * C / 4;
         bn_reduce_pow2_kernel<true><<<bn_grid(total4), 256, 0, st>>>(x, dy, save_mean, save_invstd, scratch, total4, C);
         int e2 = after_launch("bn_reduce_pow2_kernel");
@@ -405,6 +417,7 @@ int sn_batchnorm_bwd(const float *dy, const float *x, const float *gamma, const 
 #undef SN_LAUNCHP
         return after_launch("bn_bwd_apply_pow2_kernel");
     }
+    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
     bn_reduce_kernel<true><<<reduce_grid(rows, C), dim3(32, 8), 0, st>>>(x, dy, save_mean, save_invstd, scratch, rows, C);
     int e = after_launch("bn_reduce_kernel");
     if (e) return e;

@@ -34,30 +34,31 @@ __global__ void __launch_bounds__(256) direct_fprop_kernel(DirectP p) {
     const int ppw = 32 / tpp;                          // pixels per warp per pass
     const int lane = threadIdx.x & 31;
     const int fg = lane % tpp, slot = lane / tpp;
-    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    const long long pix_per_iter = (long long)ppw * PPT;
+    // 32-bit index arithmetic throughout (the host guarantees P < 2^31): 64-bit divisions would cost
+    // more instructions than the FMAs of a pixel
+    const unsigned warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+    const unsigned pix_per_iter = ppw * PPT;
+    const unsigned P = (unsigned)p.P, OW = p.ow, OH = p.oh;
     float bias[FG];
 #pragma unroll
     for (int j = 0; j < FG; ++j) bias[j] = p.bias ? __ldg(p.bias + fg * FG + j) : 0.f;
 
-    for (long long base = warp_global * pix_per_iter; base < p.P; base += nwarps * pix_per_iter) {
+    for (unsigned base = warp_global * pix_per_iter; base < P; base += nwarps * pix_per_iter) {
         float acc[PPT][FG];
         const float *xb[PPT];
         int hb[PPT], wb[PPT];
         bool ok[PPT];
 #pragma unroll
         for (int q = 0; q < PPT; ++q) {
-            long long pix = base + q * ppw + slot;
-            ok[q] = pix < p.P;
-            long long pp = ok[q] ? pix : 0;
-            int j = (int)(pp % p.ow);
-            long long t = pp / p.ow;
-            int i = (int)(t % p.oh);
-            long long n = t / p.oh;
-            hb[q] = i * p.stride - p.ph;
-            wb[q] = j * p.stride - p.pw;
-            xb[q] = p.x + n * p.H * p.W * p.C;
+            unsigned pix = base + q * ppw + slot;
+            ok[q] = pix < P;
+            unsigned pp = ok[q] ? pix : 0u;
+            unsigned t = pp / OW, j = pp - t * OW;
+            unsigned n = t / OH, i = t - n * OH;
+            hb[q] = (int)i * p.stride - p.ph;
+            wb[q] = (int)j * p.stride - p.pw;
+            xb[q] = p.x + (long long)n * p.H * p.W * p.C;
 #pragma unroll
             for (int f = 0; f < FG; ++f) acc[q][f] = bias[f];
         }
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) direct_fprop_kernel(DirectP p) {
                     for (int q = 0; q < PPT; ++q) {
                         int h = hb[q] + u, w = wb[q] + v;
                         xv[q] = ((unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W)
-                                    ? __ldg(xb[q] + ((long long)h * p.W + w) * p.C + c) : 0.f;
+                                    ? __ldg(xb[q] + (h * p.W + w) * p.C + c) : 0.f;
                     }
                     const float4 *wr = reinterpret_cast<const float4 *>(ws + k * rs + fg * (FG + 4));
 #pragma unroll
@@ -88,8 +89,8 @@ __global__ void __launch_bounds__(256) direct_fprop_kernel(DirectP p) {
 #pragma unroll
         for (int q = 0; q < PPT; ++q) {
             if (!ok[q]) continue;
-            long long pix = base + q * ppw + slot;
-            float4 *dst = reinterpret_cast<float4 *>(p.y + pix * p.F + fg * FG);
+            unsigned pix = base + q * ppw + slot;
+            float4 *dst = reinterpret_cast<float4 *>(p.y + (long long)pix * p.F + fg * FG);
 #pragma unroll
             for (int f4 = 0; f4 < FG / 4; ++f4) {
                 float4 o = make_float4(acc[q][f4 * 4], acc[q][f4 * 4 + 1], acc[q][f4 * 4 + 2], acc[q][f4 * 4 + 3]);
@@ -108,54 +109,65 @@ constexpr int WG_PT = 64;     // pixels per shared-memory tile
 constexpr int WG_KP = 32;
 constexpr int WG_FT = 64;     // filters per block
 
-__global__ void __launch_bounds__(128) direct_wgrad_kernel(DirectP p, long long pix_per_block) {
+__global__ void __launch_bounds__(128) direct_wgrad_kernel(DirectP p, int pix_per_block) {
     __shared__ __align__(16) float dys[WG_PT][WG_FT];
     __shared__ __align__(16) float xcs[WG_PT][WG_KP];
+    __shared__ int row_h[WG_PT], row_w[WG_PT], row_off[WG_PT];   // per tile row: i*s-ph, j*s-pw, n*H*W*C (or -1)
     const int t = threadIdx.x;
     const int f4 = (t & 15) * 4, k4 = (t >> 4) * 4;
     const int f0 = blockIdx.y * WG_FT;
-    const long long p_begin = (long long)blockIdx.x * pix_per_block;
-    const long long p_end = min(p.P, p_begin + pix_per_block);
+    const int P = (int)p.P;
+    const int p_begin = blockIdx.x * pix_per_block;
+    const int p_end = min(P, p_begin + pix_per_block);
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    // this thread always gathers column k = t % 32 of the column tile: decode (u, v, c) once
+    const int gk = t & 31;
     const int kwC = p.kw * p.C;
+    const int gu = gk / kwC, gv = (gk % kwC) / p.C, gc = gk % p.C;
+    const int HWC = p.H * p.W * p.C;
 
-    for (long long pt = p_begin; pt < p_end; pt += WG_PT) {
+    for (int pt = p_begin; pt < p_end; pt += WG_PT) {
+        if (t < WG_PT) {
+            int pix = pt + t;
+            if (pix < p_end) {
+                int tt = pix / p.ow, j = pix - tt * p.ow;
+                int n = tt / p.oh, i = tt - n * p.oh;
+                row_h[t] = i * p.stride - p.ph; row_w[t] = j * p.stride - p.pw; row_off[t] = n * HWC;
+            } else {
+                row_off[t] = -1;
+            }
+        }
         // dY tile: WG_PT x 64 floats, 128-bit coalesced
 #pragma unroll
         for (int r = 0; r < (WG_PT * WG_FT / 4) / 128; ++r) {
             int idx = r * 128 + t;
             int row = idx / (WG_FT / 4), c4 = (idx % (WG_FT / 4)) * 4;
-            long long pix = pt + row;
+            int pix = pt + row;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pix < p_end) v = ldg4(p.dy + pix * p.F + f0 + c4);
+            if (pix < p_end) v = ldg4(p.dy + (long long)pix * p.F + f0 + c4);
             *reinterpret_cast<float4 *>(&dys[row][c4]) = v;
         }
+        __syncthreads();
         // column tile: xcs[row][k] = x[n, i*s+u-ph, j*s+v-pw, c], k = (u*kw+v)*C + c; xcs[row][K] = 1
 #pragma unroll
         for (int r = 0; r < (WG_PT * WG_KP) / 128; ++r) {
-            int idx = r * 128 + t;
-            int row = idx / WG_KP, k = idx % WG_KP;
-            long long pix = pt + row;
+            int row = r * 4 + (t >> 5);
             float v = 0.f;
-            if (pix < p_end) {
-                if (k < p.K) {
-                    int j = (int)(pix % p.ow);
-                    long long tt = pix / p.ow;
-                    int i = (int)(tt % p.oh);
-                    long long n = tt / p.oh;
-                    int u = k / kwC, rem = k % kwC, vv = rem / p.C, c = rem % p.C;
-                    int h = i * p.stride + u - p.ph, w = j * p.stride + vv - p.pw;
+            int off = row_off[row];
+            if (off >= 0) {
+                if (gk < p.K) {
+                    int h = row_h[row] + gu, w = row_w[row] + gv;
                     if ((unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W)
-                        v = __ldg(p.x + ((n * p.H + h) * p.W + w) * p.C + c);
-                } else if (k == p.K) {
+                        v = __ldg(p.x + (long long)off + (h * p.W + w) * p.C + gc);
+                } else if (gk == p.K) {
                     v = 1.f;
                 }
             }
-            xcs[row][k] = v;
+            xcs[row][gk] = v;
         }
         __syncthreads();
 #pragma unroll 8
@@ -214,6 +226,7 @@ int conv_fprop_direct(const float *x, const float *w, const float *bias, float *
 }
 
 bool direct_wgrad_eligible(int C, int kh, int kw, int F) { return C * kh * kw < WG_KP && (F % WG_FT) == 0; }
+// (callers have already checked that every pixel / element count fits in 31 bits: conv_geom)
 
 // dw/db are accumulated into (+=).
 int conv_wgrad_direct(const float *x, const float *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh,
@@ -232,7 +245,7 @@ int conv_wgrad_direct(const float *x, const float *dy, float *dw, float *db, int
     long long ppb = ((tiles + bx - 1) / bx) * WG_PT;
     bx = (p.P + ppb - 1) / ppb;
     dim3 grid((unsigned)bx, fy);
-    direct_wgrad_kernel<<<grid, 128, 0, st>>>(p, ppb);
+    direct_wgrad_kernel<<<grid, 128, 0, st>>>(p, (int)ppb);
     return after_launch("direct_wgrad_kernel");
 }
 
