@@ -14,6 +14,11 @@ int conv_wgrad_tc(const float *x, const float *dy, float *dw, int N, int C, int 
                   int OW, int pad_h, int pad_w, cudaStream_t st);
 int flip_transpose_filters(const float *w, float *wt, int F, int C, int kh, int kw, cudaStream_t st);
 int colsum_accumulate(const float *dy, float *db, long long rows, int F, cudaStream_t st);
+bool stem_tc_eligible(int N, int C, int OH, int OW, int F, int kh, int kw);
+int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
+                       int kw, int stride, int ph, int pw, int act, cudaStream_t st);
+int conv_stem_wgrad_tc(const float *x, const float *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh, int kw,
+                       int stride, int ph, int pw, cudaStream_t st);
 bool direct_fprop_eligible(int C, int kh, int kw, int F);
 bool direct_wgrad_eligible(int C, int kh, int kw, int F);
 int conv_fprop_direct(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F,
@@ -44,6 +49,9 @@ int sn_conv2d_fprop(const float *x, const float *w, const float *bias, float *y,
     if (e) return e;
     const bool geom_ok = N > 0 && C > 0 && F > 0 && kh > 0 && kw > 0 && stride > 0 && pad_h >= 0 && pad_w >= 0 &&
                          H + 2 * pad_h >= kh && W + 2 * pad_w >= kw;
+    if (geom_ok && precision == SN_PREC_TF32 && (((uintptr_t)y | (uintptr_t)bias) & 15) == 0 &&
+        stem_tc_eligible(N, C, (H + 2 * pad_h - kh) / stride + 1, (W + 2 * pad_w - kw) / stride + 1, F, kh, kw))
+        return conv_stem_fprop_tc(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, as_stream(stream));
     if (geom_ok && (((uintptr_t)y) & 15) == 0 && direct_fprop_eligible(C, kh, kw, F))
         return conv_fprop_direct(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, as_stream(stream));
     if (geom_ok && precision == SN_PREC_TF32) {
@@ -85,6 +93,15 @@ int sn_conv2d_wgrad(const float *x, const float *dy, float *dw, float *db, int N
     if (e) return e;
     const bool geom_ok = N > 0 && C > 0 && F > 0 && kh > 0 && kw > 0 && stride > 0 && pad_h >= 0 && pad_w >= 0 &&
                          H + 2 * pad_h >= kh && W + 2 * pad_w >= kw;
+    if (geom_ok && precision == SN_PREC_TF32 && (((uintptr_t)dy) & 15) == 0 && (C * kh * kw < 32 || !db) &&
+        stem_tc_eligible(N, C, (H + 2 * pad_h - kh) / stride + 1, (W + 2 * pad_w - kw) / stride + 1, F, kh, kw)) {
+        cudaStream_t st = as_stream(stream);
+        if (!accumulate) {
+            SN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)F * kh * kw * C, st));
+            if (db) SN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * F, st));
+        }
+        return conv_stem_wgrad_tc(x, dy, dw, db, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, st);
+    }
     if (geom_ok && (((uintptr_t)dy) & 15) == 0 && direct_wgrad_eligible(C, kh, kw, F)) {
         cudaStream_t st = as_stream(stream);
         if (!accumulate) {

@@ -1,0 +1,369 @@
+// Tiny-C convolution (C*kh*kw <= 32: the RGB stem of config 3) on the tensor pipe, tf32 tier.
+//
+// The contraction is only K = 27 long, so a TMA box per filter tap would move almost nothing per
+// load.  Instead the CUDA cores build the COLUMN TILE in shared memory — one 128-byte row of
+// K (padded to 32) fp32 values per output pixel, written directly in the swizzled layout the UMMA
+// descriptor expects — and tcgen05.mma contracts it.  The column matrix still never exists in
+// HBM.  Per 128-pixel tile this is 128 x 27 cached gathers + ONE group of 4 MMAs, so both kernels
+// run at the speed of their HBM stream (the output map for fprop, dY for wgrad).
+//
+//   fprop : D[128 px][F]  = Xcol[128 px][32] (K-major, SW128)      * W[F][32]^T (K-major, SW128)
+//   wgrad : D[128 f][32k] += dY[64 px][128 f]^T (MN-major via TMA) * Xcol[64 px][32] (MN-major),
+//           both in the 128B-swizzle/32B-atom layout fp32 MN-major operands need; column K of Xcol
+//           is the constant 1, so D[f][K] = sum_p dY[p][f] is the bias gradient for free.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+using namespace sn;
+using namespace sn::tc;
+
+namespace {
+
+struct StemP {
+    const float *x, *w, *bias;
+    float *y, *dw, *db;
+    int N, C, H, W, F, kh, kw, stride, ph, pw, oh, ow;
+    int K;        // C*kh*kw <= 32
+    int P;        // N*oh*ow
+    int act;
+    int tiles;    // fprop: ceil(P/128); wgrad: ceil(P/64)
+    int tiles_per_cta;   // wgrad
+};
+
+// A builder thread owns 8 consecutive k's of one pixel row; their tap offsets are loop invariant.
+struct KSlice {
+    int du[8], dv[8], off[8];      // tap row / column and element offset (u*W + v)*C + c; du < 0 marks k >= K
+};
+__device__ __forceinline__ void make_kslice(const StemP &p, int kq, KSlice &ks) {
+    const int kwC = p.kw * p.C;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = kq * 8 + e;
+        if (k < p.K) {
+            const int u = k / kwC, r = k - u * kwC, v = r / p.C, c = r - v * p.C;
+            ks.du[e] = u; ks.dv[e] = v; ks.off[e] = (u * p.W + v) * p.C + c;
+        } else {
+            ks.du[e] = -1; ks.dv[e] = 0; ks.off[e] = 0;
+        }
+    }
+}
+// the 8 column values of pixel `pix` for this slice; `one_at` (>= 0) plants the constant-one column
+__device__ __forceinline__ void gather_slice(const StemP &p, const KSlice &ks, int pix, int kq, int one_at, float (&col)[8]) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) col[e] = 0.f;
+    if (pix >= p.P) return;
+    const int t = pix / p.ow, j = pix - t * p.ow;
+    const int n = t / p.oh, i = t - n * p.oh;
+    const int hb = i * p.stride - p.ph, wb = j * p.stride - p.pw;
+    const float *base = p.x + (long long)n * p.H * p.W * p.C + (hb * p.W + wb) * p.C;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        if (ks.du[e] >= 0) {
+            const int h = hb + ks.du[e], w = wb + ks.dv[e];
+            if ((unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W) col[e] = __ldg(base + ks.off[e]);
+        } else if (kq * 8 + e == one_at) {
+            col[e] = 1.f;
+        }
+    }
+}
+
+// ============================================================================== fprop
+constexpr int SF_BUILDERS = 512;               // 4 threads per pixel row
+constexpr int SF_THREADS = 32 + SF_BUILDERS + 128;   // warp 0: MMA, warps 1-16: column builders, warps 17-20: epilogue
+constexpr int SF_ABUF = 3;
+constexpr int SF_A_BYTES = 128 * 128;
+
+template <int BN>
+__global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const StemP p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sB = smem;                                   // [BN][128 B], SW128 K-major
+    uint8_t *sA = smem + BN * 128;                        // SF_ABUF x [128][128 B]
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(sA + SF_ABUF * SF_A_BYTES);
+    uint64_t *a_empty = a_full + SF_ABUF;
+    uint64_t *t_full = a_empty + SF_ABUF;
+    uint64_t *t_empty = t_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // weights -> smem in the swizzled K-major layout: row f, 16-byte chunk j at (j ^ (f & 7)) * 16
+    for (int i = threadIdx.x; i < BN * 32; i += SF_THREADS) {
+        const int f = i >> 5, k = i & 31;
+        float v = (f < p.F && k < p.K) ? __ldg(p.w + (long long)f * p.K + k) : 0.f;
+        const int chunk = (k >> 2) ^ (f & 7);
+        *reinterpret_cast<float *>(sB + f * 128 + chunk * 16 + (k & 3) * 4) = v;
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < SF_ABUF; ++i) { mbar_init(&a_full[i], SF_BUILDERS); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 0) { tmem_alloc(tmem_ptr, 2 * BN < 32 ? 32 : 2 * BN); tmem_relinquish(); }
+    fence_proxy_async();            // the weight tile was written through the generic proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(2, 128, BN, 0, 0);
+            const uint64_t bdesc = make_smem_desc(smem_u32(sB), 0, 1024);
+            int buf = 0; uint32_t phase = 0; int iter = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++iter) {
+                const int acc = iter & 1;
+                mbar_wait(&t_empty[acc], ((iter >> 1) & 1) ^ 1);
+                mbar_wait(&a_full[buf], phase);
+                tc_fence_after();
+                const uint64_t adesc = make_smem_desc(smem_u32(sA + buf * SF_A_BYTES), 0, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_tf32(tmem_base + acc * BN, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : 0u);
+                mma_commit(&a_empty[buf]);
+                mma_commit(&t_full[acc]);
+                if (++buf == SF_ABUF) { buf = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp <= SF_BUILDERS / 32) {
+        // ---------------- column builders: thread (r, kq) builds k = 8kq..8kq+7 of pixel row r ----------------
+        const int bt = threadIdx.x - 32;
+        const int r = bt >> 2, kq = bt & 3;
+        KSlice ks;
+        make_kslice(p, kq, ks);
+        int buf = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            float col[8];
+            gather_slice(p, ks, tile * 128 + r, kq, -1, col);
+            mbar_wait(&a_empty[buf], phase ^ 1);
+            uint8_t *row = sA + buf * SF_A_BYTES + r * 128;
+            // SW128 K-major: 16-byte chunk j of row r lives at (j ^ (r & 7)) * 16
+            *reinterpret_cast<float4 *>(row + (((2 * kq) ^ (r & 7)) * 16)) = make_float4(col[0], col[1], col[2], col[3]);
+            *reinterpret_cast<float4 *>(row + (((2 * kq + 1) ^ (r & 7)) * 16)) = make_float4(col[4], col[5], col[6], col[7]);
+            fence_proxy_async();               // make the generic-proxy writes visible to the tensor core
+            mbar_arrive(&a_full[buf]);
+            if (++buf == SF_ABUF) { buf = 0; phase ^= 1; }
+        }
+    } else {
+        // ---------------- epilogue: TMEM -> bias/ReLU -> NHWC output ----------------
+        const int q = warp & 3;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++iter) {
+            const int acc = iter & 1;
+            mbar_wait(&t_full[acc], (iter >> 1) & 1);
+            tc_fence_after();
+            const int pix = tile * 128 + q * 32 + lane;
+            float *orow = p.y + (long long)pix * p.F;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t rr[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), rr);
+                tmem_ld_wait();
+                if (pix < p.P) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; jj += 4) {
+                        if (c0 + jj < p.F) {
+                            float4 v = make_float4(__uint_as_float(rr[jj]), __uint_as_float(rr[jj + 1]), __uint_as_float(rr[jj + 2]),
+                                                   __uint_as_float(rr[jj + 3]));
+                            if (p.bias) {
+                                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + jj));
+                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                            }
+                            if (p.act == SN_ACT_RELU) { v.x = relu_keep_sign(v.x); v.y = relu_keep_sign(v.y); v.z = relu_keep_sign(v.z); v.w = relu_keep_sign(v.w); }
+                            *reinterpret_cast<float4 *>(orow + c0 + jj) = v;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN < 32 ? 32 : 2 * BN); }
+}
+
+// ============================================================================== wgrad
+constexpr int SW_BUILDERS = 256;               // 4 threads per pixel row
+constexpr int SW_THREADS = 32 + SW_BUILDERS + 128;   // warp 0: TMA + MMA, warps 1-8: column builders, warps 9-12: epilogue
+constexpr int SW_PB = 64;                      // pixels per stage
+constexpr int SW_STAGES = 4;
+constexpr int SW_ATOM = SW_PB * 128;           // one 32-wide atom column: 64 pixel rows x 128 B
+constexpr int SW_A_BYTES = 4 * SW_ATOM;        // 128 filters
+constexpr int SW_STAGE_BYTES = SW_A_BYTES + SW_ATOM;
+
+__global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const StemP p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + SW_STAGES * SW_STAGE_BYTES);
+    uint64_t *empty = full + SW_STAGES;
+    uint64_t *acc_full = empty + SW_STAGES;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f_tile = blockIdx.y;
+    const int t0 = blockIdx.x * p.tiles_per_cta;
+    const int t1 = min(p.tiles, t0 + p.tiles_per_cta);
+    const int nst = t1 - t0;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmDY);
+        // full: 1 arrive.expect_tx by the TMA thread + one arrival per builder thread
+        for (int i = 0; i < SW_STAGES; ++i) { mbar_init(&full[i], 1 + SW_BUILDERS); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) { tmem_alloc(tmem_ptr, 32); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (nst > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                // one thread is both the TMA producer and the MMA issuer (the MMAs are negligible here):
+                // it runs the loads LOOKAHEAD stages ahead of the MMAs.
+                constexpr uint32_t idesc = make_idesc(2, 128, 32, 1, 1);
+                int ld = 0, ld_stage = 0; uint32_t ld_phase = 0;
+                int stage = 0; uint32_t phase = 0;
+                for (int s = 0; s < nst; ++s) {
+                    while (ld < nst && ld < s + SW_STAGES) {
+                        mbar_wait(&empty[ld_stage], ld_phase ^ 1);
+                        mbar_expect_tx(&full[ld_stage], SW_A_BYTES);
+                        uint8_t *sa = smem + ld_stage * SW_STAGE_BYTES;
+#pragma unroll
+                        for (int a = 0; a < 4; ++a)
+                            tma_load_2d(sa + a * SW_ATOM, &tmDY, &full[ld_stage], f_tile * 128 + a * 32, (t0 + ld) * SW_PB);
+                        ++ld;
+                        if (++ld_stage == SW_STAGES) { ld_stage = 0; ld_phase ^= 1; }
+                    }
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * SW_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < SW_PB / 8; ++k) {
+                        const uint64_t adesc = make_smem_desc(sa + k * 1024, SW_ATOM, 512, LAYOUT_SW128_BASE32B);
+                        const uint64_t bdesc = make_smem_desc(sa + SW_A_BYTES + k * 1024, SW_ATOM, 512, LAYOUT_SW128_BASE32B);
+                        mma_tf32(tmem_base, adesc, bdesc, idesc, (s | k) != 0 ? 1u : 0u);
+                    }
+                    mma_commit(&empty[stage]);
+                    if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
+                }
+                mma_commit(acc_full);
+            }
+        } else if (warp <= SW_BUILDERS / 32) {
+            // column builders: thread (r, kq) builds k = 8kq..8kq+7 (one 32-byte chunk) of pixel row r
+            const int bt = threadIdx.x - 32;
+            const int r = bt >> 2, kq = bt & 3;
+            KSlice ks;
+            make_kslice(p, kq, ks);
+            const int one_at = p.db ? p.K : -1;
+            int stage = 0; uint32_t phase = 0;
+            for (int s = 0; s < nst; ++s) {
+                float col[8];
+                gather_slice(p, ks, (t0 + s) * SW_PB + r, kq, one_at, col);   // rows past the end stay 0 (dY is TMA zero-filled too)
+                mbar_wait(&empty[stage], phase ^ 1);
+                // 128B swizzle with 32-byte atoms: 32-byte chunk j of row r lives at (j ^ (r & 3)) * 32
+                uint8_t *dst = smem + stage * SW_STAGE_BYTES + SW_A_BYTES + r * 128 + ((kq ^ (r & 3)) * 32);
+                *reinterpret_cast<float4 *>(dst) = make_float4(col[0], col[1], col[2], col[3]);
+                *reinterpret_cast<float4 *>(dst + 16) = make_float4(col[4], col[5], col[6], col[7]);
+                fence_proxy_async();
+                mbar_arrive(&full[stage]);
+                if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
+            }
+        } else {
+            // epilogue (warps 9..12): dW[f][k] += D[f][k], db[f] += D[f][K]
+            const int q = warp & 3;
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+            uint32_t rr[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), rr);
+            tmem_ld_wait();
+            const int f = f_tile * 128 + q * 32 + lane;
+            if (f < p.F) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    if (k < p.K) atomicAdd(p.dw + (long long)f * p.K + k, __uint_as_float(rr[k]));
+                    else if (k == p.K && p.db) atomicAdd(p.db + f, __uint_as_float(rr[k]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 32); }
+}
+
+void fill_geom(StemP &p, int N, int C, int H, int W, int F, int kh, int kw, int stride, int ph, int pw) {
+    p.N = N; p.C = C; p.H = H; p.W = W; p.F = F; p.kh = kh; p.kw = kw; p.stride = stride; p.ph = ph; p.pw = pw;
+    p.oh = (H + 2 * ph - kh) / stride + 1; p.ow = (W + 2 * pw - kw) / stride + 1;
+    p.K = C * kh * kw; p.P = N * p.oh * p.ow;
+}
+
+template <int BN>
+int launch_stem_fprop(const StemP &p, cudaStream_t st) {
+    const int smem = BN * 128 + SF_ABUF * SF_A_BYTES + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        SN_CUDA(cudaFuncSetAttribute(stem_fprop_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    int grid = p.tiles < num_sms() ? p.tiles : num_sms();
+    stem_fprop_kernel<BN><<<grid, SF_THREADS, smem, st>>>(p);
+    return after_launch("stem_fprop_kernel");
+}
+
+}  // namespace
+
+namespace sn {
+
+bool stem_tc_eligible(int N, int C, int OH, int OW, int F, int kh, int kw) {
+    const int K = C * kh * kw;
+    if (K > 32 || (F & 15) || F > 256 || F < 16) return false;
+    return (long long)N * OH * OW >= 4096;          // small maps: the direct kernel is latency-equivalent
+}
+
+int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
+                       int kw, int stride, int ph, int pw, int act, cudaStream_t st) {
+    StemP p{};
+    fill_geom(p, N, C, H, W, F, kh, kw, stride, ph, pw);
+    p.x = x; p.w = w; p.bias = bias; p.y = y; p.act = act;
+    p.tiles = (p.P + 127) / 128;
+    if (F <= 32) return launch_stem_fprop<32>(p, st);
+    if (F <= 64) return launch_stem_fprop<64>(p, st);
+    if (F <= 128) return launch_stem_fprop<128>(p, st);
+    return launch_stem_fprop<256>(p, st);
+}
+
+// dw/db accumulated into (+=).  Requires K < 32 when db != NULL (the ones column).
+int conv_stem_wgrad_tc(const float *x, const float *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh, int kw,
+                       int stride, int ph, int pw, cudaStream_t st) {
+    StemP p{};
+    fill_geom(p, N, C, H, W, F, kh, kw, stride, ph, pw);
+    p.x = x; p.dw = dw; p.db = db;
+    p.tiles = (p.P + SW_PB - 1) / SW_PB;
+    const int f_tiles = (F + 127) / 128;
+    int ctas = num_sms() / f_tiles;
+    if (ctas < 1) ctas = 1;
+    if (ctas > p.tiles) ctas = p.tiles;
+    p.tiles_per_cta = (p.tiles + ctas - 1) / ctas;
+    ctas = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+    CUtensorMap tmDY;
+    long long ddims[2] = {F, p.P};
+    long long dstr[2] = {1, F};
+    int dbox[2] = {32, SW_PB};
+    int e = make_tmap_f32(&tmDY, dy, 2, ddims, dstr, dbox, true);
+    if (e) return e;
+    const int smem = SW_STAGES * SW_STAGE_BYTES + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        SN_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    stem_wgrad_kernel<<<dim3(ctas, f_tiles), SW_THREADS, smem, st>>>(tmDY, p);
+    return after_launch("stem_wgrad_kernel");
+}
+
+}  // namespace sn

@@ -61,6 +61,9 @@ def _run_conv(shape, precision='tf32'):
     (2, 48, 8, 8, 64, 1, 1, 'VALID', 'relu'),        # 1x1, C not a multiple of 32 (zero-filled k-block tail)
     (5, 64, 8, 8, 96, 5, 1, 'SAME', 'linear'),       # 5x5 taps
     (2, 64, 18, 18, 64, 3, 1, 'VALID', 'relu'),      # VALID 18->16 (power-of-two output, non-power-of-two input)
+    (8, 3, 32, 32, 64, 3, 1, 'SAME', 'relu'),        # cfg3 stem: column tile built in smem + tcgen05 (conv_stem_tc.cu)
+    (20, 3, 29, 31, 48, 3, 2, 'VALID', 'linear'),    # stem path, ragged everything, stride 2
+    (16, 1, 28, 28, 16, 2, 1, 'VALID', 'relu'),      # cfg1-like (K = 4) on the stem path
 ])
 def test_conv2d_tf32_vs_oracle(shape):
     out = _run_conv(shape)
@@ -140,7 +143,7 @@ def test_trajectory_cfg3_tf32():
     net.fit(X, Y, 16, 1, shuffle=False)
     m = _vgg('tf32')
     m.fit(X, Y, batch_size=16, epochs=1, shuffle=False, validation_ratio=0., verbose=0)
-    assert np.allclose(m.train_loss, net.train_loss, rtol=2e-2)      # loss after ~10 TF32 layers
+    assert np.allclose(m.train_loss, net.train_loss, rtol=5e-2)      # 2nd loss follows a TF32 update in a loss~10 regime
     convs = [l for l in m.layers if l.__class__.__name__ == 'Conv2D']
     # Trajectory-level bound, NOT the op-level TOL_TF32: on a random-init net ~1e-3 of the ReLU
     # masks sit within TF32 rounding of the kink; a weight gradient is a random-sign sum over P
