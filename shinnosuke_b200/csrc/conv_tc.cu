@@ -89,18 +89,22 @@ struct IgemmParams {
     int act, accumulate;
 };
 
-template <int BN> struct IgemmCfg {
+// KS = k-blocks (128-byte K slabs) per pipeline stage.  A stage must carry enough MMA time
+// (KS * 128*BN*32 / 2048 cycles) to amortise the per-stage barrier round trips of the single
+// producer and issuer threads; narrow tiles therefore use KS = 2.
+template <int BN, int KS> struct IgemmCfg {
     static constexpr int B_BYTES = BN * BK * 4;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
+    static constexpr int SLAB_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = KS * SLAB_BYTES;
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;      // power of two >= 32
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, int KS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
-    using Cfg = IgemmCfg<BN>;
+    using Cfg = IgemmCfg<BN, KS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -112,7 +116,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = p.tiles_m * p.tiles_n;
-    const int kblocks = p.ntaps * p.cblocks;
+    const int kblocks = p.ntaps * p.cblocks;          // a multiple of KS (host-checked)
+    const int kstages = kblocks / KS;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -139,14 +144,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 int n0, h0;
                 if (p.bands_per_image) { n0 = tm / p.bands_per_image; h0 = (tm % p.bands_per_image) * p.th; }
                 else { n0 = tm * p.tn; h0 = 0; }
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    const int tap = kb / p.cblocks, cb = kb % p.cblocks;
-                    const int u = tap / p.taps_w, v = tap % p.taps_w;
+                int tap = 0, cb = 0, u = 0, v = 0;
+                for (int ks = 0; ks < kstages; ++ks) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    uint8_t *sa = smem + stage * Cfg::STAGE_BYTES;
-                    tma_load_4d(sa, &tmA, &full_bar[stage], cb * BK, v - p.pad_w, h0 + u - p.pad_h, n0);
-                    tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], tap * p.C + cb * BK, tn_idx * BN);
+#pragma unroll
+                    for (int s = 0; s < KS; ++s) {
+                        uint8_t *sa = smem + stage * Cfg::STAGE_BYTES + s * Cfg::SLAB_BYTES;
+                        tma_load_4d(sa, &tmA, &full_bar[stage], cb * BK, v - p.pad_w, h0 + u - p.pad_h, n0);
+                        tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], tap * p.C + cb * BK, tn_idx * BN);
+                        if (++cb == p.cblocks) { cb = 0; ++tap; if (++v == p.taps_w) { v = 0; ++u; } }
+                    }
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -162,16 +170,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 mbar_wait(&tmem_empty[acc], ((iter >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < kblocks; ++kb) {
+                for (int ks = 0; ks < kstages; ++ks) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint64_t adesc = make_smem_desc(sa, 0, 1024);
-                    const uint64_t bdesc = make_smem_desc(sa + A_BYTES, 0, 1024);
 #pragma unroll
-                    for (int k = 0; k < BK / UK; ++k) {
-                        // advancing K inside the 128-byte swizzle row: +32 bytes = +2 descriptor units
-                        mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int s = 0; s < KS; ++s) {
+                        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES + s * Cfg::SLAB_BYTES);
+                        const uint64_t adesc = make_smem_desc(sa, 0, 1024);
+                        const uint64_t bdesc = make_smem_desc(sa + A_BYTES, 0, 1024);
+#pragma unroll
+                        for (int k = 0; k < BK / UK; ++k) {
+                            // advancing K inside the 128-byte swizzle row: +32 bytes = +2 descriptor units
+                            mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | s | k) != 0 ? 1u : 0u);
+                        }
                     }
                     mma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -275,18 +286,22 @@ struct WgradParams {
     int pad_h, pad_w;
 };
 
-template <int CN> struct WgradCfg {
-    static constexpr int B_BYTES = (CN / 32) * ATOM_BYTES;
-    static constexpr int STAGE_BYTES = WG_A_BYTES + B_BYTES;
-    static constexpr int STAGES = (CN <= 64) ? 8 : (CN <= 128 ? 6 : 4);
-    static constexpr int TMEM_COLS = CN < 32 ? 32 : CN;
+// TAPS consecutive filter taps share one dY tile per stage (their X tiles differ only by the tap
+// shift): 1/TAPS of the dY traffic from L2 and TAPS x the MMA time per barrier round trip.
+constexpr int pow2_at_least(int v) { int r = 32; while (r < v) r *= 2; return r; }
+template <int CN, int TAPS> struct WgradCfg {
+    static constexpr int B_BYTES = (CN / 32) * ATOM_BYTES;           // per tap
+    static constexpr int STAGE_BYTES = WG_A_BYTES + TAPS * B_BYTES;
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+    static constexpr int TMEM_COLS = pow2_at_least(TAPS * CN);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static_assert(TAPS * CN <= 512, "accumulators exceed TMEM");
 };
 
-template <int CN>
+template <int CN, int TAPS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
-    using Cfg = WgradCfg<CN>;
+    using Cfg = WgradCfg<CN, TAPS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -300,7 +315,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     // work item of this CTA
     const int split = blockIdx.x % p.splits;
     int item = blockIdx.x / p.splits;
-    const int tap = item % p.ntaps; item /= p.ntaps;
+    const int tap_groups = p.ntaps / TAPS;
+    const int tap0 = (item % tap_groups) * TAPS; item /= tap_groups;
     const int ct = item % p.c_tiles;
     const int ft = item / p.c_tiles;
     const int pb0 = split * p.pblocks_per_split;
@@ -326,7 +342,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     if (nkb > 0) {
         if (warp == 0) {
             if (lane == 0) {
-                const int u = tap / p.taps_w, v = tap % p.taps_w;
                 int stage = 0; uint32_t phase = 0;
                 for (int pb = pb0; pb < pb1; ++pb) {
                     const int pix = pb * PB;
@@ -340,9 +355,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                     for (int a = 0; a < 4; ++a)
                         tma_load_2d(sa + a * ATOM_BYTES, &tmDY, &full_bar[stage], ft * 128 + a * 32, pix);
 #pragma unroll
-                    for (int b = 0; b < CN / 32; ++b)
-                        tma_load_4d(sa + WG_A_BYTES + b * ATOM_BYTES, &tmX, &full_bar[stage], ct * CN + b * 32, v - p.pad_w,
-                                    i0 + u - p.pad_h, n0);
+                    for (int t = 0; t < TAPS; ++t) {
+                        const int u = (tap0 + t) / p.taps_w, v = (tap0 + t) % p.taps_w;
+#pragma unroll
+                        for (int b = 0; b < CN / 32; ++b)
+                            tma_load_4d(sa + WG_A_BYTES + t * Cfg::B_BYTES + b * ATOM_BYTES, &tmX, &full_bar[stage],
+                                        ct * CN + b * 32, v - p.pad_w, i0 + u - p.pad_h, n0);
+                    }
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -359,8 +378,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                         // UMMA K-step k = pixel rows 8k..8k+7 of every atom column (+1024 B) = two 4-row
                         // K groups 512 B apart (SBO); atom columns of 32 f / 32 c are ATOM_BYTES apart (LBO)
                         const uint64_t adesc = make_smem_desc(sa + k * 1024, ATOM_BYTES, 512, LAYOUT_SW128_BASE32B);
-                        const uint64_t bdesc = make_smem_desc(sa + WG_A_BYTES + k * 1024, ATOM_BYTES, 512, LAYOUT_SW128_BASE32B);
-                        mma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+                        for (int t = 0; t < TAPS; ++t) {
+                            const uint64_t bdesc = make_smem_desc(sa + WG_A_BYTES + t * Cfg::B_BYTES + k * 1024, ATOM_BYTES, 512,
+                                                                  LAYOUT_SW128_BASE32B);
+                            mma_tf32(tmem_base + t * CN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
                     mma_commit(&empty_bar[stage]);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -372,18 +395,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
             mbar_wait(acc_full, 0);
             tc_fence_after();
             const int f = ft * 128 + q * 32 + lane;
-            float *row = p.dw + ((long long)f * p.ntaps + tap) * p.C + ct * CN;
             constexpr int CHUNK = (CN >= 32) ? 32 : 16;
 #pragma unroll 1
-            for (int c0 = 0; c0 < CN; c0 += CHUNK) {
-                uint32_t r[CHUNK];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-                if constexpr (CHUNK == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
-                tmem_ld_wait();
-                if (f < p.F) {
+            for (int t = 0; t < TAPS; ++t) {
+                float *row = p.dw + ((long long)f * p.ntaps + tap0 + t) * p.C + ct * CN;
+#pragma unroll 1
+                for (int c0 = 0; c0 < CN; c0 += CHUNK) {
+                    uint32_t r[CHUNK];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * CN + c0);
+                    if constexpr (CHUNK == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+                    tmem_ld_wait();
+                    if (f < p.F) {
 #pragma unroll
-                    for (int j = 0; j < CHUNK; ++j)
-                        if (ct * CN + c0 + j < p.C) atomicAdd(row + c0 + j, __uint_as_float(r[j]));
+                        for (int j = 0; j < CHUNK; ++j)
+                            if (ct * CN + c0 + j < p.C) atomicAdd(row + c0 + j, __uint_as_float(r[j]));
+                    }
                 }
             }
         }
@@ -397,16 +423,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     }
 }
 
-template <int CN>
+template <int CN, int TAPS>
 int launch_wgrad(const CUtensorMap &tmDY, const CUtensorMap &tmX, const WgradParams &p, cudaStream_t st) {
-    using Cfg = WgradCfg<CN>;
+    using Cfg = WgradCfg<CN, TAPS>;
     static bool configured = false;
     if (!configured) {
-        SN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        SN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<CN, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    int grid = p.f_tiles * p.c_tiles * p.ntaps * p.splits;
-    conv_wgrad_kernel<CN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tmDY, tmX, p);
+    int grid = p.f_tiles * p.c_tiles * (p.ntaps / TAPS) * p.splits;
+    conv_wgrad_kernel<CN, TAPS><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tmDY, tmX, p);
     return after_launch("conv_wgrad_kernel");
 }
 
@@ -432,18 +458,24 @@ bool tile_geometry(int N, int OH, int OW, TileGeom &g) {
     return g.th <= 256;
 }
 
-template <int BN>
-int launch_igemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const IgemmParams &p, cudaStream_t st) {
-    using Cfg = IgemmCfg<BN>;
+template <int BN, int KS>
+int launch_igemm_ks(const CUtensorMap &tmA, const CUtensorMap &tmB, const IgemmParams &p, cudaStream_t st) {
+    using Cfg = IgemmCfg<BN, KS>;
     static bool configured = false;
     if (!configured) {
-        SN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        SN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
     int tiles = p.tiles_m * p.tiles_n;
     int grid = tiles < num_sms() ? tiles : num_sms();
-    conv_igemm_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+    conv_igemm_kernel<BN, KS><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
     return after_launch("conv_igemm_kernel");
+}
+template <int BN>
+int launch_igemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const IgemmParams &p, cudaStream_t st) {
+    const int kblocks = p.ntaps * p.cblocks;
+    if (BN <= 128 && (kblocks % 2) == 0) return launch_igemm_ks<BN, 2>(tmA, tmB, p, st);
+    return launch_igemm_ks<BN, 1>(tmA, tmB, p, st);
 }
 
 }  // namespace
@@ -465,7 +497,9 @@ int conv_igemm_tc(const float *x, const float *w, const float *bias, float *out,
     TileGeom g;
     if (!tile_geometry(N, OH, OW, g)) { set_error("conv_igemm_tc: unsupported output geometry %dx%d", OH, OW); return SN_ERR_UNSUPPORTED; }
     if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)out) & 15) { set_error("conv_igemm_tc: tensors must be 16-byte aligned"); return SN_ERR_INVALID_ARG; }
-    const int BN = F > 128 ? 256 : (F > 64 ? 128 : (F > 32 ? 64 : (F > 16 ? 32 : 16)));
+    int BN = F > 128 ? 256 : (F > 64 ? 128 : (F > 32 ? 64 : (F > 16 ? 32 : 16)));
+    // few pixel tiles (deep, small maps): halve the filter tile so that more of the 148 SMs get one
+    if (BN == 256 && ((long long)N * OH * OW + BM - 1) / BM * ((F + 255) / 256) < (3 * num_sms()) / 4) BN = 128;
     CUtensorMap tmA, tmB;
     long long adims[4] = {C, IW, IH, N};
     long long astr[4] = {1, C, (long long)IW * C, (long long)IH * IW * C};
@@ -508,12 +542,14 @@ int conv_wgrad_tc(const float *x, const float *dy, float *dw, int N, int C, int 
     if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) { set_error("conv_wgrad_tc: tensors must be 16-byte aligned"); return SN_ERR_INVALID_ARG; }
     const int S = OH * OW;
     const long long P = (long long)N * S;
-    const int CN = (C % 256 == 0) ? 256 : ((C % 128 == 0) ? 128 : ((C % 64 == 0) ? 64 : 32));
+    const int TAPS = (kh * kw) % 3 == 0 ? 3 : 1;
+    int CN = (C % 256 == 0) ? 256 : ((C % 128 == 0) ? 128 : ((C % 64 == 0) ? 64 : 32));
+    if (TAPS == 3 && CN > 128) CN = 128;                  // 3 accumulators of CN columns must fit the 512 TMEM columns
     WgradParams p{};
     p.dw = dw; p.F = F; p.C = C; p.ntaps = kh * kw; p.taps_w = kw;
     p.c_tiles = C / CN; p.f_tiles = (F + 127) / 128;
     p.pblocks = (int)((P + PB - 1) / PB);
-    int items = p.f_tiles * p.c_tiles * p.ntaps;
+    int items = p.f_tiles * p.c_tiles * (p.ntaps / TAPS);
     int splits = num_sms() / items;
     if (splits < 1) splits = 1;
     if (splits > p.pblocks) splits = p.pblocks;
@@ -533,11 +569,18 @@ int conv_wgrad_tc(const float *x, const float *dy, float *dw, int N, int C, int 
     int xbox[4] = {32, OW, p.th, p.tn};
     e = make_tmap_f32(&tmX, x, 4, xdims, xstr, xbox, true);
     if (e) return e;
+    if (TAPS == 3) {
+        switch (CN) {
+            case 32: return launch_wgrad<32, 3>(tmDY, tmX, p, st);
+            case 64: return launch_wgrad<64, 3>(tmDY, tmX, p, st);
+            default: return launch_wgrad<128, 3>(tmDY, tmX, p, st);
+        }
+    }
     switch (CN) {
-        case 32: return launch_wgrad<32>(tmDY, tmX, p, st);
-        case 64: return launch_wgrad<64>(tmDY, tmX, p, st);
-        case 128: return launch_wgrad<128>(tmDY, tmX, p, st);
-        default: return launch_wgrad<256>(tmDY, tmX, p, st);
+        case 32: return launch_wgrad<32, 1>(tmDY, tmX, p, st);
+        case 64: return launch_wgrad<64, 1>(tmDY, tmX, p, st);
+        case 128: return launch_wgrad<128, 1>(tmDY, tmX, p, st);
+        default: return launch_wgrad<256, 1>(tmDY, tmX, p, st);
     }
 }
 
