@@ -175,6 +175,24 @@ SN_API int sn_batchnorm_bwd(const float *dy, const float *x, const float *gamma,
                      float *dx, float *dgamma, float *dbeta, double *scratch,
                      long long rows, int C, int accumulate_dx, int mask_relu, void *stream);
 
+/* Per-channel sums for the training statistics only (pass 1 of sn_batchnorm_fwd_train): zeroes
+ * `scratch` (>= 16*C doubles) and accumulates sum(x - x[0][c]) and sum((x - x[0][c])^2) into it.
+ * Needs C = 4*2^k <= 1024. */
+SN_API int sn_batchnorm_stats(const float *x, double *scratch, long long rows, int C, void *stream);
+
+/* BatchNormalization immediately followed by MaxPooling2D((2,2)) (stride 2), fused: the normalised
+ * map is never written.  x: conv output (N,H,W,C); y_pool: (N,H/2,W/2,C); code: one byte per
+ * pooled element (same meaning as sn_maxpool2d_fwd).  Requires sn_bn_pool_supported(). */
+SN_API int sn_bn_pool_supported(int N, int H, int W, int C);
+SN_API int sn_bn_pool_fwd_train(const float *x, const float *gamma, const float *beta, float *y_pool, uint8_t *code,
+                         float *save_mean, float *save_invstd, float *moving_mean, float *moving_var,
+                         double *scratch, int N, int H, int W, int C, float eps, float momentum,
+                         int pool_mode, void *stream);
+/* backward of the fused pair: dy_pool (N,H/2,W/2,C) -> dx (N,H,W,C) (overwritten), dgamma/dbeta += */
+SN_API int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, const float *gamma,
+                   const float *save_mean, const float *save_invstd, float *dx, float *dgamma, float *dbeta,
+                   double *scratch, int N, int H, int W, int C, int pool_mode, int mask_relu, void *stream);
+
 /* ------------------------------------------------------------------ loss */
 /* Softmax._forward, utils/Activator.py:108-110 (row-wise; the reference's global shift cancels) */
 SN_API int sn_softmax_fwd(const float *logits, float *probs, int rows, int classes, void *stream);

@@ -364,6 +364,16 @@ static dim3 reduce_grid(long long rows, int C) {
 
 extern "C" {
 
+int sn_batchnorm_stats(const float *x, double *scratch, long long rows, int C, void *stream) {
+    SN_REQUIRE(x && scratch && rows > 0, "bad arguments");
+    SN_REQUIRE(bn_pow2(C) && (((uintptr_t)x) & 15) == 0, "needs C = 4*2^k <= 1024 and a 16-byte aligned tensor");
+    cudaStream_t st = as_stream(stream);
+    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C * BN_SLOTS, st));
+    const long long total4 = rows * C / 4;
+    bn_reduce_pow2_kernel<false><<<bn_grid(total4), 256, 0, st>>>(x, nullptr, nullptr, nullptr, scratch, total4, C);
+    return after_launch("bn_reduce_pow2_kernel");
+}
+
 int sn_batchnorm_fwd_train(const float *x, const float *gamma, const float *beta, float *y, float *save_mean,
                            float *save_invstd, float *moving_mean, float *moving_var, double *scratch,
                            long long rows, int C, float eps, float momentum, void *stream) {

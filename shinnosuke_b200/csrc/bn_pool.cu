@@ -1,0 +1,287 @@
+// BatchNormalization fused with the 2x2/stride-2 MaxPooling2D that follows it (the
+// Conv -> BN -> Pool block of BASELINE configs 3 and 4).  The normalised map is never written to
+// HBM: forward reads the conv output once for the statistics and once to normalise + pool;
+// backward scatters the pooled gradient through the pool codes on the fly while it reduces and
+// applies the BatchNorm gradient.  Versus the separate layers this removes the write + re-read of
+// the BN output (forward) and the write + two re-reads of the pool's dX (backward): about 45 %
+// of the block's element-wise HBM traffic.
+//
+// Semantics are exactly the two reference layers back to back (layers/Normalization.py:93-230,
+// layers/Convolution.py:287-362): biased variance, eps in the sqrt, moving statistics, tie-split
+// or first-argmax routing, and (optionally) the producing layer's ReLU mask applied to dX.
+#include "common.cuh"
+using namespace sn;
+
+namespace {
+
+constexpr int SLOTS = 8;        // must match bn.cu (layout of the float64 scratch)
+
+__device__ __forceinline__ void slot_sums(const double *__restrict__ scratch, int C, int c, double &a, double &b) {
+    a = 0; b = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) { a += scratch[(size_t)s * 2 * C + c]; b += scratch[(size_t)s * 2 * C + C + c]; }
+}
+
+__device__ __forceinline__ float comp(const float4 &v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
+__device__ __forceinline__ void setc(float4 &v, int k, float x) { if (k == 0) v.x = x; else if (k == 1) v.y = x; else if (k == 2) v.z = x; else v.w = x; }
+
+// window index space: idx = ((n*oh + i)*ow + j)*Q + cq, Q = C/4.  256 % Q == 0 and the grid stride
+// is a multiple of 256, so a thread always works on the same channel quad.
+struct Win { const float *p00; long long rowstride; };
+__device__ __forceinline__ Win window(const float *x, long long idx, int Q, int ow, int oh, int W, int C) {
+    const int cq = (int)(idx % Q);
+    long long pix = idx / Q;
+    const int j = (int)(pix % ow);
+    long long t = pix / ow;
+    const int i = (int)(t % oh);
+    const long long n = t / oh;
+    Win w;
+    w.rowstride = (long long)W * C;
+    w.p00 = x + ((n * 2 * oh + 2 * i) * W + 2 * j) * C + cq * 4;      // H == 2*oh
+    return w;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_pool_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
+                                                          const float *__restrict__ beta, float *__restrict__ y,
+                                                          uint32_t *__restrict__ code, float *__restrict__ save_mean,
+                                                          float *__restrict__ save_invstd, float *__restrict__ moving_mean,
+                                                          float *__restrict__ moving_var, const double *__restrict__ scratch,
+                                                          long long windows4, int C, int W, int oh, int ow, long long rows,
+                                                          float eps, float momentum) {
+    const int Q = C >> 2;
+    const int cq = threadIdx.x % Q;
+    float sc[4], sh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = cq * 4 + k;
+        const double pivot = (double)__ldg(x + c);
+        double s1, s2;
+        slot_sums(scratch, C, c, s1, s2);
+        const double m1 = s1 / (double)rows;
+        double var = s2 / (double)rows - m1 * m1;
+        if (var < 0) var = 0;
+        const double m = pivot + m1;
+        const double is = 1.0 / sqrt(var + (double)eps);
+        const float g = __ldg(gamma + c);
+        sc[k] = (float)(g * is);
+        sh[k] = (float)(__ldg(beta + c) - g * is * m);
+        if (blockIdx.x == 0 && threadIdx.x < Q) {
+            save_mean[c] = (float)m;
+            save_invstd[c] = (float)is;
+            moving_mean[c] = momentum * moving_mean[c] + (1.f - momentum) * (float)m;
+            moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * (float)var;
+        }
+    }
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < windows4; idx += stride) {
+        const Win w = window(x, idx, Q, ow, oh, W, C);
+        float4 v[4];
+        v[0] = ldg4(w.p00); v[1] = ldg4(w.p00 + C); v[2] = ldg4(w.p00 + w.rowstride); v[3] = ldg4(w.p00 + w.rowstride + C);
+        float4 out;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a0 = fmaf(comp(v[0], k), sc[k], sh[k]), a1 = fmaf(comp(v[1], k), sc[k], sh[k]);
+            const float a2 = fmaf(comp(v[2], k), sc[k], sh[k]), a3 = fmaf(comp(v[3], k), sc[k], sh[k]);
+            float m = a0; uint32_t am = 0;
+            if (a1 > m) { m = a1; am = 1; }
+            if (a2 > m) { m = a2; am = 2; }
+            if (a3 > m) { m = a3; am = 3; }
+            uint32_t cd;
+            if (MODE == SN_POOL_FIRST_ARGMAX) cd = am;
+            else cd = (a0 == m ? 1u : 0u) | (a1 == m ? 2u : 0u) | (a2 == m ? 4u : 0u) | (a3 == m ? 8u : 0u);
+            setc(out, k, m);
+            packed |= cd << (8 * k);
+        }
+        *reinterpret_cast<float4 *>(y + idx * 4) = out;
+        code[idx] = packed;
+    }
+}
+
+// gradient of the BN output at window element e of channel lane k, from the pooled gradient
+template <int MODE>
+__device__ __forceinline__ float routed(float g, uint32_t cd, int e) {
+    if (MODE == SN_POOL_FIRST_ARGMAX) return cd == (uint32_t)e ? g : 0.f;
+    if (!((cd >> e) & 1u)) return 0.f;
+    const int cnt = __popc(cd);
+    return cnt > 1 ? g / (float)cnt : g;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(const float *__restrict__ dyp, const uint32_t *__restrict__ code,
+                                                                 const float *__restrict__ x, const float *__restrict__ mean,
+                                                                 const float *__restrict__ invstd, double *__restrict__ scratch,
+                                                                 long long windows4, int C, int W, int oh, int ow) {
+    const int Q = C >> 2;
+    const int cq = threadIdx.x % Q;
+    float mu[4], is[4];
+    {
+        const float4 a = ldg4(mean + cq * 4), b = ldg4(invstd + cq * 4);
+        mu[0] = a.x; mu[1] = a.y; mu[2] = a.z; mu[3] = a.w; is[0] = b.x; is[1] = b.y; is[2] = b.z; is[3] = b.w;
+    }
+    double da[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};
+    const long long stride = (long long)gridDim.x * 256;
+    long long idx = blockIdx.x * 256ll + threadIdx.x;
+    while (idx < windows4) {
+        float fa[4] = {0, 0, 0, 0}, fb[4] = {0, 0, 0, 0};
+#pragma unroll 1
+        for (int it = 0; it < 16 && idx < windows4; ++it, idx += stride) {
+            const Win w = window(x, idx, Q, ow, oh, W, C);
+            const float4 g = ldg4(dyp + idx * 4);
+            const uint32_t packed = __ldg(code + idx);
+            float4 v[4];
+            v[0] = ldg4(w.p00); v[1] = ldg4(w.p00 + C); v[2] = ldg4(w.p00 + w.rowstride); v[3] = ldg4(w.p00 + w.rowstride + C);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t cd = (packed >> (8 * k)) & 0xffu;
+                const float gk = comp(g, k);
+                fa[k] += gk;                                        // the routed shares of a window sum to gk
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float r = routed<MODE>(gk, cd, e);
+                    fb[k] = fmaf(r, (comp(v[e], k) - mu[k]) * is[k], fb[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { da[k] += (double)fa[k]; db[k] += (double)fb[k]; }
+    }
+    __shared__ double sa[256][4], sb[256][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sa[threadIdx.x][k] = da[k]; sb[threadIdx.x][k] = db[k]; }
+    __syncthreads();
+    if (threadIdx.x < Q) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double ta = 0, tb = 0;
+            for (int t = threadIdx.x; t < 256; t += Q) { ta += sa[t][k]; tb += sb[t][k]; }
+            double *slot = scratch + (size_t)(blockIdx.x % SLOTS) * 2 * C;
+            atomicAdd(slot + cq * 4 + k, ta);
+            atomicAdd(slot + C + cq * 4 + k, tb);
+        }
+    }
+}
+
+template <int MODE, bool MASK>
+__global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__restrict__ dyp, const uint32_t *__restrict__ code,
+                                                                const float *__restrict__ x, const float *__restrict__ gamma,
+                                                                const float *__restrict__ mean, const float *__restrict__ invstd,
+                                                                float *__restrict__ dx, float *__restrict__ dgamma,
+                                                                float *__restrict__ dbeta, const double *__restrict__ scratch,
+                                                                long long windows4, int C, int W, int oh, int ow, long long rows) {
+    const int Q = C >> 2;
+    const int cq = threadIdx.x % Q;
+    float k1[4], k2[4], k3[4], mu[4], is[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = cq * 4 + k;
+        double sdy, sdyx;
+        slot_sums(scratch, C, c, sdy, sdyx);
+        mu[k] = __ldg(mean + c);
+        is[k] = __ldg(invstd + c);
+        k1[k] = __ldg(gamma + c) * is[k];
+        k2[k] = (float)(sdy / (double)rows);
+        k3[k] = (float)(sdyx / (double)rows);
+        if (blockIdx.x == 0 && threadIdx.x < Q) {
+            if (dbeta) dbeta[c] += (float)sdy;
+            if (dgamma) dgamma[c] += (float)sdyx;
+        }
+    }
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < windows4; idx += stride) {
+        const Win w = window(x, idx, Q, ow, oh, W, C);
+        const float4 g = ldg4(dyp + idx * 4);
+        const uint32_t packed = __ldg(code + idx);
+        float4 v[4], o[4];
+        v[0] = ldg4(w.p00); v[1] = ldg4(w.p00 + C); v[2] = ldg4(w.p00 + w.rowstride); v[3] = ldg4(w.p00 + w.rowstride + C);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t cd = (packed >> (8 * k)) & 0xffu;
+            const float gk = comp(g, k);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float xv = comp(v[e], k);
+                const float xh = (xv - mu[k]) * is[k];
+                float r = k1[k] * (routed<MODE>(gk, cd, e) - k2[k] - xh * k3[k]);
+                if (MASK && relu_blocked(xv)) r = 0.f;
+                setc(o[e], k, r);
+            }
+        }
+        float *d00 = dx + (w.p00 - x);
+        *reinterpret_cast<float4 *>(d00) = o[0];
+        *reinterpret_cast<float4 *>(d00 + C) = o[1];
+        *reinterpret_cast<float4 *>(d00 + w.rowstride) = o[2];
+        *reinterpret_cast<float4 *>(d00 + w.rowstride + C) = o[3];
+    }
+}
+
+int grid_for_windows(long long windows4) {
+    long long need = (windows4 + 255) / 256;
+    long long cap = (long long)num_sms() * 8;
+    return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+bool shape_ok(int N, int H, int W, int C) {
+    if (N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || (C & 3)) return false;
+    const int q = C >> 2;
+    return q >= 1 && q <= 256 && (q & (q - 1)) == 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sn_bn_pool_supported(int N, int H, int W, int C) { return shape_ok(N, H, W, C) ? 1 : 0; }
+
+int sn_bn_pool_fwd_train(const float *x, const float *gamma, const float *beta, float *y_pool, uint8_t *code,
+                         float *save_mean, float *save_invstd, float *moving_mean, float *moving_var, double *scratch,
+                         int N, int H, int W, int C, float eps, float momentum, int pool_mode, void *stream) {
+    SN_REQUIRE(x && gamma && beta && y_pool && code && save_mean && save_invstd && moving_mean && moving_var && scratch, "null tensor");
+    SN_REQUIRE(shape_ok(N, H, W, C), "unsupported shape (needs even H, W and C = 4*2^k <= 1024)");
+    SN_REQUIRE(pool_mode == SN_POOL_TIE_SPLIT || pool_mode == SN_POOL_FIRST_ARGMAX, "unknown pool mode");
+    SN_REQUIRE(((((uintptr_t)x) | ((uintptr_t)y_pool)) & 15) == 0 && (((uintptr_t)code) & 3) == 0, "misaligned tensor");
+    cudaStream_t st = as_stream(stream);
+    const long long rows = (long long)N * H * W;
+    // pass 1: per-channel statistics of x (the plain BatchNorm reduction, scratch zeroed inside)
+    int e = sn_batchnorm_stats(x, scratch, rows, C, stream);
+    if (e) return e;
+    const int oh = H / 2, ow = W / 2;
+    const long long windows4 = (long long)N * oh * ow * (C / 4);
+    const int grid = grid_for_windows(windows4);
+    if (pool_mode == SN_POOL_TIE_SPLIT)
+        bn_pool_fwd_kernel<SN_POOL_TIE_SPLIT><<<grid, 256, 0, st>>>(x, gamma, beta, y_pool, (uint32_t *)code, save_mean, save_invstd,
+                                                                    moving_mean, moving_var, scratch, windows4, C, W, oh, ow, rows, eps, momentum);
+    else
+        bn_pool_fwd_kernel<SN_POOL_FIRST_ARGMAX><<<grid, 256, 0, st>>>(x, gamma, beta, y_pool, (uint32_t *)code, save_mean, save_invstd,
+                                                                       moving_mean, moving_var, scratch, windows4, C, W, oh, ow, rows, eps, momentum);
+    return after_launch("bn_pool_fwd_kernel");
+}
+
+int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, const float *gamma, const float *save_mean,
+                   const float *save_invstd, float *dx, float *dgamma, float *dbeta, double *scratch, int N, int H, int W,
+                   int C, int pool_mode, int mask_relu, void *stream) {
+    SN_REQUIRE(dy_pool && code && x && gamma && save_mean && save_invstd && dx && scratch, "null tensor");
+    SN_REQUIRE(shape_ok(N, H, W, C), "unsupported shape (needs even H, W and C = 4*2^k <= 1024)");
+    SN_REQUIRE(pool_mode == SN_POOL_TIE_SPLIT || pool_mode == SN_POOL_FIRST_ARGMAX, "unknown pool mode");
+    cudaStream_t st = as_stream(stream);
+    const long long rows = (long long)N * H * W;
+    const int oh = H / 2, ow = W / 2;
+    const long long windows4 = (long long)N * oh * ow * (C / 4);
+    const int grid = grid_for_windows(windows4);
+    const uint32_t *cd = (const uint32_t *)code;
+    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C * SLOTS, st));
+    if (pool_mode == SN_POOL_TIE_SPLIT)
+        bn_pool_bwd_reduce_kernel<SN_POOL_TIE_SPLIT><<<grid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow);
+    else
+        bn_pool_bwd_reduce_kernel<SN_POOL_FIRST_ARGMAX><<<grid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow);
+    int e = after_launch("bn_pool_bwd_reduce_kernel");
+    if (e) return e;
+#define SN_LAUNCH(M, K) bn_pool_bwd_apply_kernel<M, K><<<grid, 256, 0, st>>>(dy_pool, cd, x, gamma, save_mean, save_invstd, dx, dgamma, dbeta, scratch, windows4, C, W, oh, ow, rows)
+    if (pool_mode == SN_POOL_TIE_SPLIT) { if (mask_relu) SN_LAUNCH(SN_POOL_TIE_SPLIT, true); else SN_LAUNCH(SN_POOL_TIE_SPLIT, false); }
+    else { if (mask_relu) SN_LAUNCH(SN_POOL_FIRST_ARGMAX, true); else SN_LAUNCH(SN_POOL_FIRST_ARGMAX, false); }
+#undef SN_LAUNCH
+    return after_launch("bn_pool_bwd_apply_kernel");
+}
+
+}  // extern "C"

@@ -184,11 +184,34 @@ class MaxPooling2D(Layer):
         self._infer(self.input_shape)
         return self
 
+    def _fused_buffers(self, N, C, H, W):
+        """Output and code buffers for the BatchNormalization layer that computes this pool's forward
+        as part of its own (csrc/bn_pool.cu)."""
+        from ..device import empty, torch
+        oh, ow = H // 2, W // 2
+        y = self._buf('out', (N, C, oh, ow), 'nhwc')
+        key = ('code', N * C * oh * ow)
+        code = self._bufs.get(key)
+        if code is None:
+            code = empty(key[1], torch().uint8)
+            self._bufs[key] = code
+        self._code, self._code_mode = code, self.mode
+        self.input_shape = (N, C, H, W)
+        return y, code
+
     def forward(self, is_training=True):
         """layers/Convolution.py:287-324.  'reshape' mode keeps a tie bit-mask, 'im2col' mode the
         first-argmax index; both are one byte per output element in (n,i,j,c) order.  On maps
         whose side is not a multiple of the pool the reference's 'reshape' mode raises; here it
         floors like the layer's own declared output_shape."""
+        fused = getattr(self, '_fused_output', None)
+        if fused is not None:                       # already computed by the preceding BatchNormalization
+            self._fused_output = None
+            self._fused_bwd = True
+            self.output_tensor = fused
+            super(MaxPooling2D, self).forward(is_training)
+            return
+        self._fused_bwd = False
         x = self.input_tensor
         N, C, H, W = x.shape
         self.input_shape = x.shape
@@ -221,6 +244,8 @@ class MaxPooling2D(Layer):
 
     def backward(self):
         """layers/Convolution.py:326-362."""
+        if getattr(self, '_fused_bwd', False):
+            return                                   # the fused BatchNormalization.backward consumes self.grads
         g = self.grads
         N, C, H, W = self.input_shape
         p, s = self.pool_size[0], self.stride
@@ -232,4 +257,5 @@ class MaxPooling2D(Layer):
     def __getstate__(self):
         d = Layer.__getstate__(self)
         d.pop('_code', None)
+        d.pop('_fused_output', None)
         return d

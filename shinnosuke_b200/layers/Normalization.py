@@ -3,7 +3,7 @@ import numpy as np
 
 from .Base import Layer, Variable
 from ..device import DeviceTensor, current_stream, zeros, torch
-from .._lib import lib
+from .._lib import lib, POOL_MODE
 from ..utils.Initializers import get_initializer
 
 
@@ -29,6 +29,8 @@ class BatchNormalization(Layer):
         self._mm_host = np.asarray(self.moving_mean_initializer(n_in), dtype=np.float64)
         self._mv_host = np.asarray(self.moving_variance_initializer(n_in), dtype=np.float64)
         self._stats = None
+        self._fuse_with_pool = None      # set by the model when a 2x2/stride-2 MaxPooling2D is the only consumer
+        self._fused_active = False
         self.output_shape = shape
 
     def connect(self, prev_layer):
@@ -63,8 +65,25 @@ class BatchNormalization(Layer):
         C = x.shape[1]
         rows = x.size // C
         s = self._device_stats(C)
-        y = self._buf('out', x.shape, x.layout)
         st = current_stream()
+        pool = self._fuse_with_pool
+        self._fused_active = bool(is_training and pool is not None and x.ndim == 4 and
+                                  lib.load().sn_bn_pool_supported(x.shape[0], x.shape[2], x.shape[3], C))
+        if self._fused_active:
+            # BN + 2x2 max-pool in one pass (csrc/bn_pool.cu): the normalised map is never materialised,
+            # so this layer has no output_tensor of its own in this mode (compile(..., fuse=False) keeps it).
+            N, _, H, W = x.shape
+            yp, code = pool._fused_buffers(N, C, H, W)
+            lib.sn_bn_pool_fwd_train(x.ptr, gamma.output_tensor.ptr, beta.output_tensor.ptr, yp.ptr, code.data_ptr(),
+                                     s['mean'].ptr, s['invstd'].ptr, s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(),
+                                     N, H, W, C, float(self.epsilon), float(self.momentum), POOL_MODE[pool.mode], st)
+            pool._fused_output = yp
+            pool.input_tensor = None
+            self.output_tensor = None
+            self._grads_written = False
+            self._grads_premasked = False
+            return
+        y = self._buf('out', x.shape, x.layout)
         if is_training:
             lib.sn_batchnorm_fwd_train(x.ptr, gamma.output_tensor.ptr, beta.output_tensor.ptr, y.ptr, s['mean'].ptr,
                                        s['invstd'].ptr, s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows, C,
@@ -80,11 +99,33 @@ class BatchNormalization(Layer):
         only consumer is this BN, its mask `pre-activation < 0` (utils/Activator.py:25) is applied
         while dX is written, saving that layer one read-modify-write pass over its gradient."""
         gamma, beta = self.variables
-        x, g = self.input_tensor, self.grads
+        x = self.input_tensor
         C = x.shape[1]
-        rows = x.size // C
         s = self._stats
         st = current_stream()
+        if self._fused_active:
+            pool = self._fuse_with_pool
+            N, _, H, W = x.shape
+            for layer in self.inbounds:
+                fuse = bool(layer.require_grads and layer._fused_relu() and len(layer.outbound_layers) == 1
+                            and not layer._grads_written)
+
+                def fused_writer(dst, acc, fuse=fuse):
+                    out = self._buf('dx_tmp', x.shape, x.layout) if acc else dst
+                    lib.sn_bn_pool_bwd(pool.grads.ptr, pool._code.data_ptr(), x.ptr, gamma.output_tensor.ptr, s['mean'].ptr,
+                                       s['invstd'].ptr, out.ptr, gamma.grads.ptr if gamma.require_grads else None,
+                                       beta.grads.ptr if beta.require_grads else None, s['scratch'].data_ptr(),
+                                       N, H, W, C, POOL_MODE[pool._code_mode], 1 if fuse else 0, st)
+                    if acc:
+                        dst.add_(out)
+                if layer.require_grads:
+                    self._push_grad(layer, fused_writer)
+                    layer._grads_premasked = fuse
+                else:
+                    fused_writer(self._buf('dx_unused', x.shape, x.layout), 0, False)
+            return
+        g = self.grads
+        rows = x.size // C
         for layer in self.inbounds:
             fuse = bool(layer.require_grads and getattr(layer, '_fused_relu', lambda: False)()
                         and len(layer.outbound_layers) == 1 and not layer._grads_written)

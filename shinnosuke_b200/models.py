@@ -74,12 +74,20 @@ class _Trainer(object):
         raise NotImplementedError
 
     # ---- compile ---------------------------------------------------------
-    def _finish_compile(self, optimizer, loss, precision):
+    def _finish_compile(self, optimizer, loss, precision, fuse=True):
         if precision not in PRECISION:
             raise ValueError('precision must be one of %s' % sorted(PRECISION))
         self.precision = precision
+        from .layers.Normalization import BatchNormalization
+        from .layers.Convolution import MaxPooling2D
         for layer in self._forward_order():
             layer.precision = precision
+            if isinstance(layer, BatchNormalization):
+                # BatchNormalization -> MaxPooling2D((2,2)) with no other consumer runs as one fused pass
+                nxt = layer.outbound_layers[0] if len(layer.outbound_layers) == 1 else None
+                ok = (fuse and isinstance(nxt, MaxPooling2D) and tuple(nxt.pool_size) == (2, 2) and nxt.stride == 2
+                      and len(nxt.inbounds) == 1)
+                layer._fuse_with_pool = nxt if ok else None
         self.loss = get_objective(loss)
         self.optimizer = get_optimizer(optimizer)
 
@@ -386,7 +394,7 @@ class Sequential(_Trainer):
     def add(self, layer):
         self.layers.append(layer)
 
-    def compile(self, optimizer, loss, precision='fp32'):
+    def compile(self, optimizer, loss, precision='fp32', fuse=True):
         """models.py:30-43: connect the layers in order (shape inference + host-side parameter
         creation, same RNG consumption as the reference), collect the trainable variables."""
         assert self.layers
@@ -399,7 +407,7 @@ class Sequential(_Trainer):
                 if var.require_grads:
                     trainable_variables.append(var)
         self.trainable_variables = trainable_variables
-        self._finish_compile(optimizer, loss, precision)
+        self._finish_compile(optimizer, loss, precision, fuse)
 
     def _forward_order(self):
         return self.layers
@@ -462,7 +470,7 @@ class Model(_Trainer):
                     ready.append(m)
         return order
 
-    def compile(self, optimizer, loss, precision='fp32'):
+    def compile(self, optimizer, loss, precision='fp32', fuse=True):
         assert self.inputs is not None and self.outputs is not None
         self.forward_graph = self._kahn(self.inputs, lambda n: n.outbound_layers, lambda n: n.inbounds)
         self.backward_graph = self._kahn(self.outputs, lambda n: n.inbounds, lambda n: n.outbound_layers)
@@ -474,7 +482,7 @@ class Model(_Trainer):
                 if isinstance(var, Variable) and var.require_grads and var not in tv:
                     tv.append(var)
         self.trainable_variables = tv
-        self._finish_compile(optimizer, loss, precision)
+        self._finish_compile(optimizer, loss, precision, fuse)
 
     def _forward_order(self):
         return self.forward_graph

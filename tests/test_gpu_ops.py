@@ -321,3 +321,49 @@ def test_empty_batch_is_a_noop():
     lib.sn_conv2d_fprop(8, 8, None, 8, 0, 3, 8, 8, 4, 3, 3, 1, 1, 1, 0, 0, None)
     lib.sn_maxpool2d_fwd(8, 8, None, 0, 8, 8, 4, 2, 2, 0, None)
     lib.sn_sgd_update(8, 8, 0, 0.1, 1.0, None)
+
+
+@pytest.mark.parametrize('mode', ['reshape', 'im2col'])
+@pytest.mark.parametrize('shape', [(4, 64, 8, 8), (2, 16, 6, 10), (3, 256, 4, 4)])
+def test_fused_batchnorm_maxpool_pair(shape, mode):
+    """csrc/bn_pool.cu: BatchNormalization -> MaxPooling2D((2,2)) as ONE pass must equal the two
+    oracle layers back to back (forward values, pool codes, dX with the producer's ReLU mask,
+    dgamma/dbeta, moving statistics)."""
+    from shinnosuke_b200 import Sequential, Conv2D, BatchNormalization, MaxPooling2D, Input, Activation
+    from shinnosuke_b200.device import as_device
+    N, C, H, W = shape
+    r = np.random.default_rng(C + H)
+    x = r.standard_normal((N, 3, H, W)).astype(np.float32).astype(np.float64)
+    w = (0.3 * r.standard_normal((C, 3, 3, 3))).astype(np.float32).astype(np.float64)
+    b = (0.1 * r.standard_normal((1, C))).astype(np.float32).astype(np.float64)
+    gam = (1 + 0.3 * r.standard_normal(C)).astype(np.float32).astype(np.float64)
+    gam[::5] *= -1                                            # negative gamma: max must be taken AFTER normalisation
+    bet = (0.2 * r.standard_normal(C)).astype(np.float32).astype(np.float64)
+    gup = r.standard_normal((N, C, H // 2, W // 2)).astype(np.float32).astype(np.float64)
+    conv = Conv2D(C, (3, 3), padding='SAME', activation='relu')
+    bn = BatchNormalization()
+    pool = MaxPooling2D((2, 2))
+    inp = Input((None, 3, H, W)); src = Activation('linear')(inp); conv(src); bn(conv); pool(bn)
+    pool.mode = mode
+    bn._fuse_with_pool = pool
+    set_params(conv, w, b); set_params(bn, gam, bet)
+    inp.input_tensor = x
+    for l in (inp, src, conv, bn, pool):
+        l.forward(True)
+    assert bn._fused_active and bn.output_tensor is None
+    yc, cc = O.conv2d_forward(x, w, b, 1, (1, 1), 'relu')
+    yb, cb, mm, mv = O.batchnorm_forward(yc, gam, bet, np.zeros(C), np.ones(C))
+    yp, cp = O.maxpool_forward(yb, 2, None, mode)
+    assert rel_err(np.asarray(pool.output_tensor), yp) < TOL32
+    assert rel_err(bn.moving_mean, mm) < TOL32 and rel_err(bn.moving_variance, mv) < TOL32
+    pool._seed_grads(as_device(gup))
+    pool.backward(); bn.backward()
+    assert conv._grads_premasked
+    conv.backward()
+    dyb = O.maxpool_backward(gup, cp)
+    dxb, dg, dbt = O.batchnorm_backward(dyb, cb)
+    dxc, dw, db = O.conv2d_backward(dxb, cc)
+    assert rel_err(np.asarray(bn.variables[0].grads), dg) < TOL32
+    assert rel_err(np.asarray(bn.variables[1].grads), dbt) < TOL32
+    assert rel_err(np.asarray(conv.variables[0].grads), dw) < TOL32
+    assert rel_err(np.asarray(src.grads), dxc) < TOL32

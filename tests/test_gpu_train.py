@@ -207,3 +207,26 @@ def test_full_size_cfg3_properties():
     w = m._arena.w.clone()
     m.optimizer.update(m.trainable_variables)
     assert (m._arena.w == w).all().item()
+
+
+def test_fused_and_unfused_models_agree():
+    """compile(fuse=True) (BatchNormalization+MaxPooling2D as one pass, the default) and fuse=False
+    (one kernel per layer, every layer's output_tensor materialised) train identically."""
+    r, X = _data((32, 3, 32, 32), kind='normal')
+    Y = O.to_categorical(np.concatenate([np.arange(10), r.integers(0, 10, 22)]))
+    from shinnosuke_b200 import Sequential, Conv2D, BatchNormalization, MaxPooling2D, Flatten, Dense
+    runs = []
+    for fuse in (True, False):
+        np.random.seed(0)
+        m = Sequential()
+        m.add(Conv2D(64, (3, 3), input_shape=(None, 3, 32, 32), padding='SAME', activation='relu'))
+        m.add(BatchNormalization()); m.add(MaxPooling2D((2, 2)))
+        m.add(Conv2D(128, (3, 3), padding='SAME', activation='relu'))
+        m.add(BatchNormalization()); m.add(MaxPooling2D((2, 2)))
+        m.add(Flatten()); m.add(Dense(10, activation='softmax'))
+        m.compile('sgd', 'sparse_categorical_crossentropy', fuse=fuse)
+        m.fit(X, Y, batch_size=16, epochs=2, shuffle=True, validation_ratio=0., verbose=0)
+        runs.append((m.train_loss, np.asarray(m.layers[0].variables[0].output_tensor)))
+        assert (m.layers[1].output_tensor is None) == fuse
+    assert np.allclose(runs[0][0], runs[1][0], rtol=1e-5)
+    assert rel_err(runs[0][1], runs[1][1]) < 1e-5
