@@ -165,6 +165,12 @@ def kernel_work(name, a, precision):
     if name == 'sn_batchnorm_bwd':
         rows, C = a[0], a[1]
         return 'bytes', 4.0 * rows * C * 5          # read dy,x (reduce), read dy,x + write dx (apply)
+    if name == 'sn_bn_pool_fwd_train':
+        N, H, W, C = a[:4]
+        return 'bytes', 8.0 * N * H * W * C + 5.0 * N * (H // 2) * (W // 2) * C     # x read twice; pooled y + code written
+    if name == 'sn_bn_pool_bwd':
+        N, H, W, C = a[:4]
+        return 'bytes', 12.0 * N * H * W * C + 10.0 * N * (H // 2) * (W // 2) * C   # x twice + dx; dy_pool + code twice
     if name == 'sn_sgd_update':
         return 'bytes', 16.0 * a[0]
     if name == 'sn_momentum_update':

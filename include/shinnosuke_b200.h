@@ -160,7 +160,7 @@ SN_API int sn_maxpool2d_bwd(const float *dy, const uint8_t *code, float *dx,
 /* ---------------------------------------------------- BatchNormalization */
 /* BatchNormalization.forward (training), layers/Normalization.py:116-128, channel = last
  * (fastest) index of x[rows][C].  Writes y, save_mean[C], save_invstd[C] and updates the moving
- * statistics in place.  scratch: >= 16*C doubles of device memory, zeroed by the call. */
+ * statistics in place.  scratch: >= 20*C doubles of device memory, zeroed by the call. */
 SN_API int sn_batchnorm_fwd_train(const float *x, const float *gamma, const float *beta, float *y,
                            float *save_mean, float *save_invstd, float *moving_mean, float *moving_var,
                            double *scratch, long long rows, int C, float eps, float momentum, void *stream);
@@ -175,10 +175,12 @@ SN_API int sn_batchnorm_bwd(const float *dy, const float *x, const float *gamma,
                      float *dx, float *dgamma, float *dbeta, double *scratch,
                      long long rows, int C, int accumulate_dx, int mask_relu, void *stream);
 
-/* Per-channel sums for the training statistics only (pass 1 of sn_batchnorm_fwd_train): zeroes
- * `scratch` (>= 16*C doubles) and accumulates sum(x - x[0][c]) and sum((x - x[0][c])^2) into it.
- * Needs C = 4*2^k <= 1024. */
-SN_API int sn_batchnorm_stats(const float *x, double *scratch, long long rows, int C, void *stream);
+/* Pass 1 of sn_batchnorm_fwd_train on its own: per-channel batch statistics of x[rows][C] ->
+ * save_mean / save_invstd, moving statistics updated, and the apply-pass constants left in
+ * `scratch` (>= 20*C doubles, zeroed by the call).  Needs C = 4*2^k <= 1024. */
+SN_API int sn_batchnorm_stats(const float *x, const float *gamma, const float *beta, float *save_mean,
+                       float *save_invstd, float *moving_mean, float *moving_var, double *scratch,
+                       long long rows, int C, float eps, float momentum, void *stream);
 
 /* BatchNormalization immediately followed by MaxPooling2D((2,2)) (stride 2), fused: the normalised
  * map is never written.  x: conv output (N,H,W,C); y_pool: (N,H/2,W/2,C); code: one byte per

@@ -3,6 +3,7 @@
 // direction; per-channel sums are accumulated in float64 (B200 has full-rate-enough FP64 for a
 // memory-bound reduction) so the 1e-5 tier holds even when |mean| >> std.
 #include "common.cuh"
+#include "bn_common.cuh"
 using namespace sn;
 
 // blockDim = (32, 8): threadIdx.x walks 4 channels each (float4), threadIdx.y walks rows.
@@ -177,12 +178,11 @@ __global__ void bn_bwd_apply_kernel(const float *__restrict__ dy, const float *_
 // bounded run (the forward shifts by a per-channel pivot x[0][c], so E[(x-k)^2] - E[x-k]^2 has no
 // cancellation); across threads and blocks they are combined in float64.
 constexpr int BN_UNROLL = 4;
-constexpr int BN_SLOTS = 8;      // copies of the per-channel sums: keeps same-address atomic chains short
 
 template <bool BWD>
 __global__ void __launch_bounds__(256) bn_reduce_pow2_kernel(const float *__restrict__ x, const float *__restrict__ dy,
                                                              const float *__restrict__ mean, const float *__restrict__ invstd,
-                                                             double *__restrict__ scratch, long long total4, int C) {
+                                                             double *__restrict__ scratch, long long total4, int C, BnFinal fin) {
     const int Q = C >> 2;
     const int cq = threadIdx.x % Q;
     float k0[4], k1[4];          // STATS: pivot, unused.   BWD: mean, invstd
@@ -236,44 +236,16 @@ __global__ void __launch_bounds__(256) bn_reduce_pow2_kernel(const float *__rest
             atomicAdd(slot + C + cq * 4 + k, tb);
         }
     }
+    bn_finalize_last_block(scratch, fin);
 }
 
-__device__ __forceinline__ void bn_slot_sums(const double *__restrict__ scratch, int C, int c, double &a, double &b) {
-    a = 0; b = 0;
-#pragma unroll
-    for (int s = 0; s < BN_SLOTS; ++s) { a += scratch[(size_t)s * 2 * C + c]; b += scratch[(size_t)s * 2 * C + C + c]; }
-}
-
-__global__ void __launch_bounds__(256) bn_apply_train_pow2_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
-                                                                  const float *__restrict__ beta, float *__restrict__ y,
-                                                                  float *__restrict__ save_mean, float *__restrict__ save_invstd,
-                                                                  float *__restrict__ moving_mean, float *__restrict__ moving_var,
-                                                                  const double *__restrict__ scratch, long long total4, int C,
-                                                                  long long rows, float eps, float momentum) {
+__global__ void __launch_bounds__(256) bn_apply_train_pow2_kernel(const float *__restrict__ x, float *__restrict__ y,
+                                                                  const double *__restrict__ scratch, long long total4, int C) {
     const int Q = C >> 2;
     const int cq = threadIdx.x % Q;
-    float sc[4], sh[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int c = cq * 4 + k;
-        const double pivot = (double)__ldg(x + c);
-        double s1, s2;
-        bn_slot_sums(scratch, C, c, s1, s2);
-        const double m1 = s1 / (double)rows;                           // E[x - pivot]
-        double var = s2 / (double)rows - m1 * m1;
-        if (var < 0) var = 0;
-        const double m = pivot + m1;
-        const double is = 1.0 / sqrt(var + (double)eps);
-        const float g = __ldg(gamma + c);
-        sc[k] = (float)(g * is);
-        sh[k] = (float)(__ldg(beta + c) - g * is * m);
-        if (blockIdx.x == 0 && threadIdx.x < Q) {
-            save_mean[c] = (float)m;
-            save_invstd[c] = (float)is;
-            moving_mean[c] = momentum * moving_mean[c] + (1.f - momentum) * (float)m;
-            moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * (float)var;
-        }
-    }
+    const float *prm = bn_params(scratch, C);
+    const float4 sc4 = ldg4(prm + cq * 4), sh4 = ldg4(prm + C + cq * 4);
+    const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
     const long long stride = (long long)gridDim.x * 256;
     for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total4; i += BN_UNROLL * stride) {
         float4 v[BN_UNROLL];
@@ -292,29 +264,13 @@ __global__ void __launch_bounds__(256) bn_apply_train_pow2_kernel(const float *_
 
 template <bool ACC, bool MASK>
 __global__ void __launch_bounds__(256) bn_bwd_apply_pow2_kernel(const float *__restrict__ dy, const float *__restrict__ x,
-                                                                const float *__restrict__ gamma, const float *__restrict__ mean,
-                                                                const float *__restrict__ invstd, float *__restrict__ dx,
-                                                                float *__restrict__ dgamma, float *__restrict__ dbeta,
-                                                                const double *__restrict__ scratch, long long total4, int C,
-                                                                long long rows) {
+                                                                float *__restrict__ dx, const double *__restrict__ scratch,
+                                                                long long total4, int C) {
     const int Q = C >> 2;
     const int cq = threadIdx.x % Q;
-    float k1[4], k2[4], k3[4], mu[4], is[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int c = cq * 4 + k;
-        double sdy, sdyx;
-        bn_slot_sums(scratch, C, c, sdy, sdyx);
-        mu[k] = __ldg(mean + c);
-        is[k] = __ldg(invstd + c);
-        k1[k] = __ldg(gamma + c) * is[k];
-        k2[k] = (float)(sdy / (double)rows);
-        k3[k] = (float)(sdyx / (double)rows);
-        if (blockIdx.x == 0 && threadIdx.x < Q) {
-            if (dbeta) dbeta[c] += (float)sdy;
-            if (dgamma) dgamma[c] += (float)sdyx;
-        }
-    }
+    const float *prm = bn_params(scratch, C);
+    const float4 a4 = ldg4(prm + cq * 4), b4 = ldg4(prm + C + cq * 4), c4 = ldg4(prm + 2 * C + cq * 4);
+    const float pa[4] = {a4.x, a4.y, a4.z, a4.w}, pb[4] = {b4.x, b4.y, b4.z, b4.w}, pc[4] = {c4.x, c4.y, c4.z, c4.w};
     const long long stride = (long long)gridDim.x * 256;
     for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total4; i += 2 * stride) {
         float4 g[2], xv[2], old[2];
@@ -331,8 +287,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_pow2_kernel(const float *__r
             float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, gs[4] = {g[u].x, g[u].y, g[u].z, g[u].w}, r[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                float xh = (xs[k] - mu[k]) * is[k];
-                r[k] = k1[k] * (gs[k] - k2[k] - xh * k3[k]);
+                r[k] = fmaf(pa[k], gs[k], fmaf(pb[k], xs[k], pc[k]));       // gamma*invstd*(dy - mean(dy) - xhat*mean(dy*xhat))
                 if (MASK && relu_blocked(xs[k])) r[k] = 0.f;
             }
             if (ACC) { r[0] += old[u].x; r[1] += old[u].y; r[2] += old[u].z; r[3] += old[u].w; }
@@ -364,13 +319,19 @@ static dim3 reduce_grid(long long rows, int C) {
 
 extern "C" {
 
-int sn_batchnorm_stats(const float *x, double *scratch, long long rows, int C, void *stream) {
+int sn_batchnorm_stats(const float *x, const float *gamma, const float *beta, float *save_mean, float *save_invstd,
+                       float *moving_mean, float *moving_var, double *scratch, long long rows, int C, float eps,
+                       float momentum, void *stream) {
     SN_REQUIRE(x && scratch && rows > 0, "bad arguments");
     SN_REQUIRE(bn_pow2(C) && (((uintptr_t)x) & 15) == 0, "needs C = 4*2^k <= 1024 and a 16-byte aligned tensor");
     cudaStream_t st = as_stream(stream);
-    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C * BN_SLOTS, st));
+    SN_REQUIRE(gamma && beta && save_mean && save_invstd && moving_mean && moving_var, "null tensor");
+    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * BN_SCRATCH_DOUBLES_PER_C * C, st));
     const long long total4 = rows * C / 4;
-    bn_reduce_pow2_kernel<false><<<bn_grid(total4), 256, 0, st>>>(x, nullptr, nullptr, nullptr, scratch, total4, C);
+    BnFinal fin{};
+    fin.bwd = 0; fin.rows = rows; fin.C = C; fin.x = x; fin.gamma = gamma; fin.beta = beta; fin.save_mean = save_mean;
+    fin.save_invstd = save_invstd; fin.moving_mean = moving_mean; fin.moving_var = moving_var; fin.eps = eps; fin.momentum = momentum;
+    bn_reduce_pow2_kernel<false><<<bn_grid(total4), 256, 0, st>>>(x, nullptr, nullptr, nullptr, scratch, total4, C, fin);
     return after_launch("bn_reduce_pow2_kernel");
 }
 
@@ -381,13 +342,11 @@ int sn_batchnorm_fwd_train(const float *x, const float *gamma, const float *beta
     SN_REQUIRE(rows > 0 && C > 0 && C <= 4096, "bad shape (C must be <= 4096)");
     cudaStream_t st = as_stream(stream);
     if (bn_pow2(C) && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0) {
-        SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C * BN_SLOTS, st));
-        const long long total4 = rows * C / 4;
-        bn_reduce_pow2_kernel<false><<<bn_grid(total4), 256, 0, st>>>(x, nullptr, nullptr, nullptr, scratch, total4, C);
-        int e2 = after_launch("bn_reduce_pow2_kernel");
+        int e2 = sn_batchnorm_stats(x, gamma, beta, save_mean, save_invstd, moving_mean, moving_var, scratch, rows, C, eps,
+                                    momentum, stream);
         if (e2) return e2;
-        bn_apply_train_pow2_kernel<<<bn_grid(total4), 256, 0, st>>>(x, gamma, beta, y, save_mean, save_invstd, moving_mean,
-                                                                  moving_var, scratch, total4, C, rows, eps, momentum);
+        const long long total4 = rows * C / 4;
+        bn_apply_train_pow2_kernel<<<bn_grid(total4), 256, 0, st>>>(x, y, scratch, total4, C);
         return after_launch("bn_apply_train_pow2_kernel");
     }
     SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
@@ -415,13 +374,16 @@ int sn_batchnorm_bwd(const float *dy, const float *x, const float *gamma, const 
     SN_REQUIRE(rows > 0 && C > 0 && C <= 2048, "bad shape (C must be <= 2048)");
     cudaStream_t st = as_stream(stream);
     if (bn_pow2(C) && ((((uintptr_t)x) | ((uintptr_t)dy) | ((uintptr_t)dx)) & 15) == 0) {
-        SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C * BN_SLOTS, st));
+        SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * BN_SCRATCH_DOUBLES_PER_C * C, st));
         const long long total4 = rows * C / 4;
-        bn_reduce_pow2_kernel<true><<<bn_grid(total4), 256, 0, st>>>(x, dy, save_mean, save_invstd, scratch, total4, C);
+        BnFinal fin{};
+        fin.bwd = 1; fin.rows = rows; fin.C = C; fin.gamma = gamma; fin.mean = save_mean; fin.invstd = save_invstd;
+        fin.dgamma = dgamma; fin.dbeta = dbeta;
+        bn_reduce_pow2_kernel<true><<<bn_grid(total4), 256, 0, st>>>(x, dy, save_mean, save_invstd, scratch, total4, C, fin);
         int e2 = after_launch("bn_reduce_pow2_kernel");
         if (e2) return e2;
         const int g2 = bn_grid(total4);
-#define SN_LAUNCHP(A, M) bn_bwd_apply_pow2_kernel<A, M><<<g2, 256, 0, st>>>(dy, x, gamma, save_mean, save_invstd, dx, dgamma, dbeta, scratch, total4, C, rows)
+#define SN_LAUNCHP(A, M) bn_bwd_apply_pow2_kernel<A, M><<<g2, 256, 0, st>>>(dy, x, dx, scratch, total4, C)
         if (accumulate_dx) { if (mask_relu) SN_LAUNCHP(true, true); else SN_LAUNCHP(true, false); }
         else { if (mask_relu) SN_LAUNCHP(false, true); else SN_LAUNCHP(false, false); }
 #undef SN_LAUNCHP

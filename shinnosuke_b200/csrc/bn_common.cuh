@@ -1,0 +1,90 @@
+// Shared by bn.cu and bn_pool.cu: layout of the float64 scratch and the "last block finalises"
+// step that turns the per-channel sums into the few fp32 constants the apply pass needs.
+//
+// scratch (>= 20*C doubles, zeroed by the host wrapper before the reduce kernel):
+//   [0, 16C)        BN_SLOTS copies of {sum_a[C], sum_b[C]}  (slot = blockIdx.x % BN_SLOTS: short atomic chains)
+//   [16C, 18C)      4*C floats: p0[C], p1[C], p2[C] (apply-pass constants), 1 spare row
+//   [18C]           ticket counter (unsigned)
+//
+// Doing the float64 division / sqrt ONCE per channel here (instead of in the prologue of every
+// apply block) matters: B200 issues 64 FP64 ops/clk/SM, and a 256-thread block recomputing
+// 4 channels each spent ~2 us in its prologue.
+#pragma once
+#include "common.cuh"
+
+namespace sn {
+
+constexpr int BN_SLOTS = 8;
+constexpr int BN_SCRATCH_DOUBLES_PER_C = 20;
+
+struct BnFinal {
+    int bwd;                       // 0: forward statistics, 1: backward sums
+    long long rows;
+    int C;
+    // forward
+    const float *x;                // pivot row x[0][c]
+    const float *gamma, *beta;
+    float *save_mean, *save_invstd, *moving_mean, *moving_var;
+    float eps, momentum;
+    // backward
+    const float *mean, *invstd;
+    float *dgamma, *dbeta;
+};
+
+__device__ __forceinline__ float *bn_params(double *scratch, int C) { return reinterpret_cast<float *>(scratch + 16 * (size_t)C); }
+__device__ __forceinline__ const float *bn_params(const double *scratch, int C) { return reinterpret_cast<const float *>(scratch + 16 * (size_t)C); }
+
+// Call at the end of a reduce kernel, after this block's atomics.  The last block to arrive
+// computes, per channel:
+//   forward : p0 = gamma*invstd, p1 = beta - gamma*invstd*mean            (y  = p0*x + p1)
+//   backward: p0 = gamma*invstd, p1 = -p0*k3*invstd, p2 = -p0*k2 - p1*mean (dx = p0*dy + p1*x + p2)
+//             with k2 = sum(dy)/rows, k3 = sum(dy*xhat)/rows; dgamma += sum(dy*xhat), dbeta += sum(dy)
+__device__ __forceinline__ void bn_finalize_last_block(double *scratch, const BnFinal &f) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned *ticket = reinterpret_cast<unsigned *>(scratch + 18 * (size_t)f.C);
+        is_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int C = f.C;
+    float *prm = bn_params(scratch, C);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double a = 0, b = 0;
+#pragma unroll
+        for (int s = 0; s < BN_SLOTS; ++s) {
+            a += __ldcg(scratch + (size_t)s * 2 * C + c);
+            b += __ldcg(scratch + (size_t)s * 2 * C + C + c);
+        }
+        if (!f.bwd) {
+            const double pivot = (double)f.x[c];
+            const double m1 = a / (double)f.rows;                       // E[x - pivot]
+            double var = b / (double)f.rows - m1 * m1;
+            if (var < 0) var = 0;
+            const double m = pivot + m1;
+            const double is = 1.0 / sqrt(var + (double)f.eps);
+            const double g = (double)f.gamma[c];
+            prm[c] = (float)(g * is);
+            prm[C + c] = (float)((double)f.beta[c] - g * is * m);
+            f.save_mean[c] = (float)m;
+            f.save_invstd[c] = (float)is;
+            f.moving_mean[c] = f.momentum * f.moving_mean[c] + (1.f - f.momentum) * (float)m;
+            f.moving_var[c] = f.momentum * f.moving_var[c] + (1.f - f.momentum) * (float)var;
+        } else {
+            const double is = (double)f.invstd[c], mu = (double)f.mean[c];
+            const double k2 = a / (double)f.rows, k3 = b / (double)f.rows;
+            const double p0 = (double)f.gamma[c] * is;
+            const double p1 = -p0 * k3 * is;
+            prm[c] = (float)p0;
+            prm[C + c] = (float)p1;
+            prm[2 * C + c] = (float)(-p0 * k2 - p1 * mu);
+            if (f.dbeta) f.dbeta[c] += (float)a;
+            if (f.dgamma) f.dgamma[c] += (float)b;
+        }
+    }
+}
+
+}  // namespace sn

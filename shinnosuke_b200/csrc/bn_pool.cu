@@ -10,17 +10,10 @@
 // layers/Convolution.py:287-362): biased variance, eps in the sqrt, moving statistics, tie-split
 // or first-argmax routing, and (optionally) the producing layer's ReLU mask applied to dX.
 #include "common.cuh"
+#include "bn_common.cuh"
 using namespace sn;
 
 namespace {
-
-constexpr int SLOTS = 8;        // must match bn.cu (layout of the float64 scratch)
-
-__device__ __forceinline__ void slot_sums(const double *__restrict__ scratch, int C, int c, double &a, double &b) {
-    a = 0; b = 0;
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) { a += scratch[(size_t)s * 2 * C + c]; b += scratch[(size_t)s * 2 * C + C + c]; }
-}
 
 __device__ __forceinline__ float comp(const float4 &v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
 __device__ __forceinline__ void setc(float4 &v, int k, float x) { if (k == 0) v.x = x; else if (k == 1) v.y = x; else if (k == 2) v.z = x; else v.w = x; }
@@ -42,37 +35,14 @@ __device__ __forceinline__ Win window(const float *x, long long idx, int Q, int 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) bn_pool_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
-                                                          const float *__restrict__ beta, float *__restrict__ y,
-                                                          uint32_t *__restrict__ code, float *__restrict__ save_mean,
-                                                          float *__restrict__ save_invstd, float *__restrict__ moving_mean,
-                                                          float *__restrict__ moving_var, const double *__restrict__ scratch,
-                                                          long long windows4, int C, int W, int oh, int ow, long long rows,
-                                                          float eps, float momentum) {
+__global__ void __launch_bounds__(256) bn_pool_fwd_kernel(const float *__restrict__ x, float *__restrict__ y,
+                                                          uint32_t *__restrict__ code, const double *__restrict__ scratch,
+                                                          long long windows4, int C, int W, int oh, int ow) {
     const int Q = C >> 2;
     const int cq = threadIdx.x % Q;
-    float sc[4], sh[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int c = cq * 4 + k;
-        const double pivot = (double)__ldg(x + c);
-        double s1, s2;
-        slot_sums(scratch, C, c, s1, s2);
-        const double m1 = s1 / (double)rows;
-        double var = s2 / (double)rows - m1 * m1;
-        if (var < 0) var = 0;
-        const double m = pivot + m1;
-        const double is = 1.0 / sqrt(var + (double)eps);
-        const float g = __ldg(gamma + c);
-        sc[k] = (float)(g * is);
-        sh[k] = (float)(__ldg(beta + c) - g * is * m);
-        if (blockIdx.x == 0 && threadIdx.x < Q) {
-            save_mean[c] = (float)m;
-            save_invstd[c] = (float)is;
-            moving_mean[c] = momentum * moving_mean[c] + (1.f - momentum) * (float)m;
-            moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * (float)var;
-        }
-    }
+    const float *prm = bn_params(scratch, C);
+    const float4 sc4 = ldg4(prm + cq * 4), sh4 = ldg4(prm + C + cq * 4);
+    const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
     const long long stride = (long long)gridDim.x * 256;
     for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < windows4; idx += stride) {
         const Win w = window(x, idx, Q, ow, oh, W, C);
@@ -112,7 +82,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(const float *__restrict__ dyp, const uint32_t *__restrict__ code,
                                                                  const float *__restrict__ x, const float *__restrict__ mean,
                                                                  const float *__restrict__ invstd, double *__restrict__ scratch,
-                                                                 long long windows4, int C, int W, int oh, int ow) {
+                                                                 long long windows4, int C, int W, int oh, int ow, BnFinal fin) {
     const int Q = C >> 2;
     const int cq = threadIdx.x % Q;
     float mu[4], is[4];
@@ -156,38 +126,24 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(const float *__
         for (int k = 0; k < 4; ++k) {
             double ta = 0, tb = 0;
             for (int t = threadIdx.x; t < 256; t += Q) { ta += sa[t][k]; tb += sb[t][k]; }
-            double *slot = scratch + (size_t)(blockIdx.x % SLOTS) * 2 * C;
+            double *slot = scratch + (size_t)(blockIdx.x % BN_SLOTS) * 2 * C;
             atomicAdd(slot + cq * 4 + k, ta);
             atomicAdd(slot + C + cq * 4 + k, tb);
         }
     }
+    bn_finalize_last_block(scratch, fin);
 }
 
 template <int MODE, bool MASK>
 __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__restrict__ dyp, const uint32_t *__restrict__ code,
-                                                                const float *__restrict__ x, const float *__restrict__ gamma,
-                                                                const float *__restrict__ mean, const float *__restrict__ invstd,
-                                                                float *__restrict__ dx, float *__restrict__ dgamma,
-                                                                float *__restrict__ dbeta, const double *__restrict__ scratch,
-                                                                long long windows4, int C, int W, int oh, int ow, long long rows) {
+                                                                const float *__restrict__ x, float *__restrict__ dx,
+                                                                const double *__restrict__ scratch, long long windows4, int C,
+                                                                int W, int oh, int ow) {
     const int Q = C >> 2;
     const int cq = threadIdx.x % Q;
-    float k1[4], k2[4], k3[4], mu[4], is[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int c = cq * 4 + k;
-        double sdy, sdyx;
-        slot_sums(scratch, C, c, sdy, sdyx);
-        mu[k] = __ldg(mean + c);
-        is[k] = __ldg(invstd + c);
-        k1[k] = __ldg(gamma + c) * is[k];
-        k2[k] = (float)(sdy / (double)rows);
-        k3[k] = (float)(sdyx / (double)rows);
-        if (blockIdx.x == 0 && threadIdx.x < Q) {
-            if (dbeta) dbeta[c] += (float)sdy;
-            if (dgamma) dgamma[c] += (float)sdyx;
-        }
-    }
+    const float *prm = bn_params(scratch, C);
+    const float4 a4 = ldg4(prm + cq * 4), b4 = ldg4(prm + C + cq * 4), c4 = ldg4(prm + 2 * C + cq * 4);
+    const float pa[4] = {a4.x, a4.y, a4.z, a4.w}, pb[4] = {b4.x, b4.y, b4.z, b4.w}, pc[4] = {c4.x, c4.y, c4.z, c4.w};
     const long long stride = (long long)gridDim.x * 256;
     for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < windows4; idx += stride) {
         const Win w = window(x, idx, Q, ow, oh, W, C);
@@ -202,8 +158,7 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__r
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float xv = comp(v[e], k);
-                const float xh = (xv - mu[k]) * is[k];
-                float r = k1[k] * (routed<MODE>(gk, cd, e) - k2[k] - xh * k3[k]);
+                float r = fmaf(pa[k], routed<MODE>(gk, cd, e), fmaf(pb[k], xv, pc[k]));
                 if (MASK && relu_blocked(xv)) r = 0.f;
                 setc(o[e], k, r);
             }
@@ -244,17 +199,15 @@ int sn_bn_pool_fwd_train(const float *x, const float *gamma, const float *beta, 
     cudaStream_t st = as_stream(stream);
     const long long rows = (long long)N * H * W;
     // pass 1: per-channel statistics of x (the plain BatchNorm reduction, scratch zeroed inside)
-    int e = sn_batchnorm_stats(x, scratch, rows, C, stream);
+    int e = sn_batchnorm_stats(x, gamma, beta, save_mean, save_invstd, moving_mean, moving_var, scratch, rows, C, eps, momentum, stream);
     if (e) return e;
     const int oh = H / 2, ow = W / 2;
     const long long windows4 = (long long)N * oh * ow * (C / 4);
     const int grid = grid_for_windows(windows4);
     if (pool_mode == SN_POOL_TIE_SPLIT)
-        bn_pool_fwd_kernel<SN_POOL_TIE_SPLIT><<<grid, 256, 0, st>>>(x, gamma, beta, y_pool, (uint32_t *)code, save_mean, save_invstd,
-                                                                    moving_mean, moving_var, scratch, windows4, C, W, oh, ow, rows, eps, momentum);
+        bn_pool_fwd_kernel<SN_POOL_TIE_SPLIT><<<grid, 256, 0, st>>>(x, y_pool, (uint32_t *)code, scratch, windows4, C, W, oh, ow);
     else
-        bn_pool_fwd_kernel<SN_POOL_FIRST_ARGMAX><<<grid, 256, 0, st>>>(x, gamma, beta, y_pool, (uint32_t *)code, save_mean, save_invstd,
-                                                                       moving_mean, moving_var, scratch, windows4, C, W, oh, ow, rows, eps, momentum);
+        bn_pool_fwd_kernel<SN_POOL_FIRST_ARGMAX><<<grid, 256, 0, st>>>(x, y_pool, (uint32_t *)code, scratch, windows4, C, W, oh, ow);
     return after_launch("bn_pool_fwd_kernel");
 }
 
@@ -270,14 +223,17 @@ int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, co
     const long long windows4 = (long long)N * oh * ow * (C / 4);
     const int grid = grid_for_windows(windows4);
     const uint32_t *cd = (const uint32_t *)code;
-    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C * SLOTS, st));
+    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * BN_SCRATCH_DOUBLES_PER_C * C, st));
+    BnFinal fin{};
+    fin.bwd = 1; fin.rows = rows; fin.C = C; fin.gamma = gamma; fin.mean = save_mean; fin.invstd = save_invstd;
+    fin.dgamma = dgamma; fin.dbeta = dbeta;
     if (pool_mode == SN_POOL_TIE_SPLIT)
-        bn_pool_bwd_reduce_kernel<SN_POOL_TIE_SPLIT><<<grid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow);
+        bn_pool_bwd_reduce_kernel<SN_POOL_TIE_SPLIT><<<grid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
     else
-        bn_pool_bwd_reduce_kernel<SN_POOL_FIRST_ARGMAX><<<grid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow);
+        bn_pool_bwd_reduce_kernel<SN_POOL_FIRST_ARGMAX><<<grid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
     int e = after_launch("bn_pool_bwd_reduce_kernel");
     if (e) return e;
-#define SN_LAUNCH(M, K) bn_pool_bwd_apply_kernel<M, K><<<grid, 256, 0, st>>>(dy_pool, cd, x, gamma, save_mean, save_invstd, dx, dgamma, dbeta, scratch, windows4, C, W, oh, ow, rows)
+#define SN_LAUNCH(M, K) bn_pool_bwd_apply_kernel<M, K><<<grid, 256, 0, st>>>(dy_pool, cd, x, dx, scratch, windows4, C, W, oh, ow)
     if (pool_mode == SN_POOL_TIE_SPLIT) { if (mask_relu) SN_LAUNCH(SN_POOL_TIE_SPLIT, true); else SN_LAUNCH(SN_POOL_TIE_SPLIT, false); }
     else { if (mask_relu) SN_LAUNCH(SN_POOL_FIRST_ARGMAX, true); else SN_LAUNCH(SN_POOL_FIRST_ARGMAX, false); }
 #undef SN_LAUNCH

@@ -46,7 +46,7 @@ class BatchNormalization(Layer):
         if self._stats is None:
             self._stats = dict(mm=DeviceTensor.from_numpy(self._mm_host), mv=DeviceTensor.from_numpy(self._mv_host),
                                mean=DeviceTensor.empty((C,)), invstd=DeviceTensor.empty((C,)),
-                               scratch=zeros(16 * C, torch().float64))
+                               scratch=zeros(20 * C + 2, torch().float64))
         return self._stats
 
     @property
