@@ -13,6 +13,9 @@ int conv_igemm_tc(const float *x, const float *w, const float *bias, float *out,
 int conv_wgrad_tc(const float *x, const float *dy, float *dw, int N, int C, int IH, int IW, int F, int kh, int kw, int OH,
                   int OW, int pad_h, int pad_w, cudaStream_t st);
 int flip_transpose_filters(const float *w, float *wt, int F, int C, int kh, int kw, cudaStream_t st);
+bool wgrad_halo_eligible(int N, int C, int OH, int OW, int F, int kh, int kw, int stride);
+int conv_wgrad_halo_tc(const float *x, const float *dy, float *dw, int N, int C, int IH, int IW, int F, int kh, int kw, int OH,
+                       int OW, int pad_h, int pad_w, cudaStream_t st);
 int colsum_accumulate(const float *dy, float *db, long long rows, int F, cudaStream_t st);
 bool stem_tc_eligible(int N, int C, int OH, int OW, int F, int kh, int kw);
 int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
@@ -112,13 +115,15 @@ int sn_conv2d_wgrad(const float *x, const float *dy, float *dw, float *db, int N
     }
     if (geom_ok && precision == SN_PREC_TF32) {
         const int oh = (H + 2 * pad_h - kh) / stride + 1, ow = (W + 2 * pad_w - kw) / stride + 1;
-        if (wgrad_tc_eligible(N, C, oh, ow, F, stride)) {
+        const bool halo = wgrad_halo_eligible(N, C, oh, ow, F, kh, kw, stride);
+        if (halo || wgrad_tc_eligible(N, C, oh, ow, F, stride)) {
             cudaStream_t st = as_stream(stream);
             if (!accumulate) {
                 SN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)F * kh * kw * C, st));
                 if (db) SN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * F, st));
             }
-            e = conv_wgrad_tc(x, dy, dw, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, st);
+            e = halo ? conv_wgrad_halo_tc(x, dy, dw, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, st)
+                     : conv_wgrad_tc(x, dy, dw, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, st);
             if (e || !db) return e;
             return colsum_accumulate(dy, db, (long long)N * oh * ow, F, st);
         }

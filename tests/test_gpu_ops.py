@@ -61,14 +61,13 @@ def test_conv2d_golden(name):
 def test_conv2d_vs_oracle(shape):
     from shinnosuke_b200 import Conv2D
     N, C, H, W, F, k, stride, padding, act = shape
-    r = np.random.default_rng(hash(shape) % 2**32)
+    r = np.random.default_rng(sum((i + 1) * v for i, v in enumerate(shape[:7])))      # stable across processes
     x = r.standard_normal((N, C, H, W)).astype(np.float32).astype(np.float64)
     w = (0.1 * r.standard_normal((F, C, k, k))).astype(np.float32).astype(np.float64)
     b = r.standard_normal((1, F)).astype(np.float32).astype(np.float64)
     (_, _, oh, ow), pad = O.conv_output_shape((N, C, H, W), F, (k, k), stride, padding)
     gup = r.standard_normal((N, F, oh, ow)).astype(np.float32).astype(np.float64)
     y_ref, cache = O.conv2d_forward(x, w, b, stride, pad, act)
-    dx_ref, dw_ref, db_ref = O.conv2d_backward(gup, cache)
     layer = Conv2D(F, (k, k), stride=stride, padding=padding, activation=act)
     from shinnosuke_b200 import Input, Activation
     from shinnosuke_b200.device import as_device
@@ -77,7 +76,17 @@ def test_conv2d_vs_oracle(shape):
     inp.input_tensor = x
     for l in (inp, src, layer):
         l.forward(True)
-    assert rel_err(np.asarray(layer.output_tensor), y_ref) < TOL32
+    y = np.asarray(layer.output_tensor)
+    assert rel_err(y, y_ref) < TOL32
+    if act == 'relu':
+        # a pre-activation within fp32 rounding (~1e-7) of zero may sit on the other side of the ReLU
+        # kink than in float64; one such element moves dW by a whole |g*x| term.  The backward kernels
+        # are therefore checked against the oracle run with the mask the device forward produced, and
+        # the number of such elements is bounded (expected: 0, rarely 1).
+        blocked = np.signbit(y)
+        assert np.count_nonzero(blocked != (cache['z'] < 0)) <= 2
+        cache['z'] = np.where(blocked, -1.0, 1.0)
+    dx_ref, dw_ref, db_ref = O.conv2d_backward(gup, cache)
     layer._seed_grads(as_device(gup)); layer.backward()
     assert rel_err(np.asarray(layer.variables[0].grads), dw_ref) < TOL32
     assert rel_err(np.asarray(layer.variables[1].grads).reshape(-1), db_ref) < TOL32
