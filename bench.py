@@ -36,6 +36,9 @@ CONFIGS = {
     'cfg1': dict(name='README CNN 1x28x28: Conv2D(8,2x2,VALID,relu)+MaxPool2x2+Flatten+Dense10, SGD',
                  shape=(1, 28, 28), per_gpu_batch=256, flops_per_sample=0.174e6),
     'cfg2': dict(name='MLP 784-500-10, SGD', shape=(784,), per_gpu_batch=128, flops_per_sample=1.60e6),
+    'cfg4': dict(name='ResNet-style 3x32x32 (functional API): Conv64 + residual block@64 + pool + Conv128 + residual block@128 '
+                      '+ pool + Dense10, BatchNorm in the blocks, SGD', shape=(3, 32, 32), per_gpu_batch=128,
+                 flops_per_sample=1026.8e6),
 }
 
 
@@ -52,7 +55,7 @@ def peaks():
 def synth(cfg, n, seed=1234):
     r = np.random.default_rng(seed)
     shape = CONFIGS[cfg]['shape']
-    if cfg == 'cfg3':
+    if cfg in ('cfg3', 'cfg4'):
         X = r.standard_normal((n,) + shape, dtype=np.float32)
     else:
         X = r.random((n,) + shape, dtype=np.float32)
@@ -63,8 +66,25 @@ def synth(cfg, n, seed=1234):
 
 
 def build_model(cfg, precision):
-    from shinnosuke_b200 import Sequential, Conv2D, BatchNormalization, MaxPooling2D, Flatten, Dense
+    from shinnosuke_b200 import (Sequential, Model, Input, Conv2D, BatchNormalization, MaxPooling2D, Flatten, Dense,
+                                 Activation, Add)
     np.random.seed(0)
+    if cfg == 'cfg4':
+        def block(h, width):
+            r = Conv2D(width, (3, 3), padding='SAME', activation='linear', initializer='normal')(h)
+            r = Activation('relu')(BatchNormalization()(r))
+            r = Conv2D(width, (3, 3), padding='SAME', activation='linear', initializer='normal')(r)
+            r = BatchNormalization()(r)
+            return MaxPooling2D((2, 2))(Activation('relu')(Add()([h, r])))
+        x_in = Input(shape=(None, 3, 32, 32))
+        h = Conv2D(64, (3, 3), padding='SAME', activation='relu', initializer='normal')(x_in)
+        h = block(h, 64)
+        h = Conv2D(128, (3, 3), padding='SAME', activation='relu', initializer='normal')(h)
+        h = block(h, 128)
+        y = Dense(10, activation='softmax')(Flatten()(h))
+        m = Model(inputs=x_in, outputs=y)
+        m.compile(optimizer='sgd', loss='sparse_categorical_crossentropy', precision=precision)
+        return m
     m = Sequential()
     if cfg == 'cfg3':
         first = True
@@ -90,7 +110,7 @@ def build_model(cfg, precision):
 
 def oracle_spec(cfg):
     from oracle import shinnosuke_oracle as O
-    return {'cfg1': O.spec_cfg1, 'cfg2': O.spec_cfg2, 'cfg3': O.spec_cfg3}[cfg]()
+    return {'cfg1': O.spec_cfg1, 'cfg2': O.spec_cfg2, 'cfg3': O.spec_cfg3, 'cfg4': O.spec_cfg4}[cfg]()
 
 
 class ClockSampler(object):
@@ -238,7 +258,7 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = args.config
-    sample_batch = {'cfg3': 64, 'cfg1': 256, 'cfg2': 128}[cfg]
+    sample_batch = {'cfg3': 64, 'cfg1': 256, 'cfg2': 128, 'cfg4': 32}[cfg]
     steps = max(1, args.steps)
     value, s_per_step = cpu_oracle_throughput(cfg, sample_batch, steps, max(1, min(args.warmup, 2)))
     cores = os.cpu_count()
@@ -298,7 +318,7 @@ def run_ours(args):
     losses_e2e = list(m.train_loss[-K:])
 
     # ---- leg 2: inputs resident in HBM, graph replays (value) -------------------
-    inp = m.layers[0]
+    inp = m._input_layer()
     n_loc = B
     xs = inp._buf('fit_x0', (n_loc,) + X.shape[1:], 'nhwc' if X.ndim == 4 else 'flat')
     ys = inp._buf('fit_y0', (n_loc, Y.shape[1]), 'flat')
@@ -336,8 +356,8 @@ def run_ours(args):
             os.makedirs(os.path.dirname(os.path.abspath(args.kernel_table)), exist_ok=True)
             with open(args.kernel_table, 'w') as f:
                 json.dump(dict(config=cfg, per_gpu_batch=B, precision=precision, step_ms_graph=dev_ms / K, kernels=rows), f, indent=1)
-        cpu_batch = {'cfg3': 64, 'cfg1': 256, 'cfg2': 128}[cfg]
-        cpu_steps = {'cfg3': 6, 'cfg1': 30, 'cfg2': 200}[cfg]
+        cpu_batch = {'cfg3': 64, 'cfg1': 256, 'cfg2': 128, 'cfg4': 32}[cfg]
+        cpu_steps = {'cfg3': 6, 'cfg1': 30, 'cfg2': 200, 'cfg4': 3}[cfg]
         if world == 1 and not args.no_cpu_baseline:
             cpu_val, _ = cpu_oracle_throughput(cfg, cpu_batch, cpu_steps)
             cpu = dict(value=cpu_val, unit='samples/s', cores=os.cpu_count(), kind='port',
@@ -349,7 +369,7 @@ def run_ours(args):
                     warmup=Wm, ms_per_step=dev_ms / K, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype=precision, data='synthetic',
                     config=dict(workload=CONFIGS[cfg]['name'], per_gpu_batch=B, global_batch=G, parallelism='dp%d' % world,
-                                precision=precision, l2='working set per step exceeds the 126 MB L2 (no flush)' if cfg == 'cfg3' and B >= 256
+                                precision=precision, l2='working set per step exceeds the 126 MB L2 (no flush)' if cfg in ('cfg3', 'cfg4') and B >= 128
                                 else 'small working set, no flush: the step is launch-latency bound',
                                 step_tflops=CONFIGS[cfg]['flops_per_sample'] * G / world / (dev_ms / K * 1e-3) / 1e12),
                     clocks=clocks,

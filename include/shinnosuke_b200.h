@@ -91,6 +91,8 @@ SN_API int sn_nhwc_to_nchw(const float *src, float *dst, int N, int C, int H, in
 SN_API int sn_cast_f64_to_f32(const double *src, float *dst, long long n, void *stream);
 SN_API int sn_cast_f32_to_f64(const float *src, double *dst, long long n, void *stream);
 SN_API int sn_axpy(float alpha, const float *x, float *y, long long n, void *stream);     /* y += alpha*x */
+/* Add.forward, layers/Base.py:378-385: out = a + b (same shapes; residual connections) */
+SN_API int sn_add(const float *a, const float *b, float *out, long long n, void *stream);
 
 /* ---------------------------------------------------------------- Conv2D */
 /* Conv2D.forward, layers/Convolution.py:131-161 (true zero padding):

@@ -377,7 +377,9 @@ def to_categorical(labels):
 # a tiny sequential driver (models.py:30-137) used for trajectory parity and as
 # the bench CPU baseline.  ``spec`` is a list of tuples:
 #   ('conv', F, k, stride, padding, act) | ('pool', p) | ('pool', p, mode) |
-#   ('flatten',) | ('dense', n_out, act) | ('bn',)
+#   ('flatten',) | ('dense', n_out, act) | ('bn',) | ('act', name)
+#   ('tap', key) | ('add', key)  — residual connection (layers/Base.py:352-411, Add): 'tap'
+#   remembers the current map, 'add' sums it back in; backward sends the gradient both ways.
 # --------------------------------------------------------------------------
 
 class OracleNet:
@@ -418,6 +420,8 @@ class OracleNet:
                 c = shape[1]
                 self.slots.append(self._add(np.ones(c), np.zeros(c)))
                 self.state.append(dict(mm=np.zeros(c), mv=np.ones(c)))
+            elif kind in ('act', 'tap', 'add'):
+                self.slots.append(()); self.state.append({})
             else:
                 raise ValueError(kind)
         self.velocity = None
@@ -433,6 +437,7 @@ class OracleNet:
 
     def forward(self, x, is_training=True):
         caches = []
+        taps = {}
         h = x
         for op, slot, st in zip(self.spec, self.slots, self.state):
             kind = op[0]
@@ -454,11 +459,21 @@ class OracleNet:
                                                  st['mm'], st['mv'], is_training=is_training)
                 if is_training:
                     st['mm'], st['mv'] = mm, mv
+            elif kind == 'act':
+                c = h
+                h = apply_activation(h, op[1])
+            elif kind == 'tap':
+                taps[op[1]] = h
+                c = None
+            elif kind == 'add':
+                h = taps[op[1]] + h
+                c = None
             caches.append(c)
         return h, caches
 
     def backward(self, dy, caches):
         g = dy
+        skip = {}
         for li in range(len(self.spec) - 1, -1, -1):
             op, slot, c = self.spec[li], self.slots[li], caches[li]
             kind = op[0]
@@ -478,6 +493,12 @@ class OracleNet:
                 g, dgm, dbt = batchnorm_backward(g, c)
                 self.grads[slot[0]] = self.grads[slot[0]] + dgm
                 self.grads[slot[1]] = self.grads[slot[1]] + dbt
+            elif kind == 'act':
+                g = activation_backward(g, c, op[1])
+            elif kind == 'add':
+                skip[op[1]] = g                     # the same gradient reaches both operands
+            elif kind == 'tap':
+                g = g + skip[op[1]]
 
     def step(self, xs, ys):
         """One minibatch of models.py:70-92: forward, loss grad, backward sweep,
@@ -508,6 +529,20 @@ def spec_cfg1():
 
 def spec_cfg2():
     return [('dense', 500, 'relu'), ('dense', 10, 'softmax')], (None, 784)
+
+
+def spec_residual(width, k=3, padding='SAME', stem=True):
+    """One residual block of BASELINE config 4: [Conv-BN-ReLU-Conv-BN] + skip, ReLU, 2x2 pool."""
+    s = [('conv', width, k, 1, padding, 'relu')] if stem else []
+    s += [('tap', 'skip'), ('conv', width, k, 1, padding, 'linear'), ('bn',), ('act', 'relu'),
+          ('conv', width, k, 1, padding, 'linear'), ('bn',), ('add', 'skip'), ('act', 'relu'), ('pool', 2)]
+    return s
+
+
+def spec_cfg4():
+    """stem Conv64 -> residual block @64 -> pool -> Conv128 -> residual block @128 -> pool -> Dense10."""
+    s = spec_residual(64) + spec_residual(128) + [('flatten',), ('dense', 10, 'softmax')]
+    return s, (None, 3, 32, 32)
 
 
 def spec_cfg3():

@@ -63,6 +63,20 @@ __global__ void axpy_kernel(float a, const float *__restrict__ x, float *__restr
         for (long long i = t; i < n; i += stride) y[i] += a * x[i];
     }
 }
+__global__ void add_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ o, long long n) {
+    long long n4 = n >> 2;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)o) & 15) == 0) {
+        for (long long i = t; i < n4; i += stride) {
+            float4 x = ldg4(a + 4 * i), y = ldg4(b + 4 * i);
+            reinterpret_cast<float4 *>(o)[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+        }
+        for (long long i = 4 * n4 + t; i < n; i += stride) o[i] = a[i] + b[i];
+    } else {
+        for (long long i = t; i < n; i += stride) o[i] = a[i] + b[i];
+    }
+}
 __global__ void relu_bwd_kernel(float *__restrict__ dy, const float *__restrict__ y, long long n) {
     long long n4 = n >> 2;
     long long stride = (long long)gridDim.x * blockDim.x;
@@ -228,6 +242,12 @@ int sn_axpy(float alpha, const float *x, float *y, long long n, void *stream) {
     if (!n) return SN_OK;
     axpy_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(alpha, x, y, n);
     return after_launch("axpy_kernel");
+}
+int sn_add(const float *a, const float *b, float *out, long long n, void *stream) {
+    SN_REQUIRE(a && b && out && n >= 0, "bad arguments");
+    if (!n) return SN_OK;
+    add_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(a, b, out, n);
+    return after_launch("add_kernel");
 }
 int sn_relu_bwd(float *dy, const float *y, long long n, void *stream) {
     SN_REQUIRE(dy && y && n >= 0, "bad arguments");

@@ -257,3 +257,38 @@ def upload_batch(layer, host_array):
     lib.sn_memcpy_h2d(out.ptr, a.ctypes.data, a.nbytes, st)
     lib.sn_stream_sync(st)
     return out
+
+
+class Add(Layer):
+    """Element-wise sum of two layers (reference: layers/Base.py:352-411), the residual connection
+    of BASELINE config 4.  The reference's `Add.__call__` dereferences `output_tensor.shape` of its
+    operands at graph-build time, when it is still None (:358-359), and its model then
+    registers the operand LAYERS as trainable variables (:324); here the shape comes from
+    `output_shape` and the layer has no variables.  Operands must have equal shapes (no
+    broadcasting: the broadcast-reduction branch of :392-409 is off the training path)."""
+
+    def __call__(self, inbounds):
+        if not isinstance(inbounds, (list, tuple)) or len(inbounds) != 2:
+            raise ValueError('Add takes a list of two layers')
+        x, y = inbounds
+        if tuple(x.output_shape[1:]) != tuple(y.output_shape[1:]):
+            raise NotImplementedError('device Add needs operands of equal shape, got %s and %s'
+                                      % (x.output_shape, y.output_shape))
+        super(Add, self).__call__(list(inbounds))
+        self.output_shape = tuple(x.output_shape)
+        return self
+
+    def connect(self, inbound):
+        raise TypeError('Add has two operands: use the functional API, Add()([a, b])')
+
+    def forward(self, is_training=True):
+        a, b = (layer.output_tensor for layer in self.inbounds)
+        out = self._buf('out', a.shape, a.layout)
+        lib.sn_add(a.ptr, b.ptr, out.ptr, a.size, current_stream())
+        self.output_tensor = out
+        super(Add, self).forward(is_training)
+
+    def backward(self):
+        g = self.grads
+        for layer in self.inbounds:
+            self._push_grad(layer, lambda dst, acc: dst.add_(g) if acc else dst.copy_from(g))

@@ -1,5 +1,5 @@
 from .Base import *          # noqa: F401,F403
-from .Base import Layer, Variable, Input
+from .Base import Layer, Variable, Input, Add
 from .Activation import Activation
 from .FC import Flatten, Dense
 from .Convolution import Conv2D, ZeroPadding2D, MaxPooling2D

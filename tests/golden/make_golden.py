@@ -300,6 +300,39 @@ def traj_cfg3_small():
          denseW=m.layers[-1].variables[0].output_tensor, xsum=np.array(X.sum()))
 
 
+def traj_residual():
+    """Functional residual graph (BASELINE config 4's building block) through the reference with
+    the two oracle-side workarounds of SURVEY.md 8(c)(iii): operands of Add get a dummy
+    output_tensor before Add()([a, b]) (layers/Base.py:358-359 dereferences it at build time), and
+    trainable_variables is filtered to real Variables after compile (models.py:304-307).  1x1 VALID
+    convolutions, because the reference cannot back-propagate through a mid-network ZeroPadding2D."""
+    from reference.layers.Base import Add
+    np.random.seed(0)
+    X_in = Input(shape=(None, 3, 8, 8))
+    stem = Conv2D(8, (1, 1), padding='VALID', activation='relu', initializer='normal')(X_in)
+    r = Conv2D(8, (1, 1), padding='VALID', activation='linear', initializer='normal')(stem)
+    r = BatchNormalization()(r)
+    r = Activation('relu')(r)
+    r = Conv2D(8, (1, 1), padding='VALID', activation='linear', initializer='normal')(r)
+    r = BatchNormalization()(r)
+    stem.output_tensor = np.zeros((1, 8, 8, 8)); r.output_tensor = np.zeros((1, 8, 8, 8))
+    h = Add()([stem, r])
+    stem.output_tensor = None; r.output_tensor = None
+    h = Activation('relu')(h)
+    h = MaxPooling2D((2, 2))(h)
+    h = Flatten()(h)
+    y = Dense(10, initializer='normal', activation='softmax')(h)
+    model = Model(inputs=X_in, outputs=y)
+    model.compile(optimizer='sgd', loss='sparse_categorical_crossentropy')
+    model.trainable_variables = [v for v in model.trainable_variables if isinstance(v, Variable)]
+    r_ = np.random.default_rng(1234)
+    X = f32(r_.standard_normal((48, 3, 8, 8)))
+    Y = to_categorical(np.concatenate([np.arange(10), r_.integers(0, 10, 38)]))
+    quiet(model.fit, X, Y, batch_size=16, epochs=1, shuffle=False, validation_ratio=0.)
+    save('traj_residual', train_loss=np.array(model.train_loss), train_acc=np.array(model.train_acc),
+         stemW=stem.variables[0].output_tensor, denseW=y.variables[0].output_tensor, xsum=np.array(X.sum()))
+
+
 class _FirstPad(object):
     """Sequential.compile calls layers[0].connect(None); ZeroPadding2D.connect
     dereferences prev_layer (layers/Convolution.py:219).  This thin proxy gives
@@ -343,3 +376,4 @@ if __name__ == '__main__':
     traj_cfg2()
     traj_cfg1()
     traj_cfg3_small()
+    traj_residual()

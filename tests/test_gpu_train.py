@@ -230,3 +230,50 @@ def test_fused_and_unfused_models_agree():
         assert (m.layers[1].output_tensor is None) == fuse
     assert np.allclose(runs[0][0], runs[1][0], rtol=1e-5)
     assert rel_err(runs[0][1], runs[1][1]) < 1e-5
+
+
+def _residual_model(width, k, padding, in_shape, precision='fp32'):
+    from shinnosuke_b200 import Model, Input, Conv2D, BatchNormalization, Activation, Add, MaxPooling2D, Flatten, Dense
+    np.random.seed(0)
+    X_in = Input(shape=(None,) + in_shape)
+    stem = Conv2D(width, (k, k), padding=padding, activation='relu', initializer='normal')(X_in)
+    r = Conv2D(width, (k, k), padding=padding, activation='linear', initializer='normal')(stem)
+    r = BatchNormalization()(r)
+    r = Activation('relu')(r)
+    r = Conv2D(width, (k, k), padding=padding, activation='linear', initializer='normal')(r)
+    r = BatchNormalization()(r)
+    h = Add()([stem, r])
+    h = Activation('relu')(h)
+    h = MaxPooling2D((2, 2))(h)
+    h = Flatten()(h)
+    y = Dense(10, initializer='normal', activation='softmax')(h)
+    model = Model(inputs=X_in, outputs=y)
+    model.compile(optimizer='sgd', loss='sparse_categorical_crossentropy', precision=precision)
+    return model, stem, y
+
+
+def test_trajectory_residual_add_vs_reference():
+    """BASELINE config 4's building block through the functional API (Add), against the fixture the
+    live reference produced (1x1 VALID convolutions, see tests/golden/make_golden.py)."""
+    g = load_golden('traj_residual')
+    r, X = _data((48, 3, 8, 8), kind='normal')
+    Y = O.to_categorical(np.concatenate([np.arange(10), r.integers(0, 10, 38)]))
+    model, stem, y = _residual_model(8, 1, 'VALID', (3, 8, 8))
+    assert [l.__class__.__name__ for l in model.forward_graph].count('Add') == 1
+    assert sum(v.size for v in model.trainable_variables) == 3 * 8 + 8 + 2 * (64 + 8) + 4 * 8 + 128 * 10 + 10
+    model.fit(X, Y, batch_size=16, epochs=1, shuffle=False, validation_ratio=0., verbose=0)
+    assert np.allclose(model.train_loss, g['train_loss'], rtol=2e-5)
+    assert rel_err(np.asarray(stem.variables[0].output_tensor), g['stemW']) < TOL32
+    assert rel_err(np.asarray(y.variables[0].output_tensor), g['denseW']) < TOL32
+
+
+def test_trajectory_residual_3x3_same_vs_oracle():
+    r, X = _data((32, 3, 16, 16), kind='normal')
+    Y = O.to_categorical(np.concatenate([np.arange(10), r.integers(0, 10, 22)]))
+    np.random.seed(0)
+    net = O.OracleNet(O.spec_residual(32) + [('flatten',), ('dense', 10, 'softmax')], (None, 3, 16, 16))
+    net.fit(X, Y, 16, 2, shuffle=True)
+    model, stem, y = _residual_model(32, 3, 'SAME', (3, 16, 16))
+    model.fit(X, Y, batch_size=16, epochs=2, shuffle=True, validation_ratio=0., verbose=0)
+    assert np.allclose(model.train_loss, net.train_loss, rtol=5e-5)
+    assert rel_err(np.asarray(stem.variables[0].output_tensor), net.params[0]) < 2e-5

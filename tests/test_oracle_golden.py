@@ -209,3 +209,18 @@ def test_trajectory_cfg3_small():
     assert rel_err(net.state[1]['mm'], g['bn1_mm']) < 1e-9
     assert rel_err(net.state[10]['mv'], g['bn4_mv']) < 1e-9
     assert rel_err(net.params[-2], g['denseW']) < 1e-9
+
+
+def test_trajectory_residual():
+    """Functional residual graph (Add) against the live reference (with its two workarounds)."""
+    g = load_golden('traj_residual')
+    r, X = _data((48, 3, 8, 8), kind='normal')
+    Y = O.to_categorical(np.concatenate([np.arange(10), r.integers(0, 10, 38)]))
+    assert abs(X.sum() - float(g['xsum'])) < 1e-6
+    np.random.seed(0)
+    spec = O.spec_residual(8, k=1, padding='VALID') + [('flatten',), ('dense', 10, 'softmax')]
+    net = O.OracleNet(spec, (None, 3, 8, 8))
+    net.fit(X, Y, 16, 1, shuffle=False)
+    assert np.allclose(net.train_loss, g['train_loss'], rtol=1e-9, atol=0)
+    assert rel_err(net.params[0], g['stemW']) < 1e-9
+    assert rel_err(net.params[-2], g['denseW']) < 1e-9
