@@ -126,7 +126,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       '-lms', '20'], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 

@@ -68,6 +68,10 @@ SN_API int sn_malloc(void **ptr, size_t bytes);
 SN_API int sn_free(void *ptr);
 SN_API int sn_malloc_host(void **ptr, size_t bytes);          /* pinned */
 SN_API int sn_free_host(void *ptr);
+/* page-lock / unlock caller-owned host memory in place (so that sn_memcpy_h2d from it is truly
+ * asynchronous without a staging copy) */
+SN_API int sn_host_register(void *ptr, size_t bytes);
+SN_API int sn_host_unregister(void *ptr);
 SN_API int sn_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
 SN_API int sn_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
 SN_API int sn_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);

@@ -41,6 +41,12 @@ int sn_malloc(void **ptr, size_t bytes) { SN_REQUIRE(ptr, "null out pointer"); S
 int sn_free(void *ptr) { SN_CUDA(cudaFree(ptr)); return SN_OK; }
 int sn_malloc_host(void **ptr, size_t bytes) { SN_REQUIRE(ptr, "null out pointer"); SN_CUDA(cudaMallocHost(ptr, bytes)); return SN_OK; }
 int sn_free_host(void *ptr) { SN_CUDA(cudaFreeHost(ptr)); return SN_OK; }
+int sn_host_register(void *ptr, size_t bytes) {
+    SN_REQUIRE(ptr && bytes, "bad arguments");
+    SN_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return SN_OK;
+}
+int sn_host_unregister(void *ptr) { SN_CUDA(cudaHostUnregister(ptr)); return SN_OK; }
 int sn_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
     SN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(stream))); return SN_OK;
 }
