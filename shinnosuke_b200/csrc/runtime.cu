@@ -43,10 +43,18 @@ int sn_malloc_host(void **ptr, size_t bytes) { SN_REQUIRE(ptr, "null out pointer
 int sn_free_host(void *ptr) { SN_CUDA(cudaFreeHost(ptr)); return SN_OK; }
 int sn_host_register(void *ptr, size_t bytes) {
     SN_REQUIRE(ptr && bytes, "bad arguments");
-    SN_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();            // a refused registration must not poison later launch checks
+        return check_cuda(e, "cudaHostRegister");
+    }
     return SN_OK;
 }
-int sn_host_unregister(void *ptr) { SN_CUDA(cudaHostUnregister(ptr)); return SN_OK; }
+int sn_host_unregister(void *ptr) {
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return check_cuda(e, "cudaHostUnregister"); }
+    return SN_OK;
+}
 int sn_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
     SN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(stream))); return SN_OK;
 }

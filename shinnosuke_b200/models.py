@@ -190,8 +190,14 @@ class _Trainer(object):
         ~1 ms).  Returns False if the driver refuses (e.g. memory already locked by someone else)."""
         ptr = arr.ctypes.data
         hit = self._pinned_user.get(ptr)
-        if hit is not None and hit[1] >= arr.nbytes:
-            return True
+        if hit is not None:
+            if hit[1] >= arr.nbytes:
+                return True
+            try:                                              # same base, longer array: re-lock the longer range
+                lib.sn_host_unregister(ptr)
+            except Exception:
+                pass
+            del self._pinned_user[ptr]
         if len(self._pinned_user) >= 8:                       # bounded cache
             old_ptr, (_, _) = next(iter(self._pinned_user.items()))
             try:
