@@ -74,12 +74,13 @@ constexpr int SF_ABUF = 3;
 constexpr int SF_A_BYTES = 128 * 128;
 
 template <int BN>
-__global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const StemP p) {
+__global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_constant__ CUtensorMap tmO, const StemP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sB = smem;                                   // [BN][128 B], SW128 K-major
     uint8_t *sA = smem + BN * 128;                        // SF_ABUF x [128][128 B]
-    uint64_t *a_full = reinterpret_cast<uint64_t *>(sA + SF_ABUF * SF_A_BYTES);
+    uint8_t *epi_stage = sA + SF_ABUF * SF_A_BYTES;       // 4 x (32 rows x 128 B) staging tiles for the TMA-store epilogue
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(epi_stage + 4 * 4096);
     uint64_t *a_empty = a_full + SF_ABUF;
     uint64_t *t_full = a_empty + SF_ABUF;
     uint64_t *t_empty = t_full + 2;
@@ -151,33 +152,36 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const StemP p
             const int acc = iter & 1;
             mbar_wait(&t_full[acc], (iter >> 1) & 1);
             tc_fence_after();
-            const int pix = tile * 128 + q * 32 + lane;
-            float *orow = p.y + (long long)pix * p.F;
+            uint8_t *st = epi_stage + q * 4096;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t rr[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), rr);
                 tmem_ld_wait();
-                if (pix < p.P) {
+                if (c0 >= p.F) continue;
+                if (lane == 0) tma_store_wait_read();               // the previous store has drained this warp's tile
+                __syncwarp();
 #pragma unroll
-                    for (int jj = 0; jj < 32; jj += 4) {
-                        if (c0 + jj < p.F) {
-                            float4 v = make_float4(__uint_as_float(rr[jj]), __uint_as_float(rr[jj + 1]), __uint_as_float(rr[jj + 2]),
-                                                   __uint_as_float(rr[jj + 3]));
-                            if (p.bias) {
-                                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + jj));
-                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                            }
-                            if (p.act == SN_ACT_RELU) { v.x = relu_keep_sign(v.x); v.y = relu_keep_sign(v.y); v.z = relu_keep_sign(v.z); v.w = relu_keep_sign(v.w); }
-                            *reinterpret_cast<float4 *>(orow + c0 + jj) = v;
-                        }
+                for (int jj = 0; jj < 32; jj += 4) {
+                    float4 v = make_float4(__uint_as_float(rr[jj]), __uint_as_float(rr[jj + 1]), __uint_as_float(rr[jj + 2]),
+                                           __uint_as_float(rr[jj + 3]));
+                    if (p.bias && c0 + jj < p.F) {
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + jj));
+                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
                     }
+                    if (p.act == SN_ACT_RELU) { v.x = relu_keep_sign(v.x); v.y = relu_keep_sign(v.y); v.z = relu_keep_sign(v.z); v.w = relu_keep_sign(v.w); }
+                    *reinterpret_cast<float4 *>(st + lane * 128 + (((jj >> 2) ^ (lane & 7)) * 16)) = v;
                 }
+                fence_proxy_async();
+                __syncwarp();
+                // one TMA store per 32 x 32 sub-tile: full 128-byte lines, clipped at the tensor bounds
+                if (lane == 0) { tma_store_2d(&tmO, st, c0, tile * 128 + q * 32); tma_store_commit(); }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[acc]);
         }
+        if (lane == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -304,14 +308,20 @@ void fill_geom(StemP &p, int N, int C, int H, int W, int F, int kh, int kw, int 
 
 template <int BN>
 int launch_stem_fprop(const StemP &p, cudaStream_t st) {
-    const int smem = BN * 128 + SF_ABUF * SF_A_BYTES + 1024 + 256;
+    const int smem = BN * 128 + SF_ABUF * SF_A_BYTES + 4 * 4096 + 1024 + 256;
+    CUtensorMap tmO;
+    long long odims[2] = {p.F, p.P};
+    long long ostr[2] = {1, p.F};
+    int obox[2] = {32, 32};
+    int e = make_tmap_f32(&tmO, p.y, 2, odims, ostr, obox);
+    if (e) return e;
     static bool configured = false;
     if (!configured) {
         SN_CUDA(cudaFuncSetAttribute(stem_fprop_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     int grid = p.tiles < num_sms() ? p.tiles : num_sms();
-    stem_fprop_kernel<BN><<<grid, SF_THREADS, smem, st>>>(p);
+    stem_fprop_kernel<BN><<<grid, SF_THREADS, smem, st>>>(tmO, p);
     return after_launch("stem_fprop_kernel");
 }
 

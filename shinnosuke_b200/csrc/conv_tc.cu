@@ -87,7 +87,10 @@ struct IgemmParams {
     int bands_per_image;   // OH / th when an image is split into row bands, else 0
     int pad_h, pad_w;
     int act, accumulate;
+    int tma_store;         // epilogue stages 32x32 sub-tiles in smem and writes them with TMA stores
 };
+
+constexpr int EPI_STAGE_BYTES = 4 * 4096;       // one 32-row x 128-byte staging tile per epilogue warp
 
 // KS = k-blocks (128-byte K slabs) per pipeline stage.  A stage must carry enough MMA time
 // (KS * 128*BN*32 / 2048 cycles) to amortise the per-stage barrier round trips of the single
@@ -98,16 +101,18 @@ template <int BN, int KS> struct IgemmCfg {
     static constexpr int STAGE_BYTES = KS * SLAB_BYTES;
     static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;      // power of two >= 32
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN, int KS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmO, const IgemmParams p) {
     using Cfg = IgemmCfg<BN, KS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint8_t *epi_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                 // 1024-byte aligned (stage sizes are)
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi_stage + EPI_STAGE_BYTES);
     uint64_t *empty_bar = full_bar + Cfg::STAGES;
     uint64_t *tmem_full = empty_bar + Cfg::STAGES;
     uint64_t *tmem_empty = tmem_full + 2;
@@ -210,6 +215,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if constexpr (CHUNK == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
                 tmem_ld_wait();
                 const int f0 = tn_idx * BN + c0;
+                if constexpr (CHUNK == 32) {
+                    if (p.tma_store) {
+                        // bias / ReLU in registers, then this warp's 32 rows x 32 columns go to its staging
+                        // tile in the 128-byte-swizzled layout of the output tensor map, and ONE TMA store
+                        // writes them as full 128-byte lines (rows / columns past the tensor are clipped)
+                        uint8_t *st = epi_stage + q * 4096;
+                        if (lane == 0) tma_store_wait_read();           // previous store has drained the tile
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                                   __uint_as_float(r[j + 3]));
+                            if (p.bias && f0 + j < p.F) {
+                                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + f0 + j));
+                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                            }
+                            if (p.act == SN_ACT_RELU) {
+                                v.x = relu_keep_sign(v.x); v.y = relu_keep_sign(v.y); v.z = relu_keep_sign(v.z); v.w = relu_keep_sign(v.w);
+                            }
+                            *reinterpret_cast<float4 *>(st + lane * 128 + (((j >> 2) ^ (lane & 7)) * 16)) = v;
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) { tma_store_2d(&tmO, st, f0, tm * BM + q * 32); tma_store_commit(); }
+                        continue;
+                    }
+                }
                 if (row_ok) {
                     if (f0 + CHUNK <= p.F && (p.F & 3) == 0) {
 #pragma unroll
@@ -246,6 +278,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (p.tma_store && lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -459,7 +492,7 @@ bool tile_geometry(int N, int OH, int OW, TileGeom &g) {
 }
 
 template <int BN, int KS>
-int launch_igemm_ks(const CUtensorMap &tmA, const CUtensorMap &tmB, const IgemmParams &p, cudaStream_t st) {
+int launch_igemm_ks(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO, const IgemmParams &p, cudaStream_t st) {
     using Cfg = IgemmCfg<BN, KS>;
     static bool configured = false;
     if (!configured) {
@@ -468,14 +501,14 @@ int launch_igemm_ks(const CUtensorMap &tmA, const CUtensorMap &tmB, const IgemmP
     }
     int tiles = p.tiles_m * p.tiles_n;
     int grid = tiles < num_sms() ? tiles : num_sms();
-    conv_igemm_kernel<BN, KS><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+    conv_igemm_kernel<BN, KS><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmO, p);
     return after_launch("conv_igemm_kernel");
 }
 template <int BN>
-int launch_igemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const IgemmParams &p, cudaStream_t st) {
+int launch_igemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO, const IgemmParams &p, cudaStream_t st) {
     const int kblocks = p.ntaps * p.cblocks;
-    if (BN <= 128 && (kblocks % 2) == 0) return launch_igemm_ks<BN, 2>(tmA, tmB, p, st);
-    return launch_igemm_ks<BN, 1>(tmA, tmB, p, st);
+    if (BN <= 128 && (kblocks % 2) == 0) return launch_igemm_ks<BN, 2>(tmA, tmB, tmO, p, st);
+    return launch_igemm_ks<BN, 1>(tmA, tmB, tmO, p, st);
 }
 
 }  // namespace
@@ -518,12 +551,22 @@ int conv_igemm_tc(const float *x, const float *w, const float *bias, float *out,
     p.tiles_m = (p.rows + BM - 1) / BM; p.tiles_n = (F + BN - 1) / BN;
     p.th = g.th; p.tn = g.tn; p.bands_per_image = g.bands_per_image;
     p.pad_h = pad_h; p.pad_w = pad_w; p.act = act; p.accumulate = accumulate;
+    // TMA-store epilogue: full-line writes instead of 16-byte pieces of 32 different rows per instruction
+    CUtensorMap tmO = tmB;
+    p.tma_store = (!accumulate && BN >= 32 && (F & 3) == 0 && (!bias || (((uintptr_t)bias) & 15) == 0)) ? 1 : 0;
+    if (p.tma_store) {
+        long long odims[2] = {F, p.rows};
+        long long ostr[2] = {1, F};
+        int obox[2] = {32, 32};
+        e = make_tmap_f32(&tmO, out, 2, odims, ostr, obox);
+        if (e) return e;
+    }
     switch (BN) {
-        case 16: return launch_igemm<16>(tmA, tmB, p, st);
-        case 32: return launch_igemm<32>(tmA, tmB, p, st);
-        case 64: return launch_igemm<64>(tmA, tmB, p, st);
-        case 128: return launch_igemm<128>(tmA, tmB, p, st);
-        default: return launch_igemm<256>(tmA, tmB, p, st);
+        case 16: return launch_igemm<16>(tmA, tmB, tmO, p, st);
+        case 32: return launch_igemm<32>(tmA, tmB, tmO, p, st);
+        case 64: return launch_igemm<64>(tmA, tmB, tmO, p, st);
+        case 128: return launch_igemm<128>(tmA, tmB, tmO, p, st);
+        default: return launch_igemm<256>(tmA, tmB, tmO, p, st);
     }
 }
 

@@ -64,6 +64,17 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *m, uin
         : "memory");
 }
 
+// bulk tensor STORE shared -> global (clipped at the tensor bounds), tracked by bulk async-groups
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the committed stores have finished READING shared memory (the buffer may be reused)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------ tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
