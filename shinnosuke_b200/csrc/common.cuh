@@ -64,7 +64,8 @@ inline int grid_for(long long work, int block, int ctas_per_sm = 8) {
 __device__ __forceinline__ float relu_keep_sign(float z) {
     // max(0, z) with the sign of a negative pre-activation kept as -0.0f: numerically
     // zero for every consumer, but "pre-activation < 0" stays recoverable for backward.
-    return z > 0.f ? z : (z < 0.f ? -0.f : 0.f);
+    // (z == -0.0f is NOT < 0, so it yields +0.0f and the gradient passes, like the reference.)
+    return __uint_as_float(__float_as_uint(fmaxf(z, 0.f)) | (z < 0.f ? 0x80000000u : 0u));
 }
 __device__ __forceinline__ bool relu_blocked(float y) { return __float_as_uint(y) == 0x80000000u; }
 

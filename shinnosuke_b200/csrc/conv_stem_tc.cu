@@ -47,29 +47,32 @@ __device__ __forceinline__ void make_kslice(const StemP &p, int kq, KSlice &ks) 
         }
     }
 }
-// the 8 column values of pixel `pix` for this slice; `one_at` (>= 0) plants the constant-one column
+// the 8 column values of pixel `pix` for this slice; `one_at` (>= 0) plants the constant-one column.
+// Branch-free: every lane always issues its 8 loads (from a safe address when the tap is padding or
+// the pixel is past the end), so they pipeline instead of forming 8 divergent load-use chains.
 __device__ __forceinline__ void gather_slice(const StemP &p, const KSlice &ks, int pix, int kq, int one_at, float (&col)[8]) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) col[e] = 0.f;
-    if (pix >= p.P) return;
-    const int t = pix / p.ow, j = pix - t * p.ow;
+    const bool live = pix < p.P;
+    const int pp = live ? pix : 0;
+    const int t = pp / p.ow, j = pp - t * p.ow;
     const int n = t / p.oh, i = t - n * p.oh;
     const int hb = i * p.stride - p.ph, wb = j * p.stride - p.pw;
     const float *base = p.x + (long long)n * p.H * p.W * p.C + (hb * p.W + wb) * p.C;
+    float v[8];
+    bool ok[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        if (ks.du[e] >= 0) {
-            const int h = hb + ks.du[e], w = wb + ks.dv[e];
-            if ((unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W) col[e] = __ldg(base + ks.off[e]);
-        } else if (kq * 8 + e == one_at) {
-            col[e] = 1.f;
-        }
+        const int h = hb + ks.du[e], w = wb + ks.dv[e];
+        ok[e] = live && ks.du[e] >= 0 && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
+        v[e] = __ldg(ok[e] ? base + ks.off[e] : p.x);
     }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) col[e] = ok[e] ? v[e] : ((live && kq * 8 + e == one_at) ? 1.f : 0.f);
 }
 
 // ============================================================================== fprop
 constexpr int SF_BUILDERS = 512;               // 4 threads per pixel row
-constexpr int SF_THREADS = 32 + SF_BUILDERS + 128;   // warp 0: MMA, warps 1-16: column builders, warps 17-20: epilogue
+constexpr int SF_EPI_WARPS = 8;                // two per TMEM lane quarter: the tile loop is all epilogue
+constexpr int SF_THREADS = 32 + SF_BUILDERS + 32 * SF_EPI_WARPS;   // warp 0: MMA, warps 1-16: column builders, warps 17-24: epilogue
 constexpr int SF_ABUF = 3;
 constexpr int SF_A_BYTES = 128 * 128;
 
@@ -79,8 +82,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sB = smem;                                   // [BN][128 B], SW128 K-major
     uint8_t *sA = smem + BN * 128;                        // SF_ABUF x [128][128 B]
-    uint8_t *epi_stage = sA + SF_ABUF * SF_A_BYTES;       // 4 x (32 rows x 128 B) staging tiles for the TMA-store epilogue
-    uint64_t *a_full = reinterpret_cast<uint64_t *>(epi_stage + 4 * 4096);
+    uint8_t *epi_stage = sA + SF_ABUF * SF_A_BYTES;       // per epilogue warp: 2 x (32 rows x 128 B) staging tiles for TMA stores
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(epi_stage + 2 * SF_EPI_WARPS * 4096);
     uint64_t *a_empty = a_full + SF_ABUF;
     uint64_t *t_full = a_empty + SF_ABUF;
     uint64_t *t_empty = t_full + 2;
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < SF_ABUF; ++i) { mbar_init(&a_full[i], SF_BUILDERS); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], SF_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 0) { tmem_alloc(tmem_ptr, 2 * BN < 32 ? 32 : 2 * BN); tmem_relinquish(); }
@@ -147,19 +150,23 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
     } else {
         // ---------------- epilogue: TMEM -> bias/ReLU -> NHWC output ----------------
         const int q = warp & 3;
+        const int ew = warp - 1 - SF_BUILDERS / 32;          // 0..7
+        const int half = ew >> 2;                            // which 32-column chunks this warp takes
         int iter = 0;
+        unsigned epi_flip = 0;
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++iter) {
             const int acc = iter & 1;
             mbar_wait(&t_full[acc], (iter >> 1) & 1);
             tc_fence_after();
-            uint8_t *st = epi_stage + q * 4096;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 uint32_t rr[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), rr);
                 tmem_ld_wait();
                 if (c0 >= p.F) continue;
-                if (lane == 0) tma_store_wait_read();               // the previous store has drained this warp's tile
+                uint8_t *st = epi_stage + (ew * 2 + (epi_flip & 1)) * 4096;
+                ++epi_flip;
+                if (lane == 0) tma_store_wait_read1();              // the store issued two sub-tiles ago has drained this buffer
                 __syncwarp();
 #pragma unroll
                 for (int jj = 0; jj < 32; jj += 4) {
@@ -280,7 +287,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
         } else {
             // epilogue (warps 9..12): dW[f][k] += D[f][k], db[f] += D[f][K]
             const int q = warp & 3;
-            mbar_wait(acc_full, 0);
+            mbar_wait_sleep(acc_full, 0);        // whole-kernel wait: do not steal issue slots from the builders
             tc_fence_after();
             uint32_t rr[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), rr);
@@ -308,7 +315,7 @@ void fill_geom(StemP &p, int N, int C, int H, int W, int F, int kh, int kw, int 
 
 template <int BN>
 int launch_stem_fprop(const StemP &p, cudaStream_t st) {
-    const int smem = BN * 128 + SF_ABUF * SF_A_BYTES + 4 * 4096 + 1024 + 256;
+    const int smem = BN * 128 + SF_ABUF * SF_A_BYTES + 2 * SF_EPI_WARPS * 4096 + 1024 + 256;
     CUtensorMap tmO;
     long long odims[2] = {p.F, p.P};
     long long ostr[2] = {1, p.F};

@@ -141,7 +141,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
             }
         } else {
             const int q = warp & 3;
-            mbar_wait(acc_full, 0);
+            mbar_wait_sleep(acc_full, 0);
             tc_fence_after();
             const int f = ft * 128 + q * 32 + lane;
 #pragma unroll 1
