@@ -395,7 +395,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='cfg3', choices=sorted(CONFIGS))
     ap.add_argument('--per-gpu-batch', type=int, default=0)
-    ap.add_argument('--precision', default='tf32', choices=['fp32', 'tf32'])
+    ap.add_argument('--precision', default='tf32', choices=['fp32', 'tf32', 'bf16'])
     ap.add_argument('--kernel-table', default='', help='write the per-kernel CUDA-event table (JSON) here')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

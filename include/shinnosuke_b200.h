@@ -52,7 +52,8 @@ extern "C" {
 /* arithmetic tier of the contraction kernels */
 #define SN_PREC_FP32 0   /* CUDA-core FFMA, fp32 operands and accumulators (1e-5 tier)      */
 #define SN_PREC_TF32 1   /* tcgen05.mma kind::tf32, fp32 storage, fp32 TMEM accumulators    */
-#define SN_PREC_BF16 2   /* tcgen05.mma kind::f16 on bf16 copies of the operands (reserved)  */
+#define SN_PREC_BF16 2   /* tcgen05.mma kind::f16 on bf16 copies of the operands: the *_bf16
+                            entry points below; the fp32-pointer entry points treat it as TF32 */
 
 /* max-pool backward semantics (layers/Convolution.py:266-269) */
 #define SN_POOL_TIE_SPLIT    0   /* 'reshape' mode: ties share the gradient equally         */
@@ -130,6 +131,27 @@ SN_API int sn_relu_fwd(const float *x, float *y, long long n, void *stream);
 SN_API int sn_pad2d_fwd(const float *x, float *y, int N, int H, int W, int C, int pad_h, int pad_w, void *stream);
 SN_API int sn_pad2d_bwd(const float *dy, float *dx, int N, int H, int W, int C, int pad_h, int pad_w,
                  int accumulate, void *stream);
+
+/* bf16 tier (north_star: "bf16 inputs and fp32 accumulation", 1e-2 against float64).  The
+ * operands are bf16 COPIES made with sn_cast_f32_to_bf16 (x, dY) / sn_flip_transpose_filters_bf16
+ * (filters for dgrad); accumulators, bias, activation, outputs and weight gradients stay fp32.
+ * op: 0 = fprop, 1 = dgrad, 2 = wgrad.  Shapes the tensor-core kernels do not take report 0 from
+ * sn_conv2d_bf16_supported and must use the fp32-pointer entry points. */
+SN_API int sn_cast_f32_to_bf16(const float *src, void *dst_bf16, long long n, void *stream);
+SN_API int sn_flip_transpose_filters_bf16(const float *w, void *wt_bf16, int F, int C, int kh, int kw, void *stream);
+SN_API int sn_conv2d_bf16_supported(int op, int N, int C, int H, int W, int F, int kh, int kw,
+                             int stride, int pad_h, int pad_w);
+SN_API int sn_conv2d_fprop_bf16(const void *x_bf16, const void *w_bf16, const float *bias, float *y,
+                         int N, int C, int H, int W, int F, int kh, int kw,
+                         int stride, int pad_h, int pad_w, int act, void *stream);
+/* wt_bf16: filters flipped and transposed by sn_flip_transpose_filters_bf16 */
+SN_API int sn_conv2d_dgrad_bf16(const void *dy_bf16, const void *wt_bf16, float *dx,
+                         int N, int C, int H, int W, int F, int kh, int kw,
+                         int stride, int pad_h, int pad_w, int accumulate, void *stream);
+/* dw += (always accumulates); db += column sums of the fp32 dY when both are non-NULL */
+SN_API int sn_conv2d_wgrad_bf16(const void *x_bf16, const void *dy_bf16, const float *dy_f32, float *dw, float *db,
+                         int N, int C, int H, int W, int F, int kh, int kw,
+                         int stride, int pad_h, int pad_w, void *stream);
 
 /* ----------------------------------------------------------------- Dense */
 /* Dense.forward, layers/FC.py:124-134: y = act(x . W + b), x[M][K], w[Nout][K] */

@@ -135,5 +135,5 @@ class _Lib(object):
 lib = _Lib()
 
 ACT = {'linear': 0, 'relu': 1}
-PRECISION = {'fp32': 0, 'tf32': 1}      # the header reserves 2 for a bf16 tier
+PRECISION = {'fp32': 0, 'tf32': 1, 'bf16': 2}
 POOL_MODE = {'reshape': 0, 'im2col': 1}

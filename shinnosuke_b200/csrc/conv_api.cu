@@ -6,16 +6,18 @@ namespace sn {
 int conv_fprop_simt(const float *, const float *, const float *, float *, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv_dgrad_simt(const float *, const float *, float *, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv_wgrad_simt(const float *, const float *, float *, float *, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
-bool conv_tc_eligible(int N, int C, int OH, int OW, int F, int stride);
+bool conv_tc_eligible(int N, int C, int OH, int OW, int F, int stride, bool bf16 = false);
 bool wgrad_tc_eligible(int N, int C, int OH, int OW, int F, int stride);
-int conv_igemm_tc(const float *x, const float *w, const float *bias, float *out, int N, int C, int IH, int IW, int F, int kh,
-                  int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, cudaStream_t st);
+int conv_igemm_tc(const void *x, const void *w, const float *bias, float *out, int N, int C, int IH, int IW, int F, int kh,
+                  int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, bool bf16, cudaStream_t st);
+int flip_transpose_filters_bf16(const float *w, void *wt, int F, int C, int kh, int kw, cudaStream_t st);
+int cast_f32_to_bf16(const float *src, void *dst, long long n, cudaStream_t st);
 int conv_wgrad_tc(const float *x, const float *dy, float *dw, int N, int C, int IH, int IW, int F, int kh, int kw, int OH,
                   int OW, int pad_h, int pad_w, cudaStream_t st);
 int flip_transpose_filters(const float *w, float *wt, int F, int C, int kh, int kw, cudaStream_t st);
-bool wgrad_halo_eligible(int N, int C, int OH, int OW, int F, int kh, int kw, int stride);
-int conv_wgrad_halo_tc(const float *x, const float *dy, float *dw, int N, int C, int IH, int IW, int F, int kh, int kw, int OH,
-                       int OW, int pad_h, int pad_w, cudaStream_t st);
+bool wgrad_halo_eligible(int N, int C, int OH, int OW, int F, int kh, int kw, int stride, bool bf16 = false);
+int conv_wgrad_halo_tc(const void *x, const void *dy, float *dw, int N, int C, int IH, int IW, int F, int kh, int kw, int OH,
+                       int OW, int pad_h, int pad_w, bool bf16, cudaStream_t st);
 int colsum_accumulate(const float *dy, float *db, long long rows, int F, cudaStream_t st);
 bool stem_tc_eligible(int N, int C, int OH, int OW, int F, int kh, int kw);
 int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
@@ -31,11 +33,7 @@ int conv_wgrad_direct(const float *x, const float *dy, float *dw, float *db, int
 }
 
 static int check_prec(int precision) {
-    if (precision == SN_PREC_BF16) {
-        set_error("the bf16 tier is not built yet; use SN_PREC_TF32 (tensor cores) or SN_PREC_FP32");
-        return SN_ERR_UNSUPPORTED;
-    }
-    if (precision != SN_PREC_FP32 && precision != SN_PREC_TF32) {
+    if (precision != SN_PREC_FP32 && precision != SN_PREC_TF32 && precision != SN_PREC_BF16) {
         set_error("unknown precision tier %d", precision);
         return SN_ERR_INVALID_ARG;
     }
@@ -52,15 +50,15 @@ int sn_conv2d_fprop(const float *x, const float *w, const float *bias, float *y,
     if (e) return e;
     const bool geom_ok = N > 0 && C > 0 && F > 0 && kh > 0 && kw > 0 && stride > 0 && pad_h >= 0 && pad_w >= 0 &&
                          H + 2 * pad_h >= kh && W + 2 * pad_w >= kw;
-    if (geom_ok && precision == SN_PREC_TF32 && (((uintptr_t)y | (uintptr_t)bias) & 15) == 0 &&
+    if (geom_ok && precision != SN_PREC_FP32 && (((uintptr_t)y | (uintptr_t)bias) & 15) == 0 &&
         stem_tc_eligible(N, C, (H + 2 * pad_h - kh) / stride + 1, (W + 2 * pad_w - kw) / stride + 1, F, kh, kw))
         return conv_stem_fprop_tc(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, as_stream(stream));
     if (geom_ok && (((uintptr_t)y) & 15) == 0 && direct_fprop_eligible(C, kh, kw, F))
         return conv_fprop_direct(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, as_stream(stream));
-    if (geom_ok && precision == SN_PREC_TF32) {
+    if (geom_ok && precision != SN_PREC_FP32) {
         const int oh = (H + 2 * pad_h - kh) / stride + 1, ow = (W + 2 * pad_w - kw) / stride + 1;
         if (conv_tc_eligible(N, C, oh, ow, F, stride))
-            return conv_igemm_tc(x, w, bias, y, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, act, 0, as_stream(stream));
+            return conv_igemm_tc(x, w, bias, y, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, act, 0, false, as_stream(stream));
     }
     return conv_fprop_simt(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, as_stream(stream));
 }
@@ -75,7 +73,7 @@ int sn_conv2d_dgrad(const float *dy, const float *w, float *dx, int N, int C, in
     SN_REQUIRE(dy && w && dx, "null tensor");
     int e = check_prec(precision);
     if (e) return e;
-    if (N > 0 && precision == SN_PREC_TF32 && workspace && stride == 1 && H + 2 * pad_h >= kh && W + 2 * pad_w >= kw &&
+    if (N > 0 && precision != SN_PREC_FP32 && workspace && stride == 1 && H + 2 * pad_h >= kh && W + 2 * pad_w >= kw &&
         kh - 1 - pad_h >= 0 && kw - 1 - pad_w >= 0) {
         // dX = forward convolution of dY (N, oh, ow, F) with Wt[c][kh-1-u][kw-1-v][f], padding k-1-p, output (H, W)
         const int oh = H + 2 * pad_h - kh + 1, ow = W + 2 * pad_w - kw + 1;
@@ -83,7 +81,7 @@ int sn_conv2d_dgrad(const float *dy, const float *w, float *dx, int N, int C, in
             e = flip_transpose_filters(w, (float *)workspace, F, C, kh, kw, as_stream(stream));
             if (e) return e;
             return conv_igemm_tc(dy, (const float *)workspace, nullptr, dx, N, F, oh, ow, C, kh, kw, H, W, kh - 1 - pad_h,
-                                 kw - 1 - pad_w, SN_ACT_LINEAR, accumulate, as_stream(stream));
+                                 kw - 1 - pad_w, SN_ACT_LINEAR, accumulate, false, as_stream(stream));
         }
     }
     return conv_dgrad_simt(dy, w, dx, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, accumulate, as_stream(stream));
@@ -96,7 +94,7 @@ int sn_conv2d_wgrad(const float *x, const float *dy, float *dw, float *db, int N
     if (e) return e;
     const bool geom_ok = N > 0 && C > 0 && F > 0 && kh > 0 && kw > 0 && stride > 0 && pad_h >= 0 && pad_w >= 0 &&
                          H + 2 * pad_h >= kh && W + 2 * pad_w >= kw;
-    if (geom_ok && precision == SN_PREC_TF32 && (((uintptr_t)dy) & 15) == 0 && (C * kh * kw < 32 || !db) &&
+    if (geom_ok && precision != SN_PREC_FP32 && (((uintptr_t)dy) & 15) == 0 && (C * kh * kw < 32 || !db) &&
         stem_tc_eligible(N, C, (H + 2 * pad_h - kh) / stride + 1, (W + 2 * pad_w - kw) / stride + 1, F, kh, kw)) {
         cudaStream_t st = as_stream(stream);
         if (!accumulate) {
@@ -113,7 +111,7 @@ int sn_conv2d_wgrad(const float *x, const float *dy, float *dw, float *db, int N
         }
         return conv_wgrad_direct(x, dy, dw, db, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, st);
     }
-    if (geom_ok && precision == SN_PREC_TF32) {
+    if (geom_ok && precision != SN_PREC_FP32) {
         const int oh = (H + 2 * pad_h - kh) / stride + 1, ow = (W + 2 * pad_w - kw) / stride + 1;
         const bool halo = wgrad_halo_eligible(N, C, oh, ow, F, kh, kw, stride);
         if (halo || wgrad_tc_eligible(N, C, oh, ow, F, stride)) {
@@ -122,13 +120,65 @@ int sn_conv2d_wgrad(const float *x, const float *dy, float *dw, float *db, int N
                 SN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)F * kh * kw * C, st));
                 if (db) SN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * F, st));
             }
-            e = halo ? conv_wgrad_halo_tc(x, dy, dw, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, st)
+            e = halo ? conv_wgrad_halo_tc(x, dy, dw, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, false, st)
                      : conv_wgrad_tc(x, dy, dw, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, st);
             if (e || !db) return e;
             return colsum_accumulate(dy, db, (long long)N * oh * ow, F, st);
         }
     }
     return conv_wgrad_simt(x, dy, dw, db, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, accumulate, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------ bf16 tier
+static bool bf16_geom(int N, int C, int H, int W, int F, int kh, int kw, int stride, int ph, int pw, int &oh, int &ow) {
+    if (N <= 0 || C <= 0 || F <= 0 || kh <= 0 || kw <= 0 || stride != 1 || ph < 0 || pw < 0 || H + 2 * ph < kh || W + 2 * pw < kw)
+        return false;
+    oh = H + 2 * ph - kh + 1; ow = W + 2 * pw - kw + 1;
+    return true;
+}
+
+int sn_cast_f32_to_bf16(const float *src, void *dst_bf16, long long n, void *stream) {
+    SN_REQUIRE(src && dst_bf16 && n >= 0, "bad arguments");
+    return cast_f32_to_bf16(src, dst_bf16, n, as_stream(stream));
+}
+int sn_flip_transpose_filters_bf16(const float *w, void *wt_bf16, int F, int C, int kh, int kw, void *stream) {
+    SN_REQUIRE(w && wt_bf16 && F > 0 && C > 0 && kh > 0 && kw > 0, "bad arguments");
+    return flip_transpose_filters_bf16(w, wt_bf16, F, C, kh, kw, as_stream(stream));
+}
+int sn_conv2d_bf16_supported(int op, int N, int C, int H, int W, int F, int kh, int kw, int stride, int pad_h, int pad_w) {
+    int oh, ow;
+    if (!bf16_geom(N, C, H, W, F, kh, kw, stride, pad_h, pad_w, oh, ow)) return 0;
+    if (op == 0) return (F % 4 == 0 && conv_tc_eligible(N, C, oh, ow, F, 1, true)) ? 1 : 0;
+    if (op == 1) return (kh - 1 - pad_h >= 0 && kw - 1 - pad_w >= 0 && C % 4 == 0 && conv_tc_eligible(N, F, H, W, C, 1, true)) ? 1 : 0;
+    if (op == 2) return wgrad_halo_eligible(N, C, oh, ow, F, kh, kw, 1, true) ? 1 : 0;
+    return 0;
+}
+int sn_conv2d_fprop_bf16(const void *x, const void *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
+                         int kw, int stride, int pad_h, int pad_w, int act, void *stream) {
+    SN_REQUIRE(x && w && y, "null tensor");
+    SN_REQUIRE(sn_conv2d_bf16_supported(0, N, C, H, W, F, kh, kw, stride, pad_h, pad_w), "shape not supported by the bf16 kernels");
+    int oh, ow;
+    bf16_geom(N, C, H, W, F, kh, kw, stride, pad_h, pad_w, oh, ow);
+    return conv_igemm_tc(x, w, bias, y, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, act, 0, true, as_stream(stream));
+}
+int sn_conv2d_dgrad_bf16(const void *dy, const void *wt, float *dx, int N, int C, int H, int W, int F, int kh, int kw, int stride,
+                         int pad_h, int pad_w, int accumulate, void *stream) {
+    SN_REQUIRE(dy && wt && dx, "null tensor");
+    SN_REQUIRE(sn_conv2d_bf16_supported(1, N, C, H, W, F, kh, kw, stride, pad_h, pad_w), "shape not supported by the bf16 kernels");
+    int oh, ow;
+    bf16_geom(N, C, H, W, F, kh, kw, stride, pad_h, pad_w, oh, ow);
+    return conv_igemm_tc(dy, wt, nullptr, dx, N, F, oh, ow, C, kh, kw, H, W, kh - 1 - pad_h, kw - 1 - pad_w, SN_ACT_LINEAR,
+                         accumulate, true, as_stream(stream));
+}
+int sn_conv2d_wgrad_bf16(const void *x, const void *dy, const float *dy_f32, float *dw, float *db, int N, int C, int H, int W,
+                         int F, int kh, int kw, int stride, int pad_h, int pad_w, void *stream) {
+    SN_REQUIRE(x && dy && dw, "null tensor");
+    SN_REQUIRE(sn_conv2d_bf16_supported(2, N, C, H, W, F, kh, kw, stride, pad_h, pad_w), "shape not supported by the bf16 kernels");
+    int oh, ow;
+    bf16_geom(N, C, H, W, F, kh, kw, stride, pad_h, pad_w, oh, ow);
+    int e = conv_wgrad_halo_tc(x, dy, dw, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, true, as_stream(stream));
+    if (e || !db || !dy_f32) return e;
+    return colsum_accumulate(dy_f32, db, (long long)N * oh * ow, F, as_stream(stream));
 }
 
 // Dense is the H = W = kh = kw = 1 convolution: x[M][K] are M "pixels" of K channels.

@@ -22,6 +22,7 @@
 //   Split over pixel ranges across CTAs (the output is tiny), fp32 red.global.add epilogue.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <cuda_bf16.h>
 #include <mutex>
 
 using namespace sn;
@@ -44,13 +45,18 @@ EncodeTiledFn get_encode_tiled() {
 
 int make_tmap_f32(CUtensorMap *out, const void *base, int rank, const long long *dims, const long long *strides_elems,
                   const int *box, bool atom32b) {
+    return make_tmap(out, base, rank, dims, strides_elems, box, atom32b, false);
+}
+
+int make_tmap(CUtensorMap *out, const void *base, int rank, const long long *dims, const long long *strides_elems,
+              const int *box, bool atom32b, bool bf16) {
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return SN_ERR_UNSUPPORTED; }
     cuuint64_t gdim[5], gstr[5];
     cuuint32_t bdim[5], estr[5];
     for (int i = 0; i < rank; ++i) { gdim[i] = (cuuint64_t)dims[i]; bdim[i] = (cuuint32_t)box[i]; estr[i] = 1; }
-    for (int i = 1; i < rank; ++i) gstr[i - 1] = (cuuint64_t)strides_elems[i] * 4;
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bdim, estr,
+    for (int i = 1; i < rank; ++i) gstr[i - 1] = (cuuint64_t)strides_elems[i] * (bf16 ? 2 : 4);
+    CUresult r = enc(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bdim, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -70,7 +76,7 @@ namespace {
 constexpr int BM = 128;          // output pixels per tile (UMMA M)
 constexpr int BK = 32;           // fp32 contraction elements per k-block = one 128-byte swizzle row
 constexpr int UK = 8;            // UMMA K for kind::tf32
-constexpr int A_BYTES = BM * BK * 4;
+constexpr int A_BYTES = BM * BK * 4;     // = 128 rows x 128 B for bf16 operands too (64 elements per row)
 constexpr int NUM_THREADS = 192;
 
 struct IgemmParams {
@@ -104,7 +110,9 @@ template <int BN, int KS> struct IgemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int KS>
+// BF16: the operands are bf16 copies (64 elements per 128-byte row, UMMA K = 16, kind::f16); the
+// accumulators, bias, activation and output stay fp32.  Byte geometry of the tiles is identical.
+template <int BN, int KS, bool BF16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const IgemmParams p) {
@@ -120,6 +128,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    constexpr int BKE = BF16 ? 64 : 32;               // contraction elements per 128-byte k-block
     const int num_tiles = p.tiles_m * p.tiles_n;
     const int kblocks = p.ntaps * p.cblocks;          // a multiple of KS (host-checked)
     const int kstages = kblocks / KS;
@@ -156,8 +165,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                     for (int s = 0; s < KS; ++s) {
                         uint8_t *sa = smem + stage * Cfg::STAGE_BYTES + s * Cfg::SLAB_BYTES;
-                        tma_load_4d(sa, &tmA, &full_bar[stage], cb * BK, v - p.pad_w, h0 + u - p.pad_h, n0);
-                        tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], tap * p.C + cb * BK, tn_idx * BN);
+                        tma_load_4d(sa, &tmA, &full_bar[stage], cb * BKE, v - p.pad_w, h0 + u - p.pad_h, n0);
+                        tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], tap * p.C + cb * BKE, tn_idx * BN);
                         if (++cb == p.cblocks) { cb = 0; ++tap; if (++v == p.taps_w) { v = 0; ++u; } }
                     }
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -167,7 +176,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(2, BM, BN, 0, 0);
+            constexpr uint32_t idesc = make_idesc(BF16 ? 1 : 2, BM, BN, 0, 0);
             int stage = 0; uint32_t phase = 0;
             int iter = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
@@ -186,7 +195,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                         for (int k = 0; k < BK / UK; ++k) {
                             // advancing K inside the 128-byte swizzle row: +32 bytes = +2 descriptor units
-                            mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | s | k) != 0 ? 1u : 0u);
+                            if constexpr (BF16) mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | s | k) != 0 ? 1u : 0u);
+                            else mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | s | k) != 0 ? 1u : 0u);
                         }
                     }
                     mma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
@@ -300,6 +310,33 @@ __global__ void flip_transpose_filters_kernel(const float *__restrict__ w, float
         int u2 = (int)(t % kh);
         int c = (int)(t / kh);
         wt[i] = w[(((long long)f * kh + (kh - 1 - u2)) * kw + (kw - 1 - v2)) * C + c];
+    }
+}
+
+__global__ void flip_transpose_filters_bf16_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ wt, int F, int C, int kh, int kw) {
+    const long long total = (long long)F * kh * kw * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int f = (int)(i % F);
+        long long t = i / F;
+        int v2 = (int)(t % kw); t /= kw;
+        int u2 = (int)(t % kh);
+        int c = (int)(t / kh);
+        wt[i] = __float2bfloat16_rn(w[(((long long)f * kh + (kh - 1 - u2)) * kw + (kw - 1 - v2)) * C + c]);
+    }
+}
+
+__global__ void cast_f32_bf16_kernel(const float *__restrict__ s, __nv_bfloat16 *__restrict__ d, long long n) {
+    const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x, t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if ((((uintptr_t)s) & 15) == 0 && (((uintptr_t)d) & 7) == 0) {
+        for (long long i = t; i < n4; i += stride) {
+            const float4 v = ldg4(s + 4 * i);
+            __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+            uint2 o; o.x = *reinterpret_cast<uint32_t *>(&a); o.y = *reinterpret_cast<uint32_t *>(&b);
+            reinterpret_cast<uint2 *>(d)[i] = o;
+        }
+        for (long long i = 4 * n4 + t; i < n; i += stride) d[i] = __float2bfloat16_rn(s[i]);
+    } else {
+        for (long long i = t; i < n; i += stride) d[i] = __float2bfloat16_rn(s[i]);
     }
 }
 
@@ -491,24 +528,25 @@ bool tile_geometry(int N, int OH, int OW, TileGeom &g) {
     return g.th <= 256;
 }
 
-template <int BN, int KS>
+template <int BN, int KS, bool BF16>
 int launch_igemm_ks(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO, const IgemmParams &p, cudaStream_t st) {
     using Cfg = IgemmCfg<BN, KS>;
     static bool configured = false;
     if (!configured) {
-        SN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        SN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, KS, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
     int tiles = p.tiles_m * p.tiles_n;
     int grid = tiles < num_sms() ? tiles : num_sms();
-    conv_igemm_kernel<BN, KS><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmO, p);
+    conv_igemm_kernel<BN, KS, BF16><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmO, p);
     return after_launch("conv_igemm_kernel");
 }
 template <int BN>
-int launch_igemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO, const IgemmParams &p, cudaStream_t st) {
+int launch_igemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO, const IgemmParams &p, bool bf16, cudaStream_t st) {
     const int kblocks = p.ntaps * p.cblocks;
-    if (BN <= 128 && (kblocks % 2) == 0) return launch_igemm_ks<BN, 2>(tmA, tmB, tmO, p, st);
-    return launch_igemm_ks<BN, 1>(tmA, tmB, tmO, p, st);
+    const bool ks2 = BN <= 128 && (kblocks % 2) == 0;
+    if (bf16) return ks2 ? launch_igemm_ks<BN, 2, true>(tmA, tmB, tmO, p, st) : launch_igemm_ks<BN, 1, true>(tmA, tmB, tmO, p, st);
+    return ks2 ? launch_igemm_ks<BN, 2, false>(tmA, tmB, tmO, p, st) : launch_igemm_ks<BN, 1, false>(tmA, tmB, tmO, p, st);
 }
 
 }  // namespace
@@ -516,17 +554,17 @@ int launch_igemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorM
 namespace sn {
 
 // Can the tensor-core path take this forward-style convolution (stride 1)?
-bool conv_tc_eligible(int N, int C, int OH, int OW, int F, int stride) {
+bool conv_tc_eligible(int N, int C, int OH, int OW, int F, int stride, bool bf16) {
     TileGeom g;
-    if (stride != 1 || (C & 3) || C < 8) return false;
+    if (stride != 1 || (C & (bf16 ? 7 : 3)) || C < 8) return false;
     if (!tile_geometry(N, OH, OW, g)) return false;
     long long flops = 2ll * N * OH * OW * F * C;
     return flops >= (1ll << 22);            // tiny problems stay on the CUDA-core kernel (launch-latency bound anyway)
 }
 
 // x: NHWC (N, IH, IW, C); w: [F][kh*kw][C]; out: (N*OH*OW, F).
-int conv_igemm_tc(const float *x, const float *w, const float *bias, float *out, int N, int C, int IH, int IW, int F, int kh,
-                  int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, cudaStream_t st) {
+int conv_igemm_tc(const void *x, const void *w, const float *bias, float *out, int N, int C, int IH, int IW, int F, int kh,
+                  int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, bool bf16, cudaStream_t st) {
     TileGeom g;
     if (!tile_geometry(N, OH, OW, g)) { set_error("conv_igemm_tc: unsupported output geometry %dx%d", OH, OW); return SN_ERR_UNSUPPORTED; }
     if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)out) & 15) { set_error("conv_igemm_tc: tensors must be 16-byte aligned"); return SN_ERR_INVALID_ARG; }
@@ -536,18 +574,19 @@ int conv_igemm_tc(const float *x, const float *w, const float *bias, float *out,
     CUtensorMap tmA, tmB;
     long long adims[4] = {C, IW, IH, N};
     long long astr[4] = {1, C, (long long)IW * C, (long long)IH * IW * C};
-    int abox[4] = {BK, OW, g.th, g.tn};
-    int e = make_tmap_f32(&tmA, x, 4, adims, astr, abox);
+    const int bke = bf16 ? 64 : 32;
+    int abox[4] = {bke, OW, g.th, g.tn};
+    int e = make_tmap(&tmA, x, 4, adims, astr, abox, false, bf16);
     if (e) return e;
     long long ktot = (long long)kh * kw * C;
     long long bdims[2] = {ktot, F};
     long long bstr[2] = {1, ktot};
-    int bbox[2] = {BK, BN > 256 ? 256 : BN};
-    e = make_tmap_f32(&tmB, w, 2, bdims, bstr, bbox);
+    int bbox[2] = {bke, BN > 256 ? 256 : BN};
+    e = make_tmap(&tmB, w, 2, bdims, bstr, bbox, false, bf16);
     if (e) return e;
     IgemmParams p{};
     p.out = out; p.bias = bias; p.rows = N * OH * OW; p.F = F; p.taps_w = kw; p.ntaps = kh * kw; p.C = C;
-    p.cblocks = (C + BK - 1) / BK;
+    p.cblocks = (C + bke - 1) / bke;
     p.tiles_m = (p.rows + BM - 1) / BM; p.tiles_n = (F + BN - 1) / BN;
     p.th = g.th; p.tn = g.tn; p.bands_per_image = g.bands_per_image;
     p.pad_h = pad_h; p.pad_w = pad_w; p.act = act; p.accumulate = accumulate;
@@ -562,11 +601,11 @@ int conv_igemm_tc(const float *x, const float *w, const float *bias, float *out,
         if (e) return e;
     }
     switch (BN) {
-        case 16: return launch_igemm<16>(tmA, tmB, tmO, p, st);
-        case 32: return launch_igemm<32>(tmA, tmB, tmO, p, st);
-        case 64: return launch_igemm<64>(tmA, tmB, tmO, p, st);
-        case 128: return launch_igemm<128>(tmA, tmB, tmO, p, st);
-        default: return launch_igemm<256>(tmA, tmB, tmO, p, st);
+        case 16: return launch_igemm<16>(tmA, tmB, tmO, p, bf16, st);
+        case 32: return launch_igemm<32>(tmA, tmB, tmO, p, bf16, st);
+        case 64: return launch_igemm<64>(tmA, tmB, tmO, p, bf16, st);
+        case 128: return launch_igemm<128>(tmA, tmB, tmO, p, bf16, st);
+        default: return launch_igemm<256>(tmA, tmB, tmO, p, bf16, st);
     }
 }
 
@@ -625,6 +664,18 @@ int conv_wgrad_tc(const float *x, const float *dy, float *dw, int N, int C, int 
         case 128: return launch_wgrad<128, 1>(tmDY, tmX, p, st);
         default: return launch_wgrad<256, 1>(tmDY, tmX, p, st);
     }
+}
+
+int flip_transpose_filters_bf16(const float *w, void *wt, int F, int C, int kh, int kw, cudaStream_t st) {
+    long long total = (long long)F * kh * kw * C;
+    flip_transpose_filters_bf16_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, (__nv_bfloat16 *)wt, F, C, kh, kw);
+    return after_launch("flip_transpose_filters_bf16_kernel");
+}
+
+int cast_f32_to_bf16(const float *src, void *dst, long long n, cudaStream_t st) {
+    if (n <= 0) return SN_OK;
+    cast_f32_bf16_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(src, (__nv_bfloat16 *)dst, n);
+    return after_launch("cast_f32_bf16_kernel");
 }
 
 int flip_transpose_filters(const float *w, float *wt, int F, int C, int kh, int kw, cudaStream_t st) {

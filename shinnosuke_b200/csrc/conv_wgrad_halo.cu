@@ -20,17 +20,28 @@
 // pixel blocks across CTAs, red.global.add.v4.f32 epilogue (= the reference's `+=`).
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <cuda_bf16.h>
 
 using namespace sn;
 using namespace sn::tc;
 
 namespace {
 
-constexpr int HB_PB = 64;                       // output pixels per stage (8 UMMA K-steps)
-constexpr int HB_ATOM = HB_PB * 128;            // dY atom column: 64 pixel rows x 128 B (32 filters)
-constexpr int HB_A_BYTES = 4 * HB_ATOM;         // 128 filters
+constexpr int HB_PB = 64;                       // output pixels per stage
+constexpr int HB_ATOM = HB_PB * 128;            // one atom column: 64 pixel rows x 128 B (32 fp32 / 64 bf16 filters or channels)
 constexpr int HB_THREADS = 192;
 constexpr int HB_MAX_KW = 5;
+// fp32 (tf32) operands: 4 atom columns of dY, 8-pixel K-steps, K groups of 4 rows (32-byte-atom swizzle)
+// bf16 operands       : 2 atom columns of dY, 16-pixel K-steps, K groups of 8 rows (plain 128-byte swizzle)
+template <bool BF16> struct HaloT {
+    static constexpr int A_ATOMS = BF16 ? 2 : 4;
+    static constexpr int A_BYTES = A_ATOMS * HB_ATOM;
+    static constexpr int KSTEP_PX = BF16 ? 16 : 8;
+    static constexpr int KSTEPS = HB_PB / KSTEP_PX;
+    static constexpr int ELEMS = BF16 ? 64 : 32;          // elements per 128-byte atom row
+    static constexpr uint32_t LAYOUT = BF16 ? LAYOUT_SW128 : LAYOUT_SW128_BASE32B;
+    static constexpr uint32_t KGROUP_BYTES = BF16 ? 1024 : 512;
+};
 
 struct HaloP {
     float *dw;
@@ -43,14 +54,14 @@ struct HaloP {
     int stage_bytes, stages;
     int pad_h, pad_w;
     int krow[HB_PB / 8];       // halo row index of the first pixel of each K-step
-    unsigned b_sbo;            // 512 (8 px in one image row) or Wp*128 (OW == 4: two rows of 4)
+    unsigned b_sbo;            // stride between the two K groups of one K-step in the halo tile
 };
 
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int CN>
+template <int CN, bool BF16>
 __global__ void __launch_bounds__(HB_THREADS, 1)
 conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const HaloP p) {
     extern __shared__ uint8_t smem_raw[];
@@ -59,7 +70,8 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
     uint64_t *empty_bar = full_bar + 8;
     uint64_t *acc_full = empty_bar + 8;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_full + 1);
-    constexpr int ATOMS = CN / 32;
+    using T = HaloT<BF16>;
+    constexpr int ATOMS = CN / T::ELEMS;
     constexpr uint32_t TMEM_COLS = 512;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -88,7 +100,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
     if (nst > 0) {
         if (warp == 0) {
             if (lane == 0) {
-                const uint32_t tx_bytes = HB_A_BYTES + ATOMS * p.tn * p.th * p.Wp * 128;
+                const uint32_t tx_bytes = T::A_BYTES + ATOMS * p.tn * p.th * p.Wp * 128;
                 int stage = 0; uint32_t phase = 0;
                 int pix = b0 * HB_PB;
                 int n0 = pix / p.S, i0 = (p.S >= HB_PB) ? (pix - n0 * p.S) / p.OW : 0;
@@ -97,10 +109,11 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
                     uint8_t *sa = smem + stage * p.stage_bytes;
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) tma_load_2d(sa + a * HB_ATOM, &tmDY, &full_bar[stage], ft * 128 + a * 32, pix);
+                    for (int a = 0; a < T::A_ATOMS; ++a)
+                        tma_load_2d(sa + a * HB_ATOM, &tmDY, &full_bar[stage], ft * 128 + a * T::ELEMS, pix);
 #pragma unroll
                     for (int a = 0; a < ATOMS; ++a)
-                        tma_load_4d(sa + HB_A_BYTES + a * p.b_atom_bytes, &tmX, &full_bar[stage], ct * CN + a * 32, -p.pad_w,
+                        tma_load_4d(sa + T::A_BYTES + a * p.b_atom_bytes, &tmX, &full_bar[stage], ct * CN + a * T::ELEMS, -p.pad_w,
                                     i0 + u - p.pad_h, n0);
                     pix += HB_PB;
                     if (p.S >= HB_PB) { i0 += p.th; if (i0 * p.OW >= p.S) { i0 = 0; ++n0; } } else { n0 += p.tn; }
@@ -109,13 +122,13 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
             }
         } else if (warp == 1) {
             if (lane == 0) {
-                constexpr uint32_t idesc = make_idesc(2, 128, CN, 1, 1);      // both operands MN-major
+                constexpr uint32_t idesc = make_idesc(BF16 ? 1 : 2, 128, CN, 1, 1);      // both operands MN-major
                 // descriptor templates: everything but the 14-bit start address
-                const uint64_t a_hi = make_smem_desc(0, HB_ATOM, 512, LAYOUT_SW128_BASE32B);
-                const uint64_t b_hi = make_smem_desc(0, p.b_atom_bytes, p.b_sbo, LAYOUT_SW128_BASE32B);
-                uint32_t krow8[HB_PB / 8];                                   // K-step start rows, in 16-byte units
+                const uint64_t a_hi = make_smem_desc(0, HB_ATOM, T::KGROUP_BYTES, T::LAYOUT);
+                const uint64_t b_hi = make_smem_desc(0, p.b_atom_bytes, p.b_sbo, T::LAYOUT);
+                uint32_t krow8[T::KSTEPS];                                   // K-step start rows, in 16-byte units
 #pragma unroll
-                for (int k = 0; k < HB_PB / 8; ++k) krow8[k] = (uint32_t)p.krow[k] * 8u;
+                for (int k = 0; k < T::KSTEPS; ++k) krow8[k] = (uint32_t)p.krow[k] * 8u;
                 const int kw = p.kw;
                 int stage = 0; uint32_t phase = 0;
                 uint32_t accum = 0;
@@ -123,14 +136,17 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa16 = smem_u32(smem + stage * p.stage_bytes) >> 4;
-                    const uint32_t sb16 = sa16 + (HB_A_BYTES >> 4);
+                    const uint32_t sb16 = sa16 + (T::A_BYTES >> 4);
 #pragma unroll
-                    for (int k = 0; k < HB_PB / 8; ++k) {
-                        const uint64_t adesc = a_hi | (uint64_t)(sa16 + k * 64);      // +1024 B per K-step
+                    for (int k = 0; k < T::KSTEPS; ++k) {
+                        const uint64_t adesc = a_hi | (uint64_t)(sa16 + k * (T::KSTEP_PX * 8));   // K-step = KSTEP_PX rows of 128 B
                         const uint32_t brow = sb16 + krow8[k];
 #pragma unroll
                         for (int v = 0; v < HB_MAX_KW; ++v) {
-                            if (v < kw) mma_tf32(tmem_base + v * CN, adesc, b_hi | (uint64_t)(brow + v * 8), idesc, accum);
+                            if (v < kw) {
+                                if constexpr (BF16) mma_bf16(tmem_base + v * CN, adesc, b_hi | (uint64_t)(brow + v * 8), idesc, accum);
+                                else mma_tf32(tmem_base + v * CN, adesc, b_hi | (uint64_t)(brow + v * 8), idesc, accum);
+                            }
                         }
                         accum = 1;
                     }
@@ -167,12 +183,16 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
-bool block_geometry(int OH, int OW, int &th, int &tn) {
-    if (OW != 4 && OW != 8 && OW != 16 && OW != 32 && OW != 64) return false;
+// a K-step (8 px fp32 / 16 px bf16) is two K groups (4 / 8 halo rows each): either both lie in one
+// image row (contiguous), or each is exactly one image row (OW == group size) and they are Wp rows apart
+bool block_geometry(int OH, int OW, bool bf16, int &th, int &tn) {
+    const int group = bf16 ? 8 : 4;
+    if (OW != group && OW != 2 * group && OW != 4 * group && OW != 8 * group && OW != 16 * group) return false;
+    if (OW > 64) return false;
     const int S = OH * OW;
     if (S >= HB_PB) { if (S % HB_PB) return false; th = HB_PB / OW; tn = 1; }
     else { if (HB_PB % S) return false; th = OH; tn = HB_PB / S; }
-    if (OW == 4 && (th & 1)) return false;
+    if (OW == group && (th & 1)) return false;
     return true;
 }
 
@@ -182,40 +202,54 @@ int cn_for(int C, int kw) {
     return 0;
 }
 
+template <int CN, bool BF16>
+int launch_halo(const CUtensorMap &tmDY, const CUtensorMap &tmX, const HaloP &p, int grid, int smem, cudaStream_t st) {
+    static int configured = 0;
+    if (configured < smem) {
+        SN_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel<CN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    conv_wgrad_halo_kernel<CN, BF16><<<grid, HB_THREADS, smem, st>>>(tmDY, tmX, p);
+    return after_launch("conv_wgrad_halo_kernel");
+}
+
 }  // namespace
 
 namespace sn {
 
-bool wgrad_halo_eligible(int N, int C, int OH, int OW, int F, int kh, int kw, int stride) {
+bool wgrad_halo_eligible(int N, int C, int OH, int OW, int F, int kh, int kw, int stride, bool bf16) {
     int th, tn;
-    if (stride != 1 || kw < 2 || kw > HB_MAX_KW || kh > 16 || (F & 3)) return false;
-    if (!cn_for(C, kw) || !block_geometry(OH, OW, th, tn)) return false;
+    if (stride != 1 || kw < 2 || kw > HB_MAX_KW || kh > 16 || (F & (bf16 ? 7 : 3))) return false;
+    if (!cn_for(C, kw) || !block_geometry(OH, OW, bf16, th, tn)) return false;
     if (OW + kw - 1 > 256 || th > 256 || tn > 256) return false;
     const int CN = cn_for(C, kw);
     const int b_atom = ((tn * th * (OW + kw - 1) * 128) + 1023) / 1024 * 1024;
-    if (HB_A_BYTES + (CN / 32) * b_atom > 100 * 1024) return false;          // at least two stages
+    const int a_bytes = bf16 ? HaloT<true>::A_BYTES : HaloT<false>::A_BYTES;
+    if (a_bytes + (CN / (bf16 ? 64 : 32)) * b_atom > 100 * 1024) return false;          // at least two stages
     long long flops = 2ll * N * OH * OW * F * C * kh * kw;
     return flops >= (1ll << 26);
 }
 
 // x: NHWC (N, IH, IW, C); dy: (N*OH*OW, F); dw: [F][kh*kw][C] accumulated into (+=).
-int conv_wgrad_halo_tc(const float *x, const float *dy, float *dw, int N, int C, int IH, int IW, int F, int kh, int kw, int OH,
-                       int OW, int pad_h, int pad_w, cudaStream_t st) {
+int conv_wgrad_halo_tc(const void *x, const void *dy, float *dw, int N, int C, int IH, int IW, int F, int kh, int kw, int OH,
+                       int OW, int pad_h, int pad_w, bool bf16, cudaStream_t st) {
     if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) { set_error("conv_wgrad_halo_tc: tensors must be 16-byte aligned"); return SN_ERR_INVALID_ARG; }
     HaloP p{};
     const int CN = cn_for(C, kw);
     p.dw = dw; p.F = F; p.C = C; p.ntaps = kh * kw; p.kw = kw; p.kh = kh;
     p.OW = OW; p.S = OH * OW;
-    if (!CN || !block_geometry(OH, OW, p.th, p.tn)) { set_error("conv_wgrad_halo_tc: unsupported geometry"); return SN_ERR_UNSUPPORTED; }
+    if (!CN || !block_geometry(OH, OW, bf16, p.th, p.tn)) { set_error("conv_wgrad_halo_tc: unsupported geometry"); return SN_ERR_UNSUPPORTED; }
+    const int elems = bf16 ? 64 : 32, kstep_px = bf16 ? 16 : 8, group = bf16 ? 8 : 4;
+    const int a_bytes = bf16 ? HaloT<true>::A_BYTES : HaloT<false>::A_BYTES;
     p.Wp = OW + kw - 1;
     p.b_atom_bytes = ((p.tn * p.th * p.Wp * 128) + 1023) / 1024 * 1024;
-    p.stage_bytes = HB_A_BYTES + (CN / 32) * p.b_atom_bytes;
+    p.stage_bytes = a_bytes + (CN / elems) * p.b_atom_bytes;
     p.stages = (200 * 1024) / p.stage_bytes;
     if (p.stages > 6) p.stages = 6;
     p.pad_h = pad_h; p.pad_w = pad_w;
-    p.b_sbo = (OW >= 8) ? 512u : (unsigned)p.Wp * 128u;
-    for (int k = 0; k < HB_PB / 8; ++k) {
-        const int pl = k * 8;
+    p.b_sbo = (OW >= 2 * group) ? (unsigned)group * 128u : (unsigned)p.Wp * 128u;
+    for (int k = 0; k < HB_PB / kstep_px; ++k) {
+        const int pl = k * kstep_px;
         const int nl = pl / (p.th * OW), rem = pl % (p.th * OW);
         p.krow[k] = (nl * p.th + rem / OW) * p.Wp + rem % OW;
     }
@@ -231,25 +265,18 @@ int conv_wgrad_halo_tc(const float *x, const float *dy, float *dw, int N, int C,
     CUtensorMap tmDY, tmX;
     long long ddims[2] = {F, P};
     long long dstr[2] = {1, F};
-    int dbox[2] = {32, HB_PB};
-    int e = make_tmap_f32(&tmDY, dy, 2, ddims, dstr, dbox, true);
+    int dbox[2] = {elems, HB_PB};
+    int e = make_tmap(&tmDY, dy, 2, ddims, dstr, dbox, !bf16, bf16);
     if (e) return e;
     long long xdims[4] = {C, IW, IH, N};
     long long xstr[4] = {1, C, (long long)IW * C, (long long)IH * IW * C};
-    int xbox[4] = {32, p.Wp, p.th, p.tn};
-    e = make_tmap_f32(&tmX, x, 4, xdims, xstr, xbox, true);
+    int xbox[4] = {elems, p.Wp, p.th, p.tn};
+    e = make_tmap(&tmX, x, 4, xdims, xstr, xbox, !bf16, bf16);
     if (e) return e;
     const int smem = p.stages * p.stage_bytes + 1024 + 256;
-    if (CN == 128) {
-        static int configured = 0;
-        if (configured < smem) { SN_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = smem; }
-        conv_wgrad_halo_kernel<128><<<items * p.splits, HB_THREADS, smem, st>>>(tmDY, tmX, p);
-    } else {
-        static int configured = 0;
-        if (configured < smem) { SN_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = smem; }
-        conv_wgrad_halo_kernel<64><<<items * p.splits, HB_THREADS, smem, st>>>(tmDY, tmX, p);
-    }
-    return after_launch("conv_wgrad_halo_kernel");
+    const int grid = items * p.splits;
+    if (bf16) return CN == 128 ? launch_halo<128, true>(tmDY, tmX, p, grid, smem, st) : launch_halo<64, true>(tmDY, tmX, p, grid, smem, st);
+    return CN == 128 ? launch_halo<128, false>(tmDY, tmX, p, grid, smem, st) : launch_halo<64, false>(tmDY, tmX, p, grid, smem, st);
 }
 
 }  // namespace sn

@@ -213,6 +213,8 @@ class Layer(object):
         d['_bufs'] = {}
         for k in ('input_tensor', 'output_tensor', 'grads'):
             d[k] = None
+        for k in ('_xb', '_bf16_support'):
+            d.pop(k, None)
         return d
 
 

@@ -88,11 +88,37 @@ class Conv2D(Layer):
         kh, kw = self.filter_size
         oh, ow = self.output_shape[2:]
         y = self._buf('out', (N, F, oh, ow), 'nhwc')
-        lib.sn_conv2d_fprop(x.ptr, W.output_tensor.ptr, b.output_tensor.ptr, y.ptr, N, C, H, Wd, F, kh, kw,
-                            self.stride, self.pad_size[0], self.pad_size[1], self._act_code(),
-                            PRECISION[self.precision], current_stream())
+        geom = (N, C, H, Wd, F, kh, kw, self.stride, self.pad_size[0], self.pad_size[1])
+        st = current_stream()
+        self._xb = None
+        if self.precision == 'bf16' and self._bf16_ok(0, geom):
+            # bf16 tier: bf16 copies of the input map and the filters, fp32 accumulation and output
+            self._xb = self._bf16_buf('x_bf16', x.size)
+            wb = self._bf16_buf('w_bf16', W.size)
+            lib.sn_cast_f32_to_bf16(x.ptr, self._xb.data_ptr(), x.size, st)
+            lib.sn_cast_f32_to_bf16(W.output_tensor.ptr, wb.data_ptr(), W.size, st)
+            lib.sn_conv2d_fprop_bf16(self._xb.data_ptr(), wb.data_ptr(), b.output_tensor.ptr, y.ptr, *geom, self._act_code(), st)
+        else:
+            lib.sn_conv2d_fprop(x.ptr, W.output_tensor.ptr, b.output_tensor.ptr, y.ptr, *geom, self._act_code(),
+                                PRECISION[self.precision], st)
         self.output_tensor = y
         super(Conv2D, self).forward(is_training)
+
+    def _bf16_ok(self, op, geom):
+        key = (op,) + tuple(geom)
+        cache = self.__dict__.setdefault('_bf16_support', {})
+        if key not in cache:
+            cache[key] = bool(lib.load().sn_conv2d_bf16_supported(op, *geom))
+        return cache[key]
+
+    def _bf16_buf(self, name, n):
+        from ..device import empty, torch
+        key = (name, int(n))
+        t = self._bufs.get(key)
+        if t is None:
+            t = empty(int(n), torch().bfloat16)
+            self._bufs[key] = t
+        return t
 
     def backward(self):
         """layers/Convolution.py:182-205."""
@@ -106,9 +132,28 @@ class Conv2D(Layer):
         if self._act_code() == ACT['relu'] and not self._grads_premasked:
             lib.sn_relu_bwd(g.ptr, y.ptr, g.size, st)
         geom = (N, C, H, Wd, F, kh, kw, self.stride, self.pad_size[0], self.pad_size[1])
+        needs_dx = any(layer.require_grads for layer in self.inbounds)
+        bf16 = self.precision == 'bf16'
+        wgrad_bf16 = bf16 and self._xb is not None and self._bf16_ok(2, geom)
+        dgrad_bf16 = bf16 and needs_dx and self._bf16_ok(1, geom)
+        gb = None
+        if wgrad_bf16 or dgrad_bf16:
+            gb = self._bf16_buf('dy_bf16', g.size)
+            lib.sn_cast_f32_to_bf16(g.ptr, gb.data_ptr(), g.size, st)
         if W.require_grads or b.require_grads:
-            lib.sn_conv2d_wgrad(x.ptr, g.ptr, W.grads.ptr, b.grads.ptr if b.require_grads else None,
-                                *geom, 1, prec, st)
+            if wgrad_bf16:
+                lib.sn_conv2d_wgrad_bf16(self._xb.data_ptr(), gb.data_ptr(), g.ptr, W.grads.ptr,
+                                         b.grads.ptr if b.require_grads else None, *geom, st)
+            else:
+                lib.sn_conv2d_wgrad(x.ptr, g.ptr, W.grads.ptr, b.grads.ptr if b.require_grads else None,
+                                    *geom, 1, prec, st)
+        if dgrad_bf16:
+            wtb = self._bf16_buf('wt_bf16', W.size)
+            lib.sn_flip_transpose_filters_bf16(W.output_tensor.ptr, wtb.data_ptr(), F, C, kh, kw, st)
+            for layer in self.inbounds:
+                self._push_grad(layer, lambda dst, acc: lib.sn_conv2d_dgrad_bf16(
+                    gb.data_ptr(), wtb.data_ptr(), dst.ptr, *geom, acc, st))
+            return
         ws_bytes = lib.sn_conv2d_dgrad_workspace(C, F, kh, kw, prec)
         ws = self._buf('dgrad_ws', (ws_bytes // 4,), 'flat').ptr if ws_bytes else None
         for layer in self.inbounds:

@@ -152,8 +152,60 @@ def test_trajectory_cfg3_tf32():
     assert rel_err(np.asarray(convs[1].variables[0].output_tensor), net.params[4]) < 5e-2
 
 
-def test_bf16_tier_is_reported_as_not_built():
-    from shinnosuke_b200 import Sequential, Dense
-    m = Sequential([Dense(4, n_in=8)])
-    with pytest.raises(ValueError):
-        m.compile('sgd', 'sparse_categorical_crossentropy', precision='bf16')
+# ------------------------------------------------------------------------------ bf16 tier
+TOL_BF16 = 1e-2      # north_star: "1e-2 for bf16 against float64 NumPy"
+
+
+@pytest.mark.parametrize('shape', [
+    (4, 64, 16, 16, 128, 3, 1, 'SAME', 'relu'),      # cfg3 conv2 (wgrad: 16-px K-steps inside one image row)
+    (6, 128, 8, 8, 256, 3, 1, 'SAME', 'relu'),       # cfg3 conv3 (wgrad: K-step = two image rows of 8)
+    (24, 256, 4, 4, 256, 3, 1, 'SAME', 'linear'),    # cfg3 conv4 (bf16 fprop/dgrad, wgrad falls back to tf32 halo)
+    (2, 64, 32, 32, 64, 3, 1, 'SAME', 'relu'),       # cfg4 res64
+    (3, 64, 16, 16, 48, 5, 1, 'SAME', 'linear'),     # 5x5 taps, masked filter tile
+])
+def test_conv2d_bf16_vs_oracle(shape):
+    out = _run_conv(shape, 'bf16')
+    for name, (got, ref) in out.items():
+        assert rel_err(got, ref) < TOL_BF16, name
+
+
+def test_bf16_kernels_exact_on_bf16_representable_data():
+    """Small dyadic inputs are exact in bf16, so the bf16 tensor-core kernels (fprop, dgrad via flipped
+    filters, halo wgrad with 16-pixel K-steps) must match the oracle to fp32 accumulation accuracy."""
+    from shinnosuke_b200 import Conv2D, Input, Activation
+    from shinnosuke_b200.device import as_device
+    r = np.random.default_rng(11)
+    for (N, C, H, F) in [(4, 64, 16, 128), (4, 128, 8, 256)]:
+        x = r.integers(-8, 9, (N, C, H, H)).astype(np.float64) / 8.0
+        w = r.integers(-8, 9, (F, C, 3, 3)).astype(np.float64) / 16.0
+        b = r.integers(-4, 5, (1, F)).astype(np.float64)
+        gup = r.integers(-8, 9, (N, F, H, H)).astype(np.float64) / 4.0
+        y_ref, cache = O.conv2d_forward(x, w, b, 1, (1, 1), 'linear')
+        dx_ref, dw_ref, db_ref = O.conv2d_backward(gup, cache)
+        layer = Conv2D(F, (3, 3), padding='SAME', activation='linear')
+        inp = Input((None, C, H, H)); src = Activation('linear')(inp); layer(src)
+        layer.precision = 'bf16'
+        set_params(layer, w, b)
+        inp.input_tensor = x
+        for l in (inp, src, layer):
+            l.forward(True)
+        assert layer._xb is not None                      # the bf16 path was taken
+        assert rel_err(np.asarray(layer.output_tensor), y_ref) < 1e-6
+        layer._seed_grads(as_device(gup)); layer.backward()
+        assert rel_err(np.asarray(layer.variables[0].grads), dw_ref) < 1e-6
+        assert rel_err(np.asarray(src.grads), dx_ref) < 1e-6
+        assert rel_err(np.asarray(layer.variables[1].grads).reshape(-1), db_ref) < 1e-6
+
+
+def test_trajectory_cfg3_bf16():
+    from test_gpu_train import _vgg, _data
+    r, X = _data((32, 3, 32, 32), kind='normal')
+    Y = O.to_categorical(np.concatenate([np.arange(10), r.integers(0, 10, 22)]))
+    np.random.seed(0)
+    spec, ishape = O.spec_cfg3()
+    net = O.OracleNet(spec, ishape)
+    net.fit(X, Y, 16, 1, shuffle=False)
+    m = _vgg('bf16')
+    m.fit(X, Y, batch_size=16, epochs=1, shuffle=False, validation_ratio=0., verbose=0)
+    assert abs(m.train_loss[0] - net.train_loss[0]) < 2e-2 * net.train_loss[0]     # forward only
+    assert np.isfinite(m.train_loss).all()
