@@ -167,7 +167,8 @@ class ClockSampler(object):
 def kernel_work(name, a, precision):
     """Algorithmic work of one launch from its integer arguments (SURVEY.md 8(d) formulas).
     Returns (kind, amount): kind 'flops' or 'bytes'."""
-    if name in ('sn_conv2d_fprop', 'sn_conv2d_dgrad', 'sn_conv2d_wgrad'):
+    if name in ('sn_conv2d_fprop', 'sn_conv2d_dgrad', 'sn_conv2d_wgrad', 'sn_conv2d_fprop_bf16', 'sn_conv2d_dgrad_bf16',
+                'sn_conv2d_wgrad_bf16'):
         N, C, H, W, F, kh, kw, stride, ph, pw = a[:10]
         oh = (H + 2 * ph - kh) // stride + 1
         ow = (W + 2 * pw - kw) // stride + 1
@@ -195,6 +196,8 @@ def kernel_work(name, a, precision):
         return 'bytes', 16.0 * a[0]
     if name == 'sn_momentum_update':
         return 'bytes', 20.0 * a[0]
+    if name == 'sn_cast_f32_to_bf16':
+        return 'bytes', 6.0 * a[0]
     if name in ('sn_relu_bwd',):
         return 'bytes', 12.0 * a[0]
     if name in ('sn_nchw_to_nhwc', 'sn_nhwc_to_nchw'):
@@ -216,7 +219,9 @@ def roofline_from_profile(summary, precision, pk):
         r['share'] = r['ms'] * r['launches'] / total if total else 0.0
     top = rows[0]
     if top['kind'] == 'flops':
-        tensor_peak = {'fp32': None, 'tf32': pk['bf16'] / 2, 'bf16': pk['bf16']}[precision]
+        # the roof of the kernel that actually ran: bf16 entry points against the bf16 peak, the
+        # fp32-pointer tensor kernels (tf32) against half of it
+        tensor_peak = pk['bf16'] if top['name'].endswith('_bf16') else {'fp32': None, 'tf32': pk['bf16'] / 2, 'bf16': pk['bf16'] / 2}[precision]
         achieved = top['work'] / (top['ms'] * 1e-3) / 1e12
         if tensor_peak is None:
             # CUDA-core tier: there is no tensor-pipe roof; report against the TF32 tensor roof it competes with

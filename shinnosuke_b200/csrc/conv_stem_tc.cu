@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
     uint64_t *t_empty = t_full + 2;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(t_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     // weights -> smem in the swizzled K-major layout: row f, 16-byte chunk j at (j ^ (f & 7)) * 16
     for (int i = threadIdx.x; i < BN * 32; i += SF_THREADS) {
@@ -108,10 +108,10 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);     // shuffle from lane 0: provably warp-uniform
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // warp-uniform control flow; the elected lane issues (operands stay in uniform registers)
             constexpr uint32_t idesc = make_idesc(2, 128, BN, 0, 0);
             const uint64_t bdesc = make_smem_desc(smem_u32(sB), 0, 1024);
             int buf = 0; uint32_t phase = 0; int iter = 0;
@@ -121,10 +121,13 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
                 mbar_wait(&a_full[buf], phase);
                 tc_fence_after();
                 const uint64_t adesc = make_smem_desc(smem_u32(sA + buf * SF_A_BYTES), 0, 1024);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mma_tf32(tmem_base + acc * BN, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : 0u);
-                mma_commit(&a_empty[buf]);
-                mma_commit(&t_full[acc]);
+                    for (int k = 0; k < 4; ++k) mma_tf32(tmem_base + acc * BN, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : 0u);
+                    mma_commit(&a_empty[buf]);
+                    mma_commit(&t_full[acc]);
+                }
+                __syncwarp();
                 if (++buf == SF_ABUF) { buf = 0; phase ^= 1; }
             }
         }
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
     uint64_t *acc_full = empty + SW_STAGES;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_full + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int f_tile = blockIdx.y;
     const int t0 = blockIdx.x * p.tiles_per_cta;
     const int t1 = min(p.tiles, t0 + p.tiles_per_cta);
@@ -229,24 +232,27 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);     // shuffle from lane 0: provably warp-uniform
 
     if (nst > 0) {
         if (warp == 0) {
-            if (lane == 0) {
-                // one thread is both the TMA producer and the MMA issuer (the MMAs are negligible here):
-                // it runs the loads LOOKAHEAD stages ahead of the MMAs.
+            {
+                // one warp is both the TMA producer and the MMA issuer (the MMAs are negligible here): it runs the
+                // loads SW_STAGES ahead of the MMAs.  Warp-uniform control flow, the elected lane issues.
                 constexpr uint32_t idesc = make_idesc(2, 128, 32, 1, 1);
                 int ld = 0, ld_stage = 0; uint32_t ld_phase = 0;
                 int stage = 0; uint32_t phase = 0;
                 for (int s = 0; s < nst; ++s) {
                     while (ld < nst && ld < s + SW_STAGES) {
                         mbar_wait(&empty[ld_stage], ld_phase ^ 1);
-                        mbar_expect_tx(&full[ld_stage], SW_A_BYTES);
                         uint8_t *sa = smem + ld_stage * SW_STAGE_BYTES;
+                        if (elect_one()) {
+                            mbar_expect_tx(&full[ld_stage], SW_A_BYTES);
 #pragma unroll
-                        for (int a = 0; a < 4; ++a)
-                            tma_load_2d(sa + a * SW_ATOM, &tmDY, &full[ld_stage], f_tile * 128 + a * 32, (t0 + ld) * SW_PB);
+                            for (int a = 0; a < 4; ++a)
+                                tma_load_2d(sa + a * SW_ATOM, &tmDY, &full[ld_stage], f_tile * 128 + a * 32, (t0 + ld) * SW_PB);
+                        }
+                        __syncwarp();
                         ++ld;
                         if (++ld_stage == SW_STAGES) { ld_stage = 0; ld_phase ^= 1; }
                     }
@@ -257,12 +263,14 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
                     for (int k = 0; k < SW_PB / 8; ++k) {
                         const uint64_t adesc = make_smem_desc(sa + k * 1024, SW_ATOM, 512, LAYOUT_SW128_BASE32B);
                         const uint64_t bdesc = make_smem_desc(sa + SW_A_BYTES + k * 1024, SW_ATOM, 512, LAYOUT_SW128_BASE32B);
-                        mma_tf32(tmem_base, adesc, bdesc, idesc, (s | k) != 0 ? 1u : 0u);
+                        if (elect_one()) mma_tf32(tmem_base, adesc, bdesc, idesc, (s | k) != 0 ? 1u : 0u);
                     }
-                    mma_commit(&empty[stage]);
+                    if (elect_one()) mma_commit(&empty[stage]);
+                    __syncwarp();
                     if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
                 }
-                mma_commit(acc_full);
+                if (elect_one()) mma_commit(acc_full);
+                __syncwarp();
             }
         } else if (warp <= SW_BUILDERS / 32) {
             // column builders: thread (r, kq) builds k = 8kq..8kq+7 (one 32-byte chunk) of pixel row r

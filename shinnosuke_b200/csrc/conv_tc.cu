@@ -126,7 +126,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role index
     const int lane = threadIdx.x & 31;
     constexpr int BKE = BF16 ? 64 : 32;               // contraction elements per 128-byte k-block
     const int num_tiles = p.tiles_m * p.tiles_n;
@@ -147,11 +147,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);     // shuffle from lane 0: provably warp-uniform
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // The whole warp runs the (uniform) control flow and address arithmetic; lane 0 issues.
+        // UTMALDG / UTCHMMA take their operands from UNIFORM registers: under a divergent
+        // `if (lane == 0)` every operand needed an R2UR move per instruction (~100 cycles per MMA).
+        {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int tm = tile / p.tiles_n, tn_idx = tile % p.tiles_n;
@@ -161,21 +164,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 int tap = 0, cb = 0, u = 0, v = 0;
                 for (int ks = 0; ks < kstages; ++ks) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    if (elect_one()) mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
 #pragma unroll
                     for (int s = 0; s < KS; ++s) {
                         uint8_t *sa = smem + stage * Cfg::STAGE_BYTES + s * Cfg::SLAB_BYTES;
-                        tma_load_4d(sa, &tmA, &full_bar[stage], cb * BKE, v - p.pad_w, h0 + u - p.pad_h, n0);
-                        tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], tap * p.C + cb * BKE, tn_idx * BN);
+                        if (elect_one()) {
+                            tma_load_4d(sa, &tmA, &full_bar[stage], cb * BKE, v - p.pad_w, h0 + u - p.pad_h, n0);
+                            tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], tap * p.C + cb * BKE, tn_idx * BN);
+                        }
                         if (++cb == p.cblocks) { cb = 0; ++tap; if (++v == p.taps_w) { v = 0; ++u; } }
                     }
+                    __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (warp-uniform control flow, lane 0 issues) =====================
+        {
             constexpr uint32_t idesc = make_idesc(BF16 ? 1 : 2, BM, BN, 0, 0);
             int stage = 0; uint32_t phase = 0;
             int iter = 0;
@@ -192,17 +198,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES + s * Cfg::SLAB_BYTES);
                         const uint64_t adesc = make_smem_desc(sa, 0, 1024);
                         const uint64_t bdesc = make_smem_desc(sa + A_BYTES, 0, 1024);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / UK; ++k) {
-                            // advancing K inside the 128-byte swizzle row: +32 bytes = +2 descriptor units
-                            if constexpr (BF16) mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | s | k) != 0 ? 1u : 0u);
-                            else mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | s | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < BK / UK; ++k) {
+                                // advancing K inside the 128-byte swizzle row: +32 bytes = +2 descriptor units
+                                if constexpr (BF16) mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | s | k) != 0 ? 1u : 0u);
+                                else mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | s | k) != 0 ? 1u : 0u);
+                            }
                         }
                     }
-                    mma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
+                    if (elect_one()) mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                mma_commit(&tmem_full[acc]);                       // accumulator complete -> epilogue
+                if (elect_one()) mma_commit(&tmem_full[acc]);        // accumulator complete -> epilogue
+                __syncwarp();
             }
         }
     } else {
@@ -379,7 +389,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     uint64_t *acc_full = empty_bar + Cfg::STAGES;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_full + 1);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role index
     const int lane = threadIdx.x & 31;
 
     // work item of this CTA
@@ -407,11 +417,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);     // shuffle from lane 0: provably warp-uniform
 
     if (nkb > 0) {
         if (warp == 0) {
-            if (lane == 0) {
+            {   // warp-uniform control flow; the elected lane issues (see conv_igemm_kernel)
                 int stage = 0; uint32_t phase = 0;
                 for (int pb = pb0; pb < pb1; ++pb) {
                     const int pix = pb * PB;
@@ -419,24 +429,27 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                     if (p.S >= PB) { n0 = pix / p.S; i0 = (pix % p.S) / p.OW; }
                     else { n0 = pix / p.S; i0 = 0; }
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     uint8_t *sa = smem + stage * Cfg::STAGE_BYTES;
+                    if (elect_one()) {
+                        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
-                        tma_load_2d(sa + a * ATOM_BYTES, &tmDY, &full_bar[stage], ft * 128 + a * 32, pix);
+                        for (int a = 0; a < 4; ++a)
+                            tma_load_2d(sa + a * ATOM_BYTES, &tmDY, &full_bar[stage], ft * 128 + a * 32, pix);
 #pragma unroll
-                    for (int t = 0; t < TAPS; ++t) {
-                        const int u = (tap0 + t) / p.taps_w, v = (tap0 + t) % p.taps_w;
+                        for (int t = 0; t < TAPS; ++t) {
+                            const int u = (tap0 + t) / p.taps_w, v = (tap0 + t) % p.taps_w;
 #pragma unroll
-                        for (int b = 0; b < CN / 32; ++b)
-                            tma_load_4d(sa + WG_A_BYTES + t * Cfg::B_BYTES + b * ATOM_BYTES, &tmX, &full_bar[stage],
-                                        ct * CN + b * 32, v - p.pad_w, i0 + u - p.pad_h, n0);
+                            for (int b = 0; b < CN / 32; ++b)
+                                tma_load_4d(sa + WG_A_BYTES + t * Cfg::B_BYTES + b * ATOM_BYTES, &tmX, &full_bar[stage],
+                                            ct * CN + b * 32, v - p.pad_w, i0 + u - p.pad_h, n0);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         } else if (warp == 1) {
-            if (lane == 0) {
+            {
                 constexpr uint32_t idesc = make_idesc(2, 128, CN, 1, 1);      // both operands MN-major
                 int stage = 0; uint32_t phase = 0;
                 for (int kb = 0; kb < nkb; ++kb) {
@@ -452,13 +465,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                         for (int t = 0; t < TAPS; ++t) {
                             const uint64_t bdesc = make_smem_desc(sa + WG_A_BYTES + t * Cfg::B_BYTES + k * 1024, ATOM_BYTES, 512,
                                                                   LAYOUT_SW128_BASE32B);
-                            mma_tf32(tmem_base + t * CN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                            if (elect_one()) mma_tf32(tmem_base + t * CN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                     }
-                    mma_commit(&empty_bar[stage]);
+                    if (elect_one()) mma_commit(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                mma_commit(acc_full);
+                if (elect_one()) mma_commit(acc_full);
+                __syncwarp();
             }
         } else {
             const int q = warp & 3;

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 using namespace sn;
 using namespace sn::tc;
@@ -74,7 +75,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
     constexpr int ATOMS = CN / T::ELEMS;
     constexpr uint32_t TMEM_COLS = 512;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int split = blockIdx.x % p.splits;
     int item = blockIdx.x / p.splits;
     const int u = item % p.kh; item /= p.kh;
@@ -95,33 +96,36 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);     // shuffle from lane 0: provably warp-uniform
 
     if (nst > 0) {
         if (warp == 0) {
-            if (lane == 0) {
+            {   // warp-uniform control flow, lane 0 issues (TMA / MMA operands live in uniform registers)
                 const uint32_t tx_bytes = T::A_BYTES + ATOMS * p.tn * p.th * p.Wp * 128;
                 int stage = 0; uint32_t phase = 0;
                 int pix = b0 * HB_PB;
                 int n0 = pix / p.S, i0 = (p.S >= HB_PB) ? (pix - n0 * p.S) / p.OW : 0;
                 for (int b = b0; b < b1; ++b) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], tx_bytes);
                     uint8_t *sa = smem + stage * p.stage_bytes;
+                    if (elect_one()) {
+                        mbar_expect_tx(&full_bar[stage], tx_bytes);
 #pragma unroll
-                    for (int a = 0; a < T::A_ATOMS; ++a)
-                        tma_load_2d(sa + a * HB_ATOM, &tmDY, &full_bar[stage], ft * 128 + a * T::ELEMS, pix);
+                        for (int a = 0; a < T::A_ATOMS; ++a)
+                            tma_load_2d(sa + a * HB_ATOM, &tmDY, &full_bar[stage], ft * 128 + a * T::ELEMS, pix);
 #pragma unroll
-                    for (int a = 0; a < ATOMS; ++a)
-                        tma_load_4d(sa + T::A_BYTES + a * p.b_atom_bytes, &tmX, &full_bar[stage], ct * CN + a * T::ELEMS, -p.pad_w,
-                                    i0 + u - p.pad_h, n0);
+                        for (int a = 0; a < ATOMS; ++a)
+                            tma_load_4d(sa + T::A_BYTES + a * p.b_atom_bytes, &tmX, &full_bar[stage], ct * CN + a * T::ELEMS,
+                                        -p.pad_w, i0 + u - p.pad_h, n0);
+                    }
+                    __syncwarp();
                     pix += HB_PB;
                     if (p.S >= HB_PB) { i0 += p.th; if (i0 * p.OW >= p.S) { i0 = 0; ++n0; } } else { n0 += p.tn; }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         } else if (warp == 1) {
-            if (lane == 0) {
+            {
                 constexpr uint32_t idesc = make_idesc(BF16 ? 1 : 2, 128, CN, 1, 1);      // both operands MN-major
                 // descriptor templates: everything but the 14-bit start address
                 const uint64_t a_hi = make_smem_desc(0, HB_ATOM, T::KGROUP_BYTES, T::LAYOUT);
@@ -143,17 +147,19 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
                         const uint32_t brow = sb16 + krow8[k];
 #pragma unroll
                         for (int v = 0; v < HB_MAX_KW; ++v) {
-                            if (v < kw) {
+                            if (v < kw && elect_one()) {
                                 if constexpr (BF16) mma_bf16(tmem_base + v * CN, adesc, b_hi | (uint64_t)(brow + v * 8), idesc, accum);
                                 else mma_tf32(tmem_base + v * CN, adesc, b_hi | (uint64_t)(brow + v * 8), idesc, accum);
                             }
                         }
                         accum = 1;
                     }
-                    mma_commit(&empty_bar[stage]);
+                    if (elect_one()) mma_commit(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                mma_commit(acc_full);
+                if (elect_one()) mma_commit(acc_full);
+                __syncwarp();
             }
         } else {
             const int q = warp & 3;
