@@ -11,6 +11,7 @@
 // or first-argmax routing, and (optionally) the producing layer's ReLU mask applied to dX.
 #include "common.cuh"
 #include "bn_common.cuh"
+#include <stdlib.h>
 using namespace sn;
 
 namespace {
@@ -171,9 +172,9 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__r
     }
 }
 
-int grid_for_windows(long long windows4) {
+int grid_for_windows(long long windows4, int ctas_per_sm = 8) {
     long long need = (windows4 + 255) / 256;
-    long long cap = (long long)num_sms() * 8;
+    long long cap = (long long)num_sms() * ctas_per_sm;
     return (int)(need < 1 ? 1 : (need < cap ? need : cap));
 }
 
@@ -222,15 +223,17 @@ int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, co
     const int oh = H / 2, ow = W / 2;
     const long long windows4 = (long long)N * oh * ow * (C / 4);
     const int grid = grid_for_windows(windows4);
+    // fewer, longer-lived reduce blocks on small maps (see bn.cu: bn_reduce_ctas)
+    const int rgrid = grid_for_windows(windows4, rows * C * 4 >= (100ll << 20) ? 8 : 3);
     const uint32_t *cd = (const uint32_t *)code;
     SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * BN_SCRATCH_DOUBLES_PER_C * C, st));
     BnFinal fin{};
     fin.bwd = 1; fin.rows = rows; fin.C = C; fin.gamma = gamma; fin.mean = save_mean; fin.invstd = save_invstd;
     fin.dgamma = dgamma; fin.dbeta = dbeta;
     if (pool_mode == SN_POOL_TIE_SPLIT)
-        bn_pool_bwd_reduce_kernel<SN_POOL_TIE_SPLIT><<<grid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
+        bn_pool_bwd_reduce_kernel<SN_POOL_TIE_SPLIT><<<rgrid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
     else
-        bn_pool_bwd_reduce_kernel<SN_POOL_FIRST_ARGMAX><<<grid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
+        bn_pool_bwd_reduce_kernel<SN_POOL_FIRST_ARGMAX><<<rgrid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
     int e = after_launch("bn_pool_bwd_reduce_kernel");
     if (e) return e;
 #define SN_LAUNCH(M, K) bn_pool_bwd_apply_kernel<M, K><<<grid, 256, 0, st>>>(dy_pool, cd, x, dx, scratch, windows4, C, W, oh, ow)
