@@ -138,9 +138,11 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
         KSlice ks;
         make_kslice(p, kq, ks);
         int buf = 0; uint32_t phase = 0;
+        float col[8], nxt[8];
+        if ((int)blockIdx.x < p.tiles) gather_slice(p, ks, blockIdx.x * 128 + r, kq, -1, col);
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-            float col[8];
-            gather_slice(p, ks, tile * 128 + r, kq, -1, col);
+            // the next tile's loads are in flight while this one waits for its buffer and stores
+            if (tile + (int)gridDim.x < p.tiles) gather_slice(p, ks, (tile + gridDim.x) * 128 + r, kq, -1, nxt);
             mbar_wait(&a_empty[buf], phase ^ 1);
             uint8_t *row = sA + buf * SF_A_BYTES + r * 128;
             // SW128 K-major: 16-byte chunk j of row r lives at (j ^ (r & 7)) * 16
@@ -149,6 +151,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
             fence_proxy_async();               // make the generic-proxy writes visible to the tensor core
             mbar_arrive(&a_full[buf]);
             if (++buf == SF_ABUF) { buf = 0; phase ^= 1; }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) col[e] = nxt[e];
         }
     } else {
         // ---------------- epilogue: TMEM -> bias/ReLU -> NHWC output ----------------
@@ -280,9 +284,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
             make_kslice(p, kq, ks);
             const int one_at = p.db ? p.K : -1;
             int stage = 0; uint32_t phase = 0;
+            float col[8], nxt[8];
+            gather_slice(p, ks, t0 * SW_PB + r, kq, one_at, col);   // rows past the end stay 0 (dY is TMA zero-filled too)
             for (int s = 0; s < nst; ++s) {
-                float col[8];
-                gather_slice(p, ks, (t0 + s) * SW_PB + r, kq, one_at, col);   // rows past the end stay 0 (dY is TMA zero-filled too)
+                // the next stage's loads are in flight while this one waits for its slot and stores
+                if (s + 1 < nst) gather_slice(p, ks, (t0 + s + 1) * SW_PB + r, kq, one_at, nxt);
                 mbar_wait(&empty[stage], phase ^ 1);
                 // 128B swizzle with 32-byte atoms: 32-byte chunk j of row r lives at (j ^ (r & 3)) * 32
                 uint8_t *dst = smem + stage * SW_STAGE_BYTES + SW_A_BYTES + r * 128 + ((kq ^ (r & 3)) * 32);
@@ -291,6 +297,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
                 fence_proxy_async();
                 mbar_arrive(&full[stage]);
                 if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) col[e] = nxt[e];
             }
         } else {
             // epilogue (warps 9..12): dW[f][k] += D[f][k], db[f] += D[f][K]
