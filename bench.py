@@ -168,7 +168,7 @@ def kernel_work(name, a, precision):
     """Algorithmic work of one launch from its integer arguments (SURVEY.md 8(d) formulas).
     Returns (kind, amount): kind 'flops' or 'bytes'."""
     if name in ('sn_conv2d_fprop', 'sn_conv2d_dgrad', 'sn_conv2d_wgrad', 'sn_conv2d_fprop_bf16', 'sn_conv2d_dgrad_bf16',
-                'sn_conv2d_wgrad_bf16'):
+                'sn_conv2d_wgrad_bf16', 'sn_conv2d_fprop_stats', 'sn_conv2d_fprop_bf16_stats'):
         N, C, H, W, F, kh, kw, stride, ph, pw = a[:10]
         oh = (H + 2 * ph - kh) // stride + 1
         ow = (W + 2 * pw - kw) // stride + 1
@@ -189,9 +189,15 @@ def kernel_work(name, a, precision):
     if name == 'sn_bn_pool_fwd_train':
         N, H, W, C = a[:4]
         return 'bytes', 8.0 * N * H * W * C + 5.0 * N * (H // 2) * (W // 2) * C     # x read twice; pooled y + code written
+    if name == 'sn_bn_pool_fwd_apply':
+        N, H, W, C = a[:4]
+        return 'bytes', 4.0 * N * H * W * C + 5.0 * N * (H // 2) * (W // 2) * C     # x read once; pooled y + code written
+    if name == 'sn_batchnorm_fwd_apply':
+        return 'bytes', 8.0 * a[0] * a[1]
     if name == 'sn_bn_pool_bwd':
         N, H, W, C = a[:4]
-        return 'bytes', 12.0 * N * H * W * C + 10.0 * N * (H // 2) * (W // 2) * C   # x twice + dx; dy_pool + code twice
+        # reduce: dy_pool + y_pool; apply: x read, dx written, dy_pool + code read
+        return 'bytes', 8.0 * N * H * W * C + 13.0 * N * (H // 2) * (W // 2) * C
     if name == 'sn_sgd_update':
         return 'bytes', 16.0 * a[0]
     if name == 'sn_momentum_update':

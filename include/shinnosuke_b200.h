@@ -107,6 +107,18 @@ SN_API int sn_add(const float *a, const float *b, float *out, long long n, void 
 SN_API int sn_conv2d_fprop(const float *x, const float *w, const float *bias, float *y,
                     int N, int C, int H, int W, int F, int kh, int kw,
                     int stride, int pad_h, int pad_w, int act, int precision, void *stream);
+/* sn_conv2d_fprop that also leaves the per-channel sums of its output (sum y, sum y^2: the batch
+ * statistics a following BatchNormalization needs, layers/Normalization.py:116-118) in
+ * `bn_scratch` (>= 20*F doubles), saving that layer its own read of y.  The sums are ADDED: the
+ * scratch must be all zero on entry, which is how cudaMemset or any of the sn_batchnorm_* /
+ * sn_bn_pool_* calls on a C = 4*2^k map leave it (their finalise step re-zeroes what it consumed).
+ * Only the tensor-core kernels do this: ask sn_conv2d_fprop_stats_supported (bf16_operands = 1
+ * for sn_conv2d_fprop_bf16_stats) first.  Follow with sn_batchnorm_finalize_stats. */
+SN_API int sn_conv2d_fprop_stats_supported(int precision, int bf16_operands, int N, int C, int H, int W, int F,
+                                    int kh, int kw, int stride, int pad_h, int pad_w);
+SN_API int sn_conv2d_fprop_stats(const float *x, const float *w, const float *bias, float *y,
+                          int N, int C, int H, int W, int F, int kh, int kw,
+                          int stride, int pad_h, int pad_w, int act, int precision, double *bn_scratch, void *stream);
 /* Conv2D.backward dX, layers/Convolution.py:199-202 + utils/ConvCol.py:24-42 (col2im-free).
  * The tensor-core tiers run dgrad as a forward convolution of dY with the filters flipped and
  * transposed; `workspace` holds that copy (sn_conv2d_dgrad_workspace() bytes, device memory,
@@ -144,6 +156,9 @@ SN_API int sn_conv2d_bf16_supported(int op, int N, int C, int H, int W, int F, i
 SN_API int sn_conv2d_fprop_bf16(const void *x_bf16, const void *w_bf16, const float *bias, float *y,
                          int N, int C, int H, int W, int F, int kh, int kw,
                          int stride, int pad_h, int pad_w, int act, void *stream);
+SN_API int sn_conv2d_fprop_bf16_stats(const void *x_bf16, const void *w_bf16, const float *bias, float *y,
+                               int N, int C, int H, int W, int F, int kh, int kw,
+                               int stride, int pad_h, int pad_w, int act, double *bn_scratch, void *stream);
 /* wt_bf16: filters flipped and transposed by sn_flip_transpose_filters_bf16 */
 SN_API int sn_conv2d_dgrad_bf16(const void *dy_bf16, const void *wt_bf16, float *dx,
                          int N, int C, int H, int W, int F, int kh, int kw,
@@ -210,6 +225,15 @@ SN_API int sn_batchnorm_stats(const float *x, const float *gamma, const float *b
                        float *save_invstd, float *moving_mean, float *moving_var, double *scratch,
                        long long rows, int C, float eps, float momentum, void *stream);
 
+/* The two halves of the training forward when the producing convolution already reduced the
+ * statistics (sn_conv2d_fprop_stats): finalize turns the sums in `scratch` into save_mean /
+ * save_invstd, updates the moving statistics and leaves the apply constants in `scratch`; apply
+ * is y = gamma*(x-mean)*invstd + beta.  Both need C = 4*2^k <= 1024. */
+SN_API int sn_batchnorm_finalize_stats(const float *gamma, const float *beta, float *save_mean, float *save_invstd,
+                                float *moving_mean, float *moving_var, double *scratch,
+                                long long rows, int C, float eps, float momentum, void *stream);
+SN_API int sn_batchnorm_fwd_apply(const float *x, float *y, const double *scratch, long long rows, int C, void *stream);
+
 /* BatchNormalization immediately followed by MaxPooling2D((2,2)) (stride 2), fused: the normalised
  * map is never written.  x: conv output (N,H,W,C); y_pool: (N,H/2,W/2,C); code: one byte per
  * pooled element (same meaning as sn_maxpool2d_fwd).  Requires sn_bn_pool_supported(). */
@@ -218,10 +242,18 @@ SN_API int sn_bn_pool_fwd_train(const float *x, const float *gamma, const float 
                          float *save_mean, float *save_invstd, float *moving_mean, float *moving_var,
                          double *scratch, int N, int H, int W, int C, float eps, float momentum,
                          int pool_mode, void *stream);
-/* backward of the fused pair: dy_pool (N,H/2,W/2,C) -> dx (N,H,W,C) (overwritten), dgamma/dbeta += */
-SN_API int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, const float *gamma,
-                   const float *save_mean, const float *save_invstd, float *dx, float *dgamma, float *dbeta,
-                   double *scratch, int N, int H, int W, int C, int pool_mode, int mask_relu, void *stream);
+/* pass 2 of sn_bn_pool_fwd_train alone (constants already in scratch: sn_batchnorm_stats or
+ * sn_batchnorm_finalize_stats ran) */
+SN_API int sn_bn_pool_fwd_apply(const float *x, float *y_pool, uint8_t *code, const double *scratch,
+                         int N, int H, int W, int C, int pool_mode, void *stream);
+/* backward of the fused pair: dy_pool (N,H/2,W/2,C) -> dx (N,H,W,C) (overwritten), dgamma/dbeta +=.
+ * y_pool / beta (both or neither; may be NULL): the forward's pooled output and the shift it was
+ * computed with.  With them the two reductions of BatchNormalization.backward (:196-203) read the
+ * pooled tensors only, since every pool winner satisfies xhat = (y_pool - beta)/gamma. */
+SN_API int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, const float *y_pool,
+                   const float *gamma, const float *beta, const float *save_mean, const float *save_invstd,
+                   float *dx, float *dgamma, float *dbeta, double *scratch, int N, int H, int W, int C,
+                   int pool_mode, int mask_relu, void *stream);
 
 /* ------------------------------------------------------------------ loss */
 /* Softmax._forward, utils/Activator.py:108-110 (row-wise; the reference's global shift cancels) */

@@ -297,6 +297,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_pow2_kernel(const float *__r
     }
 }
 
+__global__ void bn_finalize_kernel(double *scratch, BnFinal fin) { bn_finalize_channels(scratch, fin); }
+
 static bool bn_pow2(int C) {
     if (C & 3) return false;
     int q = C >> 2;
@@ -338,6 +340,26 @@ int sn_batchnorm_stats(const float *x, const float *gamma, const float *beta, fl
     fin.save_invstd = save_invstd; fin.moving_mean = moving_mean; fin.moving_var = moving_var; fin.eps = eps; fin.momentum = momentum;
     bn_reduce_pow2_kernel<false><<<bn_grid(total4, bn_reduce_ctas(total4)), 256, 0, st>>>(x, nullptr, nullptr, nullptr, scratch, total4, C, fin);
     return after_launch("bn_reduce_pow2_kernel");
+}
+
+int sn_batchnorm_finalize_stats(const float *gamma, const float *beta, float *save_mean, float *save_invstd,
+                                float *moving_mean, float *moving_var, double *scratch, long long rows, int C, float eps,
+                                float momentum, void *stream) {
+    SN_REQUIRE(gamma && beta && save_mean && save_invstd && moving_mean && moving_var && scratch, "null tensor");
+    SN_REQUIRE(rows > 0 && bn_pow2(C), "needs C = 4*2^k <= 1024");
+    BnFinal fin{};
+    fin.bwd = 0; fin.rows = rows; fin.C = C; fin.x = nullptr; fin.gamma = gamma; fin.beta = beta; fin.save_mean = save_mean;
+    fin.save_invstd = save_invstd; fin.moving_mean = moving_mean; fin.moving_var = moving_var; fin.eps = eps; fin.momentum = momentum;
+    bn_finalize_kernel<<<1, C < 256 ? C : 256, 0, as_stream(stream)>>>(scratch, fin);
+    return after_launch("bn_finalize_kernel");
+}
+
+int sn_batchnorm_fwd_apply(const float *x, float *y, const double *scratch, long long rows, int C, void *stream) {
+    SN_REQUIRE(x && y && scratch && rows > 0, "bad arguments");
+    SN_REQUIRE(bn_pow2(C) && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0, "needs C = 4*2^k <= 1024 and 16-byte aligned tensors");
+    const long long total4 = rows * C / 4;
+    bn_apply_train_pow2_kernel<<<bn_grid(total4), 256, 0, as_stream(stream)>>>(x, y, scratch, total4, C);
+    return after_launch("bn_apply_train_pow2_kernel");
 }
 
 int sn_batchnorm_fwd_train(const float *x, const float *gamma, const float *beta, float *y, float *save_mean,

@@ -1,7 +1,8 @@
 // Shared by bn.cu and bn_pool.cu: layout of the float64 scratch and the "last block finalises"
 // step that turns the per-channel sums into the few fp32 constants the apply pass needs.
 //
-// scratch (>= 20*C doubles, zeroed by the host wrapper before the reduce kernel):
+// scratch (>= 20*C doubles, zeroed by the host wrapper before the reduce kernel; the finalise step
+// leaves the sums and the ticket zero again):
 //   [0, 16C)        BN_SLOTS copies of {sum_a[C], sum_b[C]}  (slot = blockIdx.x % BN_SLOTS: short atomic chains)
 //   [16C, 18C)      4*C floats: p0[C], p1[C], p2[C] (apply-pass constants), 1 spare row
 //   [18C]           ticket counter (unsigned)
@@ -34,22 +35,13 @@ struct BnFinal {
 __device__ __forceinline__ float *bn_params(double *scratch, int C) { return reinterpret_cast<float *>(scratch + 16 * (size_t)C); }
 __device__ __forceinline__ const float *bn_params(const double *scratch, int C) { return reinterpret_cast<const float *>(scratch + 16 * (size_t)C); }
 
-// Call at the end of a reduce kernel, after this block's atomics.  The last block to arrive
-// computes, per channel:
+// Turns the per-channel sums in `scratch` into the apply-pass constants, per channel:
 //   forward : p0 = gamma*invstd, p1 = beta - gamma*invstd*mean            (y  = p0*x + p1)
 //   backward: p0 = gamma*invstd, p1 = -p0*k3*invstd, p2 = -p0*k2 - p1*mean (dx = p0*dy + p1*x + p2)
 //             with k2 = sum(dy)/rows, k3 = sum(dy*xhat)/rows; dgamma += sum(dy*xhat), dbeta += sum(dy)
-__device__ __forceinline__ void bn_finalize_last_block(double *scratch, const BnFinal &f) {
-    __shared__ bool is_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned *ticket = reinterpret_cast<unsigned *>(scratch + 18 * (size_t)f.C);
-        is_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
+// Forward sums are of (x - pivot), pivot = f.x[0][c], or of x itself when f.x == nullptr (sums that
+// a convolution epilogue produced).  One block's threads stride over the channels.
+__device__ __forceinline__ void bn_finalize_channels(double *scratch, const BnFinal &f) {
     const int C = f.C;
     float *prm = bn_params(scratch, C);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -58,9 +50,13 @@ __device__ __forceinline__ void bn_finalize_last_block(double *scratch, const Bn
         for (int s = 0; s < BN_SLOTS; ++s) {
             a += __ldcg(scratch + (size_t)s * 2 * C + c);
             b += __ldcg(scratch + (size_t)s * 2 * C + C + c);
+            // consumed: leave the sums zero again, so that a producer that only ADDS into the scratch
+            // (the convolution epilogues, sn_conv2d_fprop_stats) needs no memset before it
+            scratch[(size_t)s * 2 * C + c] = 0.0;
+            scratch[(size_t)s * 2 * C + C + c] = 0.0;
         }
         if (!f.bwd) {
-            const double pivot = (double)f.x[c];
+            const double pivot = f.x ? (double)f.x[c] : 0.0;
             const double m1 = a / (double)f.rows;                       // E[x - pivot]
             double var = b / (double)f.rows - m1 * m1;
             if (var < 0) var = 0;
@@ -85,6 +81,23 @@ __device__ __forceinline__ void bn_finalize_last_block(double *scratch, const Bn
             if (f.dgamma) f.dgamma[c] += (float)b;
         }
     }
+}
+
+// Call at the end of a reduce kernel, after this block's atomics: the last block to arrive
+// runs bn_finalize_channels.
+__device__ __forceinline__ void bn_finalize_last_block(double *scratch, const BnFinal &f) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned *ticket = reinterpret_cast<unsigned *>(scratch + 18 * (size_t)f.C);
+        is_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned *>(scratch + 18 * (size_t)f.C) = 0u;    // ticket back to rest
+    bn_finalize_channels(scratch, f);
 }
 
 }  // namespace sn

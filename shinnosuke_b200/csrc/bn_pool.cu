@@ -135,6 +135,91 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(const float *__
     bn_finalize_last_block(scratch, fin);
 }
 
+// The same two sums from the POOLED tensors alone.  Every winner of a window carries the pooled
+// value P = gamma*xhat + beta, and the routed shares of a window add up to its pooled gradient g, so
+//   sum(dy) = sum g          sum(dy * xhat) = sum g * (P - beta) / gamma
+// with no look at the full-resolution map (4x the bytes of P) or at the codes.  Channels whose gamma
+// is too small for that division to be accurate (|gamma| < max(1,|beta|)/16, including gamma == 0)
+// take the window route above, per thread.
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_pool_bwd_reduce_pooled_kernel(const float *__restrict__ dyp, const float *__restrict__ yp,
+                                                                        const uint32_t *__restrict__ code, const float *__restrict__ x,
+                                                                        const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                                        const float *__restrict__ mean, const float *__restrict__ invstd,
+                                                                        double *__restrict__ scratch, long long windows4, int C, int W,
+                                                                        int oh, int ow, BnFinal fin) {
+    const int Q = C >> 2;
+    const int cq = threadIdx.x % Q;
+    float mu[4], is[4], bt[4], rg[4];
+    bool fast = true;
+    {
+        const float4 a = ldg4(mean + cq * 4), b = ldg4(invstd + cq * 4), g = ldg4(gamma + cq * 4), be = ldg4(beta + cq * 4);
+        mu[0] = a.x; mu[1] = a.y; mu[2] = a.z; mu[3] = a.w; is[0] = b.x; is[1] = b.y; is[2] = b.z; is[3] = b.w;
+        bt[0] = be.x; bt[1] = be.y; bt[2] = be.z; bt[3] = be.w;
+        const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            fast = fast && fabsf(gg[k]) * 16.f >= fmaxf(1.f, fabsf(bt[k]));
+            rg[k] = 1.f / gg[k];
+        }
+    }
+    double da[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};
+    const long long stride = (long long)gridDim.x * 256;
+    long long idx = blockIdx.x * 256ll + threadIdx.x;
+    while (idx < windows4) {
+        float fa[4] = {0, 0, 0, 0}, fb[4] = {0, 0, 0, 0};
+        if (fast) {
+#pragma unroll 4
+            for (int it = 0; it < 32 && idx < windows4; ++it, idx += stride) {
+                const float4 g = ldg4(dyp + idx * 4), pv = ldg4(yp + idx * 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float gk = comp(g, k);
+                    fa[k] += gk;
+                    fb[k] = fmaf(gk, (comp(pv, k) - bt[k]) * rg[k], fb[k]);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int it = 0; it < 16 && idx < windows4; ++it, idx += stride) {
+                const Win w = window(x, idx, Q, ow, oh, W, C);
+                const float4 g = ldg4(dyp + idx * 4);
+                const uint32_t packed = __ldg(code + idx);
+                float4 v[4];
+                v[0] = ldg4(w.p00); v[1] = ldg4(w.p00 + C); v[2] = ldg4(w.p00 + w.rowstride); v[3] = ldg4(w.p00 + w.rowstride + C);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t cd = (packed >> (8 * k)) & 0xffu;
+                    const float gk = comp(g, k);
+                    fa[k] += gk;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float r = routed<MODE>(gk, cd, e);
+                        fb[k] = fmaf(r, (comp(v[e], k) - mu[k]) * is[k], fb[k]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { da[k] += (double)fa[k]; db[k] += (double)fb[k]; }
+    }
+    __shared__ double sa[256][4], sb[256][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sa[threadIdx.x][k] = da[k]; sb[threadIdx.x][k] = db[k]; }
+    __syncthreads();
+    if (threadIdx.x < Q) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double ta = 0, tb = 0;
+            for (int t = threadIdx.x; t < 256; t += Q) { ta += sa[t][k]; tb += sb[t][k]; }
+            double *slot = scratch + (size_t)(blockIdx.x % BN_SLOTS) * 2 * C;
+            atomicAdd(slot + cq * 4 + k, ta);
+            atomicAdd(slot + C + cq * 4 + k, tb);
+        }
+    }
+    bn_finalize_last_block(scratch, fin);
+}
+
 template <int MODE, bool MASK>
 __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__restrict__ dyp, const uint32_t *__restrict__ code,
                                                                 const float *__restrict__ x, float *__restrict__ dx,
@@ -197,11 +282,20 @@ int sn_bn_pool_fwd_train(const float *x, const float *gamma, const float *beta, 
     SN_REQUIRE(shape_ok(N, H, W, C), "unsupported shape (needs even H, W and C = 4*2^k <= 1024)");
     SN_REQUIRE(pool_mode == SN_POOL_TIE_SPLIT || pool_mode == SN_POOL_FIRST_ARGMAX, "unknown pool mode");
     SN_REQUIRE(((((uintptr_t)x) | ((uintptr_t)y_pool)) & 15) == 0 && (((uintptr_t)code) & 3) == 0, "misaligned tensor");
-    cudaStream_t st = as_stream(stream);
     const long long rows = (long long)N * H * W;
     // pass 1: per-channel statistics of x (the plain BatchNorm reduction, scratch zeroed inside)
     int e = sn_batchnorm_stats(x, gamma, beta, save_mean, save_invstd, moving_mean, moving_var, scratch, rows, C, eps, momentum, stream);
     if (e) return e;
+    return sn_bn_pool_fwd_apply(x, y_pool, code, scratch, N, H, W, C, pool_mode, stream);
+}
+
+int sn_bn_pool_fwd_apply(const float *x, float *y_pool, uint8_t *code, const double *scratch, int N, int H, int W, int C,
+                         int pool_mode, void *stream) {
+    SN_REQUIRE(x && y_pool && code && scratch, "null tensor");
+    SN_REQUIRE(shape_ok(N, H, W, C), "unsupported shape (needs even H, W and C = 4*2^k <= 1024)");
+    SN_REQUIRE(pool_mode == SN_POOL_TIE_SPLIT || pool_mode == SN_POOL_FIRST_ARGMAX, "unknown pool mode");
+    SN_REQUIRE(((((uintptr_t)x) | ((uintptr_t)y_pool)) & 15) == 0 && (((uintptr_t)code) & 3) == 0, "misaligned tensor");
+    cudaStream_t st = as_stream(stream);
     const int oh = H / 2, ow = W / 2;
     const long long windows4 = (long long)N * oh * ow * (C / 4);
     const int grid = grid_for_windows(windows4);
@@ -212,9 +306,9 @@ int sn_bn_pool_fwd_train(const float *x, const float *gamma, const float *beta, 
     return after_launch("bn_pool_fwd_kernel");
 }
 
-int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, const float *gamma, const float *save_mean,
-                   const float *save_invstd, float *dx, float *dgamma, float *dbeta, double *scratch, int N, int H, int W,
-                   int C, int pool_mode, int mask_relu, void *stream) {
+int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, const float *y_pool, const float *gamma,
+                   const float *beta, const float *save_mean, const float *save_invstd, float *dx, float *dgamma, float *dbeta,
+                   double *scratch, int N, int H, int W, int C, int pool_mode, int mask_relu, void *stream) {
     SN_REQUIRE(dy_pool && code && x && gamma && save_mean && save_invstd && dx && scratch, "null tensor");
     SN_REQUIRE(shape_ok(N, H, W, C), "unsupported shape (needs even H, W and C = 4*2^k <= 1024)");
     SN_REQUIRE(pool_mode == SN_POOL_TIE_SPLIT || pool_mode == SN_POOL_FIRST_ARGMAX, "unknown pool mode");
@@ -230,7 +324,13 @@ int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, co
     BnFinal fin{};
     fin.bwd = 1; fin.rows = rows; fin.C = C; fin.gamma = gamma; fin.mean = save_mean; fin.invstd = save_invstd;
     fin.dgamma = dgamma; fin.dbeta = dbeta;
-    if (pool_mode == SN_POOL_TIE_SPLIT)
+    if (y_pool && beta) {
+        SN_REQUIRE((((uintptr_t)y_pool) & 15) == 0, "misaligned tensor");
+        if (pool_mode == SN_POOL_TIE_SPLIT)
+            bn_pool_bwd_reduce_pooled_kernel<SN_POOL_TIE_SPLIT><<<rgrid, 256, 0, st>>>(dy_pool, y_pool, cd, x, gamma, beta, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
+        else
+            bn_pool_bwd_reduce_pooled_kernel<SN_POOL_FIRST_ARGMAX><<<rgrid, 256, 0, st>>>(dy_pool, y_pool, cd, x, gamma, beta, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
+    } else if (pool_mode == SN_POOL_TIE_SPLIT)
         bn_pool_bwd_reduce_kernel<SN_POOL_TIE_SPLIT><<<rgrid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
     else
         bn_pool_bwd_reduce_kernel<SN_POOL_FIRST_ARGMAX><<<rgrid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);

@@ -9,7 +9,7 @@ int conv_wgrad_simt(const float *, const float *, float *, float *, int, int, in
 bool conv_tc_eligible(int N, int C, int OH, int OW, int F, int stride, bool bf16 = false);
 bool wgrad_tc_eligible(int N, int C, int OH, int OW, int F, int stride);
 int conv_igemm_tc(const void *x, const void *w, const float *bias, float *out, int N, int C, int IH, int IW, int F, int kh,
-                  int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, bool bf16, cudaStream_t st);
+                  int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, bool bf16, double *stats, cudaStream_t st);
 int flip_transpose_filters_bf16(const float *w, void *wt, int F, int C, int kh, int kw, cudaStream_t st);
 int cast_f32_to_bf16(const float *src, void *dst, long long n, cudaStream_t st);
 int conv_wgrad_tc(const float *x, const float *dy, float *dw, int N, int C, int IH, int IW, int F, int kh, int kw, int OH,
@@ -21,7 +21,7 @@ int conv_wgrad_halo_tc(const void *x, const void *dy, float *dw, int N, int C, i
 int colsum_accumulate(const float *dy, float *db, long long rows, int F, cudaStream_t st);
 bool stem_tc_eligible(int N, int C, int OH, int OW, int F, int kh, int kw);
 int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
-                       int kw, int stride, int ph, int pw, int act, cudaStream_t st);
+                       int kw, int stride, int ph, int pw, int act, double *stats, cudaStream_t st);
 int conv_stem_wgrad_tc(const float *x, const float *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh, int kw,
                        int stride, int ph, int pw, cudaStream_t st);
 bool direct_fprop_eligible(int C, int kh, int kw, int F);
@@ -40,10 +40,11 @@ static int check_prec(int precision) {
     return SN_OK;
 }
 
-extern "C" {
+// Which forward kernels can also produce the BatchNorm sums of their output (TMA-store epilogues)
+static bool igemm_stats_ok(int F) { return F > 16 && F <= 512 && (F & 3) == 0; }
 
-int sn_conv2d_fprop(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F,
-                    int kh, int kw, int stride, int pad_h, int pad_w, int act, int precision, void *stream) {
+static int fprop_impl(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F,
+                      int kh, int kw, int stride, int pad_h, int pad_w, int act, int precision, double *stats, void *stream) {
     SN_REQUIRE(x && w && y, "null tensor");
     SN_REQUIRE(act == SN_ACT_LINEAR || act == SN_ACT_RELU, "unknown activation");
     int e = check_prec(precision);
@@ -52,15 +53,43 @@ int sn_conv2d_fprop(const float *x, const float *w, const float *bias, float *y,
                          H + 2 * pad_h >= kh && W + 2 * pad_w >= kw;
     if (geom_ok && precision != SN_PREC_FP32 && (((uintptr_t)y | (uintptr_t)bias) & 15) == 0 &&
         stem_tc_eligible(N, C, (H + 2 * pad_h - kh) / stride + 1, (W + 2 * pad_w - kw) / stride + 1, F, kh, kw))
-        return conv_stem_fprop_tc(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, as_stream(stream));
-    if (geom_ok && (((uintptr_t)y) & 15) == 0 && direct_fprop_eligible(C, kh, kw, F))
+        return conv_stem_fprop_tc(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, stats, as_stream(stream));
+    if (!stats && geom_ok && (((uintptr_t)y) & 15) == 0 && direct_fprop_eligible(C, kh, kw, F))
         return conv_fprop_direct(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, as_stream(stream));
     if (geom_ok && precision != SN_PREC_FP32) {
         const int oh = (H + 2 * pad_h - kh) / stride + 1, ow = (W + 2 * pad_w - kw) / stride + 1;
         if (conv_tc_eligible(N, C, oh, ow, F, stride))
-            return conv_igemm_tc(x, w, bias, y, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, act, 0, false, as_stream(stream));
+            return conv_igemm_tc(x, w, bias, y, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, act, 0, false, stats, as_stream(stream));
     }
+    SN_REQUIRE(!stats, "no BatchNorm statistics from this kernel family (ask sn_conv2d_fprop_stats_supported first)");
     return conv_fprop_simt(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, as_stream(stream));
+}
+
+extern "C" {
+
+int sn_conv2d_fprop(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F,
+                    int kh, int kw, int stride, int pad_h, int pad_w, int act, int precision, void *stream) {
+    return fprop_impl(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, precision, nullptr, stream);
+}
+
+int sn_conv2d_fprop_stats(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F,
+                          int kh, int kw, int stride, int pad_h, int pad_w, int act, int precision, double *bn_scratch,
+                          void *stream) {
+    SN_REQUIRE(bn_scratch, "null statistics buffer");
+    return fprop_impl(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, precision, bn_scratch, stream);
+}
+
+int sn_conv2d_fprop_stats_supported(int precision, int bf16_operands, int N, int C, int H, int W, int F, int kh, int kw,
+                                    int stride, int pad_h, int pad_w) {
+    if (N <= 0 || C <= 0 || F <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad_h < 0 || pad_w < 0 || H + 2 * pad_h < kh ||
+        W + 2 * pad_w < kw)
+        return 0;
+    if (bf16_operands) return (sn_conv2d_bf16_supported(0, N, C, H, W, F, kh, kw, stride, pad_h, pad_w) && igemm_stats_ok(F)) ? 1 : 0;
+    if (precision != SN_PREC_TF32 && precision != SN_PREC_BF16) return 0;
+    const int oh = (H + 2 * pad_h - kh) / stride + 1, ow = (W + 2 * pad_w - kw) / stride + 1;
+    if (stem_tc_eligible(N, C, oh, ow, F, kh, kw)) return 1;
+    if (direct_fprop_eligible(C, kh, kw, F)) return 0;
+    return (conv_tc_eligible(N, C, oh, ow, F, stride) && igemm_stats_ok(F)) ? 1 : 0;
 }
 
 size_t sn_conv2d_dgrad_workspace(int C, int F, int kh, int kw, int precision) {
@@ -81,7 +110,7 @@ int sn_conv2d_dgrad(const float *dy, const float *w, float *dx, int N, int C, in
             e = flip_transpose_filters(w, (float *)workspace, F, C, kh, kw, as_stream(stream));
             if (e) return e;
             return conv_igemm_tc(dy, (const float *)workspace, nullptr, dx, N, F, oh, ow, C, kh, kw, H, W, kh - 1 - pad_h,
-                                 kw - 1 - pad_w, SN_ACT_LINEAR, accumulate, false, as_stream(stream));
+                                 kw - 1 - pad_w, SN_ACT_LINEAR, accumulate, false, nullptr, as_stream(stream));
         }
     }
     return conv_dgrad_simt(dy, w, dx, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, accumulate, as_stream(stream));
@@ -159,7 +188,16 @@ int sn_conv2d_fprop_bf16(const void *x, const void *w, const float *bias, float 
     SN_REQUIRE(sn_conv2d_bf16_supported(0, N, C, H, W, F, kh, kw, stride, pad_h, pad_w), "shape not supported by the bf16 kernels");
     int oh, ow;
     bf16_geom(N, C, H, W, F, kh, kw, stride, pad_h, pad_w, oh, ow);
-    return conv_igemm_tc(x, w, bias, y, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, act, 0, true, as_stream(stream));
+    return conv_igemm_tc(x, w, bias, y, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, act, 0, true, nullptr, as_stream(stream));
+}
+int sn_conv2d_fprop_bf16_stats(const void *x, const void *w, const float *bias, float *y, int N, int C, int H, int W, int F,
+                               int kh, int kw, int stride, int pad_h, int pad_w, int act, double *bn_scratch, void *stream) {
+    SN_REQUIRE(x && w && y && bn_scratch, "null tensor");
+    SN_REQUIRE(sn_conv2d_fprop_stats_supported(SN_PREC_BF16, 1, N, C, H, W, F, kh, kw, stride, pad_h, pad_w),
+               "shape not supported by the bf16 kernels with statistics");
+    int oh, ow;
+    bf16_geom(N, C, H, W, F, kh, kw, stride, pad_h, pad_w, oh, ow);
+    return conv_igemm_tc(x, w, bias, y, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, act, 0, true, bn_scratch, as_stream(stream));
 }
 int sn_conv2d_dgrad_bf16(const void *dy, const void *wt, float *dx, int N, int C, int H, int W, int F, int kh, int kw, int stride,
                          int pad_h, int pad_w, int accumulate, void *stream) {
@@ -168,7 +206,7 @@ int sn_conv2d_dgrad_bf16(const void *dy, const void *wt, float *dx, int N, int C
     int oh, ow;
     bf16_geom(N, C, H, W, F, kh, kw, stride, pad_h, pad_w, oh, ow);
     return conv_igemm_tc(dy, wt, nullptr, dx, N, F, oh, ow, C, kh, kw, H, W, kh - 1 - pad_h, kw - 1 - pad_w, SN_ACT_LINEAR,
-                         accumulate, true, as_stream(stream));
+                         accumulate, true, nullptr, as_stream(stream));
 }
 int sn_conv2d_wgrad_bf16(const void *x, const void *dy, const float *dy_f32, float *dw, float *db, int N, int C, int H, int W,
                          int F, int kh, int kw, int stride, int pad_h, int pad_w, void *stream) {

@@ -13,6 +13,7 @@
 //           is the constant 1, so D[f][K] = sum_p dY[p][f] is the bias gradient for free.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "bn_common.cuh"
 
 using namespace sn;
 using namespace sn::tc;
@@ -28,6 +29,7 @@ struct StemP {
     int act;
     int tiles;    // fprop: ceil(P/128); wgrad: ceil(P/64)
     int tiles_per_cta;   // wgrad
+    double *stats;       // fprop: optional BatchNorm sums of the output, stats[slot][{sum, sumsq}][F] (see conv_tc.cu)
 };
 
 // A builder thread owns 8 consecutive k's of one pixel row; their tap offsets are loop invariant.
@@ -83,7 +85,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
     uint8_t *sB = smem;                                   // [BN][128 B], SW128 K-major
     uint8_t *sA = smem + BN * 128;                        // SF_ABUF x [128][128 B]
     uint8_t *epi_stage = sA + SF_ABUF * SF_A_BYTES;       // per epilogue warp: 2 x (32 rows x 128 B) staging tiles for TMA stores
-    uint64_t *a_full = reinterpret_cast<uint64_t *>(epi_stage + 2 * SF_EPI_WARPS * 4096);
+    float *sstat = reinterpret_cast<float *>(epi_stage + 2 * SF_EPI_WARPS * 4096);        // [2][BN] per-CTA column sums
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(sstat + 2 * BN);
     uint64_t *a_empty = a_full + SF_ABUF;
     uint64_t *t_full = a_empty + SF_ABUF;
     uint64_t *t_empty = t_full + 2;
@@ -104,6 +107,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
         fence_barrier_init();
     }
     if (warp == 0) { tmem_alloc(tmem_ptr, 2 * BN < 32 ? 32 : 2 * BN); tmem_relinquish(); }
+    for (int i = threadIdx.x; i < 2 * BN; i += SF_THREADS) sstat[i] = 0.f;
     fence_proxy_async();            // the weight tile was written through the generic proxy
     tc_fence_before();
     __syncthreads();
@@ -190,6 +194,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
                 __syncwarp();
                 // one TMA store per 32 x 32 sub-tile: full 128-byte lines, clipped at the tensor bounds
                 if (lane == 0) { tma_store_2d(&tmO, st, c0, tile * 128 + q * 32); tma_store_commit(); }
+                if (p.stats) staged_tile_colsums(st, lane, p.P - (tile * 128 + q * 32), sstat + c0, sstat + BN + c0, p.F - c0);
             }
             tc_fence_before();
             __syncwarp();
@@ -200,6 +205,13 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
     tc_fence_before();
     __syncthreads();
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN < 32 ? 32 : 2 * BN); }
+    if (p.stats) {
+        double *slot = p.stats + (size_t)(blockIdx.x % BN_SLOTS) * 2 * p.F;
+        for (int f = threadIdx.x; f < p.F; f += SF_THREADS) {
+            atomicAdd(slot + f, (double)sstat[f]);
+            atomicAdd(slot + p.F + f, (double)sstat[BN + f]);
+        }
+    }
 }
 
 // ============================================================================== wgrad
@@ -331,7 +343,7 @@ void fill_geom(StemP &p, int N, int C, int H, int W, int F, int kh, int kw, int 
 
 template <int BN>
 int launch_stem_fprop(const StemP &p, cudaStream_t st) {
-    const int smem = BN * 128 + SF_ABUF * SF_A_BYTES + 2 * SF_EPI_WARPS * 4096 + 1024 + 256;
+    const int smem = BN * 128 + SF_ABUF * SF_A_BYTES + 2 * SF_EPI_WARPS * 4096 + 2 * BN * 4 + 1024 + 256;
     CUtensorMap tmO;
     long long odims[2] = {p.F, p.P};
     long long ostr[2] = {1, p.F};
@@ -359,10 +371,11 @@ bool stem_tc_eligible(int N, int C, int OH, int OW, int F, int kh, int kw) {
 }
 
 int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
-                       int kw, int stride, int ph, int pw, int act, cudaStream_t st) {
+                       int kw, int stride, int ph, int pw, int act, double *stats, cudaStream_t st) {
     StemP p{};
     fill_geom(p, N, C, H, W, F, kh, kw, stride, ph, pw);
     p.x = x; p.w = w; p.bias = bias; p.y = y; p.act = act;
+    p.stats = stats;              // zero on entry (caller's contract): no memset node in the step graph
     p.tiles = (p.P + 127) / 128;
     if (F <= 32) return launch_stem_fprop<32>(p, st);
     if (F <= 64) return launch_stem_fprop<64>(p, st);

@@ -22,6 +22,7 @@
 //   Split over pixel ranges across CTAs (the output is tiny), fp32 red.global.add epilogue.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "bn_common.cuh"
 #include <cuda_bf16.h>
 #include <mutex>
 
@@ -94,7 +95,16 @@ struct IgemmParams {
     int pad_h, pad_w;
     int act, accumulate;
     int tma_store;         // epilogue stages 32x32 sub-tiles in smem and writes them with TMA stores
+    double *stats;         // optional: per-channel sums of the output and of its square (BatchNorm statistics), see below
 };
+
+// BatchNorm statistics in the epilogue: the BatchNormalization that consumes a convolution needs
+// sum(y) and sum(y^2) per channel, which would otherwise cost a full re-read of y.  Each epilogue
+// warp column-sums its 32x32 staging tile out of shared memory (lane = column; the swizzle makes
+// the row-wise reads conflict-free), accumulates into a per-CTA fp32 table, and the CTA adds its
+// table to stats[slot][{sum, sumsq}][F] (float64, slot = blockIdx.x % BN_SLOTS) once at the end.
+constexpr int STAT_MAX_F = 512;
+constexpr int STAT_BYTES = 2 * STAT_MAX_F * 4;
 
 constexpr int EPI_STAGE_BYTES = 4 * 4096;       // one 32-row x 128-byte staging tile per epilogue warp
 
@@ -107,7 +117,7 @@ template <int BN, int KS> struct IgemmCfg {
     static constexpr int STAGE_BYTES = KS * SLAB_BYTES;
     static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;      // power of two >= 32
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + STAT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // BF16: the operands are bf16 copies (64 elements per 128-byte row, UMMA K = 16, kind::f16); the
@@ -120,7 +130,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *epi_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                 // 1024-byte aligned (stage sizes are)
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi_stage + EPI_STAGE_BYTES);
+    float *sstat = reinterpret_cast<float *>(epi_stage + EPI_STAGE_BYTES);      // [2][STAT_MAX_F]
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi_stage + EPI_STAGE_BYTES + STAT_BYTES);
     uint64_t *empty_bar = full_bar + Cfg::STAGES;
     uint64_t *tmem_full = empty_bar + Cfg::STAGES;
     uint64_t *tmem_empty = tmem_full + 2;
@@ -144,6 +155,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
         tmem_relinquish();
     }
+    if (p.stats)
+        for (int i = threadIdx.x; i < 2 * STAT_MAX_F; i += NUM_THREADS) sstat[i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -259,6 +272,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) { tma_store_2d(&tmO, st, f0, tm * BM + q * 32); tma_store_commit(); }
+                        if (p.stats)
+                            staged_tile_colsums(st, lane, p.rows - (tm * BM + q * 32), sstat + f0, sstat + STAT_MAX_F + f0, p.F - f0);
                         continue;
                     }
                 }
@@ -299,6 +314,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
         if (p.tma_store && lane == 0) tma_store_wait_all();
+        __syncwarp();
+        if (p.stats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");           // the four epilogue warps only
+            double *slot = p.stats + (size_t)(blockIdx.x % BN_SLOTS) * 2 * p.F;
+            for (int f = threadIdx.x - 64; f < p.F; f += 128) {
+                atomicAdd(slot + f, (double)sstat[f]);
+                atomicAdd(slot + p.F + f, (double)sstat[STAT_MAX_F + f]);
+            }
+        }
     }
 
     tc_fence_before();
@@ -579,7 +603,7 @@ bool conv_tc_eligible(int N, int C, int OH, int OW, int F, int stride, bool bf16
 
 // x: NHWC (N, IH, IW, C); w: [F][kh*kw][C]; out: (N*OH*OW, F).
 int conv_igemm_tc(const void *x, const void *w, const float *bias, float *out, int N, int C, int IH, int IW, int F, int kh,
-                  int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, bool bf16, cudaStream_t st) {
+                  int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, bool bf16, double *stats, cudaStream_t st) {
     TileGeom g;
     if (!tile_geometry(N, OH, OW, g)) { set_error("conv_igemm_tc: unsupported output geometry %dx%d", OH, OW); return SN_ERR_UNSUPPORTED; }
     if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)out) & 15) { set_error("conv_igemm_tc: tensors must be 16-byte aligned"); return SN_ERR_INVALID_ARG; }
@@ -614,6 +638,10 @@ int conv_igemm_tc(const void *x, const void *w, const float *bias, float *out, i
         int obox[2] = {32, 32};
         e = make_tmap_f32(&tmO, out, 2, odims, ostr, obox);
         if (e) return e;
+    }
+    if (stats) {
+        if (!p.tma_store || F > STAT_MAX_F) { set_error("conv_igemm_tc: no BatchNorm statistics for this shape (F = %d)", F); return SN_ERR_UNSUPPORTED; }
+        p.stats = stats;          // zero on entry (caller's contract): no memset node in the step graph
     }
     switch (BN) {
         case 16: return launch_igemm<16>(tmA, tmB, tmO, p, bf16, st);

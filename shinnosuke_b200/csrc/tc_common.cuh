@@ -190,4 +190,45 @@ int make_tmap_f32(CUtensorMap *out, const void *base, int rank, const long long 
 int make_tmap(CUtensorMap *out, const void *base, int rank, const long long *dims, const long long *strides_elems,
               const int *box, bool atom32b, bool bf16);
 
+
+// Column sums of one epilogue staging tile: 32 rows x 32 fp32 columns in the 128-byte-swizzled
+// layout the TMA store reads (16-byte chunk j of row r at (j ^ (r & 7)) * 16).  Lane l takes the
+// column pair 2*(l & 15) of rows 16*(l >> 4) .. +15 with 8-byte loads (each half warp reads one
+// whole row: conflict-free) and packed f32x2 adds / fmas, one shuffle joins the two row halves,
+// and lanes 0..15 add {sum, sum of squares} of their two columns to the per-CTA tables in shared
+// memory.  nvalid (< 32 only in the last pixel tile) masks rows past the end of the tensor.
+__device__ __forceinline__ void staged_tile_colsums(const uint8_t *st, int lane, int nvalid, float *ssum, float *ssq, int ncols) {
+    const int cp = lane & 15, r0 = (lane >> 4) * 16;
+    const uint8_t *base = st + (cp & 1) * 8;
+    const int chunk = cp >> 1;
+    float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+    if (nvalid >= 32) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int r = r0 + i;
+            const float2 v = *reinterpret_cast<const float2 *>(base + r * 128 + ((chunk ^ (r & 7)) * 16));
+            a = __fadd2_rn(a, v);
+            b = __ffma2_rn(v, v, b);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int r = r0 + i;
+            float2 v = *reinterpret_cast<const float2 *>(base + r * 128 + ((chunk ^ (r & 7)) * 16));
+            if (r >= nvalid) v = make_float2(0.f, 0.f);
+            a = __fadd2_rn(a, v);
+            b = __ffma2_rn(v, v, b);
+        }
+    }
+    a.x += __shfl_down_sync(0xffffffffu, a.x, 16);
+    a.y += __shfl_down_sync(0xffffffffu, a.y, 16);
+    b.x += __shfl_down_sync(0xffffffffu, b.x, 16);
+    b.y += __shfl_down_sync(0xffffffffu, b.y, 16);
+    if (lane < 16) {
+        const int c = 2 * cp;
+        if (c < ncols) { atomicAdd(ssum + c, a.x); atomicAdd(ssq + c, b.x); }
+        if (c + 1 < ncols) { atomicAdd(ssum + c + 1, a.y); atomicAdd(ssq + c + 1, b.y); }
+    }
+}
+
 }  // namespace sn

@@ -91,18 +91,44 @@ class Conv2D(Layer):
         geom = (N, C, H, Wd, F, kh, kw, self.stride, self.pad_size[0], self.pad_size[1])
         st = current_stream()
         self._xb = None
-        if self.precision == 'bf16' and self._bf16_ok(0, geom):
+        bf16 = self.precision == 'bf16' and self._bf16_ok(0, geom)
+        # the BatchNormalization fed by this layer alone takes its batch statistics from our epilogue
+        bn = getattr(self, '_stats_to', None) if is_training else None
+        scratch = None
+        if bn is not None and self._stats_ok(bf16, geom):
+            scratch = bn._device_stats(F)['scratch'].data_ptr()
+            bn._stats_from = self
+        elif bn is not None:
+            bn._stats_from = None
+        if bf16:
             # bf16 tier: bf16 copies of the input map and the filters, fp32 accumulation and output
             self._xb = self._bf16_buf('x_bf16', x.size)
             wb = self._bf16_buf('w_bf16', W.size)
             lib.sn_cast_f32_to_bf16(x.ptr, self._xb.data_ptr(), x.size, st)
             lib.sn_cast_f32_to_bf16(W.output_tensor.ptr, wb.data_ptr(), W.size, st)
-            lib.sn_conv2d_fprop_bf16(self._xb.data_ptr(), wb.data_ptr(), b.output_tensor.ptr, y.ptr, *geom, self._act_code(), st)
+            if scratch:
+                lib.sn_conv2d_fprop_bf16_stats(self._xb.data_ptr(), wb.data_ptr(), b.output_tensor.ptr, y.ptr, *geom,
+                                               self._act_code(), scratch, st)
+            else:
+                lib.sn_conv2d_fprop_bf16(self._xb.data_ptr(), wb.data_ptr(), b.output_tensor.ptr, y.ptr, *geom,
+                                         self._act_code(), st)
+        elif scratch:
+            lib.sn_conv2d_fprop_stats(x.ptr, W.output_tensor.ptr, b.output_tensor.ptr, y.ptr, *geom, self._act_code(),
+                                      PRECISION[self.precision], scratch, st)
         else:
             lib.sn_conv2d_fprop(x.ptr, W.output_tensor.ptr, b.output_tensor.ptr, y.ptr, *geom, self._act_code(),
                                 PRECISION[self.precision], st)
         self.output_tensor = y
         super(Conv2D, self).forward(is_training)
+
+    def _stats_ok(self, bf16, geom):
+        key = ('stats', bool(bf16)) + tuple(geom)
+        cache = self.__dict__.setdefault('_bf16_support', {})
+        if key not in cache:
+            F = geom[4]
+            pow2 = F % 4 == 0 and (F // 4) & (F // 4 - 1) == 0 and F <= 1024     # what the BN apply kernels take
+            cache[key] = bool(pow2 and lib.load().sn_conv2d_fprop_stats_supported(PRECISION[self.precision], int(bf16), *geom))
+        return cache[key]
 
     def _bf16_ok(self, op, geom):
         key = (op,) + tuple(geom)

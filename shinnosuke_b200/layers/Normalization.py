@@ -67,6 +67,10 @@ class BatchNormalization(Layer):
         s = self._device_stats(C)
         st = current_stream()
         pool = self._fuse_with_pool
+        # the producing convolution already left sum(x), sum(x^2) in our scratch (its epilogue): no reduce pass
+        prestats = bool(is_training and getattr(self, '_stats_from', None) is not None
+                        and self._stats_from is self.inbounds[0])
+        self._stats_from = None
         self._fused_active = bool(is_training and pool is not None and x.ndim == 4 and
                                   lib.load().sn_bn_pool_supported(x.shape[0], x.shape[2], x.shape[3], C))
         if self._fused_active:
@@ -74,9 +78,16 @@ class BatchNormalization(Layer):
             # so this layer has no output_tensor of its own in this mode (compile(..., fuse=False) keeps it).
             N, _, H, W = x.shape
             yp, code = pool._fused_buffers(N, C, H, W)
-            lib.sn_bn_pool_fwd_train(x.ptr, gamma.output_tensor.ptr, beta.output_tensor.ptr, yp.ptr, code.data_ptr(),
-                                     s['mean'].ptr, s['invstd'].ptr, s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(),
-                                     N, H, W, C, float(self.epsilon), float(self.momentum), POOL_MODE[pool.mode], st)
+            if prestats:
+                lib.sn_batchnorm_finalize_stats(gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
+                                                s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows, C,
+                                                float(self.epsilon), float(self.momentum), st)
+                lib.sn_bn_pool_fwd_apply(x.ptr, yp.ptr, code.data_ptr(), s['scratch'].data_ptr(), N, H, W, C,
+                                         POOL_MODE[pool.mode], st)
+            else:
+                lib.sn_bn_pool_fwd_train(x.ptr, gamma.output_tensor.ptr, beta.output_tensor.ptr, yp.ptr, code.data_ptr(),
+                                         s['mean'].ptr, s['invstd'].ptr, s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(),
+                                         N, H, W, C, float(self.epsilon), float(self.momentum), POOL_MODE[pool.mode], st)
             pool._fused_output = yp
             pool.input_tensor = None
             self.output_tensor = None
@@ -84,7 +95,12 @@ class BatchNormalization(Layer):
             self._grads_premasked = False
             return
         y = self._buf('out', x.shape, x.layout)
-        if is_training:
+        if is_training and prestats:
+            lib.sn_batchnorm_finalize_stats(gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
+                                            s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows, C,
+                                            float(self.epsilon), float(self.momentum), st)
+            lib.sn_batchnorm_fwd_apply(x.ptr, y.ptr, s['scratch'].data_ptr(), rows, C, st)
+        elif is_training:
             lib.sn_batchnorm_fwd_train(x.ptr, gamma.output_tensor.ptr, beta.output_tensor.ptr, y.ptr, s['mean'].ptr,
                                        s['invstd'].ptr, s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows, C,
                                        float(self.epsilon), float(self.momentum), st)
@@ -112,7 +128,8 @@ class BatchNormalization(Layer):
 
                 def fused_writer(dst, acc, fuse=fuse):
                     out = self._buf('dx_tmp', x.shape, x.layout) if acc else dst
-                    lib.sn_bn_pool_bwd(pool.grads.ptr, pool._code.data_ptr(), x.ptr, gamma.output_tensor.ptr, s['mean'].ptr,
+                    lib.sn_bn_pool_bwd(pool.grads.ptr, pool._code.data_ptr(), x.ptr, pool.output_tensor.ptr,
+                                       gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr,
                                        s['invstd'].ptr, out.ptr, gamma.grads.ptr if gamma.require_grads else None,
                                        beta.grads.ptr if beta.require_grads else None, s['scratch'].data_ptr(),
                                        N, H, W, C, POOL_MODE[pool._code_mode], 1 if fuse else 0, st)

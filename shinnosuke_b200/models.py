@@ -80,7 +80,7 @@ class _Trainer(object):
             raise ValueError('precision must be one of %s' % sorted(PRECISION))
         self.precision = precision
         from .layers.Normalization import BatchNormalization
-        from .layers.Convolution import MaxPooling2D
+        from .layers.Convolution import MaxPooling2D, Conv2D
         for layer in self._forward_order():
             layer.precision = precision
             if isinstance(layer, BatchNormalization):
@@ -89,6 +89,13 @@ class _Trainer(object):
                 ok = (fuse and isinstance(nxt, MaxPooling2D) and tuple(nxt.pool_size) == (2, 2) and nxt.stride == 2
                       and len(nxt.inbounds) == 1)
                 layer._fuse_with_pool = nxt if ok else None
+                # Conv2D -> BatchNormalization with no other consumer: the tensor-core convolution
+                # epilogues reduce the batch statistics, so the BN skips its own pass over the map
+                prev = layer.inbounds[0] if len(layer.inbounds) == 1 else None
+                layer._stats_from = None
+                if isinstance(prev, Conv2D):
+                    feeds = fuse and precision != 'fp32' and len(prev.outbound_layers) == 1
+                    prev._stats_to = layer if feeds else None
         self.loss = get_objective(loss)
         self.optimizer = get_optimizer(optimizer)
 

@@ -209,3 +209,82 @@ def test_trajectory_cfg3_bf16():
     m.fit(X, Y, batch_size=16, epochs=1, shuffle=False, validation_ratio=0., verbose=0)
     assert abs(m.train_loss[0] - net.train_loss[0]) < 2e-2 * net.train_loss[0]     # forward only
     assert np.isfinite(m.train_loss).all()
+
+
+# ------------------------------------------------------------------ BatchNorm statistics from the conv epilogue
+def _conv_bn_pair(shape, precision, with_pool):
+    """Conv2D -> BatchNormalization (-> MaxPooling2D) driven through the layers, once with the conv
+    epilogue reducing the batch statistics and once with the BN's own reduce pass."""
+    from shinnosuke_b200 import Conv2D, Input, Activation, BatchNormalization, MaxPooling2D
+    from shinnosuke_b200.device import as_device
+    N, C, H, W, F, k, padding, act = shape
+    r = np.random.default_rng(sum((i + 1) * v for i, v in enumerate(shape[:6])))
+    x = r.standard_normal((N, C, H, W)).astype(np.float32).astype(np.float64)
+    w = (0.2 * r.standard_normal((F, C, k, k))).astype(np.float32).astype(np.float64)
+    b = r.standard_normal((1, F)).astype(np.float32).astype(np.float64)
+    gamma = (1 + 0.3 * r.standard_normal(F)).astype(np.float32).astype(np.float64)
+    beta = r.standard_normal(F).astype(np.float32).astype(np.float64)
+    out = {}
+    for mode in ('epilogue', 'own'):
+        inp = Input((None, C, H, W)); src = Activation('linear')(inp)
+        conv = Conv2D(F, (k, k), padding=padding, activation=act)(src)
+        bn = BatchNormalization()(conv)
+        layers = [inp, src, conv, bn]
+        if with_pool:
+            pool = MaxPooling2D((2, 2))(bn)
+            bn._fuse_with_pool = pool
+            layers.append(pool)
+        for l in layers:
+            l.precision = precision
+        conv._stats_to = bn if mode == 'epilogue' else None
+        set_params(conv, w, b)
+        set_params(bn, gamma, beta)
+        inp.input_tensor = x
+        for l in layers:
+            l.forward(True)
+        last = layers[-1]
+        y = np.asarray(last.output_tensor)
+        g = r.standard_normal(y.shape) if mode == 'epilogue' else out['epilogue']['g']
+        last._seed_grads(as_device(g))
+        for l in reversed(layers[2:]):
+            l.backward()
+        out[mode] = dict(g=g, y=y, conv_y=np.asarray(conv.output_tensor), mean=bn._stats['mean'].numpy(),
+                         invstd=bn._stats['invstd'].numpy(), mm=bn.moving_mean, mv=bn.moving_variance,
+                         dgamma=np.asarray(bn.variables[0].grads), dz=np.asarray(conv.grads), dx=np.asarray(src.grads),
+                         used=(mode == 'epilogue' and conv._stats_ok(conv._xb is not None,
+                                                                     (N, C, H, W, F, k, k, 1) + tuple(conv.pad_size))))
+    return out
+
+
+@pytest.mark.parametrize('precision', ['tf32', 'bf16'])
+@pytest.mark.parametrize('with_pool', [True, False])
+@pytest.mark.parametrize('shape', [
+    (8, 3, 32, 32, 64, 3, 'SAME', 'relu'),        # stem kernel epilogue
+    (6, 3, 30, 30, 32, 3, 'VALID', 'linear'),     # stem, ragged last pixel tile (6*28*28 = 4704 rows)
+    (4, 64, 16, 16, 128, 3, 'SAME', 'relu'),      # implicit-GEMM epilogue
+    (19, 32, 8, 8, 64, 3, 'SAME', 'relu'),        # 1216 output pixels: the half-empty last tile must not count
+    (6, 128, 8, 8, 256, 3, 'SAME', 'linear'),     # two filter tiles per pixel tile
+])
+def test_bn_statistics_from_conv_epilogue(shape, precision, with_pool):
+    out = _conv_bn_pair(shape, precision, with_pool)
+    a, b = out['epilogue'], out['own']
+    assert a['used'], 'the convolution epilogue did not take the statistics for this shape'
+    np.testing.assert_array_equal(a['conv_y'], b['conv_y'])          # same kernel, same output
+    # the statistics themselves against float64 sums of the very map they describe
+    cy = a['conv_y'].astype(np.float64)
+    mean = cy.mean(axis=(0, 2, 3)); var = cy.var(axis=(0, 2, 3))
+    assert rel_err(a['mean'], mean) < 1e-5
+    assert rel_err(a['invstd'], 1 / np.sqrt(var + 1e-6)) < 1e-5
+    # and everything downstream against the BatchNormalization that reduced x itself
+    for key in ('y', 'mm', 'mv', 'dgamma', 'dz'):
+        assert rel_err(a[key], b[key]) < 2e-5, key
+    # dX passes through the reduced-precision dgrad: a 1e-7 difference in dZ can flip an operand's
+    # rounding to 10 (7) mantissa bits, so the two runs agree only to that tier's resolution
+    assert rel_err(a['dx'], b['dx']) < (TOL_TF32 if precision == 'tf32' else TOL_BF16)
+
+
+def test_fp32_tier_never_takes_epilogue_statistics():
+    out = _conv_bn_pair((4, 64, 16, 16, 128, 3, 'SAME', 'relu'), 'fp32', True)
+    assert not out['epilogue']['used']
+    for key in ('y', 'dx', 'dgamma'):
+        np.testing.assert_array_equal(out['epilogue'][key], out['own'][key])
