@@ -236,24 +236,28 @@ SN_API int sn_batchnorm_fwd_apply(const float *x, float *y, const double *scratc
 
 /* BatchNormalization immediately followed by MaxPooling2D((2,2)) (stride 2), fused: the normalised
  * map is never written.  x: conv output (N,H,W,C); y_pool: (N,H/2,W/2,C); code: one byte per
- * pooled element (same meaning as sn_maxpool2d_fwd).  Requires sn_bn_pool_supported(). */
+ * pooled element (same meaning as sn_maxpool2d_fwd).  Requires sn_bn_pool_supported().
+ * y_pool_bf16 (may be NULL): also write the bf16 copy the next convolution of the bf16 tier reads. */
 SN_API int sn_bn_pool_supported(int N, int H, int W, int C);
-SN_API int sn_bn_pool_fwd_train(const float *x, const float *gamma, const float *beta, float *y_pool, uint8_t *code,
+SN_API int sn_bn_pool_fwd_train(const float *x, const float *gamma, const float *beta, float *y_pool, void *y_pool_bf16, uint8_t *code,
                          float *save_mean, float *save_invstd, float *moving_mean, float *moving_var,
                          double *scratch, int N, int H, int W, int C, float eps, float momentum,
                          int pool_mode, void *stream);
 /* pass 2 of sn_bn_pool_fwd_train alone (constants already in scratch: sn_batchnorm_stats or
  * sn_batchnorm_finalize_stats ran) */
-SN_API int sn_bn_pool_fwd_apply(const float *x, float *y_pool, uint8_t *code, const double *scratch,
+SN_API int sn_bn_pool_fwd_apply(const float *x, float *y_pool, void *y_pool_bf16, uint8_t *code, const double *scratch,
                          int N, int H, int W, int C, int pool_mode, void *stream);
 /* backward of the fused pair: dy_pool (N,H/2,W/2,C) -> dx (N,H,W,C) (overwritten), dgamma/dbeta +=.
  * y_pool / beta (both or neither; may be NULL): the forward's pooled output and the shift it was
  * computed with.  With them the two reductions of BatchNormalization.backward (:196-203) read the
- * pooled tensors only, since every pool winner satisfies xhat = (y_pool - beta)/gamma. */
+ * pooled tensors only, since every pool winner satisfies xhat = (y_pool - beta)/gamma.
+ * Outputs for the producing Conv2D's backward (layers/Convolution.py:186-197), each optional but
+ * at least one of dx / dx_bf16: dx (fp32), dx_bf16 (the bf16 operand copy of the same values),
+ * dx_colsum[C] += sum over rows of dx (that layer's bias gradient, :192; needs scratch >= 28*C doubles). */
 SN_API int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, const float *y_pool,
                    const float *gamma, const float *beta, const float *save_mean, const float *save_invstd,
-                   float *dx, float *dgamma, float *dbeta, double *scratch, int N, int H, int W, int C,
-                   int pool_mode, int mask_relu, void *stream);
+                   float *dx, void *dx_bf16, float *dx_colsum, float *dgamma, float *dbeta, double *scratch,
+                   int N, int H, int W, int C, int pool_mode, int mask_relu, void *stream);
 
 /* ------------------------------------------------------------------ loss */
 /* Softmax._forward, utils/Activator.py:108-110 (row-wise; the reference's global shift cancels) */

@@ -11,6 +11,7 @@
 // or first-argmax routing, and (optionally) the producing layer's ReLU mask applied to dX.
 #include "common.cuh"
 #include "bn_common.cuh"
+#include <cuda_bf16.h>
 #include <stdlib.h>
 using namespace sn;
 
@@ -35,8 +36,16 @@ __device__ __forceinline__ Win window(const float *x, long long idx, int Q, int 
     return w;
 }
 
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16 *dst, const float4 &v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t *>(&lo); u.y = *reinterpret_cast<uint32_t *>(&hi);
+    *reinterpret_cast<uint2 *>(dst) = u;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) bn_pool_fwd_kernel(const float *__restrict__ x, float *__restrict__ y,
+                                                          __nv_bfloat16 *__restrict__ y_bf16,
                                                           uint32_t *__restrict__ code, const double *__restrict__ scratch,
                                                           long long windows4, int C, int W, int oh, int ow) {
     const int Q = C >> 2;
@@ -66,6 +75,7 @@ __global__ void __launch_bounds__(256) bn_pool_fwd_kernel(const float *__restric
             packed |= cd << (8 * k);
         }
         *reinterpret_cast<float4 *>(y + idx * 4) = out;
+        if (y_bf16) store_bf16x4(y_bf16 + idx * 4, out);          // the next convolution's bf16 operand copy
         code[idx] = packed;
     }
 }
@@ -142,7 +152,7 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(const float *__
 // is too small for that division to be accurate (|gamma| < max(1,|beta|)/16, including gamma == 0)
 // take the window route above, per thread.
 template <int MODE>
-__global__ void __launch_bounds__(256) bn_pool_bwd_reduce_pooled_kernel(const float *__restrict__ dyp, const float *__restrict__ yp,
+__global__ void __launch_bounds__(256, 3) bn_pool_bwd_reduce_pooled_kernel(const float *__restrict__ dyp, const float *__restrict__ yp,
                                                                         const uint32_t *__restrict__ code, const float *__restrict__ x,
                                                                         const float *__restrict__ gamma, const float *__restrict__ beta,
                                                                         const float *__restrict__ mean, const float *__restrict__ invstd,
@@ -150,11 +160,10 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_pooled_kernel(const fl
                                                                         int oh, int ow, BnFinal fin) {
     const int Q = C >> 2;
     const int cq = threadIdx.x % Q;
-    float mu[4], is[4], bt[4], rg[4];
+    float bt[4], rg[4];
     bool fast = true;
     {
-        const float4 a = ldg4(mean + cq * 4), b = ldg4(invstd + cq * 4), g = ldg4(gamma + cq * 4), be = ldg4(beta + cq * 4);
-        mu[0] = a.x; mu[1] = a.y; mu[2] = a.z; mu[3] = a.w; is[0] = b.x; is[1] = b.y; is[2] = b.z; is[3] = b.w;
+        const float4 g = ldg4(gamma + cq * 4), be = ldg4(beta + cq * 4);
         bt[0] = be.x; bt[1] = be.y; bt[2] = be.z; bt[3] = be.w;
         const float gg[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
@@ -163,27 +172,46 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_pooled_kernel(const fl
             rg[k] = 1.f / gg[k];
         }
     }
-    double da[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};
+    // float64 running sums live in shared memory (they are folded into rarely): 16 registers less
+    __shared__ double sa[256][4], sb[256][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sa[threadIdx.x][k] = 0.0; sb[threadIdx.x][k] = 0.0; }
     const long long stride = (long long)gridDim.x * 256;
     long long idx = blockIdx.x * 256ll + threadIdx.x;
     while (idx < windows4) {
         float fa[4] = {0, 0, 0, 0}, fb[4] = {0, 0, 0, 0};
         if (fast) {
-#pragma unroll 4
-            for (int it = 0; it < 32 && idx < windows4; ++it, idx += stride) {
-                const float4 g = ldg4(dyp + idx * 4), pv = ldg4(yp + idx * 4);
+            // 8 independent 16-byte loads in flight per thread, 8 such batches between float64 folds
+            for (int it = 0; it < 8 && idx < windows4; ++it) {
+                if (idx + 3 * stride < windows4) {
+                    float4 g[4], pv[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float gk = comp(g, k);
-                    fa[k] += gk;
-                    fb[k] = fmaf(gk, (comp(pv, k) - bt[k]) * rg[k], fb[k]);
+                    for (int u = 0; u < 4; ++u) { g[u] = ldg4(dyp + (idx + u * stride) * 4); pv[u] = ldg4(yp + (idx + u * stride) * 4); }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float gk = comp(g[u], k);
+                            fa[k] += gk;
+                            fb[k] = fmaf(gk, (comp(pv[u], k) - bt[k]) * rg[k], fb[k]);
+                        }
+                    idx += 4 * stride;
+                } else {
+                    const float4 g = ldg4(dyp + idx * 4), pv = ldg4(yp + idx * 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float gk = comp(g, k);
+                        fa[k] += gk;
+                        fb[k] = fmaf(gk, (comp(pv, k) - bt[k]) * rg[k], fb[k]);
+                    }
+                    idx += stride;
                 }
             }
         } else {
 #pragma unroll 1
             for (int it = 0; it < 16 && idx < windows4; ++it, idx += stride) {
                 const Win w = window(x, idx, Q, ow, oh, W, C);
-                const float4 g = ldg4(dyp + idx * 4);
+                const float4 g = ldg4(dyp + idx * 4), mu4 = ldg4(mean + cq * 4), is4 = ldg4(invstd + cq * 4);
                 const uint32_t packed = __ldg(code + idx);
                 float4 v[4];
                 v[0] = ldg4(w.p00); v[1] = ldg4(w.p00 + C); v[2] = ldg4(w.p00 + w.rowstride); v[3] = ldg4(w.p00 + w.rowstride + C);
@@ -195,17 +223,14 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_pooled_kernel(const fl
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const float r = routed<MODE>(gk, cd, e);
-                        fb[k] = fmaf(r, (comp(v[e], k) - mu[k]) * is[k], fb[k]);
+                        fb[k] = fmaf(r, (comp(v[e], k) - comp(mu4, k)) * comp(is4, k), fb[k]);
                     }
                 }
             }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { da[k] += (double)fa[k]; db[k] += (double)fb[k]; }
+        for (int k = 0; k < 4; ++k) { sa[threadIdx.x][k] += (double)fa[k]; sb[threadIdx.x][k] += (double)fb[k]; }
     }
-    __shared__ double sa[256][4], sb[256][4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { sa[threadIdx.x][k] = da[k]; sb[threadIdx.x][k] = db[k]; }
     __syncthreads();
     if (threadIdx.x < Q) {
 #pragma unroll
@@ -223,13 +248,15 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_pooled_kernel(const fl
 template <int MODE, bool MASK>
 __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__restrict__ dyp, const uint32_t *__restrict__ code,
                                                                 const float *__restrict__ x, float *__restrict__ dx,
-                                                                const double *__restrict__ scratch, long long windows4, int C,
+                                                                __nv_bfloat16 *__restrict__ dx_bf16, float *__restrict__ colsum,
+                                                                double *__restrict__ scratch, long long windows4, int C,
                                                                 int W, int oh, int ow) {
     const int Q = C >> 2;
     const int cq = threadIdx.x % Q;
     const float *prm = bn_params(scratch, C);
     const float4 a4 = ldg4(prm + cq * 4), b4 = ldg4(prm + C + cq * 4), c4 = ldg4(prm + 2 * C + cq * 4);
     const float pa[4] = {a4.x, a4.y, a4.z, a4.w}, pb[4] = {b4.x, b4.y, b4.z, b4.w}, pc[4] = {c4.x, c4.y, c4.z, c4.w};
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};                  // this thread's share of sum_rows dx[., c] (the producer's bias gradient)
     const long long stride = (long long)gridDim.x * 256;
     for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < windows4; idx += stride) {
         const Win w = window(x, idx, Q, ow, oh, W, C);
@@ -247,13 +274,58 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__r
                 float r = fmaf(pa[k], routed<MODE>(gk, cd, e), fmaf(pb[k], xv, pc[k]));
                 if (MASK && relu_blocked(xv)) r = 0.f;
                 setc(o[e], k, r);
+                cs[k] += r;
             }
         }
-        float *d00 = dx + (w.p00 - x);
-        *reinterpret_cast<float4 *>(d00) = o[0];
-        *reinterpret_cast<float4 *>(d00 + C) = o[1];
-        *reinterpret_cast<float4 *>(d00 + w.rowstride) = o[2];
-        *reinterpret_cast<float4 *>(d00 + w.rowstride + C) = o[3];
+        const long long off = w.p00 - x;
+        if (dx) {
+            float *d00 = dx + off;
+            *reinterpret_cast<float4 *>(d00) = o[0];
+            *reinterpret_cast<float4 *>(d00 + C) = o[1];
+            *reinterpret_cast<float4 *>(d00 + w.rowstride) = o[2];
+            *reinterpret_cast<float4 *>(d00 + w.rowstride + C) = o[3];
+        }
+        if (dx_bf16) {
+            __nv_bfloat16 *b00 = dx_bf16 + off;
+            store_bf16x4(b00, o[0]);
+            store_bf16x4(b00 + C, o[1]);
+            store_bf16x4(b00 + w.rowstride, o[2]);
+            store_bf16x4(b00 + w.rowstride + C, o[3]);
+        }
+    }
+    if (colsum) {
+        // block sums -> BN_SLOTS slot rows in the scratch (same-address atomics serialise at ~10 ns
+        // each: one row would cost a chain of gridDim.x of them) -> the last block adds the rows up
+        __shared__ float scs[256][4];
+        __shared__ bool is_last;
+        double *slots = scratch + 20 * (size_t)C;        // [BN_SLOTS][C], float64: the result does not depend on the arrival order
+#pragma unroll
+        for (int k = 0; k < 4; ++k) scs[threadIdx.x][k] = cs[k];
+        __syncthreads();
+        if (threadIdx.x < Q) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float t = 0.f;
+                for (int j = threadIdx.x; j < 256; j += Q) t += scs[j][k];
+                atomicAdd(slots + (size_t)(blockIdx.x % BN_SLOTS) * C + cq * 4 + k, (double)t);
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned *ticket = reinterpret_cast<unsigned *>(scratch + 18 * (size_t)C) + 1;
+            is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            for (int c = threadIdx.x; c < C; c += 256) {
+                double t = 0.0;
+#pragma unroll
+                for (int sl = 0; sl < BN_SLOTS; ++sl) t += __ldcg(slots + (size_t)sl * C + c);
+                colsum[c] += (float)t;
+            }
+        }
     }
 }
 
@@ -275,7 +347,7 @@ extern "C" {
 
 int sn_bn_pool_supported(int N, int H, int W, int C) { return shape_ok(N, H, W, C) ? 1 : 0; }
 
-int sn_bn_pool_fwd_train(const float *x, const float *gamma, const float *beta, float *y_pool, uint8_t *code,
+int sn_bn_pool_fwd_train(const float *x, const float *gamma, const float *beta, float *y_pool, void *y_pool_bf16, uint8_t *code,
                          float *save_mean, float *save_invstd, float *moving_mean, float *moving_var, double *scratch,
                          int N, int H, int W, int C, float eps, float momentum, int pool_mode, void *stream) {
     SN_REQUIRE(x && gamma && beta && y_pool && code && save_mean && save_invstd && moving_mean && moving_var && scratch, "null tensor");
@@ -286,30 +358,33 @@ int sn_bn_pool_fwd_train(const float *x, const float *gamma, const float *beta, 
     // pass 1: per-channel statistics of x (the plain BatchNorm reduction, scratch zeroed inside)
     int e = sn_batchnorm_stats(x, gamma, beta, save_mean, save_invstd, moving_mean, moving_var, scratch, rows, C, eps, momentum, stream);
     if (e) return e;
-    return sn_bn_pool_fwd_apply(x, y_pool, code, scratch, N, H, W, C, pool_mode, stream);
+    return sn_bn_pool_fwd_apply(x, y_pool, y_pool_bf16, code, scratch, N, H, W, C, pool_mode, stream);
 }
 
-int sn_bn_pool_fwd_apply(const float *x, float *y_pool, uint8_t *code, const double *scratch, int N, int H, int W, int C,
-                         int pool_mode, void *stream) {
+int sn_bn_pool_fwd_apply(const float *x, float *y_pool, void *y_pool_bf16, uint8_t *code, const double *scratch, int N, int H,
+                         int W, int C, int pool_mode, void *stream) {
     SN_REQUIRE(x && y_pool && code && scratch, "null tensor");
     SN_REQUIRE(shape_ok(N, H, W, C), "unsupported shape (needs even H, W and C = 4*2^k <= 1024)");
     SN_REQUIRE(pool_mode == SN_POOL_TIE_SPLIT || pool_mode == SN_POOL_FIRST_ARGMAX, "unknown pool mode");
-    SN_REQUIRE(((((uintptr_t)x) | ((uintptr_t)y_pool)) & 15) == 0 && (((uintptr_t)code) & 3) == 0, "misaligned tensor");
+    SN_REQUIRE(((((uintptr_t)x) | ((uintptr_t)y_pool)) & 15) == 0 && (((uintptr_t)code) & 3) == 0 && (((uintptr_t)y_pool_bf16) & 7) == 0,
+               "misaligned tensor");
     cudaStream_t st = as_stream(stream);
     const int oh = H / 2, ow = W / 2;
     const long long windows4 = (long long)N * oh * ow * (C / 4);
     const int grid = grid_for_windows(windows4);
     if (pool_mode == SN_POOL_TIE_SPLIT)
-        bn_pool_fwd_kernel<SN_POOL_TIE_SPLIT><<<grid, 256, 0, st>>>(x, y_pool, (uint32_t *)code, scratch, windows4, C, W, oh, ow);
+        bn_pool_fwd_kernel<SN_POOL_TIE_SPLIT><<<grid, 256, 0, st>>>(x, y_pool, (__nv_bfloat16 *)y_pool_bf16, (uint32_t *)code, scratch, windows4, C, W, oh, ow);
     else
-        bn_pool_fwd_kernel<SN_POOL_FIRST_ARGMAX><<<grid, 256, 0, st>>>(x, y_pool, (uint32_t *)code, scratch, windows4, C, W, oh, ow);
+        bn_pool_fwd_kernel<SN_POOL_FIRST_ARGMAX><<<grid, 256, 0, st>>>(x, y_pool, (__nv_bfloat16 *)y_pool_bf16, (uint32_t *)code, scratch, windows4, C, W, oh, ow);
     return after_launch("bn_pool_fwd_kernel");
 }
 
 int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, const float *y_pool, const float *gamma,
-                   const float *beta, const float *save_mean, const float *save_invstd, float *dx, float *dgamma, float *dbeta,
-                   double *scratch, int N, int H, int W, int C, int pool_mode, int mask_relu, void *stream) {
-    SN_REQUIRE(dy_pool && code && x && gamma && save_mean && save_invstd && dx && scratch, "null tensor");
+                   const float *beta, const float *save_mean, const float *save_invstd, float *dx, void *dx_bf16,
+                   float *dx_colsum, float *dgamma, float *dbeta, double *scratch, int N, int H, int W, int C, int pool_mode,
+                   int mask_relu, void *stream) {
+    SN_REQUIRE(dy_pool && code && x && gamma && save_mean && save_invstd && (dx || dx_bf16) && scratch, "null tensor");
+    SN_REQUIRE(((((uintptr_t)x) | ((uintptr_t)dx) | ((uintptr_t)dy_pool)) & 15) == 0 && (((uintptr_t)dx_bf16) & 7) == 0, "misaligned tensor");
     SN_REQUIRE(shape_ok(N, H, W, C), "unsupported shape (needs even H, W and C = 4*2^k <= 1024)");
     SN_REQUIRE(pool_mode == SN_POOL_TIE_SPLIT || pool_mode == SN_POOL_FIRST_ARGMAX, "unknown pool mode");
     cudaStream_t st = as_stream(stream);
@@ -320,12 +395,14 @@ int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, co
     // fewer, longer-lived reduce blocks on small maps (see bn.cu: bn_reduce_ctas)
     const int rgrid = grid_for_windows(windows4, rows * C * 4 >= (100ll << 20) ? 8 : 3);
     const uint32_t *cd = (const uint32_t *)code;
-    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * BN_SCRATCH_DOUBLES_PER_C * C, st));
+    // (+8*C doubles: the BN_SLOTS x C slot rows of the dx_colsum reduction)
+    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (BN_SCRATCH_DOUBLES_PER_C + (dx_colsum ? BN_SLOTS : 0)) * C, st));
     BnFinal fin{};
     fin.bwd = 1; fin.rows = rows; fin.C = C; fin.gamma = gamma; fin.mean = save_mean; fin.invstd = save_invstd;
     fin.dgamma = dgamma; fin.dbeta = dbeta;
     if (y_pool && beta) {
         SN_REQUIRE((((uintptr_t)y_pool) & 15) == 0, "misaligned tensor");
+        const int rgrid = grid_for_windows(windows4, 3);          // one resident wave (3 CTAs/SM by registers)
         if (pool_mode == SN_POOL_TIE_SPLIT)
             bn_pool_bwd_reduce_pooled_kernel<SN_POOL_TIE_SPLIT><<<rgrid, 256, 0, st>>>(dy_pool, y_pool, cd, x, gamma, beta, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
         else
@@ -336,7 +413,7 @@ int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, co
         bn_pool_bwd_reduce_kernel<SN_POOL_FIRST_ARGMAX><<<rgrid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
     int e = after_launch("bn_pool_bwd_reduce_kernel");
     if (e) return e;
-#define SN_LAUNCH(M, K) bn_pool_bwd_apply_kernel<M, K><<<grid, 256, 0, st>>>(dy_pool, cd, x, dx, scratch, windows4, C, W, oh, ow)
+#define SN_LAUNCH(M, K) bn_pool_bwd_apply_kernel<M, K><<<grid, 256, 0, st>>>(dy_pool, cd, x, dx, (__nv_bfloat16 *)dx_bf16, dx_colsum, scratch, windows4, C, W, oh, ow)
     if (pool_mode == SN_POOL_TIE_SPLIT) { if (mask_relu) SN_LAUNCH(SN_POOL_TIE_SPLIT, true); else SN_LAUNCH(SN_POOL_TIE_SPLIT, false); }
     else { if (mask_relu) SN_LAUNCH(SN_POOL_FIRST_ARGMAX, true); else SN_LAUNCH(SN_POOL_FIRST_ARGMAX, false); }
 #undef SN_LAUNCH

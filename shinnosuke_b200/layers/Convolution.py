@@ -104,7 +104,9 @@ class Conv2D(Layer):
             # bf16 tier: bf16 copies of the input map and the filters, fp32 accumulation and output
             self._xb = self._bf16_buf('x_bf16', x.size)
             wb = self._bf16_buf('w_bf16', W.size)
-            lib.sn_cast_f32_to_bf16(x.ptr, self._xb.data_ptr(), x.size, st)
+            if getattr(self, '_xb_filled_for', None) is not x:       # else the producing kernel already wrote the copy
+                lib.sn_cast_f32_to_bf16(x.ptr, self._xb.data_ptr(), x.size, st)
+            self._xb_filled_for = None
             lib.sn_cast_f32_to_bf16(W.output_tensor.ptr, wb.data_ptr(), W.size, st)
             if scratch:
                 lib.sn_conv2d_fprop_bf16_stats(self._xb.data_ptr(), wb.data_ptr(), b.output_tensor.ptr, y.ptr, *geom,
@@ -129,6 +131,28 @@ class Conv2D(Layer):
             pow2 = F % 4 == 0 and (F // 4) & (F // 4 - 1) == 0 and F <= 1024     # what the BN apply kernels take
             cache[key] = bool(pow2 and lib.load().sn_conv2d_fprop_stats_supported(PRECISION[self.precision], int(bf16), *geom))
         return cache[key]
+
+    def _bf16_input_buffer(self, shape):
+        """For a producer that can write our bf16 operand copy itself (the fused BN+pool kernel): the
+        buffer sn_conv2d_fprop_bf16 will read for an input of `shape`, or None when this layer's
+        forward stays on the fp32 pointers.  The producer then sets `_xb_filled_for` to the tensor."""
+        N, C, H, Wd = shape
+        kh, kw = self.filter_size
+        geom = (N, C, H, Wd, self.filter_nums, kh, kw, self.stride, self.pad_size[0], self.pad_size[1])
+        if self.precision == 'bf16' and self._bf16_ok(0, geom):
+            return self._bf16_buf('x_bf16', N * C * H * Wd)
+        return None
+
+    def _bf16_grad_plan(self):
+        """(wgrad on bf16 operands?, dgrad on bf16 operands?) for the current input."""
+        x = self.input_tensor
+        N, C, H, Wd = x.shape
+        kh, kw = self.filter_size
+        geom = (N, C, H, Wd, self.filter_nums, kh, kw, self.stride, self.pad_size[0], self.pad_size[1])
+        bf16 = self.precision == 'bf16'
+        needs_dx = any(layer.require_grads for layer in self.inbounds)
+        return (bool(bf16 and self._xb is not None and self._bf16_ok(2, geom)),
+                bool(bf16 and needs_dx and self._bf16_ok(1, geom)))
 
     def _bf16_ok(self, op, geom):
         key = (op,) + tuple(geom)
@@ -159,20 +183,23 @@ class Conv2D(Layer):
             lib.sn_relu_bwd(g.ptr, y.ptr, g.size, st)
         geom = (N, C, H, Wd, F, kh, kw, self.stride, self.pad_size[0], self.pad_size[1])
         needs_dx = any(layer.require_grads for layer in self.inbounds)
-        bf16 = self.precision == 'bf16'
-        wgrad_bf16 = bf16 and self._xb is not None and self._bf16_ok(2, geom)
-        dgrad_bf16 = bf16 and needs_dx and self._bf16_ok(1, geom)
+        wgrad_bf16, dgrad_bf16 = self._bf16_grad_plan()
+        # a fused BN+pool backward may already have delivered the bias gradient (column sums of
+        # our gradient map) and the bf16 copy of that map while it wrote it
+        db_done = bool(self.__dict__.pop('_db_done', False))
+        gb_ready = bool(self.__dict__.pop('_gb_ready', False))
         gb = None
         if wgrad_bf16 or dgrad_bf16:
             gb = self._bf16_buf('dy_bf16', g.size)
-            lib.sn_cast_f32_to_bf16(g.ptr, gb.data_ptr(), g.size, st)
-        if W.require_grads or b.require_grads:
+            if not gb_ready:
+                lib.sn_cast_f32_to_bf16(g.ptr, gb.data_ptr(), g.size, st)
+        db = b.grads.ptr if (b.require_grads and not db_done) else None
+        if W.require_grads or db is not None:
             if wgrad_bf16:
-                lib.sn_conv2d_wgrad_bf16(self._xb.data_ptr(), gb.data_ptr(), g.ptr, W.grads.ptr,
-                                         b.grads.ptr if b.require_grads else None, *geom, st)
+                lib.sn_conv2d_wgrad_bf16(self._xb.data_ptr(), gb.data_ptr(), g.ptr if db is not None else None, W.grads.ptr,
+                                         db, *geom, st)
             else:
-                lib.sn_conv2d_wgrad(x.ptr, g.ptr, W.grads.ptr, b.grads.ptr if b.require_grads else None,
-                                    *geom, 1, prec, st)
+                lib.sn_conv2d_wgrad(x.ptr, g.ptr, W.grads.ptr, db, *geom, 1, prec, st)
         if dgrad_bf16:
             wtb = self._bf16_buf('wt_bf16', W.size)
             lib.sn_flip_transpose_filters_bf16(W.output_tensor.ptr, wtb.data_ptr(), F, C, kh, kw, st)

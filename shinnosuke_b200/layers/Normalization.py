@@ -3,7 +3,7 @@ import numpy as np
 
 from .Base import Layer, Variable
 from ..device import DeviceTensor, current_stream, zeros, torch
-from .._lib import lib, POOL_MODE
+from .._lib import lib, POOL_MODE, ACT
 from ..utils.Initializers import get_initializer
 
 
@@ -46,7 +46,7 @@ class BatchNormalization(Layer):
         if self._stats is None:
             self._stats = dict(mm=DeviceTensor.from_numpy(self._mm_host), mv=DeviceTensor.from_numpy(self._mv_host),
                                mean=DeviceTensor.empty((C,)), invstd=DeviceTensor.empty((C,)),
-                               scratch=zeros(20 * C + 2, torch().float64))
+                               scratch=zeros(28 * C + 2, torch().float64))
         return self._stats
 
     @property
@@ -78,14 +78,20 @@ class BatchNormalization(Layer):
             # so this layer has no output_tensor of its own in this mode (compile(..., fuse=False) keeps it).
             N, _, H, W = x.shape
             yp, code = pool._fused_buffers(N, C, H, W)
+            # the next convolution's bf16 operand copy, written while the pooled map is produced
+            nxt = pool.outbound_layers[0] if len(pool.outbound_layers) == 1 else None
+            ypb = nxt._bf16_input_buffer(yp.shape) if hasattr(nxt, '_bf16_input_buffer') else None
+            ypb_ptr = ypb.data_ptr() if ypb is not None else None
+            if ypb is not None:
+                nxt._xb_filled_for = yp
             if prestats:
                 lib.sn_batchnorm_finalize_stats(gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
                                                 s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows, C,
                                                 float(self.epsilon), float(self.momentum), st)
-                lib.sn_bn_pool_fwd_apply(x.ptr, yp.ptr, code.data_ptr(), s['scratch'].data_ptr(), N, H, W, C,
+                lib.sn_bn_pool_fwd_apply(x.ptr, yp.ptr, ypb_ptr, code.data_ptr(), s['scratch'].data_ptr(), N, H, W, C,
                                          POOL_MODE[pool.mode], st)
             else:
-                lib.sn_bn_pool_fwd_train(x.ptr, gamma.output_tensor.ptr, beta.output_tensor.ptr, yp.ptr, code.data_ptr(),
+                lib.sn_bn_pool_fwd_train(x.ptr, gamma.output_tensor.ptr, beta.output_tensor.ptr, yp.ptr, ypb_ptr, code.data_ptr(),
                                          s['mean'].ptr, s['invstd'].ptr, s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(),
                                          N, H, W, C, float(self.epsilon), float(self.momentum), POOL_MODE[pool.mode], st)
             pool._fused_output = yp
@@ -126,11 +132,30 @@ class BatchNormalization(Layer):
                 fuse = bool(layer.require_grads and layer._fused_relu() and len(layer.outbound_layers) == 1
                             and not layer._grads_written)
 
-                def fused_writer(dst, acc, fuse=fuse):
+                # what a Conv2D producer whose gradient map is exactly our dX can take directly:
+                # its bias gradient (column sums of dX, post-mask), and in the bf16 tier the bf16 copy
+                # of dX its wgrad / dgrad read (then the fp32 map need not be written at all)
+                sole = bool(layer.require_grads and len(layer.outbound_layers) == 1 and not layer._grads_written
+                            and hasattr(layer, '_bf16_grad_plan') and (fuse or layer._act_code() == ACT['linear']))
+                colsum = gb = None
+                want_f32 = True
+                if sole:
+                    bias = layer.variables[1]
+                    if bias.require_grads:
+                        colsum = bias.grads.ptr
+                        layer._db_done = True
+                    wg16, dg16 = layer._bf16_grad_plan()
+                    if wg16 or dg16:
+                        gb = layer._bf16_buf('dy_bf16', x.size).data_ptr()
+                        layer._gb_ready = True
+                        needs_dx = any(l.require_grads for l in layer.inbounds)
+                        want_f32 = not (wg16 and (dg16 or not needs_dx))
+
+                def fused_writer(dst, acc, fuse=fuse, colsum=colsum, gb=gb, want_f32=want_f32):
                     out = self._buf('dx_tmp', x.shape, x.layout) if acc else dst
                     lib.sn_bn_pool_bwd(pool.grads.ptr, pool._code.data_ptr(), x.ptr, pool.output_tensor.ptr,
                                        gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr,
-                                       s['invstd'].ptr, out.ptr, gamma.grads.ptr if gamma.require_grads else None,
+                                       s['invstd'].ptr, out.ptr if (want_f32 or acc) else None, gb, colsum, gamma.grads.ptr if gamma.require_grads else None,
                                        beta.grads.ptr if beta.require_grads else None, s['scratch'].data_ptr(),
                                        N, H, W, C, POOL_MODE[pool._code_mode], 1 if fuse else 0, st)
                     if acc:
