@@ -45,6 +45,16 @@ __device__ __forceinline__ const float *bn_params(const double *scratch, int C) 
 __device__ __forceinline__ void bn_finalize_channels(double *scratch, const BnFinal &f) {
     const int C = f.C;
     float *prm = bn_params(scratch, C);
+    // No float64 divide / sqrt below (each is a long dependent chain on this part's few FP64 units,
+    // and this code is the serial tail of a kernel): 1/rows comes from a float seed refined by two
+    // Newton steps, 1/sqrt from rsqrtf refined by two — both exact to float64 rounding.
+    double inv_rows;
+    {
+        const double r = (double)f.rows;
+        double y = (double)(1.0f / (float)f.rows);
+        y = y * (2.0 - r * y);
+        inv_rows = y * (2.0 - r * y);
+    }
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         double a = 0, b = 0;
 #pragma unroll
@@ -58,11 +68,14 @@ __device__ __forceinline__ void bn_finalize_channels(double *scratch, const BnFi
         }
         if (!f.bwd) {
             const double pivot = f.x ? (double)f.x[c] : 0.0;
-            const double m1 = a / (double)f.rows;                       // E[x - pivot]
-            double var = b / (double)f.rows - m1 * m1;
+            const double m1 = a * inv_rows;                             // E[x - pivot]
+            double var = b * inv_rows - m1 * m1;
             if (var < 0) var = 0;
             const double m = pivot + m1;
-            const double is = 1.0 / sqrt(var + (double)f.eps);
+            const double ve = var + (double)f.eps;
+            double is = (double)rsqrtf((float)ve);
+            is = is * (1.5 - 0.5 * ve * is * is);
+            is = is * (1.5 - 0.5 * ve * is * is);
             const double g = (double)f.gamma[c];
             prm[c] = (float)(g * is);
             prm[C + c] = (float)((double)f.beta[c] - g * is * m);
@@ -72,7 +85,7 @@ __device__ __forceinline__ void bn_finalize_channels(double *scratch, const BnFi
             f.moving_var[c] = f.momentum * f.moving_var[c] + (1.f - f.momentum) * (float)var;
         } else {
             const double is = (double)f.invstd[c], mu = (double)f.mean[c];
-            const double k2 = a / (double)f.rows, k3 = b / (double)f.rows;
+            const double k2 = a * inv_rows, k3 = b * inv_rows;
             const double p0 = (double)f.gamma[c] * is;
             const double p1 = -p0 * k3 * is;
             prm[c] = (float)p0;

@@ -402,7 +402,11 @@ int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, co
     fin.dgamma = dgamma; fin.dbeta = dbeta;
     if (y_pool && beta) {
         SN_REQUIRE((((uintptr_t)y_pool) & 15) == 0, "misaligned tensor");
-        const int rgrid = grid_for_windows(windows4, 3);          // one resident wave (3 CTAs/SM by registers)
+        // one resident wave (3 CTAs/SM by registers); on small maps at least 8 windows per thread, so
+        // that the per-block tail (shared-memory fold, 2*C float64 atomics, ticket) stays amortised
+        int rgrid = grid_for_windows(windows4, 3);
+        const long long by_work = windows4 / (256 * 8);
+        if (by_work < rgrid) rgrid = by_work < 1 ? 1 : (int)by_work;
         if (pool_mode == SN_POOL_TIE_SPLIT)
             bn_pool_bwd_reduce_pooled_kernel<SN_POOL_TIE_SPLIT><<<rgrid, 256, 0, st>>>(dy_pool, y_pool, cd, x, gamma, beta, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
         else

@@ -19,7 +19,7 @@ bool wgrad_halo_eligible(int N, int C, int OH, int OW, int F, int kh, int kw, in
 int conv_wgrad_halo_tc(const void *x, const void *dy, float *dw, int N, int C, int IH, int IW, int F, int kh, int kw, int OH,
                        int OW, int pad_h, int pad_w, bool bf16, cudaStream_t st);
 int colsum_accumulate(const float *dy, float *db, long long rows, int F, cudaStream_t st);
-bool stem_tc_eligible(int N, int C, int OH, int OW, int F, int kh, int kw);
+bool stem_tc_eligible(int N, int C, int H, int W, int F, int kh, int kw, int stride, int ph, int pw);
 int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
                        int kw, int stride, int ph, int pw, int act, double *stats, cudaStream_t st);
 int conv_stem_wgrad_tc(const float *x, const float *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh, int kw,
@@ -51,8 +51,8 @@ static int fprop_impl(const float *x, const float *w, const float *bias, float *
     if (e) return e;
     const bool geom_ok = N > 0 && C > 0 && F > 0 && kh > 0 && kw > 0 && stride > 0 && pad_h >= 0 && pad_w >= 0 &&
                          H + 2 * pad_h >= kh && W + 2 * pad_w >= kw;
-    if (geom_ok && precision != SN_PREC_FP32 && (((uintptr_t)y | (uintptr_t)bias) & 15) == 0 &&
-        stem_tc_eligible(N, C, (H + 2 * pad_h - kh) / stride + 1, (W + 2 * pad_w - kw) / stride + 1, F, kh, kw))
+    if (geom_ok && precision != SN_PREC_FP32 && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)bias) & 15) == 0 &&
+        stem_tc_eligible(N, C, H, W, F, kh, kw, stride, pad_h, pad_w))
         return conv_stem_fprop_tc(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, stats, as_stream(stream));
     if (!stats && geom_ok && (((uintptr_t)y) & 15) == 0 && direct_fprop_eligible(C, kh, kw, F))
         return conv_fprop_direct(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, as_stream(stream));
@@ -87,7 +87,7 @@ int sn_conv2d_fprop_stats_supported(int precision, int bf16_operands, int N, int
     if (bf16_operands) return (sn_conv2d_bf16_supported(0, N, C, H, W, F, kh, kw, stride, pad_h, pad_w) && igemm_stats_ok(F)) ? 1 : 0;
     if (precision != SN_PREC_TF32 && precision != SN_PREC_BF16) return 0;
     const int oh = (H + 2 * pad_h - kh) / stride + 1, ow = (W + 2 * pad_w - kw) / stride + 1;
-    if (stem_tc_eligible(N, C, oh, ow, F, kh, kw)) return 1;
+    if (stem_tc_eligible(N, C, H, W, F, kh, kw, stride, pad_h, pad_w)) return 1;
     if (direct_fprop_eligible(C, kh, kw, F)) return 0;
     return (conv_tc_eligible(N, C, oh, ow, F, stride) && igemm_stats_ok(F)) ? 1 : 0;
 }
@@ -123,8 +123,8 @@ int sn_conv2d_wgrad(const float *x, const float *dy, float *dw, float *db, int N
     if (e) return e;
     const bool geom_ok = N > 0 && C > 0 && F > 0 && kh > 0 && kw > 0 && stride > 0 && pad_h >= 0 && pad_w >= 0 &&
                          H + 2 * pad_h >= kh && W + 2 * pad_w >= kw;
-    if (geom_ok && precision != SN_PREC_FP32 && (((uintptr_t)dy) & 15) == 0 && (C * kh * kw < 32 || !db) &&
-        stem_tc_eligible(N, C, (H + 2 * pad_h - kh) / stride + 1, (W + 2 * pad_w - kw) / stride + 1, F, kh, kw)) {
+    if (geom_ok && precision != SN_PREC_FP32 && (((uintptr_t)dy | (uintptr_t)x) & 15) == 0 && (C * kh * kw < 32 || !db) &&
+        stem_tc_eligible(N, C, H, W, F, kh, kw, stride, pad_h, pad_w)) {
         cudaStream_t st = as_stream(stream);
         if (!accumulate) {
             SN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)F * kh * kw * C, st));

@@ -30,11 +30,61 @@ struct StemP {
     int tiles;    // fprop: ceil(P/128); wgrad: ceil(P/64)
     int tiles_per_cta;   // wgrad
     double *stats;       // fprop: optional BatchNorm sums of the output, stats[slot][{sum, sumsq}][F] (see conv_tc.cu)
+    int Hp;              // H + 2*ph: rows of one image in padded coordinates
+    int BW;              // floats per patch row: (W + 2*pw)*C rounded up to 32 (128-byte aligned TMA destinations)
+    int c0;              // first column of a patch row in elements of the real row: -(pw*C rounded up to 4) (16-byte aligned box start)
+    int shift;           // c0 + pw*C + shift == 0: where padded column 0 sits inside a patch row
+    float inv_ow, inv_oh;
 };
 
-// A builder thread owns 8 consecutive k's of one pixel row; their tap offsets are loop invariant.
+// ---- input patches -------------------------------------------------------------------------
+// The pixels of one tile are consecutive in (n, i, j) order, so their windows read a run of whole
+// input rows.  A producer warp brings that run into shared memory with TMA, one box per row of the
+// ZERO-PADDED image: tensor map (W*C, H, N), box (BW, 1, 1) starting at column -pw*C and row
+// hp - ph, so the left/right halo columns, the top/bottom padding rows and the rows between two
+// images all arrive as zeros from the TMA's out-of-bounds fill.  Patch row G - G_lo holds padded
+// row G = n*(H + 2ph) + hp.  The builders then assemble im2col rows with 8 unconditional LDS each.
+// (Gathering the taps from global memory, or copying the span with LDG, left the builder warps
+// waiting out one L2 round trip per tile: the ring of PATCH_STAGES TMA patches hides it.)
+constexpr int PATCH_STAGES = 4;
+
+__device__ __forceinline__ int fast_div(int x, int d, float inv, int &rem) {      // exact for 0 <= x < 2^24
+    int q = __float2int_rz(__int2float_rz(x) * inv);
+    rem = x - q * d;
+    if (rem < 0) { rem += d; --q; } else if (rem >= d) { rem -= d; ++q; }
+    return q;
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// producer warp: patch of pixels [pix0, pix0 + npix) -> stage buffer `dst`, G_lo -> *info
+__device__ __forceinline__ void patch_produce(const StemP &p, const CUtensorMap *tmX, float *dst, int *info, uint64_t *bar, int pix0,
+                                              int npix, int lane) {
+    const int pix1 = min(pix0 + npix, p.P) - 1;
+    int j, i0, i1;
+    const int t0 = fast_div(pix0, p.ow, p.inv_ow, j), n0 = fast_div(t0, p.oh, p.inv_oh, i0);
+    const int t1 = fast_div(pix1, p.ow, p.inv_ow, j), n1 = fast_div(t1, p.oh, p.inv_oh, i1);
+    const int g_lo = n0 * p.Hp + i0 * p.stride, g_hi = n1 * p.Hp + i1 * p.stride + p.kh - 1;
+    const int rows = g_hi - g_lo + 1;
+    if (lane == 0) { *info = g_lo; mbar_expect_tx(bar, (uint32_t)(rows * p.BW * 4)); }
+    __syncwarp();
+    // warp-uniform loop, the elected lane issues: UTMALDG takes its operands from uniform registers
+    int n = n0, hp = i0 * p.stride;
+    for (int row = 0; row < rows; ++row) {
+        if (elect_one()) tma_load_3d(dst + row * p.BW, tmX, bar, p.c0, hp - p.ph, n);
+        if (++hp == p.Hp) { hp = 0; ++n; }
+    }
+    __syncwarp();
+}
+
+// A builder thread owns 8 consecutive k's of one pixel row; their patch offsets are loop invariant.
 struct KSlice {
-    int du[8], dv[8], off[8];      // tap row / column and element offset (u*W + v)*C + c; du < 0 marks k >= K
+    int off[8];          // (u*BW + v*C + c) for k = 8*kq + e, or -1 when k >= K
 };
 __device__ __forceinline__ void make_kslice(const StemP &p, int kq, KSlice &ks) {
     const int kwC = p.kw * p.C;
@@ -42,55 +92,52 @@ __device__ __forceinline__ void make_kslice(const StemP &p, int kq, KSlice &ks) 
     for (int e = 0; e < 8; ++e) {
         const int k = kq * 8 + e;
         if (k < p.K) {
-            const int u = k / kwC, r = k - u * kwC, v = r / p.C, c = r - v * p.C;
-            ks.du[e] = u; ks.dv[e] = v; ks.off[e] = (u * p.W + v) * p.C + c;
+            const int u = k / kwC, r = k - u * kwC;          // r = v*C + c
+            ks.off[e] = u * p.BW + r;
         } else {
-            ks.du[e] = -1; ks.dv[e] = 0; ks.off[e] = 0;
+            ks.off[e] = -1;
         }
     }
 }
-// the 8 column values of pixel `pix` for this slice; `one_at` (>= 0) plants the constant-one column.
-// Branch-free: every lane always issues its 8 loads (from a safe address when the tap is padding or
-// the pixel is past the end), so they pipeline instead of forming 8 divergent load-use chains.
-__device__ __forceinline__ void gather_slice(const StemP &p, const KSlice &ks, int pix, int kq, int one_at, float (&col)[8]) {
+// the 8 column values of pixel `pix` for this slice, read from the patch; `one_at` (>= 0) plants the
+// constant-one column.  Rows past the end of the tensor are all zero.
+__device__ __forceinline__ void build_slice(const StemP &p, const KSlice &ks, const float *patch, int g_lo, int pix, int kq,
+                                            int one_at, float (&col)[8]) {
     const bool live = pix < p.P;
-    const int pp = live ? pix : 0;
-    const int t = pp / p.ow, j = pp - t * p.ow;
-    const int n = t / p.oh, i = t - n * p.oh;
-    const int hb = i * p.stride - p.ph, wb = j * p.stride - p.pw;
-    const float *base = p.x + (long long)n * p.H * p.W * p.C + (hb * p.W + wb) * p.C;
-    float v[8];
-    bool ok[8];
+    int j, i;
+    const int t = fast_div(live ? pix : 0, p.ow, p.inv_ow, j), n = fast_div(t, p.oh, p.inv_oh, i);
+    const float *base = patch + (n * p.Hp + i * p.stride - g_lo) * p.BW + j * p.stride * p.C + p.shift;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int h = hb + ks.du[e], w = wb + ks.dv[e];
-        ok[e] = live && ks.du[e] >= 0 && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
-        v[e] = __ldg(ok[e] ? base + ks.off[e] : p.x);
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) col[e] = ok[e] ? v[e] : ((live && kq * 8 + e == one_at) ? 1.f : 0.f);
+    for (int e = 0; e < 8; ++e)
+        col[e] = (live && ks.off[e] >= 0) ? base[ks.off[e]] : ((live && kq * 8 + e == one_at) ? 1.f : 0.f);
 }
 
 // ============================================================================== fprop
 constexpr int SF_BUILDERS = 512;               // 4 threads per pixel row
 constexpr int SF_EPI_WARPS = 8;                // two per TMEM lane quarter: the tile loop is all epilogue
-constexpr int SF_THREADS = 32 + SF_BUILDERS + 32 * SF_EPI_WARPS;   // warp 0: MMA, warps 1-16: column builders, warps 17-24: epilogue
+constexpr int SF_THREADS = 64 + SF_BUILDERS + 32 * SF_EPI_WARPS;   // warp 0: MMA, warp 1: patch producer, warps 2-17: column builders, warps 18-25: epilogue
+constexpr int SF_PATCH_FLOATS = 4096;          // per patch stage; stem_tc_eligible bounds the rows by this
 constexpr int SF_ABUF = 3;
 constexpr int SF_A_BYTES = 128 * 128;
 
 template <int BN>
-__global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_constant__ CUtensorMap tmO, const StemP p) {
+__global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX,
+                                                                   const StemP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sB = smem;                                   // [BN][128 B], SW128 K-major
     uint8_t *sA = smem + BN * 128;                        // SF_ABUF x [128][128 B]
     uint8_t *epi_stage = sA + SF_ABUF * SF_A_BYTES;       // per epilogue warp: 2 x (32 rows x 128 B) staging tiles for TMA stores
     float *sstat = reinterpret_cast<float *>(epi_stage + 2 * SF_EPI_WARPS * 4096);        // [2][BN] per-CTA column sums
-    uint64_t *a_full = reinterpret_cast<uint64_t *>(sstat + 2 * BN);
+    float *patch = sstat + 2 * BN;                                                        // PATCH_STAGES x SF_PATCH_FLOATS
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(patch + PATCH_STAGES * SF_PATCH_FLOATS);
     uint64_t *a_empty = a_full + SF_ABUF;
     uint64_t *t_full = a_empty + SF_ABUF;
     uint64_t *t_empty = t_full + 2;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(t_empty + 2);
+    uint64_t *p_full = t_empty + 2;
+    uint64_t *p_empty = p_full + PATCH_STAGES;
+    int *pinfo = reinterpret_cast<int *>(p_empty + PATCH_STAGES);
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(pinfo + PATCH_STAGES);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
@@ -104,6 +151,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
     if (threadIdx.x == 0) {
         for (int i = 0; i < SF_ABUF; ++i) { mbar_init(&a_full[i], SF_BUILDERS); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], SF_EPI_WARPS); }
+        for (int i = 0; i < PATCH_STAGES; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], SF_BUILDERS / 32); }
+        tma_prefetch_desc(&tmX);
         fence_barrier_init();
     }
     if (warp == 0) { tmem_alloc(tmem_ptr, 2 * BN < 32 ? 32 : 2 * BN); tmem_relinquish(); }
@@ -135,18 +184,26 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
                 if (++buf == SF_ABUF) { buf = 0; phase ^= 1; }
             }
         }
-    } else if (warp <= SF_BUILDERS / 32) {
+    } else if (warp == 1) {
+        // ---------------- patch producer: runs PATCH_STAGES tiles ahead of the builders ----------------
+        int ps = 0; uint32_t pphase = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            mbar_wait(&p_empty[ps], pphase ^ 1);
+            patch_produce(p, &tmX, patch + ps * SF_PATCH_FLOATS, pinfo + ps, &p_full[ps], tile * 128, 128, lane);
+            if (++ps == PATCH_STAGES) { ps = 0; pphase ^= 1; }
+        }
+    } else if (warp < 2 + SF_BUILDERS / 32) {
         // ---------------- column builders: thread (r, kq) builds k = 8kq..8kq+7 of pixel row r ----------------
-        const int bt = threadIdx.x - 32;
+        const int bt = threadIdx.x - 64;
         const int r = bt >> 2, kq = bt & 3;
         KSlice ks;
         make_kslice(p, kq, ks);
         int buf = 0; uint32_t phase = 0;
-        float col[8], nxt[8];
-        if ((int)blockIdx.x < p.tiles) gather_slice(p, ks, blockIdx.x * 128 + r, kq, -1, col);
+        int ps = 0; uint32_t pphase = 0;
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-            // the next tile's loads are in flight while this one waits for its buffer and stores
-            if (tile + (int)gridDim.x < p.tiles) gather_slice(p, ks, (tile + gridDim.x) * 128 + r, kq, -1, nxt);
+            mbar_wait(&p_full[ps], pphase);
+            float col[8];
+            build_slice(p, ks, patch + ps * SF_PATCH_FLOATS, pinfo[ps], tile * 128 + r, kq, -1, col);
             mbar_wait(&a_empty[buf], phase ^ 1);
             uint8_t *row = sA + buf * SF_A_BYTES + r * 128;
             // SW128 K-major: 16-byte chunk j of row r lives at (j ^ (r & 7)) * 16
@@ -155,13 +212,14 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
             fence_proxy_async();               // make the generic-proxy writes visible to the tensor core
             mbar_arrive(&a_full[buf]);
             if (++buf == SF_ABUF) { buf = 0; phase ^= 1; }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) col[e] = nxt[e];
+            __syncwarp();                      // every lane's patch reads are complete (their values were just stored)
+            if (lane == 0) mbar_arrive(&p_empty[ps]);
+            if (++ps == PATCH_STAGES) { ps = 0; pphase ^= 1; }
         }
     } else {
         // ---------------- epilogue: TMEM -> bias/ReLU -> NHWC output ----------------
         const int q = warp & 3;
-        const int ew = warp - 1 - SF_BUILDERS / 32;          // 0..7
+        const int ew = warp - 2 - SF_BUILDERS / 32;          // 0..7
         const int half = ew >> 2;                            // which 32-column chunks this warp takes
         int iter = 0;
         unsigned epi_flip = 0;
@@ -216,20 +274,26 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
 
 // ============================================================================== wgrad
 constexpr int SW_BUILDERS = 256;               // 4 threads per pixel row
-constexpr int SW_THREADS = 32 + SW_BUILDERS + 128;   // warp 0: TMA + MMA, warps 1-8: column builders, warps 9-12: epilogue
+constexpr int SW_THREADS = 64 + SW_BUILDERS + 128;   // warp 0: TMA (dY) + MMA, warp 1: patch producer, warps 2-9: column builders, warps 10-13: epilogue
 constexpr int SW_PB = 64;                      // pixels per stage
 constexpr int SW_STAGES = 4;
 constexpr int SW_ATOM = SW_PB * 128;           // one 32-wide atom column: 64 pixel rows x 128 B
 constexpr int SW_A_BYTES = 4 * SW_ATOM;        // 128 filters
 constexpr int SW_STAGE_BYTES = SW_A_BYTES + SW_ATOM;
+constexpr int SW_PATCH_FLOATS = 2048;          // per patch stage (a 64-pixel stage spans about half the rows of a 128-pixel tile)
 
-__global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const StemP p) {
+__global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                                                                   const StemP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + SW_STAGES * SW_STAGE_BYTES);
+    float *patch = reinterpret_cast<float *>(smem + SW_STAGES * SW_STAGE_BYTES);        // PATCH_STAGES x SW_PATCH_FLOATS
+    uint64_t *full = reinterpret_cast<uint64_t *>(patch + PATCH_STAGES * SW_PATCH_FLOATS);
     uint64_t *empty = full + SW_STAGES;
     uint64_t *acc_full = empty + SW_STAGES;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_full + 1);
+    uint64_t *p_full = acc_full + 1;
+    uint64_t *p_empty = p_full + PATCH_STAGES;
+    int *pinfo = reinterpret_cast<int *>(p_empty + PATCH_STAGES);
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(pinfo + PATCH_STAGES);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int f_tile = blockIdx.y;
@@ -242,6 +306,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
         // full: 1 arrive.expect_tx by the TMA thread + one arrival per builder thread
         for (int i = 0; i < SW_STAGES; ++i) { mbar_init(&full[i], 1 + SW_BUILDERS); mbar_init(&empty[i], 1); }
         mbar_init(acc_full, 1);
+        for (int i = 0; i < PATCH_STAGES; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], SW_BUILDERS / 32); }
+        tma_prefetch_desc(&tmX);
         fence_barrier_init();
     }
     if (warp == 0) { tmem_alloc(tmem_ptr, 32); tmem_relinquish(); }
@@ -288,19 +354,27 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
                 if (elect_one()) mma_commit(acc_full);
                 __syncwarp();
             }
-        } else if (warp <= SW_BUILDERS / 32) {
+        } else if (warp == 1) {
+            // patch producer: PATCH_STAGES stages ahead of the builders
+            int ps = 0; uint32_t pphase = 0;
+            for (int s = 0; s < nst; ++s) {
+                mbar_wait(&p_empty[ps], pphase ^ 1);
+                patch_produce(p, &tmX, patch + ps * SW_PATCH_FLOATS, pinfo + ps, &p_full[ps], (t0 + s) * SW_PB, SW_PB, lane);
+                if (++ps == PATCH_STAGES) { ps = 0; pphase ^= 1; }
+            }
+        } else if (warp < 2 + SW_BUILDERS / 32) {
             // column builders: thread (r, kq) builds k = 8kq..8kq+7 (one 32-byte chunk) of pixel row r
-            const int bt = threadIdx.x - 32;
+            const int bt = threadIdx.x - 64;
             const int r = bt >> 2, kq = bt & 3;
             KSlice ks;
             make_kslice(p, kq, ks);
             const int one_at = p.db ? p.K : -1;
             int stage = 0; uint32_t phase = 0;
-            float col[8], nxt[8];
-            gather_slice(p, ks, t0 * SW_PB + r, kq, one_at, col);   // rows past the end stay 0 (dY is TMA zero-filled too)
+            int ps = 0; uint32_t pphase = 0;
             for (int s = 0; s < nst; ++s) {
-                // the next stage's loads are in flight while this one waits for its slot and stores
-                if (s + 1 < nst) gather_slice(p, ks, (t0 + s + 1) * SW_PB + r, kq, one_at, nxt);
+                mbar_wait(&p_full[ps], pphase);
+                float col[8];
+                build_slice(p, ks, patch + ps * SW_PATCH_FLOATS, pinfo[ps], (t0 + s) * SW_PB + r, kq, one_at, col);   // rows past the end stay 0 (dY is TMA zero-filled too)
                 mbar_wait(&empty[stage], phase ^ 1);
                 // 128B swizzle with 32-byte atoms: 32-byte chunk j of row r lives at (j ^ (r & 3)) * 32
                 uint8_t *dst = smem + stage * SW_STAGE_BYTES + SW_A_BYTES + r * 128 + ((kq ^ (r & 3)) * 32);
@@ -309,11 +383,12 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
                 fence_proxy_async();
                 mbar_arrive(&full[stage]);
                 if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) col[e] = nxt[e];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_empty[ps]);
+                if (++ps == PATCH_STAGES) { ps = 0; pphase ^= 1; }
             }
         } else {
-            // epilogue (warps 9..12): dW[f][k] += D[f][k], db[f] += D[f][K]
+            // epilogue (warps 10..13): dW[f][k] += D[f][k], db[f] += D[f][K]
             const int q = warp & 3;
             mbar_wait_sleep(acc_full, 0);        // whole-kernel wait: do not steal issue slots from the builders
             tc_fence_after();
@@ -335,16 +410,32 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 32); }
 }
 
+// one patch row = one TMA box: its shared-memory address must be 128-byte aligned, so the pitch is a multiple of 32 floats
+int patch_row_floats(int W, int C, int pw) { return ((((pw * C + 3) & ~3) - pw * C) + (W + 2 * pw) * C + 31) & ~31; }
+
 void fill_geom(StemP &p, int N, int C, int H, int W, int F, int kh, int kw, int stride, int ph, int pw) {
     p.N = N; p.C = C; p.H = H; p.W = W; p.F = F; p.kh = kh; p.kw = kw; p.stride = stride; p.ph = ph; p.pw = pw;
     p.oh = (H + 2 * ph - kh) / stride + 1; p.ow = (W + 2 * pw - kw) / stride + 1;
     p.K = C * kh * kw; p.P = N * p.oh * p.ow;
+    p.Hp = H + 2 * ph; p.BW = patch_row_floats(W, C, pw);
+    p.c0 = -((pw * C + 3) & ~3); p.shift = -p.c0 - pw * C;
+    p.inv_ow = 1.f / (float)p.ow; p.inv_oh = 1.f / (float)p.oh;
+}
+
+// x as (W*C, H, N) with one-row boxes of BW floats, no swizzle: see "input patches" above
+int make_patch_tmap(CUtensorMap *tm, const StemP &p) {
+    long long dims[3] = {(long long)p.W * p.C, p.H, p.N};
+    long long strs[3] = {1, (long long)p.W * p.C, (long long)p.H * p.W * p.C};
+    int box[3] = {p.BW, 1, 1};
+    return make_tmap_linear_f32(tm, p.x, 3, dims, strs, box);
 }
 
 template <int BN>
 int launch_stem_fprop(const StemP &p, cudaStream_t st) {
-    const int smem = BN * 128 + SF_ABUF * SF_A_BYTES + 2 * SF_EPI_WARPS * 4096 + 2 * BN * 4 + 1024 + 256;
-    CUtensorMap tmO;
+    const int smem = BN * 128 + SF_ABUF * SF_A_BYTES + 2 * SF_EPI_WARPS * 4096 + 2 * BN * 4 + PATCH_STAGES * SF_PATCH_FLOATS * 4 + 1024 + 256;
+    CUtensorMap tmO, tmX;
+    int ex = make_patch_tmap(&tmX, p);
+    if (ex) return ex;
     long long odims[2] = {p.F, p.P};
     long long ostr[2] = {1, p.F};
     int obox[2] = {32, 32};
@@ -356,7 +447,7 @@ int launch_stem_fprop(const StemP &p, cudaStream_t st) {
         configured = true;
     }
     int grid = p.tiles < num_sms() ? p.tiles : num_sms();
-    stem_fprop_kernel<BN><<<grid, SF_THREADS, smem, st>>>(tmO, p);
+    stem_fprop_kernel<BN><<<grid, SF_THREADS, smem, st>>>(tmO, tmX, p);
     return after_launch("stem_fprop_kernel");
 }
 
@@ -364,10 +455,20 @@ int launch_stem_fprop(const StemP &p, cudaStream_t st) {
 
 namespace sn {
 
-bool stem_tc_eligible(int N, int C, int OH, int OW, int F, int kh, int kw) {
+bool stem_tc_eligible(int N, int C, int H, int W, int F, int kh, int kw, int stride, int ph, int pw) {
     const int K = C * kh * kw;
     if (K > 32 || (F & 15) || F > 256 || F < 16) return false;
-    return (long long)N * OH * OW >= 4096;          // small maps: the direct kernel is latency-equivalent
+    const int OH = (H + 2 * ph - kh) / stride + 1, OW = (W + 2 * pw - kw) / stride + 1;
+    const long long P = (long long)N * OH * OW;
+    // TMA patch rows: 16-byte row pitch in global memory, box <= 256 elements, pixel indices exact in
+    // fp32 (fast_div), and the padded rows that 128 (fprop) / 64 (wgrad) consecutive pixels touch —
+    // image boundary included — must fit a patch stage
+    const int bw = patch_row_floats(W, C, pw);
+    if (((W * C) & 3) || bw > 256 || P >= (1 << 24)) return false;
+    const long long extra = kh + 2 * ph + stride;
+    const long long rows128 = (long long)(127 / OW + 2) * stride + extra, rows64 = (long long)(63 / OW + 2) * stride + extra;
+    if (rows128 * bw > SF_PATCH_FLOATS || rows64 * bw > SW_PATCH_FLOATS) return false;
+    return P >= 4096;          // small maps: the direct kernel is latency-equivalent
 }
 
 int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
@@ -402,13 +503,16 @@ int conv_stem_wgrad_tc(const float *x, const float *dy, float *dw, float *db, in
     int dbox[2] = {32, SW_PB};
     int e = make_tmap_f32(&tmDY, dy, 2, ddims, dstr, dbox, true);
     if (e) return e;
-    const int smem = SW_STAGES * SW_STAGE_BYTES + 1024 + 256;
+    const int smem = SW_STAGES * SW_STAGE_BYTES + PATCH_STAGES * SW_PATCH_FLOATS * 4 + 1024 + 256;
+    CUtensorMap tmX;
+    e = make_patch_tmap(&tmX, p);
+    if (e) return e;
     static bool configured = false;
     if (!configured) {
         SN_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    stem_wgrad_kernel<<<dim3(ctas, f_tiles), SW_THREADS, smem, st>>>(tmDY, p);
+    stem_wgrad_kernel<<<dim3(ctas, f_tiles), SW_THREADS, smem, st>>>(tmDY, tmX, p);
     return after_launch("stem_wgrad_kernel");
 }
 

@@ -49,6 +49,26 @@ int make_tmap_f32(CUtensorMap *out, const void *base, int rank, const long long 
     return make_tmap(out, base, rank, dims, strides_elems, box, atom32b, false);
 }
 
+// fp32, no swizzle: rows land in shared memory exactly as the box enumerates them
+int make_tmap_linear_f32(CUtensorMap *out, const void *base, int rank, const long long *dims, const long long *strides_elems,
+                         const int *box) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return SN_ERR_UNSUPPORTED; }
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = (cuuint64_t)dims[i]; bdim[i] = (cuuint32_t)box[i]; estr[i] = 1; }
+    for (int i = 1; i < rank; ++i) gstr[i - 1] = (cuuint64_t)strides_elems[i] * 4;
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bdim, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (linear) failed (%d): rank %d dims %lld %lld %lld box %d %d %d", (int)r, rank, dims[0],
+                  rank > 1 ? dims[1] : 0, rank > 2 ? dims[2] : 0, box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0);
+        return SN_ERR_UNSUPPORTED;
+    }
+    return SN_OK;
+}
+
 int make_tmap(CUtensorMap *out, const void *base, int rank, const long long *dims, const long long *strides_elems,
               const int *box, bool atom32b, bool bf16) {
     EncodeTiledFn enc = get_encode_tiled();

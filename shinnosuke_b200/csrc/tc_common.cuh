@@ -187,6 +187,8 @@ EncodeTiledFn get_encode_tiled();
 int make_tmap_f32(CUtensorMap *out, const void *base, int rank, const long long *dims, const long long *strides_elems,
                   const int *box, bool atom32b = false);
 // same for fp32 or bf16 elements (strides in elements)
+int make_tmap_linear_f32(CUtensorMap *out, const void *base, int rank, const long long *dims, const long long *strides_elems,
+                         const int *box);
 int make_tmap(CUtensorMap *out, const void *base, int rank, const long long *dims, const long long *strides_elems,
               const int *box, bool atom32b, bool bf16);
 

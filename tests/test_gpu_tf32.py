@@ -64,6 +64,9 @@ def _run_conv(shape, precision='tf32'):
     (8, 3, 32, 32, 64, 3, 1, 'SAME', 'relu'),        # cfg3 stem: column tile built in smem + tcgen05 (conv_stem_tc.cu)
     (20, 3, 29, 31, 48, 3, 2, 'VALID', 'linear'),    # stem path, ragged everything, stride 2
     (16, 1, 28, 28, 16, 2, 1, 'VALID', 'relu'),      # cfg1-like (K = 4) on the stem path
+    (20, 3, 29, 32, 48, 3, 2, 'VALID', 'linear'),    # stem path with stride 2: patches skip rows, tiles straddle images
+    (16, 2, 24, 24, 32, 3, 1, 'SAME', 'relu'),       # stem path, C = 2 (patch box starts 4 floats left of the row, shift 2)
+    (16, 1, 28, 28, 32, 5, 1, 'SAME', 'relu'),       # stem path, 5x5 taps with two halo columns / rows
 ])
 def test_conv2d_tf32_vs_oracle(shape):
     out = _run_conv(shape)
@@ -261,7 +264,7 @@ def _conv_bn_pair(shape, precision, with_pool):
 @pytest.mark.parametrize('with_pool', [True, False])
 @pytest.mark.parametrize('shape', [
     (8, 3, 32, 32, 64, 3, 'SAME', 'relu'),        # stem kernel epilogue
-    (6, 3, 30, 30, 32, 3, 'VALID', 'linear'),     # stem, ragged last pixel tile (6*28*28 = 4704 rows)
+    (6, 3, 30, 32, 32, 3, 'VALID', 'linear'),     # stem, ragged last pixel tile (6*28*30 = 5040 rows), tiles straddle images
     (4, 64, 16, 16, 128, 3, 'SAME', 'relu'),      # implicit-GEMM epilogue
     (19, 32, 8, 8, 64, 3, 'SAME', 'relu'),        # 1216 output pixels: the half-empty last tile must not count
     (6, 128, 8, 8, 256, 3, 'SAME', 'linear'),     # two filter tiles per pixel tile
