@@ -128,8 +128,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
     uint8_t *sB = smem;                                   // [BN][128 B], SW128 K-major
     uint8_t *sA = smem + BN * 128;                        // SF_ABUF x [128][128 B]
     uint8_t *epi_stage = sA + SF_ABUF * SF_A_BYTES;       // per epilogue warp: 2 x (32 rows x 128 B) staging tiles for TMA stores
-    float *sstat = reinterpret_cast<float *>(epi_stage + 2 * SF_EPI_WARPS * 4096);        // [2][BN] per-CTA column sums
-    float *patch = sstat + 2 * BN;                                                        // PATCH_STAGES x SF_PATCH_FLOATS
+    float *sstat = reinterpret_cast<float *>(epi_stage + 2 * SF_EPI_WARPS * 4096);        // [epilogue warp][{sum, sumsq}][BN] column sums
+    float *patch = sstat + SF_EPI_WARPS * 2 * BN;                                                        // PATCH_STAGES x SF_PATCH_FLOATS
     uint64_t *a_full = reinterpret_cast<uint64_t *>(patch + PATCH_STAGES * SF_PATCH_FLOATS);
     uint64_t *a_empty = a_full + SF_ABUF;
     uint64_t *t_full = a_empty + SF_ABUF;
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
         fence_barrier_init();
     }
     if (warp == 0) { tmem_alloc(tmem_ptr, 2 * BN < 32 ? 32 : 2 * BN); tmem_relinquish(); }
-    for (int i = threadIdx.x; i < 2 * BN; i += SF_THREADS) sstat[i] = 0.f;
+    for (int i = threadIdx.x; i < SF_EPI_WARPS * 2 * BN; i += SF_THREADS) sstat[i] = 0.f;
     fence_proxy_async();            // the weight tile was written through the generic proxy
     tc_fence_before();
     __syncthreads();
@@ -252,7 +252,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
                 __syncwarp();
                 // one TMA store per 32 x 32 sub-tile: full 128-byte lines, clipped at the tensor bounds
                 if (lane == 0) { tma_store_2d(&tmO, st, c0, tile * 128 + q * 32); tma_store_commit(); }
-                if (p.stats) staged_tile_colsums(st, lane, p.P - (tile * 128 + q * 32), sstat + c0, sstat + BN + c0, p.F - c0);
+                if (p.stats)
+                    staged_tile_colsums(st, lane, p.P - (tile * 128 + q * 32), sstat + ew * 2 * BN + c0, sstat + (ew * 2 + 1) * BN + c0, p.F - c0);
             }
             tc_fence_before();
             __syncwarp();
@@ -266,8 +267,11 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
     if (p.stats) {
         double *slot = p.stats + (size_t)(blockIdx.x % BN_SLOTS) * 2 * p.F;
         for (int f = threadIdx.x; f < p.F; f += SF_THREADS) {
-            atomicAdd(slot + f, (double)sstat[f]);
-            atomicAdd(slot + p.F + f, (double)sstat[BN + f]);
+            double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int e = 0; e < SF_EPI_WARPS; ++e) { s1 += (double)sstat[e * 2 * BN + f]; s2 += (double)sstat[(e * 2 + 1) * BN + f]; }
+            atomicAdd(slot + f, s1);
+            atomicAdd(slot + p.F + f, s2);
         }
     }
 }
@@ -432,7 +436,7 @@ int make_patch_tmap(CUtensorMap *tm, const StemP &p) {
 
 template <int BN>
 int launch_stem_fprop(const StemP &p, cudaStream_t st) {
-    const int smem = BN * 128 + SF_ABUF * SF_A_BYTES + 2 * SF_EPI_WARPS * 4096 + 2 * BN * 4 + PATCH_STAGES * SF_PATCH_FLOATS * 4 + 1024 + 256;
+    const int smem = BN * 128 + SF_ABUF * SF_A_BYTES + 2 * SF_EPI_WARPS * 4096 + SF_EPI_WARPS * 2 * BN * 4 + PATCH_STAGES * SF_PATCH_FLOATS * 4 + 1024 + 256;
     CUtensorMap tmO, tmX;
     int ex = make_patch_tmap(&tmX, p);
     if (ex) return ex;

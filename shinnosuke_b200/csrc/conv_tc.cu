@@ -121,10 +121,10 @@ struct IgemmParams {
 // BatchNorm statistics in the epilogue: the BatchNormalization that consumes a convolution needs
 // sum(y) and sum(y^2) per channel, which would otherwise cost a full re-read of y.  Each epilogue
 // warp column-sums its 32x32 staging tile out of shared memory (lane = column; the swizzle makes
-// the row-wise reads conflict-free), accumulates into a per-CTA fp32 table, and the CTA adds its
-// table to stats[slot][{sum, sumsq}][F] (float64, slot = blockIdx.x % BN_SLOTS) once at the end.
+// the row-wise reads conflict-free), accumulates into its own fp32 table, and the CTA adds the four
+// tables to stats[slot][{sum, sumsq}][F] (float64, slot = blockIdx.x % BN_SLOTS) once at the end.
 constexpr int STAT_MAX_F = 512;
-constexpr int STAT_BYTES = 2 * STAT_MAX_F * 4;
+constexpr int STAT_BYTES = 4 * 2 * STAT_MAX_F * 4;          // [epilogue warp][{sum, sumsq}][STAT_MAX_F]
 
 constexpr int EPI_STAGE_BYTES = 4 * 4096;       // one 32-row x 128-byte staging tile per epilogue warp
 
@@ -150,7 +150,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *epi_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                 // 1024-byte aligned (stage sizes are)
-    float *sstat = reinterpret_cast<float *>(epi_stage + EPI_STAGE_BYTES);      // [2][STAT_MAX_F]
+    float *sstat = reinterpret_cast<float *>(epi_stage + EPI_STAGE_BYTES);      // [4][2][STAT_MAX_F]
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi_stage + EPI_STAGE_BYTES + STAT_BYTES);
     uint64_t *empty_bar = full_bar + Cfg::STAGES;
     uint64_t *tmem_full = empty_bar + Cfg::STAGES;
@@ -176,7 +176,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tmem_relinquish();
     }
     if (p.stats)
-        for (int i = threadIdx.x; i < 2 * STAT_MAX_F; i += NUM_THREADS) sstat[i] = 0.f;
+        for (int i = threadIdx.x; i < 4 * 2 * STAT_MAX_F; i += NUM_THREADS) sstat[i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -293,7 +293,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         __syncwarp();
                         if (lane == 0) { tma_store_2d(&tmO, st, f0, tm * BM + q * 32); tma_store_commit(); }
                         if (p.stats)
-                            staged_tile_colsums(st, lane, p.rows - (tm * BM + q * 32), sstat + f0, sstat + STAT_MAX_F + f0, p.F - f0);
+                            staged_tile_colsums(st, lane, p.rows - (tm * BM + q * 32), sstat + q * 2 * STAT_MAX_F + f0,
+                                                sstat + (q * 2 + 1) * STAT_MAX_F + f0, p.F - f0);
                         continue;
                     }
                 }
@@ -339,8 +340,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             asm volatile("bar.sync 1, 128;" ::: "memory");           // the four epilogue warps only
             double *slot = p.stats + (size_t)(blockIdx.x % BN_SLOTS) * 2 * p.F;
             for (int f = threadIdx.x - 64; f < p.F; f += 128) {
-                atomicAdd(slot + f, (double)sstat[f]);
-                atomicAdd(slot + p.F + f, (double)sstat[STAT_MAX_F + f]);
+                double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                for (int wq = 0; wq < 4; ++wq) { s1 += (double)sstat[wq * 2 * STAT_MAX_F + f]; s2 += (double)sstat[(wq * 2 + 1) * STAT_MAX_F + f]; }
+                atomicAdd(slot + f, s1);
+                atomicAdd(slot + p.F + f, s2);
             }
         }
     }

@@ -197,8 +197,10 @@ int make_tmap(CUtensorMap *out, const void *base, int rank, const long long *dim
 // layout the TMA store reads (16-byte chunk j of row r at (j ^ (r & 7)) * 16).  Lane l takes the
 // column pair 2*(l & 15) of rows 16*(l >> 4) .. +15 with 8-byte loads (each half warp reads one
 // whole row: conflict-free) and packed f32x2 adds / fmas, one shuffle joins the two row halves,
-// and lanes 0..15 add {sum, sum of squares} of their two columns to the per-CTA tables in shared
-// memory.  nvalid (< 32 only in the last pixel tile) masks rows past the end of the tensor.
+// and lanes 0..15 add {sum, sum of squares} of their two columns to THIS WARP's tables in shared
+// memory (plain read-modify-write: fp32 atomicAdd on shared memory is a CAS spin loop, ~20 us per
+// launch when four warps share a table).  nvalid (< 32 only in the last pixel tile) masks rows past
+// the end of the tensor.
 __device__ __forceinline__ void staged_tile_colsums(const uint8_t *st, int lane, int nvalid, float *ssum, float *ssq, int ncols) {
     const int cp = lane & 15, r0 = (lane >> 4) * 16;
     const uint8_t *base = st + (cp & 1) * 8;
@@ -228,8 +230,8 @@ __device__ __forceinline__ void staged_tile_colsums(const uint8_t *st, int lane,
     b.y += __shfl_down_sync(0xffffffffu, b.y, 16);
     if (lane < 16) {
         const int c = 2 * cp;
-        if (c < ncols) { atomicAdd(ssum + c, a.x); atomicAdd(ssq + c, b.x); }
-        if (c + 1 < ncols) { atomicAdd(ssum + c + 1, a.y); atomicAdd(ssq + c + 1, b.y); }
+        if (c < ncols) { ssum[c] += a.x; ssq[c] += b.x; }
+        if (c + 1 < ncols) { ssum[c + 1] += a.y; ssq[c + 1] += b.y; }
     }
 }
 
