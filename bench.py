@@ -166,78 +166,98 @@ class ClockSampler(object):
 # --------------------------------------------------------------- roofline table
 def kernel_work(name, a, precision):
     """Algorithmic work of one launch from its integer arguments (SURVEY.md 8(d) formulas).
-    Returns (kind, amount): kind 'flops' or 'bytes'."""
-    if name in ('sn_conv2d_fprop', 'sn_conv2d_dgrad', 'sn_conv2d_wgrad', 'sn_conv2d_fprop_bf16', 'sn_conv2d_dgrad_bf16',
-                'sn_conv2d_wgrad_bf16', 'sn_conv2d_fprop_stats', 'sn_conv2d_fprop_bf16_stats'):
+    Returns (flops, bytes): the bytes are the tensors the operation must read and write once."""
+    conv = ('sn_conv2d_fprop', 'sn_conv2d_dgrad', 'sn_conv2d_wgrad', 'sn_conv2d_fprop_bf16', 'sn_conv2d_dgrad_bf16',
+            'sn_conv2d_wgrad_bf16', 'sn_conv2d_fprop_stats', 'sn_conv2d_fprop_bf16_stats')
+    if name in conv:
         N, C, H, W, F, kh, kw, stride, ph, pw = a[:10]
         oh = (H + 2 * ph - kh) // stride + 1
         ow = (W + 2 * pw - kw) // stride + 1
-        return 'flops', 2.0 * N * F * oh * ow * C * kh * kw
+        x, y, w = N * C * H * W, N * F * oh * ow, F * C * kh * kw
+        flops = 2.0 * y * C * kh * kw
+        if 'bf16' in name:
+            # bf16 operand copies in, fp32 result out (fprop: y, dgrad: dx = x-sized, wgrad: dw)
+            byt = {'fprop': 2 * x + 2 * w + 4 * y, 'dgrad': 2 * y + 2 * w + 4 * x, 'wgrad': 2 * x + 2 * y + 4 * w}
+        else:
+            byt = {'fprop': 4 * (x + w + y), 'dgrad': 4 * (x + w + y), 'wgrad': 4 * (x + w + y)}
+        return flops, float(byt['fprop' if 'fprop' in name else ('dgrad' if 'dgrad' in name else 'wgrad')])
     if name in ('sn_dense_fprop', 'sn_dense_dgrad', 'sn_dense_wgrad'):
         M, K, Nout = a[:3]
-        return 'flops', 2.0 * M * K * Nout
+        return 2.0 * M * K * Nout, 4.0 * (M * K + K * Nout + M * Nout)
     if name in ('sn_maxpool2d_fwd', 'sn_maxpool2d_bwd'):
         N, H, W, C, pool, stride = a[:6]
         oh, ow = (H - pool) // stride + 1, (W - pool) // stride + 1
-        return 'bytes', 4.0 * N * C * (H * W + oh * ow) + N * C * oh * ow
+        return 0.0, 4.0 * N * C * (H * W + oh * ow) + N * C * oh * ow
     if name == 'sn_batchnorm_fwd_train':
         rows, C = a[0], a[1]
-        return 'bytes', 4.0 * rows * C * 3          # read x (stats), read x + write y (apply)
+        return 0.0, 4.0 * rows * C * 3          # read x (stats), read x + write y (apply)
     if name == 'sn_batchnorm_bwd':
         rows, C = a[0], a[1]
-        return 'bytes', 4.0 * rows * C * 5          # read dy,x (reduce), read dy,x + write dx (apply)
+        return 0.0, 4.0 * rows * C * 5          # read dy,x (reduce), read dy,x + write dx (apply)
     if name == 'sn_bn_pool_fwd_train':
         N, H, W, C = a[:4]
-        return 'bytes', 8.0 * N * H * W * C + 5.0 * N * (H // 2) * (W // 2) * C     # x read twice; pooled y + code written
+        return 0.0, 8.0 * N * H * W * C + 5.0 * N * (H // 2) * (W // 2) * C     # x read twice; pooled y + code written
     if name == 'sn_bn_pool_fwd_apply':
         N, H, W, C = a[:4]
-        return 'bytes', 4.0 * N * H * W * C + 5.0 * N * (H // 2) * (W // 2) * C     # x read once; pooled y + code written
+        return 0.0, 4.0 * N * H * W * C + 5.0 * N * (H // 2) * (W // 2) * C     # x read once; pooled y + code written
     if name == 'sn_batchnorm_fwd_apply':
-        return 'bytes', 8.0 * a[0] * a[1]
+        return 0.0, 8.0 * a[0] * a[1]
     if name == 'sn_bn_pool_bwd':
         N, H, W, C = a[:4]
-        # reduce: dy_pool + y_pool; apply: x read, dx written, dy_pool + code read
-        return 'bytes', 8.0 * N * H * W * C + 13.0 * N * (H // 2) * (W // 2) * C
+        # reduce: dy_pool + y_pool; apply: x read, dx written (fp32), dy_pool + code read
+        return 0.0, 8.0 * N * H * W * C + 13.0 * N * (H // 2) * (W // 2) * C
     if name == 'sn_sgd_update':
-        return 'bytes', 16.0 * a[0]
+        return 0.0, 16.0 * a[0]
     if name == 'sn_momentum_update':
-        return 'bytes', 20.0 * a[0]
+        return 0.0, 20.0 * a[0]
     if name == 'sn_cast_f32_to_bf16':
-        return 'bytes', 6.0 * a[0]
+        return 0.0, 6.0 * a[0]
     if name in ('sn_relu_bwd',):
-        return 'bytes', 12.0 * a[0]
+        return 0.0, 12.0 * a[0]
     if name in ('sn_nchw_to_nhwc', 'sn_nhwc_to_nchw'):
-        return 'bytes', 8.0 * a[0] * a[1] * a[2] * a[3]
-    return 'bytes', 0.0
+        return 0.0, 8.0 * a[0] * a[1] * a[2] * a[3]
+    return 0.0, 0.0
+
+
+def ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+    `ncu --set full` capture, keyed like the kernel table; see profiles/README.md."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def roofline_from_profile(summary, precision, pk):
-    """Pick the kernel class with the largest share of the step and report it against its roof."""
+    """Pick the kernel class with the largest share of the step and report it against its roof: the
+    tensor pipe if its flops at the tensor peak take longer than its bytes at the HBM peak, else HBM."""
     rows = []
     total = 0.0
     for (name, a), ms_list in summary.items():
         ms = float(np.mean(ms_list))
-        kind, amount = kernel_work(name, a, precision)
-        rows.append(dict(name=name, args=list(a), ms=ms, launches=len(ms_list), kind=kind, work=amount))
+        flops, byt = kernel_work(name, a, precision)
+        # the roof of the kernel that actually ran: bf16 entry points against the bf16 peak, the
+        # fp32-pointer tensor kernels (tf32) against half of it (also the reference point of the fp32 tier)
+        tensor_peak = pk['bf16'] if '_bf16' in name else pk['bf16'] / 2
+        t_tensor, t_hbm = flops / (tensor_peak * 1e12), byt / (pk['hbm'] * 1e9)
+        kind = 'flops' if t_tensor > t_hbm else 'bytes'
+        rows.append(dict(name=name, args=list(a), ms=ms, launches=len(ms_list), kind=kind, work=flops if kind == 'flops' else byt,
+                         flops=flops, bytes=byt, tensor_peak=tensor_peak))
         total += float(np.sum(ms_list))
     rows.sort(key=lambda r: -r['ms'] * r['launches'])
     for r in rows:
         r['share'] = r['ms'] * r['launches'] / total if total else 0.0
     top = rows[0]
     if top['kind'] == 'flops':
-        # the roof of the kernel that actually ran: bf16 entry points against the bf16 peak, the
-        # fp32-pointer tensor kernels (tf32) against half of it
-        tensor_peak = pk['bf16'] if top['name'].endswith('_bf16') else {'fp32': None, 'tf32': pk['bf16'] / 2, 'bf16': pk['bf16'] / 2}[precision]
-        achieved = top['work'] / (top['ms'] * 1e-3) / 1e12
-        if tensor_peak is None:
-            # CUDA-core tier: there is no tensor-pipe roof; report against the TF32 tensor roof it competes with
-            tensor_peak = pk['bf16'] / 2
-        roof = dict(bound='tensor', achieved=achieved, peak=tensor_peak, unit='TFLOP/s', frac=achieved / tensor_peak)
+        achieved = top['flops'] / (top['ms'] * 1e-3) / 1e12
+        roof = dict(bound='tensor', achieved=achieved, peak=top['tensor_peak'], unit='TFLOP/s', frac=achieved / top['tensor_peak'])
     else:
-        achieved = top['work'] / (top['ms'] * 1e-3) / 1e9
+        achieved = top['bytes'] / (top['ms'] * 1e-3) / 1e9
         roof = dict(bound='hbm', achieved=achieved, peak=pk['hbm'], unit='GB/s', frac=achieved / pk['hbm'])
+    key = '%s|%s|%s' % (precision, top['name'], ','.join(str(v) for v in top['args'][:4]))
     roof.update(kernel=top['name'], kernel_args=top['args'], kernel_ms=top['ms'], share_of_step=top['share'],
-                traffic=None, peak_source=pk['source'])
+                traffic=ncu_traffic().get(key), peak_source=pk['source'])
     return roof, rows
 
 
@@ -352,6 +372,10 @@ def run_ours(args):
     launches_per_step = int(lib.sn_launch_count())
     lib.start_profiling()
     for _ in range(min(K, 10)):
+        # A few ms of device-side spinning first, so that the host has the whole eager step enqueued
+        # before the GPU reaches it: otherwise entries that launch several kernels get host launch
+        # gaps inside their event brackets whenever the GPU catches up with the Python loop.
+        torch.cuda._sleep(int(1.2e7))
         m._run_step(xs, ys, G)
     summary = lib.stop_profiling()
     m.use_cuda_graph = True
@@ -406,7 +430,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='cfg3', choices=sorted(CONFIGS))
     ap.add_argument('--per-gpu-batch', type=int, default=0)
-    ap.add_argument('--precision', default='tf32', choices=['fp32', 'tf32', 'bf16'])
+    ap.add_argument('--precision', default='bf16', choices=['fp32', 'tf32', 'bf16'])
     ap.add_argument('--kernel-table', default='', help='write the per-kernel CUDA-event table (JSON) here')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
