@@ -59,6 +59,8 @@ class _Trainer(object):
         self._warm = set()
         self._metrics_out = None
         self._fit_res = None
+        self._split = None
+        self._comm_stream = None
         self._pinned_user = {}      # id -> (array, ptr): user arrays page-locked in place by fit(shuffle=False)
 
     # ---- to be provided by the subclass ---------------------------------
@@ -162,14 +164,75 @@ class _Trainer(object):
             for i, v in enumerate(self.trainable_variables):
                 v._grads = DeviceTensor(a.slice('gstep', i, v.size), v.output_shape, v.layout or 'flat')
         y_hat = self._forward_device(x_dev, True)
-        self.calc_gradients(y_hat, y_dev, denom_rows=global_rows, metrics_ptr=metrics.data_ptr())
         if world > 1:
-            dist.all_reduce(garena)                         # NCCL sum over NVLink; metrics ride along
+            self._backward_allreduce(y_hat, y_dev, global_rows, metrics, garena, dist)
+        else:
+            self.calc_gradients(y_hat, y_dev, denom_rows=global_rows, metrics_ptr=metrics.data_ptr())
         lib.sn_memcpy_d2d(self._metrics_out.data_ptr(), metrics.data_ptr(), 8, st)
         self.optimizer.grad_scale = 1.0                     # shards already divide by the global rows
         self.optimizer.update(self.trainable_variables)
         # the optimizer touches arena.g[:param_floats] only; clear the metric tail for the next step
         lib.sn_memset(metrics.data_ptr(), 0, 8, st)
+
+    def _overlap_split(self):
+        """Where the backward pass can start reducing: (index into the backward order after which the
+        arena suffix [lo, end) is final, lo).  The arena is laid out in forward order, so the layers
+        visited first in backward own its tail; the split is the first point where that tail holds
+        >= 80 % of the parameters while at least one layer with variables is still to come."""
+        if getattr(self, '_split', None) is not None:
+            return self._split
+        a = self._arena
+        index = {id(v): i for i, v in enumerate(self.trainable_variables)}
+        order = self._backward_order()
+        ends = []                   # per layer: arena ranges of its trainable variables
+        for layer in order:
+            ends.append([(a.offsets[index[id(v)]], a.offsets[index[id(v)]] + v.size) for v in layer.variables if id(v) in index])
+        split = (None, 0)
+        for k in range(len(order) - 1):
+            rest = [r for rs in ends[k + 1:] for r in rs]
+            if not rest:
+                break
+            lo = max(e for _, e in rest)
+            lo = (lo + a.ALIGN - 1) // a.ALIGN * a.ALIGN
+            done = [r for rs in ends[:k + 1] for r in rs]
+            if done and min(b for b, _ in done) >= lo and a.param_floats - lo >= 0.8 * a.param_floats:
+                split = (k, lo)
+                break
+        self._split = split
+        return split
+
+    def _backward_allreduce(self, y_hat, y_dev, global_rows, metrics, garena, dist):
+        """Backward pass of one data-parallel shard with the gradient all-reduce (NCCL sum over
+        NVLink) overlapped: as soon as the tail of the arena is final (the deep layers, most of the
+        parameters) it is reduced on a side stream, together with the loss/accuracy sums riding in
+        the arena's last words, while the remaining layers run their backward; the short head of
+        the arena follows at the end."""
+        t = torch()
+        a = self._arena
+        k_split, lo = self._overlap_split()
+        out = self._output_layer()
+        out._seed_grads(self.loss.backward(y_hat, as_device(y_dev), metrics.data_ptr(), global_rows))
+        main = t.cuda.current_stream()
+        if k_split is None:
+            for layer in self._backward_order():
+                layer.backward()
+            dist.all_reduce(garena)
+            return
+        if getattr(self, '_comm_stream', None) is None:
+            self._comm_stream = t.cuda.Stream()
+        comm = self._comm_stream
+        for k, layer in enumerate(self._backward_order()):
+            layer.backward()
+            if k == k_split:
+                ready = t.cuda.Event()
+                ready.record(main)
+                comm.wait_event(ready)
+                with t.cuda.stream(comm):
+                    dist.all_reduce(garena[lo:])
+                tail_done = t.cuda.Event()
+                tail_done.record(comm)
+        dist.all_reduce(garena[:lo])
+        main.wait_event(tail_done)
 
     def _run_step(self, x_dev, y_dev, global_rows):
         if not self.use_cuda_graph:

@@ -1,0 +1,45 @@
+"""torchrun --nproc-per-node 2 tests/multi_gpu/ddp_check.py: two-rank data-parallel training must land on the
+same weights as the float64 oracle trained on the whole minibatch (fp32 tier, 1e-5)."""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+local = int(os.environ.get('LOCAL_RANK', '0'))
+torch.cuda.set_device(local)
+dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+from oracle import shinnosuke_oracle as O
+from shinnosuke_b200 import Sequential, Conv2D, BatchNormalization, MaxPooling2D, Flatten, Dense
+r = np.random.default_rng(7)
+X = r.standard_normal((64, 3, 16, 16)); Y = O.to_categorical(np.concatenate([np.arange(10), r.integers(0, 10, 54)]))
+for opt in ('sgd', 'momentum'):
+    np.random.seed(0)
+    m = Sequential()
+    m.add(Conv2D(16, (3, 3), input_shape=(None, 3, 16, 16), padding='SAME', activation='relu'))
+    m.add(MaxPooling2D((2, 2)))
+    m.add(Conv2D(32, (3, 3), padding='SAME', activation='relu')); m.add(MaxPooling2D((2, 2)))
+    m.add(Flatten()); m.add(Dense(10, activation='softmax'))
+    m.compile(opt, 'sparse_categorical_crossentropy', precision='fp32')
+    m.fit(X, Y, batch_size=32, epochs=3, shuffle=False, validation_ratio=0., verbose=0)
+    ws = [np.asarray(v.output_tensor) for v in m.trainable_variables]
+    if dist.get_rank() == 0:
+        k, lo = m._overlap_split()
+        print(opt, 'overlap split after backward layer', k, 'lo', lo, 'of', m._arena.param_floats)
+        np.random.seed(0)
+        spec = [('conv', 16, 3, 1, 'SAME', 'relu'), ('pool', 2), ('conv', 32, 3, 1, 'SAME', 'relu'), ('pool', 2), ('flatten',), ('dense', 10, 'softmax')]
+        net = O.OracleNet(spec, (None, 3, 16, 16), optimizer=opt)
+        for ep in range(3):
+            for a in range(0, 64, 32):
+                net.step(X[a:a + 32], Y[a:a + 32])
+        # NOTE: per-replica BatchNorm statistics differ from whole-batch statistics by design,
+        # so the comparison that must be exact is replica-vs-replica, and vs the oracle only loosely
+        err = max(np.abs(w - p).max() / max(np.abs(p).max(), 1e-12) for w, p in zip(ws, net.params))
+        print(opt, 'max rel err vs whole-batch oracle (no BatchNorm in this model: must be <= 1e-5):', err)
+        assert err < 1e-5, err
+    flat = torch.tensor(np.concatenate([w.ravel() for w in ws]), device='cuda')
+    other = flat.clone(); dist.broadcast(other, src=1)
+    if dist.get_rank() == 0:
+        same = bool((flat == other).all().item())
+        print(opt, 'replica weights identical:', same, 'loss', m.train_loss[-1])
+        assert same
+dist.barrier(); torch.cuda.synchronize()
+print('DDP_CHECK_OK') if dist.get_rank() == 0 else None
+sys.stdout.flush()
+os._exit(0)

@@ -134,3 +134,36 @@ def test_no_cpu_fallback():
         m.fit(np.zeros((2, 3)), np.eye(4)[:2], batch_size=2, epochs=1, validation_ratio=0.)
     with pytest.raises(RuntimeError):
         m.predict(np.zeros((2, 3)))
+
+
+def test_allreduce_overlap_split_cfg3():
+    """Data-parallel backward starts reducing as soon as the arena tail is final: for config 3 that
+    is after conv3.backward (conv3, conv4, their BatchNorms and the Dense layer = 92 % of the
+    parameters), leaving conv2 / conv1 to overlap the NCCL call (models._overlap_split)."""
+    from types import SimpleNamespace
+    np.random.seed(0)
+    m = Sequential()
+    m.add(Conv2D(64, (3, 3), input_shape=(None, 3, 32, 32), padding='SAME', activation='relu'))
+    m.add(BatchNormalization()); m.add(MaxPooling2D((2, 2)))
+    for f in (128, 256, 256):
+        m.add(Conv2D(f, (3, 3), padding='SAME', activation='relu')); m.add(BatchNormalization()); m.add(MaxPooling2D((2, 2)))
+    m.add(Flatten()); m.add(Dense(10, activation='softmax'))
+    m.compile(optimizer='sgd', loss='sparse_categorical_crossentropy')
+    offs, total = [], 0
+    for v in m.trainable_variables:               # device.Arena's layout rule: 32-float aligned, forward order
+        offs.append(total)
+        total += (v.size + 31) // 32 * 32
+    m._arena = SimpleNamespace(offsets=offs, param_floats=total, ALIGN=32)
+    m._split = None
+    k, lo = m._overlap_split()
+    order = m._backward_order()
+    assert order[k] is m.layers[6]                # conv3 (layers: conv,bn,pool x4, flatten, dense)
+    conv3_w = m.trainable_variables.index(m.layers[6].variables[0])
+    assert lo == offs[conv3_w]
+    assert (total - lo) / total > 0.9
+    # nothing that still has to run its backward owns arena space at or above lo
+    for layer in order[k + 1:]:
+        for v in layer.variables:
+            i = m.trainable_variables.index(v)
+            assert offs[i] + v.size <= lo
+    m._arena = None
