@@ -123,12 +123,18 @@ class ClockSampler(object):
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         self.p = None
 
-    def start(self):
+    def start(self, wait_s=8.0):
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                       '-lms', '20'], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       '-lms', '10'], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+            return
+        # nvidia-smi needs a while to come up (seconds on an 8-GPU box): the timed region is only tens
+        # of milliseconds long, so do not enter it before the first sample has been written
+        t0 = time.time()
+        while time.time() - t0 < wait_s and os.path.getsize(self.f.name) == 0:
+            time.sleep(0.02)
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
@@ -338,7 +344,8 @@ def run_ours(args):
     # warm-up: same call, same arrays (captures the step graphs, page-locks the host arrays once)
     m.fit(Xt, Yt, batch_size=G, epochs=1, shuffle=False, validation_ratio=0., verbose=0)
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
