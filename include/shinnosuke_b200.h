@@ -180,6 +180,17 @@ SN_API int sn_dense_dgrad(const float *dy, const float *w, float *dx,
 SN_API int sn_dense_wgrad(const float *x, const float *dy, float *dw, float *db,
                    int M, int K, int Nout, int accumulate, int precision, void *stream);
 
+/* The classifier head: Dense with 1 <= n_out <= 16 (every BASELINE config ends in Dense(10, softmax)),
+ * far too thin for GEMM tiles.  fprop = x.W + b with an optional row softmax (layers/FC.py:124-134,
+ * utils/Activator.py:108-110) in one launch; bwd = dW += x^T.dZ, db += sum dZ, dX (=|+=) dZ.W^T
+ * (layers/FC.py:140-153) in one launch that reads x once.  Any of dw / db / dx may be NULL. */
+SN_API int sn_dense_head_supported(int M, int K, int Nout);
+SN_API int sn_dense_head_fprop(const float *x, const float *w, const float *bias, float *out,
+                        int M, int K, int Nout, int softmax, void *stream);
+SN_API int sn_dense_head_bwd(const float *x, const float *dz, const float *w, float *dw, float *db, float *dx,
+                      int M, int K, int Nout, int accumulate_dx, void *stream);
+
+
 /* ---------------------------------------------------------- MaxPooling2D */
 /* MaxPooling2D.forward, layers/Convolution.py:287-324.  x NHWC (N,H,W,C) -> y (N,oh,ow,C),
  * oh = (H-pool)/stride+1 (floor).  `code` (one byte per output element, order (n,i,j,c)) is

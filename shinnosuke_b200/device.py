@@ -11,6 +11,12 @@ layout tag saying how that logical tensor is stored:
     'nhwc'    : logical (N, C, H, W)         stored as [N][H][W][C]
     'krsc'    : logical (F, C, kh, kw)       stored as [F][kh][kw][C]
     'dense_w' : logical (n_in, n_out)        stored as [n_out][n_in]
+
+and two parametrised layouts (tuples) that let Flatten hand an NHWC map to the Dense behind it
+without a transpose kernel (the reference flattens NCHW in (c,i,j) order, layers/FC.py:39-48):
+
+    ('flat_hwc', C, H, W)    : logical (N, C*H*W) in (c,i,j) order    stored as [N][H][W][C]
+    ('dense_w_hwc', C, H, W) : logical (C*H*W, n_out), rows (c,i,j)   stored as [n_out][H][W][C]
 """
 import ctypes
 
@@ -62,6 +68,12 @@ def _to_storage(arr, layout):
         a = a.transpose(0, 2, 3, 1)
     elif layout == 'dense_w':
         a = a.T
+    elif isinstance(layout, tuple) and layout[0] == 'flat_hwc':
+        _, c, h, w = layout
+        a = a.reshape(a.shape[0], c, h, w).transpose(0, 2, 3, 1)
+    elif isinstance(layout, tuple) and layout[0] == 'dense_w_hwc':
+        _, c, h, w = layout
+        a = a.T.reshape(a.shape[1], c, h, w).transpose(0, 2, 3, 1)
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
@@ -75,6 +87,13 @@ def _from_storage(a, shape, layout):
     elif layout == 'dense_w':
         n_in, n_out = shape
         a = a.reshape(n_out, n_in).T
+    elif isinstance(layout, tuple) and layout[0] == 'flat_hwc':
+        _, c, h, w = layout
+        a = a.reshape(shape[0], h, w, c).transpose(0, 3, 1, 2).reshape(shape)
+    elif isinstance(layout, tuple) and layout[0] == 'dense_w_hwc':
+        _, c, h, w = layout
+        n_in, n_out = shape
+        a = a.reshape(n_out, h, w, c).transpose(0, 3, 1, 2).reshape(n_out, n_in).T
     else:
         a = a.reshape(shape)
     return np.ascontiguousarray(a, dtype=np.float64)

@@ -85,6 +85,22 @@ class Variable(object):
             self._grads = DeviceTensor.zeros(self.output_shape, layout)
         return self._dev
 
+    def relayout(self, layout):
+        """Change the device storage order (before or after placement; the logical value is kept)."""
+        if layout == self.layout:
+            return
+        if self._dev is not None:
+            self._host = self._dev.numpy()
+            grads = self._grads.numpy() if self._grads is not None else None
+            self.layout = layout
+            self._dev = DeviceTensor(self._dev.buf, self.output_shape, layout)
+            self._dev.set(self._host)
+            if self._grads is not None:
+                self._grads = DeviceTensor(self._grads.buf, self.output_shape, layout)
+                self._grads.set(grads)
+        else:
+            self.layout = layout
+
     def to_host(self):
         """Pull the current value back into the host copy (pickling, inspection)."""
         if self._dev is not None:

@@ -37,7 +37,12 @@ class Flatten(Layer):
         order of the next Dense's weights; the device map is NHWC, so this is a real transpose."""
         x = self.input_tensor
         self.input_shape = x.shape
-        if x.ndim == 4:
+        if x.ndim == 4 and getattr(self, '_hwc_passthrough', False):
+            # the only consumer is a Dense whose weight rows are stored in (i,j,c) order (set up by
+            # compile()): the NHWC map IS its input, no transpose kernel either way
+            N, C, H, W = x.shape
+            y = x.view((N, C * H * W), ('flat_hwc', C, H, W))
+        elif x.ndim == 4:
             N, C, H, W = x.shape
             y = self._buf('out', (N, C * H * W), 'flat')
             lib.sn_nhwc_to_nchw(x.ptr, y.ptr, N, C, H, W, 0, current_stream())
@@ -45,13 +50,26 @@ class Flatten(Layer):
             y = x.view((x.shape[0], int(np.prod(x.shape[1:]))))
         self.output_tensor = y
         super(Flatten, self).forward(is_training)
+        self._grads_alias = None
+        if is_training and self.require_grads and isinstance(y.layout, tuple) and len(self.inbounds) == 1:
+            prev = self.inbounds[0]
+            if prev.require_grads and len(prev.outbound_layers) == 1 and prev.grads is not None:
+                # our gradient buffer IS the producer's: the Dense behind us writes dX straight into it
+                self.grads = prev.grads.view(y.shape, y.layout)
+                self._grads_alias = prev
 
     def backward(self):
         """layers/FC.py:53-58."""
         g = self.grads
         st = current_stream()
+        if getattr(self, '_grads_alias', None) is not None:
+            self._grads_alias._grads_written = True      # nothing to move
+            return
         for layer in self.inbounds:
-            if len(self.input_shape) == 4:
+            if len(self.input_shape) == 4 and isinstance(g.layout, tuple) and g.layout[0] == 'flat_hwc':
+                def writer(dst, acc):                   # the gradient already is the NHWC map
+                    dst.add_(g) if acc else dst.copy_from(g)
+            elif len(self.input_shape) == 4:
                 N, C, H, W = self.input_shape
 
                 def writer(dst, acc):
@@ -112,6 +130,16 @@ class Dense(Layer):
             raise NotImplementedError('Dense on the device supports linear/relu/softmax (got %s)' % name)
         return name
 
+    def _use_hwc_rows(self, c, h, w):
+        """compile() hook: the Flatten in front of this layer passes its NHWC map through, so the
+        weight rows (and their gradients) are stored in (i,j,c) order on the device."""
+        Wv = self.variables[0]
+        assert Wv.output_shape[0] == c * h * w
+        Wv.relayout(('dense_w_hwc', c, h, w))
+
+    def _head(self, M, K):
+        return self._act_name() in ('linear', 'softmax') and bool(lib.load().sn_dense_head_supported(M, K, self.n_out))
+
     def forward(self, is_training=True):
         """layers/FC.py:124-134."""
         W, b = self._param_ptrs()
@@ -119,8 +147,21 @@ class Dense(Layer):
         if x.ndim != 2:
             raise NotImplementedError('Dense on the device takes (N, features) inputs')
         M, K = x.shape
+        hwc_w = isinstance(W.output_tensor.layout, tuple)
+        hwc_x = isinstance(x.layout, tuple)
+        if hwc_w != hwc_x or (hwc_w and tuple(W.output_tensor.layout[1:]) != tuple(x.layout[1:])):
+            raise RuntimeError('Dense: input feature order %r does not match the weight row order %r'
+                               % (x.layout, W.output_tensor.layout))
         act = self._act_name()
         st = current_stream()
+        if self._head(M, K):
+            # thin classifier head (n_out <= 16): one launch for x.W + b (+ softmax), csrc/dense_head.cu
+            out = self._buf('probs' if act == 'softmax' else 'out', (M, self.n_out), 'flat')
+            lib.sn_dense_head_fprop(x.ptr, W.output_tensor.ptr, b.output_tensor.ptr, out.ptr, M, K, self.n_out,
+                                    1 if act == 'softmax' else 0, st)
+            self.output_tensor = out
+            super(Dense, self).forward(is_training)
+            return
         z = self._buf('out', (M, self.n_out), 'flat')
         lib.sn_dense_fprop(x.ptr, W.output_tensor.ptr, b.output_tensor.ptr, z.ptr, M, K, self.n_out,
                            ACT['relu'] if act == 'relu' else ACT['linear'], PRECISION[self.precision], st)
@@ -141,6 +182,23 @@ class Dense(Layer):
         prec = PRECISION[self.precision]
         if self._act_name() == 'relu' and not self._grads_premasked:
             lib.sn_relu_bwd(g.ptr, self.output_tensor.ptr, g.size, st)
+        if self._head(M, K):
+            # dW += x^T.dZ, db += sum dZ and dX in ONE launch that reads x once
+            dw = W.grads.ptr if W.require_grads else None
+            db = b.grads.ptr if b.require_grads else None
+            targets = [layer for layer in self.inbounds if layer.require_grads]
+            if not targets:
+                if dw is not None or db is not None:
+                    lib.sn_dense_head_bwd(x.ptr, g.ptr, W.output_tensor.ptr, dw, db, None, M, K, self.n_out, 0, st)
+                return
+            for i, layer in enumerate(targets):
+                first = i == 0
+
+                def writer(dst, acc, first=first):
+                    lib.sn_dense_head_bwd(x.ptr, g.ptr, W.output_tensor.ptr, dw if first else None, db if first else None,
+                                          dst.ptr, M, K, self.n_out, acc, st)
+                self._push_grad(layer, writer)
+            return
         if W.require_grads or b.require_grads:
             lib.sn_dense_wgrad(x.ptr, g.ptr, W.grads.ptr, b.grads.ptr if b.require_grads else None,
                                M, K, self.n_out, 1, prec, st)

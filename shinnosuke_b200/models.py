@@ -98,6 +98,18 @@ class _Trainer(object):
                 if isinstance(prev, Conv2D):
                     feeds = fuse and precision != 'fp32' and len(prev.outbound_layers) == 1
                     prev._stats_to = layer if feeds else None
+        # Flatten -> Dense with nobody else on either side: the NHWC map is handed through as it is and
+        # the Dense keeps its weight rows in (i,j,c) order (no transpose kernel forward or backward)
+        from .layers.FC import Flatten, Dense
+        for layer in self._forward_order():
+            if isinstance(layer, Flatten):
+                nxt = layer.outbound_layers[0] if len(layer.outbound_layers) == 1 else None
+                shp = layer.inbounds[0].output_shape if len(layer.inbounds) == 1 else None
+                ok = (fuse and isinstance(nxt, Dense) and len(nxt.inbounds) == 1 and shp is not None and len(shp) == 4
+                      and shp[2] * shp[3] > 1 and shp[1] > 1)
+                layer._hwc_passthrough = bool(ok)
+                if isinstance(nxt, Dense) and len(nxt.inbounds) == 1 and shp is not None and len(shp) == 4:
+                    nxt.variables[0].relayout(('dense_w_hwc',) + tuple(int(v) for v in shp[1:]) if ok else 'dense_w')
         self.loss = get_objective(loss)
         self.optimizer = get_optimizer(optimizer)
 
