@@ -126,7 +126,14 @@ struct IgemmParams {
 constexpr int STAT_MAX_F = 512;
 constexpr int STAT_BYTES = 4 * 2 * STAT_MAX_F * 4;          // [epilogue warp][{sum, sumsq}][STAT_MAX_F]
 
-constexpr int EPI_STAGE_BYTES = 4 * 4096;       // one 32-row x 128-byte staging tile per epilogue warp
+// Epilogue: EPI_WARPS warps, two per TMEM lane quarter (a warp may only read the quarter
+// warp_id % 4), alternating over the 32-column chunks of the tile.  One epilogue warp per scheduler
+// is a ~300-instruction dependent chain per chunk (~2300 cycles): with four warps the epilogue of a
+// 128x128 tile (9150 cycles) took twice the tile's operand ingest, and the profile showed the
+// epilogue warps never waiting.
+constexpr int EPI_WARPS = 8;
+constexpr int IG_THREADS = 64 + 32 * EPI_WARPS;         // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 4096;       // one 32-row x 128-byte staging tile per epilogue warp
 
 // KS = k-blocks (128-byte K slabs) per pipeline stage.  A stage must carry enough MMA time
 // (KS * 128*BN*32 / 2048 cycles) to amortise the per-stage barrier round trips of the single
@@ -135,7 +142,9 @@ template <int BN, int KS> struct IgemmCfg {
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int SLAB_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGE_BYTES = KS * SLAB_BYTES;
-    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+    static constexpr int RING_BUDGET = 232448 - (EPI_STAGE_BYTES + STAT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/);
+    static constexpr int STAGES = RING_BUDGET / STAGE_BYTES > 8 ? 8 : RING_BUDGET / STAGE_BYTES;
+    static_assert(STAGES >= 3, "pipeline too shallow: use KS = 1 for this tile width");
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;      // power of two >= 32
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + STAT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -143,7 +152,7 @@ template <int BN, int KS> struct IgemmCfg {
 // BF16: the operands are bf16 copies (64 elements per 128-byte row, UMMA K = 16, kind::f16); the
 // accumulators, bias, activation and output stay fp32.  Byte geometry of the tiles is identical.
 template <int BN, int KS, bool BF16>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(IG_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const IgemmParams p) {
     using Cfg = IgemmCfg<BN, KS>;
@@ -168,7 +177,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -176,7 +185,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tmem_relinquish();
     }
     if (p.stats)
-        for (int i = threadIdx.x; i < 4 * 2 * STAT_MAX_F; i += NUM_THREADS) sstat[i] = 0.f;
+        for (int i = threadIdx.x; i < 4 * 2 * STAT_MAX_F; i += IG_THREADS) sstat[i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -251,6 +260,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                  // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;        // which of the quarter's two warps: even or odd chunks
         int iter = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
             const int tm = tile / p.tiles_n, tn_idx = tile % p.tiles_n;
@@ -262,7 +272,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             float *orow = p.out + (long long)row * p.F;
             constexpr int CHUNK = (BN >= 32) ? 32 : 16;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += CHUNK) {
+            for (int c0 = half * CHUNK; c0 < BN; c0 += 2 * CHUNK) {
                 uint32_t r[CHUNK];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
                 if constexpr (CHUNK == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
@@ -273,7 +283,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         // bias / ReLU in registers, then this warp's 32 rows x 32 columns go to its staging
                         // tile in the 128-byte-swizzled layout of the output tensor map, and ONE TMA store
                         // writes them as full 128-byte lines (rows / columns past the tensor are clipped)
-                        uint8_t *st = epi_stage + q * 4096;
+                        uint8_t *st = epi_stage + (warp - 2) * 4096;
                         if (lane == 0) tma_store_wait_read();           // previous store has drained the tile
                         __syncwarp();
 #pragma unroll
@@ -337,9 +347,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (p.tma_store && lane == 0) tma_store_wait_all();
         __syncwarp();
         if (p.stats) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");           // the four epilogue warps only
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");           // the epilogue warps only
             double *slot = p.stats + (size_t)(blockIdx.x % BN_SLOTS) * 2 * p.F;
-            for (int f = threadIdx.x - 64; f < p.F; f += 128) {
+            for (int f = threadIdx.x - 64; f < p.F; f += 32 * EPI_WARPS) {
                 double s1 = 0.0, s2 = 0.0;
 #pragma unroll
                 for (int wq = 0; wq < 4; ++wq) { s1 += (double)sstat[wq * 2 * STAT_MAX_F + f]; s2 += (double)sstat[(wq * 2 + 1) * STAT_MAX_F + f]; }
@@ -601,15 +611,17 @@ int launch_igemm_ks(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtens
     }
     int tiles = p.tiles_m * p.tiles_n;
     int grid = tiles < num_sms() ? tiles : num_sms();
-    conv_igemm_kernel<BN, KS, BF16><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmO, p);
+    conv_igemm_kernel<BN, KS, BF16><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmO, p);
     return after_launch("conv_igemm_kernel");
 }
 template <int BN>
 int launch_igemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO, const IgemmParams &p, bool bf16, cudaStream_t st) {
     const int kblocks = p.ntaps * p.cblocks;
-    const bool ks2 = BN <= 128 && (kblocks % 2) == 0;
-    if (bf16) return ks2 ? launch_igemm_ks<BN, 2, true>(tmA, tmB, tmO, p, st) : launch_igemm_ks<BN, 1, true>(tmA, tmB, tmO, p, st);
-    return ks2 ? launch_igemm_ks<BN, 2, false>(tmA, tmB, tmO, p, st) : launch_igemm_ks<BN, 1, false>(tmA, tmB, tmO, p, st);
+    if constexpr (BN <= 64) {             // (a 2-slab stage of a 128-wide tile would leave only 2 ring stages)
+        if ((kblocks % 2) == 0)
+            return bf16 ? launch_igemm_ks<BN, 2, true>(tmA, tmB, tmO, p, st) : launch_igemm_ks<BN, 2, false>(tmA, tmB, tmO, p, st);
+    }
+    return bf16 ? launch_igemm_ks<BN, 1, true>(tmA, tmB, tmO, p, st) : launch_igemm_ks<BN, 1, false>(tmA, tmB, tmO, p, st);
 }
 
 }  // namespace

@@ -5,8 +5,9 @@
 // that read x once each:
 //
 //   forward   (layers/FC.py:124-134 + utils/Activator.py:108-110)
-//             one warp per row: lanes stride over K (coalesced), n_out accumulators per lane,
-//             butterfly reduction, bias, softmax in registers.
+//             block = 4 rows x all K: 256 threads stride over feature quads (coalesced 128-bit loads,
+//             every W element fetched serves 4 rows), shuffle + shared-memory reduction, bias,
+//             softmax by one warp per row.
 //   backward  (layers/FC.py:140-153)
 //             block = 32 features x a slice of the rows; dZ lives in shared memory; a thread owns one
 //             feature column: dX[r][k] = sum_o dZ[r][o]*W[o][k] is written on the fly while
@@ -20,54 +21,79 @@ namespace {
 
 constexpr int MAXO = 16;
 
+constexpr int HF_ROWS = 4;         // rows per block: each W element fetched by a thread serves 4 rows
+
+// block = 4 rows x all K: thread t owns the feature quads {t, t+256, ...}; 4*O partial sums per thread,
+// reduced by shuffles inside the warps and through shared memory across them
 template <int O>
 __global__ void __launch_bounds__(256) dense_head_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                              const float *__restrict__ bias, float *__restrict__ out, int M, int K,
                                                              int softmax) {
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= M) return;
-    const float *xr = x + (long long)row * K;
-    float acc[O];
+    __shared__ float sred[8][HF_ROWS][O];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * HF_ROWS;
+    float acc[HF_ROWS][O];
 #pragma unroll
-    for (int o = 0; o < O; ++o) acc[o] = 0.f;
+    for (int r = 0; r < HF_ROWS; ++r)
+#pragma unroll
+        for (int o = 0; o < O; ++o) acc[r][o] = 0.f;
+    const float *xr[HF_ROWS];
+#pragma unroll
+    for (int r = 0; r < HF_ROWS; ++r) xr[r] = x + (long long)min(r0 + r, M - 1) * K;      // clamped: extra rows are discarded below
     if ((K & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)w)) & 15) == 0) {
-        for (int k = lane * 4; k < K; k += 128) {
-            const float4 xv = __ldg(reinterpret_cast<const float4 *>(xr + k));
+        for (int k = threadIdx.x * 4; k < K; k += 1024) {
+            float4 xv[HF_ROWS];
+#pragma unroll
+            for (int r = 0; r < HF_ROWS; ++r) xv[r] = __ldg(reinterpret_cast<const float4 *>(xr[r] + k));
 #pragma unroll
             for (int o = 0; o < O; ++o) {
                 const float4 wv = __ldg(reinterpret_cast<const float4 *>(w + (long long)o * K + k));
-                acc[o] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[o]))));
+#pragma unroll
+                for (int r = 0; r < HF_ROWS; ++r)
+                    acc[r][o] = fmaf(xv[r].x, wv.x, fmaf(xv[r].y, wv.y, fmaf(xv[r].z, wv.z, fmaf(xv[r].w, wv.w, acc[r][o]))));
             }
         }
     } else {
-        for (int k = lane; k < K; k += 32) {
-            const float xv = __ldg(xr + k);
+        for (int k = threadIdx.x; k < K; k += 256) {
+            float xv[HF_ROWS];
 #pragma unroll
-            for (int o = 0; o < O; ++o) acc[o] = fmaf(xv, __ldg(w + (long long)o * K + k), acc[o]);
+            for (int r = 0; r < HF_ROWS; ++r) xv[r] = __ldg(xr[r] + k);
+#pragma unroll
+            for (int o = 0; o < O; ++o) {
+                const float wv = __ldg(w + (long long)o * K + k);
+#pragma unroll
+                for (int r = 0; r < HF_ROWS; ++r) acc[r][o] = fmaf(xv[r], wv, acc[r][o]);
+            }
         }
     }
 #pragma unroll
-    for (int o = 0; o < O; ++o) {
+    for (int r = 0; r < HF_ROWS; ++r)
 #pragma unroll
-        for (int s = 16; s; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
-        if (bias) acc[o] += __ldg(bias + o);
+        for (int o = 0; o < O; ++o) {
+#pragma unroll
+            for (int s = 16; s; s >>= 1) acc[r][o] += __shfl_xor_sync(0xffffffffu, acc[r][o], s);
+            if (lane == 0) sred[wid][r][o] = acc[r][o];
+        }
+    __syncthreads();
+    // warp r finishes row r: lane o sums the 8 warps' partials of logit o
+    if (wid < HF_ROWS && r0 + wid < M) {
+        float z = -INFINITY;
+        if (lane < O) {
+            z = bias ? __ldg(bias + lane) : 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) z += sred[q][wid][lane];
+        }
+        if (softmax) {
+            float m = z;
+#pragma unroll
+            for (int s = 16; s; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+            float e = lane < O ? expf(z - m) : 0.f, t = e;
+#pragma unroll
+            for (int s = 16; s; s >>= 1) t += __shfl_xor_sync(0xffffffffu, t, s);
+            z = e / t;
+        }
+        if (lane < O) out[(long long)(r0 + wid) * O + lane] = z;
     }
-    if (softmax) {
-        float m = acc[0];
-#pragma unroll
-        for (int o = 1; o < O; ++o) m = fmaxf(m, acc[o]);
-        float s = 0.f;
-#pragma unroll
-        for (int o = 0; o < O; ++o) { acc[o] = expf(acc[o] - m); s += acc[o]; }
-        const float inv = 1.f / s;
-#pragma unroll
-        for (int o = 0; o < O; ++o) acc[o] *= inv;
-    }
-    // every lane holds the full row; lane o writes element o
-#pragma unroll
-    for (int o = 0; o < O; ++o)
-        if (lane == o) out[(long long)row * O + o] = acc[o];
 }
 
 constexpr int HB_FEATS = 32;       // features per block (one warp-wide coalesced line of x / dX)
@@ -127,7 +153,7 @@ __global__ void __launch_bounds__(256) dense_head_bwd_kernel(const float *__rest
 
 template <int O>
 int launch_fwd(const float *x, const float *w, const float *bias, float *out, int M, int K, int softmax, cudaStream_t st) {
-    dense_head_fwd_kernel<O><<<(M + 7) / 8, 256, 0, st>>>(x, w, bias, out, M, K, softmax);
+    dense_head_fwd_kernel<O><<<(M + HF_ROWS - 1) / HF_ROWS, 256, 0, st>>>(x, w, bias, out, M, K, softmax);
     return after_launch("dense_head_fwd_kernel");
 }
 template <int O>
