@@ -24,6 +24,9 @@ int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, float 
                        int kw, int stride, int ph, int pw, int act, double *stats, cudaStream_t st);
 int conv_stem_wgrad_tc(const float *x, const float *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh, int kw,
                        int stride, int ph, int pw, cudaStream_t st);
+bool tiny_wgrad_eligible(int C, int kh, int kw, int F);
+int conv_wgrad_tiny(const float *x, const float *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh,
+                    int kw, int stride, int ph, int pw, cudaStream_t st);
 bool direct_fprop_eligible(int C, int kh, int kw, int F);
 bool direct_wgrad_eligible(int C, int kh, int kw, int F);
 int conv_fprop_direct(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F,
@@ -131,6 +134,15 @@ int sn_conv2d_wgrad(const float *x, const float *dy, float *dw, float *db, int N
             if (db) SN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * F, st));
         }
         return conv_stem_wgrad_tc(x, dy, dw, db, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, st);
+    }
+    if (geom_ok && tiny_wgrad_eligible(C, kh, kw, F) && (long long)N * H * W * C < (1ll << 31) &&
+        (long long)N * F * ((H + 2 * pad_h - kh) / stride + 1) * ((W + 2 * pad_w - kw) / stride + 1) < (1ll << 31)) {
+        cudaStream_t st = as_stream(stream);
+        if (!accumulate) {
+            SN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)F * kh * kw * C, st));
+            if (db) SN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * F, st));
+        }
+        return conv_wgrad_tiny(x, dy, dw, db, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, st);
     }
     if (geom_ok && (((uintptr_t)dy) & 15) == 0 && direct_wgrad_eligible(C, kh, kw, F)) {
         cudaStream_t st = as_stream(stream);

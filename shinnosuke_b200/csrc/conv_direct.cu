@@ -194,6 +194,75 @@ __global__ void __launch_bounds__(128) direct_wgrad_kernel(DirectP p, int pix_pe
     }
 }
 
+// ---------------------------------------------------------------------------------- tiny wgrad
+// F <= FT filters and K <= KT taps (config 1: F = 8, K = 4): dW and db together are a few dozen
+// numbers, so every thread keeps ALL of them in registers and streams pixels (two 128-bit loads of
+// dY, K scalar gathers of x per pixel); warps fold with shuffles, the block through shared memory,
+// one atomic per output per block.  One wave of blocks: each output sees <= #SM same-address atomics.
+template <int FT, int KT>
+__global__ void __launch_bounds__(256) tiny_wgrad_kernel(DirectP p) {
+    float acc[FT][KT + 1];
+#pragma unroll
+    for (int f = 0; f < FT; ++f)
+#pragma unroll
+        for (int k = 0; k <= KT; ++k) acc[f][k] = 0.f;
+    const int P = (int)p.P, kwC = p.kw * p.C;
+    const bool vec = (p.F & 3) == 0 && (((uintptr_t)p.dy) & 15) == 0;
+    for (int pix = blockIdx.x * 256 + threadIdx.x; pix < P; pix += gridDim.x * 256) {
+        const int t = pix / p.ow, j = pix - t * p.ow, n = t / p.oh, i = t - n * p.oh;
+        float d[FT];
+        const float *dyp = p.dy + (long long)pix * p.F;
+        if (vec) {
+#pragma unroll
+            for (int f = 0; f < FT; f += 4) {
+                float4 v = f < p.F ? ldg4(dyp + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+                d[f] = v.x; d[f + 1] = v.y; d[f + 2] = v.z; d[f + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int f = 0; f < FT; ++f) d[f] = f < p.F ? __ldg(dyp + f) : 0.f;
+        }
+        const int hb = i * p.stride - p.ph, wb = j * p.stride - p.pw;
+        const float *xb = p.x + (long long)n * p.H * p.W * p.C;
+        int u = 0, r = 0;                 // k = u*kw*C + r, r = v*C + c
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            float xv = 0.f;
+            if (k < p.K) {
+                const int v = r / p.C, c = r - v * p.C, h = hb + u, w = wb + v;
+                if ((unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W) xv = __ldg(xb + (h * p.W + w) * p.C + c);
+            }
+#pragma unroll
+            for (int f = 0; f < FT; ++f) acc[f][k] = fmaf(d[f], xv, acc[f][k]);
+            if (++r == kwC) { r = 0; ++u; }
+        }
+#pragma unroll
+        for (int f = 0; f < FT; ++f) acc[f][KT] += d[f];
+    }
+    __shared__ float red[8][FT * (KT + 1)];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int f = 0; f < FT; ++f)
+#pragma unroll
+        for (int k = 0; k <= KT; ++k) {
+            float v = acc[f][k];
+#pragma unroll
+            for (int s = 16; s; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+            if (lane == 0) red[wid][f * (KT + 1) + k] = v;
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < FT * (KT + 1); i += 256) {
+        const int f = i / (KT + 1), k = i - f * (KT + 1);
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v += red[q][i];
+        if (f < p.F) {
+            if (k < p.K) atomicAdd(p.dw + (long long)f * p.K + k, v);
+            else if (k == KT && p.db) atomicAdd(p.db + f, v);
+        }
+    }
+}
+
 }  // namespace
 
 namespace sn {
@@ -247,6 +316,27 @@ int conv_wgrad_direct(const float *x, const float *dy, float *dw, float *db, int
     dim3 grid((unsigned)bx, fy);
     direct_wgrad_kernel<<<grid, 128, 0, st>>>(p, (int)ppb);
     return after_launch("direct_wgrad_kernel");
+}
+
+bool tiny_wgrad_eligible(int C, int kh, int kw, int F) {
+    const int K = C * kh * kw;
+    return (F <= 8 && K <= 9) || (F <= 16 && K <= 4);
+}
+// dw/db are accumulated into (+=).
+int conv_wgrad_tiny(const float *x, const float *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh,
+                    int kw, int stride, int ph, int pw, cudaStream_t st) {
+    DirectP p{};
+    p.x = x; p.dy = dy; p.dw = dw; p.db = db; p.N = N; p.C = C; p.H = H; p.W = W; p.F = F; p.kh = kh; p.kw = kw;
+    p.stride = stride; p.ph = ph; p.pw = pw;
+    p.oh = (H + 2 * ph - kh) / stride + 1; p.ow = (W + 2 * pw - kw) / stride + 1;
+    p.K = C * kh * kw; p.P = (long long)N * p.oh * p.ow;
+    if (p.P == 0) return SN_OK;
+    long long need = (p.P + 255) / 256;
+    const int grid = (int)(need < num_sms() ? need : num_sms());
+    if (F <= 8 && p.K <= 4) tiny_wgrad_kernel<8, 4><<<grid, 256, 0, st>>>(p);
+    else if (F <= 8) tiny_wgrad_kernel<8, 9><<<grid, 256, 0, st>>>(p);
+    else tiny_wgrad_kernel<16, 4><<<grid, 256, 0, st>>>(p);
+    return after_launch("tiny_wgrad_kernel");
 }
 
 }  // namespace sn

@@ -132,7 +132,7 @@ constexpr int STAT_BYTES = 4 * 2 * STAT_MAX_F * 4;          // [epilogue warp][{
 // 128x128 tile (9150 cycles) took twice the tile's operand ingest, and the profile showed the
 // epilogue warps never waiting.
 constexpr int EPI_WARPS = 8;
-constexpr int IG_THREADS = 64 + 32 * EPI_WARPS;         // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
+constexpr int IG_THREADS = 64 + 32 * EPI_WARPS;         // warp 0: TMA producer, warp 1: MMA issuer, warps 2..: epilogue
 constexpr int EPI_STAGE_BYTES = EPI_WARPS * 4096;       // one 32-row x 128-byte staging tile per epilogue warp
 
 // KS = k-blocks (128-byte K slabs) per pipeline stage.  A stage must carry enough MMA time
@@ -260,7 +260,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                  // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;        // which of the quarter's two warps: even or odd chunks
+        const int half = (warp - 2) >> 2;        // which of the quarter's EPI_WARPS/4 warps: chunks half, half + EPI_WARPS/4, ...
         int iter = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
             const int tm = tile / p.tiles_n, tn_idx = tile % p.tiles_n;
@@ -272,7 +272,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             float *orow = p.out + (long long)row * p.F;
             constexpr int CHUNK = (BN >= 32) ? 32 : 16;
 #pragma unroll 1
-            for (int c0 = half * CHUNK; c0 < BN; c0 += 2 * CHUNK) {
+            for (int c0 = half * CHUNK; c0 < BN; c0 += (EPI_WARPS / 4) * CHUNK) {
                 uint32_t r[CHUNK];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
                 if constexpr (CHUNK == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);

@@ -233,7 +233,10 @@ def test_fused_and_unfused_models_agree():
     # max-pool decision, and each such flip shifts a few first-layer weights by ~2e-4 of max|w|
     # (measured: identical configurations land either at ~5e-6 or at k * 2e-4).  So: the bulk of
     # the weights must agree to 1e-5, and no weight may be further off than a handful of flips.
-    assert np.allclose(runs[0][0], runs[1][0], rtol=5e-5)
+    # (losses: the first two steps agree to rounding; after a flip the later ones move by up to ~1e-3
+    # in this deliberately stiff setting — initial loss 25, lr 0.01)
+    assert np.allclose(runs[0][0][:2], runs[1][0][:2], rtol=2e-5)
+    assert np.allclose(runs[0][0], runs[1][0], rtol=3e-3)
     err = np.abs(runs[0][1] - runs[1][1]) / np.abs(runs[1][1]).max()
     assert np.quantile(err, 0.99) < 1e-5
     assert err.max() < 2e-3
