@@ -289,6 +289,14 @@ SN_API int sn_sgd_update(float *w, float *g, long long n, float lr, float grad_s
  * If gstep != NULL (data-parallel): g += grad_scale*gstep ; gstep = 0 first. */
 SN_API int sn_momentum_update(float *w, float *g, float *v, float *gstep, long long n,
                        float lr, float rho, float grad_scale, void *stream);
+/* RMSprop (kind 0), AdaGrad (1), AdaDelta (2), Adam (3): utils/Optimizers.py:61-157 over a flat
+ * arena.  s1 / s2: state buffers of n floats (s2 for AdaDelta and Adam), zero before the first
+ * step.  p1, p2 = rho / (beta1, beta2).  None of them zeroes g (as in the reference); gstep as in
+ * sn_momentum_update.  tick (Adam only): 3 floats of device memory, zero before the first step,
+ * holding the reference's iteration counter (which advances by two per update) and the two bias
+ * corrections, so that a captured graph of the step stays correct when replayed. */
+SN_API int sn_adaptive_update(int kind, float *w, float *g, float *s1, float *s2, float *gstep, float *tick,
+                       long long n, float lr, float p1, float p2, float eps, float grad_scale, void *stream);
 
 #ifdef __cplusplus
 }

@@ -331,7 +331,7 @@ def scce_backward(y_hat, y):
 
 
 # --------------------------------------------------------------------------
-# optimizers  (utils/Optimizers.py:24-57)
+# optimizers  (utils/Optimizers.py:24-157)
 # --------------------------------------------------------------------------
 
 def sgd_update(params, grads, lr=0.01):
@@ -347,6 +347,43 @@ def momentum_update(params, grads, velocity, lr=0.01, rho=0.9):
     for i in range(len(params)):
         velocity[i] = rho * velocity[i] + (1 - rho) * grads[i]
         params[i] = params[i] - lr * velocity[i]
+
+
+def rmsprop_update(params, grads, ms, lr=0.001, rho=0.9, eps=1e-7):
+    """s <- rho*s + (1-rho)*g^2 ; w <- w - lr*g/sqrt(s+eps) ; g NOT zeroed (utils/Optimizers.py:72-80)."""
+    for i in range(len(params)):
+        ms[i] = rho * ms[i] + (1 - rho) * np.square(grads[i])
+        params[i] = params[i] - lr * grads[i] / np.sqrt(ms[i] + eps)
+
+
+def adagrad_update(params, grads, ms, lr=0.01, eps=1e-7):
+    """s <- s + g^2 ; w <- w - lr*g/sqrt(s+eps) ; g NOT zeroed (utils/Optimizers.py:90-97)."""
+    for i in range(len(params)):
+        ms[i] = ms[i] + np.power(grads[i], 2)
+        params[i] = params[i] - lr * grads[i] / np.sqrt(ms[i] + eps)
+
+
+def adadelta_update(params, grads, ms, dx, rho=0.95, eps=1e-7):
+    """s <- rho*s + (1-rho)*g^2 ; u = sqrt((x+eps)/(s+eps))*g ; w <- w - u ; x <- rho*x + (1-rho)*u^2.
+    `lr` is not used; g NOT zeroed (utils/Optimizers.py:110-123)."""
+    for i in range(len(params)):
+        ms[i] = rho * ms[i] + (1 - rho) * np.power(grads[i], 2)
+        u = np.sqrt((dx[i] + eps) / (ms[i] + eps)) * grads[i]
+        params[i] = params[i] - u
+        dx[i] = rho * dx[i] + (1 - rho) * np.power(u, 2)
+
+
+def adam_update(params, grads, vs, ms, iterations, lr=0.001, beta1=0.9, beta2=0.999, eps=1e-7):
+    """utils/Optimizers.py:138-157.  `iterations` is the counter value AFTER Adam's own `+= 1`
+    (the base class adds another one afterwards, so successive updates see 1, 3, 5, ...):
+    v <- b1*v + (1-b1)*g ; m <- b2*m + (1-b2)*g^2 ;
+    w <- w - lr * (v/(1-b1^it)) / (sqrt(m/(1-b2^it)) + eps) ; g NOT zeroed."""
+    for i in range(len(params)):
+        vs[i] = beta1 * vs[i] + (1 - beta1) * grads[i]
+        ms[i] = beta2 * ms[i] + (1 - beta2) * np.square(grads[i])
+        v_c = vs[i] / (1 - pow(beta1, iterations))
+        m_c = ms[i] / (1 - pow(beta2, iterations))
+        params[i] = params[i] - lr * (v_c / (np.sqrt(m_c) + eps))
 
 
 # --------------------------------------------------------------------------

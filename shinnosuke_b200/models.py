@@ -131,7 +131,9 @@ class _Trainer(object):
         if dist is not None and dist.get_world_size() > 1:
             # replicas must start from identical weights: rank 0's initial values win
             dist.broadcast(arena.w, src=0)
-            if isinstance(self.optimizer, Momentum):
+            if isinstance(self.optimizer, Momentum) or getattr(self.optimizer, 'needs_gstep', False):
+                # optimizers that never zero the gradients: each step's all-reduced gradients go
+                # through gstep and are folded into the persistent arena.g by the update kernel
                 arena.gstep = zeros(arena.total)
         lib.sn_stream_sync(current_stream())
 

@@ -1,4 +1,5 @@
-"""SGD / Momentum on the device (reference: utils/Optimizers.py:8-57).
+"""The reference's optimizers on the device (utils/Optimizers.py:8-157): SGD, Momentum, RMSprop,
+AdaGrad, AdaDelta, Adam.
 
 When the variables live in a model's parameter arena the update is ONE fused kernel over the
 flat arena; stand-alone variables are updated one kernel each.  Bug-compatible details kept:
@@ -72,6 +73,105 @@ class Momentum(Optimizer):
         return d
 
 
+class _Adaptive(Optimizer):
+    """RMSprop / AdaGrad / AdaDelta / Adam share one kernel family (csrc/optimizers.cu).  Like
+    Momentum — and like the reference — they never zero the gradients."""
+    KIND = None
+    TWO_STATES = False
+
+    def _params(self):
+        raise NotImplementedError
+
+    def _state(self, owner, n):
+        st = self.__dict__.setdefault('_states', {})
+        key = (id(owner), n)
+        if key not in st:
+            st[key] = (zeros(n), zeros(n) if self.TWO_STATES else None, zeros(4) if self.KIND == 3 else None, owner)
+        return st[key][:3]
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d['_states'] = {}               # device state is not pickled (the reference pickles its arrays; documented)
+        return d
+
+    def update(self, trainable_variables):
+        st = current_stream()
+        lr, p1, p2, eps = self._params()
+        arena = self._arena(trainable_variables)
+        if arena is not None:
+            s1, s2, tick = self._state(arena, arena.total)
+            gstep = arena.gstep.data_ptr() if arena.gstep is not None else None
+            lib.sn_adaptive_update(self.KIND, arena.w.data_ptr(), arena.g.data_ptr(), s1.data_ptr(),
+                                   s2.data_ptr() if s2 is not None else None, gstep,
+                                   tick.data_ptr() if tick is not None else None, arena.param_floats,
+                                   float(lr), float(p1), float(p2), float(eps), float(self.grad_scale), st)
+        else:
+            for var in trainable_variables:
+                var.ensure_device()
+                s1, s2, tick = self._state(var, var.size)
+                lib.sn_adaptive_update(self.KIND, var.output_tensor.ptr, var.grads.ptr, s1.data_ptr(),
+                                       s2.data_ptr() if s2 is not None else None, None,
+                                       tick.data_ptr() if tick is not None else None, var.size,
+                                       float(lr), float(p1), float(p2), float(eps), 1.0, st)
+        super(_Adaptive, self).update(trainable_variables)
+
+    needs_gstep = True          # data parallel: gradients persist, so each step's go through arena.gstep
+
+
+class RMSprop(_Adaptive):
+    KIND = 0
+
+    def __init__(self, lr=0.001, decay=0.0, rho=0.9, epsilon=1e-7, *args, **kwargs):
+        self.rho = rho
+        self.epsilon = epsilon
+        super(RMSprop, self).__init__(lr, decay)
+
+    def _params(self):
+        return self.lr, self.rho, 0.0, self.epsilon
+
+
+class AdaGrad(_Adaptive):
+    KIND = 1
+
+    def __init__(self, lr=0.01, decay=0.0, epsilon=1e-7):
+        super(AdaGrad, self).__init__(lr, decay)
+        self.epsilon = epsilon
+
+    def _params(self):
+        return self.lr, 0.0, 0.0, self.epsilon
+
+
+class AdaDelta(_Adaptive):
+    KIND = 2
+    TWO_STATES = True
+
+    def __init__(self, decay=0.0, lr=1.0, rho=0.95, epsilon=1e-7):
+        super(AdaDelta, self).__init__(lr, decay)
+        self.rho = rho
+        self.epsilon = epsilon
+
+    def _params(self):
+        return self.lr, self.rho, 0.0, self.epsilon          # lr is accepted and unused (:110-123)
+
+
+class Adam(_Adaptive):
+    KIND = 3
+    TWO_STATES = True
+
+    def __init__(self, lr=0.001, decay=0.0, beta1=0.9, beta2=0.999, epsilon=1e-7, *args, **kwargs):
+        self.beta1 = beta1
+        self.beta2 = beta2
+        self.epsilon = epsilon
+        super(Adam, self).__init__(lr, decay)
+
+    def _params(self):
+        return self.lr, self.beta1, self.beta2, self.epsilon
+
+    def update(self, trainable_variables):
+        self.iterations += 1            # utils/Optimizers.py:139: two increments per update (the device tick mirrors it)
+        super(Adam, self).update(trainable_variables)
+
+
 def get_optimizer(optimizer):
     if isinstance(optimizer, str):
         key = optimizer.lower()
@@ -79,8 +179,14 @@ def get_optimizer(optimizer):
             return StochasticGradientDescent()
         if key == 'momentum':
             return Momentum()
-        if key in ('adam', 'rmsprop', 'adagrad', 'adadelta'):
-            raise NotImplementedError('optimizer %r is off the accelerated hot path (SURVEY.md section 2 row 6)' % optimizer)
+        if key == 'adam':
+            return Adam()
+        if key == 'rmsprop':
+            return RMSprop()
+        if key == 'adagrad':
+            return AdaGrad()
+        if key == 'adadelta':
+            return AdaDelta()
         raise ValueError('unknown optimizer type!')
     if isinstance(optimizer, Optimizer):
         return copy.deepcopy(optimizer)

@@ -201,6 +201,35 @@ def optimizer_case():
     save('optimizers', **out)
 
 
+def adaptive_optimizer_case():
+    """RMSprop / AdaGrad / AdaDelta / Adam (utils/Optimizers.py:61-157) on the same weights and
+    gradient stream as optimizer_case.  None of them zeroes the gradients, and Adam counts two
+    iterations per update (its own `+= 1` plus the base class's): both are reproduced as they are."""
+    from reference.utils.Optimizers import RMSprop, AdaGrad, AdaDelta, Adam
+    r = np.random.default_rng(11)
+    w0 = [f32(r.standard_normal((7, 5))), f32(r.standard_normal((1, 5)))]
+    gs = [[f32(r.standard_normal(w.shape)) for w in w0] for _ in range(4)]
+    out = {}
+    cases = (('rmsprop', RMSprop(lr=0.01, rho=0.9)), ('adagrad', AdaGrad(lr=0.05)), ('adadelta', AdaDelta(rho=0.95)),
+             ('adam', Adam(lr=0.01, beta1=0.9, beta2=0.999)))
+    for oname, opt in cases:
+        vs = [Variable(w.copy()) for w in w0]
+        for v in vs:
+            v.grads = np.zeros_like(v.output_tensor)
+        for t in range(4):
+            for v, g in zip(vs, gs[t]):
+                v.grads = v.grads + g          # layers accumulate with +=; these optimizers never reset
+            opt.update(vs)
+            for i, v in enumerate(vs):
+                out['%s_w%d_t%d' % (oname, i, t)] = v.output_tensor.copy()
+        out['%s_iterations' % oname] = np.array(opt.iterations)
+    for i, w in enumerate(w0):
+        out['w%d' % i] = w
+        for t in range(4):
+            out['g%d_t%d' % (i, t)] = gs[t][i]
+    save('optimizers_adaptive', **out)
+
+
 def batches_case():
     X = np.arange(23 * 2, dtype=np.float64).reshape(23, 2)
     Y = np.arange(23, dtype=np.float64).reshape(23, 1)
@@ -371,6 +400,7 @@ if __name__ == '__main__':
     bn_case('bn_2d', (16, 12), seed=1)
     loss_case()
     optimizer_case()
+    adaptive_optimizer_case()
     batches_case()
     colcase()
     traj_cfg2()

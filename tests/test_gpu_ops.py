@@ -376,3 +376,69 @@ def test_fused_batchnorm_maxpool_pair(shape, mode):
     assert rel_err(np.asarray(bn.variables[1].grads), dbt) < TOL32
     assert rel_err(np.asarray(conv.variables[0].grads), dw) < TOL32
     assert rel_err(np.asarray(src.grads), dxc) < TOL32
+
+
+# ------------------------------------------------------------------ RMSprop / AdaGrad / AdaDelta / Adam
+@pytest.mark.parametrize('name', ['rmsprop', 'adagrad', 'adadelta', 'adam'])
+def test_adaptive_optimizers_match_reference_golden(name):
+    """utils/Optimizers.py:61-157 on the device against the values the live reference produced
+    (tests/golden/optimizers_adaptive.npz): four updates on a never-zeroed gradient stream."""
+    from shinnosuke_b200.layers.Base import Variable
+    from shinnosuke_b200.utils.Optimizers import RMSprop, AdaGrad, AdaDelta, Adam
+    g = load_golden('optimizers_adaptive')
+    opt = dict(rmsprop=RMSprop(lr=0.01, rho=0.9), adagrad=AdaGrad(lr=0.05), adadelta=AdaDelta(rho=0.95),
+               adam=Adam(lr=0.01, beta1=0.9, beta2=0.999))[name]
+    vs = [Variable(g['w0'].copy()), Variable(g['w1'].copy())]
+    for v in vs:
+        v.ensure_device()
+    acc = [np.zeros_like(g['w0']), np.zeros_like(g['w1'])]
+    for t in range(4):
+        for i, v in enumerate(vs):
+            acc[i] = acc[i] + g['g%d_t%d' % (i, t)]           # layers accumulate with +=; never reset
+            v.grads = acc[i]
+        opt.update(vs)
+        for i, v in enumerate(vs):
+            assert rel_err(np.asarray(v.output_tensor), g['%s_w%d_t%d' % (name, i, t)]) < 1e-5, (name, t, i)
+    assert opt.iterations == int(g['%s_iterations' % name])
+
+
+@pytest.mark.parametrize('name', ['adam', 'rmsprop'])
+def test_adaptive_optimizer_training_matches_oracle_under_graph_replay(name):
+    """A whole model trained with Adam / RMSprop: eager first steps, then captured-graph replays
+    (Adam's bias correction must advance on the device), against the float64 oracle."""
+    from shinnosuke_b200 import Sequential, Dense
+    r = np.random.default_rng(3)
+    X = r.random((96, 20)).astype(np.float32).astype(np.float64)
+    Y = O.to_categorical(np.concatenate([np.arange(10), r.integers(0, 10, 86)]))
+    np.random.seed(0)
+    m = Sequential()
+    m.add(Dense(32, n_in=20, activation='relu'))
+    m.add(Dense(10, activation='softmax'))
+    m.compile(name, 'sparse_categorical_crossentropy')
+    m.fit(X, Y, batch_size=16, epochs=2, shuffle=False, validation_ratio=0., verbose=0)        # 12 steps, 8+ of them replays
+    np.random.seed(0)
+    w1 = 0.1 * np.random.randn(20, 32); w2 = 0.1 * np.random.randn(32, 10)      # initializer 'Normal' (std 0.1), layer order
+    params = [w1, np.zeros((1, 32)), w2, np.zeros((1, 10))]
+    grads = [np.zeros_like(p) for p in params]
+    s1 = [np.zeros_like(p) for p in params]; s2 = [np.zeros_like(p) for p in params]
+    it = 0
+    losses = []
+    for ep in range(2):
+        for a in range(0, 96, 16):
+            xs, ys = X[a:a + 16], Y[a:a + 16]
+            z1 = xs @ params[0] + params[1]; h = np.maximum(z1, 0)
+            p = O.softmax_forward(h @ params[2] + params[3])
+            losses.append(O.scce_loss(p, ys))
+            dz2 = O.scce_backward(p, ys)
+            grads[2] += h.T @ dz2; grads[3] += dz2.sum(0, keepdims=True)
+            dh = dz2 @ params[2].T; dh[z1 < 0] = 0
+            grads[0] += xs.T @ dh; grads[1] += dh.sum(0, keepdims=True)
+            if name == 'adam':
+                it += 1
+                O.adam_update(params, grads, s1, s2, it)
+                it += 1
+            else:
+                O.rmsprop_update(params, grads, s1)
+    assert np.allclose(m.train_loss, losses, rtol=2e-5)
+    for v, pr in zip(m.trainable_variables, params):
+        assert rel_err(np.asarray(v.output_tensor), pr) < 2e-5

@@ -127,6 +127,32 @@ def test_optimizers_match_reference():
                 assert rel_err(grads[i], g['%s_g%d_t%d' % (name, i, t)]) < TOL or not grads[i].any()
 
 
+def test_adaptive_optimizers_match_reference():
+    g = load_golden('optimizers_adaptive')
+    for name in ('rmsprop', 'adagrad', 'adadelta', 'adam'):
+        params = [g['w0'].copy(), g['w1'].copy()]
+        grads = [np.zeros_like(p) for p in params]
+        s1 = [np.zeros_like(p) for p in params]
+        s2 = [np.zeros_like(p) for p in params]
+        it = 0
+        for t in range(4):
+            for i in range(2):
+                grads[i] = grads[i] + g['g%d_t%d' % (i, t)]          # never zeroed by these optimizers
+            if name == 'rmsprop':
+                O.rmsprop_update(params, grads, s1, lr=0.01, rho=0.9)
+            elif name == 'adagrad':
+                O.adagrad_update(params, grads, s1, lr=0.05)
+            elif name == 'adadelta':
+                O.adadelta_update(params, grads, s1, s2, rho=0.95)
+            else:
+                it += 1
+                O.adam_update(params, grads, s1, s2, it, lr=0.01, beta1=0.9, beta2=0.999)
+                it += 1                                              # the base class's increment
+            for i in range(2):
+                assert rel_err(params[i], g['%s_w%d_t%d' % (name, i, t)]) < TOL, (name, t)
+    assert int(g['adam_iterations']) == 8 and int(g['rmsprop_iterations']) == 4
+
+
 def test_get_batches_matches_reference():
     g = load_golden('get_batches')
     X = np.arange(46, dtype=np.float64).reshape(23, 2)
