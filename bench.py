@@ -65,7 +65,7 @@ def synth(cfg, n, seed=1234):
     return X, Y
 
 
-def build_model(cfg, precision):
+def build_model(cfg, precision, sync_bn=False):
     from shinnosuke_b200 import (Sequential, Model, Input, Conv2D, BatchNormalization, MaxPooling2D, Flatten, Dense,
                                  Activation, Add)
     np.random.seed(0)
@@ -83,7 +83,7 @@ def build_model(cfg, precision):
         h = block(h, 128)
         y = Dense(10, activation='softmax')(Flatten()(h))
         m = Model(inputs=x_in, outputs=y)
-        m.compile(optimizer='sgd', loss='sparse_categorical_crossentropy', precision=precision)
+        m.compile(optimizer='sgd', loss='sparse_categorical_crossentropy', precision=precision, sync_bn=sync_bn)
         return m
     m = Sequential()
     if cfg == 'cfg3':
@@ -104,7 +104,7 @@ def build_model(cfg, precision):
     else:
         m.add(Dense(500, activation='relu', n_in=784))
         m.add(Dense(10, activation='softmax'))
-    m.compile(optimizer='sgd', loss='sparse_categorical_crossentropy', precision=precision)
+    m.compile(optimizer='sgd', loss='sparse_categorical_crossentropy', precision=precision, sync_bn=sync_bn)
     return m
 
 
@@ -329,7 +329,7 @@ def run_ours(args):
     K, Wm = args.steps, max(3, args.warmup)
     precision = args.precision
     pk = peaks()
-    m = build_model(cfg, precision)
+    m = build_model(cfg, precision, args.sync_bn)
 
     # every rank holds the whole synthetic set, like every rank running the same script would
     X, Y = synth(cfg, G * max(K, Wm, 4))
@@ -411,7 +411,7 @@ def run_ours(args):
                     warmup=Wm, ms_per_step=dev_ms / K, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype=precision, data='synthetic',
                     config=dict(workload=CONFIGS[cfg]['name'], per_gpu_batch=B, global_batch=G, parallelism='dp%d' % world,
-                                precision=precision, l2='working set per step exceeds the 126 MB L2 (no flush)' if cfg in ('cfg3', 'cfg4') and B >= 128
+                                precision=precision, sync_bn=bool(args.sync_bn), l2='working set per step exceeds the 126 MB L2 (no flush)' if cfg in ('cfg3', 'cfg4') and B >= 128
                                 else 'small working set, no flush: the step is launch-latency bound',
                                 step_tflops=CONFIGS[cfg]['flops_per_sample'] * G / world / (dev_ms / K * 1e-3) / 1e12),
                     clocks=clocks,
@@ -440,6 +440,7 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['fp32', 'tf32', 'bf16'])
     ap.add_argument('--kernel-table', default='', help='write the per-kernel CUDA-event table (JSON) here')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--sync-bn', action='store_true', help='cross-replica BatchNorm statistics (exact data parallelism; N > 1)')
     args = ap.parse_args()
     wd = int(os.environ.get('SN_BENCH_WATCHDOG', '0'))
     if wd > 0:      # debugging aid: dump every thread's stack and exit if the run takes longer than this

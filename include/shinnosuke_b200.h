@@ -270,6 +270,28 @@ SN_API int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float
                    float *dx, void *dx_bf16, float *dx_colsum, float *dgamma, float *dbeta, double *scratch,
                    int N, int H, int W, int C, int pool_mode, int mask_relu, void *stream);
 
+/* Cross-replica BatchNormalization (SyncBN) under data parallelism: the statistics of
+ * layers/Normalization.py:116-118 and the two sums of :196-203 are over the WHOLE minibatch, which
+ * is sharded.  Each direction runs in halves around an all-reduce the caller performs on
+ * scratch[0, 16*C) (float64): *_local leaves this replica's sums there (dgamma / dbeta, which are
+ * per-replica contributions, are accumulated at once), the caller all-reduces, *_finalize_* /
+ * sn_batchnorm_finalize_stats turns the global sums into the apply constants with the GLOBAL row
+ * count, *_apply writes the result.  C = 4*2^k <= 1024. */
+SN_API int sn_batchnorm_local_stats(const float *x, double *scratch, long long rows, int C, void *stream);
+SN_API int sn_batchnorm_bwd_local(const float *dy, const float *x, const float *save_mean, const float *save_invstd,
+                           float *dgamma, float *dbeta, double *scratch, long long rows, int C, void *stream);
+SN_API int sn_batchnorm_finalize_bwd(const float *gamma, const float *save_mean, const float *save_invstd,
+                              double *scratch, long long rows, int C, void *stream);
+SN_API int sn_batchnorm_bwd_apply(const float *dy, const float *x, float *dx, const double *scratch,
+                           long long rows, int C, int accumulate_dx, int mask_relu, void *stream);
+SN_API int sn_bn_pool_bwd_local(const float *dy_pool, const uint8_t *code, const float *x, const float *y_pool,
+                         const float *gamma, const float *beta, const float *save_mean, const float *save_invstd,
+                         float *dgamma, float *dbeta, double *scratch, int N, int H, int W, int C,
+                         int pool_mode, void *stream);
+SN_API int sn_bn_pool_bwd_apply(const float *dy_pool, const uint8_t *code, const float *x, float *dx, void *dx_bf16,
+                         float *dx_colsum, double *scratch, int N, int H, int W, int C,
+                         int pool_mode, int mask_relu, void *stream);
+
 /* ------------------------------------------------------------------ loss */
 /* Softmax._forward, utils/Activator.py:108-110 (row-wise; the reference's global shift cancels) */
 SN_API int sn_softmax_fwd(const float *logits, float *probs, int rows, int classes, void *stream);

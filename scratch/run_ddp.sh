@@ -1,2 +1,3 @@
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 tests/multi_gpu/ddp_check.py > gpurun_out/ddp.log 2>&1
-grep -v "OMP_NUM\|\*\*\*\*" gpurun_out/ddp.log | grep -B30 "Error\|error" | head -60
+echo "exit $?"
+grep -v "OMP_NUM\|\*\*\*\*" gpurun_out/ddp.log | grep -v "^$" | tail -25

@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(256) bn_reduce_pow2_kernel(const float *__rest
     const int cq = threadIdx.x % Q;
     float k0[4], k1[4];          // STATS: pivot, unused.   BWD: mean, invstd
     {
-        float4 a = ldg4((BWD ? mean : x) + cq * 4);
+        // forward pivot: row 0 of x, or 0 when the sums must be combinable across replicas (fin.x == nullptr)
+        float4 a = (BWD || fin.x) ? ldg4((BWD ? mean : x) + cq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         k0[0] = a.x; k0[1] = a.y; k0[2] = a.z; k0[3] = a.w;
         if (BWD) { float4 b = ldg4(invstd + cq * 4); k1[0] = b.x; k1[1] = b.y; k1[2] = b.z; k1[3] = b.w; }
     }
@@ -360,6 +361,56 @@ int sn_batchnorm_fwd_apply(const float *x, float *y, const double *scratch, long
     const long long total4 = rows * C / 4;
     bn_apply_train_pow2_kernel<<<bn_grid(total4), 256, 0, as_stream(stream)>>>(x, y, scratch, total4, C);
     return after_launch("bn_apply_train_pow2_kernel");
+}
+
+// ---- cross-replica (SyncBN) halves: local sums -> [caller all-reduces scratch[0, 16*C)] -> finalise with the global row count
+int sn_batchnorm_local_stats(const float *x, double *scratch, long long rows, int C, void *stream) {
+    SN_REQUIRE(x && scratch && rows > 0, "bad arguments");
+    SN_REQUIRE(bn_pow2(C) && (((uintptr_t)x) & 15) == 0, "needs C = 4*2^k <= 1024 and a 16-byte aligned tensor");
+    cudaStream_t st = as_stream(stream);
+    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * BN_SCRATCH_DOUBLES_PER_C * C, st));
+    const long long total4 = rows * C / 4;
+    BnFinal fin{};
+    fin.bwd = 0; fin.defer = 1; fin.rows = rows; fin.C = C; fin.x = nullptr;          // pivot 0: sums of x and x^2
+    bn_reduce_pow2_kernel<false><<<bn_grid(total4, bn_reduce_ctas(total4)), 256, 0, st>>>(x, nullptr, nullptr, nullptr, scratch, total4, C, fin);
+    return after_launch("bn_reduce_pow2_kernel");
+}
+
+int sn_batchnorm_bwd_local(const float *dy, const float *x, const float *save_mean, const float *save_invstd, float *dgamma,
+                           float *dbeta, double *scratch, long long rows, int C, void *stream) {
+    SN_REQUIRE(dy && x && save_mean && save_invstd && scratch && rows > 0, "bad arguments");
+    SN_REQUIRE(bn_pow2(C) && ((((uintptr_t)x) | ((uintptr_t)dy)) & 15) == 0, "needs C = 4*2^k <= 1024 and 16-byte aligned tensors");
+    cudaStream_t st = as_stream(stream);
+    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * BN_SCRATCH_DOUBLES_PER_C * C, st));
+    const long long total4 = rows * C / 4;
+    BnFinal fin{};
+    fin.bwd = 1; fin.defer = 1; fin.rows = rows; fin.C = C; fin.mean = save_mean; fin.invstd = save_invstd;
+    fin.dgamma = dgamma; fin.dbeta = dbeta;
+    bn_reduce_pow2_kernel<true><<<bn_grid(total4, bn_reduce_ctas(total4)), 256, 0, st>>>(x, dy, save_mean, save_invstd, scratch, total4, C, fin);
+    return after_launch("bn_reduce_pow2_kernel");
+}
+
+int sn_batchnorm_finalize_bwd(const float *gamma, const float *save_mean, const float *save_invstd, double *scratch,
+                              long long rows, int C, void *stream) {
+    SN_REQUIRE(gamma && save_mean && save_invstd && scratch && rows > 0 && bn_pow2(C), "bad arguments");
+    BnFinal fin{};
+    fin.bwd = 1; fin.rows = rows; fin.C = C; fin.gamma = gamma; fin.mean = save_mean; fin.invstd = save_invstd;
+    bn_finalize_kernel<<<1, C < 256 ? C : 256, 0, as_stream(stream)>>>(scratch, fin);
+    return after_launch("bn_finalize_kernel");
+}
+
+int sn_batchnorm_bwd_apply(const float *dy, const float *x, float *dx, const double *scratch, long long rows, int C,
+                           int accumulate_dx, int mask_relu, void *stream) {
+    SN_REQUIRE(dy && x && dx && scratch && rows > 0, "bad arguments");
+    SN_REQUIRE(bn_pow2(C) && ((((uintptr_t)x) | ((uintptr_t)dy) | ((uintptr_t)dx)) & 15) == 0, "needs C = 4*2^k <= 1024 and 16-byte aligned tensors");
+    cudaStream_t st = as_stream(stream);
+    const long long total4 = rows * C / 4;
+    const int g2 = bn_grid(total4);
+#define SN_LAUNCHP(A, M) bn_bwd_apply_pow2_kernel<A, M><<<g2, 256, 0, st>>>(dy, x, dx, scratch, total4, C)
+    if (accumulate_dx) { if (mask_relu) SN_LAUNCHP(true, true); else SN_LAUNCHP(true, false); }
+    else { if (mask_relu) SN_LAUNCHP(false, true); else SN_LAUNCHP(false, false); }
+#undef SN_LAUNCHP
+    return after_launch("bn_bwd_apply_pow2_kernel");
 }
 
 int sn_batchnorm_fwd_train(const float *x, const float *gamma, const float *beta, float *y, float *save_mean,

@@ -21,6 +21,8 @@ constexpr int BN_SCRATCH_DOUBLES_PER_C = 20;
 
 struct BnFinal {
     int bwd;                       // 0: forward statistics, 1: backward sums
+    int defer;                     // 1: cross-replica (SyncBN) phase 1 — keep the LOCAL sums in the scratch for an
+                                   //    all-reduce; only dgamma / dbeta (local by definition) are taken now
     long long rows;
     int C;
     // forward
@@ -111,6 +113,20 @@ __device__ __forceinline__ void bn_finalize_last_block(double *scratch, const Bn
     if (!is_last) return;
     __threadfence();
     if (threadIdx.x == 0) *reinterpret_cast<unsigned *>(scratch + 18 * (size_t)f.C) = 0u;    // ticket back to rest
+    if (f.defer) {
+        if (f.bwd)
+            for (int c = threadIdx.x; c < f.C; c += blockDim.x) {
+                double a = 0, b = 0;
+#pragma unroll
+                for (int s = 0; s < BN_SLOTS; ++s) {
+                    a += __ldcg(scratch + (size_t)s * 2 * f.C + c);
+                    b += __ldcg(scratch + (size_t)s * 2 * f.C + f.C + c);
+                }
+                if (f.dbeta) f.dbeta[c] += (float)a;
+                if (f.dgamma) f.dgamma[c] += (float)b;
+            }
+        return;
+    }
     bn_finalize_channels(scratch, f);
 }
 

@@ -379,49 +379,78 @@ int sn_bn_pool_fwd_apply(const float *x, float *y_pool, void *y_pool_bf16, uint8
     return after_launch("bn_pool_fwd_kernel");
 }
 
-int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, const float *y_pool, const float *gamma,
-                   const float *beta, const float *save_mean, const float *save_invstd, float *dx, void *dx_bf16,
-                   float *dx_colsum, float *dgamma, float *dbeta, double *scratch, int N, int H, int W, int C, int pool_mode,
-                   int mask_relu, void *stream) {
-    SN_REQUIRE(dy_pool && code && x && gamma && save_mean && save_invstd && (dx || dx_bf16) && scratch, "null tensor");
-    SN_REQUIRE(((((uintptr_t)x) | ((uintptr_t)dx) | ((uintptr_t)dy_pool)) & 15) == 0 && (((uintptr_t)dx_bf16) & 7) == 0, "misaligned tensor");
+// phases: 1 = memset + reductions (with `defer`: local sums stay in the scratch), 2 = apply
+static int bn_pool_bwd_impl(int phases, int defer, const float *dy_pool, const uint8_t *code, const float *x, const float *y_pool,
+                            const float *gamma, const float *beta, const float *save_mean, const float *save_invstd, float *dx,
+                            void *dx_bf16, float *dx_colsum, float *dgamma, float *dbeta, double *scratch, int N, int H, int W,
+                            int C, int pool_mode, int mask_relu, void *stream) {
+    SN_REQUIRE(dy_pool && code && x && scratch, "null tensor");
     SN_REQUIRE(shape_ok(N, H, W, C), "unsupported shape (needs even H, W and C = 4*2^k <= 1024)");
     SN_REQUIRE(pool_mode == SN_POOL_TIE_SPLIT || pool_mode == SN_POOL_FIRST_ARGMAX, "unknown pool mode");
+    SN_REQUIRE(((((uintptr_t)x) | ((uintptr_t)dx) | ((uintptr_t)dy_pool)) & 15) == 0 && (((uintptr_t)dx_bf16) & 7) == 0, "misaligned tensor");
     cudaStream_t st = as_stream(stream);
     const long long rows = (long long)N * H * W;
     const int oh = H / 2, ow = W / 2;
     const long long windows4 = (long long)N * oh * ow * (C / 4);
     const int grid = grid_for_windows(windows4);
-    // fewer, longer-lived reduce blocks on small maps (see bn.cu: bn_reduce_ctas)
-    const int rgrid = grid_for_windows(windows4, rows * C * 4 >= (100ll << 20) ? 8 : 3);
     const uint32_t *cd = (const uint32_t *)code;
-    // (+8*C doubles: the BN_SLOTS x C slot rows of the dx_colsum reduction)
-    SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (BN_SCRATCH_DOUBLES_PER_C + (dx_colsum ? BN_SLOTS : 0)) * C, st));
-    BnFinal fin{};
-    fin.bwd = 1; fin.rows = rows; fin.C = C; fin.gamma = gamma; fin.mean = save_mean; fin.invstd = save_invstd;
-    fin.dgamma = dgamma; fin.dbeta = dbeta;
-    if (y_pool && beta) {
-        SN_REQUIRE((((uintptr_t)y_pool) & 15) == 0, "misaligned tensor");
-        // one resident wave (3 CTAs/SM by registers); on small maps at least 8 windows per thread, so
-        // that the per-block tail (shared-memory fold, 2*C float64 atomics, ticket) stays amortised
-        int rgrid = grid_for_windows(windows4, 3);
-        const long long by_work = windows4 / (256 * 8);
-        if (by_work < rgrid) rgrid = by_work < 1 ? 1 : (int)by_work;
-        if (pool_mode == SN_POOL_TIE_SPLIT)
-            bn_pool_bwd_reduce_pooled_kernel<SN_POOL_TIE_SPLIT><<<rgrid, 256, 0, st>>>(dy_pool, y_pool, cd, x, gamma, beta, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
+    if (phases & 1) {
+        SN_REQUIRE(gamma && save_mean && save_invstd, "null tensor");
+        // fewer, longer-lived reduce blocks on small maps (see bn.cu: bn_reduce_ctas)
+        int rgrid = grid_for_windows(windows4, rows * C * 4 >= (100ll << 20) ? 8 : 3);
+        // (+8*C doubles: the BN_SLOTS x C slot rows of the dx_colsum reduction)
+        SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (BN_SCRATCH_DOUBLES_PER_C + BN_SLOTS) * C, st));
+        BnFinal fin{};
+        fin.bwd = 1; fin.defer = defer; fin.rows = rows; fin.C = C; fin.gamma = gamma; fin.mean = save_mean; fin.invstd = save_invstd;
+        fin.dgamma = dgamma; fin.dbeta = dbeta;
+        if (y_pool && beta) {
+            SN_REQUIRE((((uintptr_t)y_pool) & 15) == 0, "misaligned tensor");
+            // one resident wave (3 CTAs/SM by registers); on small maps at least 8 windows per thread, so
+            // that the per-block tail (shared-memory fold, 2*C float64 atomics, ticket) stays amortised
+            rgrid = grid_for_windows(windows4, 3);
+            const long long by_work = windows4 / (256 * 8);
+            if (by_work < rgrid) rgrid = by_work < 1 ? 1 : (int)by_work;
+            if (pool_mode == SN_POOL_TIE_SPLIT)
+                bn_pool_bwd_reduce_pooled_kernel<SN_POOL_TIE_SPLIT><<<rgrid, 256, 0, st>>>(dy_pool, y_pool, cd, x, gamma, beta, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
+            else
+                bn_pool_bwd_reduce_pooled_kernel<SN_POOL_FIRST_ARGMAX><<<rgrid, 256, 0, st>>>(dy_pool, y_pool, cd, x, gamma, beta, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
+        } else if (pool_mode == SN_POOL_TIE_SPLIT)
+            bn_pool_bwd_reduce_kernel<SN_POOL_TIE_SPLIT><<<rgrid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
         else
-            bn_pool_bwd_reduce_pooled_kernel<SN_POOL_FIRST_ARGMAX><<<rgrid, 256, 0, st>>>(dy_pool, y_pool, cd, x, gamma, beta, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
-    } else if (pool_mode == SN_POOL_TIE_SPLIT)
-        bn_pool_bwd_reduce_kernel<SN_POOL_TIE_SPLIT><<<rgrid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
-    else
-        bn_pool_bwd_reduce_kernel<SN_POOL_FIRST_ARGMAX><<<rgrid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
-    int e = after_launch("bn_pool_bwd_reduce_kernel");
-    if (e) return e;
+            bn_pool_bwd_reduce_kernel<SN_POOL_FIRST_ARGMAX><<<rgrid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
+        int e = after_launch("bn_pool_bwd_reduce_kernel");
+        if (e) return e;
+    }
+    if (phases & 2) {
+        SN_REQUIRE(dx || dx_bf16, "null tensor");
 #define SN_LAUNCH(M, K) bn_pool_bwd_apply_kernel<M, K><<<grid, 256, 0, st>>>(dy_pool, cd, x, dx, (__nv_bfloat16 *)dx_bf16, dx_colsum, scratch, windows4, C, W, oh, ow)
-    if (pool_mode == SN_POOL_TIE_SPLIT) { if (mask_relu) SN_LAUNCH(SN_POOL_TIE_SPLIT, true); else SN_LAUNCH(SN_POOL_TIE_SPLIT, false); }
-    else { if (mask_relu) SN_LAUNCH(SN_POOL_FIRST_ARGMAX, true); else SN_LAUNCH(SN_POOL_FIRST_ARGMAX, false); }
+        if (pool_mode == SN_POOL_TIE_SPLIT) { if (mask_relu) SN_LAUNCH(SN_POOL_TIE_SPLIT, true); else SN_LAUNCH(SN_POOL_TIE_SPLIT, false); }
+        else { if (mask_relu) SN_LAUNCH(SN_POOL_FIRST_ARGMAX, true); else SN_LAUNCH(SN_POOL_FIRST_ARGMAX, false); }
 #undef SN_LAUNCH
-    return after_launch("bn_pool_bwd_apply_kernel");
+        return after_launch("bn_pool_bwd_apply_kernel");
+    }
+    return SN_OK;
+}
+
+int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, const float *y_pool, const float *gamma,
+                   const float *beta, const float *save_mean, const float *save_invstd, float *dx, void *dx_bf16,
+                   float *dx_colsum, float *dgamma, float *dbeta, double *scratch, int N, int H, int W, int C, int pool_mode,
+                   int mask_relu, void *stream) {
+    return bn_pool_bwd_impl(3, 0, dy_pool, code, x, y_pool, gamma, beta, save_mean, save_invstd, dx, dx_bf16, dx_colsum, dgamma, dbeta,
+                            scratch, N, H, W, C, pool_mode, mask_relu, stream);
+}
+
+int sn_bn_pool_bwd_local(const float *dy_pool, const uint8_t *code, const float *x, const float *y_pool, const float *gamma,
+                         const float *beta, const float *save_mean, const float *save_invstd, float *dgamma, float *dbeta,
+                         double *scratch, int N, int H, int W, int C, int pool_mode, void *stream) {
+    return bn_pool_bwd_impl(1, 1, dy_pool, code, x, y_pool, gamma, beta, save_mean, save_invstd, nullptr, nullptr, nullptr, dgamma, dbeta,
+                            scratch, N, H, W, C, pool_mode, 0, stream);
+}
+
+int sn_bn_pool_bwd_apply(const float *dy_pool, const uint8_t *code, const float *x, float *dx, void *dx_bf16, float *dx_colsum,
+                         double *scratch, int N, int H, int W, int C, int pool_mode, int mask_relu, void *stream) {
+    return bn_pool_bwd_impl(2, 0, dy_pool, code, x, nullptr, nullptr, nullptr, nullptr, nullptr, dx, dx_bf16, dx_colsum, nullptr, nullptr,
+                            scratch, N, H, W, C, pool_mode, mask_relu, stream);
 }
 
 }  // extern "C"

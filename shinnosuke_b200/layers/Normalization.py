@@ -49,6 +49,25 @@ class BatchNormalization(Layer):
                                scratch=zeros(28 * C + 2, torch().float64))
         return self._stats
 
+    # ---- cross-replica statistics (compile(sync_bn=True) under torchrun) ---------------------
+    def _sync(self, is_training=True):
+        """(torch.distributed, global rows per local row) when this layer must reduce its sums over
+        all replicas, else None.  `_global_batch` is set by the model before every step."""
+        if not (is_training and getattr(self, '_sync_bn', False)):
+            return None
+        d = torch().distributed
+        if not (d.is_available() and d.is_initialized() and d.get_world_size() > 1):
+            return None
+        return d
+
+    def _global_rows(self, x, rows):
+        gb = getattr(self, '_global_batch', None)
+        n_loc = x.shape[0]
+        return rows if not gb else (rows // n_loc) * int(gb)
+
+    def _allreduce_sums(self, d, s, C):
+        d.all_reduce(s['scratch'][:16 * C])          # float64 {sum_a, sum_b} x 8 slots, summed over the replicas
+
     @property
     def moving_mean(self):
         return self._stats['mm'].numpy() if self._stats is not None else self._mm_host
@@ -71,6 +90,10 @@ class BatchNormalization(Layer):
         prestats = bool(is_training and getattr(self, '_stats_from', None) is not None
                         and self._stats_from is self.inbounds[0])
         self._stats_from = None
+        sync = self._sync(is_training)
+        rows_g = self._global_rows(x, rows) if sync is not None else rows
+        if sync is not None and not (C % 4 == 0 and (C // 4) & (C // 4 - 1) == 0 and C <= 1024):
+            raise NotImplementedError('sync_bn needs a channel count of the form 4*2^k <= 1024 (got %d)' % C)
         self._fused_active = bool(is_training and pool is not None and x.ndim == 4 and
                                   lib.load().sn_bn_pool_supported(x.shape[0], x.shape[2], x.shape[3], C))
         if self._fused_active:
@@ -84,9 +107,13 @@ class BatchNormalization(Layer):
             ypb_ptr = ypb.data_ptr() if ypb is not None else None
             if ypb is not None:
                 nxt._xb_filled_for = yp
-            if prestats:
+            if prestats or sync is not None:
+                if not prestats:
+                    lib.sn_batchnorm_local_stats(x.ptr, s['scratch'].data_ptr(), rows, C, st)
+                if sync is not None:
+                    self._allreduce_sums(sync, s, C)
                 lib.sn_batchnorm_finalize_stats(gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
-                                                s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows, C,
+                                                s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows_g, C,
                                                 float(self.epsilon), float(self.momentum), st)
                 lib.sn_bn_pool_fwd_apply(x.ptr, yp.ptr, ypb_ptr, code.data_ptr(), s['scratch'].data_ptr(), N, H, W, C,
                                          POOL_MODE[pool.mode], st)
@@ -101,9 +128,13 @@ class BatchNormalization(Layer):
             self._grads_premasked = False
             return
         y = self._buf('out', x.shape, x.layout)
-        if is_training and prestats:
+        if is_training and (prestats or sync is not None):
+            if not prestats:
+                lib.sn_batchnorm_local_stats(x.ptr, s['scratch'].data_ptr(), rows, C, st)
+            if sync is not None:
+                self._allreduce_sums(sync, s, C)
             lib.sn_batchnorm_finalize_stats(gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
-                                            s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows, C,
+                                            s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows_g, C,
                                             float(self.epsilon), float(self.momentum), st)
             lib.sn_batchnorm_fwd_apply(x.ptr, y.ptr, s['scratch'].data_ptr(), rows, C, st)
         elif is_training:
@@ -125,6 +156,8 @@ class BatchNormalization(Layer):
         C = x.shape[1]
         s = self._stats
         st = current_stream()
+        sync = self._sync(True)
+        rows_g = self._global_rows(x, x.size // C) if sync is not None else x.size // C
         if self._fused_active:
             pool = self._fuse_with_pool
             N, _, H, W = x.shape
@@ -153,11 +186,24 @@ class BatchNormalization(Layer):
 
                 def fused_writer(dst, acc, fuse=fuse, colsum=colsum, gb=gb, want_f32=want_f32):
                     out = self._buf('dx_tmp', x.shape, x.layout) if acc else dst
-                    lib.sn_bn_pool_bwd(pool.grads.ptr, pool._code.data_ptr(), x.ptr, pool.output_tensor.ptr,
-                                       gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr,
-                                       s['invstd'].ptr, out.ptr if (want_f32 or acc) else None, gb, colsum, gamma.grads.ptr if gamma.require_grads else None,
-                                       beta.grads.ptr if beta.require_grads else None, s['scratch'].data_ptr(),
-                                       N, H, W, C, POOL_MODE[pool._code_mode], 1 if fuse else 0, st)
+                    dgam = gamma.grads.ptr if gamma.require_grads else None
+                    dbet = beta.grads.ptr if beta.require_grads else None
+                    if sync is not None:
+                        # local sums (+ this replica's dgamma / dbeta), all-reduce, global constants, apply
+                        lib.sn_bn_pool_bwd_local(pool.grads.ptr, pool._code.data_ptr(), x.ptr, pool.output_tensor.ptr,
+                                                 gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
+                                                 dgam, dbet, s['scratch'].data_ptr(), N, H, W, C, POOL_MODE[pool._code_mode], st)
+                        self._allreduce_sums(sync, s, C)
+                        lib.sn_batchnorm_finalize_bwd(gamma.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
+                                                      s['scratch'].data_ptr(), rows_g, C, st)
+                        lib.sn_bn_pool_bwd_apply(pool.grads.ptr, pool._code.data_ptr(), x.ptr,
+                                                 out.ptr if (want_f32 or acc) else None, gb, colsum, s['scratch'].data_ptr(),
+                                                 N, H, W, C, POOL_MODE[pool._code_mode], 1 if fuse else 0, st)
+                    else:
+                        lib.sn_bn_pool_bwd(pool.grads.ptr, pool._code.data_ptr(), x.ptr, pool.output_tensor.ptr,
+                                           gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr,
+                                           s['invstd'].ptr, out.ptr if (want_f32 or acc) else None, gb, colsum, dgam, dbet,
+                                           s['scratch'].data_ptr(), N, H, W, C, POOL_MODE[pool._code_mode], 1 if fuse else 0, st)
                     if acc:
                         dst.add_(out)
                 if layer.require_grads:
@@ -173,10 +219,18 @@ class BatchNormalization(Layer):
                         and len(layer.outbound_layers) == 1 and not layer._grads_written)
 
             def writer(dst, acc, fuse=fuse):
+                dgam = gamma.grads.ptr if gamma.require_grads else None
+                dbet = beta.grads.ptr if beta.require_grads else None
+                if sync is not None:
+                    lib.sn_batchnorm_bwd_local(g.ptr, x.ptr, s['mean'].ptr, s['invstd'].ptr, dgam, dbet,
+                                               s['scratch'].data_ptr(), rows, C, st)
+                    self._allreduce_sums(sync, s, C)
+                    lib.sn_batchnorm_finalize_bwd(gamma.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
+                                                  s['scratch'].data_ptr(), rows_g, C, st)
+                    lib.sn_batchnorm_bwd_apply(g.ptr, x.ptr, dst.ptr, s['scratch'].data_ptr(), rows, C, acc, 1 if fuse else 0, st)
+                    return
                 lib.sn_batchnorm_bwd(g.ptr, x.ptr, gamma.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr, dst.ptr,
-                                     gamma.grads.ptr if gamma.require_grads else None,
-                                     beta.grads.ptr if beta.require_grads else None,
-                                     s['scratch'].data_ptr(), rows, C, acc, 1 if fuse else 0, st)
+                                     dgam, dbet, s['scratch'].data_ptr(), rows, C, acc, 1 if fuse else 0, st)
             if layer.require_grads:
                 self._push_grad(layer, writer)
                 layer._grads_premasked = fuse

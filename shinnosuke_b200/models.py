@@ -77,7 +77,7 @@ class _Trainer(object):
         raise NotImplementedError
 
     # ---- compile ---------------------------------------------------------
-    def _finish_compile(self, optimizer, loss, precision, fuse=True):
+    def _finish_compile(self, optimizer, loss, precision, fuse=True, sync_bn=False):
         if precision not in PRECISION:
             raise ValueError('precision must be one of %s' % sorted(PRECISION))
         self.precision = precision
@@ -86,6 +86,7 @@ class _Trainer(object):
         for layer in self._forward_order():
             layer.precision = precision
             if isinstance(layer, BatchNormalization):
+                layer._sync_bn = bool(sync_bn)          # cross-replica statistics under torchrun
                 # BatchNormalization -> MaxPooling2D((2,2)) with no other consumer runs as one fused pass
                 nxt = layer.outbound_layers[0] if len(layer.outbound_layers) == 1 else None
                 ok = (fuse and isinstance(nxt, MaxPooling2D) and tuple(nxt.pool_size) == (2, 2) and nxt.stride == 2
@@ -177,6 +178,10 @@ class _Trainer(object):
             # data-parallel Momentum: layers accumulate this step's gradients into gstep
             for i, v in enumerate(self.trainable_variables):
                 v._grads = DeviceTensor(a.slice('gstep', i, v.size), v.output_shape, v.layout or 'flat')
+        if world > 1:
+            for layer in self._forward_order():
+                if getattr(layer, '_sync_bn', False):
+                    layer._global_batch = global_rows
         y_hat = self._forward_device(x_dev, True)
         if world > 1:
             self._backward_allreduce(y_hat, y_dev, global_rows, metrics, garena, dist)
@@ -527,7 +532,7 @@ class Sequential(_Trainer):
     def add(self, layer):
         self.layers.append(layer)
 
-    def compile(self, optimizer, loss, precision='fp32', fuse=True):
+    def compile(self, optimizer, loss, precision='fp32', fuse=True, sync_bn=False):
         """models.py:30-43: connect the layers in order (shape inference + host-side parameter
         creation, same RNG consumption as the reference), collect the trainable variables."""
         assert self.layers
@@ -540,7 +545,7 @@ class Sequential(_Trainer):
                 if var.require_grads:
                     trainable_variables.append(var)
         self.trainable_variables = trainable_variables
-        self._finish_compile(optimizer, loss, precision, fuse)
+        self._finish_compile(optimizer, loss, precision, fuse, sync_bn)
 
     def _forward_order(self):
         return self.layers
@@ -603,7 +608,7 @@ class Model(_Trainer):
                     ready.append(m)
         return order
 
-    def compile(self, optimizer, loss, precision='fp32', fuse=True):
+    def compile(self, optimizer, loss, precision='fp32', fuse=True, sync_bn=False):
         assert self.inputs is not None and self.outputs is not None
         self.forward_graph = self._kahn(self.inputs, lambda n: n.outbound_layers, lambda n: n.inbounds)
         self.backward_graph = self._kahn(self.outputs, lambda n: n.inbounds, lambda n: n.outbound_layers)
@@ -615,7 +620,7 @@ class Model(_Trainer):
                 if isinstance(var, Variable) and var.require_grads and var not in tv:
                     tv.append(var)
         self.trainable_variables = tv
-        self._finish_compile(optimizer, loss, precision, fuse)
+        self._finish_compile(optimizer, loss, precision, fuse, sync_bn)
 
     def _forward_order(self):
         return self.forward_graph
