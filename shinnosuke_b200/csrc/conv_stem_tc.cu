@@ -35,6 +35,7 @@ struct StemP {
     int c0;              // first column of a patch row in elements of the real row: -(pw*C rounded up to 4) (16-byte aligned box start)
     int shift;           // c0 + pw*C + shift == 0: where padded column 0 sits inside a patch row
     float inv_ow, inv_oh;
+    int R128, R64;       // padded rows of a 128- / 64-pixel run that starts at column 0 inside one image (0: never happens)
 };
 
 // ---- input patches -------------------------------------------------------------------------
@@ -63,16 +64,24 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, uin
 }
 
 // producer warp: patch of pixels [pix0, pix0 + npix) -> stage buffer `dst`, G_lo -> *info
-__device__ __forceinline__ void patch_produce(const StemP &p, const CUtensorMap *tmX, float *dst, int *info, uint64_t *bar, int pix0,
-                                              int npix, int lane) {
+// tmXr: the same tensor with a box of `rfull` rows — when the run of pixels starts at column 0 and
+// stays inside one image (the common case: image sizes are multiples of the tile), the whole patch
+// is ONE box whose rows above / below the image are zero-filled like the halo columns.
+__device__ __forceinline__ void patch_produce(const StemP &p, const CUtensorMap *tmX, const CUtensorMap *tmXr, int rfull, float *dst,
+                                              int *info, uint64_t *bar, int pix0, int npix, int lane) {
     const int pix1 = min(pix0 + npix, p.P) - 1;
-    int j, i0, i1;
-    const int t0 = fast_div(pix0, p.ow, p.inv_ow, j), n0 = fast_div(t0, p.oh, p.inv_oh, i0);
+    int j0, j, i0, i1;
+    const int t0 = fast_div(pix0, p.ow, p.inv_ow, j0), n0 = fast_div(t0, p.oh, p.inv_oh, i0);
     const int t1 = fast_div(pix1, p.ow, p.inv_ow, j), n1 = fast_div(t1, p.oh, p.inv_oh, i1);
     const int g_lo = n0 * p.Hp + i0 * p.stride, g_hi = n1 * p.Hp + i1 * p.stride + p.kh - 1;
     const int rows = g_hi - g_lo + 1;
     if (lane == 0) { *info = g_lo; mbar_expect_tx(bar, (uint32_t)(rows * p.BW * 4)); }
     __syncwarp();
+    if (rfull > 0 && j0 == 0 && n0 == n1 && rows == rfull) {
+        if (elect_one()) tma_load_3d(dst, tmXr, bar, p.c0, i0 * p.stride - p.ph, n0);
+        __syncwarp();
+        return;
+    }
     // warp-uniform loop, the elected lane issues: UTMALDG takes its operands from uniform registers
     int n = n0, hp = i0 * p.stride;
     for (int row = 0; row < rows; ++row) {
@@ -122,7 +131,7 @@ constexpr int SF_A_BYTES = 128 * 128;
 
 template <int BN>
 __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX,
-                                                                   const StemP p) {
+                                                                   const __grid_constant__ CUtensorMap tmXr, const StemP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sB = smem;                                   // [BN][128 B], SW128 K-major
@@ -189,7 +198,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
         int ps = 0; uint32_t pphase = 0;
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             mbar_wait(&p_empty[ps], pphase ^ 1);
-            patch_produce(p, &tmX, patch + ps * SF_PATCH_FLOATS, pinfo + ps, &p_full[ps], tile * 128, 128, lane);
+            patch_produce(p, &tmX, &tmXr, p.R128, patch + ps * SF_PATCH_FLOATS, pinfo + ps, &p_full[ps], tile * 128, 128, lane);
             if (++ps == PATCH_STAGES) { ps = 0; pphase ^= 1; }
         }
     } else if (warp < 2 + SF_BUILDERS / 32) {
@@ -277,23 +286,34 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
 }
 
 // ============================================================================== wgrad
-constexpr int SW_BUILDERS = 256;               // 4 threads per pixel row
-constexpr int SW_THREADS = 64 + SW_BUILDERS + 128;   // warp 0: TMA (dY) + MMA, warp 1: patch producer, warps 2-9: column builders, warps 10-13: epilogue
+constexpr int SW_BUILDERS = 256;               // 4 threads per pixel row build one stage ...
+constexpr int SW_GROUPS = 2;                   // ... and two such groups take alternate stages: a builder warp's stage is a
+                                               // ~200-instruction dependent chain (~1000 cycles), twice the MMA time of a stage
+constexpr int SW_THREADS = 64 + SW_GROUPS * SW_BUILDERS + 128;   // warp 0: TMA (dY) + MMA, warp 1: patch producer, warps 2-17: column builders, warps 18-21: epilogue
 constexpr int SW_PB = 64;                      // pixels per stage
-constexpr int SW_STAGES = 4;
+// NA = 32-filter atoms of dY actually loaded per stage (2 when F <= 64, else 4).  The MMA is always
+// M = 128: with NA = 2 its upper 64 rows read whatever follows in shared memory (the next stage /
+// the patch ring) and produce accumulator rows the epilogue never looks at — rows of D depend only
+// on the same rows of A — which halves the stage and deepens the ring from 4 to 6 stages.
+template <int NA> struct SwCfg {
+    static constexpr int STAGES = NA == 2 ? 6 : 4;
+};
+constexpr int SW_MAX_STAGES = 6;
 constexpr int SW_ATOM = SW_PB * 128;           // one 32-wide atom column: 64 pixel rows x 128 B
-constexpr int SW_A_BYTES = 4 * SW_ATOM;        // 128 filters
-constexpr int SW_STAGE_BYTES = SW_A_BYTES + SW_ATOM;
 constexpr int SW_PATCH_FLOATS = 2048;          // per patch stage (a 64-pixel stage spans about half the rows of a 128-pixel tile)
 
+template <int NA>
 __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
-                                                                   const StemP p) {
+                                                                   const __grid_constant__ CUtensorMap tmXr, const StemP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int SW_STAGES = SwCfg<NA>::STAGES;
+    constexpr int SW_A_BYTES = NA * SW_ATOM;
+    constexpr int SW_STAGE_BYTES = SW_A_BYTES + SW_ATOM;
     float *patch = reinterpret_cast<float *>(smem + SW_STAGES * SW_STAGE_BYTES);        // PATCH_STAGES x SW_PATCH_FLOATS
     uint64_t *full = reinterpret_cast<uint64_t *>(patch + PATCH_STAGES * SW_PATCH_FLOATS);
-    uint64_t *empty = full + SW_STAGES;
-    uint64_t *acc_full = empty + SW_STAGES;
+    uint64_t *empty = full + SW_MAX_STAGES;
+    uint64_t *acc_full = empty + SW_MAX_STAGES;
     uint64_t *p_full = acc_full + 1;
     uint64_t *p_empty = p_full + PATCH_STAGES;
     int *pinfo = reinterpret_cast<int *>(p_empty + PATCH_STAGES);
@@ -335,7 +355,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
                         if (elect_one()) {
                             mbar_expect_tx(&full[ld_stage], SW_A_BYTES);
 #pragma unroll
-                            for (int a = 0; a < 4; ++a)
+                            for (int a = 0; a < NA; ++a)
                                 tma_load_2d(sa + a * SW_ATOM, &tmDY, &full[ld_stage], f_tile * 128 + a * 32, (t0 + ld) * SW_PB);
                         }
                         __syncwarp();
@@ -363,19 +383,21 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
             int ps = 0; uint32_t pphase = 0;
             for (int s = 0; s < nst; ++s) {
                 mbar_wait(&p_empty[ps], pphase ^ 1);
-                patch_produce(p, &tmX, patch + ps * SW_PATCH_FLOATS, pinfo + ps, &p_full[ps], (t0 + s) * SW_PB, SW_PB, lane);
+                patch_produce(p, &tmX, &tmXr, p.R64, patch + ps * SW_PATCH_FLOATS, pinfo + ps, &p_full[ps], (t0 + s) * SW_PB, SW_PB, lane);
                 if (++ps == PATCH_STAGES) { ps = 0; pphase ^= 1; }
             }
-        } else if (warp < 2 + SW_BUILDERS / 32) {
-            // column builders: thread (r, kq) builds k = 8kq..8kq+7 (one 32-byte chunk) of pixel row r
-            const int bt = threadIdx.x - 64;
+        } else if (warp < 2 + SW_GROUPS * SW_BUILDERS / 32) {
+            // column builders: thread (r, kq) of group g builds k = 8kq..8kq+7 (one 32-byte chunk) of pixel
+            // row r of the stages s = g, g + SW_GROUPS, ...
+            const int grp = (threadIdx.x - 64) / SW_BUILDERS;
+            const int bt = (threadIdx.x - 64) - grp * SW_BUILDERS;
             const int r = bt >> 2, kq = bt & 3;
             KSlice ks;
             make_kslice(p, kq, ks);
             const int one_at = p.db ? p.K : -1;
-            int stage = 0; uint32_t phase = 0;
-            int ps = 0; uint32_t pphase = 0;
-            for (int s = 0; s < nst; ++s) {
+            for (int s = grp; s < nst; s += SW_GROUPS) {
+                const int stage = s % SW_STAGES, ps = s % PATCH_STAGES;
+                const uint32_t phase = (s / SW_STAGES) & 1, pphase = (s / PATCH_STAGES) & 1;
                 mbar_wait(&p_full[ps], pphase);
                 float col[8];
                 build_slice(p, ks, patch + ps * SW_PATCH_FLOATS, pinfo[ps], (t0 + s) * SW_PB + r, kq, one_at, col);   // rows past the end stay 0 (dY is TMA zero-filled too)
@@ -386,13 +408,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
                 *reinterpret_cast<float4 *>(dst + 16) = make_float4(col[4], col[5], col[6], col[7]);
                 fence_proxy_async();
                 mbar_arrive(&full[stage]);
-                if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_empty[ps]);
-                if (++ps == PATCH_STAGES) { ps = 0; pphase ^= 1; }
             }
         } else {
-            // epilogue (warps 10..13): dW[f][k] += D[f][k], db[f] += D[f][K]
+            // epilogue (last four warps): dW[f][k] += D[f][k], db[f] += D[f][K]
             const int q = warp & 3;
             mbar_wait_sleep(acc_full, 0);        // whole-kernel wait: do not steal issue slots from the builders
             tc_fence_after();
@@ -423,22 +443,31 @@ void fill_geom(StemP &p, int N, int C, int H, int W, int F, int kh, int kw, int 
     p.K = C * kh * kw; p.P = N * p.oh * p.ow;
     p.Hp = H + 2 * ph; p.BW = patch_row_floats(W, C, pw);
     p.c0 = -((pw * C + 3) & ~3); p.shift = -p.c0 - pw * C;
+    // a run of npx pixels from column 0 inside one image spans (npx/ow - 1)*stride + kh padded rows
+    auto full_rows = [&](int npx) {
+        if (npx % p.ow || (p.oh * p.ow) % npx) return 0;
+        const int r = (npx / p.ow - 1) * stride + kh;
+        return r <= 256 ? r : 0;
+    };
+    p.R128 = full_rows(128); p.R64 = full_rows(64);
     p.inv_ow = 1.f / (float)p.ow; p.inv_oh = 1.f / (float)p.oh;
 }
 
 // x as (W*C, H, N) with one-row boxes of BW floats, no swizzle: see "input patches" above
-int make_patch_tmap(CUtensorMap *tm, const StemP &p) {
+int make_patch_tmap(CUtensorMap *tm, const StemP &p, int rows = 1) {
     long long dims[3] = {(long long)p.W * p.C, p.H, p.N};
     long long strs[3] = {1, (long long)p.W * p.C, (long long)p.H * p.W * p.C};
-    int box[3] = {p.BW, 1, 1};
+    int box[3] = {p.BW, rows > 0 ? rows : 1, 1};
     return make_tmap_linear_f32(tm, p.x, 3, dims, strs, box);
 }
 
 template <int BN>
 int launch_stem_fprop(const StemP &p, cudaStream_t st) {
     const int smem = BN * 128 + SF_ABUF * SF_A_BYTES + 2 * SF_EPI_WARPS * 4096 + SF_EPI_WARPS * 2 * BN * 4 + PATCH_STAGES * SF_PATCH_FLOATS * 4 + 1024 + 256;
-    CUtensorMap tmO, tmX;
+    CUtensorMap tmO, tmX, tmXr;
     int ex = make_patch_tmap(&tmX, p);
+    if (ex) return ex;
+    ex = make_patch_tmap(&tmXr, p, p.R128);
     if (ex) return ex;
     long long odims[2] = {p.F, p.P};
     long long ostr[2] = {1, p.F};
@@ -451,7 +480,7 @@ int launch_stem_fprop(const StemP &p, cudaStream_t st) {
         configured = true;
     }
     int grid = p.tiles < num_sms() ? p.tiles : num_sms();
-    stem_fprop_kernel<BN><<<grid, SF_THREADS, smem, st>>>(tmO, tmX, p);
+    stem_fprop_kernel<BN><<<grid, SF_THREADS, smem, st>>>(tmO, tmX, tmXr, p);
     return after_launch("stem_fprop_kernel");
 }
 
@@ -507,16 +536,21 @@ int conv_stem_wgrad_tc(const float *x, const float *dy, float *dw, float *db, in
     int dbox[2] = {32, SW_PB};
     int e = make_tmap_f32(&tmDY, dy, 2, ddims, dstr, dbox, true);
     if (e) return e;
-    const int smem = SW_STAGES * SW_STAGE_BYTES + PATCH_STAGES * SW_PATCH_FLOATS * 4 + 1024 + 256;
-    CUtensorMap tmX;
+    const bool na2 = F <= 64;
+    const int smem = (na2 ? SwCfg<2>::STAGES * 3 : SwCfg<4>::STAGES * 5) * SW_ATOM + PATCH_STAGES * SW_PATCH_FLOATS * 4 + 1024 + 256;
+    CUtensorMap tmX, tmXr;
     e = make_patch_tmap(&tmX, p);
     if (e) return e;
-    static bool configured = false;
-    if (!configured) {
-        SN_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+    e = make_patch_tmap(&tmXr, p, p.R64);
+    if (e) return e;
+    static bool configured[2] = {false, false};
+    if (!configured[na2]) {
+        if (na2) SN_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else SN_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured[na2] = true;
     }
-    stem_wgrad_kernel<<<dim3(ctas, f_tiles), SW_THREADS, smem, st>>>(tmDY, tmX, p);
+    if (na2) stem_wgrad_kernel<2><<<dim3(ctas, f_tiles), SW_THREADS, smem, st>>>(tmDY, tmX, tmXr, p);
+    else stem_wgrad_kernel<4><<<dim3(ctas, f_tiles), SW_THREADS, smem, st>>>(tmDY, tmX, tmXr, p);
     return after_launch("stem_wgrad_kernel");
 }
 

@@ -48,9 +48,20 @@ def current_stream():
     return torch().cuda.current_stream().cuda_stream
 
 
+_POISON = bool(int(__import__('os').environ.get('SN_DEBUG_POISON', '0')))
+
+
 def empty(n, dtype=None):
     t = require_cuda()
-    return t.empty(int(n), dtype=dtype or t.float32, device='cuda')
+    buf = t.empty(int(n), dtype=dtype or t.float32, device='cuda')
+    if _POISON and t.cuda.is_current_stream_capturing():
+        raise RuntimeError('device buffer of %d elements allocated while a CUDA graph is being captured' % int(n))
+    if _POISON and buf.is_floating_point():
+        # debugging aid (tests/test_gpu_train.py::test_no_uninitialised_reads): fresh buffers start as
+        # NaN, so a kernel that reads memory nobody wrote shows up in the results
+        buf.fill_(float('nan'))
+        t.cuda.synchronize()            # the fill runs on the current stream; other streams may write the buffer next
+    return buf
 
 
 def zeros(n, dtype=None):

@@ -23,8 +23,12 @@ class SparseCategoricalCrossEntropy(Objective):
         p = as_device(y_hat)
         y = as_device(y_true)
         rows, classes = p.size // p.shape[-1], p.shape[-1]
-        if self._dz is None or self._dz.shape != p.shape:
-            self._dz = DeviceTensor.empty(p.shape, 'flat')
+        # one gradient buffer per logits shape, kept for the life of the loss: captured step graphs hold
+        # its address, and a ragged last minibatch alternates with the full ones
+        bufs = self.__dict__.setdefault('_dz_by_shape', {})
+        if p.shape not in bufs:
+            bufs[p.shape] = DeviceTensor.empty(p.shape, 'flat')
+        self._dz = bufs[p.shape]
         st = current_stream()
         if metrics_ptr is None:
             if self._metrics is None:
