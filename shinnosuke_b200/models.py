@@ -127,7 +127,7 @@ class _Trainer(object):
         vl = VariableList(tv)
         vl.arena = arena
         self.trainable_variables = vl
-        self._metrics_out = zeros(2)
+        self._metrics_out = zeros(4)          # two (loss, acc) slots: fit() reads one back while the next step writes the other
         dist = _dist()
         if dist is not None and dist.get_world_size() > 1:
             # replicas must start from identical weights: rank 0's initial values win
@@ -165,7 +165,7 @@ class _Trainer(object):
         a = self._arena
         return a.gstep if a.gstep is not None else a.g
 
-    def _step_body(self, x_dev, y_dev, global_rows):
+    def _step_body(self, x_dev, y_dev, global_rows, mslot=0):
         """forward, loss, backward, gradient all-reduce, update.  No host sync inside: this is
         what gets captured in the CUDA graph."""
         a = self._arena
@@ -187,7 +187,7 @@ class _Trainer(object):
             self._backward_allreduce(y_hat, y_dev, global_rows, metrics, garena, dist)
         else:
             self.calc_gradients(y_hat, y_dev, denom_rows=global_rows, metrics_ptr=metrics.data_ptr())
-        lib.sn_memcpy_d2d(self._metrics_out.data_ptr(), metrics.data_ptr(), 8, st)
+        lib.sn_memcpy_d2d(self._metrics_out.data_ptr() + 8 * mslot, metrics.data_ptr(), 8, st)
         self.optimizer.grad_scale = 1.0                     # shards already divide by the global rows
         self.optimizer.update(self.trainable_variables)
         # the optimizer touches arena.g[:param_floats] only; clear the metric tail for the next step
@@ -253,23 +253,23 @@ class _Trainer(object):
         dist.all_reduce(garena[:lo])
         main.wait_event(tail_done)
 
-    def _run_step(self, x_dev, y_dev, global_rows):
+    def _run_step(self, x_dev, y_dev, global_rows, mslot=0):
         if not self.use_cuda_graph:
-            self._step_body(x_dev, y_dev, global_rows)
+            self._step_body(x_dev, y_dev, global_rows, mslot)
             return
-        key = (x_dev.ptr, y_dev.ptr, x_dev.shape, global_rows)
+        key = (x_dev.ptr, y_dev.ptr, x_dev.shape, global_rows, mslot)
         graph = self._graphs.get(key)
         if graph is None:
             if key not in self._warm:
                 # first step of this shape runs eagerly: allocates every layer buffer and loads
                 # every kernel, so that nothing but launches happens during capture
                 self._warm.add(key)
-                self._step_body(x_dev, y_dev, global_rows)
+                self._step_body(x_dev, y_dev, global_rows, mslot)
                 return
             t = torch()
             graph = t.cuda.CUDAGraph()
             with t.cuda.graph(graph):
-                self._step_body(x_dev, y_dev, global_rows)
+                self._step_body(x_dev, y_dev, global_rows, mslot)
             self._graphs[key] = graph
         graph.replay()
 
@@ -314,6 +314,7 @@ class _Trainer(object):
                        y=[t.empty((n_loc_max, y_row), dtype=t.float32).pin_memory() for _ in range(depth)],
                        copy_stream=t.cuda.Stream(), metrics=None,
                        h2d_done=[t.cuda.Event() for _ in range(2)], compute_done=[t.cuda.Event() for _ in range(2)],
+                       d2h_stream=t.cuda.Stream(), d2h_done=[t.cuda.Event() for _ in range(2)],
                        slot_copied=[t.cuda.Event() for _ in range(depth)])
             self._fit_res = res
         if res['metrics'] is None or res['metrics'].shape[0] < n_batches:
@@ -364,7 +365,7 @@ class _Trainer(object):
             shards.append((a + (rows * rank) // world, a + (rows * (rank + 1)) // world, rows))
         n_loc_max = max(hi - lo for lo, hi, _ in shards)
         res = self._fit_resources(n_loc_max, x_row, y_row, len(slices))
-        depth, copy_stream = res['depth'], res['copy_stream']
+        depth, copy_stream, d2h_stream = res['depth'], res['copy_stream'], res['d2h_stream']
         inp = self._input_layer()
         is4d = train_X.ndim == 4 and train_X.shape[1] > 1 and train_X.shape[2] * train_X.shape[3] > 1
         x_layout = 'nhwc' if train_X.ndim == 4 else 'flat'
@@ -446,9 +447,14 @@ class _Trainer(object):
                         pending_slots.append(slot)
                     # ---- stage 3: compute stream ---------------------------------
                     compute_stream.wait_event(res['h2d_done'][j])
-                    self._run_step(xs, ys, rows)
+                    compute_stream.wait_event(res['d2h_done'][j])       # metric slot j was read back (two steps ago)
+                    self._run_step(xs, ys, rows, mslot=j)
                     res['compute_done'][j].record(compute_stream)
-                    lib.sn_memcpy_d2h(pin_metrics[bi].data_ptr(), self._metrics_out.data_ptr(), 8, st)
+                    # the (loss, acc) pair of this step goes home on its own stream: a DMA queued on the
+                    # compute stream would sit between two graph launches
+                    d2h_stream.wait_event(res['compute_done'][j])
+                    lib.sn_memcpy_d2h(pin_metrics[bi].data_ptr(), self._metrics_out.data_ptr() + 8 * j, 8, d2h_stream.cuda_stream)
+                    res['d2h_done'][j].record(d2h_stream)
                     step_no += 1
                     # hand staging slots whose copy has certainly finished back to the gather thread
                     while len(pending_slots) > 2:
@@ -459,6 +465,7 @@ class _Trainer(object):
                         self.valid_loss.append(valid_loss)
                         self.valid_acc.append(valid_acc)
                 lib.sn_stream_sync(st)
+                d2h_stream.synchronize()
                 gap = time.time() - start_time
                 mets = pin_metrics.numpy()
                 for bi, (_, _, rows) in enumerate(shards):
@@ -477,6 +484,7 @@ class _Trainer(object):
             for _ in range(depth + 1):
                 free_slots.release()
             copy_stream.synchronize()
+            d2h_stream.synchronize()
             if not direct:
                 worker.join(timeout=10)
 
