@@ -151,6 +151,14 @@ SN_API int sn_pad2d_bwd(const float *dy, float *dx, int N, int H, int W, int C, 
  * sn_conv2d_bf16_supported and must use the fp32-pointer entry points. */
 SN_API int sn_cast_f32_to_bf16(const float *src, void *dst_bf16, long long n, void *stream);
 SN_API int sn_flip_transpose_filters_bf16(const float *w, void *wt_bf16, int F, int C, int kh, int kw, void *stream);
+/* All bf16 weight operands of a training step in one launch: shadow_bf16[0, n) = bf16(arena[0, n))
+ * (Conv2D.forward's filters are slices of it), plus, for each of `ntasks` convolutions, the
+ * flipped + transposed dgrad operand of sn_flip_transpose_filters_bf16.  tasks_dev: device array of
+ * 8 int64 per task {element offset of W in the arena, device address of Wt, F, C, kh, kw, first
+ * unit, units} where a unit is one 32x32 (f, c) tile of one tap: units = kh*kw*ceil(F/32)*ceil(C/32),
+ * first unit = running sum; flip_units = total. */
+SN_API int sn_conv_weights_prepare_bf16(const float *arena, void *shadow_bf16, long long n, const long long *tasks_dev,
+                                 int ntasks, int flip_units, void *stream);
 SN_API int sn_conv2d_bf16_supported(int op, int N, int C, int H, int W, int F, int kh, int kw,
                              int stride, int pad_h, int pad_w);
 SN_API int sn_conv2d_fprop_bf16(const void *x_bf16, const void *w_bf16, const float *bias, float *y,

@@ -12,6 +12,7 @@ int conv_igemm_tc(const void *x, const void *w, const float *bias, float *out, i
                   int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, bool bf16, double *stats, cudaStream_t st);
 int flip_transpose_filters_bf16(const float *w, void *wt, int F, int C, int kh, int kw, cudaStream_t st);
 int cast_f32_to_bf16(const float *src, void *dst, long long n, cudaStream_t st);
+int prepare_weights_bf16(const float *arena, void *shadow, long long n, const long long *tasks, int ntasks, int flip_units, cudaStream_t st);
 int conv_wgrad_tc(const float *x, const float *dy, float *dw, int N, int C, int IH, int IW, int F, int kh, int kw, int OH,
                   int OW, int pad_h, int pad_w, cudaStream_t st);
 int flip_transpose_filters(const float *w, float *wt, int F, int C, int kh, int kw, cudaStream_t st);
@@ -193,6 +194,12 @@ int sn_conv2d_bf16_supported(int op, int N, int C, int H, int W, int F, int kh, 
     if (op == 1) return (kh - 1 - pad_h >= 0 && kw - 1 - pad_w >= 0 && C % 4 == 0 && conv_tc_eligible(N, F, H, W, C, 1, true)) ? 1 : 0;
     if (op == 2) return wgrad_halo_eligible(N, C, oh, ow, F, kh, kw, 1, true) ? 1 : 0;
     return 0;
+}
+int sn_conv_weights_prepare_bf16(const float *arena, void *shadow_bf16, long long n, const long long *tasks_dev, int ntasks,
+                                 int flip_units, void *stream) {
+    SN_REQUIRE(arena && shadow_bf16 && n >= 0 && ntasks >= 0 && ntasks <= 64 && (ntasks == 0 || tasks_dev) && flip_units >= 0, "bad arguments");
+    SN_REQUIRE(((((uintptr_t)arena) & 15) | (((uintptr_t)shadow_bf16) & 7)) == 0, "misaligned arena");
+    return prepare_weights_bf16(arena, shadow_bf16, n, tasks_dev, ntasks, flip_units, as_stream(stream));
 }
 int sn_conv2d_fprop_bf16(const void *x, const void *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
                          int kw, int stride, int pad_h, int pad_w, int act, void *stream) {

@@ -393,6 +393,58 @@ __global__ void flip_transpose_filters_bf16_kernel(const float *__restrict__ w, 
     }
 }
 
+// One launch per training step for ALL convolutions of the bf16 tier: the bf16 shadow of the whole
+// parameter arena (the fprop operands are slices of it) and every dgrad operand
+// Wt[c][kh-1-u][kw-1-v][f] = W[f][u][v][c].  A block is one work unit: either 1024 consecutive arena
+// elements to cast, or one 32 (f) x 32 (c) tile of one tap of one convolution, transposed through
+// shared memory so that both the fp32 reads (c fastest) and the bf16 writes (f fastest) coalesce.
+// tasks: 8 int64 per convolution {arena offset of W, address of Wt, F, C, kh, kw, first unit, units}.
+__global__ void __launch_bounds__(256) prepare_weights_bf16_kernel(const float *__restrict__ arena, __nv_bfloat16 *__restrict__ shadow,
+                                                                   long long n, int cast_units, const long long *__restrict__ tasks,
+                                                                   int ntasks) {
+    __shared__ float tile[32][33];
+    const int u = blockIdx.x;
+    if (u < cast_units) {
+        const long long i = (long long)u * 1024 + threadIdx.x * 4;
+        if (i + 3 < n) {
+            const float4 v = *reinterpret_cast<const float4 *>(arena + i);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 o; o.x = *reinterpret_cast<uint32_t *>(&lo); o.y = *reinterpret_cast<uint32_t *>(&hi);
+            *reinterpret_cast<uint2 *>(shadow + i) = o;
+        } else {
+            for (long long j = i; j < n && j < i + 4; ++j) shadow[j] = __float2bfloat16_rn(arena[j]);
+        }
+        return;
+    }
+    const int tu = u - cast_units;
+    for (int t = 0; t < ntasks; ++t) {
+        const long long *tk = tasks + 8 * t;
+        const int first = (int)tk[6], units = (int)tk[7];
+        if (tu < first || tu >= first + units) continue;
+        const int F = (int)tk[2], C = (int)tk[3], kh = (int)tk[4], kw = (int)tk[5];
+        const int ftiles = (F + 31) >> 5, ctiles = (C + 31) >> 5;
+        int r = tu - first;
+        const int ct = r % ctiles; r /= ctiles;
+        const int ft = r % ftiles; r /= ftiles;
+        const int tap = r;                                   // u*kw + v of W
+        const int uu = tap / kw, vv = tap - uu * kw;
+        const int tap2 = (kh - 1 - uu) * kw + (kw - 1 - vv); // position in Wt
+        const float *w = arena + tk[0];
+        __nv_bfloat16 *wt = reinterpret_cast<__nv_bfloat16 *>(tk[1]);
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+        for (int rr = ty; rr < 32; rr += 8) {                // rows = f, columns = c (contiguous in W)
+            const int f = ft * 32 + rr, c = ct * 32 + tx;
+            tile[rr][tx] = (f < F && c < C) ? w[((long long)f * kh * kw + tap) * C + c] : 0.f;
+        }
+        __syncthreads();
+        for (int rr = ty; rr < 32; rr += 8) {                // rows = c, columns = f (contiguous in Wt)
+            const int c = ct * 32 + rr, f = ft * 32 + tx;
+            if (c < C && f < F) wt[((long long)c * kh * kw + tap2) * F + f] = __float2bfloat16_rn(tile[tx][rr]);
+        }
+        return;
+    }
+}
+
 __global__ void cast_f32_bf16_kernel(const float *__restrict__ s, __nv_bfloat16 *__restrict__ d, long long n) {
     const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x, t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if ((((uintptr_t)s) & 15) == 0 && (((uintptr_t)d) & 7) == 0) {
@@ -749,6 +801,13 @@ int flip_transpose_filters_bf16(const float *w, void *wt, int F, int C, int kh, 
     long long total = (long long)F * kh * kw * C;
     flip_transpose_filters_bf16_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, (__nv_bfloat16 *)wt, F, C, kh, kw);
     return after_launch("flip_transpose_filters_bf16_kernel");
+}
+
+int prepare_weights_bf16(const float *arena, void *shadow, long long n, const long long *tasks, int ntasks, int flip_units, cudaStream_t st) {
+    const int cast_units = (int)((n + 1023) / 1024);
+    if (cast_units + flip_units == 0) return SN_OK;
+    prepare_weights_bf16_kernel<<<cast_units + flip_units, 256, 0, st>>>(arena, (__nv_bfloat16 *)shadow, n, cast_units, tasks, ntasks);
+    return after_launch("prepare_weights_bf16_kernel");
 }
 
 int cast_f32_to_bf16(const float *src, void *dst, long long n, cudaStream_t st) {

@@ -103,16 +103,21 @@ class Conv2D(Layer):
         if bf16:
             # bf16 tier: bf16 copies of the input map and the filters, fp32 accumulation and output
             self._xb = self._bf16_buf('x_bf16', x.size)
-            wb = self._bf16_buf('w_bf16', W.size)
             if getattr(self, '_xb_filled_for', None) is not x:       # else the producing kernel already wrote the copy
                 lib.sn_cast_f32_to_bf16(x.ptr, self._xb.data_ptr(), x.size, st)
             self._xb_filled_for = None
-            lib.sn_cast_f32_to_bf16(W.output_tensor.ptr, wb.data_ptr(), W.size, st)
+            prepared = getattr(self, '_w_prepared', None)            # the model cast every filter of this step in one launch
+            if prepared is not None:
+                wb_ptr = prepared[0]
+            else:
+                wb = self._bf16_buf('w_bf16', W.size)
+                lib.sn_cast_f32_to_bf16(W.output_tensor.ptr, wb.data_ptr(), W.size, st)
+                wb_ptr = wb.data_ptr()
             if scratch:
-                lib.sn_conv2d_fprop_bf16_stats(self._xb.data_ptr(), wb.data_ptr(), b.output_tensor.ptr, y.ptr, *geom,
+                lib.sn_conv2d_fprop_bf16_stats(self._xb.data_ptr(), wb_ptr, b.output_tensor.ptr, y.ptr, *geom,
                                                self._act_code(), scratch, st)
             else:
-                lib.sn_conv2d_fprop_bf16(self._xb.data_ptr(), wb.data_ptr(), b.output_tensor.ptr, y.ptr, *geom,
+                lib.sn_conv2d_fprop_bf16(self._xb.data_ptr(), wb_ptr, b.output_tensor.ptr, y.ptr, *geom,
                                          self._act_code(), st)
         elif scratch:
             lib.sn_conv2d_fprop_stats(x.ptr, W.output_tensor.ptr, b.output_tensor.ptr, y.ptr, *geom, self._act_code(),
@@ -200,9 +205,12 @@ class Conv2D(Layer):
                                          db, *geom, st)
             else:
                 lib.sn_conv2d_wgrad(x.ptr, g.ptr, W.grads.ptr, db, *geom, 1, prec, st)
+        self._used_wt_bf16 = bool(dgrad_bf16)
         if dgrad_bf16:
             wtb = self._bf16_buf('wt_bf16', W.size)
-            lib.sn_flip_transpose_filters_bf16(W.output_tensor.ptr, wtb.data_ptr(), F, C, kh, kw, st)
+            prepared = getattr(self, '_w_prepared', None)
+            if prepared is None or not prepared[1]:
+                lib.sn_flip_transpose_filters_bf16(W.output_tensor.ptr, wtb.data_ptr(), F, C, kh, kw, st)
             for layer in self.inbounds:
                 self._push_grad(layer, lambda dst, acc: lib.sn_conv2d_dgrad_bf16(
                     gb.data_ptr(), wtb.data_ptr(), dst.ptr, *geom, acc, st))

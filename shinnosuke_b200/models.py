@@ -20,7 +20,7 @@ import time
 
 import numpy as np
 
-from .device import Arena, DeviceTensor, as_device, current_stream, require_cuda, torch, zeros
+from .device import Arena, DeviceTensor, as_device, current_stream, empty, require_cuda, torch, zeros
 from ._lib import lib, PRECISION
 from .layers.Base import Layer, Variable, Input
 from .utils.MiniBatch import batch_permutation, batch_slices
@@ -61,6 +61,8 @@ class _Trainer(object):
         self._fit_res = None
         self._split = None
         self._comm_stream = None
+        self._bf16_shadow = None
+        self._prep_tasks = {}
         self._pinned_user = {}      # id -> (array, ptr): user arrays page-locked in place by fit(shuffle=False)
 
     # ---- to be provided by the subclass ---------------------------------
@@ -165,6 +167,48 @@ class _Trainer(object):
         a = self._arena
         return a.gstep if a.gstep is not None else a.g
 
+    def _prepare_bf16_weights(self, n_batch):
+        """bf16 tier: ONE launch casts the whole parameter arena to its bf16 shadow (every Conv2D's fprop
+        filters are slices of it) and writes the flipped + transposed dgrad operand of every
+        convolution whose dgrad runs on bf16 operands at this batch size (three casts + three flips
+        for config 3 otherwise).  Returns the layers it served; they are released at the end of the step."""
+        from .layers.Convolution import Conv2D
+        a = self._arena
+        t = torch()
+        if getattr(self, '_bf16_shadow', None) is None:
+            self._bf16_shadow = empty(a.total, t.bfloat16)
+            self._prep_tasks = {}
+        index = {id(v): i for i, v in enumerate(self.trainable_variables)}
+        convs = [l for l in self._forward_order() if isinstance(l, Conv2D) and l.variables and id(l.variables[0]) in index
+                 and l.input_shape is not None and len(l.input_shape) == 4]
+
+        def flips_dgrad(l):             # Conv2D._bf16_grad_plan's rule for the dgrad operand, from static shapes
+            _, C, H, Wd = l.input_shape
+            kh, kw = l.filter_size
+            geom = (n_batch, C, H, Wd, l.filter_nums, kh, kw, l.stride, l.pad_size[0], l.pad_size[1])
+            return any(p.require_grads for p in l.inbounds) and l._bf16_ok(1, geom)
+        key = n_batch
+        if key not in self._prep_tasks:
+            flips = [l for l in convs if flips_dgrad(l)]
+            rows, start = [], 0
+            for l in flips:
+                W = l.variables[0]
+                F, C = l.filter_nums, W.output_shape[1]
+                kh, kw = l.filter_size
+                wt = l._bf16_buf('wt_bf16', W.size)
+                units = kh * kw * ((F + 31) // 32) * ((C + 31) // 32)       # one 32x32 (f, c) tile of one tap each
+                rows.append([a.offsets[index[id(W)]], wt.data_ptr(), F, C, kh, kw, start, units])
+                start += units
+            table = t.tensor(rows if rows else [[0] * 8], dtype=t.int64, device='cuda')
+            self._prep_tasks[key] = (table, len(rows), start, set(id(l) for l in flips))
+        table, ntasks, flip_elems, flipped = self._prep_tasks[key]
+        lib.sn_conv_weights_prepare_bf16(a.w.data_ptr(), self._bf16_shadow.data_ptr(), a.param_floats, table.data_ptr(), ntasks,
+                                         flip_elems, current_stream())
+        for l in convs:
+            W = l.variables[0]
+            l._w_prepared = (self._bf16_shadow.data_ptr() + 2 * a.offsets[index[id(W)]], id(l) in flipped)
+        return convs
+
     def _step_body(self, x_dev, y_dev, global_rows, mslot=0):
         """forward, loss, backward, gradient all-reduce, update.  No host sync inside: this is
         what gets captured in the CUDA graph."""
@@ -182,6 +226,14 @@ class _Trainer(object):
             for layer in self._forward_order():
                 if getattr(layer, '_sync_bn', False):
                     layer._global_batch = global_rows
+        prepared = self._prepare_bf16_weights(int(x_dev.shape[0])) if self.precision == 'bf16' else ()
+        try:
+            self._step_rest(x_dev, y_dev, global_rows, mslot, a, st, dist, world, garena, metrics)
+        finally:
+            for layer in prepared:
+                layer._w_prepared = None
+
+    def _step_rest(self, x_dev, y_dev, global_rows, mslot, a, st, dist, world, garena, metrics):
         y_hat = self._forward_device(x_dev, True)
         if world > 1:
             self._backward_allreduce(y_hat, y_dev, global_rows, metrics, garena, dist)
