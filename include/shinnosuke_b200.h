@@ -272,7 +272,7 @@ SN_API int sn_bn_pool_fwd_apply(const float *x, float *y_pool, void *y_pool_bf16
  * pooled tensors only, since every pool winner satisfies xhat = (y_pool - beta)/gamma.
  * Outputs for the producing Conv2D's backward (layers/Convolution.py:186-197), each optional but
  * at least one of dx / dx_bf16: dx (fp32), dx_bf16 (the bf16 operand copy of the same values),
- * dx_colsum[C] += sum over rows of dx (that layer's bias gradient, :192; needs scratch >= 28*C doubles). */
+ * dx_colsum[C] += sum over rows of dx (that layer's bias gradient, :192; needs scratch >= 28*C doubles whose last 8*C are zero on first use and left zero). */
 SN_API int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, const float *y_pool,
                    const float *gamma, const float *beta, const float *save_mean, const float *save_invstd,
                    float *dx, void *dx_bf16, float *dx_colsum, float *dgamma, float *dbeta, double *scratch,

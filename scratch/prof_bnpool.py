@@ -15,7 +15,7 @@ def run(N, H, W, C):
     code = torch.randint(1, 15, (N * (H // 2) * (W // 2) * C,), dtype=torch.uint8, device='cuda')
     g = torch.ones(C, device='cuda'); b = torch.zeros(C, device='cuda'); mean = torch.zeros(C, device='cuda'); inv = torch.ones(C, device='cuda')
     dg = torch.zeros(C, device='cuda'); db = torch.zeros(C, device='cuda'); dx = torch.empty_like(x); cs = torch.zeros(C, device='cuda')
-    scr = torch.zeros(28 * C + 2, dtype=torch.float64, device='cuda')
+    scr = torch.zeros(52 * C + 2, dtype=torch.float64, device='cuda')
     a = (dyp.data_ptr(), code.data_ptr(), x.data_ptr(), yp.data_ptr(), g.data_ptr(), b.data_ptr(), mean.data_ptr(), inv.data_ptr())
     def local():
         lib.sn_bn_pool_bwd_local(*a, dg.data_ptr(), db.data_ptr(), scr.data_ptr(), N, H, W, C, 0, torch.cuda.current_stream().cuda_stream)

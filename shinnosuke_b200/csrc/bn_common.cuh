@@ -5,8 +5,8 @@
 // leaves the sums and the ticket zero again):
 //   [0, 16C)        BN_SLOTS copies of {sum_a[C], sum_b[C]}  (slot = blockIdx.x % BN_SLOTS: short atomic chains)
 //   [16C, 18C)      4*C floats: p0[C], p1[C], p2[C] (apply-pass constants), 1 spare row
-//   [18C]           ticket counters (two unsigned: reduce kernels, sn_bn_pool_bwd's column-sum tail)
-//   [20C, 28C)      sn_bn_pool_bwd with dx_colsum only: BN_SLOTS x C doubles of block column sums
+//   [18C]           ticket counter of the reduce kernels (unsigned)
+//   [20C, 28C)      sn_bn_pool_bwd with dx_colsum only: BN_SLOTS x C doubles of block column sums (zero at rest: colsum_fold_kernel re-zeroes them)
 //
 // Doing the float64 division / sqrt ONCE per channel here (instead of in the prologue of every
 // apply block) matters: B200 issues 64 FP64 ops/clk/SM, and a 256-thread block recomputing

@@ -17,6 +17,8 @@ using namespace sn;
 
 namespace {
 
+constexpr int COLSUM_SLOTS = BN_SLOTS;     // slot rows of the dx column-sum reduction: scratch[20C, 28C)
+
 __device__ __forceinline__ float comp(const float4 &v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
 __device__ __forceinline__ void setc(float4 &v, int k, float x) { if (k == 0) v.x = x; else if (k == 1) v.y = x; else if (k == 2) v.z = x; else v.w = x; }
 
@@ -295,10 +297,10 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__r
     }
     if (colsum) {
         // block sums -> BN_SLOTS slot rows in the scratch (same-address atomics serialise at ~10 ns
-        // each: one row would cost a chain of gridDim.x of them) -> the last block adds the rows up
+        // each: one row would cost a chain of gridDim.x of them); colsum_fold_kernel adds the rows up.
+        // (A last-block fold in here — fence, ticket, reload — cost 5.5 us of serial tail per launch.)
         __shared__ float scs[256][4];
-        __shared__ bool is_last;
-        double *slots = scratch + 20 * (size_t)C;        // [BN_SLOTS][C], float64: the result does not depend on the arrival order
+        double *slots = scratch + 20 * (size_t)C;        // [COLSUM_SLOTS][C], float64: the result does not depend on the arrival order
 #pragma unroll
         for (int k = 0; k < 4; ++k) scs[threadIdx.x][k] = cs[k];
         __syncthreads();
@@ -307,26 +309,22 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__r
             for (int k = 0; k < 4; ++k) {
                 float t = 0.f;
                 for (int j = threadIdx.x; j < 256; j += Q) t += scs[j][k];
-                atomicAdd(slots + (size_t)(blockIdx.x % BN_SLOTS) * C + cq * 4 + k, (double)t);
-            }
-        }
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned *ticket = reinterpret_cast<unsigned *>(scratch + 18 * (size_t)C) + 1;
-            is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-        }
-        __syncthreads();
-        if (is_last) {
-            __threadfence();
-            for (int c = threadIdx.x; c < C; c += 256) {
-                double t = 0.0;
-#pragma unroll
-                for (int sl = 0; sl < BN_SLOTS; ++sl) t += __ldcg(slots + (size_t)sl * C + c);
-                colsum[c] += (float)t;
+                atomicAdd(slots + (size_t)(blockIdx.x % COLSUM_SLOTS) * C + cq * 4 + k, (double)t);
             }
         }
     }
+}
+
+// adds the slot rows up and leaves them zero again for the next launch (they start zero: the scratch is
+// allocated zeroed, and only this pair of kernels touches the region)
+__global__ void colsum_fold_kernel(double *__restrict__ scratch, float *__restrict__ colsum, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double *slots = scratch + 20 * (size_t)C;
+    double t = 0.0;
+#pragma unroll 8
+    for (int sl = 0; sl < COLSUM_SLOTS; ++sl) { t += slots[(size_t)sl * C + c]; slots[(size_t)sl * C + c] = 0.0; }
+    colsum[c] += (float)t;
 }
 
 int grid_for_windows(long long windows4, int ctas_per_sm = 8) {
@@ -398,8 +396,7 @@ static int bn_pool_bwd_impl(int phases, int defer, const float *dy_pool, const u
         SN_REQUIRE(gamma && save_mean && save_invstd, "null tensor");
         // fewer, longer-lived reduce blocks on small maps (see bn.cu: bn_reduce_ctas)
         int rgrid = grid_for_windows(windows4, rows * C * 4 >= (100ll << 20) ? 8 : 3);
-        // (+8*C doubles: the BN_SLOTS x C slot rows of the dx_colsum reduction)
-        SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (BN_SCRATCH_DOUBLES_PER_C + BN_SLOTS) * C, st));
+        SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * BN_SCRATCH_DOUBLES_PER_C * C, st));
         BnFinal fin{};
         fin.bwd = 1; fin.defer = defer; fin.rows = rows; fin.C = C; fin.gamma = gamma; fin.mean = save_mean; fin.invstd = save_invstd;
         fin.dgamma = dgamma; fin.dbeta = dbeta;
@@ -427,7 +424,10 @@ static int bn_pool_bwd_impl(int phases, int defer, const float *dy_pool, const u
         if (pool_mode == SN_POOL_TIE_SPLIT) { if (mask_relu) SN_LAUNCH(SN_POOL_TIE_SPLIT, true); else SN_LAUNCH(SN_POOL_TIE_SPLIT, false); }
         else { if (mask_relu) SN_LAUNCH(SN_POOL_FIRST_ARGMAX, true); else SN_LAUNCH(SN_POOL_FIRST_ARGMAX, false); }
 #undef SN_LAUNCH
-        return after_launch("bn_pool_bwd_apply_kernel");
+        int e = after_launch("bn_pool_bwd_apply_kernel");
+        if (e || !dx_colsum) return e;
+        colsum_fold_kernel<<<(C + 255) / 256, 256, 0, st>>>(scratch, dx_colsum, C);
+        return after_launch("colsum_fold_kernel");
     }
     return SN_OK;
 }
