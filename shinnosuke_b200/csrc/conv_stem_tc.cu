@@ -122,9 +122,13 @@ __device__ __forceinline__ void build_slice(const StemP &p, const KSlice &ks, co
 }
 
 // ============================================================================== fprop
-constexpr int SF_BUILDERS = 512;               // 4 threads per pixel row
-constexpr int SF_EPI_WARPS = 8;                // two per TMEM lane quarter: the tile loop is all epilogue
-constexpr int SF_THREADS = 64 + SF_BUILDERS + 32 * SF_EPI_WARPS;   // warp 0: MMA, warp 1: patch producer, warps 2-17: column builders, warps 18-25: epilogue
+constexpr int SF_BUILDERS = 256;               // 2 threads per pixel row, 16 k's (two 32-byte slices) each
+// Two SETS of eight epilogue warps (two per TMEM lane quarter) take alternate tiles = alternate TMEM
+// accumulators: a warp's tile is a serial chain (tcgen05.ld, bias/ReLU, staging, TMA store, column
+// sums for the BatchNorm statistics) of ~2500 cycles + ~800 for the statistics, and with one set that
+// chain WAS the tile time; with two sets each has two tile times for it.
+constexpr int SF_EPI_WARPS = 16;
+constexpr int SF_THREADS = 64 + SF_BUILDERS + 32 * SF_EPI_WARPS;   // warp 0: MMA, warp 1: patch producer, warps 2-9: column builders, warps 10-25: epilogue
 constexpr int SF_PATCH_FLOATS = 4096;          // per patch stage; stem_tc_eligible bounds the rows by this
 constexpr int SF_ABUF = 3;
 constexpr int SF_A_BYTES = 128 * 128;
@@ -136,9 +140,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sB = smem;                                   // [BN][128 B], SW128 K-major
     uint8_t *sA = smem + BN * 128;                        // SF_ABUF x [128][128 B]
-    uint8_t *epi_stage = sA + SF_ABUF * SF_A_BYTES;       // per epilogue warp: 2 x (32 rows x 128 B) staging tiles for TMA stores
-    float *sstat = reinterpret_cast<float *>(epi_stage + 2 * SF_EPI_WARPS * 4096);        // [epilogue warp][{sum, sumsq}][BN] column sums
-    float *patch = sstat + SF_EPI_WARPS * 2 * BN;                                                        // PATCH_STAGES x SF_PATCH_FLOATS
+    uint8_t *epi_stage = sA + SF_ABUF * SF_A_BYTES;       // per epilogue warp: one 32 rows x 128 B staging tile for its TMA stores
+    float *sstat = reinterpret_cast<float *>(epi_stage + SF_EPI_WARPS * 4096);            // [set][quarter][{sum, sumsq}][BN] column sums
+    float *patch = sstat + 8 * 2 * BN;                                                        // PATCH_STAGES x SF_PATCH_FLOATS
     uint64_t *a_full = reinterpret_cast<uint64_t *>(patch + PATCH_STAGES * SF_PATCH_FLOATS);
     uint64_t *a_empty = a_full + SF_ABUF;
     uint64_t *t_full = a_empty + SF_ABUF;
@@ -159,13 +163,13 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < SF_ABUF; ++i) { mbar_init(&a_full[i], SF_BUILDERS); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], SF_EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], SF_EPI_WARPS / 2); }
         for (int i = 0; i < PATCH_STAGES; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], SF_BUILDERS / 32); }
         tma_prefetch_desc(&tmX);
         fence_barrier_init();
     }
     if (warp == 0) { tmem_alloc(tmem_ptr, 2 * BN < 32 ? 32 : 2 * BN); tmem_relinquish(); }
-    for (int i = threadIdx.x; i < SF_EPI_WARPS * 2 * BN; i += SF_THREADS) sstat[i] = 0.f;
+    for (int i = threadIdx.x; i < 8 * 2 * BN; i += SF_THREADS) sstat[i] = 0.f;
     fence_proxy_async();            // the weight tile was written through the generic proxy
     tc_fence_before();
     __syncthreads();
@@ -202,22 +206,26 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
             if (++ps == PATCH_STAGES) { ps = 0; pphase ^= 1; }
         }
     } else if (warp < 2 + SF_BUILDERS / 32) {
-        // ---------------- column builders: thread (r, kq) builds k = 8kq..8kq+7 of pixel row r ----------------
+        // ---------------- column builders: thread (r, h) builds k = 16h..16h+15 of pixel row r ----------------
         const int bt = threadIdx.x - 64;
-        const int r = bt >> 2, kq = bt & 3;
-        KSlice ks;
-        make_kslice(p, kq, ks);
+        const int r = bt >> 1, kq0 = (bt & 1) * 2;
+        KSlice ks0, ks1;
+        make_kslice(p, kq0, ks0);
+        make_kslice(p, kq0 + 1, ks1);
         int buf = 0; uint32_t phase = 0;
         int ps = 0; uint32_t pphase = 0;
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             mbar_wait(&p_full[ps], pphase);
-            float col[8];
-            build_slice(p, ks, patch + ps * SF_PATCH_FLOATS, pinfo[ps], tile * 128 + r, kq, -1, col);
+            float col[8], col2[8];
+            build_slice(p, ks0, patch + ps * SF_PATCH_FLOATS, pinfo[ps], tile * 128 + r, kq0, -1, col);
+            build_slice(p, ks1, patch + ps * SF_PATCH_FLOATS, pinfo[ps], tile * 128 + r, kq0 + 1, -1, col2);
             mbar_wait(&a_empty[buf], phase ^ 1);
             uint8_t *row = sA + buf * SF_A_BYTES + r * 128;
             // SW128 K-major: 16-byte chunk j of row r lives at (j ^ (r & 7)) * 16
-            *reinterpret_cast<float4 *>(row + (((2 * kq) ^ (r & 7)) * 16)) = make_float4(col[0], col[1], col[2], col[3]);
-            *reinterpret_cast<float4 *>(row + (((2 * kq + 1) ^ (r & 7)) * 16)) = make_float4(col[4], col[5], col[6], col[7]);
+            *reinterpret_cast<float4 *>(row + (((2 * kq0) ^ (r & 7)) * 16)) = make_float4(col[0], col[1], col[2], col[3]);
+            *reinterpret_cast<float4 *>(row + (((2 * kq0 + 1) ^ (r & 7)) * 16)) = make_float4(col[4], col[5], col[6], col[7]);
+            *reinterpret_cast<float4 *>(row + (((2 * kq0 + 2) ^ (r & 7)) * 16)) = make_float4(col2[0], col2[1], col2[2], col2[3]);
+            *reinterpret_cast<float4 *>(row + (((2 * kq0 + 3) ^ (r & 7)) * 16)) = make_float4(col2[4], col2[5], col2[6], col2[7]);
             fence_proxy_async();               // make the generic-proxy writes visible to the tensor core
             mbar_arrive(&a_full[buf]);
             if (++buf == SF_ABUF) { buf = 0; phase ^= 1; }
@@ -228,12 +236,14 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
     } else {
         // ---------------- epilogue: TMEM -> bias/ReLU -> NHWC output ----------------
         const int q = warp & 3;
-        const int ew = warp - 2 - SF_BUILDERS / 32;          // 0..7
-        const int half = ew >> 2;                            // which 32-column chunks this warp takes
+        const int ew = warp - 2 - SF_BUILDERS / 32;          // 0..15
+        const int set = ew >> 3;                             // which tiles (= which TMEM accumulator) this warp takes
+        const int half = (ew >> 2) & 1;                      // which 32-column chunks this warp takes
+        float *mystat = sstat + (set * 4 + q) * 2 * BN;      // shared with the other half's warp only (disjoint columns)
         int iter = 0;
-        unsigned epi_flip = 0;
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++iter) {
             const int acc = iter & 1;
+            if (acc != set) continue;
             mbar_wait(&t_full[acc], (iter >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -242,9 +252,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), rr);
                 tmem_ld_wait();
                 if (c0 >= p.F) continue;
-                uint8_t *st = epi_stage + (ew * 2 + (epi_flip & 1)) * 4096;
-                ++epi_flip;
-                if (lane == 0) tma_store_wait_read1();              // the store issued two sub-tiles ago has drained this buffer
+                uint8_t *st = epi_stage + ew * 4096;
+                if (lane == 0) tma_store_wait_read();               // this warp's previous store has drained the tile
                 __syncwarp();
 #pragma unroll
                 for (int jj = 0; jj < 32; jj += 4) {
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
                 // one TMA store per 32 x 32 sub-tile: full 128-byte lines, clipped at the tensor bounds
                 if (lane == 0) { tma_store_2d(&tmO, st, c0, tile * 128 + q * 32); tma_store_commit(); }
                 if (p.stats)
-                    staged_tile_colsums(st, lane, p.P - (tile * 128 + q * 32), sstat + ew * 2 * BN + c0, sstat + (ew * 2 + 1) * BN + c0, p.F - c0);
+                    staged_tile_colsums(st, lane, p.P - (tile * 128 + q * 32), mystat + c0, mystat + BN + c0, p.F - c0);
             }
             tc_fence_before();
             __syncwarp();
@@ -278,7 +287,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
         for (int f = threadIdx.x; f < p.F; f += SF_THREADS) {
             double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-            for (int e = 0; e < SF_EPI_WARPS; ++e) { s1 += (double)sstat[e * 2 * BN + f]; s2 += (double)sstat[(e * 2 + 1) * BN + f]; }
+            for (int e = 0; e < 8; ++e) { s1 += (double)sstat[e * 2 * BN + f]; s2 += (double)sstat[(e * 2 + 1) * BN + f]; }
             atomicAdd(slot + f, s1);
             atomicAdd(slot + p.F + f, s2);
         }
@@ -463,7 +472,7 @@ int make_patch_tmap(CUtensorMap *tm, const StemP &p, int rows = 1) {
 
 template <int BN>
 int launch_stem_fprop(const StemP &p, cudaStream_t st) {
-    const int smem = BN * 128 + SF_ABUF * SF_A_BYTES + 2 * SF_EPI_WARPS * 4096 + SF_EPI_WARPS * 2 * BN * 4 + PATCH_STAGES * SF_PATCH_FLOATS * 4 + 1024 + 256;
+    const int smem = BN * 128 + SF_ABUF * SF_A_BYTES + SF_EPI_WARPS * 4096 + 8 * 2 * BN * 4 + PATCH_STAGES * SF_PATCH_FLOATS * 4 + 1024 + 256;
     CUtensorMap tmO, tmX, tmXr;
     int ex = make_patch_tmap(&tmX, p);
     if (ex) return ex;
