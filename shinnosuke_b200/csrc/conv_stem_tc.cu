@@ -1,13 +1,17 @@
 // Tiny-C convolution (C*kh*kw <= 32: the RGB stem of config 3) on the tensor pipe, tf32 tier.
 //
 // The contraction is only K = 27 long, so a TMA box per filter tap would move almost nothing per
-// load.  Instead the CUDA cores build the COLUMN TILE in shared memory — one 128-byte row of
-// K (padded to 32) fp32 values per output pixel, written directly in the swizzled layout the UMMA
-// descriptor expects — and tcgen05.mma contracts it.  The column matrix still never exists in
-// HBM.  Per 128-pixel tile this is 128 x 27 cached gathers + ONE group of 4 MMAs, so both kernels
-// run at the speed of their HBM stream (the output map for fprop, dY for wgrad).
+// load.  Instead the input rows a tile touches come in ONCE as a patch of the zero-padded image (a
+// ring of TMA patches, see "input patches" below), builder warps assemble the COLUMN TILE from it in
+// shared memory — one 128-byte row of K (padded to 32) fp32 values per output pixel, written
+// directly in the swizzled layout the UMMA descriptor expects — and tcgen05.mma contracts it.  The
+// column matrix never exists in HBM, and both kernels are bounded by their HBM stream (the output
+// map for fprop, dY for wgrad).
 //
 //   fprop : D[128 px][F]  = Xcol[128 px][32] (K-major, SW128)      * W[F][32]^T (K-major, SW128)
+//           warp 0 MMA, warp 1 patch producer, 8 builder warps, two sets of 8 epilogue warps that
+//           take alternate tiles (TMEM -> bias/ReLU -> swizzled staging tile -> TMA store, plus the
+//           BatchNorm column sums of the tile when asked).
 //   wgrad : D[128 f][32k] += dY[64 px][128 f]^T (MN-major via TMA) * Xcol[64 px][32] (MN-major),
 //           both in the 128B-swizzle/32B-atom layout fp32 MN-major operands need; column K of Xcol
 //           is the constant 1, so D[f][K] = sum_p dY[p][f] is the bias gradient for free.

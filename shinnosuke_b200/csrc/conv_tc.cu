@@ -8,13 +8,15 @@
 //     zero fill.  Rows land 128 B apart with the 128-byte swizzle = UMMA's K-major layout.
 //   * B tile  = BN filters x 32 contraction elements of the [F][kh*kw*C] filter matrix (2-D box).
 //   * one CTA per SM, persistent over output tiles; warp 0 = TMA producer, warp 1 = MMA issuer,
-//     warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU -> global).  smem ring of STAGES
-//     k-blocks (full/empty mbarriers), two TMEM accumulator buffers so the epilogue of tile i
-//     overlaps the MMAs of tile i+1.
+//     warps 2..9 = epilogue (TMEM -> registers -> bias/ReLU -> swizzled staging tile -> TMA store,
+//     optionally the BatchNorm column sums of the tile).  smem ring of STAGES k-blocks (full/empty
+//     mbarriers), two TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs of
+//     tile i+1.  The same kernel runs bf16 operand copies (kind::f16, 64 elements per 128-byte row).
 //   dgrad (stride 1) is the same kernel on dY with the filters flipped and transposed
 //   (flip_transpose_filters_kernel), padding k-1-p.
 //
-// wgrad ("MN-major" kernel, conv_wgrad_kernel):
+// wgrad (conv_wgrad_halo.cu is the kernel the layers use; the "MN-major" conv_wgrad_kernel below is
+// the fallback for shapes it does not take):
 //     dW[f][tap][c] += sum_{p} dY[p][f] * X[p shifted by tap][c]
 //   the contraction runs over pixels, the slow index of both operands, so both are MN-major
 //   UMMA operands: A = 4 TMA boxes (32 f x 32 px) of dY, B = C/32 boxes (32 c, tw, th, tn) of X,
