@@ -174,7 +174,8 @@ def kernel_work(name, a, precision):
     """Algorithmic work of one launch from its integer arguments (SURVEY.md 8(d) formulas).
     Returns (flops, bytes): the bytes are the tensors the operation must read and write once."""
     conv = ('sn_conv2d_fprop', 'sn_conv2d_dgrad', 'sn_conv2d_wgrad', 'sn_conv2d_fprop_bf16', 'sn_conv2d_dgrad_bf16',
-            'sn_conv2d_wgrad_bf16', 'sn_conv2d_fprop_stats', 'sn_conv2d_fprop_bf16_stats')
+            'sn_conv2d_wgrad_bf16', 'sn_conv2d_fprop_stats', 'sn_conv2d_fprop_bf16_stats', 'sn_conv2d_fprop_x3',
+            'sn_conv2d_dgrad_x3', 'sn_conv2d_wgrad_x3')
     if name in conv:
         N, C, H, W, F, kh, kw, stride, ph, pw = a[:10]
         oh = (H + 2 * ph - kh) // stride + 1
@@ -437,7 +438,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='cfg3', choices=sorted(CONFIGS))
     ap.add_argument('--per-gpu-batch', type=int, default=0)
-    ap.add_argument('--precision', default='bf16', choices=['fp32', 'tf32', 'bf16'])
+    ap.add_argument('--precision', default='bf16', choices=['fp32', 'tf32x3', 'tf32', 'bf16'])
     ap.add_argument('--kernel-table', default='', help='write the per-kernel CUDA-event table (JSON) here')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--sync-bn', action='store_true', help='cross-replica BatchNorm statistics (exact data parallelism; N > 1)')

@@ -144,6 +144,27 @@ SN_API int sn_pad2d_fwd(const float *x, float *y, int N, int H, int W, int C, in
 SN_API int sn_pad2d_bwd(const float *dy, float *dx, int N, int H, int W, int C, int pad_h, int pad_w,
                  int accumulate, void *stream);
 
+/* 3xTF32: a near-fp32 tier on the tensor pipe (SURVEY.md 8(c) "FFMA or 3xTF32").
+ * x*w = xh*wh + xh*wl + xl*wh + O(2^-22) with xh = the 10-mantissa-bit truncation the tensor core
+ * applies to an fp32 operand anyway and xl = x - xh rounded to 10 bits (sn_split_tf32_lo).  Each entry
+ * point runs the tf32 kernel three times, accumulating in fp32.  Every operator is within 1e-5 of
+ * float64; because the tensor core's fp32 accumulation is not FFMA's round-to-nearest, training
+ * trajectories drift to ~3e-5, so this is precision='tf32x3', not the 'fp32' tier.  op: 0 = fprop,
+ * 1 = dgrad, 2 = wgrad; unsupported shapes (sn_conv2d_x3_supported == 0) use the fp32-pointer entry
+ * points with SN_PREC_FP32.  dgrad workspace: 2*C*F*kh*kw floats. */
+SN_API int sn_split_tf32_lo(const float *src, float *dst_lo, long long n, void *stream);
+SN_API int sn_conv2d_x3_supported(int op, int N, int C, int H, int W, int F, int kh, int kw,
+                           int stride, int pad_h, int pad_w);
+SN_API int sn_conv2d_fprop_x3(const float *x, const float *x_lo, const float *w, const float *w_lo, const float *bias,
+                       float *y, int N, int C, int H, int W, int F, int kh, int kw,
+                       int stride, int pad_h, int pad_w, int act, void *stream);
+SN_API int sn_conv2d_dgrad_x3(const float *dy, const float *dy_lo, const float *w, float *dx,
+                       int N, int C, int H, int W, int F, int kh, int kw,
+                       int stride, int pad_h, int pad_w, int accumulate, void *workspace, void *stream);
+SN_API int sn_conv2d_wgrad_x3(const float *x, const float *x_lo, const float *dy, const float *dy_lo, float *dw, float *db,
+                       int N, int C, int H, int W, int F, int kh, int kw,
+                       int stride, int pad_h, int pad_w, void *stream);
+
 /* bf16 tier (north_star: "bf16 inputs and fp32 accumulation", 1e-2 against float64).  The
  * operands are bf16 COPIES made with sn_cast_f32_to_bf16 (x, dY) / sn_flip_transpose_filters_bf16
  * (filters for dgrad); accumulators, bias, activation, outputs and weight gradients stay fp32.

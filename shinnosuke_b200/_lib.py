@@ -135,5 +135,7 @@ class _Lib(object):
 lib = _Lib()
 
 ACT = {'linear': 0, 'relu': 1}
-PRECISION = {'fp32': 0, 'tf32': 1, 'bf16': 2}
+# 'fp32'   : 1e-5 tier, CUDA-core FFMA kernels
+# 'tf32x3' : 3xTF32 on the tensor pipe for the convolutions (every operator within 1e-5, trajectories 5e-5), fp32 elsewhere
+PRECISION = {'fp32': 0, 'tf32x3': 0, 'tf32': 1, 'bf16': 2}
 POOL_MODE = {'reshape': 0, 'im2col': 1}

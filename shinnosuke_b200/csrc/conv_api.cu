@@ -1,5 +1,6 @@
 // extern "C" entry points of Conv2D and Dense; picks the kernel family for the requested tier.
 #include "common.cuh"
+#include <stdlib.h>
 using namespace sn;
 
 namespace sn {
@@ -12,6 +13,7 @@ int conv_igemm_tc(const void *x, const void *w, const float *bias, float *out, i
                   int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, bool bf16, double *stats, cudaStream_t st);
 int flip_transpose_filters_bf16(const float *w, void *wt, int F, int C, int kh, int kw, cudaStream_t st);
 int cast_f32_to_bf16(const float *src, void *dst, long long n, cudaStream_t st);
+int split_tf32_lo(const float *src, float *lo, long long n, cudaStream_t st);
 int prepare_weights_bf16(const float *arena, void *shadow, long long n, const long long *tasks, int ntasks, int flip_units, cudaStream_t st);
 int conv_wgrad_tc(const float *x, const float *dy, float *dw, int N, int C, int IH, int IW, int F, int kh, int kw, int OH,
                   int OW, int pad_h, int pad_w, cudaStream_t st);
@@ -169,6 +171,86 @@ int sn_conv2d_wgrad(const float *x, const float *dy, float *dw, float *db, int N
         }
     }
     return conv_wgrad_simt(x, dy, dw, db, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, accumulate, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------ 3xTF32 (near-fp32 tensor-core tier)
+// x*w = xh*wh + xh*wl + xl*wh + O(2^-22): three passes of the tf32 kernels over (x, w), (x_lo, w), (x, w_lo),
+// accumulating in fp32; the hi parts are the fp32 buffers themselves (the tensor core truncates).
+// Measured: every operator within 1e-5 of float64, but the tensor core's fp32 accumulation is not
+// FFMA's round-to-nearest (adding the lo*lo term changes nothing), so multi-step trajectories drift to
+// ~3e-5 where the CUDA-core tier stays under 1e-5: the tier is therefore its own precision='tf32x3'.
+int sn_split_tf32_lo(const float *src, float *dst_lo, long long n, void *stream) {
+    SN_REQUIRE(src && dst_lo && n >= 0, "bad arguments");
+    return split_tf32_lo(src, dst_lo, n, as_stream(stream));
+}
+
+static bool x3_geom(int N, int C, int H, int W, int F, int kh, int kw, int stride, int ph, int pw, int &oh, int &ow) {
+    if (N <= 0 || C <= 0 || F <= 0 || kh <= 0 || kw <= 0 || stride != 1 || ph < 0 || pw < 0 || H + 2 * ph < kh || W + 2 * pw < kw)
+        return false;
+    oh = H + 2 * ph - kh + 1; ow = W + 2 * pw - kw + 1;
+    return true;
+}
+
+int sn_conv2d_x3_supported(int op, int N, int C, int H, int W, int F, int kh, int kw, int stride, int pad_h, int pad_w) {
+    int oh, ow;
+    if (!x3_geom(N, C, H, W, F, kh, kw, stride, pad_h, pad_w, oh, ow)) return 0;
+    if (op == 0) return (F % 4 == 0 && conv_tc_eligible(N, C, oh, ow, F, 1)) ? 1 : 0;
+    if (op == 1) return (kh - 1 - pad_h >= 0 && kw - 1 - pad_w >= 0 && C % 4 == 0 && conv_tc_eligible(N, F, H, W, C, 1)) ? 1 : 0;
+    if (op == 2) return wgrad_halo_eligible(N, C, oh, ow, F, kh, kw, 1) ? 1 : 0;
+    return 0;
+}
+
+int sn_conv2d_fprop_x3(const float *x, const float *x_lo, const float *w, const float *w_lo, const float *bias, float *y, int N, int C,
+                       int H, int W, int F, int kh, int kw, int stride, int pad_h, int pad_w, int act, void *stream) {
+    SN_REQUIRE(x && x_lo && w && w_lo && y, "null tensor");
+    SN_REQUIRE(act == SN_ACT_LINEAR || act == SN_ACT_RELU, "unknown activation");
+    SN_REQUIRE(sn_conv2d_x3_supported(0, N, C, H, W, F, kh, kw, stride, pad_h, pad_w), "shape not supported by the 3xTF32 kernels");
+    int oh, ow;
+    x3_geom(N, C, H, W, F, kh, kw, stride, pad_h, pad_w, oh, ow);
+    cudaStream_t st = as_stream(stream);
+    int e = conv_igemm_tc(x, w, nullptr, y, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, SN_ACT_LINEAR, 0, false, nullptr, st);
+    if (e) return e;
+    e = conv_igemm_tc(x_lo, w, nullptr, y, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, SN_ACT_LINEAR, 1, false, nullptr, st);
+    if (e) return e;
+    return conv_igemm_tc(x, w_lo, bias, y, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, act, 1, false, nullptr, st);
+}
+
+// workspace: 2 * C*F*kh*kw floats (the flipped + transposed filters and their lo parts)
+int sn_conv2d_dgrad_x3(const float *dy, const float *dy_lo, const float *w, float *dx, int N, int C, int H, int W, int F, int kh, int kw,
+                       int stride, int pad_h, int pad_w, int accumulate, void *workspace, void *stream) {
+    SN_REQUIRE(dy && dy_lo && w && dx && workspace, "null tensor");
+    SN_REQUIRE(sn_conv2d_x3_supported(1, N, C, H, W, F, kh, kw, stride, pad_h, pad_w), "shape not supported by the 3xTF32 kernels");
+    int oh, ow;
+    x3_geom(N, C, H, W, F, kh, kw, stride, pad_h, pad_w, oh, ow);
+    cudaStream_t st = as_stream(stream);
+    float *wt = (float *)workspace, *wt_lo = wt + (size_t)C * F * kh * kw;
+    int e = flip_transpose_filters(w, wt, F, C, kh, kw, st);
+    if (e) return e;
+    e = split_tf32_lo(wt, wt_lo, (long long)C * F * kh * kw, st);
+    if (e) return e;
+    const int ph2 = kh - 1 - pad_h, pw2 = kw - 1 - pad_w;
+    e = conv_igemm_tc(dy, wt, nullptr, dx, N, F, oh, ow, C, kh, kw, H, W, ph2, pw2, SN_ACT_LINEAR, accumulate, false, nullptr, st);
+    if (e) return e;
+    e = conv_igemm_tc(dy_lo, wt, nullptr, dx, N, F, oh, ow, C, kh, kw, H, W, ph2, pw2, SN_ACT_LINEAR, 1, false, nullptr, st);
+    if (e) return e;
+    return conv_igemm_tc(dy, wt_lo, nullptr, dx, N, F, oh, ow, C, kh, kw, H, W, ph2, pw2, SN_ACT_LINEAR, 1, false, nullptr, st);
+}
+
+// dw += (always accumulates); db += column sums of dY when non-NULL
+int sn_conv2d_wgrad_x3(const float *x, const float *x_lo, const float *dy, const float *dy_lo, float *dw, float *db, int N, int C, int H,
+                       int W, int F, int kh, int kw, int stride, int pad_h, int pad_w, void *stream) {
+    SN_REQUIRE(x && x_lo && dy && dy_lo && dw, "null tensor");
+    SN_REQUIRE(sn_conv2d_x3_supported(2, N, C, H, W, F, kh, kw, stride, pad_h, pad_w), "shape not supported by the 3xTF32 kernels");
+    int oh, ow;
+    x3_geom(N, C, H, W, F, kh, kw, stride, pad_h, pad_w, oh, ow);
+    cudaStream_t st = as_stream(stream);
+    int e = conv_wgrad_halo_tc(x, dy, dw, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, false, st);
+    if (e) return e;
+    e = conv_wgrad_halo_tc(x_lo, dy, dw, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, false, st);
+    if (e) return e;
+    e = conv_wgrad_halo_tc(x, dy_lo, dw, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, false, st);
+    if (e || !db) return e;
+    return colsum_accumulate(dy, db, (long long)N * oh * ow, F, st);
 }
 
 // ------------------------------------------------------------------------------ bf16 tier

@@ -316,6 +316,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int j = 0; j < CHUNK; j += 4) {
                             float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                                    __uint_as_float(r[j + 3]));
+                            float4 *dst = reinterpret_cast<float4 *>(orow + f0 + j);
+                            // accumulate first: a 3xTF32 pass adds its partial product to the running sum and
+                            // only the last pass carries the bias and the activation
+                            if (p.accumulate) { float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
                             if (p.bias) {
                                 const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + f0 + j));
                                 v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -323,8 +327,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             if (p.act == SN_ACT_RELU) {
                                 v.x = relu_keep_sign(v.x); v.y = relu_keep_sign(v.y); v.z = relu_keep_sign(v.z); v.w = relu_keep_sign(v.w);
                             }
-                            float4 *dst = reinterpret_cast<float4 *>(orow + f0 + j);
-                            if (p.accumulate) { float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
                             *dst = v;
                         }
                     } else {
@@ -333,9 +335,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             const int f = f0 + j;
                             if (f < p.F) {
                                 float v = __uint_as_float(r[j]);
+                                if (p.accumulate) v += orow[f];
                                 if (p.bias) v += __ldg(p.bias + f);
                                 if (p.act == SN_ACT_RELU) v = relu_keep_sign(v);
-                                if (p.accumulate) v += orow[f];
                                 orow[f] = v;
                             }
                         }
@@ -444,6 +446,27 @@ __global__ void __launch_bounds__(256) prepare_weights_bf16_kernel(const float *
             if (c < C && f < F) wt[((long long)c * kh * kw + tap2) * F + f] = __float2bfloat16_rn(tile[tx][rr]);
         }
         return;
+    }
+}
+
+// lo part of the 3xTF32 split: kind::tf32 truncates its operands to 10 mantissa bits, so
+// hi = x & 0xFFFFE000 is what the tensor core sees of x itself, and x - hi is exact in fp32
+__global__ void split_tf32_lo_kernel(const float *__restrict__ s, float *__restrict__ lo, long long n) {
+    const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x, t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    // lo = x - hi is exact; it is then ROUNDED to 10 mantissa bits here (nearest, ties away), so that the
+    // tensor core's own truncation of it is exact and the split carries no systematic bias of its own
+    auto part = [](float x) {
+        const float lo = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        return __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u);
+    };
+    if (((((uintptr_t)s) | ((uintptr_t)lo)) & 15) == 0) {
+        for (long long i = t; i < n4; i += stride) {
+            const float4 v = ldg4(s + 4 * i);
+            *reinterpret_cast<float4 *>(lo + 4 * i) = make_float4(part(v.x), part(v.y), part(v.z), part(v.w));
+        }
+        for (long long i = 4 * n4 + t; i < n; i += stride) lo[i] = part(s[i]);
+    } else {
+        for (long long i = t; i < n; i += stride) lo[i] = part(s[i]);
     }
 }
 
@@ -810,6 +833,12 @@ int prepare_weights_bf16(const float *arena, void *shadow, long long n, const lo
     if (cast_units + flip_units == 0) return SN_OK;
     prepare_weights_bf16_kernel<<<cast_units + flip_units, 256, 0, st>>>(arena, (__nv_bfloat16 *)shadow, n, cast_units, tasks, ntasks);
     return after_launch("prepare_weights_bf16_kernel");
+}
+
+int split_tf32_lo(const float *src, float *lo, long long n, cudaStream_t st) {
+    if (n <= 0) return SN_OK;
+    split_tf32_lo_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(src, lo, n);
+    return after_launch("split_tf32_lo_kernel");
 }
 
 int cast_f32_to_bf16(const float *src, void *dst, long long n, cudaStream_t st) {

@@ -91,6 +91,21 @@ class Conv2D(Layer):
         geom = (N, C, H, Wd, F, kh, kw, self.stride, self.pad_size[0], self.pad_size[1])
         st = current_stream()
         self._xb = None
+        self._x_lo = None
+        if self.precision == 'tf32x3' and self._x3_ok(0, geom):
+            # near-fp32 tier on the tensor pipe: x*w = xh*wh + xh*wl + xl*wh (3xTF32), lo parts split off here
+            self._x_lo = self._buf('x_lo', x.shape, x.layout)
+            w_lo = self._buf('w_lo', (W.size,), 'flat')
+            lib.sn_split_tf32_lo(x.ptr, self._x_lo.ptr, x.size, st)
+            lib.sn_split_tf32_lo(W.output_tensor.ptr, w_lo.ptr, W.size, st)
+            lib.sn_conv2d_fprop_x3(x.ptr, self._x_lo.ptr, W.output_tensor.ptr, w_lo.ptr, b.output_tensor.ptr, y.ptr, *geom,
+                                   self._act_code(), st)
+            bn = getattr(self, '_stats_to', None)
+            if bn is not None:
+                bn._stats_from = None
+            self.output_tensor = y
+            super(Conv2D, self).forward(is_training)
+            return
         bf16 = self.precision == 'bf16' and self._bf16_ok(0, geom)
         # the BatchNormalization fed by this layer alone takes its batch statistics from our epilogue
         bn = getattr(self, '_stats_to', None) if is_training else None
@@ -159,6 +174,13 @@ class Conv2D(Layer):
         return (bool(bf16 and self._xb is not None and self._bf16_ok(2, geom)),
                 bool(bf16 and needs_dx and self._bf16_ok(1, geom)))
 
+    def _x3_ok(self, op, geom):
+        key = ('x3', op) + tuple(geom)
+        cache = self.__dict__.setdefault('_bf16_support', {})
+        if key not in cache:
+            cache[key] = bool(lib.load().sn_conv2d_x3_supported(op, *geom))
+        return cache[key]
+
     def _bf16_ok(self, op, geom):
         key = (op,) + tuple(geom)
         cache = self.__dict__.setdefault('_bf16_support', {})
@@ -188,6 +210,34 @@ class Conv2D(Layer):
             lib.sn_relu_bwd(g.ptr, y.ptr, g.size, st)
         geom = (N, C, H, Wd, F, kh, kw, self.stride, self.pad_size[0], self.pad_size[1])
         needs_dx = any(layer.require_grads for layer in self.inbounds)
+        if self.precision == 'tf32x3':
+            needs_dx = any(layer.require_grads for layer in self.inbounds)
+            w3 = (W.require_grads or b.require_grads) and self._x3_ok(2, geom)
+            d3 = needs_dx and self._x3_ok(1, geom)
+            if w3 or d3:
+                g_lo = self._buf('g_lo', g.shape, g.layout)
+                lib.sn_split_tf32_lo(g.ptr, g_lo.ptr, g.size, st)
+                db = b.grads.ptr if (b.require_grads and not self.__dict__.pop('_db_done', False)) else None
+                if w3:
+                    x_lo = self._x_lo
+                    if x_lo is None:
+                        x_lo = self._buf('x_lo', x.shape, x.layout)
+                        lib.sn_split_tf32_lo(x.ptr, x_lo.ptr, x.size, st)
+                    lib.sn_conv2d_wgrad_x3(x.ptr, x_lo.ptr, g.ptr, g_lo.ptr, W.grads.ptr, db, *geom, st)
+                elif W.require_grads or db is not None:
+                    lib.sn_conv2d_wgrad(x.ptr, g.ptr, W.grads.ptr, db, *geom, 1, prec, st)
+                if d3:
+                    ws3 = self._buf('dgrad_ws3', (2 * W.size,), 'flat').ptr
+                    for layer in self.inbounds:
+                        self._push_grad(layer, lambda dst, acc: lib.sn_conv2d_dgrad_x3(
+                            g.ptr, g_lo.ptr, W.output_tensor.ptr, dst.ptr, *geom, acc, ws3, st))
+                else:
+                    ws_bytes = lib.sn_conv2d_dgrad_workspace(C, F, kh, kw, prec)
+                    ws = self._buf('dgrad_ws', (ws_bytes // 4,), 'flat').ptr if ws_bytes else None
+                    for layer in self.inbounds:
+                        self._push_grad(layer, lambda dst, acc: lib.sn_conv2d_dgrad(
+                            g.ptr, W.output_tensor.ptr, dst.ptr, *geom, acc, prec, ws, st))
+                return
         wgrad_bf16, dgrad_bf16 = self._bf16_grad_plan()
         # a fused BN+pool backward may already have delivered the bias gradient (column sums of
         # our gradient map) and the bf16 copy of that map while it wrote it

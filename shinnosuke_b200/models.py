@@ -99,7 +99,7 @@ class _Trainer(object):
                 prev = layer.inbounds[0] if len(layer.inbounds) == 1 else None
                 layer._stats_from = None
                 if isinstance(prev, Conv2D):
-                    feeds = fuse and precision != 'fp32' and len(prev.outbound_layers) == 1
+                    feeds = fuse and precision in ('tf32', 'bf16') and len(prev.outbound_layers) == 1
                     prev._stats_to = layer if feeds else None
         # Flatten -> Dense with nobody else on either side: the NHWC map is handed through as it is and
         # the Dense keeps its weight rows in (i,j,c) order (no transpose kernel forward or backward)

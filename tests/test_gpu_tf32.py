@@ -301,3 +301,43 @@ def test_fp32_tier_never_takes_epilogue_statistics():
     assert not out['epilogue']['used']
     for key in ('y', 'dx', 'dgamma'):
         np.testing.assert_array_equal(out['epilogue'][key], out['own'][key])
+
+
+# ------------------------------------------------------------------ precision='tf32x3' (3xTF32)
+TOL_X3_OP = 1e-5          # per operator: the fp32 tier's bound
+TOL_X3_TRAJ = 5e-5        # training trajectories: the tensor core's fp32 accumulation is not FFMA's round-to-nearest
+
+
+@pytest.mark.parametrize('shape', [
+    (4, 64, 16, 16, 128, 3, 1, 'SAME', 'relu'),
+    (6, 128, 8, 8, 256, 3, 1, 'SAME', 'relu'),
+    (24, 256, 4, 4, 256, 3, 1, 'SAME', 'linear'),
+    (2, 64, 32, 32, 64, 3, 1, 'SAME', 'relu'),
+    (12, 64, 8, 8, 96, 5, 1, 'SAME', 'linear'),
+    (8, 32, 16, 16, 48, 3, 1, 'SAME', 'linear'),
+])
+def test_conv2d_3xtf32_meets_the_fp32_bound(shape):
+    """x*w = xh*wh + xh*wl + xl*wh on the tensor pipe (csrc/conv_api.cu): forward, dW, db and dX of one
+    layer within 1e-5 of the float64 oracle, where single-pass TF32 is at ~5e-4."""
+    from shinnosuke_b200._lib import lib
+    N, C, H, W, F, k, stride, padding, act = shape
+    pad = (k - 1) // 2 if padding == 'SAME' else 0
+    assert lib.load().sn_conv2d_x3_supported(0, N, C, H, W, F, k, k, stride, pad, pad)
+    out = _run_conv(shape, 'tf32x3')
+    for name, (got, ref) in out.items():
+        assert rel_err(got, ref) < TOL_X3_OP, name
+    single = _run_conv(shape, 'tf32')
+    assert rel_err(single['y'][0], single['y'][1]) > 10 * rel_err(out['y'][0], out['y'][1])      # the split really is in effect
+
+
+def test_trajectory_3xtf32_cfg3_small():
+    g = load_golden('traj_cfg3_small')
+    from test_gpu_train import _vgg, _data
+    r, X = _data((16, 3, 32, 32), kind='normal')
+    Y = O.to_categorical(np.concatenate([np.arange(10), r.integers(0, 10, 6)]))
+    m = _vgg('tf32x3')
+    m.fit(X, Y, batch_size=8, epochs=1, shuffle=False, validation_ratio=0., verbose=0)
+    assert np.allclose(m.train_loss, g['train_loss'], rtol=TOL_X3_TRAJ)
+    convs = [l for l in m.layers if l.__class__.__name__ == 'Conv2D']
+    assert rel_err(np.asarray(convs[0].variables[0].output_tensor), g['conv1W']) < TOL_X3_TRAJ
+    assert rel_err(np.asarray(m.layers[-1].variables[0].output_tensor), g['denseW']) < TOL_X3_TRAJ
