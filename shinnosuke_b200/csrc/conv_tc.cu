@@ -27,11 +27,14 @@
 #include "bn_common.cuh"
 #include <cuda_bf16.h>
 #include <mutex>
+#include <cstdlib>
 
 using namespace sn;
 using namespace sn::tc;
 
 namespace sn {
+
+long long g_igemm_pair_launches = 0;
 
 EncodeTiledFn get_encode_tiled() {
     static EncodeTiledFn fn = nullptr;
@@ -140,8 +143,11 @@ constexpr int EPI_STAGE_BYTES = EPI_WARPS * 4096;       // one 32-row x 128-byte
 // KS = k-blocks (128-byte K slabs) per pipeline stage.  A stage must carry enough MMA time
 // (KS * 128*BN*32 / 2048 cycles) to amortise the per-stage barrier round trips of the single
 // producer and issuer threads; narrow tiles therefore use KS = 2.
-template <int BN, int KS> struct IgemmCfg {
-    static constexpr int B_BYTES = BN * BK * 4;
+// PAIR: two CTAs of a cluster share every tile pair (cta_group::2, M = 256): each CTA keeps its own
+// 128 pixels of A and only HALF of the filter tile, which cuts the operand bytes an SM has to take
+// in per MMA cycle from (128 + BN) to (128 + BN/2) rows — the single-CTA tile is bound by that ingest.
+template <int BN, int KS, bool PAIR = false> struct IgemmCfg {
+    static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 4;
     static constexpr int SLAB_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGE_BYTES = KS * SLAB_BYTES;
     static constexpr int RING_BUDGET = 232448 - (EPI_STAGE_BYTES + STAT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/);
@@ -153,11 +159,11 @@ template <int BN, int KS> struct IgemmCfg {
 
 // BF16: the operands are bf16 copies (64 elements per 128-byte row, UMMA K = 16, kind::f16); the
 // accumulators, bias, activation and output stay fp32.  Byte geometry of the tiles is identical.
-template <int BN, int KS, bool BF16>
+template <int BN, int KS, bool BF16, bool PAIR>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const IgemmParams p) {
-    using Cfg = IgemmCfg<BN, KS>;
+    using Cfg = IgemmCfg<BN, KS, PAIR>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *epi_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                 // 1024-byte aligned (stage sizes are)
@@ -171,7 +177,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role index
     const int lane = threadIdx.x & 31;
     constexpr int BKE = BF16 ? 64 : 32;               // contraction elements per 128-byte k-block
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    // PAIR: the two CTAs of a cluster walk the same sequence of tile pairs; CTA `rank` owns pixel tile
+    // 2*i + rank of pair i (tiles_m is even, host-checked), both share the filter tile
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;
+    const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int num_tiles = (PAIR ? (p.tiles_m >> 1) : p.tiles_m) * p.tiles_n;
     const int kblocks = p.ntaps * p.cblocks;          // a multiple of KS (host-checked)
     const int kstages = kblocks / KS;
 
@@ -179,12 +190,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS); }
+        // PAIR: the leader's accumulator-free barrier collects the epilogue warps of both CTAs
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
         fence_barrier_init();
     }
+    if constexpr (PAIR) cluster_sync_all();            // the peer's barriers exist before anything signals them
     if (warp == 1) {
-        tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if constexpr (PAIR) { tmem_alloc_pair(tmem_ptr, Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); tmem_relinquish(); }
     }
     if (p.stats)
         for (int i = threadIdx.x; i < 4 * 2 * STAT_MAX_F; i += IG_THREADS) sstat[i] = 0.f;
@@ -200,21 +213,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // `if (lane == 0)` every operand needed an R2UR move per instruction (~100 cycles per MMA).
         {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int tm = tile / p.tiles_n, tn_idx = tile % p.tiles_n;
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+                const int tm = PAIR ? 2 * (tile / p.tiles_n) + rank : tile / p.tiles_n, tn_idx = tile % p.tiles_n;
                 int n0, h0;
                 if (p.bands_per_image) { n0 = tm / p.bands_per_image; h0 = (tm % p.bands_per_image) * p.th; }
                 else { n0 = tm * p.tn; h0 = 0; }
                 int tap = 0, cb = 0, u = 0, v = 0;
                 for (int ks = 0; ks < kstages; ++ks) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (elect_one()) mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    // PAIR: both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
+                    if (PAIR ? (rank == 0 && elect_one()) : elect_one())
+                        mbar_expect_tx(&full_bar[stage], PAIR ? 2 * Cfg::STAGE_BYTES : Cfg::STAGE_BYTES);
+                    const uint32_t full_leader = PAIR ? map_to_rank(smem_u32(&full_bar[stage]), 0) : 0u;
 #pragma unroll
                     for (int s = 0; s < KS; ++s) {
                         uint8_t *sa = smem + stage * Cfg::STAGE_BYTES + s * Cfg::SLAB_BYTES;
                         if (elect_one()) {
-                            tma_load_4d(sa, &tmA, &full_bar[stage], cb * BKE, v - p.pad_w, h0 + u - p.pad_h, n0);
-                            tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], tap * p.C + cb * BKE, tn_idx * BN);
+                            if constexpr (PAIR) {
+                                tma_load_4d_pair(sa, &tmA, full_leader, cb * BKE, v - p.pad_w, h0 + u - p.pad_h, n0);
+                                tma_load_2d_pair(sa + A_BYTES, &tmB, full_leader, tap * p.C + cb * BKE, tn_idx * BN + rank * (BN / 2));
+                            } else {
+                                tma_load_4d(sa, &tmA, &full_bar[stage], cb * BKE, v - p.pad_w, h0 + u - p.pad_h, n0);
+                                tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], tap * p.C + cb * BKE, tn_idx * BN);
+                            }
                         }
                         if (++cb == p.cblocks) { cb = 0; ++tap; if (++v == p.taps_w) { v = 0; ++u; } }
                     }
@@ -225,13 +246,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (warp-uniform control flow, lane 0 issues) =====================
-        {
-            constexpr uint32_t idesc = make_idesc(BF16 ? 1 : 2, BM, BN, 0, 0);
+        // PAIR: only the leader CTA issues; one instruction drives the tensor cores of both SMs
+        if (!PAIR || rank == 0) {
+            constexpr uint32_t idesc = make_idesc(BF16 ? 1 : 2, PAIR ? 2 * BM : BM, BN, 0, 0);
             int stage = 0; uint32_t phase = 0;
             int iter = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++iter) {
                 const int acc = iter & 1;
-                mbar_wait(&tmem_empty[acc], ((iter >> 1) & 1) ^ 1);
+                if constexpr (PAIR) mbar_wait_cluster(&tmem_empty[acc], ((iter >> 1) & 1) ^ 1);
+                else mbar_wait(&tmem_empty[acc], ((iter >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int ks = 0; ks < kstages; ++ks) {
@@ -246,16 +269,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                             for (int k = 0; k < BK / UK; ++k) {
                                 // advancing K inside the 128-byte swizzle row: +32 bytes = +2 descriptor units
-                                if constexpr (BF16) mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | s | k) != 0 ? 1u : 0u);
-                                else mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | s | k) != 0 ? 1u : 0u);
+                                const uint32_t accum = (ks | s | k) != 0 ? 1u : 0u;
+                                if constexpr (PAIR) {
+                                    if constexpr (BF16) mma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+                                    else mma_tf32_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+                                } else {
+                                    if constexpr (BF16) mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+                                    else mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+                                }
                             }
                         }
                     }
-                    if (elect_one()) mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+                    if (elect_one()) { if constexpr (PAIR) mma_commit_pair(&empty_bar[stage]); else mma_commit(&empty_bar[stage]); }
                     __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (elect_one()) mma_commit(&tmem_full[acc]);        // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (of both CTAs)
+                if (elect_one()) { if constexpr (PAIR) mma_commit_pair(&tmem_full[acc]); else mma_commit(&tmem_full[acc]); }
                 __syncwarp();
             }
         }
@@ -264,8 +295,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int q = warp & 3;                  // TMEM lane quarter this warp may read
         const int half = (warp - 2) >> 2;        // which of the quarter's EPI_WARPS/4 warps: chunks half, half + EPI_WARPS/4, ...
         int iter = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
-            const int tm = tile / p.tiles_n, tn_idx = tile % p.tiles_n;
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++iter) {
+            const int tm = PAIR ? 2 * (tile / p.tiles_n) + rank : tile / p.tiles_n, tn_idx = tile % p.tiles_n;
             const int acc = iter & 1;
             mbar_wait(&tmem_full[acc], (iter >> 1) & 1);
             tc_fence_after();
@@ -346,7 +377,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if constexpr (PAIR) mbar_arrive_cluster(map_to_rank(smem_u32(&tmem_empty[acc]), 0));
+                else mbar_arrive(&tmem_empty[acc]);
+            }
         }
         if (p.tma_store && lane == 0) tma_store_wait_all();
         __syncwarp();
@@ -364,10 +398,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();            // neither CTA leaves while the other may still signal it
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -683,16 +719,43 @@ int launch_igemm_ks(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtens
     using Cfg = IgemmCfg<BN, KS>;
     static bool configured = false;
     if (!configured) {
-        SN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, KS, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        SN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, KS, BF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
     int tiles = p.tiles_m * p.tiles_n;
     int grid = tiles < num_sms() ? tiles : num_sms();
-    conv_igemm_kernel<BN, KS, BF16><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmO, p);
+    conv_igemm_kernel<BN, KS, BF16, false><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmO, p);
     return after_launch("conv_igemm_kernel");
 }
+// CTA pairs: clusters of two, one pair per TPC, persistent over tile pairs
+template <int BN, bool BF16>
+int launch_igemm_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO, const IgemmParams &p, cudaStream_t st) {
+    using Cfg = IgemmCfg<BN, 1, true>;
+    static bool configured = false;
+    if (!configured) {
+        SN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, 1, BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int pairs = (p.tiles_m / 2) * p.tiles_n, max_pairs = num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (pairs < max_pairs ? pairs : max_pairs));
+    cfg.blockDim = dim3(IG_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SN_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, 1, BF16, true>, tmA, tmB, tmO, p));
+    ++sn::g_igemm_pair_launches;
+    return after_launch("conv_igemm_kernel (pair)");
+}
 template <int BN>
-int launch_igemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO, const IgemmParams &p, bool bf16, cudaStream_t st) {
+int launch_igemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO, const IgemmParams &p, bool bf16, bool pair,
+                 cudaStream_t st) {
+    if constexpr (BN >= 128) {
+        if (pair) return bf16 ? launch_igemm_pair<BN, true>(tmA, tmB, tmO, p, st) : launch_igemm_pair<BN, false>(tmA, tmB, tmO, p, st);
+    }
     const int kblocks = p.ntaps * p.cblocks;
     if constexpr (BN <= 64) {             // (a 2-slab stage of a 128-wide tile would leave only 2 ring stages)
         if ((kblocks % 2) == 0)
@@ -704,6 +767,19 @@ int launch_igemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorM
 }  // namespace
 
 namespace sn {
+
+// When do CTA pairs pay?  Measured (profiles/r01_igemm_pair_vs_single.txt): 256-wide tiles with at
+// least four waves of tile pairs gain 7-8 % (tf32 reaches 725 TF/s = 89 % of the TF32 roof at
+// batch 2048); with fewer tiles the longer barrier round trips across the pair cost more than the
+// halved filter traffic saves, and 128-wide tiles never gained.
+// SN_IGEMM_PAIR=0 never pairs, =2 pairs every eligible shape (tests, A/B measurements).
+static bool igemm_use_pairs(int BN, int tiles_m, int tiles_n) {
+    static int mode = -1;
+    if (mode < 0) { const char *e = getenv("SN_IGEMM_PAIR"); mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }
+    if (mode == 0 || BN < 128 || (tiles_m % 2) != 0) return false;
+    if (mode == 2) return true;
+    return BN == 256 && (tiles_m / 2) * tiles_n >= 4 * (num_sms() / 2);
+}
 
 // Can the tensor-core path take this forward-style convolution (stride 1)?
 bool conv_tc_eligible(int N, int C, int OH, int OW, int F, int stride, bool bf16) {
@@ -733,7 +809,10 @@ int conv_igemm_tc(const void *x, const void *w, const float *bias, float *out, i
     long long ktot = (long long)kh * kw * C;
     long long bdims[2] = {ktot, F};
     long long bstr[2] = {1, ktot};
-    int bbox[2] = {bke, BN > 256 ? 256 : BN};
+    // CTA pairs for the wide tiles (each CTA loads half of the filter tile): needs an even number of pixel tiles
+    const int tiles_m = (int)(((long long)N * OH * OW + BM - 1) / BM);
+    const bool pair = igemm_use_pairs(BN, tiles_m, (F + BN - 1) / BN);
+    int bbox[2] = {bke, pair ? BN / 2 : BN};
     e = make_tmap(&tmB, w, 2, bdims, bstr, bbox, false, bf16);
     if (e) return e;
     IgemmParams p{};
@@ -757,11 +836,11 @@ int conv_igemm_tc(const void *x, const void *w, const float *bias, float *out, i
         p.stats = stats;          // zero on entry (caller's contract): no memset node in the step graph
     }
     switch (BN) {
-        case 16: return launch_igemm<16>(tmA, tmB, tmO, p, bf16, st);
-        case 32: return launch_igemm<32>(tmA, tmB, tmO, p, bf16, st);
-        case 64: return launch_igemm<64>(tmA, tmB, tmO, p, bf16, st);
-        case 128: return launch_igemm<128>(tmA, tmB, tmO, p, bf16, st);
-        default: return launch_igemm<256>(tmA, tmB, tmO, p, bf16, st);
+        case 16: return launch_igemm<16>(tmA, tmB, tmO, p, bf16, false, st);
+        case 32: return launch_igemm<32>(tmA, tmB, tmO, p, bf16, false, st);
+        case 64: return launch_igemm<64>(tmA, tmB, tmO, p, bf16, false, st);
+        case 128: return launch_igemm<128>(tmA, tmB, tmO, p, bf16, pair, st);
+        default: return launch_igemm<256>(tmA, tmB, tmO, p, bf16, pair, st);
     }
 }
 

@@ -5,6 +5,7 @@
 namespace sn {
 static thread_local char g_err[512] = "";
 long long g_launch_count = 0;
+extern long long g_igemm_pair_launches;      // conv_tc.cu
 void set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -20,6 +21,7 @@ int sn_abi_version(void) { return SN_ABI_VERSION; }
 const char *sn_last_error(void) { return g_err; }
 long long sn_launch_count(void) { return g_launch_count; }
 void sn_launch_count_reset(void) { g_launch_count = 0; }
+long long sn_igemm_pair_launches(void) { return g_igemm_pair_launches; }
 
 int sn_device_count(int *count) {
     SN_REQUIRE(count, "null out pointer");

@@ -341,3 +341,37 @@ def test_trajectory_3xtf32_cfg3_small():
     convs = [l for l in m.layers if l.__class__.__name__ == 'Conv2D']
     assert rel_err(np.asarray(convs[0].variables[0].output_tensor), g['conv1W']) < TOL_X3_TRAJ
     assert rel_err(np.asarray(m.layers[-1].variables[0].output_tensor), g['denseW']) < TOL_X3_TRAJ
+
+
+def test_cta_pair_tiles_forced_on():
+    """The cta_group::2 variant of the implicit-GEMM kernel (two CTAs share a 256-pixel tile pair, each
+    loads half of the filter tile) is picked by shape and only pays on large problems; here
+    SN_IGEMM_PAIR=2 forces it wherever it is eligible and the usual parity bounds must hold: 128-wide
+    and 256-wide filter tiles, fprop and dgrad, tf32 and bf16, dyadic data exactly."""
+    import os, subprocess, sys
+    code = r'''
+import sys
+sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
+import test_gpu_tf32 as T
+from shinnosuke_b200._lib import lib
+shapes = [(4, 64, 16, 16, 128, 3, 1, 'SAME', 'relu'),        # 8 pixel tiles, 128-wide filter tile
+          (224, 32, 8, 8, 256, 3, 1, 'SAME', 'linear'),      # 112 pixel tiles, 256-wide filter tile
+          (8, 256, 8, 8, 64, 3, 1, 'SAME', 'linear')]        # dgrad of this one is a 256-filter forward conv
+for shape in shapes:
+    n0 = lib.sn_igemm_pair_launches()
+    for name, (got, ref) in T._run_conv(shape).items():
+        assert T.rel_err(got, ref) < T.TOL_TF32, (shape, name, T.rel_err(got, ref))
+    n1 = lib.sn_igemm_pair_launches()
+    for name, (got, ref) in T._run_conv(shape[:8] + ('linear',), 'bf16').items():
+        assert T.rel_err(got, ref) < T.TOL_BF16, (shape, name, T.rel_err(got, ref))
+    n2 = lib.sn_igemm_pair_launches()
+    assert n1 > n0 and n2 > n1, (shape, n0, n1, n2)
+T.test_tf32_path_is_really_taken_and_exact_on_tf32_representable_data()
+T.test_bf16_kernels_exact_on_bf16_representable_data()
+print('pair launches', lib.sn_igemm_pair_launches())
+'''
+    env = dict(os.environ, SN_IGEMM_PAIR='2')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert 'pair launches' in out.stdout
