@@ -39,6 +39,8 @@ CONFIGS = {
     'cfg4': dict(name='ResNet-style 3x32x32 (functional API): Conv64 + residual block@64 + pool + Conv128 + residual block@128 '
                       '+ pool + Dense10, BatchNorm in the blocks, SGD', shape=(3, 32, 32), per_gpu_batch=128,
                  flops_per_sample=1026.8e6),
+    'cfg5': dict(name='Embedding(1000->64) + LSTM(128) over 64 timesteps + Dense2, SGD (recurrent GEMM path)', shape=(64,),
+                 per_gpu_batch=256, flops_per_sample=3 * 2 * 64 * 192 * 512, classes=2),
 }
 
 
@@ -57,11 +59,14 @@ def synth(cfg, n, seed=1234):
     shape = CONFIGS[cfg]['shape']
     if cfg in ('cfg3', 'cfg4'):
         X = r.standard_normal((n,) + shape, dtype=np.float32)
+    elif cfg == 'cfg5':
+        X = r.integers(0, 1000, (n,) + shape).astype(np.float32)       # token ids travel as float32 values
     else:
         X = r.random((n,) + shape, dtype=np.float32)
-    labels = r.integers(0, 10, n)
-    labels[:10] = np.arange(10)
-    Y = np.eye(10, dtype=np.float32)[labels]
+    classes = CONFIGS[cfg].get('classes', 10)
+    labels = r.integers(0, classes, n)
+    labels[:classes] = np.arange(classes)
+    Y = np.eye(classes, dtype=np.float32)[labels]
     return X, Y
 
 
@@ -86,7 +91,12 @@ def build_model(cfg, precision, sync_bn=False):
         m.compile(optimizer='sgd', loss='sparse_categorical_crossentropy', precision=precision, sync_bn=sync_bn)
         return m
     m = Sequential()
-    if cfg == 'cfg3':
+    if cfg == 'cfg5':
+        from shinnosuke_b200 import Embedding, LSTM
+        m.add(Embedding(1000, 64, input_length=64))
+        m.add(LSTM(128))
+        m.add(Dense(2, activation='softmax'))
+    elif cfg == 'cfg3':
         first = True
         for f in (64, 128, 256, 256):
             kw = dict(input_shape=(None, 3, 32, 32)) if first else {}
@@ -110,7 +120,7 @@ def build_model(cfg, precision, sync_bn=False):
 
 def oracle_spec(cfg):
     from oracle import shinnosuke_oracle as O
-    return {'cfg1': O.spec_cfg1, 'cfg2': O.spec_cfg2, 'cfg3': O.spec_cfg3, 'cfg4': O.spec_cfg4}[cfg]()
+    return {'cfg1': O.spec_cfg1, 'cfg2': O.spec_cfg2, 'cfg3': O.spec_cfg3, 'cfg4': O.spec_cfg4, 'cfg5': O.spec_cfg5}[cfg]()
 
 
 class ClockSampler(object):
@@ -223,6 +233,15 @@ def kernel_work(name, a, precision):
         return 0.0, 12.0 * a[0]
     if name in ('sn_nchw_to_nhwc', 'sn_nhwc_to_nchw'):
         return 0.0, 8.0 * a[0] * a[1] * a[2] * a[3]
+    if name in ('sn_lstm_step_fwd', 'sn_lstm_step_bwd'):
+        # one timestep: the recurrent product h . Wh (N x H x 4H) + the gate tensors once
+        N, H = (a[2], a[3]) if name == 'sn_lstm_step_fwd' else (a[1], a[2])
+        return 2.0 * N * H * 4 * H, 4.0 * (4 * H * H + 2 * N * 4 * H + 4 * N * H)
+    if name in ('sn_embedding_fwd', 'sn_embedding_bwd'):
+        n_idx, vocab, dim = a[:3]
+        return 0.0, 4.0 * n_idx * (1 + 2 * dim)
+    if name == 'sn_swap_leading_axes':
+        return 0.0, 8.0 * a[0] * a[1] * a[2]
     return 0.0, 0.0
 
 
@@ -296,7 +315,7 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = args.config
-    sample_batch = {'cfg3': 64, 'cfg1': 256, 'cfg2': 128, 'cfg4': 32}[cfg]
+    sample_batch = {'cfg3': 64, 'cfg1': 256, 'cfg2': 128, 'cfg4': 32, 'cfg5': 256}[cfg]
     steps = max(1, args.steps)
     value, s_per_step = cpu_oracle_throughput(cfg, sample_batch, steps, max(1, min(args.warmup, 2)))
     cores = os.cpu_count()
@@ -399,8 +418,8 @@ def run_ours(args):
             os.makedirs(os.path.dirname(os.path.abspath(args.kernel_table)), exist_ok=True)
             with open(args.kernel_table, 'w') as f:
                 json.dump(dict(config=cfg, per_gpu_batch=B, precision=precision, step_ms_graph=dev_ms / K, kernels=rows), f, indent=1)
-        cpu_batch = {'cfg3': 64, 'cfg1': 256, 'cfg2': 128, 'cfg4': 32}[cfg]
-        cpu_steps = {'cfg3': 6, 'cfg1': 30, 'cfg2': 200, 'cfg4': 3}[cfg]
+        cpu_batch = {'cfg3': 64, 'cfg1': 256, 'cfg2': 128, 'cfg4': 32, 'cfg5': 256}[cfg]
+        cpu_steps = {'cfg3': 6, 'cfg1': 30, 'cfg2': 200, 'cfg4': 3, 'cfg5': 10}[cfg]
         if world == 1 and not args.no_cpu_baseline:
             cpu_val, _ = cpu_oracle_throughput(cfg, cpu_batch, cpu_steps)
             cpu = dict(value=cpu_val, unit='samples/s', cores=os.cpu_count(), kind='port',

@@ -324,6 +324,30 @@ SN_API int sn_bn_pool_bwd_apply(const float *dy_pool, const uint8_t *code, const
                          float *dx_colsum, double *scratch, int N, int H, int W, int C,
                          int pool_mode, int mask_relu, void *stream);
 
+/* ------------------------------------------------------ Embedding / LSTM */
+/* Embedding.forward, layers/Embeddings.py:56-63: out[i][:] = W[idx[i]][:].  Indices arrive as fp32
+ * VALUES (the minibatch pipeline moves float32; exact below 2^24); out-of-range indices are clamped. */
+SN_API int sn_embedding_fwd(const float *w, const float *idx, float *out, long long n_idx, int vocab, int dim, void *stream);
+/* Embedding.backward, :66-76: np.add.at(W.grads, idx, grads) — dw[idx[i]][:] += dy[i][:] */
+SN_API int sn_embedding_bwd(const float *idx, const float *dy, float *dw, long long n_idx, int vocab, int dim, void *stream);
+/* dst[b][a][:] (=|+=) src[a][b][:] for rows of D floats: batch-major (N,T,D) <-> time-major (T,N,D) */
+SN_API int sn_swap_leading_axes(const float *src, float *dst, int A, int B, int D, int accumulate, void *stream);
+/* One timestep of LSTMCell._forward, layers/Recurrent.py:293-309.  zx[r][0..4H) = x_t . Wx + b (row
+ * stride zx_stride floats; the input half of the reference's fused [h, x] . W product, computed for
+ * all timesteps by one Dense GEMM), wh[4H][H] = the recurrent rows of W transposed, gate columns
+ * (f, u, c~, o).  Writes the gate activations acts[N][4H], c[N][H], h[N][H] and, when h_seq != NULL,
+ * h again at h_seq[r * hseq_stride + j] (the (N,T,H) output of return_sequences=True).
+ * h_prev / c_prev may be NULL (zero initial state).  sigmoid / tanh as utils/Activator.py:58,82. */
+SN_API int sn_lstm_step_fwd(const float *zx, long long zx_stride, const float *wh, const float *h_prev, const float *c_prev,
+                     float *acts, float *c, float *h, float *h_seq, long long hseq_stride, int N, int H, void *stream);
+/* One timestep of LSTMCell._backward, :326-366: dh = dh_ext[r * dh_stride + j] (upstream gradient of
+ * this step, may be NULL) + dz_next . Wh^T (dz of step t+1, NULL at the last step); dz[N][4H] = the
+ * gate pre-activation gradients in the FORWARD column order (f, u, c~, o) — the reference
+ * concatenates them as (o, c~, u, f), which does not match its own W; dc[N][H]
+ * holds dc_{t+1} on entry (ignored when first != 0) and dc_t * f on return. */
+SN_API int sn_lstm_step_bwd(const float *dh_ext, long long dh_stride, const float *dz_next, const float *wh, const float *acts,
+                     const float *c, const float *c_prev, float *dc, float *dz, int N, int H, int first, void *stream);
+
 /* ------------------------------------------------------------------ loss */
 /* Softmax._forward, utils/Activator.py:108-110 (row-wise; the reference's global shift cancels) */
 SN_API int sn_softmax_fwd(const float *logits, float *probs, int rows, int classes, void *stream);

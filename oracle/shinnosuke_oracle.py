@@ -313,6 +313,85 @@ def batchnorm_backward(dy, cache):
 
 
 # --------------------------------------------------------------------------
+# Embedding (layers/Embeddings.py:54-76) and LSTM (layers/Recurrent.py:216-437), BASELINE config 5
+# --------------------------------------------------------------------------
+
+def embedding_forward(w, idx):
+    """layers/Embeddings.py:60: output = W[input]."""
+    return w[np.asarray(idx, dtype=np.int64)]
+
+
+def embedding_backward(w_shape, idx, dy):
+    """layers/Embeddings.py:75-76: np.add.at(W.grads, input, grads)."""
+    dw = np.zeros(w_shape)
+    np.add.at(dw, np.asarray(idx, dtype=np.int64), dy)
+    return dw
+
+
+def _sigmoid(z):
+    return 1 / (1 + np.exp(-z))        # utils/Activator.py:58
+
+
+def lstm_forward(x, w, b, h0=None, c0=None):
+    """LSTMCell._forward, layers/Recurrent.py:265-318.  x (N,T,D); w (H+D, 4H) rows [recurrent;
+    input], gate columns (f, u, c~, o); b (1,4H).  Returns h for every step (N,T,H) and the cache."""
+    n, t_steps, d = x.shape
+    h_units = w.shape[1] // 4
+    h = np.zeros((n, t_steps + 1, h_units)); c = np.zeros((n, t_steps + 1, h_units))
+    if h0 is not None:
+        h[:, 0] = h0
+    if c0 is not None:
+        c[:, 0] = c0
+    f_a = np.zeros((n, t_steps, h_units)); u_a = np.zeros_like(f_a); o_a = np.zeros_like(f_a); ct_a = np.zeros_like(f_a)
+    z = np.zeros((n, t_steps, d + h_units))
+    for t in range(1, t_steps + 1):
+        zt = np.concatenate((h[:, t - 1], x[:, t - 1]), axis=1)          # :294
+        ot = zt.dot(w) + b                                                # :295
+        f = _sigmoid(ot[:, :h_units]); u = _sigmoid(ot[:, h_units:2 * h_units])
+        ct = np.tanh(ot[:, 2 * h_units:3 * h_units]); o = _sigmoid(ot[:, 3 * h_units:])
+        c[:, t] = f * c[:, t - 1] + u * ct                                # :301
+        h[:, t] = o * np.tanh(c[:, t])                                    # :302
+        f_a[:, t - 1], u_a[:, t - 1], o_a[:, t - 1], ct_a[:, t - 1] = f, u, o, ct
+        z[:, t - 1] = zt
+    return h[:, 1:], dict(z=z, h=h, c=c, f=f_a, u=u_a, o=o_a, ct=ct_a, w=w, units=h_units)
+
+
+def lstm_backward(pre_grad, cache, return_sequences, reference_gate_order=False):
+    """LSTMCell._backward, layers/Recurrent.py:321-437.  Returns (dx, dw, db).
+
+    The reference concatenates the gate gradients as (o, c~, u, f) (:358, :406) although the forward
+    columns of W are (f, u, c~, o) (:296-299): its dW, db and dX are therefore not the gradient of
+    its own forward pass.  reference_gate_order=True reproduces the reference bit for bit (pinned by
+    tests/golden/lstm.npz); the default is the correct order, pinned by numeric differentiation in
+    tests/test_oracle_golden.py — that is what the device implements."""
+    z, h, c, w, hu = cache['z'], cache['h'], cache['c'], cache['w'], cache['units']
+    n, t_steps, _ = z.shape
+    dw = np.zeros_like(w); db = np.zeros((1, 4 * hu))
+    dx = np.zeros((n, t_steps, z.shape[2] - hu))
+    da_next = np.zeros((n, hu)); dc_next = np.zeros((n, hu))
+    for t in reversed(range(t_steps)):
+        if return_sequences:
+            da = pre_grad[:, t] + da_next                                  # :327
+        else:
+            da = pre_grad if t == t_steps - 1 else da_next                 # :372, :416
+        tc = np.tanh(c[:, t + 1])
+        f, u, o, ct = cache['f'][:, t], cache['u'][:, t], cache['o'][:, t], cache['ct'][:, t]
+        do = da * tc * o * (1 - o)                                         # :328-329
+        dc = dc_next + da * o * (1 - np.square(tc))                        # :336-337
+        dct = dc * u * (1 - np.square(ct))                                 # :339-340
+        du = dc * ct * u * (1 - u)                                         # :346-347
+        df = dc * c[:, t] * f * (1 - f)                                    # :352-353
+        dgrad = np.concatenate((do, dct, du, df) if reference_gate_order else (df, du, dct, do), axis=1)   # :358
+        dw += z[:, t].T.dot(dgrad)                                         # :360
+        db += dgrad.sum(axis=0, keepdims=True)                             # :362
+        dz = dgrad.dot(w.T)                                                # :364
+        da_next = dz[:, :hu]
+        dc_next = dc * f                                                   # :367
+        dx[:, t] = dz[:, hu:]
+    return dx, dw, db
+
+
+# --------------------------------------------------------------------------
 # loss  (utils/Objectives.py:72-91) — one-hot labels despite the "Sparse" name
 # --------------------------------------------------------------------------
 
@@ -415,6 +494,7 @@ def to_categorical(labels):
 # the bench CPU baseline.  ``spec`` is a list of tuples:
 #   ('conv', F, k, stride, padding, act) | ('pool', p) | ('pool', p, mode) |
 #   ('flatten',) | ('dense', n_out, act) | ('bn',) | ('act', name)
+#   ('embedding', vocab, dim) | ('lstm', units, return_sequences)      (BASELINE config 5)
 #   ('tap', key) | ('add', key)  — residual connection (layers/Base.py:352-411, Add): 'tap'
 #   remembers the current map, 'add' sums it back in; backward sends the gradient both ways.
 # --------------------------------------------------------------------------
@@ -459,6 +539,27 @@ class OracleNet:
                 self.state.append(dict(mm=np.zeros(c), mv=np.ones(c)))
             elif kind in ('act', 'tap', 'add'):
                 self.slots.append(()); self.state.append({})
+            elif kind == 'embedding':
+                _, vocab, dim = op
+                self.slots.append(self._add(np.random.uniform(-0.05, 0.05, size=(vocab, dim))))      # Initializers.py:29-35
+                shape = tuple(shape) + (dim,)
+                self.state.append({})
+            elif kind == 'lstm':
+                # draw order of layers/Recurrent.py:229-240: per gate (f, u, c~, o) the input block
+                # (glorot uniform), then the recurrent block (orthogonal: SVD of a standard normal matrix)
+                _, units, rs = op
+                d = shape[-1]
+                cols = []
+                for _g in range(4):
+                    fan = int(np.sqrt(d * units))          # utils/Initializers.py:12-22: shape tuples always take the sqrt(prod) branch
+                    lim = np.sqrt(6. / (fan + fan))
+                    w_l = np.random.uniform(-lim, lim, size=(d, units))
+                    u_, _s, v_ = np.linalg.svd(np.random.normal(loc=0.0, scale=1.0, size=(units, units)), full_matrices=False)
+                    cols.append(np.concatenate((u_, w_l), axis=0))
+                b = np.zeros((1, 4 * units)); b[:, :units] = 1.0                                     # unit_forget_bias (:251-254)
+                self.slots.append(self._add(np.concatenate(cols, axis=1), b))
+                shape = (shape[0], shape[1], units) if rs else (shape[0], units)
+                self.state.append({})
             else:
                 raise ValueError(kind)
         self.velocity = None
@@ -505,6 +606,12 @@ class OracleNet:
             elif kind == 'add':
                 h = taps[op[1]] + h
                 c = None
+            elif kind == 'embedding':
+                c = h
+                h = embedding_forward(self.params[slot[0]], h)
+            elif kind == 'lstm':
+                hs, c = lstm_forward(h, self.params[slot[0]], self.params[slot[1]])
+                h = hs if op[2] else hs[:, -1]
             caches.append(c)
         return h, caches
 
@@ -536,6 +643,12 @@ class OracleNet:
                 skip[op[1]] = g                     # the same gradient reaches both operands
             elif kind == 'tap':
                 g = g + skip[op[1]]
+            elif kind == 'embedding':
+                self.grads[slot[0]] = self.grads[slot[0]] + embedding_backward(self.params[slot[0]].shape, c, g)
+            elif kind == 'lstm':
+                g, dw, db = lstm_backward(g, c, op[2])
+                self.grads[slot[0]] = self.grads[slot[0]] + dw
+                self.grads[slot[1]] = self.grads[slot[1]] + db
 
     def step(self, xs, ys):
         """One minibatch of models.py:70-92: forward, loss grad, backward sweep,
@@ -580,6 +693,11 @@ def spec_cfg4():
     """stem Conv64 -> residual block @64 -> pool -> Conv128 -> residual block @128 -> pool -> Dense10."""
     s = spec_residual(64) + spec_residual(128) + [('flatten',), ('dense', 10, 'softmax')]
     return s, (None, 3, 32, 32)
+
+
+def spec_cfg5(vocab=1000, dim=64, units=128, timesteps=64, classes=2):
+    """ints [0, vocab) of shape (N, 64) -> Embedding 64 -> LSTM 128 -> Dense 2 (softmax)."""
+    return [('embedding', vocab, dim), ('lstm', units, False), ('dense', classes, 'softmax')], (None, timesteps)
 
 
 def spec_cfg3():

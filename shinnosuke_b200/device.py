@@ -17,6 +17,10 @@ without a transpose kernel (the reference flattens NCHW in (c,i,j) order, layers
 
     ('flat_hwc', C, H, W)    : logical (N, C*H*W) in (c,i,j) order    stored as [N][H][W][C]
     ('dense_w_hwc', C, H, W) : logical (C*H*W, n_out), rows (c,i,j)   stored as [n_out][H][W][C]
+
+and the LSTM weight matrix of layers/Recurrent.py:246-250, rows [recurrent; input], columns (f,u,c~,o):
+
+    ('lstm_w', H)            : logical (H + D, 4H)                    stored as [4H][H] then [4H][D]
 """
 import ctypes
 
@@ -85,6 +89,9 @@ def _to_storage(arr, layout):
     elif isinstance(layout, tuple) and layout[0] == 'dense_w_hwc':
         _, c, h, w = layout
         a = a.T.reshape(a.shape[1], c, h, w).transpose(0, 2, 3, 1)
+    elif isinstance(layout, tuple) and layout[0] == 'lstm_w':
+        h = layout[1]
+        a = np.concatenate((a[:h].T.ravel(), a[h:].T.ravel()))
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
@@ -105,6 +112,10 @@ def _from_storage(a, shape, layout):
         _, c, h, w = layout
         n_in, n_out = shape
         a = a.reshape(n_out, h, w, c).transpose(0, 3, 1, 2).reshape(n_out, n_in).T
+    elif isinstance(layout, tuple) and layout[0] == 'lstm_w':
+        h = layout[1]
+        rows, cols = shape
+        a = np.concatenate((a[:cols * h].reshape(cols, h).T, a[cols * h:].reshape(cols, rows - h).T), axis=0)
     else:
         a = a.reshape(shape)
     return np.ascontiguousarray(a, dtype=np.float64)

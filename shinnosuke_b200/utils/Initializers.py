@@ -7,14 +7,13 @@ import numpy as np
 
 
 def _fans(size):
-    """utils/Initializers.py:13-24."""
+    """utils/Initializers.py:12-22, bug-compatible: the reference tests `np.array(size).ndim`, which is
+    1 for every shape TUPLE, so its 2-D / 4-D branches never run and every scaled initializer uses
+    fan_in = fan_out = int(sqrt(prod(size))).  Identical initial weights need the same arithmetic."""
     size = np.array(size)
-    if size.ndim == 0 or size.size == 1:
-        n = int(np.sqrt(np.prod(size)))
-        return n, n
-    if size.size == 2:
+    if size.ndim == 2:
         return size[0], size[1]
-    if size.size in (4, 5):
+    if size.ndim in (4, 5):
         field = np.prod(size[2:])
         return size[1] * field, size[0] * field
     n = int(np.sqrt(np.prod(size)))

@@ -377,7 +377,72 @@ class _FirstPad(object):
         return zp
 
 
+# ---------------------------------------------------------- initializers ----
+def initializer_case():
+    """utils/Initializers.py under fixed seeds (its fan computation takes the sqrt(prod) branch for
+    every shape tuple, :12-22; the host-side initializers must reproduce that)."""
+    from reference.utils.Initializers import get_initializer
+    out = {}
+    for i, (name, size) in enumerate([('glorot_uniform', (4, 6)), ('he_normal', (8, 3, 3, 3)), ('lecun_uniform', (5, 7)),
+                                      ('he_uniform', (16, 8, 3, 3)), ('glorot_normal', (12, 12)), ('lecun_normal', (7, 3)),
+                                      ('orthogonal', (6, 4)), ('orthogonal', (5, 5)), ('uniform', (3, 4)), ('normal', (3, 4))]):
+        np.random.seed(10 + i)
+        out['%d_%s' % (i, name)] = get_initializer(name)(size)
+    save('initializers', **out)
+
+
+# ------------------------------------------------------- embedding, lstm ----
+def recurrent_case():
+    """Embedding forward/backward and LSTM forward/backward of the unmodified reference
+    (layers/Embeddings.py, layers/Recurrent.py:216-507).  The LSTM gradients stored here are the
+    reference's own — gate gradients concatenated in the wrong order (:358) — and pin the oracle's
+    reference_gate_order=True branch."""
+    from reference.layers.Embeddings import Embedding
+    from reference.layers.Recurrent import LSTM
+    np.random.seed(0)
+    r = np.random.default_rng(4242)
+    ids = r.integers(0, 50, (6, 9))
+    inp = Input((None, 9))
+    emb = Embedding(50, 8)
+    emb(inp)                                   # (the reference's Embedding.__call__ returns None)
+    Wv, = emb.variables
+    Wv.output_tensor = f32(Wv.output_tensor)
+    inp.input_tensor = ids
+    for l in (inp, emb):
+        l.forward(True)
+    Y = emb.output_tensor.copy()
+    G = f32(r.standard_normal(Y.shape))
+    emb.grads = G.copy()
+    emb.backward()
+    save('embedding', ids=ids, W=Wv.output_tensor, Y=Y, G=G, dW=Wv.grads)
+    out = {}
+    for rs in (True, False):
+        np.random.seed(1)
+        inp = Input((None, 7, 5))
+        src = Activation('linear')(inp)
+        lstm = LSTM(6, return_sequences=rs)(src)
+        W, b = lstm.variables
+        W.output_tensor = f32(W.output_tensor)
+        b.output_tensor = f32(b.output_tensor + 0.1 * r.standard_normal(b.output_tensor.shape))
+        X = f32(r.standard_normal((4, 7, 5)))
+        inp.input_tensor = X
+        for l in (inp, src, lstm):
+            l.forward(True)
+        Yl = np.array(lstm.output_tensor)
+        Gl = f32(r.standard_normal(Yl.shape))
+        lstm.grads = Gl.copy()
+        lstm.backward()
+        k = 'seq' if rs else 'last'
+        out.update({'X_' + k: X, 'W_' + k: W.output_tensor.copy(), 'b_' + k: b.output_tensor.copy(), 'Y_' + k: Yl, 'G_' + k: Gl,
+                    'dW_ref_' + k: W.grads.copy(), 'db_ref_' + k: b.grads.copy(), 'dX_ref_' + k: np.array(src.grads)})
+    save('lstm', **out)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1:                      # python make_golden.py recurrent_case ... : only these
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     conv_case('conv_katA', 2, 3, 8, 8, 4, 3, 1, 1, 'relu')
     conv_case('conv_valid_s2', 3, 5, 9, 11, 6, 3, 2, 0, 'linear', seed=1)
     conv_case('conv_cfg1_shape', 4, 1, 28, 28, 8, 2, 1, 0, 'relu', seed=2)

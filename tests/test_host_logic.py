@@ -111,16 +111,21 @@ def test_to_categorical():
 
 
 def test_initializers_consume_rng_like_reference():
+    """Every initializer against the reference's own output under the same seed
+    (tests/golden/initializers.npz) — including its fan computation, which takes the sqrt(prod)
+    branch for every shape tuple (utils/Initializers.py:12-22)."""
+    from conftest import load_golden
+    g = load_golden('initializers')
+    assert len(g) == 10
+    for key, ref in g.items():
+        i, name = key.split('_', 1)
+        np.random.seed(10 + int(i))
+        assert np.array_equal(I.get_initializer(name)(ref.shape), ref), key
     np.random.seed(3)
     a = I.get_initializer('glorot_uniform')((4, 6))
     np.random.seed(3)
-    s = np.sqrt(6. / 10)
+    s = np.sqrt(6. / (4 + 4))                       # int(sqrt(24)) = 4 for fan_in and fan_out
     assert np.array_equal(a, np.random.uniform(-s, s, size=(4, 6)))
-    np.random.seed(4)
-    b = I.get_initializer('he_normal')((8, 3, 3, 3))
-    np.random.seed(4)
-    assert np.array_equal(b, np.random.normal(0.0, np.sqrt(2. / 27), size=(8, 3, 3, 3)))
-    assert I.get_initializer('orthogonal')((6, 4)).shape == (6, 4)
 
 
 def test_no_cpu_fallback():

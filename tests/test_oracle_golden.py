@@ -250,3 +250,55 @@ def test_trajectory_residual():
     assert np.allclose(net.train_loss, g['train_loss'], rtol=1e-9, atol=0)
     assert rel_err(net.params[0], g['stemW']) < 1e-9
     assert rel_err(net.params[-2], g['denseW']) < 1e-9
+
+
+def test_embedding_matches_reference():
+    g = load_golden('embedding')
+    assert np.array_equal(O.embedding_forward(g['W'], g['ids']), g['Y'])
+    assert rel_err(O.embedding_backward(g['W'].shape, g['ids'], g['G']), g['dW']) < 1e-15
+
+
+@pytest.mark.parametrize('kind', ['seq', 'last'])
+def test_lstm_matches_reference(kind):
+    """Forward: bit for bit.  Backward: the reference's own numbers come out of the oracle's
+    reference_gate_order=True branch (gate gradients concatenated as (o, c~, u, f), Recurrent.py:358)."""
+    g = load_golden('lstm')
+    X, W, b, G = g['X_' + kind], g['W_' + kind], g['b_' + kind], g['G_' + kind]
+    hs, cache = O.lstm_forward(X, W, b)
+    y = hs if kind == 'seq' else hs[:, -1]
+    assert rel_err(y, g['Y_' + kind]) < 1e-15
+    dx, dw, db = O.lstm_backward(G, cache, kind == 'seq', reference_gate_order=True)
+    assert rel_err(dw, g['dW_ref_' + kind]) < 1e-13
+    assert rel_err(db, g['db_ref_' + kind]) < 1e-13
+    assert rel_err(dx, g['dX_ref_' + kind]) < 1e-13
+    # ... and they are NOT the gradient of the forward pass (SURVEY.md section 2 row 12)
+    dx2, dw2, db2 = O.lstm_backward(G, cache, kind == 'seq')
+    assert rel_err(dw2, g['dW_ref_' + kind]) > 1e-2
+
+
+@pytest.mark.parametrize('return_sequences', [True, False])
+def test_lstm_backward_is_the_numeric_gradient(return_sequences):
+    """The oracle's default LSTM backward (forward gate order) against central differences."""
+    r = np.random.default_rng(0)
+    N, T, D, H = 3, 5, 4, 6
+    x = r.standard_normal((N, T, D)); w = 0.5 * r.standard_normal((H + D, 4 * H)); b = r.standard_normal((1, 4 * H))
+    g = r.standard_normal((N, T, H)) if return_sequences else r.standard_normal((N, H))
+
+    def loss():
+        hs, _ = O.lstm_forward(x, w, b)
+        return float(np.sum((hs if return_sequences else hs[:, -1]) * g))
+
+    _, cache = O.lstm_forward(x, w, b)
+    dx, dw, db = O.lstm_backward(g, cache, return_sequences)
+    eps = 1e-6
+    for arr, grad in ((x, dx), (w, dw), (b, db)):
+        num = np.zeros_like(arr)
+        it = np.nditer(arr, flags=['multi_index'])
+        for _ in it:
+            i = it.multi_index
+            old = arr[i]
+            arr[i] = old + eps; lp = loss()
+            arr[i] = old - eps; lm = loss()
+            arr[i] = old
+            num[i] = (lp - lm) / (2 * eps)
+        assert rel_err(grad, num) < 1e-7
