@@ -348,6 +348,17 @@ SN_API int sn_lstm_step_fwd(const float *zx, long long zx_stride, const float *w
 SN_API int sn_lstm_step_bwd(const float *dh_ext, long long dh_stride, const float *dz_next, const float *wh, const float *acts,
                      const float *c, const float *c_prev, float *dc, float *dz, int N, int H, int first, void *stream);
 
+/* The whole recurrence in ONE launch (H = 64 or 128): clusters of H/32 CTAs own 8 batch rows, keep
+ * their slice of Wh in registers for all T steps and exchange h_t (forward) / dz_t (backward) through
+ * distributed shared memory, one cluster barrier per step.  Time-major tensors: zx, acts, dz
+ * [T][N][4H]; c_all, h_all [T+1][N][H] (slot 0 = initial state, read only through h0 / c0, which may
+ * be NULL for zeros); h_seq (N,T,H) optional.  Backward: dh_seq (N,T,H) or dh_last (N,H). */
+SN_API int sn_lstm_seq_supported(int N, int H);
+SN_API int sn_lstm_seq_fwd(const float *zx, const float *wh, const float *h0, const float *c0, float *acts, float *c_all,
+                    float *h_all, float *h_seq, int T, int N, int H, void *stream);
+SN_API int sn_lstm_seq_bwd(const float *dh_last, const float *dh_seq, const float *wh, const float *acts, const float *c_all,
+                    int c0_is_zero, float *dz, int T, int N, int H, void *stream);
+
 /* ------------------------------------------------------------------ loss */
 /* Softmax._forward, utils/Activator.py:108-110 (row-wise; the reference's global shift cancels) */
 SN_API int sn_softmax_fwd(const float *logits, float *probs, int rows, int classes, void *stream);

@@ -3,8 +3,9 @@ reference's GRU backward raises, :602).
 
 Same parameters as the reference: W (H + D, 4H) = rows [recurrent; input], gate columns
 (f, u, c~, o), b (1, 4H) with the forget-gate bias at one (:225-262).  The input half of the fused
-product is one GEMM over all timesteps, the recurrence one fused launch per step
-(csrc/recurrent.cu).  The backward pass is the CORRECT back-propagation through time: the reference
+product is one GEMM over all timesteps; the recurrence is ONE launch for the whole sequence when
+H is 64 or 128 (thread-block clusters, Wh in registers, h_t exchanged through distributed shared
+memory), else one fused launch per step (csrc/recurrent.cu).  The backward pass is the CORRECT back-propagation through time: the reference
 concatenates its gate gradients as (o, c~, u, f) (:358, :406) against forward columns (f, u, c~, o),
 so its dW / dX do not match its own forward; the oracle reproduces the
 reference's numbers with `reference_gate_order=True` and is checked against numeric gradients
@@ -112,7 +113,12 @@ class LSTM(Recurrent):
             lib.sn_memcpy_d2d(h_all.ptr, h_all.ptr + T * step, step, st)
             lib.sn_memcpy_d2d(c_all.ptr, c_all.ptr + T * step, step, st)
         hseq = self._buf('h_seq', (N, T, H), 'flat') if self.return_sequences else None
-        for t in range(T):
+        self._seq = bool(lib.load().sn_lstm_seq_supported(N, H))
+        if self._seq:
+            # the whole recurrence in one launch: clusters keep Wh in registers, h_t travels through DSMEM
+            lib.sn_lstm_seq_fwd(zx.ptr, wh, h_all.ptr if carry else None, c_all.ptr if carry else None, acts.ptr, c_all.ptr,
+                                h_all.ptr, None if hseq is None else hseq.ptr, T, N, H, st)
+        for t in range(0 if not self._seq else T, T):
             first = t == 0 and not carry
             lib.sn_lstm_step_fwd(zx.ptr + t * 4 * step, 4 * H, wh,
                                  None if first else h_all.ptr + t * step, None if first else c_all.ptr + t * step,
@@ -145,7 +151,12 @@ class LSTM(Recurrent):
         dz = self._buf('dz', (T, N, 4 * H), 'flat')
         dc = self._buf('dc', (N, H), 'flat')
         step = N * H * 4
-        for t in range(T - 1, -1, -1):
+        if self._seq:
+            if self.return_sequences:
+                lib.sn_lstm_seq_bwd(None, g.ptr, wh, acts.ptr, c_all.ptr, 1 if self._first_zero else 0, dz.ptr, T, N, H, st)
+            else:
+                lib.sn_lstm_seq_bwd(g.ptr, None, wh, acts.ptr, c_all.ptr, 1 if self._first_zero else 0, dz.ptr, T, N, H, st)
+        for t in range(T - 1 if not self._seq else -1, -1, -1):
             last = t == T - 1
             if self.return_sequences:
                 dh_ext, dh_stride = g.ptr + t * H * 4, T * H

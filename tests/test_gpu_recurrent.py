@@ -79,7 +79,11 @@ def test_lstm_matches_reference_fixture(kind):
     assert rel_err(db, db_ref) < TOL32
 
 
-@pytest.mark.parametrize('case', [(32, 16, 64, 128, False), (32, 16, 64, 128, True), (5, 3, 7, 10, True), (19, 1, 12, 33, False)])
+@pytest.mark.parametrize('case', [
+    (32, 16, 64, 128, False), (32, 16, 64, 128, True),      # whole-sequence cluster kernels (H = 128: clusters of 4)
+    (21, 9, 24, 64, True), (3, 2, 8, 64, False),             # ... H = 64 (clusters of 2), row count not a multiple of 8
+    (5, 3, 7, 10, True), (19, 1, 12, 33, False),             # per-step kernels (other H)
+])
 def test_lstm_vs_oracle(case):
     N, T, D, H, rs = case
     r = np.random.default_rng(N + T)
