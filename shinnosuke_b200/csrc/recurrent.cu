@@ -208,6 +208,8 @@ __device__ __forceinline__ uint32_t sq_ctarank() { uint32_t r; asm volatile("mov
 __device__ __forceinline__ void sq_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void sq_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void sq_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void sq_store_remote(uint32_t local_addr, uint32_t rank, float v) {
     uint32_t ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
@@ -283,6 +285,10 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_fwd_kernel(const float *__res
         const float f = sigmoidf_ref(z[0]), ug = sigmoidf_ref(z[1]), ct = tanhf(z[2]), o = sigmoidf_ref(z[3]);
         c = fmaf(f, c, ug * ct);
         const float h = o * tanhf(c);
+        const uint32_t slot = sq_smem_u32(&hbuf[nxt][fr][unit]);
+#pragma unroll
+        for (int pr = 0; pr < CL; ++pr) sq_store_remote(slot, (uint32_t)pr, h);
+        sq_cluster_arrive();                                   // the HBM stores below overlap the barrier's round trip
         if (live) {
             float *a = acts + ((long long)t * N + frow) * 4 * H + unit;
             a[0] = f; a[H] = ug; a[2 * H] = ct; a[3 * H] = o;
@@ -291,10 +297,7 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_fwd_kernel(const float *__res
             h_all[at] = h;
             if (h_seq) h_seq[((long long)frow * T + t) * H + unit] = h;
         }
-        const uint32_t slot = sq_smem_u32(&hbuf[nxt][fr][unit]);
-#pragma unroll
-        for (int pr = 0; pr < CL; ++pr) sq_store_remote(slot, (uint32_t)pr, h);
-        sq_cluster_sync();                                     // h_t is in every CTA's next buffer; `red` is free again
+        sq_cluster_wait();                                     // h_t is in every CTA's next buffer; `red` is free again
     }
 }
 
@@ -356,11 +359,6 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_bwd_kernel(const float *__res
         d[2] = dcv * ug * (1.f - ct * ct);                                     // candidate     (:340-341)
         d[3] = dh * tc * o * (1.f - o);                                        // output gate   (:329-330)
         dc = dcv * f;                                                          // :366
-        if (live) {
-            float *out = dz + ((long long)t * N + frow) * 4 * H + unit;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) out[g * H] = d[g];
-        }
         if (t > 0) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -369,7 +367,13 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_bwd_kernel(const float *__res
                 for (int pr = 0; pr < CL; ++pr) sq_store_remote(slot, (uint32_t)pr, d[g]);
             }
         }
-        sq_cluster_sync();
+        sq_cluster_arrive();
+        if (live) {
+            float *out = dz + ((long long)t * N + frow) * 4 * H + unit;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) out[g * H] = d[g];
+        }
+        sq_cluster_wait();
     }
 }
 
