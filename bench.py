@@ -237,6 +237,11 @@ def kernel_work(name, a, precision):
         # one timestep: the recurrent product h . Wh (N x H x 4H) + the gate tensors once
         N, H = (a[2], a[3]) if name == 'sn_lstm_step_fwd' else (a[1], a[2])
         return 2.0 * N * H * 4 * H, 4.0 * (4 * H * H + 2 * N * 4 * H + 4 * N * H)
+    if name in ('sn_lstm_seq_fwd', 'sn_lstm_seq_bwd'):
+        # the whole recurrence: T dependent steps (latency-bound by construction); algorithmic work = the
+        # recurrent products + the per-step tensors read / written once (zx or dh, acts, c, h / dz)
+        T, N, H = a[-3:]
+        return 2.0 * T * N * H * 4 * H, 4.0 * T * N * (2 * 4 * H + 2 * H) + 4.0 * 4 * H * H
     if name in ('sn_embedding_fwd', 'sn_embedding_bwd'):
         n_idx, vocab, dim = a[:3]
         return 0.0, 4.0 * n_idx * (1 + 2 * dim)
