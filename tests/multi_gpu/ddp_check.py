@@ -71,6 +71,28 @@ for prec, tol in (('fp32', 1e-5), ('tf32', 2e-3)):
             # the tier's tolerance here; the exactness claim is the fp32 line above
             l2 = max(abs(a - b) / abs(b) for a, b in zip(m.train_loss[:2], net.train_loss[:2]))
             assert l2 < tol, l2
+# ---- config 5 (Embedding -> LSTM -> Dense): row shards of the token matrix, the embedding scatter and the
+# whole-sequence LSTM kernels under data parallelism, against the whole-batch oracle
+from shinnosuke_b200 import Embedding, LSTM
+from shinnosuke_b200.utils.Optimizers import StochasticGradientDescent
+X5 = r.integers(0, 60, (64, 10)).astype(np.float64); Y5 = O.to_categorical(np.concatenate([np.arange(2), r.integers(0, 2, 62)]))
+np.random.seed(0)
+m = Sequential()
+m.add(Embedding(60, 16, input_length=10)); m.add(LSTM(64)); m.add(Dense(2, activation='softmax'))
+m.compile(StochasticGradientDescent(lr=0.5), 'sparse_categorical_crossentropy', precision='fp32')
+m.fit(X5, Y5, batch_size=32, epochs=3, shuffle=False, validation_ratio=0., verbose=0)
+ws = [np.asarray(v.output_tensor) for v in m.trainable_variables]
+if dist.get_rank() == 0:
+    np.random.seed(0)
+    spec5, ishape5 = O.spec_cfg5(60, 16, 64, 10)
+    net = O.OracleNet(spec5, ishape5, lr=0.5)
+    for ep in range(3):
+        for a in range(0, 64, 32):
+            net.step(X5[a:a + 32], Y5[a:a + 32])
+    err = max(np.abs(w - p).max() / max(np.abs(p).max(), 1e-12) for w, p in zip(ws, net.params))
+    lerr = max(abs(a - b) / abs(b) for a, b in zip(m.train_loss, net.train_loss))
+    print('cfg5 (Embedding + LSTM) max rel err of the weights vs the whole-batch oracle:', err, 'loss:', lerr)
+    assert err < 1e-5 and lerr < 1e-5, (err, lerr)
 dist.barrier(); torch.cuda.synchronize()
 print('DDP_CHECK_OK') if dist.get_rank() == 0 else None
 sys.stdout.flush()
