@@ -101,6 +101,8 @@ SN_API int sn_cast_f32_to_f64(const float *src, double *dst, long long n, void *
 SN_API int sn_axpy(float alpha, const float *x, float *y, long long n, void *stream);     /* y += alpha*x */
 /* Add.forward, layers/Base.py:378-385: out = a + b (same shapes; residual connections) */
 SN_API int sn_add(const float *a, const float *b, float *out, long long n, void *stream);
+/* out = relu(a + b), blocked elements written as -0.0f: Add followed by Activation('relu') (config 4's residual join) */
+SN_API int sn_add_relu(const float *a, const float *b, float *out, long long n, void *stream);
 
 /* ---------------------------------------------------------------- Conv2D */
 /* Conv2D.forward, layers/Convolution.py:131-161 (true zero padding):
@@ -275,7 +277,8 @@ SN_API int sn_batchnorm_stats(const float *x, const float *gamma, const float *b
 SN_API int sn_batchnorm_finalize_stats(const float *gamma, const float *beta, float *save_mean, float *save_invstd,
                                 float *moving_mean, float *moving_var, double *scratch,
                                 long long rows, int C, float eps, float momentum, void *stream);
-SN_API int sn_batchnorm_fwd_apply(const float *x, float *y, const double *scratch, long long rows, int C, void *stream);
+/* relu != 0: the Activation('relu') that follows the layer is applied on the way out (blocked elements = -0.0f) */
+SN_API int sn_batchnorm_fwd_apply(const float *x, float *y, const double *scratch, long long rows, int C, int relu, void *stream);
 
 /* BatchNormalization immediately followed by MaxPooling2D((2,2)) (stride 2), fused: the normalised
  * map is never written.  x: conv output (N,H,W,C); y_pool: (N,H/2,W/2,C); code: one byte per

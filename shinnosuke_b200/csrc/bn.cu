@@ -241,6 +241,9 @@ __global__ void __launch_bounds__(256) bn_reduce_pow2_kernel(const float *__rest
     bn_finalize_last_block(scratch, fin);
 }
 
+// RELU: the Activation('relu') that follows the layer, applied on the way out (blocked elements are
+// written as -0.0f, the convention every ReLU mask on the device reads back)
+template <bool RELU>
 __global__ void __launch_bounds__(256) bn_apply_train_pow2_kernel(const float *__restrict__ x, float *__restrict__ y,
                                                                   const double *__restrict__ scratch, long long total4, int C) {
     const int Q = C >> 2;
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(256) bn_apply_train_pow2_kernel(const float *_
             float4 o;
             o.x = fmaf(v[u].x, sc[0], sh[0]); o.y = fmaf(v[u].y, sc[1], sh[1]);
             o.z = fmaf(v[u].z, sc[2], sh[2]); o.w = fmaf(v[u].w, sc[3], sh[3]);
+            if (RELU) { o.x = relu_keep_sign(o.x); o.y = relu_keep_sign(o.y); o.z = relu_keep_sign(o.z); o.w = relu_keep_sign(o.w); }
             reinterpret_cast<float4 *>(y)[i + u * stride] = o;
         }
     }
@@ -355,11 +359,12 @@ int sn_batchnorm_finalize_stats(const float *gamma, const float *beta, float *sa
     return after_launch("bn_finalize_kernel");
 }
 
-int sn_batchnorm_fwd_apply(const float *x, float *y, const double *scratch, long long rows, int C, void *stream) {
+int sn_batchnorm_fwd_apply(const float *x, float *y, const double *scratch, long long rows, int C, int relu, void *stream) {
     SN_REQUIRE(x && y && scratch && rows > 0, "bad arguments");
     SN_REQUIRE(bn_pow2(C) && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0, "needs C = 4*2^k <= 1024 and 16-byte aligned tensors");
     const long long total4 = rows * C / 4;
-    bn_apply_train_pow2_kernel<<<bn_grid(total4), 256, 0, as_stream(stream)>>>(x, y, scratch, total4, C);
+    if (relu) bn_apply_train_pow2_kernel<true><<<bn_grid(total4), 256, 0, as_stream(stream)>>>(x, y, scratch, total4, C);
+    else bn_apply_train_pow2_kernel<false><<<bn_grid(total4), 256, 0, as_stream(stream)>>>(x, y, scratch, total4, C);
     return after_launch("bn_apply_train_pow2_kernel");
 }
 
@@ -424,7 +429,7 @@ int sn_batchnorm_fwd_train(const float *x, const float *gamma, const float *beta
                                     momentum, stream);
         if (e2) return e2;
         const long long total4 = rows * C / 4;
-        bn_apply_train_pow2_kernel<<<bn_grid(total4), 256, 0, st>>>(x, y, scratch, total4, C);
+        bn_apply_train_pow2_kernel<false><<<bn_grid(total4), 256, 0, st>>>(x, y, scratch, total4, C);
         return after_launch("bn_apply_train_pow2_kernel");
     }
     SN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));

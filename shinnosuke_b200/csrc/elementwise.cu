@@ -63,18 +63,20 @@ __global__ void axpy_kernel(float a, const float *__restrict__ x, float *__restr
         for (long long i = t; i < n; i += stride) y[i] += a * x[i];
     }
 }
+template <bool RELU>
 __global__ void add_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ o, long long n) {
     long long n4 = n >> 2;
     long long stride = (long long)gridDim.x * blockDim.x;
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    auto f = [](float v) { return RELU ? relu_keep_sign(v) : v; };
     if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)o) & 15) == 0) {
         for (long long i = t; i < n4; i += stride) {
             float4 x = ldg4(a + 4 * i), y = ldg4(b + 4 * i);
-            reinterpret_cast<float4 *>(o)[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+            reinterpret_cast<float4 *>(o)[i] = make_float4(f(x.x + y.x), f(x.y + y.y), f(x.z + y.z), f(x.w + y.w));
         }
-        for (long long i = 4 * n4 + t; i < n; i += stride) o[i] = a[i] + b[i];
+        for (long long i = 4 * n4 + t; i < n; i += stride) o[i] = f(a[i] + b[i]);
     } else {
-        for (long long i = t; i < n; i += stride) o[i] = a[i] + b[i];
+        for (long long i = t; i < n; i += stride) o[i] = f(a[i] + b[i]);
     }
 }
 __global__ void relu_bwd_kernel(float *__restrict__ dy, const float *__restrict__ y, long long n) {
@@ -96,9 +98,17 @@ __global__ void relu_bwd_kernel(float *__restrict__ dy, const float *__restrict_
         for (long long i = t; i < n; i += stride) if (relu_blocked(y[i])) dy[i] = 0.f;
     }
 }
-__global__ void relu_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, long long n) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        y[i] = relu_keep_sign(x[i]);
+__global__ void relu_fwd_kernel(const float *x, float *y, long long n) {
+    const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x, t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if ((((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
+        for (long long i = t; i < n4; i += stride) {
+            const float4 v = reinterpret_cast<const float4 *>(x)[i];          // (plain load: x may alias y)
+            reinterpret_cast<float4 *>(y)[i] = make_float4(relu_keep_sign(v.x), relu_keep_sign(v.y), relu_keep_sign(v.z), relu_keep_sign(v.w));
+        }
+        for (long long i = 4 * n4 + t; i < n; i += stride) y[i] = relu_keep_sign(x[i]);
+    } else {
+        for (long long i = t; i < n; i += stride) y[i] = relu_keep_sign(x[i]);
+    }
 }
 
 // ------------------------------------------------------------------ zero padding
@@ -246,7 +256,13 @@ int sn_axpy(float alpha, const float *x, float *y, long long n, void *stream) {
 int sn_add(const float *a, const float *b, float *out, long long n, void *stream) {
     SN_REQUIRE(a && b && out && n >= 0, "bad arguments");
     if (!n) return SN_OK;
-    add_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(a, b, out, n);
+    add_kernel<false><<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(a, b, out, n);
+    return after_launch("add_kernel");
+}
+int sn_add_relu(const float *a, const float *b, float *out, long long n, void *stream) {
+    SN_REQUIRE(a && b && out && n >= 0, "bad arguments");
+    if (!n) return SN_OK;
+    add_kernel<true><<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(a, b, out, n);
     return after_launch("add_kernel");
 }
 int sn_relu_bwd(float *dy, const float *y, long long n, void *stream) {
@@ -258,7 +274,7 @@ int sn_relu_bwd(float *dy, const float *y, long long n, void *stream) {
 int sn_relu_fwd(const float *x, float *y, long long n, void *stream) {
     SN_REQUIRE(x && y && n >= 0, "bad arguments");
     if (!n) return SN_OK;
-    relu_fwd_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, y, n);
+    relu_fwd_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(x, y, n);
     return after_launch("relu_fwd_kernel");
 }
 int sn_pad2d_fwd(const float *x, float *y, int N, int H, int W, int C, int pad_h, int pad_w, void *stream) {

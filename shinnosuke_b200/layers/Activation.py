@@ -29,7 +29,9 @@ class Activation(Layer):
         x = self.input_tensor
         kind = self._kind()
         st = current_stream()
-        if kind == 'linear':
+        if kind == 'linear' or getattr(self, '_folded_into', None) is not None:
+            # 'relu' folded into the producing BatchNormalization / Add by compile(): that kernel already
+            # wrote relu(x) (blocked elements as -0.0f), this layer only hands the buffer on
             self.output_tensor = x
         elif kind == 'relu':
             y = self._buf('out', x.shape, x.layout)
@@ -47,4 +49,6 @@ class Activation(Layer):
         if self._kind() == 'relu' and not self._grads_premasked:
             lib.sn_relu_bwd(g.ptr, self.output_tensor.ptr, g.size, st)
         for layer in self.inbounds:
+            if self._hand_over_grads(layer, g):
+                continue
             self._push_grad(layer, lambda dst, acc: dst.add_(g) if acc else dst.copy_from(g))

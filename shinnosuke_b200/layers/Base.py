@@ -196,6 +196,19 @@ class Layer(object):
         writer(layer.grads, acc)
         layer._grads_written = True
 
+    def _hand_over_grads(self, layer, g):
+        """dX of a pass-through layer IS its own gradient buffer: when `layer` has no other consumer
+        (nobody else will add to its gradient) it adopts the buffer instead of receiving a copy.  The
+        caller must not need `g` afterwards (its backward is over).  Returns False when a copy /
+        accumulation is needed."""
+        if not layer.require_grads or layer._grads_written or len(layer.outbound_layers) != 1:
+            return False
+        if layer.grads is None or layer.grads.size != g.size:
+            return False
+        layer.grads = g.view(layer.grads.shape, layer.grads.layout) if (layer.grads.shape != g.shape or layer.grads.layout != g.layout) else g
+        layer._grads_written = True
+        return True
+
     def _seed_grads(self, value):
         """Used by the loss (models.py:80): `outputs.grads = loss.backward(...)`."""
         self.grads = value
@@ -302,11 +315,19 @@ class Add(Layer):
     def forward(self, is_training=True):
         a, b = (layer.output_tensor for layer in self.inbounds)
         out = self._buf('out', a.shape, a.layout)
-        lib.sn_add(a.ptr, b.ptr, out.ptr, a.size, current_stream())
+        if getattr(self, '_relu_out', None) is not None:      # Add -> Activation('relu'), folded by compile()
+            lib.sn_add_relu(a.ptr, b.ptr, out.ptr, a.size, current_stream())
+        else:
+            lib.sn_add(a.ptr, b.ptr, out.ptr, a.size, current_stream())
         self.output_tensor = out
         super(Add, self).forward(is_training)
 
     def backward(self):
         g = self.grads
-        for layer in self.inbounds:
+        # the operand with no other consumer adopts the buffer instead of receiving a copy; it comes
+        # LAST, so the other operand's copy is enqueued before the adopter's backward can touch the buffer
+        order = sorted(self.inbounds, key=lambda l: len(l.outbound_layers) == 1)
+        for i, layer in enumerate(order):
+            if i == len(order) - 1 and self._hand_over_grads(layer, g):
+                continue
             self._push_grad(layer, lambda dst, acc: dst.add_(g) if acc else dst.copy_from(g))

@@ -128,6 +128,7 @@ class BatchNormalization(Layer):
             self._grads_premasked = False
             return
         y = self._buf('out', x.shape, x.layout)
+        relu_out = getattr(self, '_relu_out', None) is not None
         if is_training and (prestats or sync is not None):
             if not prestats:
                 lib.sn_batchnorm_local_stats(x.ptr, s['scratch'].data_ptr(), rows, C, st)
@@ -136,7 +137,9 @@ class BatchNormalization(Layer):
             lib.sn_batchnorm_finalize_stats(gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
                                             s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows_g, C,
                                             float(self.epsilon), float(self.momentum), st)
-            lib.sn_batchnorm_fwd_apply(x.ptr, y.ptr, s['scratch'].data_ptr(), rows, C, st)
+            # the Activation('relu') behind this layer, when compile() folded it in, rides on the apply pass
+            lib.sn_batchnorm_fwd_apply(x.ptr, y.ptr, s['scratch'].data_ptr(), rows, C, 1 if relu_out else 0, st)
+            relu_out = False
         elif is_training:
             lib.sn_batchnorm_fwd_train(x.ptr, gamma.output_tensor.ptr, beta.output_tensor.ptr, y.ptr, s['mean'].ptr,
                                        s['invstd'].ptr, s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows, C,
@@ -144,6 +147,8 @@ class BatchNormalization(Layer):
         else:
             lib.sn_batchnorm_fwd_infer(x.ptr, gamma.output_tensor.ptr, beta.output_tensor.ptr, y.ptr, s['mm'].ptr,
                                        s['mv'].ptr, rows, C, float(self.epsilon), st)
+        if relu_out:
+            lib.sn_relu_fwd(y.ptr, y.ptr, y.size, st)          # paths without the flag: in place
         self.output_tensor = y
         super(BatchNormalization, self).forward(is_training)
 

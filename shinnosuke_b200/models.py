@@ -101,6 +101,22 @@ class _Trainer(object):
                 if isinstance(prev, Conv2D):
                     feeds = fuse and precision in ('tf32', 'bf16') and len(prev.outbound_layers) == 1
                     prev._stats_to = layer if feeds else None
+        # BatchNormalization / Add -> Activation('relu') with no other consumer: the ReLU rides on the
+        # producing kernel's output pass and the Activation layer only hands the buffer on
+        from .layers.Activation import Activation
+        from .layers.Base import Add
+        for layer in self._forward_order():
+            if isinstance(layer, (BatchNormalization, Add)):
+                layer._relu_out = None
+        for layer in self._forward_order():
+            if isinstance(layer, Activation):
+                layer._folded_into = None
+                prev = layer.inbounds[0] if len(layer.inbounds) == 1 else None
+                ok = (fuse and layer._kind() == 'relu' and isinstance(prev, (BatchNormalization, Add))
+                      and len(prev.outbound_layers) == 1 and getattr(prev, '_fuse_with_pool', None) is None)
+                if ok:
+                    prev._relu_out = layer
+                    layer._folded_into = prev
         # Flatten -> Dense with nobody else on either side: the NHWC map is handed through as it is and
         # the Dense keeps its weight rows in (i,j,c) order (no transpose kernel forward or backward)
         from .layers.FC import Flatten, Dense
