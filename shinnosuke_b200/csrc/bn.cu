@@ -302,7 +302,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_pow2_kernel(const float *__r
     }
 }
 
-__global__ void bn_finalize_kernel(double *scratch, BnFinal fin) { bn_finalize_channels(scratch, fin); }
+__global__ void bn_finalize_kernel(double *scratch, BnFinal fin) {
+    bn_finalize_channels(scratch, fin, (int)(blockIdx.x * blockDim.x + threadIdx.x), (int)(gridDim.x * blockDim.x));
+}
 
 static bool bn_pow2(int C) {
     if (C & 3) return false;
@@ -355,7 +357,7 @@ int sn_batchnorm_finalize_stats(const float *gamma, const float *beta, float *sa
     BnFinal fin{};
     fin.bwd = 0; fin.rows = rows; fin.C = C; fin.x = nullptr; fin.gamma = gamma; fin.beta = beta; fin.save_mean = save_mean;
     fin.save_invstd = save_invstd; fin.moving_mean = moving_mean; fin.moving_var = moving_var; fin.eps = eps; fin.momentum = momentum;
-    bn_finalize_kernel<<<1, C < 256 ? C : 256, 0, as_stream(stream)>>>(scratch, fin);
+    bn_finalize_kernel<<<(C + 31) / 32, 32, 0, as_stream(stream)>>>(scratch, fin);     // one warp per SM
     return after_launch("bn_finalize_kernel");
 }
 
@@ -400,7 +402,7 @@ int sn_batchnorm_finalize_bwd(const float *gamma, const float *save_mean, const 
     SN_REQUIRE(gamma && save_mean && save_invstd && scratch && rows > 0 && bn_pow2(C), "bad arguments");
     BnFinal fin{};
     fin.bwd = 1; fin.rows = rows; fin.C = C; fin.gamma = gamma; fin.mean = save_mean; fin.invstd = save_invstd;
-    bn_finalize_kernel<<<1, C < 256 ? C : 256, 0, as_stream(stream)>>>(scratch, fin);
+    bn_finalize_kernel<<<(C + 31) / 32, 32, 0, as_stream(stream)>>>(scratch, fin);     // one warp per SM
     return after_launch("bn_finalize_kernel");
 }
 
