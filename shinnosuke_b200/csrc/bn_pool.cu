@@ -321,10 +321,15 @@ __global__ void colsum_fold_kernel(double *__restrict__ scratch, float *__restri
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double *slots = scratch + 20 * (size_t)C;
+    // loads first, in one batch (a load behind a store to the same array cannot be hoisted: 8 dependent L2 round trips)
+    double v[COLSUM_SLOTS];
+#pragma unroll
+    for (int sl = 0; sl < COLSUM_SLOTS; ++sl) v[sl] = __ldcg(slots + (size_t)sl * C + c);
+    const float old = colsum[c];
     double t = 0.0;
-#pragma unroll 8
-    for (int sl = 0; sl < COLSUM_SLOTS; ++sl) { t += slots[(size_t)sl * C + c]; slots[(size_t)sl * C + c] = 0.0; }
-    colsum[c] += (float)t;
+#pragma unroll
+    for (int sl = 0; sl < COLSUM_SLOTS; ++sl) { t += v[sl]; slots[(size_t)sl * C + c] = 0.0; }
+    colsum[c] = old + (float)t;
 }
 
 int grid_for_windows(long long windows4, int ctas_per_sm = 8) {
