@@ -172,3 +172,71 @@ def test_allreduce_overlap_split_cfg3():
             i = m.trainable_variables.index(v)
             assert offs[i] + v.size <= lo
     m._arena = None
+
+
+def test_sequential_compile_cfg5_matches_the_oracle_builder():
+    """Config 5 (Embedding -> LSTM -> Dense) compiles on the host with the reference's shapes and the
+    same RNG consumption as the oracle's builder (LSTM weights: per gate glorot-uniform input block,
+    then orthogonal recurrent block; forget-gate bias one; layers/Recurrent.py:229-258)."""
+    from shinnosuke_b200 import Embedding, LSTM
+    np.random.seed(0)
+    m = Sequential()
+    m.add(Embedding(1000, 64, input_length=64)); m.add(LSTM(128)); m.add(Dense(2, activation='softmax'))
+    m.compile(optimizer='sgd', loss='sparse_categorical_crossentropy', precision='bf16')
+    assert m.layers[0].output_shape == (None, 64, 64)
+    assert m.layers[1].output_shape == (None, 128)
+    assert m.layers[2].output_shape == (None, 2)
+    assert sum(v.size for v in m.trainable_variables) == 1000 * 64 + 192 * 512 + 512 + 128 * 2 + 2
+    np.random.seed(0)
+    spec, ishape = O.spec_cfg5()
+    net = O.OracleNet(spec, ishape)
+    ours = [np.asarray(v.output_tensor) for v in m.trainable_variables]
+    assert len(ours) == len(net.params)
+    for a, b in zip(ours, net.params):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    W, b = m.layers[1].variables
+    assert np.array_equal(np.asarray(b.output_tensor)[0, :128], np.ones(128)) and not np.asarray(b.output_tensor)[0, 128:].any()
+    with pytest.raises(NotImplementedError):
+        LSTM(8, return_state=True)
+    with pytest.raises(NotImplementedError):
+        LSTM(8, activation='relu')
+
+
+def test_lstm_weight_storage_layout_round_trip():
+    """('lstm_w', H): logical (H + D, 4H) rows [recurrent; input] <-> device storage [4H][H] then [4H][D]."""
+    from shinnosuke_b200.device import _to_storage, _from_storage
+    r = np.random.default_rng(0)
+    H, D = 6, 5
+    W = r.standard_normal((H + D, 4 * H)).astype(np.float32).astype(np.float64)
+    st = _to_storage(W, ('lstm_w', H))
+    assert st.dtype == np.float32 and st.shape == (4 * H * (H + D),)
+    wh, wx = st[:4 * H * H].reshape(4 * H, H), st[4 * H * H:].reshape(4 * H, D)
+    assert np.array_equal(wh, W[:H].T) and np.array_equal(wx, W[H:].T)
+    assert np.array_equal(_from_storage(st, W.shape, ('lstm_w', H)), W)
+
+
+def test_relu_folding_and_fusion_flags_cfg4():
+    """compile() folds an Activation('relu') into the BatchNormalization / Add that feeds it when that
+    layer has no other consumer, and leaves everything alone with fuse=False."""
+    from shinnosuke_b200 import Model, Input, Activation, Add
+    def build(fuse):
+        np.random.seed(0)
+        x_in = Input(shape=(None, 3, 8, 8))
+        h = Conv2D(8, (3, 3), padding='SAME', activation='relu')(x_in)
+        r = Conv2D(8, (3, 3), padding='SAME', activation='linear')(h)
+        bn1 = BatchNormalization()(r)
+        a1 = Activation('relu')(bn1)
+        r = Conv2D(8, (3, 3), padding='SAME', activation='linear')(a1)
+        bn2 = BatchNormalization()(r)
+        add = Add()([h, bn2])
+        a2 = Activation('relu')(add)
+        y = Dense(10, activation='softmax')(Flatten()(MaxPooling2D((2, 2))(a2)))
+        m = Model(inputs=x_in, outputs=y)
+        m.compile(optimizer='sgd', loss='sparse_categorical_crossentropy', precision='bf16', fuse=fuse)
+        return bn1, a1, bn2, add, a2
+    bn1, a1, bn2, add, a2 = build(True)
+    assert bn1._relu_out is a1 and a1._folded_into is bn1
+    assert add._relu_out is a2 and a2._folded_into is add
+    assert bn2._relu_out is None                      # its consumer is the Add, not a ReLU
+    bn1, a1, bn2, add, a2 = build(False)
+    assert bn1._relu_out is None and a1._folded_into is None and add._relu_out is None and a2._folded_into is None
