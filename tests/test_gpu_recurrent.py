@@ -171,3 +171,38 @@ def test_cfg5_full_size_step_properties():
     assert np.allclose(losses[0], losses[1], rtol=1e-4)
     p = np.asarray(m.predict(X[:N], is_training=False))
     assert p.shape == (N, 2) and np.allclose(p.sum(axis=1), 1.0, atol=1e-5) and (p >= 0).all()
+
+
+@pytest.mark.parametrize('H', [64, 10])            # whole-sequence cluster kernels / per-step kernels
+def test_lstm_stateful_carries_the_final_state(H):
+    """stateful=True (layers/Recurrent.py:274-276): the second training call starts from the first
+    call's final h and c, forward and backward (the carried state enters dW through h_0 and the
+    forget-gate gradient through c_0)."""
+    from shinnosuke_b200 import LSTM, Input, Activation
+    from shinnosuke_b200.device import as_device
+    N, T, D = 12, 5, 7
+    r = np.random.default_rng(H)
+    X1 = r.standard_normal((N, T, D)).astype(np.float32).astype(np.float64)
+    X2 = r.standard_normal((N, T, D)).astype(np.float32).astype(np.float64)
+    W = (0.3 * r.standard_normal((H + D, 4 * H))).astype(np.float32).astype(np.float64)
+    b = r.standard_normal((1, 4 * H)).astype(np.float32).astype(np.float64)
+    G = r.standard_normal((N, T, H)).astype(np.float32).astype(np.float64)
+    inp = Input((None, T, D)); src = Activation('linear')(inp)
+    lstm = LSTM(H, return_sequences=True, stateful=True)(src)
+    set_params(lstm, W, b)
+    inp.input_tensor = X1
+    for l in (inp, src, lstm):
+        l.forward(True)
+    y1 = np.asarray(lstm.output_tensor)
+    inp.input_tensor = X2
+    for l in (inp, src, lstm):
+        l.forward(True)
+    y2 = np.asarray(lstm.output_tensor)
+    lstm._seed_grads(as_device(G)); lstm.backward()
+    hs1, cache1 = O.lstm_forward(X1, W, b)
+    hs2, cache2 = O.lstm_forward(X2, W, b, h0=cache1['h'][:, -1], c0=cache1['c'][:, -1])
+    dx_ref, dw_ref, db_ref = O.lstm_backward(G, cache2, True)
+    assert rel_err(y1, hs1) < TOL32 and rel_err(y2, hs2) < TOL32
+    assert rel_err(np.asarray(src.grads), dx_ref) < TOL32
+    assert rel_err(np.asarray(lstm.variables[0].grads), dw_ref) < TOL32
+    assert rel_err(np.asarray(lstm.variables[1].grads), db_ref) < TOL32
