@@ -369,7 +369,8 @@ SN_API int sn_softmax_fwd(const float *logits, float *probs, int rows, int class
  * (one-hot labels).  dlogits = (probs - onehot)/denom_rows, where denom_rows is the reference's
  * N = prod(shape[:-1]) — the GLOBAL minibatch rows when `rows` is one data-parallel shard of it
  * (pass 0 for denom_rows == rows);  metrics[0] += sum(-y log p), metrics[1] += #(argmax p ==
- * argmax y).  metrics must be zeroed by the caller; may be NULL. */
+ * argmax y).  metrics must be zeroed by the caller; may be NULL.  A probability that underflowed fp32
+ * to 0 enters the loss as FLT_MIN (87.3 per sample) instead of log(0). */
 SN_API int sn_scce_bwd(const float *probs, const float *onehot, float *dlogits, float *metrics,
                 int rows, int classes, int denom_rows, void *stream);
 

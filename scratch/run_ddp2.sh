@@ -1,0 +1,8 @@
+mkdir -p gpurun_out
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 tests/multi_gpu/ddp_check.py > gpurun_out/ddp.log 2>&1
+echo "exit $?"; grep -c "DDP_CHECK_OK" gpurun_out/ddp.log
+for C in cfg4 cfg3; do
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --config $C --steps 20 --warmup 3 > gpurun_out/bench_${C}_n2.json 2> gpurun_out/bench_n2.err; tail -2 gpurun_out/bench_n2.err | grep -v OMP
+python -c "
+import json,sys; d=json.loads(open('gpurun_out/bench_%s_n2.json'%sys.argv[1]).read().strip().splitlines()[-1]); print(sys.argv[1], 'N=2', round(d['value']), 'ms', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value']), 'loss', d['e2e'].get('final_loss'))" $C
+done

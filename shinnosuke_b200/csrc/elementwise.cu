@@ -166,7 +166,9 @@ __global__ void scce_bwd_kernel(const float *__restrict__ p, const float *__rest
         for (int c = lane; c < classes; c += 32) {
             float pv = pr[c], yv = yr[c];
             dz[(long long)row * classes + c] = (pv - yv) * inv_rows;
-            if (yv != 0.f) loss -= yv * logf(pv);
+            // a probability that underflowed fp32 (logit gap > 87; the float64 reference still has it) counts
+            // as the smallest normal float instead of log(0) = -inf, which would poison the minibatch mean
+            if (yv != 0.f) loss -= yv * logf(fmaxf(pv, 1.17549435e-38f));
             if (pv > pbest) { pbest = pv; pi = c; }
             if (yv > ybest) { ybest = yv; yi = c; }
         }
