@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_pow2_kernel(const float *__r
 }
 
 __global__ void bn_finalize_kernel(double *scratch, BnFinal fin) {
+    pdl_wait();
     bn_finalize_channels(scratch, fin, (int)(blockIdx.x * blockDim.x + threadIdx.x), (int)(gridDim.x * blockDim.x));
 }
 
@@ -357,7 +358,7 @@ int sn_batchnorm_finalize_stats(const float *gamma, const float *beta, float *sa
     BnFinal fin{};
     fin.bwd = 0; fin.rows = rows; fin.C = C; fin.x = nullptr; fin.gamma = gamma; fin.beta = beta; fin.save_mean = save_mean;
     fin.save_invstd = save_invstd; fin.moving_mean = moving_mean; fin.moving_var = moving_var; fin.eps = eps; fin.momentum = momentum;
-    bn_finalize_kernel<<<(C + 31) / 32, 32, 0, as_stream(stream)>>>(scratch, fin);     // one warp per SM
+    SN_CUDA(launch_dependent(bn_finalize_kernel, dim3((C + 31) / 32), dim3(32), 0, as_stream(stream), scratch, fin));     // one warp per SM
     return after_launch("bn_finalize_kernel");
 }
 
@@ -402,7 +403,7 @@ int sn_batchnorm_finalize_bwd(const float *gamma, const float *save_mean, const 
     SN_REQUIRE(gamma && save_mean && save_invstd && scratch && rows > 0 && bn_pow2(C), "bad arguments");
     BnFinal fin{};
     fin.bwd = 1; fin.rows = rows; fin.C = C; fin.gamma = gamma; fin.mean = save_mean; fin.invstd = save_invstd;
-    bn_finalize_kernel<<<(C + 31) / 32, 32, 0, as_stream(stream)>>>(scratch, fin);     // one warp per SM
+    SN_CUDA(launch_dependent(bn_finalize_kernel, dim3((C + 31) / 32), dim3(32), 0, as_stream(stream), scratch, fin));     // one warp per SM
     return after_launch("bn_finalize_kernel");
 }
 

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(256) bn_pool_fwd_kernel(const float *__restric
                                                           __nv_bfloat16 *__restrict__ y_bf16,
                                                           uint32_t *__restrict__ code, const double *__restrict__ scratch,
                                                           long long windows4, int C, int W, int oh, int ow) {
+    pdl_wait();
     const int Q = C >> 2;
     const int cq = threadIdx.x % Q;
     const float *prm = bn_params(scratch, C);
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(256, 3) bn_pool_bwd_reduce_pooled_kernel(const
                                                                         const float *__restrict__ mean, const float *__restrict__ invstd,
                                                                         double *__restrict__ scratch, long long windows4, int C, int W,
                                                                         int oh, int ow, BnFinal fin) {
+    pdl_wait();
     const int Q = C >> 2;
     const int cq = threadIdx.x % Q;
     float bt[4], rg[4];
@@ -253,6 +255,7 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__r
                                                                 __nv_bfloat16 *__restrict__ dx_bf16, float *__restrict__ colsum,
                                                                 double *__restrict__ scratch, long long windows4, int C,
                                                                 int W, int oh, int ow) {
+    pdl_wait();
     const int Q = C >> 2;
     const int cq = threadIdx.x % Q;
     const float *prm = bn_params(scratch, C);
@@ -318,6 +321,7 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__r
 // adds the slot rows up and leaves them zero again for the next launch (they start zero: the scratch is
 // allocated zeroed, and only this pair of kernels touches the region)
 __global__ void colsum_fold_kernel(double *__restrict__ scratch, float *__restrict__ colsum, int C) {
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double *slots = scratch + 20 * (size_t)C;
@@ -376,9 +380,9 @@ int sn_bn_pool_fwd_apply(const float *x, float *y_pool, void *y_pool_bf16, uint8
     const long long windows4 = (long long)N * oh * ow * (C / 4);
     const int grid = grid_for_windows(windows4);
     if (pool_mode == SN_POOL_TIE_SPLIT)
-        bn_pool_fwd_kernel<SN_POOL_TIE_SPLIT><<<grid, 256, 0, st>>>(x, y_pool, (__nv_bfloat16 *)y_pool_bf16, (uint32_t *)code, scratch, windows4, C, W, oh, ow);
+        SN_CUDA(launch_dependent(bn_pool_fwd_kernel<SN_POOL_TIE_SPLIT>, dim3(grid), dim3(256), 0, st, x, y_pool, (__nv_bfloat16 *)y_pool_bf16, (uint32_t *)code, scratch, windows4, C, W, oh, ow));
     else
-        bn_pool_fwd_kernel<SN_POOL_FIRST_ARGMAX><<<grid, 256, 0, st>>>(x, y_pool, (__nv_bfloat16 *)y_pool_bf16, (uint32_t *)code, scratch, windows4, C, W, oh, ow);
+        SN_CUDA(launch_dependent(bn_pool_fwd_kernel<SN_POOL_FIRST_ARGMAX>, dim3(grid), dim3(256), 0, st, x, y_pool, (__nv_bfloat16 *)y_pool_bf16, (uint32_t *)code, scratch, windows4, C, W, oh, ow));
     return after_launch("bn_pool_fwd_kernel");
 }
 
@@ -425,13 +429,13 @@ static int bn_pool_bwd_impl(int phases, int defer, const float *dy_pool, const u
     }
     if (phases & 2) {
         SN_REQUIRE(dx || dx_bf16, "null tensor");
-#define SN_LAUNCH(M, K) bn_pool_bwd_apply_kernel<M, K><<<grid, 256, 0, st>>>(dy_pool, cd, x, dx, (__nv_bfloat16 *)dx_bf16, dx_colsum, scratch, windows4, C, W, oh, ow)
+#define SN_LAUNCH(M, K) SN_CUDA(launch_dependent(bn_pool_bwd_apply_kernel<M, K>, dim3(grid), dim3(256), 0, st, dy_pool, cd, x, dx, (__nv_bfloat16 *)dx_bf16, dx_colsum, scratch, windows4, C, W, oh, ow))
         if (pool_mode == SN_POOL_TIE_SPLIT) { if (mask_relu) SN_LAUNCH(SN_POOL_TIE_SPLIT, true); else SN_LAUNCH(SN_POOL_TIE_SPLIT, false); }
         else { if (mask_relu) SN_LAUNCH(SN_POOL_FIRST_ARGMAX, true); else SN_LAUNCH(SN_POOL_FIRST_ARGMAX, false); }
 #undef SN_LAUNCH
         int e = after_launch("bn_pool_bwd_apply_kernel");
         if (e || !dx_colsum) return e;
-        colsum_fold_kernel<<<(C + 255) / 256, 256, 0, st>>>(scratch, dx_colsum, C);
+        SN_CUDA(launch_dependent(colsum_fold_kernel, dim3((C + 255) / 256), dim3(256), 0, st, scratch, dx_colsum, C));
         return after_launch("colsum_fold_kernel");
     }
     return SN_OK;

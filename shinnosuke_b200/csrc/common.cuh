@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include "../../include/shinnosuke_b200.h"
 
 namespace sn {
@@ -59,6 +60,38 @@ inline int grid_for(long long work, int block, int ctas_per_sm = 8) {
     long long cap = (long long)num_sms() * ctas_per_sm;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
+}
+
+// ---- programmatic dependent launch (on by default; SN_PDL=0 launches every kernel normally) -----
+// A kernel launched through launch_dependent() may start while the previous kernel of the stream is
+// still draining: its blocks are scheduled as SMs free up and run their prologue (barrier init,
+// TMEM allocation, tensor-map prefetch, index arithmetic) until pdl_wait(), which returns once the
+// previous kernel has completed and its writes are visible.  EVERY kernel launched this way must call
+// pdl_wait() before its first access to global memory; the call is a no-op under a normal launch.
+// pdl_wait() also lets the NEXT kernel of the stream (if it was launched as a dependent) start being
+// scheduled from here on: its blocks take whatever SM resources become free and park in their own
+// pdl_wait() until this kernel has completed.  All blocks of this kernel are resident or done by the
+// time the last of them has passed this point, so the dependents cannot starve it.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("SN_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 __device__ __forceinline__ float relu_keep_sign(float z) {

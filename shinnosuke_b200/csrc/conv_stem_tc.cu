@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
+    pdl_wait();        // (the weights below are global memory the previous kernels may have written)
     // weights -> smem in the swizzled K-major layout: row f, 16-byte chunk j at (j ^ (f & 7)) * 16
     for (int i = threadIdx.x; i < BN * 32; i += SF_THREADS) {
         const int f = i >> 5, k = i & 31;
@@ -352,6 +353,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);     // shuffle from lane 0: provably warp-uniform
+    pdl_wait();
 
     if (nst > 0) {
         if (warp == 0) {
@@ -493,7 +495,7 @@ int launch_stem_fprop(const StemP &p, cudaStream_t st) {
         configured = true;
     }
     int grid = p.tiles < num_sms() ? p.tiles : num_sms();
-    stem_fprop_kernel<BN><<<grid, SF_THREADS, smem, st>>>(tmO, tmX, tmXr, p);
+    SN_CUDA(launch_dependent(stem_fprop_kernel<BN>, dim3(grid), dim3(SF_THREADS), (size_t)smem, st, tmO, tmX, tmXr, p));
     return after_launch("stem_fprop_kernel");
 }
 
@@ -562,8 +564,8 @@ int conv_stem_wgrad_tc(const float *x, const float *dy, float *dw, float *db, in
         else SN_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured[na2] = true;
     }
-    if (na2) stem_wgrad_kernel<2><<<dim3(ctas, f_tiles), SW_THREADS, smem, st>>>(tmDY, tmX, tmXr, p);
-    else stem_wgrad_kernel<4><<<dim3(ctas, f_tiles), SW_THREADS, smem, st>>>(tmDY, tmX, tmXr, p);
+    if (na2) SN_CUDA(launch_dependent(stem_wgrad_kernel<2>, dim3(ctas, f_tiles), dim3(SW_THREADS), (size_t)smem, st, tmDY, tmX, tmXr, p));
+    else SN_CUDA(launch_dependent(stem_wgrad_kernel<4>, dim3(ctas, f_tiles), dim3(SW_THREADS), (size_t)smem, st, tmDY, tmX, tmXr, p));
     return after_launch("stem_wgrad_kernel");
 }
 

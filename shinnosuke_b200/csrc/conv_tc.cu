@@ -205,6 +205,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);     // shuffle from lane 0: provably warp-uniform
+    pdl_wait();        // everything above (barriers, TMEM, descriptor prefetch) may overlap the previous kernel's tail
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -443,6 +444,7 @@ __global__ void __launch_bounds__(256) prepare_weights_bf16_kernel(const float *
                                                                    long long n, int cast_units, const long long *__restrict__ tasks,
                                                                    int ntasks) {
     __shared__ float tile[32][33];
+    pdl_wait();
     const int u = blockIdx.x;
     if (u < cast_units) {
         const long long i = (long long)u * 1024 + threadIdx.x * 4;
@@ -724,7 +726,7 @@ int launch_igemm_ks(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtens
     }
     int tiles = p.tiles_m * p.tiles_n;
     int grid = tiles < num_sms() ? tiles : num_sms();
-    conv_igemm_kernel<BN, KS, BF16, false><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmO, p);
+    SN_CUDA(launch_dependent(conv_igemm_kernel<BN, KS, BF16, false>, dim3(grid), dim3(IG_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, tmO, p));
     return after_launch("conv_igemm_kernel");
 }
 // CTA pairs: clusters of two, one pair per TPC, persistent over tile pairs
@@ -910,7 +912,7 @@ int flip_transpose_filters_bf16(const float *w, void *wt, int F, int C, int kh, 
 int prepare_weights_bf16(const float *arena, void *shadow, long long n, const long long *tasks, int ntasks, int flip_units, cudaStream_t st) {
     const int cast_units = (int)((n + 1023) / 1024);
     if (cast_units + flip_units == 0) return SN_OK;
-    prepare_weights_bf16_kernel<<<cast_units + flip_units, 256, 0, st>>>(arena, (__nv_bfloat16 *)shadow, n, cast_units, tasks, ntasks);
+    SN_CUDA(launch_dependent(prepare_weights_bf16_kernel, dim3(cast_units + flip_units), dim3(256), 0, st, arena, (__nv_bfloat16 *)shadow, n, cast_units, tasks, ntasks));
     return after_launch("prepare_weights_bf16_kernel");
 }
 

@@ -97,6 +97,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);     // shuffle from lane 0: provably warp-uniform
+    pdl_wait();
 
     if (nst > 0) {
         if (warp == 0) {
@@ -215,7 +216,7 @@ int launch_halo(const CUtensorMap &tmDY, const CUtensorMap &tmX, const HaloP &p,
         SN_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel<CN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
-    conv_wgrad_halo_kernel<CN, BF16><<<grid, HB_THREADS, smem, st>>>(tmDY, tmX, p);
+    SN_CUDA(launch_dependent(conv_wgrad_halo_kernel<CN, BF16>, dim3(grid), dim3(HB_THREADS), (size_t)smem, st, tmDY, tmX, p));
     return after_launch("conv_wgrad_halo_kernel");
 }
 

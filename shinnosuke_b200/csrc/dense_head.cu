@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256) dense_head_fwd_kernel(const float *__rest
                                                              const float *__restrict__ bias, float *__restrict__ out, int M, int K,
                                                              int softmax) {
     __shared__ float sred[8][HF_ROWS][O];
+    pdl_wait();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int r0 = blockIdx.x * HF_ROWS;
     float acc[HF_ROWS][O];
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(256) dense_head_bwd_kernel(const float *__rest
                                                              int rows_per_block, int accumulate_dx) {
     extern __shared__ float sdz[];                       // [rows of this block][O]
     __shared__ float sred[HB_ROWGROUPS][O][HB_FEATS + 1];
+    pdl_wait();
     const int f = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int k = blockIdx.x * HB_FEATS + f;
     const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block), nr = r1 - r0;
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(256) dense_head_bwd_kernel(const float *__rest
 
 template <int O>
 int launch_fwd(const float *x, const float *w, const float *bias, float *out, int M, int K, int softmax, cudaStream_t st) {
-    dense_head_fwd_kernel<O><<<(M + HF_ROWS - 1) / HF_ROWS, 256, 0, st>>>(x, w, bias, out, M, K, softmax);
+    SN_CUDA(launch_dependent(dense_head_fwd_kernel<O>, dim3((M + HF_ROWS - 1) / HF_ROWS), dim3(256), 0, st, x, w, bias, out, M, K, softmax));
     return after_launch("dense_head_fwd_kernel");
 }
 template <int O>
@@ -163,7 +165,7 @@ int launch_bwd(const float *x, const float *dz, const float *w, float *dw, float
     int rb = (fblocks >= 2 * num_sms()) ? 256 : 64;
     if (rb > M) rb = M;
     const int yblocks = (M + rb - 1) / rb;
-    dense_head_bwd_kernel<O><<<dim3(fblocks, yblocks), 256, rb * O * sizeof(float), st>>>(x, dz, w, dw, db, dx, M, K, rb, acc);
+    SN_CUDA(launch_dependent(dense_head_bwd_kernel<O>, dim3(fblocks, yblocks), dim3(256), rb * O * sizeof(float), st, x, dz, w, dw, db, dx, M, K, rb, acc));
     return after_launch("dense_head_bwd_kernel");
 }
 

@@ -155,6 +155,7 @@ __global__ void softmax_fwd_kernel(const float *__restrict__ z, float *__restric
 
 __global__ void scce_bwd_kernel(const float *__restrict__ p, const float *__restrict__ y, float *__restrict__ dz,
                                 float *__restrict__ metrics, int rows, int classes, float inv_rows) {
+    pdl_wait();
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     float loss = 0.f, hit = 0.f;
@@ -197,6 +198,7 @@ __global__ void scce_bwd_kernel(const float *__restrict__ p, const float *__rest
 
 // ------------------------------------------------------------------ optimizers
 __global__ void sgd_kernel(float *__restrict__ w, float *__restrict__ g, long long n, float lr_scaled) {
+    pdl_wait();
     long long n4 = n >> 2;
     long long stride = (long long)gridDim.x * blockDim.x;
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -305,14 +307,14 @@ int sn_scce_bwd(const float *probs, const float *onehot, float *dlogits, float *
     SN_REQUIRE(probs && onehot && dlogits && rows >= 0 && classes > 0 && denom_rows >= 0, "bad arguments");
     if (!rows) return SN_OK;
     float inv = 1.f / (float)(denom_rows > 0 ? denom_rows : rows);
-    scce_bwd_kernel<<<(rows + 7) / 8, 256, 0, as_stream(stream)>>>(probs, onehot, dlogits, metrics, rows, classes, inv);
+    SN_CUDA(launch_dependent(scce_bwd_kernel, dim3((rows + 7) / 8), dim3(256), 0, as_stream(stream), probs, onehot, dlogits, metrics, rows, classes, inv));
     return after_launch("scce_bwd_kernel");
 }
 int sn_sgd_update(float *w, float *g, long long n, float lr, float grad_scale, void *stream) {
     SN_REQUIRE(w && g && n >= 0, "bad arguments");
     if (!n) return SN_OK;
     if ((((uintptr_t)w | (uintptr_t)g) & 15) == 0)
-        sgd_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(w, g, n, lr * grad_scale);
+        SN_CUDA(launch_dependent(sgd_kernel, dim3(grid_for((n + 3) / 4, 256)), dim3(256), 0, as_stream(stream), w, g, n, lr * grad_scale));
     else
         sgd_scalar_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(w, g, n, lr * grad_scale);
     return after_launch("sgd_kernel");
