@@ -1,3 +1,5 @@
+# NOTE: needs the throw-away SN_IGEMM_DEBUG switches (skip loads / MMAs / stores) that were patched into conv_tc.cu for the
+# measurement in profiles/r01_igemm_pair_vs_single.txt and removed again; with the committed library every column is the full kernel.
 # timing decomposition of conv_igemm_kernel with the TEMPORARY SN_IGEMM_DEBUG switches (results are garbage, times are not)
 import os, sys, torch, ctypes
 sys.path.insert(0, '.')
