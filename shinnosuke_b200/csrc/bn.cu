@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(256) bn_reduce_pow2_kernel(const float *__rest
 template <bool RELU>
 __global__ void __launch_bounds__(256) bn_apply_train_pow2_kernel(const float *__restrict__ x, float *__restrict__ y,
                                                                   const double *__restrict__ scratch, long long total4, int C) {
+    pdl_wait();
     const int Q = C >> 2;
     const int cq = threadIdx.x % Q;
     const float *prm = bn_params(scratch, C);
@@ -272,6 +273,7 @@ template <bool ACC, bool MASK>
 __global__ void __launch_bounds__(256) bn_bwd_apply_pow2_kernel(const float *__restrict__ dy, const float *__restrict__ x,
                                                                 float *__restrict__ dx, const double *__restrict__ scratch,
                                                                 long long total4, int C) {
+    pdl_wait();
     const int Q = C >> 2;
     const int cq = threadIdx.x % Q;
     const float *prm = bn_params(scratch, C);
@@ -366,8 +368,8 @@ int sn_batchnorm_fwd_apply(const float *x, float *y, const double *scratch, long
     SN_REQUIRE(x && y && scratch && rows > 0, "bad arguments");
     SN_REQUIRE(bn_pow2(C) && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0, "needs C = 4*2^k <= 1024 and 16-byte aligned tensors");
     const long long total4 = rows * C / 4;
-    if (relu) bn_apply_train_pow2_kernel<true><<<bn_grid(total4), 256, 0, as_stream(stream)>>>(x, y, scratch, total4, C);
-    else bn_apply_train_pow2_kernel<false><<<bn_grid(total4), 256, 0, as_stream(stream)>>>(x, y, scratch, total4, C);
+    if (relu) SN_CUDA(launch_dependent(bn_apply_train_pow2_kernel<true>, dim3(bn_grid(total4)), dim3(256), 0, as_stream(stream), x, y, scratch, total4, C));
+    else SN_CUDA(launch_dependent(bn_apply_train_pow2_kernel<false>, dim3(bn_grid(total4)), dim3(256), 0, as_stream(stream), x, y, scratch, total4, C));
     return after_launch("bn_apply_train_pow2_kernel");
 }
 
@@ -414,7 +416,7 @@ int sn_batchnorm_bwd_apply(const float *dy, const float *x, float *dx, const dou
     cudaStream_t st = as_stream(stream);
     const long long total4 = rows * C / 4;
     const int g2 = bn_grid(total4);
-#define SN_LAUNCHP(A, M) bn_bwd_apply_pow2_kernel<A, M><<<g2, 256, 0, st>>>(dy, x, dx, scratch, total4, C)
+#define SN_LAUNCHP(A, M) SN_CUDA(launch_dependent(bn_bwd_apply_pow2_kernel<A, M>, dim3(g2), dim3(256), 0, st, dy, x, dx, scratch, total4, C))
     if (accumulate_dx) { if (mask_relu) SN_LAUNCHP(true, true); else SN_LAUNCHP(true, false); }
     else { if (mask_relu) SN_LAUNCHP(false, true); else SN_LAUNCHP(false, false); }
 #undef SN_LAUNCHP
@@ -469,7 +471,7 @@ int sn_batchnorm_bwd(const float *dy, const float *x, const float *gamma, const 
         int e2 = after_launch("bn_reduce_pow2_kernel");
         if (e2) return e2;
         const int g2 = bn_grid(total4);
-#define SN_LAUNCHP(A, M) bn_bwd_apply_pow2_kernel<A, M><<<g2, 256, 0, st>>>(dy, x, dx, scratch, total4, C)
+#define SN_LAUNCHP(A, M) SN_CUDA(launch_dependent(bn_bwd_apply_pow2_kernel<A, M>, dim3(g2), dim3(256), 0, st, dy, x, dx, scratch, total4, C))
         if (accumulate_dx) { if (mask_relu) SN_LAUNCHP(true, true); else SN_LAUNCHP(true, false); }
         else { if (mask_relu) SN_LAUNCHP(false, true); else SN_LAUNCHP(false, false); }
 #undef SN_LAUNCHP

@@ -509,6 +509,7 @@ __global__ void split_tf32_lo_kernel(const float *__restrict__ s, float *__restr
 }
 
 __global__ void cast_f32_bf16_kernel(const float *__restrict__ s, __nv_bfloat16 *__restrict__ d, long long n) {
+    pdl_wait();
     const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x, t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if ((((uintptr_t)s) & 15) == 0 && (((uintptr_t)d) & 7) == 0) {
         for (long long i = t; i < n4; i += stride) {
@@ -924,7 +925,7 @@ int split_tf32_lo(const float *src, float *lo, long long n, cudaStream_t st) {
 
 int cast_f32_to_bf16(const float *src, void *dst, long long n, cudaStream_t st) {
     if (n <= 0) return SN_OK;
-    cast_f32_bf16_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(src, (__nv_bfloat16 *)dst, n);
+    SN_CUDA(launch_dependent(cast_f32_bf16_kernel, dim3(grid_for((n + 3) / 4, 256)), dim3(256), 0, st, src, (__nv_bfloat16 *)dst, n));
     return after_launch("cast_f32_bf16_kernel");
 }
 

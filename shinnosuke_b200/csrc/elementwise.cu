@@ -48,6 +48,7 @@ __global__ void cast_f32_f64_kernel(const float *__restrict__ s, double *__restr
         d[i] = (double)s[i];
 }
 __global__ void axpy_kernel(float a, const float *__restrict__ x, float *__restrict__ y, long long n) {
+    pdl_wait();
     long long n4 = n >> 2;
     long long stride = (long long)gridDim.x * blockDim.x;
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -65,6 +66,7 @@ __global__ void axpy_kernel(float a, const float *__restrict__ x, float *__restr
 }
 template <bool RELU>
 __global__ void add_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ o, long long n) {
+    pdl_wait();
     long long n4 = n >> 2;
     long long stride = (long long)gridDim.x * blockDim.x;
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -80,6 +82,7 @@ __global__ void add_kernel(const float *__restrict__ a, const float *__restrict_
     }
 }
 __global__ void relu_bwd_kernel(float *__restrict__ dy, const float *__restrict__ y, long long n) {
+    pdl_wait();
     long long n4 = n >> 2;
     long long stride = (long long)gridDim.x * blockDim.x;
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -99,6 +102,7 @@ __global__ void relu_bwd_kernel(float *__restrict__ dy, const float *__restrict_
     }
 }
 __global__ void relu_fwd_kernel(const float *x, float *y, long long n) {
+    pdl_wait();
     const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x, t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if ((((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
         for (long long i = t; i < n4; i += stride) {
@@ -254,31 +258,31 @@ int sn_cast_f32_to_f64(const float *src, double *dst, long long n, void *stream)
 int sn_axpy(float alpha, const float *x, float *y, long long n, void *stream) {
     SN_REQUIRE(x && y && n >= 0, "bad arguments");
     if (!n) return SN_OK;
-    axpy_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(alpha, x, y, n);
+    SN_CUDA(launch_dependent(axpy_kernel, dim3(grid_for((n + 3) / 4, 256)), dim3(256), 0, as_stream(stream), alpha, x, y, n));
     return after_launch("axpy_kernel");
 }
 int sn_add(const float *a, const float *b, float *out, long long n, void *stream) {
     SN_REQUIRE(a && b && out && n >= 0, "bad arguments");
     if (!n) return SN_OK;
-    add_kernel<false><<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(a, b, out, n);
+    SN_CUDA(launch_dependent(add_kernel<false>, dim3(grid_for((n + 3) / 4, 256)), dim3(256), 0, as_stream(stream), a, b, out, n));
     return after_launch("add_kernel");
 }
 int sn_add_relu(const float *a, const float *b, float *out, long long n, void *stream) {
     SN_REQUIRE(a && b && out && n >= 0, "bad arguments");
     if (!n) return SN_OK;
-    add_kernel<true><<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(a, b, out, n);
+    SN_CUDA(launch_dependent(add_kernel<true>, dim3(grid_for((n + 3) / 4, 256)), dim3(256), 0, as_stream(stream), a, b, out, n));
     return after_launch("add_kernel");
 }
 int sn_relu_bwd(float *dy, const float *y, long long n, void *stream) {
     SN_REQUIRE(dy && y && n >= 0, "bad arguments");
     if (!n) return SN_OK;
-    relu_bwd_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(dy, y, n);
+    SN_CUDA(launch_dependent(relu_bwd_kernel, dim3(grid_for((n + 3) / 4, 256)), dim3(256), 0, as_stream(stream), dy, y, n));
     return after_launch("relu_bwd_kernel");
 }
 int sn_relu_fwd(const float *x, float *y, long long n, void *stream) {
     SN_REQUIRE(x && y && n >= 0, "bad arguments");
     if (!n) return SN_OK;
-    relu_fwd_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(x, y, n);
+    SN_CUDA(launch_dependent(relu_fwd_kernel, dim3(grid_for((n + 3) / 4, 256)), dim3(256), 0, as_stream(stream), x, y, n));
     return after_launch("relu_fwd_kernel");
 }
 int sn_pad2d_fwd(const float *x, float *y, int N, int H, int W, int C, int pad_h, int pad_w, void *stream) {
