@@ -79,13 +79,7 @@ __device__ __forceinline__ void pdl_wait() {
 
 inline bool pdl_enabled() {
     static int on = -1;
-    if (on < 0) {
-        const char *e = getenv("SN_PDL");
-        if (e && (e[0] == '0' || e[0] == '1')) on = e[0] - '0';
-        // under a profiler's injection layer (Nsight Compute / Systems) kernels are launched normally unless
-        // SN_PDL=1 insists: captures then show every kernel of the step on its own, as in profiles/
-        else on = (getenv("CUDA_INJECTION64_PATH") || getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE") || getenv("NSYS_PROFILING_SESSION_ID")) ? 0 : 1;
-    }
+    if (on < 0) { const char *e = getenv("SN_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
     return on == 1;
 }
 
