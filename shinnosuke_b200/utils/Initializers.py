@@ -57,20 +57,48 @@ class Normal(Initializer):
         return np.random.normal(loc=self.mean, scale=self.std, size=size)
 
 
-def _scaled(base, fn):
-    class _Init(Initializer):
-        def __call__(self, size):
-            fan_in, fan_out = _fans(size)
-            return base(fn(fan_in, fan_out))(size)
-    return _Init
+class _Scaled(Initializer):
+    """utils/Initializers.py:39-121: a Uniform / Normal whose scale comes from the fans.  (Module-level
+    classes: instances live on layers, and layers are pickled by save().)"""
+    base = None
+
+    @staticmethod
+    def scale(fan_in, fan_out):
+        raise NotImplementedError
+
+    def __call__(self, size):
+        fan_in, fan_out = _fans(size)
+        return self.base(self.scale(fan_in, fan_out))(size)
 
 
-LecunUniform = _scaled(Uniform, lambda i, o: np.sqrt(3. / i))
-GlorotUniform = _scaled(Uniform, lambda i, o: np.sqrt(6. / (i + o)))
-HeUniform = _scaled(Uniform, lambda i, o: np.sqrt(6. / i))
-LecunNormal = _scaled(Normal, lambda i, o: np.sqrt(1. / i))
-GlorotNormal = _scaled(Normal, lambda i, o: np.sqrt(2. / (i + o)))
-HeNormal = _scaled(Normal, lambda i, o: np.sqrt(2. / i))
+class LecunUniform(_Scaled):
+    base = Uniform
+    scale = staticmethod(lambda i, o: np.sqrt(3. / i))
+
+
+class GlorotUniform(_Scaled):
+    base = Uniform
+    scale = staticmethod(lambda i, o: np.sqrt(6. / (i + o)))
+
+
+class HeUniform(_Scaled):
+    base = Uniform
+    scale = staticmethod(lambda i, o: np.sqrt(6. / i))
+
+
+class LecunNormal(_Scaled):
+    base = Normal
+    scale = staticmethod(lambda i, o: np.sqrt(1. / i))
+
+
+class GlorotNormal(_Scaled):
+    base = Normal
+    scale = staticmethod(lambda i, o: np.sqrt(2. / (i + o)))
+
+
+class HeNormal(_Scaled):
+    base = Normal
+    scale = staticmethod(lambda i, o: np.sqrt(2. / i))
 
 
 class Orthogonal(Initializer):

@@ -240,3 +240,26 @@ def test_relu_folding_and_fusion_flags_cfg4():
     assert bn2._relu_out is None                      # its consumer is the Add, not a ReLU
     bn1, a1, bn2, add, a2 = build(False)
     assert bn1._relu_out is None and a1._folded_into is None and add._relu_out is None and a2._folded_into is None
+
+
+def test_layers_with_every_initializer_pickle():
+    """save() pickles the layers (models.py:208-220), and layers hold their initializer objects: every
+    initializer — the fan-scaled ones included — must survive a round trip, and a config-5 model's
+    layer list must come back with the same weights and storage layouts."""
+    import pickle
+    from shinnosuke_b200 import Embedding, LSTM
+    for name in ('zeros', 'ones', 'uniform', 'normal', 'glorot_uniform', 'glorot_normal', 'he_uniform', 'he_normal',
+                 'lecun_uniform', 'lecun_normal', 'orthogonal'):
+        init = pickle.loads(pickle.dumps(I.get_initializer(name)))
+        np.random.seed(1); a = init((6, 4))
+        np.random.seed(1); b = I.get_initializer(name)((6, 4))
+        assert np.array_equal(a, b), name
+    np.random.seed(0)
+    m = Sequential()
+    m.add(Embedding(50, 8, input_length=6)); m.add(LSTM(64)); m.add(Dense(2, activation='softmax', initializer='glorot_uniform'))
+    m.compile('sgd', 'sparse_categorical_crossentropy')
+    layers, opt, loss = pickle.loads(pickle.dumps([m.layers, m.optimizer, m.loss]))
+    for a, b in zip(layers, m.layers):
+        assert type(a) is type(b)
+        for va, vb in zip(a.variables, b.variables):
+            assert va.layout == vb.layout and np.array_equal(np.asarray(va.output_tensor), np.asarray(vb.output_tensor))
