@@ -263,3 +263,55 @@ def test_layers_with_every_initializer_pickle():
         assert type(a) is type(b)
         for va, vb in zip(a.variables, b.variables):
             assert va.layout == vb.layout and np.array_equal(np.asarray(va.output_tensor), np.asarray(vb.output_tensor))
+
+
+def test_gradient_hand_over_rules():
+    """Layer._hand_over_grads: a pass-through layer gives its gradient buffer to an operand only when that
+    operand has no other consumer and nothing has been written to its gradient yet; Add serves the
+    adopting operand last (layers/Base.py)."""
+    from shinnosuke_b200.layers.Base import Layer, Add
+
+    class Buf(object):
+        def __init__(self, shape, layout='nhwc'):
+            self.shape, self.layout, self.size = tuple(shape), layout, int(np.prod(shape))
+            self.log = []
+
+        def view(self, shape, layout):
+            v = Buf(shape, layout); v.base = self
+            return v
+
+        def copy_from(self, other):
+            self.log.append(('copy', other))
+
+        def add_(self, other):
+            self.log.append(('add', other))
+
+    def layer(n_consumers):
+        l = Layer()
+        l.outbound_layers = [object()] * n_consumers
+        l.grads = Buf((2, 3, 4, 4))
+        return l
+
+    src, g = Layer(), Buf((2, 3, 4, 4))
+    single, shared, written = layer(1), layer(2), layer(1)
+    written._grads_written = True
+    assert src._hand_over_grads(single, g) and single.grads is g and single._grads_written
+    own = shared.grads
+    assert not src._hand_over_grads(shared, g) and shared.grads is own
+    assert not src._hand_over_grads(written, g)
+    frozen = layer(1); frozen.require_grads = False
+    assert not src._hand_over_grads(frozen, g)
+    # Add: the multi-consumer operand gets its copy first, the single-consumer operand adopts the buffer
+    a, b = layer(2), layer(1)
+    add = Add()
+    add.inbounds = [b, a]
+    add.grads = Buf((2, 3, 4, 4))
+    a_own = a.grads
+    add.backward()
+    assert b.grads is add.grads and a.grads is a_own and a_own.log == [('copy', add.grads)]
+    # the same layer on both sides: one copy, one accumulation, no hand-over
+    c = layer(2)
+    add2 = Add(); add2.inbounds = [c, c]; add2.grads = Buf((2, 3, 4, 4))
+    c_own = c.grads
+    add2.backward()
+    assert c.grads is c_own and [k for k, _ in c_own.log] == ['copy', 'add']
