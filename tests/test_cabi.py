@@ -57,3 +57,40 @@ def test_product_does_not_import_the_oracle():
                 if re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M) or '/root/reference' in text:
                     bad.append(f)
     assert not bad
+
+
+def test_every_dependent_launch_target_waits_for_its_predecessor():
+    """Programmatic dependent launch (csrc/common.cuh): a kernel launched through launch_dependent() may
+    start before the previous kernel of the stream has finished, so its body must call pdl_wait() before
+    it touches global memory.  Static check over the sources: every kernel name passed to
+    launch_dependent() has pdl_wait() in its definition, ahead of the first __ldg / global pointer
+    dereference pattern we can recognise (the call must be in the first statements of the body or right
+    after the shared-memory / barrier prologue)."""
+    import glob
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'shinnosuke_b200', 'csrc')
+    text = {p: open(p).read() for p in glob.glob(os.path.join(root, '*.cu'))}
+    launched = set()
+    for src in text.values():
+        launched.update(re.findall(r'launch_dependent\(\s*([A-Za-z_0-9]+)', src))
+    assert len(launched) >= 20, launched
+    for name in sorted(launched):
+        bodies = []
+        for src in text.values():
+            for m in re.finditer(r'__global__[^;{]*?\b%s\s*\(' % re.escape(name), src):
+                start = src.index('{', m.end())
+                depth, i = 0, start
+                while True:
+                    depth += src[i] == '{'
+                    depth -= src[i] == '}'
+                    if depth == 0:
+                        break
+                    i += 1
+                bodies.append(src[start:i])
+        assert bodies, 'definition of %s not found' % name
+        for body in bodies:
+            assert 'pdl_wait();' in body, '%s is launched as a dependent but never calls pdl_wait()' % name
+            head = body[:body.index('pdl_wait();')]
+            assert '__ldg(' not in head and 'ldg4(' not in head and 'atomicAdd(' not in head, \
+                '%s reads or updates global memory before pdl_wait()' % name
