@@ -91,6 +91,8 @@ SN_API void      sn_launch_count_reset(void);
 /* how many of those were CTA-pair (cta_group::2) launches of the implicit-GEMM kernel: the pair tiles
  * are chosen by shape (SN_IGEMM_PAIR=0 never, =2 whenever eligible), tests use this to see which ran */
 SN_API long long sn_igemm_pair_launches(void);
+/* override the choice in-process: 0 never, 1 by shape (default), 2 whenever eligible, -1 re-read SN_IGEMM_PAIR */
+SN_API int sn_igemm_set_pair_mode(int mode);
 
 /* ----------------------------------------------------------------- layout */
 /* API-boundary transposes between the reference's NCHW and the device's NHWC. */

@@ -35,6 +35,7 @@ using namespace sn::tc;
 namespace sn {
 
 long long g_igemm_pair_launches = 0;
+int g_igemm_pair_mode = -1;          // -1: read SN_IGEMM_PAIR on first use; sn_igemm_set_pair_mode() overrides
 
 EncodeTiledFn get_encode_tiled() {
     static EncodeTiledFn fn = nullptr;
@@ -777,7 +778,7 @@ namespace sn {
 // halved filter traffic saves, and 128-wide tiles never gained.
 // SN_IGEMM_PAIR=0 never pairs, =2 pairs every eligible shape (tests, A/B measurements).
 static bool igemm_use_pairs(int BN, int tiles_m, int tiles_n) {
-    static int mode = -1;
+    int &mode = g_igemm_pair_mode;
     if (mode < 0) { const char *e = getenv("SN_IGEMM_PAIR"); mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }
     if (mode == 0 || BN < 128 || (tiles_m % 2) != 0) return false;
     if (mode == 2) return true;

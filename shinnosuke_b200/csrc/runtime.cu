@@ -6,6 +6,7 @@ namespace sn {
 static thread_local char g_err[512] = "";
 long long g_launch_count = 0;
 extern long long g_igemm_pair_launches;      // conv_tc.cu
+extern int g_igemm_pair_mode;
 void set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -22,6 +23,11 @@ const char *sn_last_error(void) { return g_err; }
 long long sn_launch_count(void) { return g_launch_count; }
 void sn_launch_count_reset(void) { g_launch_count = 0; }
 long long sn_igemm_pair_launches(void) { return g_igemm_pair_launches; }
+int sn_igemm_set_pair_mode(int mode) {
+    SN_REQUIRE(mode >= -1 && mode <= 2, "pair mode must be -1 (environment), 0 (never), 1 (by shape) or 2 (whenever eligible)");
+    g_igemm_pair_mode = mode;
+    return SN_OK;
+}
 
 int sn_device_count(int *count) {
     SN_REQUIRE(count, "null out pointer");

@@ -24,6 +24,7 @@ class Variable(object):
         self.name = name
         self.layout = layout            # storage layout on the device ('krsc', 'dense_w', 'flat')
         self._host = None if initial_value is None else np.array(initial_value, dtype=np.float64)
+        self._host_grads = None
         self.output_shape = shape if self._host is None else self._host.shape
         self._dev = None
         self._grads = None
@@ -76,6 +77,10 @@ class Variable(object):
         self._dev = DeviceTensor(wbuf, self.output_shape, layout)
         self._grads = DeviceTensor(gbuf, self.output_shape, layout)
         self._dev.set(self._host)
+        pending = getattr(self, '_host_grads', None)
+        if pending is not None:                 # unpickled mid-training: the accumulated gradients come back too
+            self._grads.set(pending)
+            self._host_grads = None
 
     def ensure_device(self):
         """Stand-alone placement for op-level use of a layer outside a model."""
@@ -83,6 +88,10 @@ class Variable(object):
             layout = self.layout or 'flat'
             self._dev = DeviceTensor.from_numpy(self._host, layout)
             self._grads = DeviceTensor.zeros(self.output_shape, layout)
+            pending = getattr(self, '_host_grads', None)
+            if pending is not None:
+                self._grads.set(pending)
+                self._host_grads = None
         return self._dev
 
     def relayout(self, layout):
@@ -106,6 +115,28 @@ class Variable(object):
         if self._dev is not None:
             self._host = self._dev.numpy()
         return self._host
+
+    # -- pickling: the reference's format is NumPy arrays only (models.py:208-220 pickles the layers,
+    # whose Variables hold `output_tensor` and `grads` ndarrays).  Device views into the parameter arena
+    # must never reach the pickle: torch would serialise the whole backing storage once per view.
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        if self._dev is not None:
+            d['_host'] = self._dev.numpy()
+        g = None
+        if self._grads is not None:
+            g = self._grads.numpy()
+            # SGD leaves the gradients zeroed (utils/Optimizers.py:32); Momentum and the adaptive optimizers
+            # never zero them (:52-55), so a resumed run needs them back
+            g = g.astype(np.float32) if np.any(g) else None
+        d['_host_grads'] = g
+        d['_dev'] = None
+        d['_grads'] = None
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self.__dict__.setdefault('_host_grads', None)
 
 
 class Layer(object):
@@ -242,7 +273,10 @@ class Layer(object):
         d['_bufs'] = {}
         for k in ('input_tensor', 'output_tensor', 'grads'):
             d[k] = None
-        for k in ('_xb', '_bf16_support'):
+        # device handles and per-step hand-over flags of the layers (bf16 operand copies, 3xTF32 lo parts,
+        # prepared filters, fused-pool outputs): none of them belongs in a checkpoint
+        for k in ('_xb', '_bf16_support', '_x_lo', '_w_prepared', '_xb_filled_for', '_code', '_fused_output', '_stats_from',
+                  '_db_done', '_gb_ready'):
             d.pop(k, None)
         return d
 
