@@ -312,26 +312,59 @@ def cpu_oracle_throughput(cfg, batch, steps, warmup=1):
     return batch * steps / dt, dt / steps
 
 
+def cpu_reference_throughput(cfg, batch, steps, warmup=1, warmup_batch=None):
+    """The UNMODIFIED reference (oracle/_ref, copied from /root/reference by oracle/make_ref.sh) through its
+    own Sequential.fit(): float64 NumPy, all host cores through OpenBLAS, same synthetic data and the same
+    seed-0 initial weights as the GPU arm.  Returns (samples/s, s/step, losses) or None when the reference
+    cannot build this config as shipped (configs 4, 5: SURVEY.md 8(c)) or oracle/_ref is missing."""
+    from oracle import ref_driver
+    if not ref_driver.can_build(cfg):
+        return None
+    wb = warmup_batch or batch
+    X, Y = synth(cfg, batch * steps + wb * warmup)
+    if warmup and wb != batch:
+        # a short untimed pass on a small batch first (imports, OpenBLAS thread pool), then the timed steps
+        ref_driver.fit_throughput(cfg, X[:wb * warmup], Y[:wb * warmup], wb, 0, warmup)
+        return ref_driver.fit_throughput(cfg, X[wb * warmup:], Y[wb * warmup:], batch, 0, steps)
+    return ref_driver.fit_throughput(cfg, X, Y, batch, warmup, steps)
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path.  The reference is a
-    pure-Python package that cannot travel to the GPU box, so this times oracle/ (its NumPy
-    restatement, pinned to the live reference by tests/golden)."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores.
+    oracle/_ref holds the unmodified reference package (pure Python, so "building" it is a copy:
+    oracle/make_ref.sh); its own Sequential.fit() runs the SAME config as the GPU arm — same layers, same
+    minibatch size, same synthetic data, same initial weights (`kind: "reference"`, `same_config: true`).
+    A step of config 3 at batch 512 takes ~10 s on 16 cores, so the number of timed steps is bounded
+    (stated in `sample`).  Configs the reference cannot construct as shipped (4: Add crashes at graph build;
+    5: wrong LSTM backward) and a box without oracle/_ref fall back to the NumPy port (`kind: "port"`)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cfg = args.config
-    sample_batch = {'cfg3': 64, 'cfg1': 256, 'cfg2': 128, 'cfg4': 32, 'cfg5': 256}[cfg]
-    steps = max(1, args.steps)
-    value, s_per_step = cpu_oracle_throughput(cfg, sample_batch, steps, max(1, min(args.warmup, 2)))
+    B = args.per_gpu_batch or CONFIGS[cfg]['per_gpu_batch']
     cores = os.cpu_count()
-    sample = '%d steps of batch %d (float64 NumPy, OpenBLAS threads = all %d cores)' % (steps, sample_batch, cores)
+    budget_steps = {'cfg3': 2, 'cfg1': 30, 'cfg2': 100}.get(cfg, 3)
+    steps = max(1, min(args.steps, budget_steps))
+    warm = max(1, min(args.warmup, 1))
+    res = cpu_reference_throughput(cfg, B, steps, warm, warmup_batch=64 if cfg == 'cfg3' else None)
+    if res is not None:
+        value, s_per_step, losses = res
+        kind, sample_batch, same = 'reference', B, True
+        sample = ('%d timed minibatches of %d through the unmodified reference Sequential.fit() (float64 NumPy, OpenBLAS on all %d '
+                  'cores), after %d untimed warm-up minibatch(es)' % (steps, B, cores, warm))
+    else:
+        sample_batch = {'cfg3': 64, 'cfg1': 256, 'cfg2': 128, 'cfg4': 32, 'cfg5': 256}[cfg]
+        value, s_per_step = cpu_oracle_throughput(cfg, sample_batch, steps, warm)
+        kind, same, losses = 'port', sample_batch == B, None
+        sample = '%d steps of batch %d (float64 NumPy port of the reference, OpenBLAS threads = all %d cores)' % (steps, sample_batch, cores)
     line = dict(impl='reference', metric='train_samples_per_sec', value=value, unit='samples/s', n_gpus=args.gpus,
-                steps=steps, warmup=args.warmup, ms_per_step=s_per_step * 1e3, higher_is_better=True, scaling='weak',
-                vs_baseline=None, dtype='f64', data='synthetic',
-                config=dict(workload=CONFIGS[cfg]['name'], per_gpu_batch=args.per_gpu_batch or CONFIGS[cfg]['per_gpu_batch'],
-                            sample_batch=sample_batch),
-                cpu_baseline=dict(value=value, unit='samples/s', cores=cores, kind='port', sample=sample),
-                e2e=dict(value=value, unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+                steps=args.steps, warmup=args.warmup, steps_timed=steps, ms_per_step=s_per_step * 1e3, higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
+                config=dict(workload=CONFIGS[cfg]['name'], per_gpu_batch=B, global_batch=B, sample_batch=sample_batch,
+                            same_config=same),
+                cpu_baseline=dict(value=value, unit='samples/s', cores=cores, kind=kind, sample=sample),
+                e2e=dict(value=value, unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
+                losses=losses)
     print(json.dumps(line))
 
 
@@ -423,14 +456,22 @@ def run_ours(args):
             os.makedirs(os.path.dirname(os.path.abspath(args.kernel_table)), exist_ok=True)
             with open(args.kernel_table, 'w') as f:
                 json.dump(dict(config=cfg, per_gpu_batch=B, precision=precision, step_ms_graph=dev_ms / K, kernels=rows), f, indent=1)
-        cpu_batch = {'cfg3': 64, 'cfg1': 256, 'cfg2': 128, 'cfg4': 32, 'cfg5': 256}[cfg]
-        cpu_steps = {'cfg3': 6, 'cfg1': 30, 'cfg2': 200, 'cfg4': 3, 'cfg5': 10}[cfg]
+        cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_val, _ = cpu_oracle_throughput(cfg, cpu_batch, cpu_steps)
-            cpu = dict(value=cpu_val, unit='samples/s', cores=os.cpu_count(), kind='port',
-                       sample='%d steps of batch %d of the same workload, float64 NumPy oracle' % (cpu_steps, cpu_batch))
-        else:
-            cpu = None
+            # the reference's own fit() at the benchmarked minibatch size when it can build the config,
+            # else the NumPy port on a smaller batch; ~10-30 s of host time either way
+            res = cpu_reference_throughput(cfg, B, {'cfg3': 2, 'cfg1': 30, 'cfg2': 100}.get(cfg, 2), 1,
+                                           warmup_batch=64 if cfg == 'cfg3' else None) if B <= 512 else None
+            if res is not None:
+                cpu = dict(value=res[0], unit='samples/s', cores=os.cpu_count(), kind='reference',
+                           sample='%d minibatches of %d through the unmodified reference Sequential.fit() (oracle/_ref), float64 NumPy'
+                                  % ({'cfg3': 2, 'cfg1': 30, 'cfg2': 100}.get(cfg, 2), B))
+            else:
+                cpu_batch = {'cfg3': 64, 'cfg1': 256, 'cfg2': 128, 'cfg4': 32, 'cfg5': 256}[cfg]
+                cpu_steps = {'cfg3': 6, 'cfg1': 30, 'cfg2': 200, 'cfg4': 3, 'cfg5': 10}[cfg]
+                cpu_val, _ = cpu_oracle_throughput(cfg, cpu_batch, cpu_steps)
+                cpu = dict(value=cpu_val, unit='samples/s', cores=os.cpu_count(), kind='port',
+                           sample='%d steps of batch %d of the same workload, float64 NumPy oracle' % (cpu_steps, cpu_batch))
         h2d = int(n_loc * (np.prod(X.shape[1:]) + Y.shape[1]) * 4)
         line = dict(metric='train_samples_per_sec', value=G * K / (dev_ms * 1e-3), unit='samples/s', n_gpus=world, steps=K,
                     warmup=Wm, ms_per_step=dev_ms / K, higher_is_better=True, scaling='weak', vs_baseline=None,

@@ -302,3 +302,23 @@ def test_lstm_backward_is_the_numeric_gradient(return_sequences):
             arr[i] = old
             num[i] = (lp - lm) / (2 * eps)
         assert rel_err(grad, num) < 1e-7
+
+
+def test_unmodified_reference_fit_matches_the_oracle_trajectory():
+    """oracle/_ref (the reference package copied by oracle/make_ref.sh; what `bench.py --impl reference`
+    times) trained through its own Sequential.fit() on bench.py's synthetic config-3 data gives the
+    oracle's losses to float64 rounding: the port and the real thing are interchangeable as the
+    checker.  Skipped where oracle/_ref has not been built."""
+    import pytest
+    from oracle import ref_driver
+    if not ref_driver.available():
+        pytest.skip('oracle/_ref not built (sh oracle/make_ref.sh)')
+    import bench
+    from oracle import shinnosuke_oracle as O
+    X, Y = bench.synth('cfg3', 24)
+    _, _, losses = ref_driver.fit_throughput('cfg3', X, Y, 8, 0, 3)
+    np.random.seed(0)
+    spec, ishape = O.spec_cfg3()
+    net = O.OracleNet(spec, ishape)
+    net.fit(X.astype(np.float64), Y.astype(np.float64), 8, 1, shuffle=False)
+    assert np.allclose(losses, net.train_loss, rtol=1e-12, atol=0)
