@@ -216,17 +216,23 @@ def kernel_work(name, a, precision):
         return 0.0, 8.0 * N * H * W * C + 5.0 * N * (H // 2) * (W // 2) * C     # x read twice; pooled y + code written
     if name == 'sn_bn_pool_fwd_apply':
         N, H, W, C = a[:4]
-        return 0.0, 4.0 * N * H * W * C + 5.0 * N * (H // 2) * (W // 2) * C     # x read once; pooled y + code written
+        bf16_out = a[-1] if len(a) >= 6 else 0          # + the bf16 copy of the pooled map the next convolution reads
+        return 0.0, 4.0 * N * H * W * C + (5.0 + 2.0 * bf16_out) * N * (H // 2) * (W // 2) * C     # x read once; pooled y + code written
     if name == 'sn_batchnorm_fwd_apply':
         return 0.0, 8.0 * a[0] * a[1]
     if name == 'sn_bn_pool_bwd':
         N, H, W, C = a[:4]
-        # reduce: dy_pool + y_pool; apply: x read, dx written (fp32), dy_pool + code read
-        return 0.0, 8.0 * N * H * W * C + 13.0 * N * (H // 2) * (W // 2) * C
+        # algorithmic: x read once, dx written once (fp32 and / or the bf16 copy the producing convolution's
+        # wgrad / dgrad read: the last two key entries say which), pooled dy, pooled y and the one-byte code
+        # read once (the kernels read dy_pool twice, once per pass: that re-read is NOT algorithmic traffic)
+        f32_out, bf16_out = (a[-2], a[-1]) if len(a) >= 8 else (1, 0)
+        return 0.0, (4.0 + 4.0 * f32_out + 2.0 * bf16_out) * N * H * W * C + 9.0 * N * (H // 2) * (W // 2) * C
     if name == 'sn_sgd_update':
         return 0.0, 16.0 * a[0]
     if name == 'sn_momentum_update':
         return 0.0, 20.0 * a[0]
+    if name == 'sn_adaptive_update':          # (kind, P): w r+w, g r, one (RMSprop, AdaGrad) or two (AdaDelta, Adam) state words r+w
+        return 0.0, (28.0 if a[0] >= 2 else 20.0) * a[1]
     if name == 'sn_cast_f32_to_bf16':
         return 0.0, 6.0 * a[0]
     if name in ('sn_relu_bwd',):
@@ -495,6 +501,97 @@ def run_ours(args):
         os._exit(0)
 
 
+
+# --------------------------------------------------------------- micro roofline sweep
+def run_micro(args):
+    """`bench.py --micro`: the HBM-bound and Dense kernels north_star sets bars for, stand-alone, at sizes
+    far beyond the 126 MB L2 (so the number is HBM, not cache): max-pool forward / backward, the fused
+    optimizer updates, Dense 784 -> 500 at large M.  Each kernel: 3 warm-up launches, then 10 timed ones
+    bracketed by CUDA events on the launching stream; the buffers of consecutive launches rotate through
+    a pool > 2 x L2 where the working set itself is smaller.  Algorithmic bytes / flops = kernel_work().
+    Prints one JSON object; profiles/ holds the committed copy."""
+    import torch
+    torch.cuda.set_device(0)
+    from shinnosuke_b200._lib import lib
+    from shinnosuke_b200.device import current_stream
+    pk = peaks()
+    st = current_stream()
+    rows = []
+
+    def timed(name, a, fn, precision='fp32', reps=10, note=None, tensor_peak=None):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
+            fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        ms = float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]))
+        flops, byt = kernel_work(name, a, precision)
+        tp = tensor_peak or pk['bf16'] / 2
+        row = dict(kernel=name, args=list(a), ms=ms, precision=precision)
+        if flops / (tp * 1e12) > byt / (pk['hbm'] * 1e9):
+            row.update(bound='tensor', achieved=flops / ms / 1e9, peak=tp, unit='TFLOP/s', frac=flops / ms / 1e9 / tp)
+        else:
+            row.update(bound='hbm', achieved=byt / ms / 1e6, peak=pk['hbm'], unit='GB/s', frac=byt / ms / 1e6 / pk['hbm'],
+                       algorithmic_bytes=byt)
+        if note:
+            row['note'] = note
+        rows.append(row)
+        print('%-22s %-34s %8.3f ms  %9.1f %s  = %.2f of %s' % (name, a, ms, row['achieved'], row['unit'], row['frac'], row['bound']),
+              file=sys.stderr, flush=True)
+
+    f32 = dict(dtype=torch.float32, device='cuda')
+    # ---- MaxPooling2D 2x2/2, tie-split codes ('reshape' mode, every BASELINE config) ----
+    for N in (512, 2048):
+        H = W = 32; C = 64
+        x = torch.randn(N * H * W * C, **f32)
+        y = torch.empty(N * (H // 2) * (W // 2) * C, **f32)
+        code = torch.empty(y.numel(), dtype=torch.uint8, device='cuda')
+        dx = torch.empty_like(x)
+        a = (N, H, W, C, 2, 2)
+        timed('sn_maxpool2d_fwd', a, lambda: lib.sn_maxpool2d_fwd(x.data_ptr(), y.data_ptr(), code.data_ptr(), N, H, W, C, 2, 2, 0, st))
+        timed('sn_maxpool2d_bwd', a, lambda: lib.sn_maxpool2d_bwd(y.data_ptr(), code.data_ptr(), dx.data_ptr(), N, H, W, C, 2, 2, 0, 0, st))
+        del x, y, code, dx
+    # ---- optimizers over a 64 M-parameter arena (256 MB per tensor) ----
+    P = 64 * 1024 * 1024
+    w = torch.randn(P, **f32); g = torch.randn(P, **f32) * 1e-3
+    timed('sn_sgd_update', (P,), lambda: lib.sn_sgd_update(w.data_ptr(), g.data_ptr(), P, 0.01, 1.0, st))
+    v = torch.zeros(P, **f32)
+    timed('sn_momentum_update', (P,), lambda: lib.sn_momentum_update(w.data_ptr(), g.data_ptr(), v.data_ptr(), None, P, 0.01, 0.9, 1.0, st))
+    s2 = torch.zeros(P, **f32); tick = torch.zeros(4, **f32)
+    timed('sn_adaptive_update', (0, P), lambda: lib.sn_adaptive_update(0, w.data_ptr(), g.data_ptr(), v.data_ptr(), None, None, None, P, 1e-3, 0.9, 0.0, 1e-7, 1.0, st),
+          note='RMSprop')
+    timed('sn_adaptive_update', (3, P), lambda: lib.sn_adaptive_update(3, w.data_ptr(), g.data_ptr(), v.data_ptr(), s2.data_ptr(), None, tick.data_ptr(), P, 1e-3, 0.9, 0.999, 1e-7, 1.0, st),
+          note='Adam')
+    del w, g, v, s2
+    # ---- Dense 784 -> 500 (config 2's layer) at large M: fprop, dX, dW ----
+    K, Nout = 784, 500
+    for M in (8192, 65536):
+        x = torch.randn(M * K, **f32); wt = torch.randn(Nout * K, **f32) * 0.05; b = torch.zeros(Nout, **f32)
+        y = torch.empty(M * Nout, **f32); dy = torch.randn(M * Nout, **f32); dx = torch.empty(M * K, **f32)
+        dw = torch.zeros(Nout * K, **f32); db = torch.zeros(Nout, **f32)
+        for prec_name, prec in (('tf32', 1), ('bf16', 2)):
+            tp = pk['bf16'] if prec_name == 'bf16' else pk['bf16'] / 2
+            ws_bytes = lib.load().sn_conv2d_dgrad_workspace(K, Nout, 1, 1, prec)
+            ws = torch.empty(max(1, ws_bytes // 4), **f32)
+            a = (M, K, Nout)
+            try:
+                timed('sn_dense_fprop', a, lambda: lib.sn_dense_fprop(x.data_ptr(), wt.data_ptr(), b.data_ptr(), y.data_ptr(), M, K, Nout, 1, prec, st),
+                      precision=prec_name, tensor_peak=tp)
+                timed('sn_dense_dgrad', a, lambda: lib.sn_dense_dgrad(dy.data_ptr(), wt.data_ptr(), dx.data_ptr(), M, K, Nout, 0, prec, ws.data_ptr(), st),
+                      precision=prec_name, tensor_peak=tp)
+                timed('sn_dense_wgrad', a, lambda: lib.sn_dense_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), M, K, Nout, 1, prec, st),
+                      precision=prec_name, tensor_peak=tp)
+            except Exception as e:          # a tier the Dense entry points do not take is reported, not hidden
+                rows.append(dict(kernel='sn_dense_*', args=list(a), precision=prec_name, error=str(e)[:200]))
+        del x, wt, y, dy, dx, dw
+    out = dict(micro=True, peaks=pk, rows=rows)
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -506,13 +603,16 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['fp32', 'tf32x3', 'tf32', 'bf16'])
     ap.add_argument('--kernel-table', default='', help='write the per-kernel CUDA-event table (JSON) here')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--micro', action='store_true', help='stand-alone roofline sweep of the pooling / optimizer / Dense kernels at > L2 sizes')
     ap.add_argument('--sync-bn', action='store_true', help='cross-replica BatchNorm statistics (exact data parallelism; N > 1)')
     args = ap.parse_args()
     wd = int(os.environ.get('SN_BENCH_WATCHDOG', '0'))
     if wd > 0:      # debugging aid: dump every thread's stack and exit if the run takes longer than this
         import faulthandler
         faulthandler.dump_traceback_later(wd, exit=True)
-    if args.impl == 'reference':
+    if args.micro:
+        run_micro(args)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_ours(args)

@@ -94,6 +94,45 @@ SN_API long long sn_igemm_pair_launches(void);
 /* override the choice in-process: 0 never, 1 by shape (default), 2 whenever eligible, -1 re-read SN_IGEMM_PAIR */
 SN_API int sn_igemm_set_pair_mode(int mode);
 
+/* ------------------------------------------------------------ CUDA graphs */
+/* The training step (reference models.py:70-92: forward sweep, loss, backward sweep, update) is ~36
+ * short kernels; it is captured ONCE per batch shape between sn_graph_begin / sn_graph_end on a
+ * stream created by sn_stream_create (every sn_* call on that stream in between is recorded, nothing
+ * runs) and replayed with sn_graph_launch.  Capture is thread-local: other host threads may keep
+ * using the device. */
+SN_API int sn_graph_begin(void *stream);
+SN_API int sn_graph_end(void *stream, void **graph_exec);
+SN_API int sn_graph_launch(void *graph_exec, void *stream);
+SN_API int sn_graph_destroy(void *graph_exec);
+SN_API int sn_stream_wait_event(void *stream, void *event);
+SN_API int sn_device_sync(void);
+
+/* ------------------------------------------------- data-parallel exchange */
+/* models.py fit() sharded over the GPUs of one NVLink / NVSwitch box: every replica
+ * runs forward + backward on its rows of the minibatch; the gradient arena (and the per-channel sums of
+ * every BatchNormalization, layers/Normalization.py:116-128) are summed over the replicas by ONE
+ * hand-written kernel each, over peer-mapped memory (csrc/comm.cu) — no NCCL on the data path.
+ * Results are bit-identical on every rank (fixed summation order).
+ *
+ * A communicator owns a "window" of device memory that every peer maps.  user_bytes of it are the
+ * caller's: a tensor that lives there (the gradient arena) is all-reduced in place, zero-copy.
+ *   one process per GPU : sn_comm_create on each rank, exchange the 64-byte handles of
+ *                         sn_comm_ipc_handle through any host channel, sn_comm_connect(all handles);
+ *   one process, G GPUs : sn_comm_init_all(G, user_bytes, comms[G]) (device r = rank r).
+ * At most 8 ranks.  All ranks must issue the same sequence of sn_allreduce_* calls (same n). */
+SN_API int sn_comm_create(int rank, int world, size_t user_bytes, void **comm);
+SN_API int sn_comm_window(void *comm, void **ptr, size_t *bytes);
+SN_API int sn_comm_ipc_handle(void *comm, void *handle64);
+SN_API int sn_comm_connect(void *comm, const void *handles /* world x 64 bytes, rank order */);
+SN_API int sn_comm_init_all(int ndev, size_t user_bytes, void **comms);
+SN_API int sn_comm_destroy(void *comm);
+/* buf (+)= sum over ranks, in place, asynchronous on `stream` (graph-capturable).  Tensors inside the
+ * window larger than 64 KB: two-shot (pull own slice from every peer, push the sum to every peer);
+ * tensors of at most 256 KB anywhere: one-shot through per-rank staging slots; anything else is
+ * staged through the window. */
+SN_API int sn_allreduce_sum_f32(void *comm, float *buf, long long n, void *stream);
+SN_API int sn_allreduce_sum_f64(void *comm, double *buf, long long n, void *stream);
+
 /* ----------------------------------------------------------------- layout */
 /* API-boundary transposes between the reference's NCHW and the device's NHWC. */
 SN_API int sn_nchw_to_nhwc(const float *src, float *dst, int N, int C, int H, int W, void *stream);
@@ -335,6 +374,10 @@ SN_API int sn_bn_pool_bwd_apply(const float *dy_pool, const uint8_t *code, const
 SN_API int sn_embedding_fwd(const float *w, const float *idx, float *out, long long n_idx, int vocab, int dim, void *stream);
 /* Embedding.backward, :66-76: np.add.at(W.grads, idx, grads) — dw[idx[i]][:] += dy[i][:] */
 SN_API int sn_embedding_bwd(const float *idx, const float *dy, float *dw, long long n_idx, int vocab, int dim, void *stream);
+/* ids follow NumPy's W[idx]: [-vocab, 0) wraps; ids outside [-vocab, vocab) (IndexError in the reference,
+ * layers/Embeddings.py:60) are clamped and COUNTED on the device; this reads (and optionally clears) the count.
+ * Synchronises the device. */
+SN_API int sn_embedding_oob_count(long long *count, int reset);
 /* dst[b][a][:] (=|+=) src[a][b][:] for rows of D floats: batch-major (N,T,D) <-> time-major (T,N,D) */
 SN_API int sn_swap_leading_axes(const float *src, float *dst, int A, int B, int D, int accumulate, void *stream);
 /* One timestep of LSTMCell._forward, layers/Recurrent.py:293-309.  zx[r][0..4H) = x_t . Wx + b (row

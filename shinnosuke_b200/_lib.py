@@ -48,7 +48,11 @@ class KernelProfiler(object):
     """Brackets every compute entry point with CUDA events on the launching stream (the last
     argument of every such call).  bench.py uses it for the per-kernel roofline; off by default."""
     SKIP = ('sn_event_', 'sn_stream_', 'sn_malloc', 'sn_free', 'sn_set_device', 'sn_device_', 'sn_memcpy_h2d',
-            'sn_memcpy_d2h')
+            'sn_memcpy_d2h', 'sn_embedding_oob_count', 'sn_comm_', 'sn_graph_', 'sn_igemm_')
+
+    # optional output pointers that change a call's algorithmic bytes: their presence (1 / 0) is appended
+    # to the integer key, in this order (bench.kernel_work reads them from the end of the tuple)
+    PTR_FLAGS = {'sn_bn_pool_bwd': (8, 9), 'sn_bn_pool_bwd_apply': (3, 4), 'sn_bn_pool_fwd_apply': (2,), 'sn_bn_pool_fwd_train': (4,)}
 
     def __init__(self, dll):
         self.dll = dll
@@ -77,7 +81,9 @@ class KernelProfiler(object):
         ms = ctypes.c_float()
         for name, args, a, b in self.records:
             self.dll.sn_event_elapsed_ms(a, b, ctypes.byref(ms))
-            key = (name, tuple(x for x in args[:-1] if isinstance(x, (int, float)) and not isinstance(x, bool) and abs(x) < (1 << 40)))
+            ints = tuple(x for x in args[:-1] if isinstance(x, (int, float)) and not isinstance(x, bool) and abs(x) < (1 << 40))
+            ints += tuple(1 if args[i] else 0 for i in self.PTR_FLAGS.get(name, ()))
+            key = (name, ints)
             out.setdefault(key, []).append(ms.value)
             self._pool += [a, b]
         self.records = []
@@ -114,6 +120,11 @@ class _Lib(object):
             raise ShinnosukeLibError('libshinnosuke_b200.so ABI version mismatch')
         self._dll = dll
         return dll
+
+    def embedding_oob_count(self, reset=True):
+        n = ctypes.c_longlong(0)
+        self.sn_embedding_oob_count(ctypes.byref(n), 1 if reset else 0)
+        return int(n.value)
 
     def __getattr__(self, name):
         dll = self.load()

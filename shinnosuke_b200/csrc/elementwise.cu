@@ -222,17 +222,6 @@ __global__ void sgd_scalar_kernel(float *__restrict__ w, float *__restrict__ g, 
         w[i] -= lr_scaled * g[i]; g[i] = 0.f;
     }
 }
-__global__ void momentum_kernel(float *__restrict__ w, float *__restrict__ g, float *__restrict__ v,
-                                float *__restrict__ gstep, long long n, float lr, float rho, float scale) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float gi = g[i];
-        if (gstep) { gi += scale * gstep[i]; gstep[i] = 0.f; g[i] = gi; }
-        float vi = rho * v[i] + (1.f - rho) * gi;
-        v[i] = vi;
-        w[i] -= lr * vi;
-    }
-}
-
 extern "C" {
 
 int sn_nchw_to_nhwc(const float *src, float *dst, int N, int C, int H, int W, void *stream) {
@@ -323,11 +312,4 @@ int sn_sgd_update(float *w, float *g, long long n, float lr, float grad_scale, v
         sgd_scalar_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(w, g, n, lr * grad_scale);
     return after_launch("sgd_kernel");
 }
-int sn_momentum_update(float *w, float *g, float *v, float *gstep, long long n, float lr, float rho, float grad_scale, void *stream) {
-    SN_REQUIRE(w && g && v && n >= 0, "bad arguments");
-    if (!n) return SN_OK;
-    momentum_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(w, g, v, gstep, n, lr, rho, grad_scale);
-    return after_launch("momentum_kernel");
-}
-
 }  // extern "C"

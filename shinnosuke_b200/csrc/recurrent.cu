@@ -22,6 +22,21 @@ using namespace sn;
 
 namespace {
 
+// Row lookup with NumPy's index semantics (the reference's W[idx]): ids in [-vocab, 0) wrap to the end
+// of the table; anything else outside [0, vocab) raises IndexError there.  A kernel cannot raise: such an
+// id is counted in g_embedding_oob (read back by sn_embedding_oob_count, which fit() checks at the end
+// of every epoch) and clamped so that the access stays in bounds.
+__device__ unsigned long long g_embedding_oob = 0ull;
+__device__ __forceinline__ int embedding_row(float id, int vocab) {
+    int row = (int)id;
+    if (row < 0) row += vocab;
+    if (row < 0 || row >= vocab) {
+        atomicAdd(&g_embedding_oob, 1ull);
+        row = row < 0 ? 0 : vocab - 1;
+    }
+    return row;
+}
+
 __global__ void __launch_bounds__(256) embedding_fwd_kernel(const float *__restrict__ w, const float *__restrict__ idx,
                                                             float *__restrict__ out, long long n_idx, int vocab, int dim4) {
     // one thread per (index, float4 of the row)
@@ -29,8 +44,7 @@ __global__ void __launch_bounds__(256) embedding_fwd_kernel(const float *__restr
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / dim4;
         const int q = (int)(i - r * dim4);
-        int row = (int)__ldg(idx + r);
-        row = row < 0 ? 0 : (row >= vocab ? vocab - 1 : row);        // NumPy would raise; clamp instead of reading out of bounds
+        const int row = embedding_row(__ldg(idx + r), vocab);
         reinterpret_cast<float4 *>(out)[i] = __ldg(reinterpret_cast<const float4 *>(w) + (long long)row * dim4 + q);
     }
 }
@@ -40,8 +54,7 @@ __global__ void __launch_bounds__(256) embedding_fwd_scalar_kernel(const float *
     const long long total = n_idx * dim;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / dim;
-        int row = (int)__ldg(idx + r);
-        row = row < 0 ? 0 : (row >= vocab ? vocab - 1 : row);
+        const int row = embedding_row(__ldg(idx + r), vocab);
         out[i] = __ldg(w + (long long)row * dim + (i - r * dim));
     }
 }
@@ -51,8 +64,7 @@ __global__ void __launch_bounds__(256) embedding_bwd_kernel(const float *__restr
     const long long total = n_idx * dim;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / dim;
-        int row = (int)__ldg(idx + r);
-        row = row < 0 ? 0 : (row >= vocab ? vocab - 1 : row);
+        const int row = embedding_row(__ldg(idx + r), vocab);
         atomicAdd(dw + (long long)row * dim + (i - r * dim), __ldg(dy + i));
     }
 }
@@ -447,6 +459,14 @@ int sn_embedding_fwd(const float *w, const float *idx, float *out, long long n_i
     return after_launch("embedding_fwd_scalar_kernel");
 }
 
+int sn_embedding_oob_count(long long *count, int reset) {
+    SN_REQUIRE(count, "null out pointer");
+    unsigned long long v = 0ull;
+    SN_CUDA(cudaMemcpyFromSymbol(&v, g_embedding_oob, sizeof(v)));
+    *count = (long long)v;
+    if (reset && v) { v = 0ull; SN_CUDA(cudaMemcpyToSymbol(g_embedding_oob, &v, sizeof(v))); }
+    return SN_OK;
+}
 int sn_embedding_bwd(const float *idx, const float *dy, float *dw, long long n_idx, int vocab, int dim, void *stream) {
     SN_REQUIRE(idx && dy && dw, "null tensor");
     SN_REQUIRE(n_idx >= 0 && vocab > 0 && dim > 0, "bad sizes");

