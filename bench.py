@@ -70,7 +70,7 @@ def synth(cfg, n, seed=1234):
     return X, Y
 
 
-def build_model(cfg, precision, sync_bn=False):
+def build_model(cfg, precision, sync_bn=None):
     from shinnosuke_b200 import (Sequential, Model, Input, Conv2D, BatchNormalization, MaxPooling2D, Flatten, Dense,
                                  Activation, Add)
     np.random.seed(0)
@@ -185,14 +185,18 @@ def kernel_work(name, a, precision):
     Returns (flops, bytes): the bytes are the tensors the operation must read and write once."""
     conv = ('sn_conv2d_fprop', 'sn_conv2d_dgrad', 'sn_conv2d_wgrad', 'sn_conv2d_fprop_bf16', 'sn_conv2d_dgrad_bf16',
             'sn_conv2d_wgrad_bf16', 'sn_conv2d_fprop_stats', 'sn_conv2d_fprop_bf16_stats', 'sn_conv2d_fprop_x3',
-            'sn_conv2d_dgrad_x3', 'sn_conv2d_wgrad_x3')
+            'sn_conv2d_dgrad_x3', 'sn_conv2d_wgrad_x3', 'sn_conv2d_fprop_bf16_stats_ybf16', 'sn_conv2d_fprop_stats_ybf16')
     if name in conv:
         N, C, H, W, F, kh, kw, stride, ph, pw = a[:10]
         oh = (H + 2 * ph - kh) // stride + 1
         ow = (W + 2 * pw - kw) // stride + 1
         x, y, w = N * C * H * W, N * F * oh * ow, F * C * kh * kw
         flops = 2.0 * y * C * kh * kw
-        if 'bf16' in name:
+        if name == 'sn_conv2d_fprop_stats_ybf16':
+            byt = {'fprop': 4 * x + 4 * w + 2 * y}              # the stem: fp32 image and filters in, bf16 map out
+        elif name == 'sn_conv2d_fprop_bf16_stats_ybf16':
+            byt = {'fprop': 2 * x + 2 * w + 2 * y}              # bf16 operand copies in, bf16 map out
+        elif 'bf16' in name:
             # bf16 operand copies in, fp32 result out (fprop: y, dgrad: dx = x-sized, wgrad: dw)
             byt = {'fprop': 2 * x + 2 * w + 4 * y, 'dgrad': 2 * y + 2 * w + 4 * x, 'wgrad': 2 * x + 2 * y + 4 * w}
         else:
@@ -214,19 +218,22 @@ def kernel_work(name, a, precision):
     if name == 'sn_bn_pool_fwd_train':
         N, H, W, C = a[:4]
         return 0.0, 8.0 * N * H * W * C + 5.0 * N * (H // 2) * (W // 2) * C     # x read twice; pooled y + code written
-    if name == 'sn_bn_pool_fwd_apply':
+    if name in ('sn_bn_pool_fwd_apply', 'sn_bn_pool_fwd_apply_xbf16'):
         N, H, W, C = a[:4]
+        xbytes = 2.0 if name.endswith('xbf16') else 4.0
         bf16_out = a[-1] if len(a) >= 6 else 0          # + the bf16 copy of the pooled map the next convolution reads
-        return 0.0, 4.0 * N * H * W * C + (5.0 + 2.0 * bf16_out) * N * (H // 2) * (W // 2) * C     # x read once; pooled y + code written
+        return 0.0, xbytes * N * H * W * C + (5.0 + 2.0 * bf16_out) * N * (H // 2) * (W // 2) * C     # x read once; pooled y + code written
     if name == 'sn_batchnorm_fwd_apply':
         return 0.0, 8.0 * a[0] * a[1]
-    if name == 'sn_bn_pool_bwd':
+    if name in ('sn_bn_pool_bwd', 'sn_bn_pool_bwd_xbf16', 'sn_bn_pool_bwd_apply', 'sn_bn_pool_bwd_apply_xbf16'):
         N, H, W, C = a[:4]
+        xbytes = 2.0 if name.endswith('xbf16') else 4.0
+        pooled = 9.0 if 'apply' not in name else 5.0           # the apply half alone reads pooled dy + code only
         # algorithmic: x read once, dx written once (fp32 and / or the bf16 copy the producing convolution's
         # wgrad / dgrad read: the last two key entries say which), pooled dy, pooled y and the one-byte code
         # read once (the kernels read dy_pool twice, once per pass: that re-read is NOT algorithmic traffic)
         f32_out, bf16_out = (a[-2], a[-1]) if len(a) >= 8 else (1, 0)
-        return 0.0, (4.0 + 4.0 * f32_out + 2.0 * bf16_out) * N * H * W * C + 9.0 * N * (H // 2) * (W // 2) * C
+        return 0.0, (xbytes + 4.0 * f32_out + 2.0 * bf16_out) * N * H * W * C + pooled * N * (H // 2) * (W // 2) * C
     if name == 'sn_sgd_update':
         return 0.0, 16.0 * a[0]
     if name == 'sn_momentum_update':
@@ -276,7 +283,7 @@ def roofline_from_profile(summary, precision, pk):
         flops, byt = kernel_work(name, a, precision)
         # the roof of the kernel that actually ran: bf16 entry points against the bf16 peak, the
         # fp32-pointer tensor kernels (tf32) against half of it (also the reference point of the fp32 tier)
-        tensor_peak = pk['bf16'] if '_bf16' in name else pk['bf16'] / 2
+        tensor_peak = pk['bf16'] if ('_bf16' in name and name != 'sn_conv2d_fprop_stats_ybf16') else pk['bf16'] / 2
         t_tensor, t_hbm = flops / (tensor_peak * 1e12), byt / (pk['hbm'] * 1e9)
         kind = 'flops' if t_tensor > t_hbm else 'bytes'
         rows.append(dict(name=name, args=list(a), ms=ms, launches=len(ms_list), kind=kind, work=flops if kind == 'flops' else byt,
@@ -393,7 +400,7 @@ def run_ours(args):
     K, Wm = args.steps, max(3, args.warmup)
     precision = args.precision
     pk = peaks()
-    m = build_model(cfg, precision, args.sync_bn)
+    m = build_model(cfg, precision, False if args.no_sync_bn else None)
 
     # every rank holds the whole synthetic set, like every rank running the same script would
     X, Y = synth(cfg, G * max(K, Wm, 4))
@@ -483,7 +490,7 @@ def run_ours(args):
                     warmup=Wm, ms_per_step=dev_ms / K, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype=precision, data='synthetic',
                     config=dict(workload=CONFIGS[cfg]['name'], per_gpu_batch=B, global_batch=G, parallelism='dp%d' % world,
-                                precision=precision, sync_bn=bool(args.sync_bn), l2='working set per step exceeds the 126 MB L2 (no flush)' if cfg in ('cfg3', 'cfg4') and B >= 128
+                                precision=precision, sync_bn=bool(world > 1 and not args.no_sync_bn), comm=('nccl' if os.environ.get('SN_COMM') == 'nccl' else 'own NVLink kernels') if world > 1 else None, l2='working set per step exceeds the 126 MB L2 (no flush)' if cfg in ('cfg3', 'cfg4') and B >= 128
                                 else 'small working set, no flush: the step is launch-latency bound',
                                 step_tflops=CONFIGS[cfg]['flops_per_sample'] * G / world / (dev_ms / K * 1e-3) / 1e12),
                     clocks=clocks,
@@ -604,7 +611,8 @@ def main():
     ap.add_argument('--kernel-table', default='', help='write the per-kernel CUDA-event table (JSON) here')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--micro', action='store_true', help='stand-alone roofline sweep of the pooling / optimizer / Dense kernels at > L2 sizes')
-    ap.add_argument('--sync-bn', action='store_true', help='cross-replica BatchNorm statistics (exact data parallelism; N > 1)')
+    ap.add_argument('--sync-bn', action='store_true', help='(default at N > 1) cross-replica BatchNorm statistics: exact data parallelism')
+    ap.add_argument('--no-sync-bn', action='store_true', help='per-replica BatchNorm statistics (a deviation from the reference; A/B only)')
     args = ap.parse_args()
     wd = int(os.environ.get('SN_BENCH_WATCHDOG', '0'))
     if wd > 0:      # debugging aid: dump every thread's stack and exit if the run takes longer than this

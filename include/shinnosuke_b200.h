@@ -132,6 +132,11 @@ SN_API int sn_comm_destroy(void *comm);
  * staged through the window. */
 SN_API int sn_allreduce_sum_f32(void *comm, float *buf, long long n, void *stream);
 SN_API int sn_allreduce_sum_f64(void *comm, double *buf, long long n, void *stream);
+/* The data-parallel tail of a training step in ONE kernel: g[0, n) = sum over ranks (as above, g inside the
+ * window), then w[i] -= lr * g[i]; g[i] = 0 for i < n_params (StochasticGradientDescent.update,
+ * utils/Optimizers.py:29-32) applied by each CTA to the elements whose sums it has just seen arrive.  The
+ * words g[n_params, n) (the step's loss / accuracy sums) are reduced and left in place. */
+SN_API int sn_allreduce_sgd_update(void *comm, float *g, float *w, long long n, long long n_params, float lr, void *stream);
 
 /* ----------------------------------------------------------------- layout */
 /* API-boundary transposes between the reference's NCHW and the device's NHWC. */
@@ -235,6 +240,18 @@ SN_API int sn_conv2d_fprop_bf16_stats(const void *x_bf16, const void *w_bf16, co
                                int N, int C, int H, int W, int F, int kh, int kw,
                                int stride, int pad_h, int pad_w, int act, double *bn_scratch, void *stream);
 /* wt_bf16: filters flipped and transposed by sn_flip_transpose_filters_bf16 */
+/* bf16 tier, a convolution whose only consumer is a fused BatchNormalization (+ 2x2 pool): the output map
+ * itself is stored in bf16 (NHWC, written once and read twice: half the bytes three times) and its
+ * per-channel sums — of the values as stored — are added to bn_scratch like sn_conv2d_fprop_stats does.
+ * bf16_operands = 1: x and w are bf16 copies (sn_conv2d_fprop_bf16's kernels); 0: the tiny-C stem kernel
+ * on the fp32 image and filters (TF32 products).  F % 8 == 0, 32 < F <= 512. */
+SN_API int sn_conv2d_fprop_ybf16_supported(int bf16_operands, int N, int C, int H, int W, int F, int kh, int kw, int stride, int pad_h, int pad_w);
+SN_API int sn_conv2d_fprop_bf16_stats_ybf16(const void *x_bf16, const void *w_bf16, const float *bias, void *y_bf16,
+                                     int N, int C, int H, int W, int F, int kh, int kw,
+                                     int stride, int pad_h, int pad_w, int act, double *bn_scratch, void *stream);
+SN_API int sn_conv2d_fprop_stats_ybf16(const float *x, const float *w, const float *bias, void *y_bf16,
+                                int N, int C, int H, int W, int F, int kh, int kw,
+                                int stride, int pad_h, int pad_w, int act, double *bn_scratch, void *stream);
 SN_API int sn_conv2d_dgrad_bf16(const void *dy_bf16, const void *wt_bf16, float *dx,
                          int N, int C, int H, int W, int F, int kh, int kw,
                          int stride, int pad_h, int pad_w, int accumulate, void *stream);
@@ -358,6 +375,16 @@ SN_API int sn_batchnorm_bwd_local(const float *dy, const float *x, const float *
                            float *dgamma, float *dbeta, double *scratch, long long rows, int C, void *stream);
 SN_API int sn_batchnorm_finalize_bwd(const float *gamma, const float *save_mean, const float *save_invstd,
                               double *scratch, long long rows, int C, void *stream);
+/* Data-parallel finalize (exact BatchNormalization over the WHOLE minibatch, layers/Normalization.py:116-128,
+ * with the minibatch sharded over the replicas of `comm`): ONE kernel folds the local sums in scratch,
+ * exchanges them with every replica over peer-mapped memory, adds them in rank order and finalises with
+ * the global row count — instead of sn_allreduce_sum_f64 + sn_batchnorm_finalize_*.  Same scratch
+ * contract as the local versions.  All replicas must call it in the same order. */
+SN_API int sn_batchnorm_finalize_stats_dp(void *comm, const float *gamma, const float *beta, float *save_mean, float *save_invstd,
+                                   float *moving_mean, float *moving_var, double *scratch, long long rows_global, int C,
+                                   float eps, float momentum, void *stream);
+SN_API int sn_batchnorm_finalize_bwd_dp(void *comm, const float *gamma, const float *save_mean, const float *save_invstd,
+                                 double *scratch, long long rows_global, int C, void *stream);
 SN_API int sn_batchnorm_bwd_apply(const float *dy, const float *x, float *dx, const double *scratch,
                            long long rows, int C, int accumulate_dx, int mask_relu, void *stream);
 SN_API int sn_bn_pool_bwd_local(const float *dy_pool, const uint8_t *code, const float *x, const float *y_pool,
@@ -367,6 +394,19 @@ SN_API int sn_bn_pool_bwd_local(const float *dy_pool, const uint8_t *code, const
 SN_API int sn_bn_pool_bwd_apply(const float *dy_pool, const uint8_t *code, const float *x, float *dx, void *dx_bf16,
                          float *dx_colsum, double *scratch, int N, int H, int W, int C,
                          int pool_mode, int mask_relu, void *stream);
+/* the same kernels reading the full-resolution map x as bf16 (the *_ybf16 convolution outputs above);
+ * everything else — pooled tensors, gradients, constants — stays fp32, a blocked ReLU element is -0.0 */
+SN_API int sn_bn_pool_fwd_apply_xbf16(const void *x_bf16, float *y_pool, void *y_pool_bf16, uint8_t *code, const double *scratch,
+                               int N, int H, int W, int C, int pool_mode, void *stream);
+SN_API int sn_bn_pool_bwd_xbf16(const float *dy_pool, const uint8_t *code, const void *x_bf16, const float *y_pool, const float *gamma,
+                         const float *beta, const float *save_mean, const float *save_invstd, float *dx, void *dx_bf16,
+                         float *dx_colsum, float *dgamma, float *dbeta, double *scratch, int N, int H, int W, int C,
+                         int pool_mode, int mask_relu, void *stream);
+SN_API int sn_bn_pool_bwd_local_xbf16(const float *dy_pool, const uint8_t *code, const void *x_bf16, const float *y_pool,
+                               const float *gamma, const float *beta, const float *save_mean, const float *save_invstd,
+                               float *dgamma, float *dbeta, double *scratch, int N, int H, int W, int C, int pool_mode, void *stream);
+SN_API int sn_bn_pool_bwd_apply_xbf16(const float *dy_pool, const uint8_t *code, const void *x_bf16, float *dx, void *dx_bf16,
+                               float *dx_colsum, double *scratch, int N, int H, int W, int C, int pool_mode, int mask_relu, void *stream);
 
 /* ------------------------------------------------------ Embedding / LSTM */
 /* Embedding.forward, layers/Embeddings.py:56-63: out[i][:] = W[idx[i]][:].  Indices arrive as fp32

@@ -52,7 +52,8 @@ class KernelProfiler(object):
 
     # optional output pointers that change a call's algorithmic bytes: their presence (1 / 0) is appended
     # to the integer key, in this order (bench.kernel_work reads them from the end of the tuple)
-    PTR_FLAGS = {'sn_bn_pool_bwd': (8, 9), 'sn_bn_pool_bwd_apply': (3, 4), 'sn_bn_pool_fwd_apply': (2,), 'sn_bn_pool_fwd_train': (4,)}
+    PTR_FLAGS = {'sn_bn_pool_bwd': (8, 9), 'sn_bn_pool_bwd_apply': (3, 4), 'sn_bn_pool_fwd_apply': (2,), 'sn_bn_pool_fwd_train': (4,),
+                 'sn_bn_pool_bwd_xbf16': (8, 9), 'sn_bn_pool_bwd_apply_xbf16': (3, 4), 'sn_bn_pool_fwd_apply_xbf16': (2,)}
 
     def __init__(self, dll):
         self.dll = dll

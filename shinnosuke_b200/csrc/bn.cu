@@ -4,6 +4,7 @@
 // memory-bound reduction) so the 1e-5 tier holds even when |mean| >> std.
 #include "common.cuh"
 #include "bn_common.cuh"
+#include "comm_dev.cuh"
 #include <stdlib.h>
 using namespace sn;
 
@@ -309,6 +310,42 @@ __global__ void bn_finalize_kernel(double *scratch, BnFinal fin) {
     bn_finalize_channels(scratch, fin, (int)(blockIdx.x * blockDim.x + threadIdx.x), (int)(gridDim.x * blockDim.x));
 }
 
+// Data-parallel finalize: the cross-replica sum of the statistics happens INSIDE this kernel, over
+// peer-mapped memory: each thread folds the local slots of its channel and stores its {sum_a, sum_b}
+// pair into this rank's slot in EVERY replica's window as four 8-byte "LL" words {32 data bits, sequence
+// number} (csrc/comm_dev.cuh); it then polls the G slots of its own window until each word carries this
+// exchange's sequence number, adds them in rank order (bit-identical on every replica) and finalises with
+// the GLOBAL row count.  No flag, no fence, no barrier: the exchange costs one one-way NVLink latency.
+// One launch instead of all-reduce + finalize, 32 bytes per channel and peer on the wire.
+// Slots are double-buffered by the parity of the sequence number (a replica can be at most one exchange
+// ahead of the slowest one, because finishing exchange k needs every replica's words of exchange k).
+__global__ void __launch_bounds__(32) bn_finalize_dp_kernel(comm::DevComm dc, double *scratch, BnFinal fin) {
+    using namespace sn::comm;
+    pdl_wait();
+    const unsigned seq = *reinterpret_cast<volatile unsigned *>(&dc.state[0]) + 1u;     // device state: written only by exchange kernels of this window
+    const int C = fin.C, c = blockIdx.x * 32 + threadIdx.x;
+    const size_t slot0 = dc.ll_off + (size_t)(seq & 1u) * MAX_RANKS * LL_SLOT_BYTES;
+    if (c < C) {
+        const BnChannelIn in = bn_channel_inputs(fin, c);
+        double a, b;
+        bn_fold_slots(scratch, C, c, a, b);
+#pragma unroll
+        for (int p = 0; p < MAX_RANKS; ++p)
+            if (p < dc.world) ll_store_f64x2(dc.t.win[p] + slot0 + (size_t)dc.rank * LL_SLOT_BYTES + (size_t)c * 32, a, b, seq);
+        const char *mine = dc.t.win[dc.rank] + slot0 + (size_t)c * 32;
+        double sa = 0.0, sb = 0.0;
+#pragma unroll
+        for (int p = 0; p < MAX_RANKS; ++p)
+            if (p < dc.world) {
+                double va, vb;
+                ll_load_f64x2(mine + (size_t)p * LL_SLOT_BYTES, va, vb, seq);
+                if (p == 0) { sa = va; sb = vb; } else { sa += va; sb += vb; }
+            }
+        bn_finalize_one(bn_params(scratch, C), fin, in, c, sa, sb, bn_inv_rows(fin.rows));
+    }
+    finish_exchange(dc.state, seq);
+}
+
 static bool bn_pow2(int C) {
     if (C & 3) return false;
     int q = C >> 2;
@@ -362,6 +399,31 @@ int sn_batchnorm_finalize_stats(const float *gamma, const float *beta, float *sa
     fin.save_invstd = save_invstd; fin.moving_mean = moving_mean; fin.moving_var = moving_var; fin.eps = eps; fin.momentum = momentum;
     SN_CUDA(launch_dependent(bn_finalize_kernel, dim3((C + 31) / 32), dim3(32), 0, as_stream(stream), scratch, fin));     // one warp per SM
     return after_launch("bn_finalize_kernel");
+}
+
+int sn_batchnorm_finalize_stats_dp(void *comm_handle, const float *gamma, const float *beta, float *save_mean, float *save_invstd,
+                                   float *moving_mean, float *moving_var, double *scratch, long long rows_global, int C, float eps,
+                                   float momentum, void *stream) {
+    SN_REQUIRE(comm_handle && gamma && beta && save_mean && save_invstd && moving_mean && moving_var && scratch, "null argument");
+    SN_REQUIRE(rows_global > 0 && bn_pow2(C), "needs C = 4*2^k <= 1024");
+    const comm::Comm *cm = static_cast<const comm::Comm *>(comm_handle);
+    SN_REQUIRE(cm->connected, "the communicator is not connected");
+    BnFinal fin{};
+    fin.bwd = 0; fin.rows = rows_global; fin.C = C; fin.x = nullptr; fin.gamma = gamma; fin.beta = beta; fin.save_mean = save_mean;
+    fin.save_invstd = save_invstd; fin.moving_mean = moving_mean; fin.moving_var = moving_var; fin.eps = eps; fin.momentum = momentum;
+    SN_CUDA(launch_dependent(bn_finalize_dp_kernel, dim3((C + 31) / 32), dim3(32), 0, as_stream(stream), comm::dev_comm(cm), scratch, fin));
+    return after_launch("bn_finalize_dp_kernel");
+}
+
+int sn_batchnorm_finalize_bwd_dp(void *comm_handle, const float *gamma, const float *save_mean, const float *save_invstd,
+                                 double *scratch, long long rows_global, int C, void *stream) {
+    SN_REQUIRE(comm_handle && gamma && save_mean && save_invstd && scratch && rows_global > 0 && bn_pow2(C), "bad arguments");
+    const comm::Comm *cm = static_cast<const comm::Comm *>(comm_handle);
+    SN_REQUIRE(cm->connected, "the communicator is not connected");
+    BnFinal fin{};
+    fin.bwd = 1; fin.rows = rows_global; fin.C = C; fin.gamma = gamma; fin.mean = save_mean; fin.invstd = save_invstd;
+    SN_CUDA(launch_dependent(bn_finalize_dp_kernel, dim3((C + 31) / 32), dim3(32), 0, as_stream(stream), comm::dev_comm(cm), scratch, fin));
+    return after_launch("bn_finalize_dp_kernel");
 }
 
 int sn_batchnorm_fwd_apply(const float *x, float *y, const double *scratch, long long rows, int C, int relu, void *stream) {

@@ -47,74 +47,100 @@ __device__ __forceinline__ const float *bn_params(const double *scratch, int C) 
 // (first, stride): which channels this thread takes — one block's threads by default; the stand-alone
 // finalize kernel spreads single warps over many SMs instead (FP64 issue is the cost: ~40 double
 // operations per channel at this part's 1/64 FP64 rate kept one SM busy for ~5 us at C = 256).
+__device__ __forceinline__ double bn_inv_rows(long long rows) {
+    // No float64 divide / sqrt (each is a long dependent chain on this part's few FP64 units, and this
+    // code is the serial tail of a kernel): 1/rows comes from a float seed refined by two Newton steps,
+    // 1/sqrt from rsqrtf refined by two — both exact to float64 rounding.
+    const double r = (double)rows;
+    double y = (double)(1.0f / (float)rows);
+    y = y * (2.0 - r * y);
+    return y * (2.0 - r * y);
+}
+
+// everything a channel's finalize step reads besides the sums, loaded up front (see the note on batched loads below)
+struct BnChannelIn {
+    float gamma, beta, pivot, mm, mv, is, mu, db, dg;
+};
+__device__ __forceinline__ BnChannelIn bn_channel_inputs(const BnFinal &f, int c) {
+    BnChannelIn in;
+    in.gamma = f.gamma ? f.gamma[c] : 0.f;
+    in.beta = (!f.bwd && f.beta) ? f.beta[c] : 0.f;
+    in.pivot = (!f.bwd && f.x) ? f.x[c] : 0.f;
+    in.mm = (!f.bwd && f.moving_mean) ? f.moving_mean[c] : 0.f;
+    in.mv = (!f.bwd && f.moving_var) ? f.moving_var[c] : 0.f;
+    in.is = (f.bwd && f.invstd) ? f.invstd[c] : 0.f;
+    in.mu = (f.bwd && f.mean) ? f.mean[c] : 0.f;
+    in.db = (f.bwd && f.dbeta) ? f.dbeta[c] : 0.f;
+    in.dg = (f.bwd && f.dgamma) ? f.dgamma[c] : 0.f;
+    return in;
+}
+
+// sums (a, b) of channel c over the whole (global) batch -> apply-pass constants and saved statistics
+__device__ __forceinline__ void bn_finalize_one(float *prm, const BnFinal &f, const BnChannelIn &in, int c, double a, double b,
+                                                double inv_rows) {
+    const int C = f.C;
+    if (!f.bwd) {
+        const double pivot = (double)in.pivot;
+        const double m1 = a * inv_rows;                             // E[x - pivot]
+        double var = b * inv_rows - m1 * m1;
+        if (var < 0) var = 0;
+        const double m = pivot + m1;
+        const double ve = var + (double)f.eps;
+        double is = (double)rsqrtf((float)ve);
+        is = is * (1.5 - 0.5 * ve * is * is);
+        is = is * (1.5 - 0.5 * ve * is * is);
+        const double g = (double)in.gamma;
+        prm[c] = (float)(g * is);
+        prm[C + c] = (float)((double)in.beta - g * is * m);
+        f.save_mean[c] = (float)m;
+        f.save_invstd[c] = (float)is;
+        f.moving_mean[c] = f.momentum * in.mm + (1.f - f.momentum) * (float)m;
+        f.moving_var[c] = f.momentum * in.mv + (1.f - f.momentum) * (float)var;
+    } else {
+        const double is = (double)in.is, mu = (double)in.mu;
+        const double k2 = a * inv_rows, k3 = b * inv_rows;
+        const double p0 = (double)in.gamma * is;
+        const double p1 = -p0 * k3 * is;
+        prm[c] = (float)p0;
+        prm[C + c] = (float)p1;
+        prm[2 * C + c] = (float)(-p0 * k2 - p1 * mu);
+        if (f.dbeta) f.dbeta[c] = in.db + (float)a;
+        if (f.dgamma) f.dgamma[c] = in.dg + (float)b;
+    }
+}
+
+// the BN_SLOTS partial sums of channel c -> (a, b); leaves the slots zero again, so that a producer
+// that only ADDS into the scratch (the convolution epilogues, sn_conv2d_fprop_stats) needs no memset
+__device__ __forceinline__ void bn_fold_slots(double *scratch, int C, int c, double &a, double &b) {
+    // ALL loads first, in one batch: this is the serial tail of a kernel (or a one-block kernel), and a
+    // load placed after a store to `scratch` cannot be hoisted above it by the compiler — 16 dependent
+    // L2 round trips cost 5-6 us per launch when the zeroing stores were interleaved with the loads
+    double va[BN_SLOTS], vb[BN_SLOTS];
+#pragma unroll
+    for (int s = 0; s < BN_SLOTS; ++s) {
+        va[s] = __ldcg(scratch + (size_t)s * 2 * C + c);
+        vb[s] = __ldcg(scratch + (size_t)s * 2 * C + C + c);
+    }
+    a = 0; b = 0;
+#pragma unroll
+    for (int s = 0; s < BN_SLOTS; ++s) { a += va[s]; b += vb[s]; }
+#pragma unroll
+    for (int s = 0; s < BN_SLOTS; ++s) {
+        scratch[(size_t)s * 2 * C + c] = 0.0;
+        scratch[(size_t)s * 2 * C + C + c] = 0.0;
+    }
+}
+
 __device__ __forceinline__ void bn_finalize_channels(double *scratch, const BnFinal &f, int first = -1, int stride = 0) {
     if (first < 0) { first = threadIdx.x; stride = blockDim.x; }
     const int C = f.C;
     float *prm = bn_params(scratch, C);
-    // No float64 divide / sqrt below (each is a long dependent chain on this part's few FP64 units,
-    // and this code is the serial tail of a kernel): 1/rows comes from a float seed refined by two
-    // Newton steps, 1/sqrt from rsqrtf refined by two — both exact to float64 rounding.
-    double inv_rows;
-    {
-        const double r = (double)f.rows;
-        double y = (double)(1.0f / (float)f.rows);
-        y = y * (2.0 - r * y);
-        inv_rows = y * (2.0 - r * y);
-    }
+    const double inv_rows = bn_inv_rows(f.rows);
     for (int c = first; c < C; c += stride) {
-        // ALL loads first, in one batch: this is the serial tail of a kernel (or a one-block kernel), and a
-        // load placed after a store to `scratch` cannot be hoisted above it by the compiler — 16 dependent
-        // L2 round trips cost 5-6 us per launch when the zeroing stores were interleaved with the loads
-        double va[BN_SLOTS], vb[BN_SLOTS];
-#pragma unroll
-        for (int s = 0; s < BN_SLOTS; ++s) {
-            va[s] = __ldcg(scratch + (size_t)s * 2 * C + c);
-            vb[s] = __ldcg(scratch + (size_t)s * 2 * C + C + c);
-        }
-        const float gamma_c = f.gamma ? f.gamma[c] : 0.f;
-        const float beta_c = (!f.bwd && f.beta) ? f.beta[c] : 0.f;
-        const float pivot_c = (!f.bwd && f.x) ? f.x[c] : 0.f;
-        const float mm_c = (!f.bwd && f.moving_mean) ? f.moving_mean[c] : 0.f, mv_c = (!f.bwd && f.moving_var) ? f.moving_var[c] : 0.f;
-        const float is_c = (f.bwd && f.invstd) ? f.invstd[c] : 0.f, mu_c = (f.bwd && f.mean) ? f.mean[c] : 0.f;
-        const float db_c = (f.bwd && f.dbeta) ? f.dbeta[c] : 0.f, dg_c = (f.bwd && f.dgamma) ? f.dgamma[c] : 0.f;
-        double a = 0, b = 0;
-#pragma unroll
-        for (int s = 0; s < BN_SLOTS; ++s) { a += va[s]; b += vb[s]; }
-        // consumed: leave the sums zero again, so that a producer that only ADDS into the scratch
-        // (the convolution epilogues, sn_conv2d_fprop_stats) needs no memset before it
-#pragma unroll
-        for (int s = 0; s < BN_SLOTS; ++s) {
-            scratch[(size_t)s * 2 * C + c] = 0.0;
-            scratch[(size_t)s * 2 * C + C + c] = 0.0;
-        }
-        if (!f.bwd) {
-            const double pivot = (double)pivot_c;
-            const double m1 = a * inv_rows;                             // E[x - pivot]
-            double var = b * inv_rows - m1 * m1;
-            if (var < 0) var = 0;
-            const double m = pivot + m1;
-            const double ve = var + (double)f.eps;
-            double is = (double)rsqrtf((float)ve);
-            is = is * (1.5 - 0.5 * ve * is * is);
-            is = is * (1.5 - 0.5 * ve * is * is);
-            const double g = (double)gamma_c;
-            prm[c] = (float)(g * is);
-            prm[C + c] = (float)((double)beta_c - g * is * m);
-            f.save_mean[c] = (float)m;
-            f.save_invstd[c] = (float)is;
-            f.moving_mean[c] = f.momentum * mm_c + (1.f - f.momentum) * (float)m;
-            f.moving_var[c] = f.momentum * mv_c + (1.f - f.momentum) * (float)var;
-        } else {
-            const double is = (double)is_c, mu = (double)mu_c;
-            const double k2 = a * inv_rows, k3 = b * inv_rows;
-            const double p0 = (double)gamma_c * is;
-            const double p1 = -p0 * k3 * is;
-            prm[c] = (float)p0;
-            prm[C + c] = (float)p1;
-            prm[2 * C + c] = (float)(-p0 * k2 - p1 * mu);
-            if (f.dbeta) f.dbeta[c] = db_c + (float)a;
-            if (f.dgamma) f.dgamma[c] = dg_c + (float)b;
-        }
+        const BnChannelIn in = bn_channel_inputs(f, c);
+        double a, b;
+        bn_fold_slots(scratch, C, c, a, b);
+        bn_finalize_one(prm, f, in, c, a, b, inv_rows);
     }
 }
 

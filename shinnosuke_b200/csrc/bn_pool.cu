@@ -24,15 +24,26 @@ __device__ __forceinline__ void setc(float4 &v, int k, float x) { if (k == 0) v.
 
 // window index space: idx = ((n*oh + i)*ow + j)*Q + cq, Q = C/4.  256 % Q == 0 and the grid stride
 // is a multiple of 256, so a thread always works on the same channel quad.
-struct Win { const float *p00; long long rowstride; };
-__device__ __forceinline__ Win window(const float *x, long long idx, int Q, int ow, int oh, int W, int C) {
+// XT: element type of the full-resolution map x — float, or __nv_bfloat16 in the bf16 tier, where the
+// producing convolution stores its output map in bf16 (half the bytes of the three passes over it: the
+// conv's write, the forward read here, the backward read here).  All arithmetic stays fp32; a blocked
+// ReLU element is -0.0 in either type.
+template <typename XT> struct WinT { const XT *p00; long long rowstride; };
+__device__ __forceinline__ float4 ldx4(const float *p) { return ldg4(p); }
+__device__ __forceinline__ float4 ldx4(const __nv_bfloat16 *p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2 *>(p));
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+}
+template <typename XT>
+__device__ __forceinline__ WinT<XT> window(const XT *x, long long idx, int Q, int ow, int oh, int W, int C) {
     const int cq = (int)(idx % Q);
     long long pix = idx / Q;
     const int j = (int)(pix % ow);
     long long t = pix / ow;
     const int i = (int)(t % oh);
     const long long n = t / oh;
-    Win w;
+    WinT<XT> w;
     w.rowstride = (long long)W * C;
     w.p00 = x + ((n * 2 * oh + 2 * i) * W + 2 * j) * C + cq * 4;      // H == 2*oh
     return w;
@@ -45,8 +56,8 @@ __device__ __forceinline__ void store_bf16x4(__nv_bfloat16 *dst, const float4 &v
     *reinterpret_cast<uint2 *>(dst) = u;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256) bn_pool_fwd_kernel(const float *__restrict__ x, float *__restrict__ y,
+template <int MODE, typename XT>
+__global__ void __launch_bounds__(256) bn_pool_fwd_kernel(const XT *__restrict__ x, float *__restrict__ y,
                                                           __nv_bfloat16 *__restrict__ y_bf16,
                                                           uint32_t *__restrict__ code, const double *__restrict__ scratch,
                                                           long long windows4, int C, int W, int oh, int ow) {
@@ -58,9 +69,9 @@ __global__ void __launch_bounds__(256) bn_pool_fwd_kernel(const float *__restric
     const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
     const long long stride = (long long)gridDim.x * 256;
     for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < windows4; idx += stride) {
-        const Win w = window(x, idx, Q, ow, oh, W, C);
+        const WinT<XT> w = window(x, idx, Q, ow, oh, W, C);
         float4 v[4];
-        v[0] = ldg4(w.p00); v[1] = ldg4(w.p00 + C); v[2] = ldg4(w.p00 + w.rowstride); v[3] = ldg4(w.p00 + w.rowstride + C);
+        v[0] = ldx4(w.p00); v[1] = ldx4(w.p00 + C); v[2] = ldx4(w.p00 + w.rowstride); v[3] = ldx4(w.p00 + w.rowstride + C);
         float4 out;
         uint32_t packed = 0;
 #pragma unroll
@@ -92,9 +103,9 @@ __device__ __forceinline__ float routed(float g, uint32_t cd, int e) {
     return cnt > 1 ? g / (float)cnt : g;
 }
 
-template <int MODE>
+template <int MODE, typename XT>
 __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(const float *__restrict__ dyp, const uint32_t *__restrict__ code,
-                                                                 const float *__restrict__ x, const float *__restrict__ mean,
+                                                                 const XT *__restrict__ x, const float *__restrict__ mean,
                                                                  const float *__restrict__ invstd, double *__restrict__ scratch,
                                                                  long long windows4, int C, int W, int oh, int ow, BnFinal fin) {
     const int Q = C >> 2;
@@ -111,11 +122,11 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(const float *__
         float fa[4] = {0, 0, 0, 0}, fb[4] = {0, 0, 0, 0};
 #pragma unroll 1
         for (int it = 0; it < 16 && idx < windows4; ++it, idx += stride) {
-            const Win w = window(x, idx, Q, ow, oh, W, C);
+            const WinT<XT> w = window(x, idx, Q, ow, oh, W, C);
             const float4 g = ldg4(dyp + idx * 4);
             const uint32_t packed = __ldg(code + idx);
             float4 v[4];
-            v[0] = ldg4(w.p00); v[1] = ldg4(w.p00 + C); v[2] = ldg4(w.p00 + w.rowstride); v[3] = ldg4(w.p00 + w.rowstride + C);
+            v[0] = ldx4(w.p00); v[1] = ldx4(w.p00 + C); v[2] = ldx4(w.p00 + w.rowstride); v[3] = ldx4(w.p00 + w.rowstride + C);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t cd = (packed >> (8 * k)) & 0xffu;
@@ -154,9 +165,9 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(const float *__
 // with no look at the full-resolution map (4x the bytes of P) or at the codes.  Channels whose gamma
 // is too small for that division to be accurate (|gamma| < max(1,|beta|)/16, including gamma == 0)
 // take the window route above, per thread.
-template <int MODE>
+template <int MODE, typename XT>
 __global__ void __launch_bounds__(256, 3) bn_pool_bwd_reduce_pooled_kernel(const float *__restrict__ dyp, const float *__restrict__ yp,
-                                                                        const uint32_t *__restrict__ code, const float *__restrict__ x,
+                                                                        const uint32_t *__restrict__ code, const XT *__restrict__ x,
                                                                         const float *__restrict__ gamma, const float *__restrict__ beta,
                                                                         const float *__restrict__ mean, const float *__restrict__ invstd,
                                                                         double *__restrict__ scratch, long long windows4, int C, int W,
@@ -214,11 +225,11 @@ __global__ void __launch_bounds__(256, 3) bn_pool_bwd_reduce_pooled_kernel(const
         } else {
 #pragma unroll 1
             for (int it = 0; it < 16 && idx < windows4; ++it, idx += stride) {
-                const Win w = window(x, idx, Q, ow, oh, W, C);
+                const WinT<XT> w = window(x, idx, Q, ow, oh, W, C);
                 const float4 g = ldg4(dyp + idx * 4), mu4 = ldg4(mean + cq * 4), is4 = ldg4(invstd + cq * 4);
                 const uint32_t packed = __ldg(code + idx);
                 float4 v[4];
-                v[0] = ldg4(w.p00); v[1] = ldg4(w.p00 + C); v[2] = ldg4(w.p00 + w.rowstride); v[3] = ldg4(w.p00 + w.rowstride + C);
+                v[0] = ldx4(w.p00); v[1] = ldx4(w.p00 + C); v[2] = ldx4(w.p00 + w.rowstride); v[3] = ldx4(w.p00 + w.rowstride + C);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint32_t cd = (packed >> (8 * k)) & 0xffu;
@@ -249,9 +260,9 @@ __global__ void __launch_bounds__(256, 3) bn_pool_bwd_reduce_pooled_kernel(const
     bn_finalize_last_block(scratch, fin);
 }
 
-template <int MODE, bool MASK>
+template <int MODE, bool MASK, typename XT>
 __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__restrict__ dyp, const uint32_t *__restrict__ code,
-                                                                const float *__restrict__ x, float *__restrict__ dx,
+                                                                const XT *__restrict__ x, float *__restrict__ dx,
                                                                 __nv_bfloat16 *__restrict__ dx_bf16, float *__restrict__ colsum,
                                                                 double *__restrict__ scratch, long long windows4, int C,
                                                                 int W, int oh, int ow) {
@@ -264,11 +275,11 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__r
     float cs[4] = {0.f, 0.f, 0.f, 0.f};                  // this thread's share of sum_rows dx[., c] (the producer's bias gradient)
     const long long stride = (long long)gridDim.x * 256;
     for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < windows4; idx += stride) {
-        const Win w = window(x, idx, Q, ow, oh, W, C);
+        const WinT<XT> w = window(x, idx, Q, ow, oh, W, C);
         const float4 g = ldg4(dyp + idx * 4);
         const uint32_t packed = __ldg(code + idx);
         float4 v[4], o[4];
-        v[0] = ldg4(w.p00); v[1] = ldg4(w.p00 + C); v[2] = ldg4(w.p00 + w.rowstride); v[3] = ldg4(w.p00 + w.rowstride + C);
+        v[0] = ldx4(w.p00); v[1] = ldx4(w.p00 + C); v[2] = ldx4(w.p00 + w.rowstride); v[3] = ldx4(w.p00 + w.rowstride + C);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t cd = (packed >> (8 * k)) & 0xffu;
@@ -368,8 +379,8 @@ int sn_bn_pool_fwd_train(const float *x, const float *gamma, const float *beta, 
     return sn_bn_pool_fwd_apply(x, y_pool, y_pool_bf16, code, scratch, N, H, W, C, pool_mode, stream);
 }
 
-int sn_bn_pool_fwd_apply(const float *x, float *y_pool, void *y_pool_bf16, uint8_t *code, const double *scratch, int N, int H,
-                         int W, int C, int pool_mode, void *stream) {
+static int bn_pool_fwd_apply_impl(const void *x, bool xbf16, float *y_pool, void *y_pool_bf16, uint8_t *code, const double *scratch, int N,
+                                  int H, int W, int C, int pool_mode, void *stream) {
     SN_REQUIRE(x && y_pool && code && scratch, "null tensor");
     SN_REQUIRE(shape_ok(N, H, W, C), "unsupported shape (needs even H, W and C = 4*2^k <= 1024)");
     SN_REQUIRE(pool_mode == SN_POOL_TIE_SPLIT || pool_mode == SN_POOL_FIRST_ARGMAX, "unknown pool mode");
@@ -379,15 +390,24 @@ int sn_bn_pool_fwd_apply(const float *x, float *y_pool, void *y_pool_bf16, uint8
     const int oh = H / 2, ow = W / 2;
     const long long windows4 = (long long)N * oh * ow * (C / 4);
     const int grid = grid_for_windows(windows4);
-    if (pool_mode == SN_POOL_TIE_SPLIT)
-        SN_CUDA(launch_dependent(bn_pool_fwd_kernel<SN_POOL_TIE_SPLIT>, dim3(grid), dim3(256), 0, st, x, y_pool, (__nv_bfloat16 *)y_pool_bf16, (uint32_t *)code, scratch, windows4, C, W, oh, ow));
-    else
-        SN_CUDA(launch_dependent(bn_pool_fwd_kernel<SN_POOL_FIRST_ARGMAX>, dim3(grid), dim3(256), 0, st, x, y_pool, (__nv_bfloat16 *)y_pool_bf16, (uint32_t *)code, scratch, windows4, C, W, oh, ow));
+#define SN_FWD(M, XT) SN_CUDA(launch_dependent(bn_pool_fwd_kernel<M, XT>, dim3(grid), dim3(256), 0, st, (const XT *)x, y_pool, (__nv_bfloat16 *)y_pool_bf16, (uint32_t *)code, scratch, windows4, C, W, oh, ow))
+    if (pool_mode == SN_POOL_TIE_SPLIT) { if (xbf16) SN_FWD(SN_POOL_TIE_SPLIT, __nv_bfloat16); else SN_FWD(SN_POOL_TIE_SPLIT, float); }
+    else { if (xbf16) SN_FWD(SN_POOL_FIRST_ARGMAX, __nv_bfloat16); else SN_FWD(SN_POOL_FIRST_ARGMAX, float); }
+#undef SN_FWD
     return after_launch("bn_pool_fwd_kernel");
 }
 
+int sn_bn_pool_fwd_apply(const float *x, float *y_pool, void *y_pool_bf16, uint8_t *code, const double *scratch, int N, int H,
+                         int W, int C, int pool_mode, void *stream) {
+    return bn_pool_fwd_apply_impl(x, false, y_pool, y_pool_bf16, code, scratch, N, H, W, C, pool_mode, stream);
+}
+int sn_bn_pool_fwd_apply_xbf16(const void *x_bf16, float *y_pool, void *y_pool_bf16, uint8_t *code, const double *scratch, int N, int H,
+                               int W, int C, int pool_mode, void *stream) {
+    return bn_pool_fwd_apply_impl(x_bf16, true, y_pool, y_pool_bf16, code, scratch, N, H, W, C, pool_mode, stream);
+}
+
 // phases: 1 = memset + reductions (with `defer`: local sums stay in the scratch), 2 = apply
-static int bn_pool_bwd_impl(int phases, int defer, const float *dy_pool, const uint8_t *code, const float *x, const float *y_pool,
+static int bn_pool_bwd_impl(int phases, int defer, bool xbf16, const float *dy_pool, const uint8_t *code, const void *x, const float *y_pool,
                             const float *gamma, const float *beta, const float *save_mean, const float *save_invstd, float *dx,
                             void *dx_bf16, float *dx_colsum, float *dgamma, float *dbeta, double *scratch, int N, int H, int W,
                             int C, int pool_mode, int mask_relu, void *stream) {
@@ -416,22 +436,26 @@ static int bn_pool_bwd_impl(int phases, int defer, const float *dy_pool, const u
             rgrid = grid_for_windows(windows4, 3);
             const long long by_work = windows4 / (256 * 8);
             if (by_work < rgrid) rgrid = by_work < 1 ? 1 : (int)by_work;
-            if (pool_mode == SN_POOL_TIE_SPLIT)
-                bn_pool_bwd_reduce_pooled_kernel<SN_POOL_TIE_SPLIT><<<rgrid, 256, 0, st>>>(dy_pool, y_pool, cd, x, gamma, beta, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
-            else
-                bn_pool_bwd_reduce_pooled_kernel<SN_POOL_FIRST_ARGMAX><<<rgrid, 256, 0, st>>>(dy_pool, y_pool, cd, x, gamma, beta, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
-        } else if (pool_mode == SN_POOL_TIE_SPLIT)
-            bn_pool_bwd_reduce_kernel<SN_POOL_TIE_SPLIT><<<rgrid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
-        else
-            bn_pool_bwd_reduce_kernel<SN_POOL_FIRST_ARGMAX><<<rgrid, 256, 0, st>>>(dy_pool, cd, x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin);
+#define SN_RP(M, XT) bn_pool_bwd_reduce_pooled_kernel<M, XT><<<rgrid, 256, 0, st>>>(dy_pool, y_pool, cd, (const XT *)x, gamma, beta, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin)
+            if (pool_mode == SN_POOL_TIE_SPLIT) { if (xbf16) SN_RP(SN_POOL_TIE_SPLIT, __nv_bfloat16); else SN_RP(SN_POOL_TIE_SPLIT, float); }
+            else { if (xbf16) SN_RP(SN_POOL_FIRST_ARGMAX, __nv_bfloat16); else SN_RP(SN_POOL_FIRST_ARGMAX, float); }
+#undef SN_RP
+        } else {
+#define SN_RW(M, XT) bn_pool_bwd_reduce_kernel<M, XT><<<rgrid, 256, 0, st>>>(dy_pool, cd, (const XT *)x, save_mean, save_invstd, scratch, windows4, C, W, oh, ow, fin)
+            if (pool_mode == SN_POOL_TIE_SPLIT) { if (xbf16) SN_RW(SN_POOL_TIE_SPLIT, __nv_bfloat16); else SN_RW(SN_POOL_TIE_SPLIT, float); }
+            else { if (xbf16) SN_RW(SN_POOL_FIRST_ARGMAX, __nv_bfloat16); else SN_RW(SN_POOL_FIRST_ARGMAX, float); }
+#undef SN_RW
+        }
         int e = after_launch("bn_pool_bwd_reduce_kernel");
         if (e) return e;
     }
     if (phases & 2) {
         SN_REQUIRE(dx || dx_bf16, "null tensor");
-#define SN_LAUNCH(M, K) SN_CUDA(launch_dependent(bn_pool_bwd_apply_kernel<M, K>, dim3(grid), dim3(256), 0, st, dy_pool, cd, x, dx, (__nv_bfloat16 *)dx_bf16, dx_colsum, scratch, windows4, C, W, oh, ow))
+#define SN_LAUNCH2(M, K, XT) SN_CUDA(launch_dependent(bn_pool_bwd_apply_kernel<M, K, XT>, dim3(grid), dim3(256), 0, st, dy_pool, cd, (const XT *)x, dx, (__nv_bfloat16 *)dx_bf16, dx_colsum, scratch, windows4, C, W, oh, ow))
+#define SN_LAUNCH(M, K) do { if (xbf16) SN_LAUNCH2(M, K, __nv_bfloat16); else SN_LAUNCH2(M, K, float); } while (0)
         if (pool_mode == SN_POOL_TIE_SPLIT) { if (mask_relu) SN_LAUNCH(SN_POOL_TIE_SPLIT, true); else SN_LAUNCH(SN_POOL_TIE_SPLIT, false); }
         else { if (mask_relu) SN_LAUNCH(SN_POOL_FIRST_ARGMAX, true); else SN_LAUNCH(SN_POOL_FIRST_ARGMAX, false); }
+#undef SN_LAUNCH2
 #undef SN_LAUNCH
         int e = after_launch("bn_pool_bwd_apply_kernel");
         if (e || !dx_colsum) return e;
@@ -445,20 +469,42 @@ int sn_bn_pool_bwd(const float *dy_pool, const uint8_t *code, const float *x, co
                    const float *beta, const float *save_mean, const float *save_invstd, float *dx, void *dx_bf16,
                    float *dx_colsum, float *dgamma, float *dbeta, double *scratch, int N, int H, int W, int C, int pool_mode,
                    int mask_relu, void *stream) {
-    return bn_pool_bwd_impl(3, 0, dy_pool, code, x, y_pool, gamma, beta, save_mean, save_invstd, dx, dx_bf16, dx_colsum, dgamma, dbeta,
+    return bn_pool_bwd_impl(3, 0, false, dy_pool, code, x, y_pool, gamma, beta, save_mean, save_invstd, dx, dx_bf16, dx_colsum, dgamma, dbeta,
                             scratch, N, H, W, C, pool_mode, mask_relu, stream);
 }
 
 int sn_bn_pool_bwd_local(const float *dy_pool, const uint8_t *code, const float *x, const float *y_pool, const float *gamma,
                          const float *beta, const float *save_mean, const float *save_invstd, float *dgamma, float *dbeta,
                          double *scratch, int N, int H, int W, int C, int pool_mode, void *stream) {
-    return bn_pool_bwd_impl(1, 1, dy_pool, code, x, y_pool, gamma, beta, save_mean, save_invstd, nullptr, nullptr, nullptr, dgamma, dbeta,
+    return bn_pool_bwd_impl(1, 1, false, dy_pool, code, x, y_pool, gamma, beta, save_mean, save_invstd, nullptr, nullptr, nullptr, dgamma, dbeta,
                             scratch, N, H, W, C, pool_mode, 0, stream);
 }
 
 int sn_bn_pool_bwd_apply(const float *dy_pool, const uint8_t *code, const float *x, float *dx, void *dx_bf16, float *dx_colsum,
                          double *scratch, int N, int H, int W, int C, int pool_mode, int mask_relu, void *stream) {
-    return bn_pool_bwd_impl(2, 0, dy_pool, code, x, nullptr, nullptr, nullptr, nullptr, nullptr, dx, dx_bf16, dx_colsum, nullptr, nullptr,
+    return bn_pool_bwd_impl(2, 0, false, dy_pool, code, x, nullptr, nullptr, nullptr, nullptr, nullptr, dx, dx_bf16, dx_colsum, nullptr, nullptr,
+                            scratch, N, H, W, C, pool_mode, mask_relu, stream);
+}
+
+// the same three with the full-resolution map x stored in bf16 (the bf16 tier's convolution outputs)
+int sn_bn_pool_bwd_xbf16(const float *dy_pool, const uint8_t *code, const void *x_bf16, const float *y_pool, const float *gamma,
+                         const float *beta, const float *save_mean, const float *save_invstd, float *dx, void *dx_bf16,
+                         float *dx_colsum, float *dgamma, float *dbeta, double *scratch, int N, int H, int W, int C, int pool_mode,
+                         int mask_relu, void *stream) {
+    return bn_pool_bwd_impl(3, 0, true, dy_pool, code, x_bf16, y_pool, gamma, beta, save_mean, save_invstd, dx, dx_bf16, dx_colsum, dgamma, dbeta,
+                            scratch, N, H, W, C, pool_mode, mask_relu, stream);
+}
+
+int sn_bn_pool_bwd_local_xbf16(const float *dy_pool, const uint8_t *code, const void *x_bf16, const float *y_pool, const float *gamma,
+                               const float *beta, const float *save_mean, const float *save_invstd, float *dgamma, float *dbeta,
+                               double *scratch, int N, int H, int W, int C, int pool_mode, void *stream) {
+    return bn_pool_bwd_impl(1, 1, true, dy_pool, code, x_bf16, y_pool, gamma, beta, save_mean, save_invstd, nullptr, nullptr, nullptr, dgamma, dbeta,
+                            scratch, N, H, W, C, pool_mode, 0, stream);
+}
+
+int sn_bn_pool_bwd_apply_xbf16(const float *dy_pool, const uint8_t *code, const void *x_bf16, float *dx, void *dx_bf16, float *dx_colsum,
+                               double *scratch, int N, int H, int W, int C, int pool_mode, int mask_relu, void *stream) {
+    return bn_pool_bwd_impl(2, 0, true, dy_pool, code, x_bf16, nullptr, nullptr, nullptr, nullptr, nullptr, dx, dx_bf16, dx_colsum, nullptr, nullptr,
                             scratch, N, H, W, C, pool_mode, mask_relu, stream);
 }
 

@@ -30,86 +30,14 @@
 // Flags are monotonically increasing sequence numbers (never reset), one word per (phase, source
 // rank, CTA); the sequence counter is advanced by the last CTA of each exchange kernel to finish.
 #include "common.cuh"
+#include "comm_dev.cuh"
 #include <new>
 #include <string.h>
 
 using namespace sn;
+using namespace sn::comm;
 
 namespace {
-
-constexpr int MAX_RANKS = 8;
-constexpr int MAX_CTAS = 64;                 // CTAs of an exchange kernel (flag slots per phase and rank)
-constexpr int CTA_THREADS = 512;
-constexpr size_t STAGE_SLOT_BYTES = 256 * 1024;      // one rank's slot of the one-shot staging area (per parity)
-constexpr size_t FLAG_WORDS = 3 * MAX_RANKS * MAX_CTAS;    // phases: 0 = two-shot entry, 1 = two-shot exit, 2 = one-shot
-constexpr size_t ALIGN = 1024;
-
-struct Window {            // layout of one rank's window, identical on every rank
-    size_t user_bytes, stage_off, flag_off, total;
-};
-Window window_layout(size_t user_bytes) {
-    Window w;
-    w.user_bytes = (user_bytes + ALIGN - 1) / ALIGN * ALIGN;
-    w.stage_off = w.user_bytes;
-    w.flag_off = w.stage_off + 2 * MAX_RANKS * STAGE_SLOT_BYTES;
-    w.total = w.flag_off + (FLAG_WORDS * sizeof(unsigned) + ALIGN - 1) / ALIGN * ALIGN;
-    return w;
-}
-
-struct DevTable {          // kernel argument: every rank's window as seen from THIS rank
-    char *win[MAX_RANKS];
-};
-
-struct Comm {
-    int rank, world, device;
-    Window lay;
-    char *local;                       // this rank's window (cudaMalloc)
-    char *peer[MAX_RANKS];             // peer[rank] == local
-    bool ipc_opened[MAX_RANKS];
-    unsigned *state;                   // device: [0] = sequence number of the last finished exchange, [1] = CTA arrival counter
-    bool connected;
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned *flag_ptr(char *win, size_t flag_off, int phase, int src_rank, int cta) {
-    return reinterpret_cast<unsigned *>(win + flag_off) + ((size_t)phase * MAX_RANKS + src_rank) * MAX_CTAS + cta;
-}
-
-// all threads of the CTA: tell every rank's CTA `blockIdx.x` that this rank reached `phase` of exchange
-// `seq`, then wait until every rank's CTA `blockIdx.x` has said the same.  Everything this CTA wrote
-// before the call is visible to the peers after their wait (CTA barrier, then a system-scope release).
-__device__ __forceinline__ void cta_exchange_flags(const DevTable &t, size_t flag_off, int phase, int rank, int world, unsigned seq) {
-    __syncthreads();
-    if ((int)threadIdx.x < world) {
-        const int peer = threadIdx.x;
-        __threadfence_system();
-        st_release_sys(flag_ptr(t.win[peer], flag_off, phase, rank, blockIdx.x), seq);
-        const unsigned *mine = flag_ptr(t.win[rank], flag_off, phase, peer, blockIdx.x);
-        while ((int)(ld_acquire_sys(mine) - seq) < 0) { }
-    }
-    __syncthreads();
-}
-
-// the last CTA of the kernel to get here publishes the new sequence number (every CTA has read the
-// old one by then, because reading it is the first thing a CTA does)
-__device__ __forceinline__ void finish_exchange(unsigned *state, unsigned seq) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&state[1], 1u) == gridDim.x - 1) {
-            state[1] = 0u;
-            __threadfence();
-            *reinterpret_cast<volatile unsigned *>(&state[0]) = seq;
-        }
-    }
-}
 
 template <typename T> struct Vec;
 template <> struct Vec<float> { using type = float4; static constexpr int N = 4; };
@@ -120,11 +48,18 @@ __device__ __forceinline__ float4 ld_cg(const float4 *p) { return __ldcg(p); }
 __device__ __forceinline__ double2 ld_cg(const double2 *p) { return __ldcg(p); }
 
 // ---- two-shot, in place, tensor at byte offset `off` of every window's user region --------------
-template <typename T>
-__global__ void __launch_bounds__(CTA_THREADS) allreduce_inplace_kernel(DevTable t, size_t flag_off, unsigned *state, size_t off,
-                                                                        long long n, int rank, int world) {
+constexpr int INPLACE_THREADS = 256;        // 4 x world vectors in flight per thread need the registers of a half-size CTA
+// SGD: the optimizer step rides on the exchange (float only).  After its exit barrier a CTA knows that the
+// sums of exactly the elements its own index walks (in every rank's slice) have arrived in its window, so it
+// applies w -= lr * g; g = 0 to those elements right there: the reference's optimizer.update
+// (utils/Optimizers.py:29-32) without another launch and another pass over the arena.
+template <typename T, bool SGD>
+__global__ void __launch_bounds__(INPLACE_THREADS) allreduce_inplace_kernel(DevTable t, size_t flag_off, unsigned *state, size_t off,
+                                                                        long long n, int rank, int world, float *w, long long n_update,
+                                                                        float lr) {
     using V = typename Vec<T>::type;
     constexpr int VN = Vec<T>::N;
+    pdl_wait();
     const unsigned seq = *reinterpret_cast<volatile unsigned *>(&state[0]) + 1u;
     // entry: every rank's backward pass has finished writing its gradients (stream order on each rank)
     cta_exchange_flags(t, flag_off, 0, rank, world, seq);
@@ -132,14 +67,35 @@ __global__ void __launch_bounds__(CTA_THREADS) allreduce_inplace_kernel(DevTable
     const long long nv = n / VN;
     const long long per = (nv + world - 1) / world;
     const long long v0 = per * rank, v1 = min(nv, v0 + per);
-    for (long long i = v0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v1; i += (long long)gridDim.x * blockDim.x) {
-        V acc = ld_cg(reinterpret_cast<const V *>(t.win[0] + off) + i);
+    // four vectors per thread and trip, ALL loads (4 x world, most of them over NVLink, ~2-3 us each way)
+    // issued before the first store: the compiler cannot hoist a load above a store through these
+    // pointers, and a thread that walks its slice one round trip at a time is pure latency
+    constexpr int U = 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = v0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < v1; i0 += U * stride) {
+        V acc[U], part[U][MAX_RANKS - 1];
 #pragma unroll
-        for (int p = 1; p < MAX_RANKS; ++p)
-            if (p < world) vadd(acc, ld_cg(reinterpret_cast<const V *>(t.win[p] + off) + i));
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < v1) {
+                acc[u] = ld_cg(reinterpret_cast<const V *>(t.win[0] + off) + i);
 #pragma unroll
-        for (int p = 0; p < MAX_RANKS; ++p)
-            if (p < world) reinterpret_cast<V *>(t.win[p] + off)[i] = acc;
+                for (int p = 1; p < MAX_RANKS; ++p)
+                    if (p < world) part[u][p - 1] = ld_cg(reinterpret_cast<const V *>(t.win[p] + off) + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < v1) {
+#pragma unroll
+                for (int p = 1; p < MAX_RANKS; ++p)
+                    if (p < world) vadd(acc[u], part[u][p - 1]);
+#pragma unroll
+                for (int p = 0; p < MAX_RANKS; ++p)
+                    if (p < world) reinterpret_cast<V *>(t.win[p] + off)[i] = acc[u];
+            }
+        }
     }
     if (rank == world - 1 && blockIdx.x == 0) {
         for (long long i = nv * VN + threadIdx.x; i < n; i += blockDim.x) {
@@ -150,6 +106,21 @@ __global__ void __launch_bounds__(CTA_THREADS) allreduce_inplace_kernel(DevTable
     }
     // exit: every rank has pushed its slice into every window
     cta_exchange_flags(t, flag_off, 1, rank, world, seq);
+    if constexpr (SGD) {
+        float4 *g4 = reinterpret_cast<float4 *>(t.win[rank] + off), *w4 = reinterpret_cast<float4 *>(w);
+        const long long nu = n_update / 4;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < world; ++p) {
+            const long long a = per * p, b = min(min(nv, a + per), nu);
+            for (long long i = a + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < b; i += stride) {
+                const float4 g = __ldcg(g4 + i);
+                float4 wv = w4[i];
+                wv.x -= lr * g.x; wv.y -= lr * g.y; wv.z -= lr * g.z; wv.w -= lr * g.w;
+                w4[i] = wv;
+                g4[i] = zero;
+            }
+        }
+    }
     finish_exchange(state, seq);
 }
 
@@ -217,10 +188,10 @@ __global__ void copy_kernel(const T *__restrict__ src, T *__restrict__ dst, long
 }
 
 int grid_two_shot(long long bytes, int world) {
-    // latency-bound: enough CTAs to keep the NVLink ports busy (a CTA moves 512 x 16 B per trip), never
+    // latency-bound: enough CTAs to keep the NVLink ports busy (a CTA moves 256 x 4 x 16 B per trip), never
     // so many that the flag exchange (world remote stores + world polls per CTA) dominates
     long long per_rank = bytes / world;
-    int g = (int)((per_rank + 32 * 1024 - 1) / (32 * 1024));
+    int g = (int)((per_rank + 16 * 1024 - 1) / (16 * 1024));
     return g < 1 ? 1 : (g > MAX_CTAS ? MAX_CTAS : g);
 }
 
@@ -236,7 +207,8 @@ int allreduce(Comm *c, T *buf, long long n, cudaStream_t st) {
     if (in_window && bytes > 64 * 1024) {
         const size_t off = (size_t)(b - c->local);
         if (off % 16) { set_error("sn_allreduce: a tensor inside the window must be 16-byte aligned"); return SN_ERR_INVALID_ARG; }
-        allreduce_inplace_kernel<T><<<grid_two_shot((long long)bytes, c->world), CTA_THREADS, 0, st>>>(t, c->lay.flag_off, c->state, off, n, c->rank, c->world);
+        SN_CUDA(launch_dependent(allreduce_inplace_kernel<T, false>, dim3(grid_two_shot((long long)bytes, c->world)), dim3(INPLACE_THREADS), 0, st,
+                                 t, c->lay.flag_off, c->state, off, n, c->rank, c->world, (float *)nullptr, 0ll, 0.f));
         return after_launch("allreduce_inplace_kernel");
     }
     if (bytes <= STAGE_SLOT_BYTES) {
@@ -252,7 +224,7 @@ int allreduce(Comm *c, T *buf, long long n, cudaStream_t st) {
         const long long m = (n - done) < (long long)cap ? (n - done) : (long long)cap;
         copy_kernel<T><<<grid_for(m, 256), 256, 0, st>>>(buf + done, reinterpret_cast<T *>(c->local), m);
         ++g_launch_count;
-        allreduce_inplace_kernel<T><<<grid_two_shot(m * (long long)sizeof(T), c->world), CTA_THREADS, 0, st>>>(t, c->lay.flag_off, c->state, 0, m, c->rank, c->world);
+        allreduce_inplace_kernel<T, false><<<grid_two_shot(m * (long long)sizeof(T), c->world), INPLACE_THREADS, 0, st>>>(t, c->lay.flag_off, c->state, 0, m, c->rank, c->world, nullptr, 0ll, 0.f);
         ++g_launch_count;
         copy_kernel<T><<<grid_for(m, 256), 256, 0, st>>>(reinterpret_cast<const T *>(c->local), buf + done, m);
         int e = after_launch("allreduce (staged)");
@@ -376,6 +348,25 @@ int sn_comm_destroy(void *comm) {
 int sn_allreduce_sum_f32(void *comm, float *buf, long long n, void *stream) {
     SN_REQUIRE(comm && (buf || n == 0), "bad arguments");
     return allreduce<float>(static_cast<Comm *>(comm), buf, n, as_stream(stream));
+}
+int sn_allreduce_sgd_update(void *comm, float *g, float *w, long long n, long long n_params, float lr, void *stream) {
+    SN_REQUIRE(comm && g && w && n > 0 && n_params >= 0 && n_params <= n, "bad arguments");
+    Comm *c = static_cast<Comm *>(comm);
+    SN_REQUIRE(c->connected, "the communicator is not connected");
+    char *b = reinterpret_cast<char *>(g);
+    const size_t bytes = (size_t)n * 4;
+    const bool in_window = b >= c->local && b + bytes <= c->local + c->lay.user_bytes;
+    if (c->world == 1 || !in_window || (n & 3) || (n_params & 3) || ((uintptr_t)w & 15) || ((size_t)(b - c->local) & 15)) {
+        // not expressible as the fused kernel: the same result in two steps
+        int e = allreduce<float>(c, g, n, as_stream(stream));
+        if (e) return e;
+        return sn_sgd_update(w, g, n_params, lr, 1.0f, stream);
+    }
+    DevTable t;
+    for (int p = 0; p < MAX_RANKS; ++p) t.win[p] = c->peer[p < c->world ? p : 0];
+    SN_CUDA(launch_dependent(allreduce_inplace_kernel<float, true>, dim3(grid_two_shot((long long)bytes, c->world)), dim3(INPLACE_THREADS), 0,
+                             as_stream(stream), t, c->lay.flag_off, c->state, (size_t)(b - c->local), n, c->rank, c->world, w, n_params, lr));
+    return after_launch("allreduce_inplace_kernel (sgd)");
 }
 int sn_allreduce_sum_f64(void *comm, double *buf, long long n, void *stream) {
     SN_REQUIRE(comm && (buf || n == 0), "bad arguments");

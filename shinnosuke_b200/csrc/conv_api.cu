@@ -9,8 +9,9 @@ int conv_dgrad_simt(const float *, const float *, float *, int, int, int, int, i
 int conv_wgrad_simt(const float *, const float *, float *, float *, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 bool conv_tc_eligible(int N, int C, int OH, int OW, int F, int stride, bool bf16 = false);
 bool wgrad_tc_eligible(int N, int C, int OH, int OW, int F, int stride);
-int conv_igemm_tc(const void *x, const void *w, const float *bias, float *out, int N, int C, int IH, int IW, int F, int kh,
-                  int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, bool bf16, double *stats, cudaStream_t st);
+int conv_igemm_tc(const void *x, const void *w, const float *bias, void *out, int N, int C, int IH, int IW, int F, int kh,
+                  int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, bool bf16, double *stats, cudaStream_t st,
+                  bool out_bf16 = false);
 int flip_transpose_filters_bf16(const float *w, void *wt, int F, int C, int kh, int kw, cudaStream_t st);
 int cast_f32_to_bf16(const float *src, void *dst, long long n, cudaStream_t st);
 int split_tf32_lo(const float *src, float *lo, long long n, cudaStream_t st);
@@ -23,8 +24,8 @@ int conv_wgrad_halo_tc(const void *x, const void *dy, float *dw, int N, int C, i
                        int OW, int pad_h, int pad_w, bool bf16, cudaStream_t st);
 int colsum_accumulate(const float *dy, float *db, long long rows, int F, cudaStream_t st);
 bool stem_tc_eligible(int N, int C, int H, int W, int F, int kh, int kw, int stride, int ph, int pw);
-int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
-                       int kw, int stride, int ph, int pw, int act, double *stats, cudaStream_t st);
+int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, void *y, int N, int C, int H, int W, int F, int kh,
+                       int kw, int stride, int ph, int pw, int act, double *stats, cudaStream_t st, bool out_bf16 = false);
 int conv_stem_wgrad_tc(const float *x, const float *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh, int kw,
                        int stride, int ph, int pw, cudaStream_t st);
 bool tiny_wgrad_eligible(int C, int kh, int kw, int F);
@@ -299,6 +300,29 @@ int sn_conv2d_fprop_bf16_stats(const void *x, const void *w, const float *bias, 
     int oh, ow;
     bf16_geom(N, C, H, W, F, kh, kw, stride, pad_h, pad_w, oh, ow);
     return conv_igemm_tc(x, w, bias, y, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, act, 0, true, bn_scratch, as_stream(stream));
+}
+// bf16 tier, convolution in front of a fused BatchNormalization (+ pool): bf16 operands, fp32 accumulation,
+// the output map stored in bf16 and its per-channel sums (of the stored values) added to bn_scratch
+int sn_conv2d_fprop_bf16_stats_ybf16(const void *x, const void *w, const float *bias, void *y_bf16, int N, int C, int H, int W, int F,
+                                     int kh, int kw, int stride, int pad_h, int pad_w, int act, double *bn_scratch, void *stream) {
+    SN_REQUIRE(x && w && y_bf16 && bn_scratch, "null tensor");
+    SN_REQUIRE(sn_conv2d_fprop_ybf16_supported(1, N, C, H, W, F, kh, kw, stride, pad_h, pad_w), "shape not supported with a bf16 output map");
+    int oh, ow;
+    bf16_geom(N, C, H, W, F, kh, kw, stride, pad_h, pad_w, oh, ow);
+    return conv_igemm_tc(x, w, bias, y_bf16, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, act, 0, true, bn_scratch, as_stream(stream), true);
+}
+// the tiny-C stem (fp32 input image and filters, TF32 products) with a bf16 output map + statistics
+int sn_conv2d_fprop_stats_ybf16(const float *x, const float *w, const float *bias, void *y_bf16, int N, int C, int H, int W, int F,
+                                int kh, int kw, int stride, int pad_h, int pad_w, int act, double *bn_scratch, void *stream) {
+    SN_REQUIRE(x && w && y_bf16 && bn_scratch, "null tensor");
+    SN_REQUIRE(sn_conv2d_fprop_ybf16_supported(0, N, C, H, W, F, kh, kw, stride, pad_h, pad_w), "shape not supported with a bf16 output map");
+    return conv_stem_fprop_tc(x, w, bias, y_bf16, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, bn_scratch, as_stream(stream), true);
+}
+int sn_conv2d_fprop_ybf16_supported(int bf16_operands, int N, int C, int H, int W, int F, int kh, int kw, int stride, int pad_h, int pad_w) {
+    if ((F & 7) || F <= 32 || F > 512) return 0;
+    if (bf16_operands) return sn_conv2d_fprop_stats_supported(SN_PREC_BF16, 1, N, C, H, W, F, kh, kw, stride, pad_h, pad_w);
+    if (N <= 0 || C <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad_h < 0 || pad_w < 0 || H + 2 * pad_h < kh || W + 2 * pad_w < kw) return 0;
+    return stem_tc_eligible(N, C, H, W, F, kh, kw, stride, pad_h, pad_w) ? 1 : 0;
 }
 int sn_conv2d_dgrad_bf16(const void *dy, const void *wt, float *dx, int N, int C, int H, int W, int F, int kh, int kw, int stride,
                          int pad_h, int pad_w, int accumulate, void *stream) {

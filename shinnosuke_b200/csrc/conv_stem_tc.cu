@@ -137,7 +137,8 @@ constexpr int SF_PATCH_FLOATS = 4096;          // per patch stage; stem_tc_eligi
 constexpr int SF_ABUF = 3;
 constexpr int SF_A_BYTES = 128 * 128;
 
-template <int BN>
+// OBF16: the output map is stored in bf16 (see conv_tc.cu): 64-byte staging rows, statistics of the rounded values
+template <int BN, bool OBF16 = false>
 __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX,
                                                                    const __grid_constant__ CUtensorMap tmXr, const StemP p) {
     extern __shared__ uint8_t smem_raw[];
@@ -260,6 +261,27 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
                 uint8_t *st = epi_stage + ew * 4096;
                 if (lane == 0) tma_store_wait_read();               // this warp's previous store has drained the tile
                 __syncwarp();
+                if constexpr (OBF16) {
+                    float v[32];
+#pragma unroll
+                    for (int jj = 0; jj < 32; jj += 4) {
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias && c0 + jj < p.F) b = __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + jj));
+                        v[jj] = __uint_as_float(rr[jj]) + b.x; v[jj + 1] = __uint_as_float(rr[jj + 1]) + b.y;
+                        v[jj + 2] = __uint_as_float(rr[jj + 2]) + b.z; v[jj + 3] = __uint_as_float(rr[jj + 3]) + b.w;
+                        if (p.act == SN_ACT_RELU) {
+                            v[jj] = relu_keep_sign(v[jj]); v[jj + 1] = relu_keep_sign(v[jj + 1]);
+                            v[jj + 2] = relu_keep_sign(v[jj + 2]); v[jj + 3] = relu_keep_sign(v[jj + 3]);
+                        }
+                    }
+                    stage_row_bf16(st, lane, v);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d(&tmO, st, c0, tile * 128 + q * 32); tma_store_commit(); }
+                    if (p.stats)
+                        staged_tile_colsums_bf16(st, lane, p.P - (tile * 128 + q * 32), mystat + c0, mystat + BN + c0, p.F - c0);
+                    continue;
+                }
 #pragma unroll
                 for (int jj = 0; jj < 32; jj += 4) {
                     float4 v = make_float4(__uint_as_float(rr[jj]), __uint_as_float(rr[jj + 1]), __uint_as_float(rr[jj + 2]),
@@ -476,7 +498,7 @@ int make_patch_tmap(CUtensorMap *tm, const StemP &p, int rows = 1) {
     return make_tmap_linear_f32(tm, p.x, 3, dims, strs, box);
 }
 
-template <int BN>
+template <int BN, bool OBF16>
 int launch_stem_fprop(const StemP &p, cudaStream_t st) {
     const int smem = BN * 128 + SF_ABUF * SF_A_BYTES + SF_EPI_WARPS * 4096 + 8 * 2 * BN * 4 + PATCH_STAGES * SF_PATCH_FLOATS * 4 + 1024 + 256;
     CUtensorMap tmO, tmX, tmXr;
@@ -487,15 +509,15 @@ int launch_stem_fprop(const StemP &p, cudaStream_t st) {
     long long odims[2] = {p.F, p.P};
     long long ostr[2] = {1, p.F};
     int obox[2] = {32, 32};
-    int e = make_tmap_f32(&tmO, p.y, 2, odims, ostr, obox);
+    int e = OBF16 ? make_tmap_bf16_sw64(&tmO, p.y, 2, odims, ostr, obox) : make_tmap_f32(&tmO, p.y, 2, odims, ostr, obox);
     if (e) return e;
     static bool configured = false;
     if (!configured) {
-        SN_CUDA(cudaFuncSetAttribute(stem_fprop_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SN_CUDA(cudaFuncSetAttribute(stem_fprop_kernel<BN, OBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     int grid = p.tiles < num_sms() ? p.tiles : num_sms();
-    SN_CUDA(launch_dependent(stem_fprop_kernel<BN>, dim3(grid), dim3(SF_THREADS), (size_t)smem, st, tmO, tmX, tmXr, p));
+    SN_CUDA(launch_dependent(stem_fprop_kernel<BN, OBF16>, dim3(grid), dim3(SF_THREADS), (size_t)smem, st, tmO, tmX, tmXr, p));
     return after_launch("stem_fprop_kernel");
 }
 
@@ -519,17 +541,24 @@ bool stem_tc_eligible(int N, int C, int H, int W, int F, int kh, int kw, int str
     return P >= 4096;          // small maps: the direct kernel is latency-equivalent
 }
 
-int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
-                       int kw, int stride, int ph, int pw, int act, double *stats, cudaStream_t st) {
+int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, void *y, int N, int C, int H, int W, int F, int kh,
+                       int kw, int stride, int ph, int pw, int act, double *stats, cudaStream_t st, bool out_bf16) {
     StemP p{};
     fill_geom(p, N, C, H, W, F, kh, kw, stride, ph, pw);
-    p.x = x; p.w = w; p.bias = bias; p.y = y; p.act = act;
+    p.x = x; p.w = w; p.bias = bias; p.y = static_cast<float *>(y); p.act = act;      // (a bf16 map when out_bf16: only the tensor map reads p.y)
     p.stats = stats;              // zero on entry (caller's contract): no memset node in the step graph
     p.tiles = (p.P + 127) / 128;
-    if (F <= 32) return launch_stem_fprop<32>(p, st);
-    if (F <= 64) return launch_stem_fprop<64>(p, st);
-    if (F <= 128) return launch_stem_fprop<128>(p, st);
-    return launch_stem_fprop<256>(p, st);
+    if (out_bf16) {
+        if (F & 7) { set_error("conv_stem_fprop_tc: a bf16 output map needs F %% 8 == 0"); return SN_ERR_UNSUPPORTED; }
+        if (F <= 32) return launch_stem_fprop<32, true>(p, st);
+        if (F <= 64) return launch_stem_fprop<64, true>(p, st);
+        if (F <= 128) return launch_stem_fprop<128, true>(p, st);
+        return launch_stem_fprop<256, true>(p, st);
+    }
+    if (F <= 32) return launch_stem_fprop<32, false>(p, st);
+    if (F <= 64) return launch_stem_fprop<64, false>(p, st);
+    if (F <= 128) return launch_stem_fprop<128, false>(p, st);
+    return launch_stem_fprop<256, false>(p, st);
 }
 
 // dw/db accumulated into (+=).  Requires K < 32 when db != NULL (the ones column).

@@ -75,6 +75,25 @@ int make_tmap_linear_f32(CUtensorMap *out, const void *base, int rank, const lon
     return SN_OK;
 }
 
+int make_tmap_bf16_sw64(CUtensorMap *out, const void *base, int rank, const long long *dims, const long long *strides_elems,
+                        const int *box) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return SN_ERR_UNSUPPORTED; }
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = (cuuint64_t)dims[i]; bdim[i] = (cuuint32_t)box[i]; estr[i] = 1; }
+    for (int i = 1; i < rank; ++i) gstr[i - 1] = (cuuint64_t)strides_elems[i] * 2;
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bdim, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (bf16, 64B swizzle) failed (%d): rank %d dims %lld %lld box %d %d", (int)r, rank, dims[0],
+                  rank > 1 ? dims[1] : 0, box[0], rank > 1 ? box[1] : 0);
+        return SN_ERR_UNSUPPORTED;
+    }
+    return SN_OK;
+}
+
 int make_tmap(CUtensorMap *out, const void *base, int rank, const long long *dims, const long long *strides_elems,
               const int *box, bool atom32b, bool bf16) {
     EncodeTiledFn enc = get_encode_tiled();
@@ -160,7 +179,10 @@ template <int BN, int KS, bool PAIR = false> struct IgemmCfg {
 
 // BF16: the operands are bf16 copies (64 elements per 128-byte row, UMMA K = 16, kind::f16); the
 // accumulators, bias, activation and output stay fp32.  Byte geometry of the tiles is identical.
-template <int BN, int KS, bool BF16, bool PAIR>
+// OBF16: the OUTPUT map is stored in bf16 as well (the bf16 tier's convolutions in front of a fused
+// BatchNormalization + pool: the map is written once and read twice, all three at half the bytes); the
+// epilogue then stages 64-byte rows (tc_common.cuh) and the statistics are those of the rounded values.
+template <int BN, int KS, bool BF16, bool PAIR, bool OBF16 = false>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const IgemmParams p) {
@@ -321,6 +343,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         uint8_t *st = epi_stage + (warp - 2) * 4096;
                         if (lane == 0) tma_store_wait_read();           // previous store has drained the tile
                         __syncwarp();
+                        if constexpr (OBF16) {
+                            float v[32];
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (p.bias && f0 + j < p.F) b = __ldg(reinterpret_cast<const float4 *>(p.bias + f0 + j));
+                                v[j] = __uint_as_float(r[j]) + b.x; v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+                                v[j + 2] = __uint_as_float(r[j + 2]) + b.z; v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+                                if (p.act == SN_ACT_RELU) {
+                                    v[j] = relu_keep_sign(v[j]); v[j + 1] = relu_keep_sign(v[j + 1]);
+                                    v[j + 2] = relu_keep_sign(v[j + 2]); v[j + 3] = relu_keep_sign(v[j + 3]);
+                                }
+                            }
+                            stage_row_bf16(st, lane, v);
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) { tma_store_2d(&tmO, st, f0, tm * BM + q * 32); tma_store_commit(); }
+                            if (p.stats)
+                                staged_tile_colsums_bf16(st, lane, p.rows - (tm * BM + q * 32), sstat + q * 2 * STAT_MAX_F + f0,
+                                                         sstat + (q * 2 + 1) * STAT_MAX_F + f0, p.F - f0);
+                            continue;
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
@@ -718,26 +762,26 @@ bool tile_geometry(int N, int OH, int OW, TileGeom &g) {
     return g.th <= 256;
 }
 
-template <int BN, int KS, bool BF16>
+template <int BN, int KS, bool BF16, bool OBF16 = false>
 int launch_igemm_ks(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO, const IgemmParams &p, cudaStream_t st) {
     using Cfg = IgemmCfg<BN, KS>;
     static bool configured = false;
     if (!configured) {
-        SN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, KS, BF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        SN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, KS, BF16, false, OBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
     int tiles = p.tiles_m * p.tiles_n;
     int grid = tiles < num_sms() ? tiles : num_sms();
-    SN_CUDA(launch_dependent(conv_igemm_kernel<BN, KS, BF16, false>, dim3(grid), dim3(IG_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, tmO, p));
+    SN_CUDA(launch_dependent(conv_igemm_kernel<BN, KS, BF16, false, OBF16>, dim3(grid), dim3(IG_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, tmO, p));
     return after_launch("conv_igemm_kernel");
 }
 // CTA pairs: clusters of two, one pair per TPC, persistent over tile pairs
-template <int BN, bool BF16>
+template <int BN, bool BF16, bool OBF16 = false>
 int launch_igemm_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO, const IgemmParams &p, cudaStream_t st) {
     using Cfg = IgemmCfg<BN, 1, true>;
     static bool configured = false;
     if (!configured) {
-        SN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, 1, BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        SN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, 1, BF16, true, OBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
     const int pairs = (p.tiles_m / 2) * p.tiles_n, max_pairs = num_sms() / 2;
@@ -750,13 +794,24 @@ int launch_igemm_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUte
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    SN_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, 1, BF16, true>, tmA, tmB, tmO, p));
+    SN_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, 1, BF16, true, OBF16>, tmA, tmB, tmO, p));
     ++sn::g_igemm_pair_launches;
     return after_launch("conv_igemm_kernel (pair)");
 }
 template <int BN>
 int launch_igemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO, const IgemmParams &p, bool bf16, bool pair,
-                 cudaStream_t st) {
+                 bool out_bf16, cudaStream_t st) {
+    if constexpr (BN >= 64) {
+        if (out_bf16) {          // bf16 operands AND a bf16 output map (host-checked)
+            if constexpr (BN >= 128) {
+                if (pair) return launch_igemm_pair<BN, true, true>(tmA, tmB, tmO, p, st);
+            }
+            if constexpr (BN == 64) {
+                if (((p.ntaps * p.cblocks) % 2) == 0) return launch_igemm_ks<BN, 2, true, true>(tmA, tmB, tmO, p, st);
+            }
+            return launch_igemm_ks<BN, 1, true, true>(tmA, tmB, tmO, p, st);
+        }
+    }
     if constexpr (BN >= 128) {
         if (pair) return bf16 ? launch_igemm_pair<BN, true>(tmA, tmB, tmO, p, st) : launch_igemm_pair<BN, false>(tmA, tmB, tmO, p, st);
     }
@@ -795,8 +850,15 @@ bool conv_tc_eligible(int N, int C, int OH, int OW, int F, int stride, bool bf16
 }
 
 // x: NHWC (N, IH, IW, C); w: [F][kh*kw][C]; out: (N*OH*OW, F).
-int conv_igemm_tc(const void *x, const void *w, const float *bias, float *out, int N, int C, int IH, int IW, int F, int kh,
-                  int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, bool bf16, double *stats, cudaStream_t st) {
+// out_bf16: `out` is a bf16 map (bf16 operands only, F % 8 == 0, F > 32, no accumulation)
+int conv_igemm_tc(const void *x, const void *w, const float *bias, void *out_any, int N, int C, int IH, int IW, int F, int kh,
+                  int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, bool bf16, double *stats, cudaStream_t st,
+                  bool out_bf16) {
+    float *out = static_cast<float *>(out_any);
+    if (out_bf16 && !(bf16 && !accumulate && F > 32 && (F & 7) == 0)) {
+        set_error("conv_igemm_tc: a bf16 output map needs bf16 operands, F %% 8 == 0, F > 32 and no accumulation (F = %d)", F);
+        return SN_ERR_UNSUPPORTED;
+    }
     TileGeom g;
     if (!tile_geometry(N, OH, OW, g)) { set_error("conv_igemm_tc: unsupported output geometry %dx%d", OH, OW); return SN_ERR_UNSUPPORTED; }
     if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)out) & 15) { set_error("conv_igemm_tc: tensors must be 16-byte aligned"); return SN_ERR_INVALID_ARG; }
@@ -828,11 +890,12 @@ int conv_igemm_tc(const void *x, const void *w, const float *bias, float *out, i
     // TMA-store epilogue: full-line writes instead of 16-byte pieces of 32 different rows per instruction
     CUtensorMap tmO = tmB;
     p.tma_store = (!accumulate && BN >= 32 && (F & 3) == 0 && (!bias || (((uintptr_t)bias) & 15) == 0)) ? 1 : 0;
+    if (out_bf16 && !p.tma_store) { set_error("conv_igemm_tc: bf16 output needs the TMA-store epilogue"); return SN_ERR_UNSUPPORTED; }
     if (p.tma_store) {
         long long odims[2] = {F, p.rows};
         long long ostr[2] = {1, F};
         int obox[2] = {32, 32};
-        e = make_tmap_f32(&tmO, out, 2, odims, ostr, obox);
+        e = out_bf16 ? make_tmap_bf16_sw64(&tmO, out, 2, odims, ostr, obox) : make_tmap_f32(&tmO, out, 2, odims, ostr, obox);
         if (e) return e;
     }
     if (stats) {
@@ -840,11 +903,11 @@ int conv_igemm_tc(const void *x, const void *w, const float *bias, float *out, i
         p.stats = stats;          // zero on entry (caller's contract): no memset node in the step graph
     }
     switch (BN) {
-        case 16: return launch_igemm<16>(tmA, tmB, tmO, p, bf16, false, st);
-        case 32: return launch_igemm<32>(tmA, tmB, tmO, p, bf16, false, st);
-        case 64: return launch_igemm<64>(tmA, tmB, tmO, p, bf16, false, st);
-        case 128: return launch_igemm<128>(tmA, tmB, tmO, p, bf16, pair, st);
-        default: return launch_igemm<256>(tmA, tmB, tmO, p, bf16, pair, st);
+        case 16: return launch_igemm<16>(tmA, tmB, tmO, p, bf16, false, false, st);
+        case 32: return launch_igemm<32>(tmA, tmB, tmO, p, bf16, false, false, st);
+        case 64: return launch_igemm<64>(tmA, tmB, tmO, p, bf16, false, out_bf16, st);
+        case 128: return launch_igemm<128>(tmA, tmB, tmO, p, bf16, pair, out_bf16, st);
+        default: return launch_igemm<256>(tmA, tmB, tmO, p, bf16, pair, out_bf16, st);
     }
 }
 

@@ -270,6 +270,9 @@ int make_tmap_linear_f32(CUtensorMap *out, const void *base, int rank, const lon
                          const int *box);
 int make_tmap(CUtensorMap *out, const void *base, int rank, const long long *dims, const long long *strides_elems,
               const int *box, bool atom32b, bool bf16);
+// bf16 tensor with the 64-byte swizzle: the epilogue staging tiles of bf16 OUTPUT maps (32 rows x 32 bf16 = 64-byte rows)
+int make_tmap_bf16_sw64(CUtensorMap *out, const void *base, int rank, const long long *dims, const long long *strides_elems,
+                        const int *box);
 
 
 // Column sums of one epilogue staging tile: 32 rows x 32 fp32 columns in the 128-byte-swizzled
@@ -309,6 +312,50 @@ __device__ __forceinline__ void staged_tile_colsums(const uint8_t *st, int lane,
     b.y += __shfl_down_sync(0xffffffffu, b.y, 16);
     if (lane < 16) {
         const int c = 2 * cp;
+        if (c < ncols) { ssum[c] += a.x; ssq[c] += b.x; }
+        if (c + 1 < ncols) { ssum[c + 1] += a.y; ssq[c + 1] += b.y; }
+    }
+}
+
+// ---- bf16 output maps (bf16 tier: the convolution's own output is stored in bf16) -----------------------
+// One epilogue warp's 32 rows x 32 columns as bf16: 64-byte rows in the TMA 64-byte swizzle (16-byte chunk j
+// of row r at (j ^ ((r >> 1) & 3)) * 16; the tile is 512-byte aligned).  Lane = row writes its four chunks
+// conflict-free (8 lanes of a 128-bit store phase cover 8 distinct 16-byte bank groups).
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void stage_row_bf16(uint8_t *st, int lane, const float (&v)[32]) {
+#pragma unroll
+    for (int jc = 0; jc < 4; ++jc) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * jc + 0], v[8 * jc + 1]); u.y = pack_bf16x2(v[8 * jc + 2], v[8 * jc + 3]);
+        u.z = pack_bf16x2(v[8 * jc + 4], v[8 * jc + 5]); u.w = pack_bf16x2(v[8 * jc + 6], v[8 * jc + 7]);
+        *reinterpret_cast<uint4 *>(st + lane * 64 + ((jc ^ ((lane >> 1) & 3)) * 16)) = u;
+    }
+}
+// Column sums of such a tile (of the ROUNDED values: the statistics describe the map as stored).  Lane l
+// takes the column pair (l & 15) of rows 2i + (l >> 4): each warp-wide 4-byte load covers two whole rows
+// = 128 contiguous bytes, conflict-free.  Same per-warp tables as staged_tile_colsums.
+__device__ __forceinline__ void staged_tile_colsums_bf16(const uint8_t *st, int lane, int nvalid, float *ssum, float *ssq, int ncols) {
+    const int pr = lane & 15, rsel = lane >> 4;
+    float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int r = 2 * i + rsel;
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(st + r * 64 + (((pr >> 2) ^ ((r >> 1) & 3)) * 16) + (pr & 3) * 4);
+        float2 v = make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+        if (r >= nvalid) v = make_float2(0.f, 0.f);
+        a = __fadd2_rn(a, v);
+        b = __ffma2_rn(v, v, b);
+    }
+    a.x += __shfl_down_sync(0xffffffffu, a.x, 16);
+    a.y += __shfl_down_sync(0xffffffffu, a.y, 16);
+    b.x += __shfl_down_sync(0xffffffffu, b.x, 16);
+    b.y += __shfl_down_sync(0xffffffffu, b.y, 16);
+    if (lane < 16) {
+        const int c = 2 * pr;
         if (c < ncols) { ssum[c] += a.x; ssq[c] += b.x; }
         if (c + 1 < ncols) { ssum[c + 1] += a.y; ssq[c + 1] += b.y; }
     }

@@ -128,19 +128,25 @@ def layout_for(shape, kind=None):
 
 
 class DeviceTensor(object):
-    __slots__ = ('buf', 'shape', 'layout', 'ptr')
+    """`dtype` is 'f32' for everything except the bf16 tier's convolution output maps in front of a fused
+    BatchNormalization ('bf16': the map is written once and read twice, at half the bytes); host views
+    are float64 either way."""
+    __slots__ = ('buf', 'shape', 'layout', 'ptr', 'dtype')
 
-    def __init__(self, buf, shape, layout='flat'):
+    def __init__(self, buf, shape, layout='flat', dtype='f32'):
         self.buf = buf
         self.shape = tuple(int(s) for s in shape)
         self.layout = layout
         self.ptr = buf.data_ptr()
+        self.dtype = dtype
         assert buf.numel() == int(np.prod(self.shape)), (buf.numel(), self.shape)
 
     # ---- construction -------------------------------------------------
     @classmethod
-    def empty(cls, shape, layout=None):
+    def empty(cls, shape, layout=None, dtype='f32'):
         shape = tuple(int(s) for s in shape)
+        if dtype == 'bf16':
+            return cls(empty(int(np.prod(shape)), torch().bfloat16), shape, layout_for(shape, layout), 'bf16')
         return cls(empty(int(np.prod(shape))), shape, layout_for(shape, layout))
 
     @classmethod
@@ -160,6 +166,7 @@ class DeviceTensor(object):
         """Upload a logical-layout host array (any float dtype) into this buffer."""
         arr = np.asarray(arr)
         assert tuple(arr.shape) == self.shape, (arr.shape, self.shape)
+        assert self.dtype == 'f32', 'bf16 maps are written by kernels only'
         host = _to_storage(arr, self.layout)
         lib.sn_memcpy_h2d(self.ptr, host.ctypes.data, host.nbytes, current_stream())
         lib.sn_stream_sync(current_stream())        # `host` is pageable and about to be freed
@@ -167,6 +174,12 @@ class DeviceTensor(object):
     # ---- host views ----------------------------------------------------
     def numpy(self):
         """float64 array in the reference's layout (synchronises)."""
+        if self.dtype == 'bf16':
+            raw = np.empty(self.buf.numel(), dtype=np.uint16)
+            lib.sn_memcpy_d2h(raw.ctypes.data, self.ptr, raw.nbytes, current_stream())
+            lib.sn_stream_sync(current_stream())
+            host = (raw.astype(np.uint32) << 16).view(np.float32)
+            return _from_storage(host, self.shape, self.layout)
         host = np.empty(self.buf.numel(), dtype=np.float32)
         lib.sn_memcpy_d2h(host.ctypes.data, self.ptr, host.nbytes, current_stream())
         lib.sn_stream_sync(current_stream())
@@ -185,18 +198,19 @@ class DeviceTensor(object):
         return len(self.shape)
 
     def view(self, shape, layout='flat'):
-        return DeviceTensor(self.buf, shape, layout)
+        return DeviceTensor(self.buf, shape, layout, self.dtype)
 
     def zero_(self):
-        lib.sn_memset(self.ptr, 0, self.buf.numel() * 4, current_stream())
+        lib.sn_memset(self.ptr, 0, self.buf.numel() * self.buf.element_size(), current_stream())
         return self
 
     def copy_from(self, other):
-        assert other.buf.numel() == self.buf.numel()
-        lib.sn_memcpy_d2d(self.ptr, other.ptr, self.buf.numel() * 4, current_stream())
+        assert other.buf.numel() == self.buf.numel() and other.dtype == self.dtype
+        lib.sn_memcpy_d2d(self.ptr, other.ptr, self.buf.numel() * self.buf.element_size(), current_stream())
         return self
 
     def add_(self, other, alpha=1.0):
+        assert self.dtype == 'f32' and other.dtype == 'f32'
         lib.sn_axpy(float(alpha), other.ptr, self.ptr, self.buf.numel(), current_stream())
         return self
 
@@ -216,15 +230,20 @@ class Arena(object):
     gradients), so the optimizer is ONE kernel and the data-parallel all-reduce ONE call."""
     ALIGN = 32          # floats (128 bytes): TMA global addresses want >= 16-byte alignment
 
-    def __init__(self, sizes, extra=0):
+    @classmethod
+    def layout(cls, sizes, extra=0):
         offs, total = [], 0
         for s in sizes:
             offs.append(total)
-            total += (int(s) + self.ALIGN - 1) // self.ALIGN * self.ALIGN
-        self.offsets, self.param_floats = offs, total
-        self.total = total + extra
+            total += (int(s) + cls.ALIGN - 1) // cls.ALIGN * cls.ALIGN
+        return offs, total, total + extra
+
+    def __init__(self, sizes, extra=0, g_alloc=None):
+        """g_alloc(n) -> zero-filled float32 tensor: lets the gradient arena live in the data-parallel
+        communicator's peer-mapped window, where it is all-reduced in place (comm.py)."""
+        self.offsets, self.param_floats, self.total = self.layout(sizes, extra)
         self.w = zeros(self.total)
-        self.g = zeros(self.total)
+        self.g = g_alloc(self.total) if g_alloc is not None else zeros(self.total)
         self.v = None       # momentum velocity, allocated on demand
         self.gstep = None   # data-parallel Momentum: per-step gradients
 

