@@ -185,14 +185,17 @@ def kernel_work(name, a, precision):
     Returns (flops, bytes): the bytes are the tensors the operation must read and write once."""
     conv = ('sn_conv2d_fprop', 'sn_conv2d_dgrad', 'sn_conv2d_wgrad', 'sn_conv2d_fprop_bf16', 'sn_conv2d_dgrad_bf16',
             'sn_conv2d_wgrad_bf16', 'sn_conv2d_fprop_stats', 'sn_conv2d_fprop_bf16_stats', 'sn_conv2d_fprop_x3',
-            'sn_conv2d_dgrad_x3', 'sn_conv2d_wgrad_x3', 'sn_conv2d_fprop_bf16_stats_ybf16', 'sn_conv2d_fprop_stats_ybf16')
+            'sn_conv2d_dgrad_x3', 'sn_conv2d_wgrad_x3', 'sn_conv2d_fprop_bf16_stats_ybf16', 'sn_conv2d_fprop_stats_ybf16',
+            'sn_conv2d_stem_fprop')
     if name in conv:
         N, C, H, W, F, kh, kw, stride, ph, pw = a[:10]
         oh = (H + 2 * ph - kh) // stride + 1
         ow = (W + 2 * pw - kw) // stride + 1
         x, y, w = N * C * H * W, N * F * oh * ow, F * C * kh * kw
         flops = 2.0 * y * C * kh * kw
-        if name == 'sn_conv2d_fprop_stats_ybf16':
+        if name == 'sn_conv2d_stem_fprop':
+            byt = {'fprop': 4 * x + 4 * w + (2 if (len(a) > 11 and a[11]) else 4) * y}       # fp32 image and filters in, fp32 or bf16 map out
+        elif name == 'sn_conv2d_fprop_stats_ybf16':
             byt = {'fprop': 4 * x + 4 * w + 2 * y}              # the stem: fp32 image and filters in, bf16 map out
         elif name == 'sn_conv2d_fprop_bf16_stats_ybf16':
             byt = {'fprop': 2 * x + 2 * w + 2 * y}              # bf16 operand copies in, bf16 map out
@@ -240,6 +243,9 @@ def kernel_work(name, a, precision):
         return 0.0, 20.0 * a[0]
     if name == 'sn_adaptive_update':          # (kind, P): w r+w, g r, one (RMSprop, AdaGrad) or two (AdaDelta, Adam) state words r+w
         return 0.0, (28.0 if a[0] >= 2 else 20.0) * a[1]
+    if name == 'sn_conv2d_stem_prepare':
+        N, C, H, W = a[:4]
+        return 0.0, 4.0 * N * H * W * (C + 4)
     if name == 'sn_cast_f32_to_bf16':
         return 0.0, 6.0 * a[0]
     if name in ('sn_relu_bwd',):

@@ -252,6 +252,16 @@ SN_API int sn_conv2d_fprop_bf16_stats_ybf16(const void *x_bf16, const void *w_bf
 SN_API int sn_conv2d_fprop_stats_ybf16(const float *x, const float *w, const float *bias, void *y_bf16,
                                 int N, int C, int H, int W, int F, int kh, int kw,
                                 int stride, int pad_h, int pad_w, int act, double *bn_scratch, void *stream);
+/* Tiny-C convolutions (C <= 4, kh*kw <= 9, stride 1: the RGB stem) on the tensor pipe with the column matrix
+ * gathered by the TMA unit (cp.async.bulk.tensor im2col, csrc/conv_stem_im2col.cu); tf32 / bf16 tiers.
+ * The input must be held as NHWC4 (channels padded to 4): sn_conv2d_stem_prepare writes that copy
+ * (N*H*W*4 floats) from the NHWC map; fprop then reads x4.  y is fp32 or (y_bf16 != 0) bf16,
+ * bn_scratch (may be NULL) receives the per-channel sums of y like sn_conv2d_fprop_stats. */
+SN_API int sn_conv2d_stem_supported(int N, int C, int H, int W, int F, int kh, int kw, int stride, int pad_h, int pad_w);
+SN_API int sn_conv2d_stem_prepare(const float *x, float *x4, int N, int C, int H, int W, void *stream);
+SN_API int sn_conv2d_stem_fprop(const float *x4, const float *w, const float *bias, void *y,
+                         int N, int C, int H, int W, int F, int kh, int kw, int stride, int pad_h, int pad_w,
+                         int act, int y_bf16, double *bn_scratch, void *stream);
 SN_API int sn_conv2d_dgrad_bf16(const void *dy_bf16, const void *wt_bf16, float *dx,
                          int N, int C, int H, int W, int F, int kh, int kw,
                          int stride, int pad_h, int pad_w, int accumulate, void *stream);

@@ -28,6 +28,10 @@ int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, void *
                        int kw, int stride, int ph, int pw, int act, double *stats, cudaStream_t st, bool out_bf16 = false);
 int conv_stem_wgrad_tc(const float *x, const float *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh, int kw,
                        int stride, int ph, int pw, cudaStream_t st);
+bool stem_im2col_eligible(int N, int C, int H, int W, int F, int kh, int kw, int stride, int ph, int pw);
+int pad_channels4(const float *x, float *x4, long long npix, int C, cudaStream_t st);
+int conv_stem_im2col_fprop(const float *x4, const float *w, const float *bias, void *y, int N, int C, int H, int W, int F, int kh, int kw,
+                           int stride, int ph, int pw, int act, double *stats, cudaStream_t st, bool out_bf16);
 bool tiny_wgrad_eligible(int C, int kh, int kw, int F);
 int conv_wgrad_tiny(const float *x, const float *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh,
                     int kw, int stride, int ph, int pw, cudaStream_t st);
@@ -342,6 +346,28 @@ int sn_conv2d_wgrad_bf16(const void *x, const void *dy, const float *dy_f32, flo
     int e = conv_wgrad_halo_tc(x, dy, dw, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, true, as_stream(stream));
     if (e || !db || !dy_f32) return e;
     return colsum_accumulate(dy_f32, db, (long long)N * oh * ow, F, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------ tiny-C stem, TMA im2col
+int sn_conv2d_stem_supported(int N, int C, int H, int W, int F, int kh, int kw, int stride, int pad_h, int pad_w) {
+    if (N <= 0 || C <= 0 || F <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad_h < 0 || pad_w < 0 || H + 2 * pad_h < kh || W + 2 * pad_w < kw)
+        return 0;
+    const char *e = getenv("SN_STEM_IM2COL");
+    if (e && e[0] == '0') return 0;
+    return stem_im2col_eligible(N, C, H, W, F, kh, kw, stride, pad_h, pad_w) ? 1 : 0;
+}
+int sn_conv2d_stem_prepare(const float *x, float *x4, int N, int C, int H, int W, void *stream) {
+    SN_REQUIRE(x && x4 && N >= 0 && C >= 1 && C <= 4 && H > 0 && W > 0, "bad arguments");
+    SN_REQUIRE((((uintptr_t)x4) & 15) == 0, "x4 must be 16-byte aligned");
+    return pad_channels4(x, x4, (long long)N * H * W, C, as_stream(stream));
+}
+int sn_conv2d_stem_fprop(const float *x4, const float *w, const float *bias, void *y, int N, int C, int H, int W, int F, int kh, int kw,
+                         int stride, int pad_h, int pad_w, int act, int y_bf16, double *bn_scratch, void *stream) {
+    SN_REQUIRE(x4 && w && y, "null tensor");
+    SN_REQUIRE(act == SN_ACT_LINEAR || act == SN_ACT_RELU, "unknown activation");
+    SN_REQUIRE(sn_conv2d_stem_supported(N, C, H, W, F, kh, kw, stride, pad_h, pad_w), "shape not supported by the im2col stem kernels");
+    SN_REQUIRE(((((uintptr_t)x4) | ((uintptr_t)y) | ((uintptr_t)bias)) & 15) == 0, "misaligned tensor");
+    return conv_stem_im2col_fprop(x4, w, bias, y, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, act, bn_scratch, as_stream(stream), y_bf16 != 0);
 }
 
 // Dense is the H = W = kh = kw = 1 convolution: x[M][K] are M "pixels" of K channels.

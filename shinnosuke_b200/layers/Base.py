@@ -276,7 +276,7 @@ class Layer(object):
         # device handles and per-step hand-over flags of the layers (bf16 operand copies, 3xTF32 lo parts,
         # prepared filters, fused-pool outputs): none of them belongs in a checkpoint
         for k in ('_xb', '_bf16_support', '_x_lo', '_w_prepared', '_xb_filled_for', '_code', '_fused_output', '_stats_from',
-                  '_db_done', '_gb_ready', '_par'):
+                  '_db_done', '_gb_ready', '_par', '_x4'):
             d.pop(k, None)
         return d
 

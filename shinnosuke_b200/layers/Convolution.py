@@ -106,6 +106,10 @@ class Conv2D(Layer):
             self.output_tensor = y
             super(Conv2D, self).forward(is_training)
             return
+        self._x4 = None
+        if self.precision in ('tf32', 'bf16') and self._stem_ok(geom):
+            self._forward_stem(x, W, b, geom, is_training, st)
+            return
         bf16 = self.precision == 'bf16' and self._bf16_ok(0, geom)
         # the BatchNormalization fed by this layer alone takes its batch statistics from our epilogue
         bn = getattr(self, '_stats_to', None) if is_training else None
@@ -166,6 +170,38 @@ class Conv2D(Layer):
                                 PRECISION[self.precision], st)
         self.output_tensor = y
         super(Conv2D, self).forward(is_training)
+
+    def _stem_ok(self, geom):
+        key = ('stem',) + tuple(geom)
+        cache = self.__dict__.setdefault('_bf16_support', {})
+        if key not in cache:
+            cache[key] = bool(lib.load().sn_conv2d_stem_supported(*geom))
+        return cache[key]
+
+    def _forward_stem(self, x, W, b, geom, is_training, st):
+        """Tiny-C convolution (the RGB stem): csrc/conv_stem_im2col.cu — the TMA unit gathers the column
+        matrix (im2col mode) from an NHWC4 copy of the input, tcgen05 contracts it (TF32 products in both
+        tensor tiers: K = 27 is far too short for operand precision to matter for speed)."""
+        N, C, H, Wd, F = geom[:5]
+        oh, ow = self.output_shape[2:]
+        x4 = self._buf('x_nhwc4', (N * H * Wd * 4,), 'flat')
+        lib.sn_conv2d_stem_prepare(x.ptr, x4.ptr, N, C, H, Wd, st)
+        self._x4 = x4
+        bn = getattr(self, '_stats_to', None) if is_training else None
+        scratch = None
+        if bn is not None:
+            pow2 = F % 4 == 0 and (F // 4) & (F // 4 - 1) == 0 and F <= 1024     # what the BN apply kernels take
+            if pow2:
+                scratch = bn._device_stats(F)['scratch'].data_ptr()
+                bn._stats_from = self
+            else:
+                bn._stats_from = None
+        ybf16 = bool(scratch and self.precision == 'bf16' and bn._takes_bf16_map((N, F, oh, ow)) and F % 8 == 0
+                     and __import__('os').environ.get('SN_BF16_MAPS', '1') != '0')
+        y = self._buf('out', (N, F, oh, ow), 'nhwc', 'bf16' if ybf16 else 'f32')
+        lib.sn_conv2d_stem_fprop(x4.ptr, W.output_tensor.ptr, b.output_tensor.ptr, y.ptr, *geom, self._act_code(), int(ybf16), scratch, st)
+        self.output_tensor = y
+        Layer.forward(self, is_training)
 
     def _stats_ok(self, bf16, geom):
         key = ('stats', bool(bf16)) + tuple(geom)
