@@ -586,20 +586,26 @@ def run_micro(args):
         x = torch.randn(M * K, **f32); wt = torch.randn(Nout * K, **f32) * 0.05; b = torch.zeros(Nout, **f32)
         y = torch.empty(M * Nout, **f32); dy = torch.randn(M * Nout, **f32); dx = torch.empty(M * K, **f32)
         dw = torch.zeros(Nout * K, **f32); db = torch.zeros(Nout, **f32)
-        for prec_name, prec in (('tf32', 1), ('bf16', 2)):
-            tp = pk['bf16'] if prec_name == 'bf16' else pk['bf16'] / 2
-            ws_bytes = lib.load().sn_conv2d_dgrad_workspace(K, Nout, 1, 1, prec)
-            ws = torch.empty(max(1, ws_bytes // 4), **f32)
-            a = (M, K, Nout)
-            try:
-                timed('sn_dense_fprop', a, lambda: lib.sn_dense_fprop(x.data_ptr(), wt.data_ptr(), b.data_ptr(), y.data_ptr(), M, K, Nout, 1, prec, st),
-                      precision=prec_name, tensor_peak=tp)
-                timed('sn_dense_dgrad', a, lambda: lib.sn_dense_dgrad(dy.data_ptr(), wt.data_ptr(), dx.data_ptr(), M, K, Nout, 0, prec, ws.data_ptr(), st),
-                      precision=prec_name, tensor_peak=tp)
-                timed('sn_dense_wgrad', a, lambda: lib.sn_dense_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), M, K, Nout, 1, prec, st),
-                      precision=prec_name, tensor_peak=tp)
-            except Exception as e:          # a tier the Dense entry points do not take is reported, not hidden
-                rows.append(dict(kernel='sn_dense_*', args=list(a), precision=prec_name, error=str(e)[:200]))
+        ws_bytes = lib.load().sn_conv2d_dgrad_workspace(K, Nout, 1, 1, 1)
+        ws = torch.empty(max(1, ws_bytes // 4), **f32)
+        a = (M, K, Nout)
+        tp = pk['bf16'] / 2
+        timed('sn_dense_fprop', a, lambda: lib.sn_dense_fprop(x.data_ptr(), wt.data_ptr(), b.data_ptr(), y.data_ptr(), M, K, Nout, 1, 1, st),
+              precision='tf32', tensor_peak=tp)
+        timed('sn_dense_dgrad', a, lambda: lib.sn_dense_dgrad(dy.data_ptr(), wt.data_ptr(), dx.data_ptr(), M, K, Nout, 0, 1, ws.data_ptr(), st),
+              precision='tf32', tensor_peak=tp)
+        timed('sn_dense_wgrad', a, lambda: lib.sn_dense_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), M, K, Nout, 1, 1, st),
+              precision='tf32', tensor_peak=tp, note='K = 784 is 24.5 TMA boxes: ragged tail zero-filled, tcgen05 kind::tf32')
+        # bf16 tier: what layers/FC.py runs — bf16 operand copies through the 1x1 case of the implicit-GEMM kernels
+        xb = x.to(torch.bfloat16); wb = wt.to(torch.bfloat16); dyb = dy.to(torch.bfloat16)
+        wtb = torch.empty(Nout * K, dtype=torch.bfloat16, device='cuda')
+        lib.sn_flip_transpose_filters_bf16(wt.data_ptr(), wtb.data_ptr(), Nout, K, 1, 1, st)
+        g = (M, K, 1, 1, Nout, 1, 1, 1, 0, 0)
+        timed('sn_conv2d_fprop_bf16', g, lambda: lib.sn_conv2d_fprop_bf16(xb.data_ptr(), wb.data_ptr(), b.data_ptr(), y.data_ptr(), *g, 1, st),
+              precision='bf16', tensor_peak=pk['bf16'], note='Dense fprop, bf16 tier')
+        timed('sn_conv2d_dgrad_bf16', g, lambda: lib.sn_conv2d_dgrad_bf16(dyb.data_ptr(), wtb.data_ptr(), dx.data_ptr(), *g, 0, st),
+              precision='bf16', tensor_peak=pk['bf16'], note='Dense dX, bf16 tier')
+        del xb, wb, dyb, wtb
         del x, wt, y, dy, dx, dw
     out = dict(micro=True, peaks=pk, rows=rows)
     print(json.dumps(out))

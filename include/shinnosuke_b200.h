@@ -88,6 +88,9 @@ SN_API int sn_event_elapsed_ms(void *start, void *stop, float *ms);   /* synchro
 /* number of kernels this library launched since the last reset (bench "gpu_launches") */
 SN_API long long sn_launch_count(void);
 SN_API void      sn_launch_count_reset(void);
+/* name of the kernel the most recent launch of this library started (tests use it to see which kernel family a
+ * shape was routed to, e.g. that a ragged-K Dense weight gradient stays on the tensor pipe) */
+SN_API const char *sn_last_kernel(void);
 /* how many of those were CTA-pair (cta_group::2) launches of the implicit-GEMM kernel: the pair tiles
  * are chosen by shape (SN_IGEMM_PAIR=0 never, =2 whenever eligible), tests use this to see which ran */
 SN_API long long sn_igemm_pair_launches(void);

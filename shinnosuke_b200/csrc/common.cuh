@@ -11,6 +11,7 @@ namespace sn {
 
 void set_error(const char *fmt, ...);
 extern long long g_launch_count;
+extern const char *g_last_kernel;
 
 inline int check_cuda(cudaError_t e, const char *what) {
     if (e != cudaSuccess) {
@@ -23,6 +24,7 @@ inline int check_cuda(cudaError_t e, const char *what) {
 // Called after every kernel launch: counts it and surfaces launch-configuration errors.
 inline int after_launch(const char *name) {
     ++g_launch_count;
+    g_last_kernel = name;
     return check_cuda(cudaPeekAtLastError(), name);
 }
 

@@ -912,7 +912,9 @@ int conv_igemm_tc(const void *x, const void *w, const float *bias, void *out_any
 }
 
 bool wgrad_tc_eligible(int N, int C, int OH, int OW, int F, int stride) {
-    if (stride != 1 || (C & 31) || (F & 3)) return false;
+    // C need not be a multiple of the 32-channel TMA box: the box that straddles the end of the tensor is
+    // zero-filled by the TMA and the epilogue skips those columns (Dense 784 -> 500: K = 784 = 24.5 boxes)
+    if (stride != 1 || (C & 3) || C < 32 || (F & 3)) return false;
     if (OW <= 0 || OW > PB || (PB % OW)) return false;
     const int S = OH * OW;
     if (S >= PB ? (S % PB) != 0 : (PB % S) != 0) return false;
@@ -928,10 +930,11 @@ int conv_wgrad_tc(const float *x, const float *dy, float *dw, int N, int C, int 
     const long long P = (long long)N * S;
     const int TAPS = (kh * kw) % 3 == 0 ? 3 : 1;
     int CN = (C % 256 == 0) ? 256 : ((C % 128 == 0) ? 128 : ((C % 64 == 0) ? 64 : 32));
+    if (C % 32) CN = C >= 128 ? 128 : (C >= 64 ? 64 : 32);       // ragged channel count: the last tile hangs over (zero-filled)
     if (TAPS == 3 && CN > 128) CN = 128;                  // 3 accumulators of CN columns must fit the 512 TMEM columns
     WgradParams p{};
     p.dw = dw; p.F = F; p.C = C; p.ntaps = kh * kw; p.taps_w = kw;
-    p.c_tiles = C / CN; p.f_tiles = (F + 127) / 128;
+    p.c_tiles = (C + CN - 1) / CN; p.f_tiles = (F + 127) / 128;
     p.pblocks = (int)((P + PB - 1) / PB);
     int items = p.f_tiles * p.c_tiles * (p.ntaps / TAPS);
     int splits = num_sms() / items;

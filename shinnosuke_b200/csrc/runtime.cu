@@ -5,6 +5,7 @@
 namespace sn {
 static thread_local char g_err[512] = "";
 long long g_launch_count = 0;
+const char *g_last_kernel = "";
 extern long long g_igemm_pair_launches;      // conv_tc.cu
 extern int g_igemm_pair_mode;
 void set_error(const char *fmt, ...) {
@@ -21,6 +22,7 @@ extern "C" {
 int sn_abi_version(void) { return SN_ABI_VERSION; }
 const char *sn_last_error(void) { return g_err; }
 long long sn_launch_count(void) { return g_launch_count; }
+const char *sn_last_kernel(void) { return g_last_kernel; }
 void sn_launch_count_reset(void) { g_launch_count = 0; }
 long long sn_igemm_pair_launches(void) { return g_igemm_pair_launches; }
 int sn_igemm_set_pair_mode(int mode) {

@@ -137,6 +137,22 @@ class Dense(Layer):
         assert Wv.output_shape[0] == c * h * w
         Wv.relayout(('dense_w_hwc', c, h, w))
 
+    def _bf16_ok(self, op, M, K):
+        key = (op, M, K)
+        cache = self.__dict__.setdefault('_bf16_support', {})
+        if key not in cache:
+            cache[key] = bool(lib.load().sn_conv2d_bf16_supported(op, M, K, 1, 1, self.n_out, 1, 1, 1, 0, 0))
+        return cache[key]
+
+    def _bf16_buf(self, name, n):
+        from ..device import empty, torch
+        key = (name, int(n))
+        t = self._bufs.get(key)
+        if t is None:
+            t = empty(int(n), torch().bfloat16)
+            self._bufs[key] = t
+        return t
+
     def _head(self, M, K):
         return self._act_name() in ('linear', 'softmax') and bool(lib.load().sn_dense_head_supported(M, K, self.n_out))
 
@@ -163,8 +179,20 @@ class Dense(Layer):
             super(Dense, self).forward(is_training)
             return
         z = self._buf('out', (M, self.n_out), 'flat')
-        lib.sn_dense_fprop(x.ptr, W.output_tensor.ptr, b.output_tensor.ptr, z.ptr, M, K, self.n_out,
-                           ACT['relu'] if act == 'relu' else ACT['linear'], PRECISION[self.precision], st)
+        act_code = ACT['relu'] if act == 'relu' else ACT['linear']
+        self._xb = None
+        if self.precision == 'bf16' and self._bf16_ok(0, M, K):
+            # bf16 tier: Dense is the 1x1 convolution on bf16 operand copies (tcgen05 kind::f16, fp32 accumulation);
+            # K need not be a multiple of the 64-element TMA box (the tail is zero-filled)
+            self._xb = self._bf16_buf('x_bf16', x.size)
+            wb = self._bf16_buf('w_bf16', W.size)
+            lib.sn_cast_f32_to_bf16(x.ptr, self._xb.data_ptr(), x.size, st)
+            lib.sn_cast_f32_to_bf16(W.output_tensor.ptr, wb.data_ptr(), W.size, st)
+            lib.sn_conv2d_fprop_bf16(self._xb.data_ptr(), wb.data_ptr(), b.output_tensor.ptr, z.ptr, M, K, 1, 1, self.n_out, 1, 1, 1, 0, 0,
+                                     act_code, st)
+        else:
+            lib.sn_dense_fprop(x.ptr, W.output_tensor.ptr, b.output_tensor.ptr, z.ptr, M, K, self.n_out, act_code,
+                               PRECISION[self.precision], st)
         if act == 'softmax':
             p = self._buf('probs', (M, self.n_out), 'flat')
             lib.sn_softmax_fwd(z.ptr, p.ptr, M, self.n_out, st)
@@ -202,6 +230,17 @@ class Dense(Layer):
         if W.require_grads or b.require_grads:
             lib.sn_dense_wgrad(x.ptr, g.ptr, W.grads.ptr, b.grads.ptr if b.require_grads else None,
                                M, K, self.n_out, 1, prec, st)
+        if not any(layer.require_grads for layer in self.inbounds):
+            return
+        if self.precision == 'bf16' and self._bf16_ok(1, M, K):
+            gb = self._bf16_buf('dy_bf16', g.size)
+            wtb = self._bf16_buf('wt_bf16', W.size)
+            lib.sn_cast_f32_to_bf16(g.ptr, gb.data_ptr(), g.size, st)
+            lib.sn_flip_transpose_filters_bf16(W.output_tensor.ptr, wtb.data_ptr(), self.n_out, K, 1, 1, st)
+            for layer in self.inbounds:
+                self._push_grad(layer, lambda dst, acc: lib.sn_conv2d_dgrad_bf16(
+                    gb.data_ptr(), wtb.data_ptr(), dst.ptr, M, K, 1, 1, self.n_out, 1, 1, 1, 0, 0, acc, st))
+            return
         ws_bytes = lib.sn_conv2d_dgrad_workspace(K, self.n_out, 1, 1, prec)
         ws = self._buf('dgrad_ws', (ws_bytes // 4,), 'flat').ptr if ws_bytes else None
         for layer in self.inbounds:

@@ -107,11 +107,17 @@ def test_tf32_path_is_really_taken_and_exact_on_tf32_representable_data():
     assert rel_err(np.asarray(layer.variables[1].grads).reshape(-1), db_ref) < 1e-6
 
 
-@pytest.mark.parametrize('mkn', [(512, 1024, 10), (128, 784, 500), (256, 512, 256), (130, 72, 66)])
-def test_dense_tf32_vs_oracle(mkn):
+@pytest.mark.parametrize('precision', ['tf32', 'bf16'])
+@pytest.mark.parametrize('mkn', [(512, 1024, 10), (128, 784, 500), (256, 512, 256), (130, 72, 66), (8192, 784, 500)])
+def test_dense_tf32_vs_oracle(mkn, precision):
+    """Dense on the tensor tiers: the 1x1 case of the implicit-GEMM kernels, bf16 operand copies in the bf16 tier;
+    K = 784 is not a multiple of the 32- / 64-element TMA box (zero-filled tail) in fprop, dX and — since the
+    contraction kernels take ragged channel counts — dW as well (config 2's layer at large M)."""
     from shinnosuke_b200 import Dense, Input, Activation
     from shinnosuke_b200.device import as_device
+    from shinnosuke_b200._lib import lib
     M, K, Nout = mkn
+    TOL_TF32 = {'tf32': 2e-3, 'bf16': 1e-2}[precision]
     r = np.random.default_rng(M + K)
     x = r.standard_normal((M, K)).astype(np.float32).astype(np.float64)
     w = (0.1 * r.standard_normal((K, Nout))).astype(np.float32).astype(np.float64)
@@ -120,16 +126,29 @@ def test_dense_tf32_vs_oracle(mkn):
     y_ref, cache = O.dense_forward(x, w, b, 'relu')
     layer = Dense(Nout, activation='relu')
     inp = Input((None, K)); src = Activation('linear')(inp); layer(src)
-    layer.precision = 'tf32'
+    layer.precision = precision
     set_params(layer, w, b)
     inp.input_tensor = x
     for l in (inp, src, layer):
         l.forward(True)
     y = np.asarray(layer.output_tensor)
     assert rel_err(y, y_ref) < TOL_TF32
+    if precision == 'bf16' and mkn in ((128, 784, 500), (8192, 784, 500), (256, 512, 256)):
+        assert layer._xb is not None, 'the bf16 tier did not take the bf16 operand path'
     cache['z'] = np.where(np.signbit(y), -1.0, 1.0)       # device mask, see _run_conv
     dx_ref, dw_ref, db_ref = O.dense_backward(gup, cache)
+    lib.start_profiling()
     layer._seed_grads(as_device(gup)); layer.backward()
+    names = [k[0] for k in lib.stop_profiling()]
+    assert 'sn_dense_wgrad' in names or 'sn_dense_head_bwd' in names
+    if mkn[1:] == (784, 500):
+        # config 2's layer: K = 784 is 24.5 TMA boxes wide; the weight gradient must not fall back to the CUDA-core kernel
+        xd = as_device(x)
+        dwt = np.zeros((K, Nout))
+        from shinnosuke_b200.device import DeviceTensor
+        dw_dev = DeviceTensor.zeros((K, Nout), 'dense_w')
+        lib.sn_dense_wgrad(xd.ptr, as_device(gup).ptr, dw_dev.ptr, None, M, K, Nout, 1, 1, __import__('shinnosuke_b200.device', fromlist=['current_stream']).current_stream())
+        assert lib.load().sn_last_kernel() in (b'conv_wgrad_kernel', b'colsum_accumulate'), lib.load().sn_last_kernel()
     assert rel_err(np.asarray(layer.variables[0].grads), dw_ref) < TOL_TF32
     assert rel_err(np.asarray(layer.variables[1].grads), db_ref) < TOL_TF32
     assert rel_err(np.asarray(src.grads), dx_ref) < TOL_TF32
