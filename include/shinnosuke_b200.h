@@ -129,6 +129,10 @@ SN_API int sn_comm_ipc_handle(void *comm, void *handle64);
 SN_API int sn_comm_connect(void *comm, const void *handles /* world x 64 bytes, rank order */);
 SN_API int sn_comm_init_all(int ndev, size_t user_bytes, void **comms);
 SN_API int sn_comm_destroy(void *comm);
+/* Waits inside the exchange kernels give up after 20 s (a replica that died must not hang the others' GPUs): the
+ * number of such give-ups of this communicator since the last reset; non-zero means the results are invalid.
+ * Synchronises the device. */
+SN_API int sn_comm_timeouts(void *comm, long long *count, int reset);
 /* buf (+)= sum over ranks, in place, asynchronous on `stream` (graph-capturable).  Tensors inside the
  * window larger than 64 KB: two-shot (pull own slice from every peer, push the sum to every peer);
  * tensors of at most 256 KB anywhere: one-shot through per-rank staging slots; anything else is

@@ -122,6 +122,11 @@ class _Lib(object):
         self._dll = dll
         return dll
 
+    def comm_timeouts(self, comm_handle, reset=True):
+        n = ctypes.c_longlong(0)
+        self.sn_comm_timeouts(comm_handle, ctypes.byref(n), 1 if reset else 0)
+        return int(n.value)
+
     def embedding_oob_count(self, reset=True):
         n = ctypes.c_longlong(0)
         self.sn_embedding_oob_count(ctypes.byref(n), 1 if reset else 0)

@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(32) bn_finalize_dp_kernel(comm::DevComm dc, do
         for (int p = 0; p < MAX_RANKS; ++p)
             if (p < dc.world) {
                 double va, vb;
-                ll_load_f64x2(mine + (size_t)p * LL_SLOT_BYTES, va, vb, seq);
+                ll_load_f64x2(mine + (size_t)p * LL_SLOT_BYTES, va, vb, seq, dc.state);
                 if (p == 0) { sa = va; sb = vb; } else { sa += va; sb += vb; }
             }
         bn_finalize_one(bn_params(scratch, C), fin, in, c, sa, sb, bn_inv_rows(fin.rows));

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(INPLACE_THREADS) allreduce_inplace_kernel(DevT
     pdl_wait();
     const unsigned seq = *reinterpret_cast<volatile unsigned *>(&state[0]) + 1u;
     // entry: every rank's backward pass has finished writing its gradients (stream order on each rank)
-    cta_exchange_flags(t, flag_off, 0, rank, world, seq);
+    cta_exchange_flags(t, flag_off, 0, rank, world, seq, state);
     // slice of this rank, in vectors; the ragged tail (n % VN elements) belongs to the last rank
     const long long nv = n / VN;
     const long long per = (nv + world - 1) / world;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(INPLACE_THREADS) allreduce_inplace_kernel(DevT
         }
     }
     // exit: every rank has pushed its slice into every window
-    cta_exchange_flags(t, flag_off, 1, rank, world, seq);
+    cta_exchange_flags(t, flag_off, 1, rank, world, seq, state);
     if constexpr (SGD) {
         float4 *g4 = reinterpret_cast<float4 *>(t.win[rank] + off), *w4 = reinterpret_cast<float4 *>(w);
         const long long nu = n_update / 4;
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(CTA_THREADS) allreduce_oneshot_kernel(DevTable
             const T v = buf[i];
             for (int p = 0; p < world; ++p) reinterpret_cast<T *>(t.win[p] + slot0 + (size_t)rank * STAGE_SLOT_BYTES)[i] = v;
         }
-    cta_exchange_flags(t, flag_off, 2, rank, world, seq);
+    cta_exchange_flags(t, flag_off, 2, rank, world, seq, state);
     const char *mine = t.win[rank] + slot0;
     if (vec_ok) {
         for (long long i = v0 + threadIdx.x; i < v1; i += blockDim.x) {
@@ -237,8 +237,8 @@ int comm_alloc(Comm *c, size_t user_bytes) {
     c->lay = window_layout(user_bytes);
     SN_CUDA(cudaMalloc(&c->local, c->lay.total));
     SN_CUDA(cudaMemset(c->local, 0, c->lay.total));
-    SN_CUDA(cudaMalloc(&c->state, 2 * sizeof(unsigned)));
-    SN_CUDA(cudaMemset(c->state, 0, 2 * sizeof(unsigned)));
+    SN_CUDA(cudaMalloc(&c->state, 4 * sizeof(unsigned)));
+    SN_CUDA(cudaMemset(c->state, 0, 4 * sizeof(unsigned)));
     SN_CUDA(cudaDeviceSynchronize());
     return SN_OK;
 }
@@ -342,6 +342,16 @@ int sn_comm_destroy(void *comm) {
     cudaSetDevice(prev);
     cudaGetLastError();
     delete c;
+    return SN_OK;
+}
+
+int sn_comm_timeouts(void *comm, long long *count, int reset) {
+    SN_REQUIRE(comm && count, "null argument");
+    Comm *c = static_cast<Comm *>(comm);
+    unsigned v = 0;
+    SN_CUDA(cudaMemcpy(&v, c->state + 2, sizeof(v), cudaMemcpyDeviceToHost));
+    *count = (long long)v;
+    if (reset && v) SN_CUDA(cudaMemset(c->state + 2, 0, sizeof(v)));
     return SN_OK;
 }
 

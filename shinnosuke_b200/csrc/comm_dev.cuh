@@ -45,6 +45,31 @@ struct Comm {
     bool connected;
 };
 
+// A replica that never arrives (its host thread / process died) must not hang the GPUs of the others for ever:
+// every wait gives up after SPIN_TIMEOUT_NS, counts the event (sn_comm_timeouts, checked by fit() at the end of
+// every epoch) and lets the kernel finish with whatever it has.
+constexpr unsigned long long SPIN_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct SpinGuard {
+    unsigned *counter;             // state[2] of the communicator: give-ups since the last sn_comm_timeouts(reset)
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    __device__ __forceinline__ explicit SpinGuard(unsigned *c) : counter(c) {}
+    __device__ __forceinline__ bool expired() {
+        if (++spins < 4096u) return false;
+        spins = 0;
+        const unsigned long long now = global_ns();
+        if (!t0) { t0 = now; return false; }
+        if (now - t0 < SPIN_TIMEOUT_NS) return false;
+        if (counter) atomicAdd(counter, 1u);
+        return true;
+    }
+};
+
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -60,7 +85,7 @@ __device__ __forceinline__ unsigned *flag_ptr(char *win, size_t flag_off, int ph
 // all threads of the CTA: tell every rank's CTA `blockIdx.x` that this rank reached `phase` of exchange
 // `seq`, then wait until every rank's CTA `blockIdx.x` has said the same.  Everything this CTA wrote
 // before the call is visible to the peers after their wait (CTA barrier, then a system-scope release).
-__device__ __forceinline__ void cta_exchange_flags(const DevTable &t, size_t flag_off, int phase, int rank, int world, unsigned seq) {
+__device__ __forceinline__ void cta_exchange_flags(const DevTable &t, size_t flag_off, int phase, int rank, int world, unsigned seq, unsigned *state) {
     __syncthreads();
     if ((int)threadIdx.x < world) {
         const int peer = threadIdx.x;
@@ -68,7 +93,8 @@ __device__ __forceinline__ void cta_exchange_flags(const DevTable &t, size_t fla
         // (a separate __threadfence_system() in front of it cost a second round trip to the farthest peer)
         st_release_sys(flag_ptr(t.win[peer], flag_off, phase, rank, blockIdx.x), seq);
         const unsigned *mine = flag_ptr(t.win[rank], flag_off, phase, peer, blockIdx.x);
-        while ((int)(ld_acquire_sys(mine) - seq) < 0) { }
+        SpinGuard guard(state + 2);
+        while ((int)(ld_acquire_sys(mine) - seq) < 0) { if (guard.expired()) break; }
     }
     __syncthreads();
 }
@@ -92,11 +118,12 @@ __device__ __forceinline__ void finish_exchange(unsigned *state, unsigned seq) {
 __device__ __forceinline__ void ll_store(void *dst, unsigned data, unsigned seq) {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(data), "r"(seq) : "memory");
 }
-__device__ __forceinline__ unsigned ll_load(const void *src, unsigned seq) {
+__device__ __forceinline__ unsigned ll_load(const void *src, unsigned seq, unsigned *state) {
     unsigned d, f;
+    SpinGuard guard(state + 2);
     do {
         asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(d), "=r"(f) : "l"(src) : "memory");
-    } while (f != seq);
+    } while (f != seq && !guard.expired());
     return d;
 }
 __device__ __forceinline__ void ll_store_f64x2(char *dst, double a, double b, unsigned seq) {
@@ -106,8 +133,8 @@ __device__ __forceinline__ void ll_store_f64x2(char *dst, double a, double b, un
     ll_store(dst + 16, (unsigned)ub, seq);
     ll_store(dst + 24, (unsigned)(ub >> 32), seq);
 }
-__device__ __forceinline__ void ll_load_f64x2(const char *src, double &a, double &b, unsigned seq) {
-    const unsigned a0 = ll_load(src, seq), a1 = ll_load(src + 8, seq), b0 = ll_load(src + 16, seq), b1 = ll_load(src + 24, seq);
+__device__ __forceinline__ void ll_load_f64x2(const char *src, double &a, double &b, unsigned seq, unsigned *state) {
+    const unsigned a0 = ll_load(src, seq, state), a1 = ll_load(src + 8, seq, state), b0 = ll_load(src + 16, seq, state), b1 = ll_load(src + 24, seq, state);
     a = __longlong_as_double((long long)(((unsigned long long)a1 << 32) | a0));
     b = __longlong_as_double((long long)(((unsigned long long)b1 << 32) | b0));
 }

@@ -55,6 +55,14 @@ inline int num_sms() {
     return sms;
 }
 
+// cudaFuncSetAttribute (dynamic shared memory above 48 KB) is per DEVICE: one process may drive several
+// (fit(n_gpus=...), sn_comm_init_all), so "already configured" is remembered per device ordinal.
+inline int current_device_slot() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+    return d & 15;
+}
+
 // grid for a grid-stride elementwise kernel: enough CTAs for `work` items, capped at a
 // multiple of the SM count (148 on B200) so the last wave is full.
 inline int grid_for(long long work, int block, int ctas_per_sm = 8) {

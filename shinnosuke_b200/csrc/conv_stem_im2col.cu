@@ -620,7 +620,8 @@ int launch_fprop(const float *x4, void *y, const Im2colP &p, cudaStream_t st) {
     int obox[2] = {BN >= 32 ? 32 : 16, 32};
     e = OBF16 ? make_tmap_bf16_sw64(&tmO, y, 2, odims, ostr, obox) : make_tmap_f32(&tmO, y, 2, odims, ostr, obox);
     if (e) return e;
-    static bool configured = false;
+    static bool configured_dev[16] = {};
+    bool &configured = configured_dev[current_device_slot()];
     if (!configured) {
         SN_CUDA(cudaFuncSetAttribute(stem_im2col_fprop_kernel<BN, OBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
@@ -665,7 +666,8 @@ int launch_rows_fprop(const float *x4, void *y, RowsP &rp, cudaStream_t st) {
     if (obox[0] > BN) obox[0] = BN;
     e = OBF16 ? make_tmap(&tmO, y, 2, odims, ostr, obox, false, true) : make_tmap_f32(&tmO, y, 2, odims, ostr, obox);
     if (e) return e;
-    static int configured = 0;
+    static int configured_dev[16] = {};
+    int &configured = configured_dev[current_device_slot()];
     if (configured < smem) {
         SN_CUDA(cudaFuncSetAttribute(stem_rows_fprop_kernel<BN, OBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;

@@ -511,7 +511,8 @@ int launch_stem_fprop(const StemP &p, cudaStream_t st) {
     int obox[2] = {32, 32};
     int e = OBF16 ? make_tmap_bf16_sw64(&tmO, p.y, 2, odims, ostr, obox) : make_tmap_f32(&tmO, p.y, 2, odims, ostr, obox);
     if (e) return e;
-    static bool configured = false;
+    static bool configured_dev[16] = {};
+    bool &configured = configured_dev[current_device_slot()];
     if (!configured) {
         SN_CUDA(cudaFuncSetAttribute(stem_fprop_kernel<BN, OBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
@@ -587,7 +588,8 @@ int conv_stem_wgrad_tc(const float *x, const float *dy, float *dw, float *db, in
     if (e) return e;
     e = make_patch_tmap(&tmXr, p, p.R64);
     if (e) return e;
-    static bool configured[2] = {false, false};
+    static bool configured_dev[16][2] = {};
+    bool (&configured)[2] = configured_dev[current_device_slot()];
     if (!configured[na2]) {
         if (na2) SN_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         else SN_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

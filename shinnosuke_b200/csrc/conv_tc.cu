@@ -730,7 +730,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 template <int CN, int TAPS>
 int launch_wgrad(const CUtensorMap &tmDY, const CUtensorMap &tmX, const WgradParams &p, cudaStream_t st) {
     using Cfg = WgradCfg<CN, TAPS>;
-    static bool configured = false;
+    static bool configured_dev[16] = {};
+    bool &configured = configured_dev[current_device_slot()];
     if (!configured) {
         SN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<CN, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
@@ -765,7 +766,8 @@ bool tile_geometry(int N, int OH, int OW, TileGeom &g) {
 template <int BN, int KS, bool BF16, bool OBF16 = false>
 int launch_igemm_ks(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO, const IgemmParams &p, cudaStream_t st) {
     using Cfg = IgemmCfg<BN, KS>;
-    static bool configured = false;
+    static bool configured_dev[16] = {};
+    bool &configured = configured_dev[current_device_slot()];
     if (!configured) {
         SN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, KS, BF16, false, OBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
@@ -779,7 +781,8 @@ int launch_igemm_ks(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtens
 template <int BN, bool BF16, bool OBF16 = false>
 int launch_igemm_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO, const IgemmParams &p, cudaStream_t st) {
     using Cfg = IgemmCfg<BN, 1, true>;
-    static bool configured = false;
+    static bool configured_dev[16] = {};
+    bool &configured = configured_dev[current_device_slot()];
     if (!configured) {
         SN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, 1, BF16, true, OBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;

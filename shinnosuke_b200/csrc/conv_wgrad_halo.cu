@@ -211,7 +211,8 @@ int cn_for(int C, int kw) {
 
 template <int CN, bool BF16>
 int launch_halo(const CUtensorMap &tmDY, const CUtensorMap &tmX, const HaloP &p, int grid, int smem, cudaStream_t st) {
-    static int configured = 0;
+    static int configured_dev[16] = {};
+    int &configured = configured_dev[current_device_slot()];
     if (configured < smem) {
         SN_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel<CN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;

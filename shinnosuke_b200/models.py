@@ -80,6 +80,7 @@ class _Trainer(object):
         self._split = None
         self._comm_stream = None
         self._par = None            # data-parallel context (comm.Parallel), created with the arena
+        self._replicas = None       # fit(n_gpus=G): this model and its G - 1 copies on the other devices
         self._cap_stream = None
         self._bf16_shadow = None
         self._prep_tasks = {}
@@ -481,15 +482,82 @@ class _Trainer(object):
             res['metrics'] = t.zeros((n_batches, 2), dtype=t.float32).pin_memory()
         return res
 
+    # ---- fit(n_gpus=G): one process, G replicas -----------------------------------------
+    def _fit_replicated(self, n_gpus, X, Y, batch_size, epochs, shuffle, validation_data, validation_ratio, verbose):
+        """models.py fit() sharding each minibatch over the GPUs of the box BY ITSELF: replica r lives on device r
+        and is driven by its own host thread through the ordinary fit() loop (rank r's rows of every minibatch, its
+        own copy stream, pinned staging and captured step graph); the replicas meet only inside the exchange kernels
+        of csrc/comm.cu (peer access between the devices of this process, sn_comm_init_all).  Threads, not a
+        sequential loop over devices: a replica's first step allocates buffers and loads kernels while another
+        replica's exchange kernel is already spinning for it, and nothing on the host may wait in between."""
+        import copy
+        import threading
+        t = require_cuda()
+        if _dist() is not None and _dist().get_world_size() > 1:
+            raise RuntimeError('fit(n_gpus=...) drives all GPUs from this process; under torchrun every rank already owns one')
+        have = t.cuda.device_count()
+        if n_gpus > have:
+            raise ValueError('fit(n_gpus=%d): only %d CUDA devices are visible' % (n_gpus, have))
+        if n_gpus > 8:
+            raise ValueError('fit(n_gpus=...): at most 8 replicas (one NVLink / NVSwitch box)')
+        reps = getattr(self, '_replicas', None)
+        if reps is None or len(reps) != n_gpus:
+            # (re)build the replicas from the host state of this model
+            if self._arena is not None:
+                self._sync_to_host()
+                self._drop_device_state()
+            self._replicas = None
+            tv = [v for v in self.trainable_variables if isinstance(v, Variable)]
+            _, _, total = Arena.layout([v.size for v in tv], Arena.ALIGN)
+            pars = Parallel.init_all(n_gpus, total)
+            reps = [self] + [copy.deepcopy(self) for _ in range(n_gpus - 1)]
+            for r, rep in enumerate(reps):
+                rep._par = pars[r]
+                rep._replicas = None
+                with t.cuda.device(r):
+                    rep._materialize()
+            for r in range(1, n_gpus):                   # identical initial weights (they are: same host values; made explicit)
+                reps[r]._arena.w.copy_(reps[0]._arena.w)
+            for r in range(n_gpus):
+                t.cuda.synchronize(r)
+            self._replicas = reps
+        # the reference draws each epoch's permutation from the GLOBAL NumPy stream (utils/MiniBatch.py:7-8): drawn
+        # once here, in order, and handed to every replica (threads must not race on that stream)
+        X = np.asarray(X)
+        m_train = X.shape[0]
+        if validation_data is None and 0. < validation_ratio < 1.:
+            m_train = X.shape[0] - int(X.shape[0] * validation_ratio)
+        perms = [batch_permutation(m_train, epoch, shuffle) for epoch in range(epochs)]
+        errors = []
+
+        def run(r, rep):
+            try:
+                t.cuda.set_device(r)
+                rep.fit(X, Y, batch_size=batch_size, epochs=epochs, shuffle=shuffle, validation_data=validation_data,
+                        validation_ratio=validation_ratio, verbose=verbose if r == 0 else 0, _perms=perms)
+            except BaseException as e:          # noqa: B902 — re-raised in the caller's thread
+                errors.append(e)
+        threads = [threading.Thread(target=run, args=(r, rep), daemon=True) for r, rep in enumerate(reps)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
+
     def fit(self, X, Y, batch_size=64, epochs=20, shuffle=True, validation_data=None, validation_ratio=0.1,
-            draw_acc_loss=False, draw_save_path=None, verbose=1):
-        """The reference's minibatch loop (models.py:62-118) as a three-stage pipeline:
+            draw_acc_loss=False, draw_save_path=None, verbose=1, n_gpus=None, _perms=None):
+        """The reference's minibatch loop (models.py:62-118).  n_gpus=G (> 1) shards every minibatch over G GPUs of
+        this box from this one process (see _fit_replicated; under torchrun each rank is a replica already and
+        n_gpus is not needed).  Per replica the loop is a three-stage pipeline:
         a host thread gathers minibatch i+1.. (get_batches' permutation order) into pinned
         staging; a copy stream moves it host->device and transposes NCHW->NHWC into one of two
         device input buffers; the compute stream replays the captured step graph and copies the
         (loss, acc) pair back.  Nothing in the loop blocks on the device except ring reuse."""
         if draw_acc_loss:
             raise NotImplementedError('live matplotlib plotting is out of scope of the device path')
+        if n_gpus is not None and int(n_gpus) > 1 and _perms is None:
+            return self._fit_replicated(int(n_gpus), X, Y, batch_size, epochs, shuffle, validation_data, validation_ratio, verbose)
         import queue
         import threading
         t = require_cuda()
@@ -583,7 +651,8 @@ class _Trainer(object):
         step_no = 0
         try:
             for epoch in range(epochs):
-                perm = batch_permutation(m, epoch, shuffle)      # reseeds the global RNG like the reference does
+                # reseeds the global RNG like the reference does (a replica thread of fit(n_gpus=...) gets the permutations drawn by its caller)
+                perm = _perms[epoch] if _perms is not None else batch_permutation(m, epoch, shuffle)
                 if not direct:
                     perms.put(perm)
                 if verbose:
@@ -639,6 +708,8 @@ class _Trainer(object):
                 d2h_stream.synchronize()
                 if has_embedding:
                     Embedding.check_ids()            # the reference raises IndexError on an id outside the table
+                if world > 1 and self._par.own_kernels and (lib.comm_timeouts(self._par.grad.handle) + lib.comm_timeouts(self._par.stats.handle)):
+                    raise RuntimeError('a data-parallel exchange timed out (a replica stopped): this epoch is invalid')
                 gap = time.time() - start_time
                 mets = pin_metrics.numpy()
                 for bi, (_, _, rows) in enumerate(shards):
@@ -692,6 +763,14 @@ class _Trainer(object):
         self._warm = set()
         self._metrics_out = None
         self._fit_res = None
+        self._cap_stream = None
+        self._comm_stream = None
+        self._bf16_shadow = None
+        self._prep_tasks = {}
+        self._split = None
+        self._replicas = None
+        if isinstance(self.trainable_variables, VariableList):      # drops the handle on the old arena
+            self.trainable_variables = list(self.trainable_variables)
         for ptr in list(getattr(self, '_pinned_user', {})):
             try:
                 lib.sn_host_unregister(ptr)

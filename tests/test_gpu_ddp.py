@@ -21,3 +21,16 @@ def test_two_rank_training_matches_whole_batch_oracle():
     out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert 'DDP_CHECK_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_fit_n_gpus_from_one_process():
+    """models.py fit() sharding each minibatch over the GPUs of the box by itself: fit(n_gpus=2) in ONE process
+    (replica threads + peer-memory exchange kernels) against the whole-batch oracle."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'tests', 'multi_gpu', 'fit_n_gpus_check.py'), '2'], cwd=root,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert 'FIT_N_GPUS_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
