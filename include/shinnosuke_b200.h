@@ -402,6 +402,13 @@ SN_API int sn_batchnorm_finalize_stats_dp(void *comm, const float *gamma, const 
                                    float eps, float momentum, void *stream);
 SN_API int sn_batchnorm_finalize_bwd_dp(void *comm, const float *gamma, const float *save_mean, const float *save_invstd,
                                  double *scratch, long long rows_global, int C, void *stream);
+/* The exchange split in two, so that independent work can run between the halves and absorb both the NVLink
+ * latency and the skew between the replicas (the backward pass puts the next layer's weight-gradient kernel
+ * there): _push folds the local sums and sends them, _pushed polls, adds and finalises.  No other exchange on
+ * this communicator may be issued between the two. */
+SN_API int sn_batchnorm_dp_push(void *comm, double *scratch, int C, void *stream);
+SN_API int sn_batchnorm_finalize_bwd_dp_pushed(void *comm, const float *gamma, const float *save_mean, const float *save_invstd,
+                                        double *scratch, long long rows_global, int C, void *stream);
 SN_API int sn_batchnorm_bwd_apply(const float *dy, const float *x, float *dx, const double *scratch,
                            long long rows, int C, int accumulate_dx, int mask_relu, void *stream);
 SN_API int sn_bn_pool_bwd_local(const float *dy_pool, const uint8_t *code, const float *x, const float *y_pool,

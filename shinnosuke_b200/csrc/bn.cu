@@ -319,6 +319,9 @@ __global__ void bn_finalize_kernel(double *scratch, BnFinal fin) {
 // One launch instead of all-reduce + finalize, 32 bytes per channel and peer on the wire.
 // Slots are double-buffered by the parity of the sequence number (a replica can be at most one exchange
 // ahead of the slowest one, because finishing exchange k needs every replica's words of exchange k).
+// PUSHED: the local sums were folded and sent by bn_dp_push_kernel earlier in the stream (other kernels ran in
+// between, so the replicas' words are normally already here): only the poll + finalize half remains.
+template <bool PUSHED>
 __global__ void __launch_bounds__(32) bn_finalize_dp_kernel(comm::DevComm dc, double *scratch, BnFinal fin) {
     using namespace sn::comm;
     pdl_wait();
@@ -327,11 +330,13 @@ __global__ void __launch_bounds__(32) bn_finalize_dp_kernel(comm::DevComm dc, do
     const size_t slot0 = dc.ll_off + (size_t)(seq & 1u) * MAX_RANKS * LL_SLOT_BYTES;
     if (c < C) {
         const BnChannelIn in = bn_channel_inputs(fin, c);
-        double a, b;
-        bn_fold_slots(scratch, C, c, a, b);
+        if (!PUSHED) {
+            double a, b;
+            bn_fold_slots(scratch, C, c, a, b);
 #pragma unroll
-        for (int p = 0; p < MAX_RANKS; ++p)
-            if (p < dc.world) ll_store_f64x2(dc.t.win[p] + slot0 + (size_t)dc.rank * LL_SLOT_BYTES + (size_t)c * 32, a, b, seq);
+            for (int p = 0; p < MAX_RANKS; ++p)
+                if (p < dc.world) ll_store_f64x2(dc.t.win[p] + slot0 + (size_t)dc.rank * LL_SLOT_BYTES + (size_t)c * 32, a, b, seq);
+        }
         const char *mine = dc.t.win[dc.rank] + slot0 + (size_t)c * 32;
         double sa = 0.0, sb = 0.0;
 #pragma unroll
@@ -344,6 +349,23 @@ __global__ void __launch_bounds__(32) bn_finalize_dp_kernel(comm::DevComm dc, do
         bn_finalize_one(bn_params(scratch, C), fin, in, c, sa, sb, bn_inv_rows(fin.rows));
     }
     finish_exchange(dc.state, seq);
+}
+
+// first half of a split exchange: fold the local slots and send them; the sequence number is NOT advanced (the
+// pull half, bn_finalize_dp_kernel<true>, reads the same one and finishes the exchange)
+__global__ void __launch_bounds__(32) bn_dp_push_kernel(comm::DevComm dc, double *scratch, int C) {
+    using namespace sn::comm;
+    pdl_wait();
+    const unsigned seq = *reinterpret_cast<volatile unsigned *>(&dc.state[0]) + 1u;
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const size_t slot0 = dc.ll_off + (size_t)(seq & 1u) * MAX_RANKS * LL_SLOT_BYTES;
+    if (c < C) {
+        double a, b;
+        bn_fold_slots(scratch, C, c, a, b);
+#pragma unroll
+        for (int p = 0; p < MAX_RANKS; ++p)
+            if (p < dc.world) ll_store_f64x2(dc.t.win[p] + slot0 + (size_t)dc.rank * LL_SLOT_BYTES + (size_t)c * 32, a, b, seq);
+    }
 }
 
 static bool bn_pow2(int C) {
@@ -411,8 +433,27 @@ int sn_batchnorm_finalize_stats_dp(void *comm_handle, const float *gamma, const 
     BnFinal fin{};
     fin.bwd = 0; fin.rows = rows_global; fin.C = C; fin.x = nullptr; fin.gamma = gamma; fin.beta = beta; fin.save_mean = save_mean;
     fin.save_invstd = save_invstd; fin.moving_mean = moving_mean; fin.moving_var = moving_var; fin.eps = eps; fin.momentum = momentum;
-    SN_CUDA(launch_dependent(bn_finalize_dp_kernel, dim3((C + 31) / 32), dim3(32), 0, as_stream(stream), comm::dev_comm(cm), scratch, fin));
+    SN_CUDA(launch_dependent(bn_finalize_dp_kernel<false>, dim3((C + 31) / 32), dim3(32), 0, as_stream(stream), comm::dev_comm(cm), scratch, fin));
     return after_launch("bn_finalize_dp_kernel");
+}
+
+int sn_batchnorm_dp_push(void *comm_handle, double *scratch, int C, void *stream) {
+    SN_REQUIRE(comm_handle && scratch && bn_pow2(C), "bad arguments");
+    const comm::Comm *cm = static_cast<const comm::Comm *>(comm_handle);
+    SN_REQUIRE(cm->connected, "the communicator is not connected");
+    SN_CUDA(launch_dependent(bn_dp_push_kernel, dim3((C + 31) / 32), dim3(32), 0, as_stream(stream), comm::dev_comm(cm), scratch, C));
+    return after_launch("bn_dp_push_kernel");
+}
+
+int sn_batchnorm_finalize_bwd_dp_pushed(void *comm_handle, const float *gamma, const float *save_mean, const float *save_invstd,
+                                        double *scratch, long long rows_global, int C, void *stream) {
+    SN_REQUIRE(comm_handle && gamma && save_mean && save_invstd && scratch && rows_global > 0 && bn_pow2(C), "bad arguments");
+    const comm::Comm *cm = static_cast<const comm::Comm *>(comm_handle);
+    SN_REQUIRE(cm->connected, "the communicator is not connected");
+    BnFinal fin{};
+    fin.bwd = 1; fin.rows = rows_global; fin.C = C; fin.gamma = gamma; fin.mean = save_mean; fin.invstd = save_invstd;
+    SN_CUDA(launch_dependent(bn_finalize_dp_kernel<true>, dim3((C + 31) / 32), dim3(32), 0, as_stream(stream), comm::dev_comm(cm), scratch, fin));
+    return after_launch("bn_finalize_dp_kernel (pushed)");
 }
 
 int sn_batchnorm_finalize_bwd_dp(void *comm_handle, const float *gamma, const float *save_mean, const float *save_invstd,
@@ -422,7 +463,7 @@ int sn_batchnorm_finalize_bwd_dp(void *comm_handle, const float *gamma, const fl
     SN_REQUIRE(cm->connected, "the communicator is not connected");
     BnFinal fin{};
     fin.bwd = 1; fin.rows = rows_global; fin.C = C; fin.gamma = gamma; fin.mean = save_mean; fin.invstd = save_invstd;
-    SN_CUDA(launch_dependent(bn_finalize_dp_kernel, dim3((C + 31) / 32), dim3(32), 0, as_stream(stream), comm::dev_comm(cm), scratch, fin));
+    SN_CUDA(launch_dependent(bn_finalize_dp_kernel<false>, dim3((C + 31) / 32), dim3(32), 0, as_stream(stream), comm::dev_comm(cm), scratch, fin));
     return after_launch("bn_finalize_dp_kernel");
 }
 

@@ -12,6 +12,26 @@ from ..device import DeviceTensor, as_device, current_stream
 from .._lib import lib
 
 
+# Work a layer's backward() has postponed (closures that only launch kernels): a Conv2D whose dX feeds a
+# data-parallel BatchNormalization hands its weight-gradient launch over, so that it runs BETWEEN the two halves of
+# that BatchNormalization's cross-replica exchange (layers/Normalization.py).  The model flushes what is left at
+# the end of the backward sweep.  One list per host thread (fit(n_gpus=...) runs one replica per thread).
+import threading as _threading
+_deferred = _threading.local()
+
+
+def defer(fn):
+    if not hasattr(_deferred, 'work'):
+        _deferred.work = []
+    _deferred.work.append(fn)
+
+
+def flush_deferred():
+    work = getattr(_deferred, 'work', None)
+    while work:
+        work.pop(0)()
+
+
 class Variable(object):
     """A trainable tensor.  Holds a host float64 array (the reference's initial value) until
     the model places it in its parameter arena; afterwards ``output_tensor`` / ``grads`` are

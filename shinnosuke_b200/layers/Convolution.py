@@ -7,7 +7,7 @@ filters [F][kh][kw][C]; np.asarray() of any tensor gives the reference's NCHW vi
 """
 import numpy as np
 
-from .Base import Layer, Variable
+from .Base import Layer, Variable, defer
 from ..device import DeviceTensor, current_stream
 from .._lib import lib, ACT, PRECISION, POOL_MODE
 from ..utils.Initializers import get_initializer
@@ -319,11 +319,17 @@ class Conv2D(Layer):
                 lib.sn_cast_f32_to_bf16(g.ptr, gb.data_ptr(), g.size, st)
         db = b.grads.ptr if (b.require_grads and not db_done) else None
         if W.require_grads or db is not None:
-            if wgrad_bf16:
-                lib.sn_conv2d_wgrad_bf16(self._xb.data_ptr(), gb.data_ptr(), g.ptr if db is not None else None, W.grads.ptr,
-                                         db, *geom, st)
+            xb = self._xb
+
+            def wgrad():
+                if wgrad_bf16:
+                    lib.sn_conv2d_wgrad_bf16(xb.data_ptr(), gb.data_ptr(), g.ptr if db is not None else None, W.grads.ptr, db, *geom, st)
+                else:
+                    lib.sn_conv2d_wgrad(x.ptr, g.ptr, W.grads.ptr, db, *geom, 1, prec, st)
+            if getattr(self, '_defer_wgrad', False) and needs_dx:
+                defer(wgrad)         # dX first; the weight gradient fills the gap in the upstream BatchNormalization's exchange
             else:
-                lib.sn_conv2d_wgrad(x.ptr, g.ptr, W.grads.ptr, db, *geom, 1, prec, st)
+                wgrad()
         self._used_wt_bf16 = bool(dgrad_bf16)
         if dgrad_bf16:
             wtb = self._bf16_buf('wt_bf16', W.size)

@@ -1,7 +1,7 @@
 """BatchNormalization on the device (reference: layers/Normalization.py:8-230)."""
 import numpy as np
 
-from .Base import Layer, Variable
+from .Base import Layer, Variable, flush_deferred
 from ..device import DeviceTensor, current_stream, zeros, torch
 from .._lib import lib, POOL_MODE, ACT
 from ..utils.Initializers import get_initializer
@@ -91,6 +91,15 @@ class BatchNormalization(Layer):
                                         float(self.epsilon), float(self.momentum), st)
 
     def _finalize_bwd(self, par, s, gamma, rows_g, C, st):
+        if par is not None and par.stats is not None and __import__('os').environ.get('SN_BN_SPLIT_EXCHANGE', '1') == '1':
+            # split exchange: send the local sums, run whatever the layers behind us postponed (a Conv2D's weight
+            # gradient: ~30 us of independent work that absorbs the NVLink latency and the skew between the
+            # replicas), then poll + finalise
+            lib.sn_batchnorm_dp_push(par.stats.handle, s['scratch'].data_ptr(), C, st)
+            flush_deferred()
+            lib.sn_batchnorm_finalize_bwd_dp_pushed(par.stats.handle, gamma.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
+                                                    s['scratch'].data_ptr(), rows_g, C, st)
+            return
         if par is not None and par.stats is not None:
             lib.sn_batchnorm_finalize_bwd_dp(par.stats.handle, gamma.output_tensor.ptr, s['mean'].ptr, s['invstd'].ptr,
                                              s['scratch'].data_ptr(), rows_g, C, st)

@@ -22,7 +22,7 @@ import numpy as np
 
 from .device import Arena, DeviceTensor, as_device, current_stream, empty, require_cuda, torch, zeros
 from ._lib import lib, PRECISION
-from .layers.Base import Layer, Variable, Input
+from .layers.Base import Layer, Variable, Input, flush_deferred
 from .utils.MiniBatch import batch_permutation, batch_slices
 from .utils.Objectives import get_objective
 from .utils.Optimizers import get_optimizer, Momentum
@@ -184,8 +184,11 @@ class _Trainer(object):
         vl.arena = arena
         self.trainable_variables = vl
         self._metrics_out = zeros(4)          # two (loss, acc) slots: fit() reads one back while the next step writes the other
+        from .layers.Convolution import Conv2D
         for layer in self._forward_order():
             layer._par = par
+            # data parallel: a convolution postpones its weight gradient into the upstream BatchNormalization's exchange
+            layer._defer_wgrad = bool(par.world > 1 and par.own_kernels and isinstance(layer, Conv2D))
         if par.world > 1:
             if keeps_grads:
                 arena.gstep = par.grad.carve_f32(arena.total) if in_window else zeros(arena.total)
@@ -219,6 +222,7 @@ class _Trainer(object):
         out._seed_grads(self.loss.backward(y_hat, as_device(y_true), metrics_ptr, denom_rows))
         for layer in self._backward_order():
             layer.backward()
+        flush_deferred()
 
     # ---- one training step on device-resident shards ---------------------
     def _grad_arena_for_step(self):
@@ -357,6 +361,7 @@ class _Trainer(object):
         if k_split is None or not overlap:
             for layer in self._backward_order():
                 layer.backward()
+            flush_deferred()
             from .utils.Optimizers import StochasticGradientDescent
             if par.own_kernels and type(self.optimizer) is StochasticGradientDescent and garena is a.g \
                     and os.environ.get('SN_FUSE_SGD', '1') == '1':
@@ -372,11 +377,13 @@ class _Trainer(object):
         for k, layer in enumerate(self._backward_order()):
             layer.backward()
             if k == k_split:
+                flush_deferred()
                 ready = t.cuda.Event()
                 ready.record(main)
                 comm.wait_event(ready)
                 with t.cuda.stream(comm):
                     par.allreduce_grads(garena[lo:], comm.cuda_stream)
+        flush_deferred()
         # the head follows on the SAME side stream: one window's flags serve one exchange at a time
         ready = t.cuda.Event()
         ready.record(main)
