@@ -150,6 +150,10 @@ struct IgemmParams {
 // tables to stats[slot][{sum, sumsq}][F] (float64, slot = blockIdx.x % BN_SLOTS) once at the end.
 constexpr int STAT_MAX_F = 512;
 constexpr int STAT_BYTES = 4 * 2 * STAT_MAX_F * 4;          // [epilogue warp][{sum, sumsq}][STAT_MAX_F]
+// the bias vector staged in shared memory once per CTA: fetched with __ldg per 32-column chunk of every tile it was eight
+// L2 round trips (long-scoreboard stalls on every FADD in ncu) in a chain the kernel turned out to be bound by
+constexpr int BIAS_MAX_F = 1024;
+constexpr int BIAS_BYTES = BIAS_MAX_F * 4;
 
 // Epilogue: EPI_WARPS warps, two per TMEM lane quarter (a warp may only read the quarter
 // warp_id % 4), alternating over the 32-column chunks of the tile.  One epilogue warp per scheduler
@@ -170,11 +174,11 @@ template <int BN, int KS, bool PAIR = false> struct IgemmCfg {
     static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 4;
     static constexpr int SLAB_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGE_BYTES = KS * SLAB_BYTES;
-    static constexpr int RING_BUDGET = 232448 - (EPI_STAGE_BYTES + STAT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/);
+    static constexpr int RING_BUDGET = 232448 - (EPI_STAGE_BYTES + STAT_BYTES + BIAS_BYTES + 1024 /*align slack*/ + 256 /*barriers*/);
     static constexpr int STAGES = RING_BUDGET / STAGE_BYTES > 8 ? 8 : RING_BUDGET / STAGE_BYTES;
     static_assert(STAGES >= 3, "pipeline too shallow: use KS = 1 for this tile width");
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;      // power of two >= 32
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + STAT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + STAT_BYTES + BIAS_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // BF16: the operands are bf16 copies (64 elements per 128-byte row, UMMA K = 16, kind::f16); the
@@ -191,7 +195,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *epi_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                 // 1024-byte aligned (stage sizes are)
     float *sstat = reinterpret_cast<float *>(epi_stage + EPI_STAGE_BYTES);      // [4][2][STAT_MAX_F]
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi_stage + EPI_STAGE_BYTES + STAT_BYTES);
+    float *sbias = reinterpret_cast<float *>(epi_stage + EPI_STAGE_BYTES + STAT_BYTES);              // [BIAS_MAX_F], zero when there is no bias
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi_stage + EPI_STAGE_BYTES + STAT_BYTES + BIAS_BYTES);
     uint64_t *empty_bar = full_bar + Cfg::STAGES;
     uint64_t *tmem_full = empty_bar + Cfg::STAGES;
     uint64_t *tmem_empty = tmem_full + 2;
@@ -229,6 +234,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);     // shuffle from lane 0: provably warp-uniform
     pdl_wait();        // everything above (barriers, TMEM, descriptor prefetch) may overlap the previous kernel's tail
+    const bool bias_staged = p.bias && p.F <= BIAS_MAX_F;
+    if (warp >= 2 && bias_staged) {
+        for (int i = threadIdx.x - 64; i < ((p.F + 31) & ~31); i += 32 * EPI_WARPS) sbias[i] = i < p.F ? __ldg(p.bias + i) : 0.f;
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * EPI_WARPS) : "memory");       // the epilogue warps only
+    }
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -348,7 +358,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (p.bias && f0 + j < p.F) b = __ldg(reinterpret_cast<const float4 *>(p.bias + f0 + j));
+                                if (bias_staged) { if (f0 + j < p.F) b = *reinterpret_cast<const float4 *>(sbias + f0 + j); }
+                                else if (p.bias && f0 + j < p.F) b = __ldg(reinterpret_cast<const float4 *>(p.bias + f0 + j));
                                 v[j] = __uint_as_float(r[j]) + b.x; v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
                                 v[j + 2] = __uint_as_float(r[j + 2]) + b.z; v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
                                 if (p.act == SN_ACT_RELU) {
@@ -370,7 +381,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                                    __uint_as_float(r[j + 3]));
                             if (p.bias && f0 + j < p.F) {
-                                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + f0 + j));
+                                const float4 b = bias_staged ? *reinterpret_cast<const float4 *>(sbias + f0 + j)
+                                                             : __ldg(reinterpret_cast<const float4 *>(p.bias + f0 + j));
                                 v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
                             }
                             if (p.act == SN_ACT_RELU) {
@@ -830,6 +842,10 @@ int launch_igemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorM
 
 namespace sn {
 
+bool conv_rows_eligible(int N, int C, int IH, int IW, int F, int kh, int kw, int OH, int OW, int pad_h, int pad_w, bool out_bf16);
+int conv_rows_igemm_tc(const void *x, const void *w, const float *bias, void *out, int N, int C, int IH, int IW, int F, int kh, int kw,
+                       int OH, int OW, int pad_h, int pad_w, int act, double *stats, bool out_bf16, cudaStream_t st);
+
 // When do CTA pairs pay?  Measured (profiles/r01_igemm_pair_vs_single.txt): 256-wide tiles with at
 // least four waves of tile pairs gain 7-8 % (tf32 reaches 725 TF/s = 89 % of the TF32 roof at
 // batch 2048); with fewer tiles the longer barrier round trips across the pair cost more than the
@@ -858,6 +874,10 @@ int conv_igemm_tc(const void *x, const void *w, const float *bias, void *out_any
                   int kw, int OH, int OW, int pad_h, int pad_w, int act, int accumulate, bool bf16, double *stats, cudaStream_t st,
                   bool out_bf16) {
     float *out = static_cast<float *>(out_any);
+    // filters resident in shared memory + row-shifted activation copies (conv_rows_tc.cu) where the layer allows
+    if (bf16 && !accumulate && (!bias || (((uintptr_t)bias) & 15) == 0) && ((((uintptr_t)x) | ((uintptr_t)w) | ((uintptr_t)out_any)) & 15) == 0 &&
+        conv_rows_eligible(N, C, IH, IW, F, kh, kw, OH, OW, pad_h, pad_w, out_bf16))
+        return conv_rows_igemm_tc(x, w, bias, out_any, N, C, IH, IW, F, kh, kw, OH, OW, pad_h, pad_w, act, stats, out_bf16, st);
     if (out_bf16 && !(bf16 && !accumulate && F > 32 && (F & 7) == 0)) {
         set_error("conv_igemm_tc: a bf16 output map needs bf16 operands, F %% 8 == 0, F > 32 and no accumulation (F = %d)", F);
         return SN_ERR_UNSUPPORTED;
