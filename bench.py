@@ -543,6 +543,8 @@ def run_ours(args):
                 mp = build_model(cfg, precision)
                 mp.fit(Xp, Yp, batch_size=64, epochs=1, shuffle=False, validation_ratio=0., verbose=0)
                 tol = {'fp32': 1e-5, 'tf32x3': 5e-5, 'tf32': 2e-3, 'bf16': 1e-2}[precision]
+                if not np.isfinite(net.train_loss[0]):
+                    raise ValueError('the oracle loss is not finite at this initialisation (softmax underflow -> log 0 in float64)')
                 err = abs(mp.train_loss[0] - net.train_loss[0]) / abs(net.train_loss[0])
                 parity = dict(check='first loss of a 64-sample minibatch vs the float64 oracle', loss=mp.train_loss[0],
                               oracle_loss=net.train_loss[0], rel_err=err, tolerance=tol, ok=bool(err < tol),
@@ -663,8 +665,12 @@ def run_micro(args):
         g = (M, K, 1, 1, Nout, 1, 1, 1, 0, 0)
         timed('sn_conv2d_fprop_bf16', g, lambda: lib.sn_conv2d_fprop_bf16(xb.data_ptr(), wb.data_ptr(), b.data_ptr(), y.data_ptr(), *g, 1, st),
               precision='bf16', tensor_peak=pk['bf16'], note='Dense fprop, bf16 tier')
-        timed('sn_conv2d_dgrad_bf16', g, lambda: lib.sn_conv2d_dgrad_bf16(dyb.data_ptr(), wtb.data_ptr(), dx.data_ptr(), *g, 0, st),
-              precision='bf16', tensor_peak=pk['bf16'], note='Dense dX, bf16 tier')
+        if lib.load().sn_conv2d_bf16_supported(1, *g):
+            timed('sn_conv2d_dgrad_bf16', g, lambda: lib.sn_conv2d_dgrad_bf16(dyb.data_ptr(), wtb.data_ptr(), dx.data_ptr(), *g, 0, st),
+                  precision='bf16', tensor_peak=pk['bf16'], note='Dense dX, bf16 tier')
+        else:
+            rows.append(dict(kernel='sn_conv2d_dgrad_bf16', args=list(g), precision='bf16',
+                             note='not taken: n_out = 500 is not a multiple of 8 bf16 elements (16-byte TMA rows); layers/FC.py uses the tf32 kernel for dX'))
         del xb, wb, dyb, wtb
         del x, wt, y, dy, dx, dw
     out = dict(micro=True, peaks=pk, rows=rows)

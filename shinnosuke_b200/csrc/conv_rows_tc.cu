@@ -270,9 +270,11 @@ bool rows_geom(int N, int C, int OH, int OW, int F, int kh, int kw, int pad_h, i
     p.copy_bytes = p.R * OW * 128;                       // a multiple of 1024 (OW is a multiple of 8)
     const int epi = RI_EPI_WARPS * (out_bf16 ? 2048 : 4096);
     const long long room = 232448 - 1024 - 1024 - epi - b_bytes;
-    if (room < 2ll * p.copy_bytes) return false;
+    if (room < 3ll * p.copy_bytes) return false;
     p.stages = (int)(room / p.copy_bytes);
     if (p.stages > 8) p.stages = 8;
+    if (p.stages < 3) return false;                              // measured: with a two-deep ring (conv2's dgrad: fp32 staging tiles leave
+                                                                 // 50 KB) the kernel waits on load latency: 36.7 us against 33.7 for conv_igemm_kernel
     if (8 * BN * 4 > p.stages * p.copy_bytes) return false;      // the statistics tables reuse the ring
     smem = (int)(b_bytes + (long long)p.stages * p.copy_bytes + epi + 1024 + 1024);
     p.tiles = N * p.tiles_per_image;

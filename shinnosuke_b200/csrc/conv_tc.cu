@@ -875,7 +875,7 @@ int conv_igemm_tc(const void *x, const void *w, const float *bias, void *out_any
                   bool out_bf16) {
     float *out = static_cast<float *>(out_any);
     // filters resident in shared memory + row-shifted activation copies (conv_rows_tc.cu) where the layer allows
-    if (bf16 && !accumulate && (!bias || (((uintptr_t)bias) & 15) == 0) && ((((uintptr_t)x) | ((uintptr_t)w) | ((uintptr_t)out_any)) & 15) == 0 &&
+    if (bf16 && !accumulate && g_igemm_pair_mode != 2 /* pairs forced: A/B measurements, tests */ && (!bias || (((uintptr_t)bias) & 15) == 0) && ((((uintptr_t)x) | ((uintptr_t)w) | ((uintptr_t)out_any)) & 15) == 0 &&
         conv_rows_eligible(N, C, IH, IW, F, kh, kw, OH, OW, pad_h, pad_w, out_bf16))
         return conv_rows_igemm_tc(x, w, bias, out_any, N, C, IH, IW, F, kh, kw, OH, OW, pad_h, pad_w, act, stats, out_bf16, st);
     if (out_bf16 && !(bf16 && !accumulate && F > 32 && (F & 7) == 0)) {
