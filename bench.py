@@ -186,7 +186,7 @@ def kernel_work(name, a, precision):
     conv = ('sn_conv2d_fprop', 'sn_conv2d_dgrad', 'sn_conv2d_wgrad', 'sn_conv2d_fprop_bf16', 'sn_conv2d_dgrad_bf16',
             'sn_conv2d_wgrad_bf16', 'sn_conv2d_fprop_stats', 'sn_conv2d_fprop_bf16_stats', 'sn_conv2d_fprop_x3',
             'sn_conv2d_dgrad_x3', 'sn_conv2d_wgrad_x3', 'sn_conv2d_fprop_bf16_stats_ybf16', 'sn_conv2d_fprop_stats_ybf16',
-            'sn_conv2d_stem_fprop')
+            'sn_conv2d_stem_fprop', 'sn_conv2d_stem_wgrad_dybf16')
     if name in conv:
         N, C, H, W, F, kh, kw, stride, ph, pw = a[:10]
         oh = (H + 2 * ph - kh) // stride + 1
@@ -195,6 +195,8 @@ def kernel_work(name, a, precision):
         flops = 2.0 * y * C * kh * kw
         if name == 'sn_conv2d_stem_fprop':
             byt = {'fprop': 4 * x + 4 * w + (2 if (len(a) > 11 and a[11]) else 4) * y}       # fp32 image and filters in, fp32 or bf16 map out
+        elif name == 'sn_conv2d_stem_wgrad_dybf16':
+            byt = {'wgrad': 4 * x + 2 * y + 4 * w}              # fp32 image and the bf16 gradient map in, fp32 dw out
         elif name == 'sn_conv2d_fprop_stats_ybf16':
             byt = {'fprop': 4 * x + 4 * w + 2 * y}              # the stem: fp32 image and filters in, bf16 map out
         elif name == 'sn_conv2d_fprop_bf16_stats_ybf16':

@@ -269,6 +269,13 @@ SN_API int sn_conv2d_stem_prepare(const float *x, float *x4, int N, int C, int H
 SN_API int sn_conv2d_stem_fprop(const float *x4, const float *w, const float *bias, void *y,
                          int N, int C, int H, int W, int F, int kh, int kw, int stride, int pad_h, int pad_w,
                          int act, int y_bf16, double *bn_scratch, void *stream);
+/* The stem's weight gradient in the bf16 tier (Conv2D.backward, layers/Convolution.py:176-196, for C*kh*kw < 32):
+ * x is the fp32 NHWC input, dy_bf16 the bf16 copy of the gradient map (what sn_bn_pool_bwd_xbf16 writes, so the
+ * fp32 map need not exist); dw += and, when db != NULL, db += column sums of dy (csrc/conv_stem_tc.cu). */
+SN_API int sn_conv2d_stem_wgrad_dybf16_supported(int N, int C, int H, int W, int F, int kh, int kw, int stride, int pad_h, int pad_w);
+SN_API int sn_conv2d_stem_wgrad_dybf16(const float *x, const void *dy_bf16, float *dw, float *db,
+                                int N, int C, int H, int W, int F, int kh, int kw,
+                                int stride, int pad_h, int pad_w, void *stream);
 SN_API int sn_conv2d_dgrad_bf16(const void *dy_bf16, const void *wt_bf16, float *dx,
                          int N, int C, int H, int W, int F, int kh, int kw,
                          int stride, int pad_h, int pad_w, int accumulate, void *stream);

@@ -26,8 +26,8 @@ int colsum_accumulate(const float *dy, float *db, long long rows, int F, cudaStr
 bool stem_tc_eligible(int N, int C, int H, int W, int F, int kh, int kw, int stride, int ph, int pw);
 int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, void *y, int N, int C, int H, int W, int F, int kh,
                        int kw, int stride, int ph, int pw, int act, double *stats, cudaStream_t st, bool out_bf16 = false);
-int conv_stem_wgrad_tc(const float *x, const float *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh, int kw,
-                       int stride, int ph, int pw, cudaStream_t st);
+int conv_stem_wgrad_tc(const float *x, const void *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh, int kw,
+                       int stride, int ph, int pw, cudaStream_t st, bool dy_bf16 = false);
 bool stem_im2col_eligible(int N, int C, int H, int W, int F, int kh, int kw, int stride, int ph, int pw);
 int pad_channels4(const float *x, float *x4, long long npix, int C, cudaStream_t st);
 int conv_stem_im2col_fprop(const float *x4, const float *w, const float *bias, void *y, int N, int C, int H, int W, int F, int kh, int kw,
@@ -346,6 +346,23 @@ int sn_conv2d_wgrad_bf16(const void *x, const void *dy, const float *dy_f32, flo
     int e = conv_wgrad_halo_tc(x, dy, dw, N, C, H, W, F, kh, kw, oh, ow, pad_h, pad_w, true, as_stream(stream));
     if (e || !db || !dy_f32) return e;
     return colsum_accumulate(dy_f32, db, (long long)N * oh * ow, F, as_stream(stream));
+}
+
+// Tiny-C stem (C*kh*kw < 32), bf16 tier: the weight gradient from the fp32 input and the bf16 copy of the gradient map
+// (what the fused BN+pool backward writes; the fp32 map then never exists).  dw / db accumulated into (+=).
+int sn_conv2d_stem_wgrad_dybf16_supported(int N, int C, int H, int W, int F, int kh, int kw, int stride, int pad_h, int pad_w) {
+    if (N <= 0 || C <= 0 || F <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad_h < 0 || pad_w < 0 || H + 2 * pad_h < kh || W + 2 * pad_w < kw)
+        return 0;
+    const char *e = getenv("SN_STEM_WGRAD_BF16");
+    if (e && e[0] == '0') return 0;
+    return (C * kh * kw < 32 && (F & 7) == 0 && stem_tc_eligible(N, C, H, W, F, kh, kw, stride, pad_h, pad_w)) ? 1 : 0;
+}
+int sn_conv2d_stem_wgrad_dybf16(const float *x, const void *dy_bf16, float *dw, float *db, int N, int C, int H, int W, int F, int kh,
+                                int kw, int stride, int pad_h, int pad_w, void *stream) {
+    SN_REQUIRE(x && dy_bf16 && dw, "null tensor");
+    SN_REQUIRE(sn_conv2d_stem_wgrad_dybf16_supported(N, C, H, W, F, kh, kw, stride, pad_h, pad_w), "shape not supported by the bf16 stem wgrad");
+    SN_REQUIRE(((((uintptr_t)x) | ((uintptr_t)dy_bf16)) & 15) == 0, "misaligned tensor");
+    return conv_stem_wgrad_tc(x, dy_bf16, dw, db, N, C, H, W, F, kh, kw, stride, pad_h, pad_w, as_stream(stream), true);
 }
 
 // ------------------------------------------------------------------------------ tiny-C stem, TMA im2col

@@ -323,37 +323,48 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
 
 // ============================================================================== wgrad
 constexpr int SW_BUILDERS = 256;               // 4 threads per pixel row build one stage ...
-constexpr int SW_GROUPS = 2;                   // ... and two such groups take alternate stages: a builder warp's stage is a
-                                               // ~200-instruction dependent chain (~1000 cycles), twice the MMA time of a stage
+constexpr int SW_GROUPS = 3;                   // ... and three such groups take stages in turn: a builder warp's stage is a
+                                               // ~200-instruction dependent chain (measured ~2700 cycles with mbarrier waits and
+                                               // LDS latencies: two groups gave 1350 cycles per stage, the whole kernel's pace)
 constexpr int SW_THREADS = 64 + SW_GROUPS * SW_BUILDERS + 128;   // warp 0: TMA (dY) + MMA, warp 1: patch producer, warps 2-17: column builders, warps 18-21: epilogue
 constexpr int SW_PB = 64;                      // pixels per stage
 // NA = 32-filter atoms of dY actually loaded per stage (2 when F <= 64, else 4).  The MMA is always
 // M = 128: with NA = 2 its upper 64 rows read whatever follows in shared memory (the next stage /
 // the patch ring) and produce accumulator rows the epilogue never looks at — rows of D depend only
 // on the same rows of A — which halves the stage and deepens the ring from 4 to 6 stages.
+// PATCHES: depth of the patch ring.  A patch slot is released when the builders of its stage are done and
+// its refill is a TMA round trip (~2700 cycles under load); with the 4 slots the fprop kernel uses, a
+// builder group found its next patch still in flight (ncu: 20 % of all warp samples on the p_full wait,
+// 1350 cycles per stage against ~500 of work) — 8 slots keep the producer four group-stages ahead.
 template <int NA> struct SwCfg {
-    static constexpr int STAGES = NA == 2 ? 6 : 4;
+    static constexpr int STAGES = NA <= 2 ? 6 : 4;
+    static constexpr int PATCHES = NA <= 2 ? 8 : 6;
 };
 constexpr int SW_MAX_STAGES = 6;
 constexpr int SW_ATOM = SW_PB * 128;           // one 32-wide atom column: 64 pixel rows x 128 B
 constexpr int SW_PATCH_FLOATS = 2048;          // per patch stage (a 64-pixel stage spans about half the rows of a 128-pixel tile)
 
-template <int NA>
+// BF16: dY arrives as the bf16 copy the fused BN+pool backward wrote (the fp32 map is then never written): atoms of
+// 64 filters (NA = 1 when F <= 64), plain 128-byte swizzle, 16-pixel K-steps; the builders round the patch values to
+// bf16 into the first 64 bytes of the same 128-byte rows (N = 64 for the MMA: columns 32..63 are whatever the rows
+// hold and land in accumulator columns nobody reads).
+template <int NA, bool BF16>
 __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                                                                    const __grid_constant__ CUtensorMap tmXr, const StemP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int SW_STAGES = SwCfg<NA>::STAGES;
+    constexpr int SW_PATCHES = SwCfg<NA>::PATCHES;
     constexpr int SW_A_BYTES = NA * SW_ATOM;
     constexpr int SW_STAGE_BYTES = SW_A_BYTES + SW_ATOM;
-    float *patch = reinterpret_cast<float *>(smem + SW_STAGES * SW_STAGE_BYTES);        // PATCH_STAGES x SW_PATCH_FLOATS
-    uint64_t *full = reinterpret_cast<uint64_t *>(patch + PATCH_STAGES * SW_PATCH_FLOATS);
+    float *patch = reinterpret_cast<float *>(smem + SW_STAGES * SW_STAGE_BYTES);        // SW_PATCHES x SW_PATCH_FLOATS
+    uint64_t *full = reinterpret_cast<uint64_t *>(patch + SW_PATCHES * SW_PATCH_FLOATS);
     uint64_t *empty = full + SW_MAX_STAGES;
     uint64_t *acc_full = empty + SW_MAX_STAGES;
     uint64_t *p_full = acc_full + 1;
-    uint64_t *p_empty = p_full + PATCH_STAGES;
-    int *pinfo = reinterpret_cast<int *>(p_empty + PATCH_STAGES);
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(pinfo + PATCH_STAGES);
+    uint64_t *p_empty = p_full + SW_PATCHES;
+    int *pinfo = reinterpret_cast<int *>(p_empty + SW_PATCHES);
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(pinfo + SW_PATCHES);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int f_tile = blockIdx.y;
@@ -366,11 +377,12 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
         // full: 1 arrive.expect_tx by the TMA thread + one arrival per builder thread
         for (int i = 0; i < SW_STAGES; ++i) { mbar_init(&full[i], 1 + SW_BUILDERS); mbar_init(&empty[i], 1); }
         mbar_init(acc_full, 1);
-        for (int i = 0; i < PATCH_STAGES; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], SW_BUILDERS / 32); }
+        for (int i = 0; i < SW_PATCHES; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], SW_BUILDERS / 32); }
         tma_prefetch_desc(&tmX);
         fence_barrier_init();
     }
-    if (warp == 0) { tmem_alloc(tmem_ptr, 32); tmem_relinquish(); }
+    constexpr uint32_t SW_TMEM_COLS = BF16 ? 64 : 32;
+    if (warp == 0) { tmem_alloc(tmem_ptr, SW_TMEM_COLS); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -382,7 +394,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
             {
                 // one warp is both the TMA producer and the MMA issuer (the MMAs are negligible here): it runs the
                 // loads SW_STAGES ahead of the MMAs.  Warp-uniform control flow, the elected lane issues.
-                constexpr uint32_t idesc = make_idesc(2, 128, 32, 1, 1);
+                constexpr uint32_t idesc = BF16 ? make_idesc(1, 128, 64, 1, 1) : make_idesc(2, 128, 32, 1, 1);
+                constexpr int A_ELEMS = BF16 ? 64 : 32;          // filters per dY atom
                 int ld = 0, ld_stage = 0; uint32_t ld_phase = 0;
                 int stage = 0; uint32_t phase = 0;
                 for (int s = 0; s < nst; ++s) {
@@ -393,7 +406,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
                             mbar_expect_tx(&full[ld_stage], SW_A_BYTES);
 #pragma unroll
                             for (int a = 0; a < NA; ++a)
-                                tma_load_2d(sa + a * SW_ATOM, &tmDY, &full[ld_stage], f_tile * 128 + a * 32, (t0 + ld) * SW_PB);
+                                tma_load_2d(sa + a * SW_ATOM, &tmDY, &full[ld_stage], f_tile * 128 + a * A_ELEMS, (t0 + ld) * SW_PB);
                         }
                         __syncwarp();
                         ++ld;
@@ -402,11 +415,20 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * SW_STAGE_BYTES);
+                    if constexpr (BF16) {
 #pragma unroll
-                    for (int k = 0; k < SW_PB / 8; ++k) {
-                        const uint64_t adesc = make_smem_desc(sa + k * 1024, SW_ATOM, 512, LAYOUT_SW128_BASE32B);
-                        const uint64_t bdesc = make_smem_desc(sa + SW_A_BYTES + k * 1024, SW_ATOM, 512, LAYOUT_SW128_BASE32B);
-                        if (elect_one()) mma_tf32(tmem_base, adesc, bdesc, idesc, (s | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < SW_PB / 16; ++k) {       // K-step = 16 pixel rows = two 8-row K groups 1024 B apart
+                            const uint64_t adesc = make_smem_desc(sa + k * 2048, SW_ATOM, 1024, LAYOUT_SW128);
+                            const uint64_t bdesc = make_smem_desc(sa + SW_A_BYTES + k * 2048, SW_ATOM, 1024, LAYOUT_SW128);
+                            if (elect_one()) mma_bf16(tmem_base, adesc, bdesc, idesc, (s | k) != 0 ? 1u : 0u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < SW_PB / 8; ++k) {
+                            const uint64_t adesc = make_smem_desc(sa + k * 1024, SW_ATOM, 512, LAYOUT_SW128_BASE32B);
+                            const uint64_t bdesc = make_smem_desc(sa + SW_A_BYTES + k * 1024, SW_ATOM, 512, LAYOUT_SW128_BASE32B);
+                            if (elect_one()) mma_tf32(tmem_base, adesc, bdesc, idesc, (s | k) != 0 ? 1u : 0u);
+                        }
                     }
                     if (elect_one()) mma_commit(&empty[stage]);
                     __syncwarp();
@@ -416,12 +438,12 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
                 __syncwarp();
             }
         } else if (warp == 1) {
-            // patch producer: PATCH_STAGES stages ahead of the builders
+            // patch producer: SW_PATCHES stages ahead of the builders
             int ps = 0; uint32_t pphase = 0;
             for (int s = 0; s < nst; ++s) {
                 mbar_wait(&p_empty[ps], pphase ^ 1);
                 patch_produce(p, &tmX, &tmXr, p.R64, patch + ps * SW_PATCH_FLOATS, pinfo + ps, &p_full[ps], (t0 + s) * SW_PB, SW_PB, lane);
-                if (++ps == PATCH_STAGES) { ps = 0; pphase ^= 1; }
+                if (++ps == SW_PATCHES) { ps = 0; pphase ^= 1; }
             }
         } else if (warp < 2 + SW_GROUPS * SW_BUILDERS / 32) {
             // column builders: thread (r, kq) of group g builds k = 8kq..8kq+7 (one 32-byte chunk) of pixel
@@ -433,16 +455,23 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
             make_kslice(p, kq, ks);
             const int one_at = p.db ? p.K : -1;
             for (int s = grp; s < nst; s += SW_GROUPS) {
-                const int stage = s % SW_STAGES, ps = s % PATCH_STAGES;
-                const uint32_t phase = (s / SW_STAGES) & 1, pphase = (s / PATCH_STAGES) & 1;
+                const int stage = s % SW_STAGES, ps = s % SW_PATCHES;
+                const uint32_t phase = (s / SW_STAGES) & 1, pphase = (s / SW_PATCHES) & 1;
                 mbar_wait(&p_full[ps], pphase);
                 float col[8];
                 build_slice(p, ks, patch + ps * SW_PATCH_FLOATS, pinfo[ps], (t0 + s) * SW_PB + r, kq, one_at, col);   // rows past the end stay 0 (dY is TMA zero-filled too)
                 mbar_wait(&empty[stage], phase ^ 1);
-                // 128B swizzle with 32-byte atoms: 32-byte chunk j of row r lives at (j ^ (r & 3)) * 32
-                uint8_t *dst = smem + stage * SW_STAGE_BYTES + SW_A_BYTES + r * 128 + ((kq ^ (r & 3)) * 32);
-                *reinterpret_cast<float4 *>(dst) = make_float4(col[0], col[1], col[2], col[3]);
-                *reinterpret_cast<float4 *>(dst + 16) = make_float4(col[4], col[5], col[6], col[7]);
+                if constexpr (BF16) {
+                    // plain 128B swizzle: 16-byte chunk j (8 bf16) of row r lives at (j ^ (r & 7)) * 16
+                    uint8_t *dst = smem + stage * SW_STAGE_BYTES + SW_A_BYTES + r * 128 + ((kq ^ (r & 7)) * 16);
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(pack_bf16x2(col[0], col[1]), pack_bf16x2(col[2], col[3]),
+                                                                 pack_bf16x2(col[4], col[5]), pack_bf16x2(col[6], col[7]));
+                } else {
+                    // 128B swizzle with 32-byte atoms: 32-byte chunk j of row r lives at (j ^ (r & 3)) * 32
+                    uint8_t *dst = smem + stage * SW_STAGE_BYTES + SW_A_BYTES + r * 128 + ((kq ^ (r & 3)) * 32);
+                    *reinterpret_cast<float4 *>(dst) = make_float4(col[0], col[1], col[2], col[3]);
+                    *reinterpret_cast<float4 *>(dst + 16) = make_float4(col[4], col[5], col[6], col[7]);
+                }
                 fence_proxy_async();
                 mbar_arrive(&full[stage]);
                 __syncwarp();
@@ -468,7 +497,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 32); }
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, SW_TMEM_COLS); }
 }
 
 // one patch row = one TMA box: its shared-memory address must be 128-byte aligned, so the pitch is a multiple of 32 floats
@@ -563,8 +592,9 @@ int conv_stem_fprop_tc(const float *x, const float *w, const float *bias, void *
 }
 
 // dw/db accumulated into (+=).  Requires K < 32 when db != NULL (the ones column).
-int conv_stem_wgrad_tc(const float *x, const float *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh, int kw,
-                       int stride, int ph, int pw, cudaStream_t st) {
+// dy_bf16: dy is the bf16 copy of the gradient map (bf16 tier, F % 8 == 0); x stays fp32 (the network input).
+int conv_stem_wgrad_tc(const float *x, const void *dy, float *dw, float *db, int N, int C, int H, int W, int F, int kh, int kw,
+                       int stride, int ph, int pw, cudaStream_t st, bool dy_bf16) {
     StemP p{};
     fill_geom(p, N, C, H, W, F, kh, kw, stride, ph, pw);
     p.x = x; p.dw = dw; p.db = db;
@@ -578,26 +608,30 @@ int conv_stem_wgrad_tc(const float *x, const float *dy, float *dw, float *db, in
     CUtensorMap tmDY;
     long long ddims[2] = {F, p.P};
     long long dstr[2] = {1, F};
-    int dbox[2] = {32, SW_PB};
-    int e = make_tmap_f32(&tmDY, dy, 2, ddims, dstr, dbox, true);
+    int dbox[2] = {dy_bf16 ? 64 : 32, SW_PB};
+    int e = dy_bf16 ? make_tmap(&tmDY, dy, 2, ddims, dstr, dbox, false, true) : make_tmap_f32(&tmDY, dy, 2, ddims, dstr, dbox, true);
     if (e) return e;
-    const bool na2 = F <= 64;
-    const int smem = (na2 ? SwCfg<2>::STAGES * 3 : SwCfg<4>::STAGES * 5) * SW_ATOM + PATCH_STAGES * SW_PATCH_FLOATS * 4 + 1024 + 256;
+    const bool small = F <= 64;                          // half the dY atoms per stage, deeper rings
+    const int na = dy_bf16 ? (small ? 1 : 2) : (small ? 2 : 4);
+    const int smem = (na <= 2 ? SwCfg<2>::STAGES : SwCfg<4>::STAGES) * (na + 1) * SW_ATOM +
+                     (na <= 2 ? SwCfg<2>::PATCHES : SwCfg<4>::PATCHES) * SW_PATCH_FLOATS * 4 + 1024 + 512;
     CUtensorMap tmX, tmXr;
     e = make_patch_tmap(&tmX, p);
     if (e) return e;
     e = make_patch_tmap(&tmXr, p, p.R64);
     if (e) return e;
-    static bool configured_dev[16][2] = {};
-    bool (&configured)[2] = configured_dev[current_device_slot()];
-    if (!configured[na2]) {
-        if (na2) SN_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        else SN_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured[na2] = true;
-    }
-    if (na2) SN_CUDA(launch_dependent(stem_wgrad_kernel<2>, dim3(ctas, f_tiles), dim3(SW_THREADS), (size_t)smem, st, tmDY, tmX, tmXr, p));
-    else SN_CUDA(launch_dependent(stem_wgrad_kernel<4>, dim3(ctas, f_tiles), dim3(SW_THREADS), (size_t)smem, st, tmDY, tmX, tmXr, p));
-    return after_launch("stem_wgrad_kernel");
+    static bool configured_dev[16][4] = {};
+    bool &configured = configured_dev[current_device_slot()][(dy_bf16 ? 2 : 0) + (small ? 1 : 0)];
+    auto go = [&](auto kernel) -> int {
+        if (!configured) {
+            SN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured = true;
+        }
+        SN_CUDA(launch_dependent(kernel, dim3(ctas, f_tiles), dim3(SW_THREADS), (size_t)smem, st, tmDY, tmX, tmXr, p));
+        return after_launch("stem_wgrad_kernel");
+    };
+    if (dy_bf16) return small ? go(stem_wgrad_kernel<1, true>) : go(stem_wgrad_kernel<2, true>);
+    return small ? go(stem_wgrad_kernel<2, false>) : go(stem_wgrad_kernel<4, false>);
 }
 
 }  // namespace sn

@@ -595,7 +595,16 @@ struct WgradParams {
     int th, tn, S;             // pixel-block box: th rows of tn images; S = OH*OW
     int OW;
     int pad_h, pad_w;
+    int tma_reduce;            // epilogue: TMA reduce-add boxes (1) or per-element atomics (0)
 };
+
+// dW as (C, taps, F), box (32 channels, 1 tap, 32 filters), 128-byte swizzle: channels / filters past the end are clipped
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *m, const void *src, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 
 // TAPS consecutive filter taps share one dY tile per stage (their X tiles differ only by the tap
 // shift): 1/TAPS of the dY traffic from L2 and TAPS x the MMA time per barrier round trip.
@@ -611,7 +620,8 @@ template <int CN, int TAPS> struct WgradCfg {
 
 template <int CN, int TAPS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                  const __grid_constant__ CUtensorMap tmDW, const WgradParams p) {
     using Cfg = WgradCfg<CN, TAPS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -712,6 +722,36 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
             tc_fence_after();
             const int f = ft * 128 + q * 32 + lane;
             constexpr int CHUNK = (CN >= 32) ? 32 : 16;
+            if (CHUNK == 32 && p.tma_reduce) {
+                // the operand ring is idle (every MMA has completed): two 32 x 128 B staging tiles per epilogue warp;
+                // one reduce-add box per (tap, 32 channels) instead of 1024 atomics (see conv_wgrad_halo.cu)
+                uint8_t *mine = smem + q * 2 * 4096;
+                int nb = 0;
+#pragma unroll 1
+                for (int t = 0; t < TAPS; ++t) {
+#pragma unroll 1
+                    for (int c0 = 0; c0 < CN; c0 += 32, ++nb) {
+                        if (ct * CN + c0 >= p.C) break;
+                        uint8_t *st = mine + (nb & 1) * 4096;
+                        if (nb >= 2) { if (lane == 0) tma_store_wait_read1(); __syncwarp(); }
+                        uint32_t r[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * CN + c0), r);
+                        tmem_ld_wait();
+                        uint8_t *dst = st + lane * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<uint4 *>(dst + ((j ^ (lane & 7)) * 16)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_reduce_add_3d(&tmDW, st, ct * CN + c0, tap0 + t, ft * 128 + q * 32);
+                            tma_store_commit();
+                        }
+                    }
+                }
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+            } else
 #pragma unroll 1
             for (int t = 0; t < TAPS; ++t) {
                 float *row = p.dw + ((long long)f * p.ntaps + tap0 + t) * p.C + ct * CN;
@@ -740,7 +780,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 }
 
 template <int CN, int TAPS>
-int launch_wgrad(const CUtensorMap &tmDY, const CUtensorMap &tmX, const WgradParams &p, cudaStream_t st) {
+int launch_wgrad(const CUtensorMap &tmDY, const CUtensorMap &tmX, const CUtensorMap &tmDW, const WgradParams &p, cudaStream_t st) {
     using Cfg = WgradCfg<CN, TAPS>;
     static bool configured_dev[16] = {};
     bool &configured = configured_dev[current_device_slot()];
@@ -749,7 +789,7 @@ int launch_wgrad(const CUtensorMap &tmDY, const CUtensorMap &tmX, const WgradPar
         configured = true;
     }
     int grid = p.f_tiles * p.c_tiles * (p.ntaps / TAPS) * p.splits;
-    conv_wgrad_kernel<CN, TAPS><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tmDY, tmX, p);
+    conv_wgrad_kernel<CN, TAPS><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tmDY, tmX, tmDW, p);
     return after_launch("conv_wgrad_kernel");
 }
 
@@ -979,18 +1019,26 @@ int conv_wgrad_tc(const float *x, const float *dy, float *dw, int N, int C, int 
     int xbox[4] = {32, OW, p.th, p.tn};
     e = make_tmap_f32(&tmX, x, 4, xdims, xstr, xbox, true);
     if (e) return e;
+    static const bool force_redg = [] { const char *v = getenv("SN_WGRAD_REDG"); return v && v[0] == '1'; }();
+    p.tma_reduce = force_redg ? 0 : 1;
+    CUtensorMap tmDW;
+    long long wdims[3] = {C, p.ntaps, F};
+    long long wstr[3] = {1, C, (long long)p.ntaps * C};
+    int wbox[3] = {32, 1, 32};
+    e = make_tmap_f32(&tmDW, dw, 3, wdims, wstr, wbox, false);
+    if (e) return e;
     if (TAPS == 3) {
         switch (CN) {
-            case 32: return launch_wgrad<32, 3>(tmDY, tmX, p, st);
-            case 64: return launch_wgrad<64, 3>(tmDY, tmX, p, st);
-            default: return launch_wgrad<128, 3>(tmDY, tmX, p, st);
+            case 32: return launch_wgrad<32, 3>(tmDY, tmX, tmDW, p, st);
+            case 64: return launch_wgrad<64, 3>(tmDY, tmX, tmDW, p, st);
+            default: return launch_wgrad<128, 3>(tmDY, tmX, tmDW, p, st);
         }
     }
     switch (CN) {
-        case 32: return launch_wgrad<32, 1>(tmDY, tmX, p, st);
-        case 64: return launch_wgrad<64, 1>(tmDY, tmX, p, st);
-        case 128: return launch_wgrad<128, 1>(tmDY, tmX, p, st);
-        default: return launch_wgrad<256, 1>(tmDY, tmX, p, st);
+        case 32: return launch_wgrad<32, 1>(tmDY, tmX, tmDW, p, st);
+        case 64: return launch_wgrad<64, 1>(tmDY, tmX, tmDW, p, st);
+        case 128: return launch_wgrad<128, 1>(tmDY, tmX, tmDW, p, st);
+        default: return launch_wgrad<256, 1>(tmDY, tmX, tmDW, p, st);
     }
 }
 

@@ -17,7 +17,12 @@
 //     every descriptor below is a 32-bit add on a precomputed base.
 //
 // Both operands are MN-major fp32 in the 128B-swizzle/32B-atom layout (see conv_tc.cu).  Split over
-// pixel blocks across CTAs, red.global.add.v4.f32 epilogue (= the reference's `+=`).
+// pixel blocks across CTAs; the partial tiles are added into dW (= the reference's `+=`) by TMA
+// REDUCE-ADD stores: an epilogue warp stages its 32 filters x kw taps x 32 channels in the (now idle)
+// operand ring, 128-byte swizzled, and one cp.reduce.async.bulk.tensor hands the 12 KB box to the L2
+// adders.  (Per-lane red.global.add.v4.f32 — the fallback when the ring is too small — kept the four
+// epilogue warps in the LSU for as long as the whole main loop took: ncu, 35 % of all warp samples
+// behind the REDG queue.)
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cuda_bf16.h>
@@ -56,15 +61,25 @@ struct HaloP {
     int pad_h, pad_w;
     int krow[HB_PB / 8];       // halo row index of the first pixel of each K-step
     unsigned b_sbo;            // stride between the two K groups of one K-step in the halo tile
+    int red_bufs;              // staging buffers (kw*32 rows x 128 B) per epilogue warp for the TMA reduce-add epilogue; 0: red.global
 };
 
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// dW as (C, taps, F): box (32 channels, kw taps, 32 filters), 128-byte swizzle; filters past F are clipped by the TMA
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *m, const void *src, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 template <int CN, bool BF16>
 __global__ void __launch_bounds__(HB_THREADS, 1)
-conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const HaloP p) {
+conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                       const __grid_constant__ CUtensorMap tmDW, const HaloP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + p.stages * p.stage_bytes);
@@ -167,6 +182,39 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
             mbar_wait_sleep(acc_full, 0);
             tc_fence_after();
             const int f = ft * 128 + q * 32 + lane;
+            if (p.red_bufs > 0) {
+                // every MMA has completed, so every operand stage has been consumed: the ring is staging space now
+                const int buf_bytes = p.kw * 32 * 128;
+                uint8_t *mine = smem + q * p.red_bufs * buf_bytes;
+                int nb = 0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < CN; c0 += 32, ++nb) {
+                    uint8_t *st = mine + (nb % p.red_bufs) * buf_bytes;
+                    if (nb >= p.red_bufs) {                   // the box that used this buffer must have been read
+                        if (lane == 0) { if (p.red_bufs == 1) tma_store_wait_read(); else tma_store_wait_read1(); }
+                        __syncwarp();
+                    }
+#pragma unroll 1
+                    for (int v = 0; v < p.kw; ++v) {
+                        uint32_t r[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(v * CN + c0), r);
+                        tmem_ld_wait();
+                        const int row = lane * p.kw + v;      // box order: channel fastest, then tap, then filter
+                        uint8_t *dst = st + row * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<uint4 *>(dst + ((j ^ (row & 7)) * 16)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_reduce_add_3d(&tmDW, st, ct * CN + c0, u * p.kw, ft * 128 + q * 32);
+                        tma_store_commit();
+                    }
+                }
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+            } else
 #pragma unroll 1
             for (int v = 0; v < p.kw; ++v) {
                 float *row = p.dw + ((long long)f * p.ntaps + u * p.kw + v) * p.C + ct * CN;
@@ -210,14 +258,14 @@ int cn_for(int C, int kw) {
 }
 
 template <int CN, bool BF16>
-int launch_halo(const CUtensorMap &tmDY, const CUtensorMap &tmX, const HaloP &p, int grid, int smem, cudaStream_t st) {
+int launch_halo(const CUtensorMap &tmDY, const CUtensorMap &tmX, const CUtensorMap &tmDW, const HaloP &p, int grid, int smem, cudaStream_t st) {
     static int configured_dev[16] = {};
     int &configured = configured_dev[current_device_slot()];
     if (configured < smem) {
         SN_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel<CN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
-    SN_CUDA(launch_dependent(conv_wgrad_halo_kernel<CN, BF16>, dim3(grid), dim3(HB_THREADS), (size_t)smem, st, tmDY, tmX, p));
+    SN_CUDA(launch_dependent(conv_wgrad_halo_kernel<CN, BF16>, dim3(grid), dim3(HB_THREADS), (size_t)smem, st, tmDY, tmX, tmDW, p));
     return after_launch("conv_wgrad_halo_kernel");
 }
 
@@ -281,10 +329,20 @@ int conv_wgrad_halo_tc(const void *x, const void *dy, float *dw, int N, int C, i
     int xbox[4] = {elems, p.Wp, p.th, p.tn};
     e = make_tmap(&tmX, x, 4, xdims, xstr, xbox, !bf16, bf16);
     if (e) return e;
+    // reduce-add epilogue: as many staging buffers per epilogue warp as the idle ring holds (all chunks, else 2, else 1)
+    static const bool force_redg = [] { const char *e = getenv("SN_WGRAD_REDG"); return e && e[0] == '1'; }();
+    const int chunks = CN / 32, buf_bytes = kw * 32 * 128, ring = p.stages * p.stage_bytes;
+    p.red_bufs = force_redg ? 0 : (4 * chunks * buf_bytes <= ring ? chunks : (8 * buf_bytes <= ring ? 2 : (4 * buf_bytes <= ring ? 1 : 0)));
+    CUtensorMap tmDW;
+    long long wdims[3] = {C, p.ntaps, F};
+    long long wstr[3] = {1, C, (long long)p.ntaps * C};
+    int wbox[3] = {32, kw, 32};
+    e = make_tmap_f32(&tmDW, dw, 3, wdims, wstr, wbox, false);
+    if (e) return e;
     const int smem = p.stages * p.stage_bytes + 1024 + 256;
     const int grid = items * p.splits;
-    if (bf16) return CN == 128 ? launch_halo<128, true>(tmDY, tmX, p, grid, smem, st) : launch_halo<64, true>(tmDY, tmX, p, grid, smem, st);
-    return CN == 128 ? launch_halo<128, false>(tmDY, tmX, p, grid, smem, st) : launch_halo<64, false>(tmDY, tmX, p, grid, smem, st);
+    if (bf16) return CN == 128 ? launch_halo<128, true>(tmDY, tmX, tmDW, p, grid, smem, st) : launch_halo<64, true>(tmDY, tmX, tmDW, p, grid, smem, st);
+    return CN == 128 ? launch_halo<128, false>(tmDY, tmX, tmDW, p, grid, smem, st) : launch_halo<64, false>(tmDY, tmX, tmDW, p, grid, smem, st);
 }
 
 }  // namespace sn

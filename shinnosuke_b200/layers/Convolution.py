@@ -240,8 +240,18 @@ class Conv2D(Layer):
         geom = (N, C, H, Wd, self.filter_nums, kh, kw, self.stride, self.pad_size[0], self.pad_size[1])
         bf16 = self.precision == 'bf16'
         needs_dx = any(layer.require_grads for layer in self.inbounds)
-        return (bool(bf16 and self._xb is not None and self._bf16_ok(2, geom)),
+        return (bool(bf16 and ((self._xb is not None and self._bf16_ok(2, geom)) or self._stem_wg16(geom))),
                 bool(bf16 and needs_dx and self._bf16_ok(1, geom)))
+
+    def _stem_wg16(self, geom):
+        """The tiny-C stem: weight gradient from the fp32 input and the bf16 gradient map (csrc/conv_stem_tc.cu)."""
+        if self._xb is not None:
+            return False
+        key = ('stem_wg16',) + tuple(geom)
+        cache = self.__dict__.setdefault('_bf16_support', {})
+        if key not in cache:
+            cache[key] = bool(lib.load().sn_conv2d_stem_wgrad_dybf16_supported(*geom))
+        return cache[key]
 
     def _x3_ok(self, op, geom):
         key = ('x3', op) + tuple(geom)
@@ -312,6 +322,9 @@ class Conv2D(Layer):
         # our gradient map) and the bf16 copy of that map while it wrote it
         db_done = bool(self.__dict__.pop('_db_done', False))
         gb_ready = bool(self.__dict__.pop('_gb_ready', False))
+        stem16 = bool(wgrad_bf16 and self._xb is None)
+        if stem16 and not gb_ready:
+            wgrad_bf16 = stem16 = False      # only worth it when the bf16 map comes for free (fused BN+pool backward)
         gb = None
         if wgrad_bf16 or dgrad_bf16:
             gb = self._bf16_buf('dy_bf16', g.size)
@@ -322,7 +335,9 @@ class Conv2D(Layer):
             xb = self._xb
 
             def wgrad():
-                if wgrad_bf16:
+                if stem16:
+                    lib.sn_conv2d_stem_wgrad_dybf16(x.ptr, gb.data_ptr(), W.grads.ptr, db, *geom, st)
+                elif wgrad_bf16:
                     lib.sn_conv2d_wgrad_bf16(xb.data_ptr(), gb.data_ptr(), g.ptr if db is not None else None, W.grads.ptr, db, *geom, st)
                 else:
                     lib.sn_conv2d_wgrad(x.ptr, g.ptr, W.grads.ptr, db, *geom, 1, prec, st)

@@ -416,3 +416,48 @@ print('pair launches', lib.sn_igemm_pair_launches())
     out = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert 'pair launches' in out.stdout
+
+
+@pytest.mark.parametrize('shape', [
+    (8, 3, 32, 32, 64, 3, 1, 1),        # cfg3 stem (one 64-filter atom, M = 128 reads the patch tile as its upper half)
+    (8, 3, 32, 32, 128, 3, 1, 1),       # two filter atoms
+    (8, 3, 32, 32, 192, 3, 1, 1),       # two filter tiles, the second half empty
+    (20, 3, 29, 31, 48, 3, 2, 0),       # ragged everything, stride 2, F not a multiple of 64
+    (16, 1, 28, 28, 16, 2, 1, 0),       # K = 4
+    (16, 2, 24, 24, 32, 3, 1, 1),       # C = 2
+    (16, 1, 28, 28, 32, 5, 1, 2),       # 5x5 taps
+    (300, 3, 32, 32, 64, 3, 1, 1),      # more 64-pixel stages than CTAs x ring depth: every ring wraps several times
+])
+def test_stem_wgrad_from_the_bf16_gradient_map(shape):
+    """sn_conv2d_stem_wgrad_dybf16 (bf16 tier: the stem's dW / db from the fp32 input and the bf16 copy of dY that the
+    fused BN+pool backward writes).  Data with <= 8 significant bits make every bf16 product exact, so the result must
+    match the float64 oracle to fp32 accumulation accuracy: a sharp check of the swizzled layouts, descriptors and
+    rings.  Random data must then stay inside the bf16 tier's 1e-2."""
+    import torch
+    from shinnosuke_b200._lib import lib
+    N, C, H, W, F, k, stride, pad = shape
+    assert lib.sn_conv2d_stem_wgrad_dybf16_supported(N, C, H, W, F, k, k, stride, pad, pad)
+    oh, ow = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    r = np.random.default_rng(N * 131 + F)
+    for exact in (True, False):
+        if exact:
+            x = r.integers(-8, 9, (N, C, H, W)).astype(np.float64) / 8.0
+            g = r.integers(-8, 9, (N, F, oh, ow)).astype(np.float64) / 4.0
+        else:
+            x = r.standard_normal((N, C, H, W)).astype(np.float32).astype(np.float64)
+            g = r.standard_normal((N, F, oh, ow)).astype(np.float32).astype(np.float64)
+        _, cache = O.conv2d_forward(x, np.zeros((F, C, k, k)), np.zeros((1, F)), stride, (pad, pad), 'linear')
+        _, dw_ref, db_ref = O.conv2d_backward(g, cache, need_dx=False)
+        xd = torch.tensor(x.transpose(0, 2, 3, 1), dtype=torch.float32, device='cuda').contiguous()
+        gd = torch.tensor(g.transpose(0, 2, 3, 1), dtype=torch.float32, device='cuda').to(torch.bfloat16).contiguous()
+        dw = torch.zeros((F, k, k, C), dtype=torch.float32, device='cuda')
+        db = torch.zeros((F,), dtype=torch.float32, device='cuda')
+        lib.sn_conv2d_stem_wgrad_dybf16(xd.data_ptr(), gd.data_ptr(), dw.data_ptr(), db.data_ptr(), N, C, H, W, F, k, k,
+                                        stride, pad, pad, None)
+        lib.sn_conv2d_stem_wgrad_dybf16(xd.data_ptr(), gd.data_ptr(), dw.data_ptr(), None, N, C, H, W, F, k, k,
+                                        stride, pad, pad, None)           # += semantics, no bias gradient this time
+        torch.cuda.synchronize()
+        got_dw = dw.cpu().numpy().astype(np.float64).transpose(0, 3, 1, 2)            # [F][kh][kw][C] -> (F, C, kh, kw)
+        tol = 2e-6 if exact else 1e-2
+        assert rel_err(got_dw, 2.0 * dw_ref) < tol, ('dw', exact)
+        assert rel_err(db.cpu().numpy().astype(np.float64), np.asarray(db_ref).reshape(-1)) < tol, ('db', exact)
