@@ -258,7 +258,7 @@ def kernel_work(name, a, precision):
         # one timestep: the recurrent product h . Wh (N x H x 4H) + the gate tensors once
         N, H = (a[2], a[3]) if name == 'sn_lstm_step_fwd' else (a[1], a[2])
         return 2.0 * N * H * 4 * H, 4.0 * (4 * H * H + 2 * N * 4 * H + 4 * N * H)
-    if name in ('sn_lstm_seq_fwd', 'sn_lstm_seq_bwd'):
+    if name in ('sn_lstm_seq_fwd', 'sn_lstm_seq_bwd', 'sn_lstm_seq_fwd_tc', 'sn_lstm_seq_bwd_tc'):
         # the whole recurrence: T dependent steps (latency-bound by construction); algorithmic work = the
         # recurrent products + the per-step tensors read / written once (zx or dh, acts, c, h / dz)
         T, N, H = a[-3:]

@@ -477,6 +477,15 @@ SN_API int sn_lstm_seq_fwd(const float *zx, const float *wh, const float *h0, co
                     float *h_all, float *h_seq, int T, int N, int H, void *stream);
 SN_API int sn_lstm_seq_bwd(const float *dh_last, const float *dh_seq, const float *wh, const float *acts, const float *c_all,
                     int c0_is_zero, float *dz, int T, int N, int H, void *stream);
+/* The same recurrence (layers/Recurrent.py:293-309 forward, :326-366 backward) with the per-step product
+ * h_{t-1}.Wh^T / dz_{t+1}.Wh on the tensor pipe (H = 128, bf16 tier: bf16 operands, fp32 accumulation and
+ * gate arithmetic): Wh resident in shared memory as the K-major UMMA A operand, 8 batch rows per CTA as the
+ * B operand, D transposed in tensor memory (lane = hidden unit), csrc/recurrent_tc.cu.  Same arguments. */
+SN_API int sn_lstm_seq_tc_supported(int N, int H);
+SN_API int sn_lstm_seq_fwd_tc(const float *zx, const float *wh, const float *h0, const float *c0, float *acts, float *c_all,
+                       float *h_all, float *h_seq, int T, int N, int H, void *stream);
+SN_API int sn_lstm_seq_bwd_tc(const float *dh_last, const float *dh_seq, const float *wh, const float *acts, const float *c_all,
+                       int c0_is_zero, float *dz, int T, int N, int H, void *stream);
 
 /* ------------------------------------------------------------------ loss */
 /* Softmax._forward, utils/Activator.py:108-110 (row-wise; the reference's global shift cancels) */

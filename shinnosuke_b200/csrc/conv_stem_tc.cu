@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
         *reinterpret_cast<float *>(sB + f * 128 + chunk * 16 + (k & 3) * 4) = v;
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < SF_ABUF; ++i) { mbar_init(&a_full[i], SF_BUILDERS); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < SF_ABUF; ++i) { mbar_init(&a_full[i], SF_BUILDERS / 32); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], SF_EPI_WARPS / 2); }
         for (int i = 0; i < PATCH_STAGES; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], SF_BUILDERS / 32); }
         tma_prefetch_desc(&tmX);
@@ -233,10 +233,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1) stem_fprop_kernel(const __grid_
             *reinterpret_cast<float4 *>(row + (((2 * kq0 + 2) ^ (r & 7)) * 16)) = make_float4(col2[0], col2[1], col2[2], col2[3]);
             *reinterpret_cast<float4 *>(row + (((2 * kq0 + 3) ^ (r & 7)) * 16)) = make_float4(col2[4], col2[5], col2[6], col2[7]);
             fence_proxy_async();               // make the generic-proxy writes visible to the tensor core
-            mbar_arrive(&a_full[buf]);
+            __syncwarp();                      // every lane's stores are fenced, its patch reads complete
+            if (lane == 0) { mbar_arrive(&a_full[buf]); mbar_arrive(&p_empty[ps]); }      // ONE arrival per warp (see stem_wgrad_kernel)
             if (++buf == SF_ABUF) { buf = 0; phase ^= 1; }
-            __syncwarp();                      // every lane's patch reads are complete (their values were just stored)
-            if (lane == 0) mbar_arrive(&p_empty[ps]);
             if (++ps == PATCH_STAGES) { ps = 0; pphase ^= 1; }
         }
     } else {
@@ -374,8 +373,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmDY);
-        // full: 1 arrive.expect_tx by the TMA thread + one arrival per builder thread
-        for (int i = 0; i < SW_STAGES; ++i) { mbar_init(&full[i], 1 + SW_BUILDERS); mbar_init(&empty[i], 1); }
+        // full: 1 arrive.expect_tx by the TMA thread + one arrival per builder warp
+        for (int i = 0; i < SW_STAGES; ++i) { mbar_init(&full[i], 1 + SW_BUILDERS / 32); mbar_init(&empty[i], 1); }
         mbar_init(acc_full, 1);
         for (int i = 0; i < SW_PATCHES; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], SW_BUILDERS / 32); }
         tma_prefetch_desc(&tmX);
@@ -393,13 +392,17 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
         if (warp == 0) {
             {
                 // one warp is both the TMA producer and the MMA issuer (the MMAs are negligible here): it runs the
-                // loads SW_STAGES ahead of the MMAs.  Warp-uniform control flow, the elected lane issues.
+                // loads SW_STAGES - 1 ahead of the MMAs.  Warp-uniform control flow, the elected lane issues.
                 constexpr uint32_t idesc = BF16 ? make_idesc(1, 128, 64, 1, 1) : make_idesc(2, 128, 32, 1, 1);
                 constexpr int A_ELEMS = BF16 ? 64 : 32;          // filters per dY atom
                 int ld = 0, ld_stage = 0; uint32_t ld_phase = 0;
                 int stage = 0; uint32_t phase = 0;
                 for (int s = 0; s < nst; ++s) {
-                    while (ld < nst && ld < s + SW_STAGES) {
+                    // SW_STAGES - 1 ahead, not SW_STAGES: the slot refilled now is the one stage s-2 used, whose MMAs
+                    // completed long ago.  Refilling the slot of stage s-1 made this warp wait for the MMAs it had
+                    // just issued before it could even look at stage s: one MMA latency + one TMA issue per stage,
+                    // serially — the pace of the kernel (1380 cycles per stage whatever builders / rings did).
+                    while (ld < nst && ld < s + SW_STAGES - 1) {
                         mbar_wait(&empty[ld_stage], ld_phase ^ 1);
                         uint8_t *sa = smem + ld_stage * SW_STAGE_BYTES;
                         if (elect_one()) {
@@ -414,19 +417,22 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
                     }
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * SW_STAGE_BYTES);
+                    // descriptors = a precomputed template | (start address >> 4): one add per MMA operand
+                    const uint32_t sa16 = smem_u32(smem + stage * SW_STAGE_BYTES) >> 4;
                     if constexpr (BF16) {
+                        const uint64_t tmpl = make_smem_desc(0, SW_ATOM, 1024, LAYOUT_SW128);
 #pragma unroll
                         for (int k = 0; k < SW_PB / 16; ++k) {       // K-step = 16 pixel rows = two 8-row K groups 1024 B apart
-                            const uint64_t adesc = make_smem_desc(sa + k * 2048, SW_ATOM, 1024, LAYOUT_SW128);
-                            const uint64_t bdesc = make_smem_desc(sa + SW_A_BYTES + k * 2048, SW_ATOM, 1024, LAYOUT_SW128);
+                            const uint64_t adesc = tmpl | (uint64_t)(sa16 + k * 128);
+                            const uint64_t bdesc = tmpl | (uint64_t)(sa16 + (SW_A_BYTES >> 4) + k * 128);
                             if (elect_one()) mma_bf16(tmem_base, adesc, bdesc, idesc, (s | k) != 0 ? 1u : 0u);
                         }
                     } else {
+                        const uint64_t tmpl = make_smem_desc(0, SW_ATOM, 512, LAYOUT_SW128_BASE32B);
 #pragma unroll
                         for (int k = 0; k < SW_PB / 8; ++k) {
-                            const uint64_t adesc = make_smem_desc(sa + k * 1024, SW_ATOM, 512, LAYOUT_SW128_BASE32B);
-                            const uint64_t bdesc = make_smem_desc(sa + SW_A_BYTES + k * 1024, SW_ATOM, 512, LAYOUT_SW128_BASE32B);
+                            const uint64_t adesc = tmpl | (uint64_t)(sa16 + k * 64);
+                            const uint64_t bdesc = tmpl | (uint64_t)(sa16 + (SW_A_BYTES >> 4) + k * 64);
                             if (elect_one()) mma_tf32(tmem_base, adesc, bdesc, idesc, (s | k) != 0 ? 1u : 0u);
                         }
                     }
@@ -438,12 +444,45 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
                 __syncwarp();
             }
         } else if (warp == 1) {
-            // patch producer: SW_PATCHES stages ahead of the builders
+            // patch producer: SW_PATCHES stages ahead of the builders.  The geometry of a stage (two divisions by ow, two
+            // by oh, the row span) is a ~100-instruction dependent chain full of I2F / F2I / R2UR round trips: done per
+            // stage by this one warp it was a serial ~1000 cycles.  Each LANE now works out one of the next 32 stages,
+            // and the per-stage work is five shuffles, the expect_tx and the TMA.
             int ps = 0; uint32_t pphase = 0;
-            for (int s = 0; s < nst; ++s) {
-                mbar_wait(&p_empty[ps], pphase ^ 1);
-                patch_produce(p, &tmX, &tmXr, p.R64, patch + ps * SW_PATCH_FLOATS, pinfo + ps, &p_full[ps], (t0 + s) * SW_PB, SW_PB, lane);
-                if (++ps == SW_PATCHES) { ps = 0; pphase ^= 1; }
+            for (int sb = 0; sb < nst; sb += 32) {
+                int g_lo = 0, rows = 0, i0s = 0, n0 = 0, fast = 0;
+                if (sb + lane < nst) {
+                    const int pix0 = (t0 + sb + lane) * SW_PB, pix1 = min(pix0 + SW_PB, p.P) - 1;
+                    int j0, j, i0, i1;
+                    const int q0 = fast_div(pix0, p.ow, p.inv_ow, j0);
+                    n0 = fast_div(q0, p.oh, p.inv_oh, i0);
+                    const int q1 = fast_div(pix1, p.ow, p.inv_ow, j), n1 = fast_div(q1, p.oh, p.inv_oh, i1);
+                    g_lo = n0 * p.Hp + i0 * p.stride;
+                    rows = n1 * p.Hp + i1 * p.stride + p.kh - 1 - g_lo + 1;
+                    i0s = i0 * p.stride;
+                    fast = (p.R64 > 0 && j0 == 0 && n0 == n1 && rows == p.R64) ? 1 : 0;
+                }
+                const int cnt = min(32, nst - sb);
+                for (int l = 0; l < cnt; ++l) {
+                    const int g_lo_s = __shfl_sync(0xffffffffu, g_lo, l), rows_s = __shfl_sync(0xffffffffu, rows, l);
+                    const int i0_s = __shfl_sync(0xffffffffu, i0s, l), n0_s = __shfl_sync(0xffffffffu, n0, l);
+                    const int fast_s = __shfl_sync(0xffffffffu, fast, l);
+                    mbar_wait(&p_empty[ps], pphase ^ 1);
+                    float *dst = patch + ps * SW_PATCH_FLOATS;
+                    if (lane == 0) { pinfo[ps] = g_lo_s; mbar_expect_tx(&p_full[ps], (uint32_t)(rows_s * p.BW * 4)); }
+                    __syncwarp();
+                    if (fast_s) {
+                        if (elect_one()) tma_load_3d(dst, &tmXr, &p_full[ps], p.c0, i0_s - p.ph, n0_s);
+                    } else {
+                        int n = n0_s, hp = i0_s;          // one box per padded row (tiles that straddle images / start mid-row)
+                        for (int row = 0; row < rows_s; ++row) {
+                            if (elect_one()) tma_load_3d(dst + row * p.BW, &tmX, &p_full[ps], p.c0, hp - p.ph, n);
+                            if (++hp == p.Hp) { hp = 0; ++n; }
+                        }
+                    }
+                    __syncwarp();
+                    if (++ps == SW_PATCHES) { ps = 0; pphase ^= 1; }
+                }
             }
         } else if (warp < 2 + SW_GROUPS * SW_BUILDERS / 32) {
             // column builders: thread (r, kq) of group g builds k = 8kq..8kq+7 (one 32-byte chunk) of pixel
@@ -472,10 +511,12 @@ __global__ void __launch_bounds__(SW_THREADS, 1) stem_wgrad_kernel(const __grid_
                     *reinterpret_cast<float4 *>(dst) = make_float4(col[0], col[1], col[2], col[3]);
                     *reinterpret_cast<float4 *>(dst + 16) = make_float4(col[4], col[5], col[6], col[7]);
                 }
+                // ONE arrival per warp: 256 per-thread arrivals on one mbarrier serialise in the shared-memory atomic
+                // unit (~4 cycles each) and were the pace of this kernel — ~1380 cycles per stage whatever the
+                // number of builder groups, the depth of the rings or the width of dY
                 fence_proxy_async();
-                mbar_arrive(&full[stage]);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&p_empty[ps]);
+                if (lane == 0) { mbar_arrive(&full[stage]); mbar_arrive(&p_empty[ps]); }
             }
         } else {
             // epilogue (last four warps): dW[f][k] += D[f][k], db[f] += D[f][K]
@@ -622,16 +663,18 @@ int conv_stem_wgrad_tc(const float *x, const void *dy, float *dw, float *db, int
     if (e) return e;
     static bool configured_dev[16][4] = {};
     bool &configured = configured_dev[current_device_slot()][(dy_bf16 ? 2 : 0) + (small ? 1 : 0)];
-    auto go = [&](auto kernel) -> int {
-        if (!configured) {
-            SN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            configured = true;
-        }
-        SN_CUDA(launch_dependent(kernel, dim3(ctas, f_tiles), dim3(SW_THREADS), (size_t)smem, st, tmDY, tmX, tmXr, p));
-        return after_launch("stem_wgrad_kernel");
-    };
-    if (dy_bf16) return small ? go(stem_wgrad_kernel<1, true>) : go(stem_wgrad_kernel<2, true>);
-    return small ? go(stem_wgrad_kernel<2, false>) : go(stem_wgrad_kernel<4, false>);
+#define SN_STEM_WGRAD_GO(NA, BF)                                                                                             \
+    do {                                                                                                                    \
+        if (!configured) {                                                                                                  \
+            SN_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<NA, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));    \
+            configured = true;                                                                                              \
+        }                                                                                                                   \
+        SN_CUDA(launch_dependent(stem_wgrad_kernel<NA, BF>, dim3(ctas, f_tiles), dim3(SW_THREADS), (size_t)smem, st, tmDY, tmX, tmXr, p)); \
+        return after_launch("stem_wgrad_kernel");                                                                           \
+    } while (0)
+    if (dy_bf16) { if (small) SN_STEM_WGRAD_GO(1, true); else SN_STEM_WGRAD_GO(2, true); }
+    if (small) SN_STEM_WGRAD_GO(2, false); else SN_STEM_WGRAD_GO(4, false);
+#undef SN_STEM_WGRAD_GO
 }
 
 }  // namespace sn

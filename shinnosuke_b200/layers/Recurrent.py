@@ -114,9 +114,11 @@ class LSTM(Recurrent):
             lib.sn_memcpy_d2d(c_all.ptr, c_all.ptr + T * step, step, st)
         hseq = self._buf('h_seq', (N, T, H), 'flat') if self.return_sequences else None
         self._seq = bool(lib.load().sn_lstm_seq_supported(N, H))
+        # bf16 tier, H = 128: the per-step product on the tensor pipe (csrc/recurrent_tc.cu)
+        self._seq_tc = bool(self._seq and self.precision == 'bf16' and lib.load().sn_lstm_seq_tc_supported(N, H))
         if self._seq:
             # the whole recurrence in one launch: clusters keep Wh in registers, h_t travels through DSMEM
-            lib.sn_lstm_seq_fwd(zx.ptr, wh, h_all.ptr if carry else None, c_all.ptr if carry else None, acts.ptr, c_all.ptr,
+            (lib.sn_lstm_seq_fwd_tc if self._seq_tc else lib.sn_lstm_seq_fwd)(zx.ptr, wh, h_all.ptr if carry else None, c_all.ptr if carry else None, acts.ptr, c_all.ptr,
                                 h_all.ptr, None if hseq is None else hseq.ptr, T, N, H, st)
         for t in range(0 if not self._seq else T, T):
             first = t == 0 and not carry
@@ -152,10 +154,11 @@ class LSTM(Recurrent):
         dc = self._buf('dc', (N, H), 'flat')
         step = N * H * 4
         if self._seq:
+            seq_bwd = lib.sn_lstm_seq_bwd_tc if getattr(self, '_seq_tc', False) else lib.sn_lstm_seq_bwd
             if self.return_sequences:
-                lib.sn_lstm_seq_bwd(None, g.ptr, wh, acts.ptr, c_all.ptr, 1 if self._first_zero else 0, dz.ptr, T, N, H, st)
+                seq_bwd(None, g.ptr, wh, acts.ptr, c_all.ptr, 1 if self._first_zero else 0, dz.ptr, T, N, H, st)
             else:
-                lib.sn_lstm_seq_bwd(g.ptr, None, wh, acts.ptr, c_all.ptr, 1 if self._first_zero else 0, dz.ptr, T, N, H, st)
+                seq_bwd(g.ptr, None, wh, acts.ptr, c_all.ptr, 1 if self._first_zero else 0, dz.ptr, T, N, H, st)
         for t in range(T - 1 if not self._seq else -1, -1, -1):
             last = t == T - 1
             if self.return_sequences:

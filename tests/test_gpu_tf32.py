@@ -422,7 +422,7 @@ print('pair launches', lib.sn_igemm_pair_launches())
     (8, 3, 32, 32, 64, 3, 1, 1),        # cfg3 stem (one 64-filter atom, M = 128 reads the patch tile as its upper half)
     (8, 3, 32, 32, 128, 3, 1, 1),       # two filter atoms
     (8, 3, 32, 32, 192, 3, 1, 1),       # two filter tiles, the second half empty
-    (20, 3, 29, 31, 48, 3, 2, 0),       # ragged everything, stride 2, F not a multiple of 64
+    (20, 3, 29, 32, 48, 3, 2, 0),       # ragged pixel tiles, stride 2 (tiles straddle images), F not a multiple of 64
     (16, 1, 28, 28, 16, 2, 1, 0),       # K = 4
     (16, 2, 24, 24, 32, 3, 1, 1),       # C = 2
     (16, 1, 28, 28, 32, 5, 1, 2),       # 5x5 taps
@@ -436,7 +436,7 @@ def test_stem_wgrad_from_the_bf16_gradient_map(shape):
     import torch
     from shinnosuke_b200._lib import lib
     N, C, H, W, F, k, stride, pad = shape
-    assert lib.sn_conv2d_stem_wgrad_dybf16_supported(N, C, H, W, F, k, k, stride, pad, pad)
+    assert lib.load().sn_conv2d_stem_wgrad_dybf16_supported(N, C, H, W, F, k, k, stride, pad, pad)
     oh, ow = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
     r = np.random.default_rng(N * 131 + F)
     for exact in (True, False):
