@@ -18,7 +18,7 @@
 // Two rows per CTA = one cell per thread and 128 CTAs at batch 256: the ~185 instructions of a cell's five
 // transcendentals are on the critical path of every step (8 rows per CTA, four cells per thread, measured
 // 2.28 us per step against 1.98 for the CUDA-core kernels — the MMAs were not the long pole).
-// fp32 everywhere except the two MMA operands (bf16, fp32 accumulation): the bf16 tier's 1e-2.
+// fp32 everywhere except the two MMA operands (bf16, fp32 accumulation) and SFU-approximated gates: the bf16 tier's 1e-2.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cuda_bf16.h>
@@ -38,7 +38,11 @@ constexpr int LT_ATOM_A = 128 * 128;       // one K-atom (64 bf16 = 128 B per ro
 constexpr int LT_ATOM_B = LT_N * 128;
 constexpr int LT_A_BYTES = 8 * LT_ATOM_A;  // forward: 4 gate tiles x 2 K-atoms; backward: 1 tile x 8 K-atoms
 
-__device__ __forceinline__ float lt_sigmoid(float z) { return 1.f / (1.f + expf(-z)); }        // utils/Activator.py:58
+// Gate non-linearities (utils/Activator.py:58, :81) on the special-function unit: ex2.approx + rcp.approx, ~1e-6
+// absolute — three orders of magnitude below the bf16 rounding of the recurrent operand this tier already accepts.
+// expf / tanhf / IEEE division cost ~185 instructions per cell, all of them on the critical path of every step.
+__device__ __forceinline__ float lt_sigmoid(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+__device__ __forceinline__ float lt_tanh(float z) { return fmaf(2.f, lt_sigmoid(2.f * z), -1.f); }
 
 // LT_CPT consecutive columns of this warp's 32 lanes
 template <int CPT>
@@ -135,15 +139,20 @@ lstm_seq_fwd_tc_kernel(const float *__restrict__ zx, const float *__restrict__ w
     const uint32_t a0 = smem_u32(s.a), b0 = smem_u32(s.b);
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(LT_CPT * half);
 
-    for (int t = 0; t < T; ++t) {
-        // this step's input projections: issued now, consumed after the MMAs
-        float zin[LT_CPT][4];
+    // The per-step operands are loaded ONE STEP AHEAD (registers): an HBM round trip is about as long as the MMAs of
+    // a step, so loads issued at the top of the step they belong to were the tail of its critical path.
+    auto load_zin = [&](int t, float (&z4)[LT_CPT][4]) {
 #pragma unroll
         for (int i = 0; i < LT_CPT; ++i) {
             const float *z = zx + ((long long)t * N + row0 + LT_CPT * half + i) * 4 * H + unit;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) zin[i][g] = live[i] ? __ldg(z + g * H) : 0.f;
+            for (int g = 0; g < 4; ++g) z4[i][g] = live[i] ? __ldg(z + g * H) : 0.f;
         }
+    };
+    float zin[LT_CPT][4], znext[LT_CPT][4];
+    load_zin(0, zin);
+    for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) load_zin(t + 1, znext);
         if (warp == 0) {
             if (elect_one()) {
 #pragma unroll
@@ -167,10 +176,10 @@ lstm_seq_fwd_tc_kernel(const float *__restrict__ zx, const float *__restrict__ w
         for (int i = 0; i < LT_CPT; ++i) {
             const float f = lt_sigmoid(__uint_as_float(zr[0][i]) + zin[i][0]);
             const float ug = lt_sigmoid(__uint_as_float(zr[1][i]) + zin[i][1]);
-            const float ct = tanhf(__uint_as_float(zr[2][i]) + zin[i][2]);
+            const float ct = lt_tanh(__uint_as_float(zr[2][i]) + zin[i][2]);
             const float o = lt_sigmoid(__uint_as_float(zr[3][i]) + zin[i][3]);
             c[i] = fmaf(f, c[i], ug * ct);                                           // layers/Recurrent.py:300-302
-            const float h = o * tanhf(c[i]);
+            const float h = o * lt_tanh(c[i]);
             if (live[i]) {
                 lt_store_bf16(s.b, LT_CPT * half + i, unit, h);
                 const int row = row0 + LT_CPT * half + i;
@@ -185,6 +194,10 @@ lstm_seq_fwd_tc_kernel(const float *__restrict__ zx, const float *__restrict__ w
         fence_proxy_async();                   // the B tile was written through the generic proxy
         __syncthreads();                       // ... by every cell thread; the accumulators have been read
         tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < LT_CPT; ++i)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) zin[i][g] = znext[i][g];
     }
     if (warp == 0) tmem_dealloc(tmem_base, 64);
 }
@@ -229,21 +242,30 @@ lstm_seq_bwd_tc_kernel(const float *__restrict__ dh_last, const float *__restric
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(LT_CPT * half);
     uint32_t phase = 0;
 
-    for (int t = T - 1; t >= 0; --t) {
-        // operands of this thread's cells, issued before the MMAs
-        float f[LT_CPT], ug[LT_CPT], ct[LT_CPT], o[LT_CPT], cv[LT_CPT], cp[LT_CPT], dh[LT_CPT];
+    struct Cell { float f, ug, ct, o, cv, cp, dh; };
+    auto load_cells = [&](int t, Cell (&cl)[LT_CPT]) {                    // (one step ahead, see the forward kernel)
 #pragma unroll
         for (int i = 0; i < LT_CPT; ++i) {
-            f[i] = ug[i] = ct[i] = o[i] = cv[i] = cp[i] = dh[i] = 0.f;
+            cl[i] = Cell{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (live[i]) {
                 const int row = row0 + LT_CPT * half + i;
                 const float *a = acts + ((long long)t * N + row) * K + unit;
-                f[i] = __ldg(a); ug[i] = __ldg(a + H); ct[i] = __ldg(a + 2 * H); o[i] = __ldg(a + 3 * H);
-                cv[i] = __ldg(c_all + ((long long)(t + 1) * N + row) * H + unit);
-                cp[i] = (t == 0 && c0_is_zero) ? 0.f : __ldg(c_all + ((long long)t * N + row) * H + unit);
-                if (dh_seq) dh[i] = __ldg(dh_seq + ((long long)row * T + t) * H + unit);
-                else if (t == T - 1 && dh_last) dh[i] = __ldg(dh_last + (long long)row * H + unit);
+                cl[i].f = __ldg(a); cl[i].ug = __ldg(a + H); cl[i].ct = __ldg(a + 2 * H); cl[i].o = __ldg(a + 3 * H);
+                cl[i].cv = __ldg(c_all + ((long long)(t + 1) * N + row) * H + unit);
+                cl[i].cp = (t == 0 && c0_is_zero) ? 0.f : __ldg(c_all + ((long long)t * N + row) * H + unit);
+                if (dh_seq) cl[i].dh = __ldg(dh_seq + ((long long)row * T + t) * H + unit);
+                else if (t == T - 1 && dh_last) cl[i].dh = __ldg(dh_last + (long long)row * H + unit);
             }
+        }
+    };
+    Cell cur[LT_CPT], nxt[LT_CPT];
+    load_cells(T - 1, cur);
+    for (int t = T - 1; t >= 0; --t) {
+        if (t > 0) load_cells(t - 1, nxt);
+        float f[LT_CPT], ug[LT_CPT], ct[LT_CPT], o[LT_CPT], cv[LT_CPT], cp[LT_CPT], dh[LT_CPT];
+#pragma unroll
+        for (int i = 0; i < LT_CPT; ++i) {
+            f[i] = cur[i].f; ug[i] = cur[i].ug; ct[i] = cur[i].ct; o[i] = cur[i].o; cv[i] = cur[i].cv; cp[i] = cur[i].cp; dh[i] = cur[i].dh;
         }
         if (t != T - 1) {
             if (warp == 0) {
@@ -272,7 +294,7 @@ lstm_seq_bwd_tc_kernel(const float *__restrict__ dh_last, const float *__restric
         }
 #pragma unroll
         for (int i = 0; i < LT_CPT; ++i) {
-            const float tc = tanhf(cv[i]);
+            const float tc = lt_tanh(cv[i]);
             const float dcv = dc[i] + dh[i] * o[i] * (1.f - tc * tc);                  // layers/Recurrent.py:337-338
             float d[4];
             d[0] = dcv * cp[i] * f[i] * (1.f - f[i]);                                  // forget gate   (:351-352)
@@ -292,6 +314,8 @@ lstm_seq_bwd_tc_kernel(const float *__restrict__ dh_last, const float *__restric
         fence_proxy_async();
         __syncthreads();
         tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < LT_CPT; ++i) cur[i] = nxt[i];
     }
     if (warp == 0) tmem_dealloc(tmem_base, 64);
 }
