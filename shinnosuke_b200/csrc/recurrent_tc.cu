@@ -136,7 +136,11 @@ lstm_seq_fwd_tc_kernel(const float *__restrict__ zx, const float *__restrict__ w
     tc_fence_after();
     const uint32_t tmem_base = *s.tmem_ptr;
     constexpr uint32_t idesc = make_idesc(1, 128, LT_N, 0, 0);
-    const uint32_t a0 = smem_u32(s.a), b0 = smem_u32(s.b);
+    // descriptors = template | (start address >> 4): one add per operand in the issuing thread.  (ncu: the tensor pipe is
+    // active ~270 cycles of a ~2250-cycle step while the cell warps wait ~1280 cycles for the commit: what a step pays
+    // for its 32 MMAs is their ISSUE, ~35 cycles per tcgen05.mma whatever its N, not their execution.)
+    const uint32_t a16 = smem_u32(s.a) >> 4, b16 = smem_u32(s.b) >> 4;
+    const uint64_t tmpl = make_smem_desc(0, 0, 1024);
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(LT_CPT * half);
 
     // The per-step operands are loaded ONE STEP AHEAD (registers): an HBM round trip is about as long as the MMAs of
@@ -159,8 +163,8 @@ lstm_seq_fwd_tc_kernel(const float *__restrict__ zx, const float *__restrict__ w
                 for (int ks = 0; ks < H / 16; ++ks)          // the four gate tiles in turn: consecutive MMAs are independent
 #pragma unroll
                     for (int m = 0; m < 4; ++m)
-                        mma_bf16(tmem_base + m * LT_N, make_smem_desc(a0 + m * 2 * LT_ATOM_A + (ks >> 2) * LT_ATOM_A + (ks & 3) * 32, 0, 1024),
-                                 make_smem_desc(b0 + (ks >> 2) * LT_ATOM_B + (ks & 3) * 32, 0, 1024), idesc, ks ? 1u : 0u);
+                        mma_bf16(tmem_base + m * LT_N, tmpl | (uint64_t)(a16 + ((m * 2 * LT_ATOM_A + (ks >> 2) * LT_ATOM_A + (ks & 3) * 32) >> 4)),
+                                 tmpl | (uint64_t)(b16 + (((ks >> 2) * LT_ATOM_B + (ks & 3) * 32) >> 4)), idesc, ks ? 1u : 0u);
                 mma_commit(s.done);
             }
             __syncwarp();
@@ -238,7 +242,11 @@ lstm_seq_bwd_tc_kernel(const float *__restrict__ dh_last, const float *__restric
     tc_fence_after();
     const uint32_t tmem_base = *s.tmem_ptr;
     constexpr uint32_t idesc = make_idesc(1, 128, LT_N, 0, 0);
-    const uint32_t a0 = smem_u32(s.a), b0 = smem_u32(s.b);
+    // descriptors = template | (start address >> 4): one add per operand in the issuing thread.  (ncu: the tensor pipe is
+    // active ~270 cycles of a ~2250-cycle step while the cell warps wait ~1280 cycles for the commit: what a step pays
+    // for its 32 MMAs is their ISSUE, ~35 cycles per tcgen05.mma whatever its N, not their execution.)
+    const uint32_t a16 = smem_u32(s.a) >> 4, b16 = smem_u32(s.b) >> 4;
+    const uint64_t tmpl = make_smem_desc(0, 0, 1024);
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(LT_CPT * half);
     uint32_t phase = 0;
 
@@ -274,8 +282,8 @@ lstm_seq_bwd_tc_kernel(const float *__restrict__ dh_last, const float *__restric
                     // latency, not its issue rate, 32 times); the cell thread adds the four partial sums
 #pragma unroll
                     for (int ks = 0; ks < K / 16; ++ks)
-                        mma_bf16(tmem_base + (ks & 3) * LT_N, make_smem_desc(a0 + (ks >> 2) * LT_ATOM_A + (ks & 3) * 32, 0, 1024),
-                                 make_smem_desc(b0 + (ks >> 2) * LT_ATOM_B + (ks & 3) * 32, 0, 1024), idesc, ks >= 4 ? 1u : 0u);
+                        mma_bf16(tmem_base + (ks & 3) * LT_N, tmpl | (uint64_t)(a16 + (((ks >> 2) * LT_ATOM_A + (ks & 3) * 32) >> 4)),
+                                 tmpl | (uint64_t)(b16 + (((ks >> 2) * LT_ATOM_B + (ks & 3) * 32) >> 4)), idesc, ks >= 4 ? 1u : 0u);
                     mma_commit(s.done);
                 }
                 __syncwarp();
