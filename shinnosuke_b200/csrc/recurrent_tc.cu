@@ -33,6 +33,8 @@ constexpr int LT_H = 128;
 constexpr int LT_ROWS = 2;                 // live batch rows per CTA
 constexpr int LT_N = 16;                   // UMMA N (M = 128 needs N % 16 == 0): rows 2..15 of the B tile stay zero
 constexpr int LT_CPT = LT_ROWS / 2;        // cells per thread
+constexpr int LT_ISSUERS = 1;              // warps that issue a step's MMAs (1, 2 or 4; two issuers on different SM
+                                           // sub-partitions measured exactly the same step time as one: 78.2 / 84.8 us)
 constexpr int LT_THREADS = 256;            // thread = (unit, half): cells (rows LT_CPT*half .. +LT_CPT-1, unit)
 constexpr int LT_ATOM_A = 128 * 128;       // one K-atom (64 bf16 = 128 B per row) of a 128-row operand tile
 constexpr int LT_ATOM_B = LT_N * 128;
@@ -113,7 +115,7 @@ lstm_seq_fwd_tc_kernel(const float *__restrict__ zx, const float *__restrict__ w
             make_uint4(lt_pack2(lo.x, lo.y), lt_pack2(lo.z, lo.w), lt_pack2(hi.x, hi.y), lt_pack2(hi.z, hi.w));
     }
     for (int i = threadIdx.x; i < 2 * LT_ATOM_B / 16; i += LT_THREADS) reinterpret_cast<uint4 *>(s.b)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (threadIdx.x == 0) { mbar_init(s.done, 1); fence_barrier_init(); }
+    if (threadIdx.x == 0) { mbar_init(s.done, LT_ISSUERS); fence_barrier_init(); }
     if (warp == 0) { tmem_alloc(s.tmem_ptr, 64); tmem_relinquish(); }
     __syncthreads();
     if (h0) {
@@ -157,14 +159,18 @@ lstm_seq_fwd_tc_kernel(const float *__restrict__ zx, const float *__restrict__ w
     load_zin(0, zin);
     for (int t = 0; t < T; ++t) {
         if (t + 1 < T) load_zin(t + 1, znext);
-        if (warp == 0) {
+        if (warp < LT_ISSUERS) {
+            // LT_ISSUERS warps (on different SM sub-partitions) issue the step's MMAs: warp w takes the gate tiles
+            // m = w, w + LT_ISSUERS, ...; each commits to the same mbarrier (count LT_ISSUERS)
             if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < H / 16; ++ks)          // the four gate tiles in turn: consecutive MMAs are independent
+                for (int ks = 0; ks < H / 16; ++ks)          // the gate tiles in turn: consecutive MMAs are independent
 #pragma unroll
-                    for (int m = 0; m < 4; ++m)
+                    for (int mm = 0; mm < 4 / LT_ISSUERS; ++mm) {
+                        const int m = warp + mm * LT_ISSUERS;
                         mma_bf16(tmem_base + m * LT_N, tmpl | (uint64_t)(a16 + ((m * 2 * LT_ATOM_A + (ks >> 2) * LT_ATOM_A + (ks & 3) * 32) >> 4)),
                                  tmpl | (uint64_t)(b16 + (((ks >> 2) * LT_ATOM_B + (ks & 3) * 32) >> 4)), idesc, ks ? 1u : 0u);
+                    }
                 mma_commit(s.done);
             }
             __syncwarp();
@@ -230,7 +236,7 @@ lstm_seq_bwd_tc_kernel(const float *__restrict__ dh_last, const float *__restric
             make_uint4(lt_pack2(v[0], v[1]), lt_pack2(v[2], v[3]), lt_pack2(v[4], v[5]), lt_pack2(v[6], v[7]));
     }
     for (int i = threadIdx.x; i < 8 * LT_ATOM_B / 16; i += LT_THREADS) reinterpret_cast<uint4 *>(s.b)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (threadIdx.x == 0) { mbar_init(s.done, 1); fence_barrier_init(); }
+    if (threadIdx.x == 0) { mbar_init(s.done, LT_ISSUERS); fence_barrier_init(); }
     if (warp == 0) { tmem_alloc(s.tmem_ptr, 64); tmem_relinquish(); }
     bool live[LT_CPT];
     float dc[LT_CPT];
@@ -276,14 +282,16 @@ lstm_seq_bwd_tc_kernel(const float *__restrict__ dh_last, const float *__restric
             f[i] = cur[i].f; ug[i] = cur[i].ug; ct[i] = cur[i].ct; o[i] = cur[i].o; cv[i] = cur[i].cv; cp[i] = cur[i].cp; dh[i] = cur[i].dh;
         }
         if (t != T - 1) {
-            if (warp == 0) {
+            if (warp < LT_ISSUERS) {
                 if (elect_one()) {
                     // the 32 K-steps go to FOUR accumulators in turn (one chain of 32 dependent MMAs paid the MMA
-                    // latency, not its issue rate, 32 times); the cell thread adds the four partial sums
+                    // latency, not its issue rate, 32 times); the cell thread adds the four partial sums.
+                    // Issuer w takes the accumulators w, w + LT_ISSUERS, ...
 #pragma unroll
                     for (int ks = 0; ks < K / 16; ++ks)
-                        mma_bf16(tmem_base + (ks & 3) * LT_N, tmpl | (uint64_t)(a16 + (((ks >> 2) * LT_ATOM_A + (ks & 3) * 32) >> 4)),
-                                 tmpl | (uint64_t)(b16 + (((ks >> 2) * LT_ATOM_B + (ks & 3) * 32) >> 4)), idesc, ks >= 4 ? 1u : 0u);
+                        if ((ks & 3) % LT_ISSUERS == warp)
+                            mma_bf16(tmem_base + (ks & 3) * LT_N, tmpl | (uint64_t)(a16 + (((ks >> 2) * LT_ATOM_A + (ks & 3) * 32) >> 4)),
+                                     tmpl | (uint64_t)(b16 + (((ks >> 2) * LT_ATOM_B + (ks & 3) * 32) >> 4)), idesc, ks >= 4 ? 1u : 0u);
                     mma_commit(s.done);
                 }
                 __syncwarp();
