@@ -35,17 +35,53 @@ __device__ __forceinline__ float4 ldx4(const __nv_bfloat16 *p) {
     return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
                        __uint_as_float(u.y & 0xffff0000u));
 }
+// Index arithmetic of a window: the pooled maps of configs 3 and 4 (and Q, always) are powers of two, so the three
+// div / mod pairs are shifts and masks; other maps take 32-bit divisions when the index space fits, 64-bit ones
+// otherwise.  (All three used to be 64-bit divisions — ~300 of the ~370 instructions of an iteration of the
+// backward apply kernel, which ran at half of its issue rate and 3.3 TB/s instead of at the HBM rate.)
+struct WinGeo {
+    int Q, ow, oh, W, C;
+    int lq, low, loh;          // log2 of Q / ow / oh, -1 when not a power of two
+};
+__device__ __forceinline__ WinGeo win_geo(int Q, int ow, int oh, int W, int C) {
+    WinGeo g;
+    g.Q = Q; g.ow = ow; g.oh = oh; g.W = W; g.C = C;
+    g.lq = __ffs(Q) - 1;
+    g.low = (ow & (ow - 1)) ? -1 : __ffs(ow) - 1;
+    g.loh = (oh & (oh - 1)) ? -1 : __ffs(oh) - 1;
+    return g;
+}
 template <typename XT>
-__device__ __forceinline__ WinT<XT> window(const XT *x, long long idx, int Q, int ow, int oh, int W, int C) {
-    const int cq = (int)(idx % Q);
-    long long pix = idx / Q;
-    const int j = (int)(pix % ow);
-    long long t = pix / ow;
-    const int i = (int)(t % oh);
-    const long long n = t / oh;
+__device__ __forceinline__ WinT<XT> window(const XT *x, long long idx, const WinGeo &g) {
+    int cq, j, i;
+    long long n;
+    if (g.low >= 0 && g.loh >= 0) {
+        cq = (int)idx & (g.Q - 1);
+        const long long pix = idx >> g.lq;
+        j = (int)pix & (g.ow - 1);
+        const long long t = pix >> g.low;
+        i = (int)t & (g.oh - 1);
+        n = t >> g.loh;
+    } else if (idx < 0x7fffffffll) {
+        const unsigned u = (unsigned)idx;
+        cq = (int)(u & (unsigned)(g.Q - 1));
+        const unsigned pix = u >> g.lq;
+        const unsigned t = pix / (unsigned)g.ow;
+        j = (int)(pix - t * (unsigned)g.ow);
+        const unsigned nn = t / (unsigned)g.oh;
+        i = (int)(t - nn * (unsigned)g.oh);
+        n = nn;
+    } else {
+        cq = (int)(idx % g.Q);
+        const long long pix = idx / g.Q;
+        j = (int)(pix % g.ow);
+        const long long t = pix / g.ow;
+        i = (int)(t % g.oh);
+        n = t / g.oh;
+    }
     WinT<XT> w;
-    w.rowstride = (long long)W * C;
-    w.p00 = x + ((n * 2 * oh + 2 * i) * W + 2 * j) * C + cq * 4;      // H == 2*oh
+    w.rowstride = (long long)g.W * g.C;
+    w.p00 = x + ((n * 2 * g.oh + 2 * i) * g.W + 2 * j) * g.C + cq * 4;      // H == 2*oh
     return w;
 }
 
@@ -63,13 +99,14 @@ __global__ void __launch_bounds__(256) bn_pool_fwd_kernel(const XT *__restrict__
                                                           long long windows4, int C, int W, int oh, int ow) {
     pdl_wait();
     const int Q = C >> 2;
+    const WinGeo geo = win_geo(Q, ow, oh, W, C);
     const int cq = threadIdx.x % Q;
     const float *prm = bn_params(scratch, C);
     const float4 sc4 = ldg4(prm + cq * 4), sh4 = ldg4(prm + C + cq * 4);
     const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
     const long long stride = (long long)gridDim.x * 256;
     for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < windows4; idx += stride) {
-        const WinT<XT> w = window(x, idx, Q, ow, oh, W, C);
+        const WinT<XT> w = window(x, idx, geo);
         float4 v[4];
         v[0] = ldx4(w.p00); v[1] = ldx4(w.p00 + C); v[2] = ldx4(w.p00 + w.rowstride); v[3] = ldx4(w.p00 + w.rowstride + C);
         float4 out;
@@ -94,13 +131,22 @@ __global__ void __launch_bounds__(256) bn_pool_fwd_kernel(const XT *__restrict__
     }
 }
 
-// gradient of the BN output at window element e of channel lane k, from the pooled gradient
+// gradient of the BN output at window element e of channel lane k, from the pooled gradient: every winner of the
+// window receives share(g, code) — g itself, or g / (number of tied maxima) in tie-split mode (x0.5 / x0.25 are the
+// exact quotients; the division by 3 stays an IEEE division) — computed ONCE per (window, channel), not per element
 template <int MODE>
-__device__ __forceinline__ float routed(float g, uint32_t cd, int e) {
-    if (MODE == SN_POOL_FIRST_ARGMAX) return cd == (uint32_t)e ? g : 0.f;
-    if (!((cd >> e) & 1u)) return 0.f;
+__device__ __forceinline__ float share(float g, uint32_t cd) {
+    if (MODE == SN_POOL_FIRST_ARGMAX) return g;
     const int cnt = __popc(cd);
-    return cnt > 1 ? g / (float)cnt : g;
+    if (cnt == 2) return g * 0.5f;
+    if (cnt == 4) return g * 0.25f;
+    if (cnt == 3) return __fdiv_rn(g, 3.f);
+    return g;
+}
+template <int MODE>
+__device__ __forceinline__ float routed(float sh, uint32_t cd, int e) {
+    if (MODE == SN_POOL_FIRST_ARGMAX) return cd == (uint32_t)e ? sh : 0.f;
+    return ((cd >> e) & 1u) ? sh : 0.f;
 }
 
 template <int MODE, typename XT>
@@ -109,6 +155,7 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(const float *__
                                                                  const float *__restrict__ invstd, double *__restrict__ scratch,
                                                                  long long windows4, int C, int W, int oh, int ow, BnFinal fin) {
     const int Q = C >> 2;
+    const WinGeo geo = win_geo(Q, ow, oh, W, C);
     const int cq = threadIdx.x % Q;
     float mu[4], is[4];
     {
@@ -122,7 +169,7 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(const float *__
         float fa[4] = {0, 0, 0, 0}, fb[4] = {0, 0, 0, 0};
 #pragma unroll 1
         for (int it = 0; it < 16 && idx < windows4; ++it, idx += stride) {
-            const WinT<XT> w = window(x, idx, Q, ow, oh, W, C);
+            const WinT<XT> w = window(x, idx, geo);
             const float4 g = ldg4(dyp + idx * 4);
             const uint32_t packed = __ldg(code + idx);
             float4 v[4];
@@ -131,10 +178,11 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(const float *__
             for (int k = 0; k < 4; ++k) {
                 const uint32_t cd = (packed >> (8 * k)) & 0xffu;
                 const float gk = comp(g, k);
+                const float sh = share<MODE>(gk, cd);
                 fa[k] += gk;                                        // the routed shares of a window sum to gk
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float r = routed<MODE>(gk, cd, e);
+                    const float r = routed<MODE>(sh, cd, e);
                     fb[k] = fmaf(r, (comp(v[e], k) - mu[k]) * is[k], fb[k]);
                 }
             }
@@ -174,6 +222,7 @@ __global__ void __launch_bounds__(256, 3) bn_pool_bwd_reduce_pooled_kernel(const
                                                                         int oh, int ow, BnFinal fin) {
     pdl_wait();
     const int Q = C >> 2;
+    const WinGeo geo = win_geo(Q, ow, oh, W, C);
     const int cq = threadIdx.x % Q;
     float bt[4], rg[4];
     bool fast = true;
@@ -225,7 +274,7 @@ __global__ void __launch_bounds__(256, 3) bn_pool_bwd_reduce_pooled_kernel(const
         } else {
 #pragma unroll 1
             for (int it = 0; it < 16 && idx < windows4; ++it, idx += stride) {
-                const WinT<XT> w = window(x, idx, Q, ow, oh, W, C);
+                const WinT<XT> w = window(x, idx, geo);
                 const float4 g = ldg4(dyp + idx * 4), mu4 = ldg4(mean + cq * 4), is4 = ldg4(invstd + cq * 4);
                 const uint32_t packed = __ldg(code + idx);
                 float4 v[4];
@@ -234,10 +283,11 @@ __global__ void __launch_bounds__(256, 3) bn_pool_bwd_reduce_pooled_kernel(const
                 for (int k = 0; k < 4; ++k) {
                     const uint32_t cd = (packed >> (8 * k)) & 0xffu;
                     const float gk = comp(g, k);
+                    const float sh = share<MODE>(gk, cd);
                     fa[k] += gk;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float r = routed<MODE>(gk, cd, e);
+                        const float r = routed<MODE>(sh, cd, e);
                         fb[k] = fmaf(r, (comp(v[e], k) - comp(mu4, k)) * comp(is4, k), fb[k]);
                     }
                 }
@@ -268,6 +318,7 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__r
                                                                 int W, int oh, int ow) {
     pdl_wait();
     const int Q = C >> 2;
+    const WinGeo geo = win_geo(Q, ow, oh, W, C);
     const int cq = threadIdx.x % Q;
     const float *prm = bn_params(scratch, C);
     const float4 a4 = ldg4(prm + cq * 4), b4 = ldg4(prm + C + cq * 4), c4 = ldg4(prm + 2 * C + cq * 4);
@@ -275,7 +326,7 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__r
     float cs[4] = {0.f, 0.f, 0.f, 0.f};                  // this thread's share of sum_rows dx[., c] (the producer's bias gradient)
     const long long stride = (long long)gridDim.x * 256;
     for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < windows4; idx += stride) {
-        const WinT<XT> w = window(x, idx, Q, ow, oh, W, C);
+        const WinT<XT> w = window(x, idx, geo);
         const float4 g = ldg4(dyp + idx * 4);
         const uint32_t packed = __ldg(code + idx);
         float4 v[4], o[4];
@@ -284,10 +335,11 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__r
         for (int k = 0; k < 4; ++k) {
             const uint32_t cd = (packed >> (8 * k)) & 0xffu;
             const float gk = comp(g, k);
+            const float sh = share<MODE>(gk, cd);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float xv = comp(v[e], k);
-                float r = fmaf(pa[k], routed<MODE>(gk, cd, e), fmaf(pb[k], xv, pc[k]));
+                float r = fmaf(pa[k], routed<MODE>(sh, cd, e), fmaf(pb[k], xv, pc[k]));
                 if (MASK && relu_blocked(xv)) r = 0.f;
                 setc(o[e], k, r);
                 cs[k] += r;
