@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256, 3) bn_pool_bwd_reduce_pooled_kernel(const
 }
 
 template <int MODE, bool MASK, typename XT>
-__global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float *__restrict__ dyp, const uint32_t *__restrict__ code,
+__global__ void __launch_bounds__(256, 4) bn_pool_bwd_apply_kernel(const float *__restrict__ dyp, const uint32_t *__restrict__ code,
                                                                 const XT *__restrict__ x, float *__restrict__ dx,
                                                                 __nv_bfloat16 *__restrict__ dx_bf16, float *__restrict__ colsum,
                                                                 double *__restrict__ scratch, long long windows4, int C,
