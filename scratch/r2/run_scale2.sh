@@ -15,10 +15,7 @@ PY
 if [ "$G" -ge 8 ]; then
   B n8_sync 8
   B n8_nosync 8 --no-sync-bn
-  B n4_sync 4
-  timeout 100 python tests/multi_gpu/fit_n_gpus_check.py 8 > $O/fit8.log 2>&1; tail -3 $O/fit8.log
 else
   timeout 500 python -m pytest tests/test_gpu_comm.py tests/test_gpu_ddp.py -m gpu -q --timeout 300 > $O/pytest_comm2.log 2>&1; tail -2 $O/pytest_comm2.log
   B n2_sync 2
-  B n2_nosync 2 --no-sync-bn
 fi
