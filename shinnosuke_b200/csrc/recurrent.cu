@@ -15,8 +15,8 @@
 // (columns in the FORWARD order f, u, c~, o; the reference concatenates them as (o, c~, u, f), :358,
 // which scrambles dW — DESIGN.md section 5) and dc_{t-1}; the weight / bias / input gradients are
 // three GEMMs over all timesteps afterwards (Dense kernels).
-// Everything here is exact fp32 FMA work in every precision tier: the per-step products are
-// N x H x 4H = 16.8 MFLOP, latency-bound.
+// Everything here is exact fp32 FMA work: the per-step products are N x H x 4H = 16.8 MFLOP, latency-bound.
+// (The bf16 tier runs the recurrence of H = 128 on the tensor pipe instead: recurrent_tc.cu.)
 #include "common.cuh"
 using namespace sn;
 

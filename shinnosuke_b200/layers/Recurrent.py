@@ -5,7 +5,9 @@ Same parameters as the reference: W (H + D, 4H) = rows [recurrent; input], gate 
 (f, u, c~, o), b (1, 4H) with the forget-gate bias at one (:225-262).  The input half of the fused
 product is one GEMM over all timesteps; the recurrence is ONE launch for the whole sequence when
 H is 64 or 128 (thread-block clusters, Wh in registers, h_t exchanged through distributed shared
-memory), else one fused launch per step (csrc/recurrent.cu).  The backward pass is the CORRECT back-propagation through time: the reference
+memory; in the bf16 tier with H = 128 the per-step product runs on the tensor pipe with Wh resident
+in shared memory as the UMMA A operand, csrc/recurrent_tc.cu), else one fused launch per step
+(csrc/recurrent.cu).  The backward pass is the CORRECT back-propagation through time: the reference
 concatenates its gate gradients as (o, c~, u, f) (:358, :406) against forward columns (f, u, c~, o),
 so its dW / dX do not match its own forward; the oracle reproduces the
 reference's numbers with `reference_gate_order=True` and is checked against numeric gradients
