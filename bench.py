@@ -341,13 +341,34 @@ def cpu_oracle_throughput(cfg, batch, steps, warmup=1):
     X, Y = synth(cfg, batch * (steps + warmup))
     X = X.astype(np.float64)
     Y = Y.astype(np.float64)
-    for i in range(warmup):
-        net.step(X[i * batch:(i + 1) * batch], Y[i * batch:(i + 1) * batch])
-    t0 = time.perf_counter()
-    for i in range(warmup, warmup + steps):
-        net.step(X[i * batch:(i + 1) * batch], Y[i * batch:(i + 1) * batch])
-    dt = time.perf_counter() - t0
+    with all_host_threads():
+        for i in range(warmup):
+            net.step(X[i * batch:(i + 1) * batch], Y[i * batch:(i + 1) * batch])
+        t0 = time.perf_counter()
+        for i in range(warmup, warmup + steps):
+            net.step(X[i * batch:(i + 1) * batch], Y[i * batch:(i + 1) * batch])
+        dt = time.perf_counter() - t0
     return batch * steps / dt, dt / steps
+
+
+def all_host_threads():
+    """Context manager: BLAS thread pools at the number of host cores.  torchrun exports OMP_NUM_THREADS=1 to every
+    rank, which would time the reference arm on ONE core at N > 1; the contract is "all the host threads it can use"."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext()
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [d.get('num_threads', 0) for d in threadpool_info() if d.get('user_api') == 'blas']
+        return max(n) if n else os.cpu_count()
+    except Exception:
+        return os.cpu_count()
 
 
 def cpu_reference_throughput(cfg, batch, steps, warmup=1, warmup_batch=None):
@@ -360,11 +381,12 @@ def cpu_reference_throughput(cfg, batch, steps, warmup=1, warmup_batch=None):
         return None
     wb = warmup_batch or batch
     X, Y = synth(cfg, batch * steps + wb * warmup)
-    if warmup and wb != batch:
-        # a short untimed pass on a small batch first (imports, OpenBLAS thread pool), then the timed steps
-        ref_driver.fit_throughput(cfg, X[:wb * warmup], Y[:wb * warmup], wb, 0, warmup)
-        return ref_driver.fit_throughput(cfg, X[wb * warmup:], Y[wb * warmup:], batch, 0, steps)
-    return ref_driver.fit_throughput(cfg, X, Y, batch, warmup, steps)
+    with all_host_threads():
+        if warmup and wb != batch:
+            # a short untimed pass on a small batch first (imports, OpenBLAS thread pool), then the timed steps
+            ref_driver.fit_throughput(cfg, X[:wb * warmup], Y[:wb * warmup], wb, 0, warmup)
+            return ref_driver.fit_throughput(cfg, X[wb * warmup:], Y[wb * warmup:], batch, 0, steps)
+        return ref_driver.fit_throughput(cfg, X, Y, batch, warmup, steps)
 
 
 def run_reference(args):
