@@ -222,7 +222,7 @@ def test_lstm_recurrence_on_the_tensor_pipe(case):
     """precision='bf16' with H = 128: h_{t-1}.Wh^T and dz_{t+1}.Wh are tcgen05 MMAs on bf16 operands (fp32
     accumulation, fp32 gates and cell state), the three big GEMMs run on the tensor pipe too.  Bound for the whole
     layer against the float64 oracle: the bf16 tier's 1e-2 (max|a-r| / max|r| per tensor) — T chained operators,
-    each re-reading the previous step's ROUNDED state (measured 1-3e-3)."""
+    each re-reading the previous step's ROUNDED state."""
     from shinnosuke_b200._lib import lib
     N, T, D, seq = case
     H = 128
